@@ -1,0 +1,170 @@
+"""Shared helpers for the tests: golden loading and deterministic model/batch reconstruction."""
+import json
+import os
+from typing import Dict
+
+import numpy as np
+import torch
+
+from offlinerlkit_b200.synthetic import make_dataset, param_recipe
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIELDS = ("observations", "actions", "next_observations", "terminals", "rewards")
+
+
+class Golden:
+    def __init__(self, name: str):
+        self.z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+        self.meta = json.loads(str(self.z["meta"]))
+
+    def group(self, prefix: str) -> Dict[str, np.ndarray]:
+        pre = prefix + "|"
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def dataset(self):
+        m = self.meta
+        d = make_dataset(m["n_data"], m["O"], m["A"], seed=m["data_seed"])
+        d["rewards"] = d["rewards"].reshape(-1, 1)
+        d["terminals"] = d["terminals"].reshape(-1, 1)
+        return d
+
+    def batch(self, t: int, data=None) -> Dict[str, torch.Tensor]:
+        data = data or self.dataset()
+        idx = self.z["idx"][t]
+        return {k: torch.from_numpy(data[k][idx]) for k in FIELDS}
+
+    def noise(self, t: int) -> Dict[str, torch.Tensor]:
+        return {k: torch.from_numpy(v) for k, v in self.group(f"noise{t}").items()}
+
+    def losses(self, t: int) -> Dict[str, float]:
+        return {k: float(v) for k, v in self.group(f"loss{t}").items()}
+
+
+def mlp_shapes(prefix, in_dim, hidden):
+    out, d = {}, in_dim
+    for i, h in enumerate(hidden):
+        out[f"{prefix}.model.{2 * i}.weight"] = (h, d)
+        out[f"{prefix}.model.{2 * i}.bias"] = (h,)
+        d = h
+    return out
+
+
+def critic_shapes(in_dim, hidden):
+    s = mlp_shapes("backbone", in_dim, hidden)
+    s["last.weight"] = (1, hidden[-1])
+    s["last.bias"] = (1,)
+    return s
+
+
+def actorprob_shapes(O, A, hidden, conditioned_sigma=True):
+    s = mlp_shapes("backbone", O, hidden)
+    if not conditioned_sigma:
+        s["dist_net.sigma_param"] = (A, 1)
+    s["dist_net.mu.weight"] = (A, hidden[-1])
+    s["dist_net.mu.bias"] = (A,)
+    if conditioned_sigma:
+        s["dist_net.sigma.weight"] = (A, hidden[-1])
+        s["dist_net.sigma.bias"] = (A,)
+    return s
+
+
+def det_actor_shapes(O, A, hidden):
+    s = mlp_shapes("backbone", O, hidden)
+    s["last.weight"] = (A, hidden[-1])
+    s["last.bias"] = (A,)
+    return s
+
+
+def ensemble_critic_shapes(O, A, hidden, E):
+    out, d = {}, O + A
+    for i, h in enumerate(list(hidden) + [1]):
+        for nm, shp in (("weight", (E, d, h)), ("bias", (E, 1, h)), ("saved_weight", (E, d, h)), ("saved_bias", (E, 1, h))):
+            out[f"model.{2 * i}.{nm}"] = shp
+        d = h
+    return out
+
+
+def dynamics_shapes(O, A, hidden, E):
+    out, d = {}, O + A
+    names = [f"backbones.{i}" for i in range(len(hidden))] + ["output_layer"]
+    dims = list(hidden) + [2 * (O + 1)]
+    head = {"max_logvar": (O + 1,), "min_logvar": (O + 1,)}
+    for n, h in zip(names, dims):
+        for nm, shp in (("weight", (E, d, h)), ("bias", (E, 1, h)), ("saved_weight", (E, d, h)), ("saved_bias", (E, 1, h))):
+            out[f"{n}.{nm}"] = shp
+        d = h
+    return {**head, **out}
+
+
+def recipe_state(shapes: Dict[str, tuple], seed: int, prefix: str) -> Dict[str, torch.Tensor]:
+    return {f"{prefix}.{k}": torch.from_numpy(v) for k, v in param_recipe(shapes, seed).items()}
+
+
+def initial_state(meta) -> Dict[str, torch.Tensor]:
+    """Rebuild the pre-step state_dict of a golden run from its parameter seeds (see make_golden.overwrite_params)."""
+    algo, O, A, hid = meta["algo"], meta["O"], meta["A"], meta["hidden"]
+    ps = meta.get("param_seeds", {})
+    st = {}
+    if algo in ("cql", "sac"):
+        st.update(recipe_state(actorprob_shapes(O, A, hid), ps["actor"], "actor"))
+        for c in ("critic1", "critic2"):
+            cs = recipe_state(critic_shapes(O + A, hid), ps[c], c)
+            st.update(cs)
+            st.update({k.replace(c + ".", c + "_old.", 1): v.clone() for k, v in cs.items()})
+    elif algo == "edac":
+        st.update(recipe_state(actorprob_shapes(O, A, hid), ps["actor"], "actor"))
+        cs = recipe_state(ensemble_critic_shapes(O, A, hid, meta["E"]), ps["critics"], "critics")
+        st.update(cs)
+        st.update({k.replace("critics.", "critics_old.", 1): v.clone() for k, v in cs.items()})
+    elif algo == "iql":
+        st.update(recipe_state(actorprob_shapes(O, A, hid, conditioned_sigma=False), ps["actor"], "actor"))
+        for c in ("critic_q1", "critic_q2"):
+            cs = recipe_state(critic_shapes(O + A, hid), ps[c], c)
+            st.update(cs)
+            st.update({k.replace(c + ".", c + "_old.", 1): v.clone() for k, v in cs.items()})
+        st.update(recipe_state(critic_shapes(O, hid), ps["critic_v"], "critic_v"))
+    elif algo == "td3bc":
+        for c, shp in (("actor", det_actor_shapes(O, A, hid)), ("critic1", critic_shapes(O + A, hid)),
+                       ("critic2", critic_shapes(O + A, hid))):
+            cs = recipe_state(shp, ps[c], c)
+            st.update(cs)
+            st.update({k.replace(c + ".", c + "_old.", 1): v.clone() for k, v in cs.items()})
+    elif algo == "dynamics":
+        raw = param_recipe(dynamics_shapes(O, A, hid, meta["E"]), meta["param_seed"])
+        st = {k: torch.from_numpy(v) for k, v in raw.items()}
+        st["max_logvar"] = torch.full((O + 1,), 0.5)
+        st["min_logvar"] = torch.full((O + 1,), -10.0)
+        st["elites"] = torch.arange(meta["n_elites"])
+    else:
+        raise KeyError(algo)
+    return st
+
+
+def tensor_stats(t: torch.Tensor) -> np.ndarray:
+    x = t.detach().double().flatten().cpu().numpy()
+    stride = max(1, x.size // 64)
+    return np.concatenate([[x.sum(), np.abs(x).sum(), np.sqrt((x * x).sum())], x[::stride][:64]])
+
+
+def rel_err(a, b) -> float:
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+def assert_stats_close(state: Dict[str, torch.Tensor], stats: Dict[str, np.ndarray], tol: float, lr_atol: float = 0.0,
+                       skip=("saved_",)):
+    """Compare a state dict with the golden per-tensor fingerprints.
+
+    The three norms are compared relatively; the 64 sampled elements use
+    ``rtol=tol`` plus ``atol=lr_atol`` (Adam's sign sensitivity, SURVEY.md section 7 "hard parts").
+    """
+    for k, ref in stats.items():
+        if any(s in k for s in skip):
+            continue
+        got = tensor_stats(state[k])
+        assert got.shape == ref.shape, k
+        np.testing.assert_allclose(got[1:3], ref[1:3], rtol=tol, err_msg=k)
+        np.testing.assert_allclose(got[3:], ref[3:], rtol=tol, atol=lr_atol + 1e-7, err_msg=k)

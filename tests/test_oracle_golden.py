@@ -1,0 +1,138 @@
+"""CPU: pin the oracle (oracle/) against the golden vectors produced by the real reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import algos, dynamics as odyn, replay as oreplay
+from tests.helpers import Golden, initial_state, assert_stats_close, rel_err, FIELDS
+
+TOL = 2e-5
+
+
+def _alpha(meta):
+    return (meta["target_entropy"], 0.0, meta["alpha_lr"])
+
+
+def _run(g, ora, with_noise=True):
+    data = g.dataset()
+    for t in range(g.meta["n_steps"]):
+        out = ora.step(g.batch(t, data), g.noise(t) if with_noise else None)
+        ref = g.losses(t)
+        assert out.keys() == ref.keys()
+        for k in ref:
+            assert out[k] == pytest.approx(ref[k], rel=TOL, abs=TOL), (t, k)
+        assert_stats_close(ora.state_dict(), g.group(f"stats{t}"), tol=TOL)
+    post = g.group("post")
+    if post:
+        sd = ora.state_dict()
+        for k, v in post.items():
+            if v.dtype.kind == "f":
+                assert rel_err(sd[k].numpy(), v) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hc", "cql_hc_lagrange", "cql_hopper"])
+def test_cql(name):
+    g = Golden(name)
+    _run(g, algos.CQLOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
+
+
+@pytest.mark.parametrize("name", ["sac_small", "sac_hc"])
+def test_sac(name):
+    g = Golden(name)
+    _run(g, algos.SACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
+
+
+@pytest.mark.parametrize("name", ["edac_small", "edac_hc"])
+def test_edac(name):
+    g = Golden(name)
+    _run(g, algos.EDACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
+
+
+@pytest.mark.parametrize("name", ["iql_small", "iql_walker", "iql_walker_b1024"])
+def test_iql(name):
+    g = Golden(name)
+    _run(g, algos.IQLOracle(initial_state(g.meta), **g.meta["hyper"]), with_noise=False)
+
+
+@pytest.mark.parametrize("name", ["td3bc_small", "td3bc_walker"])
+def test_td3bc(name):
+    g = Golden(name)
+    _run(g, algos.TD3BCOracle(initial_state(g.meta), **g.meta["hyper"]))
+
+
+def test_replay_indices_and_gather():
+    """buffer.py:96-106: the legacy NumPy global generator gives the golden indices; gather is bit-exact."""
+    g = Golden("cql_small")
+    data = g.dataset()
+    np.random.seed(g.meta["np_seed"])
+    for t in range(g.meta["n_steps"]):
+        idx = oreplay.draw_indices(g.meta["n_data"], g.meta["B"])
+        assert np.array_equal(idx, g["idx"][t])
+        got = oreplay.gather(data, idx)
+        for k in FIELDS:
+            assert np.array_equal(got[k], data[k][idx])
+
+
+def _dyn_inputs(g):
+    m = g.meta
+    from offlinerlkit_b200.synthetic import make_dataset
+    d = make_dataset(m["n_data"], m["O"], m["A"], seed=m["data_seed"])
+    x = np.concatenate([d["observations"], d["actions"]], axis=-1)
+    y = np.concatenate([d["next_observations"] - d["observations"], d["rewards"].reshape(-1, 1)], axis=-1)
+    mu, std = odyn.scaler_fit(x)
+    assert np.array_equal(mu, g["scaler_mu"]) and np.array_equal(std, g["scaler_std"])
+    return (x - mu) / std, y, mu, std
+
+
+@pytest.mark.parametrize("name", ["dynamics_small", "dynamics_hc"])
+def test_dynamics(name):
+    g = Golden(name)
+    m = g.meta
+    x, y, mu, std = _dyn_inputs(g)
+    ora = odyn.DynamicsOracle(initial_state(m), m["weight_decays"], lr=m["lr"])
+    boot = g["boot"]
+    loss = ora.learn(x[boot], y[boot], batch_size=m["B"])
+    assert loss == pytest.approx(float(g["learn_loss"]), rel=TOL)
+    assert_stats_close({k: v.detach() for k, v in ora.p.items()}, g.group("stats"), tol=TOL)
+    val = ora.validate(x[:m["holdout"]], y[:m["holdout"]])
+    assert rel_err(val, g["val"]) < TOL
+    fn = {"halfcheetah": odyn.term_halfcheetah, "hopper": odyn.term_hopper, "walker2d": odyn.term_walker2d}[m["term"]]
+    nobs, rew, term, info = ora.step(g["step_obs"], g["step_act"], mu, std, fn, m["penalty_coef"], g["step_noise"],
+                                     g["step_midx"])
+    assert rel_err(nobs, g["step_next_obs"]) < TOL and rel_err(rew, g["step_reward"]) < TOL
+    assert np.array_equal(term, g["step_terminal"])
+    assert rel_err(info["penalty"], g["step_penalty"]) < TOL
+
+
+def test_rollout_compaction():
+    """mopo.py:45-79: stable survivor compaction and per-step draw order, replayed with stored noise."""
+    from oracle import nets
+    g = Golden("rollout_small")
+    m = g.meta
+    dyn_state = {k: torch.from_numpy(v) for k, v in g.group("dyn").items()}
+    actor = {"actor." + k: torch.from_numpy(v) for k, v in g.group("actor").items()}
+    ora = odyn.DynamicsOracle(dyn_state, m["weight_decays"])
+    E, D = m["E"], m["O"] + 1
+    cur = {"row": 0}
+
+    def select_action(obs):
+        n = len(obs)
+        eps = torch.from_numpy(g["eps"][cur["row"]:cur["row"] + n])
+        with torch.no_grad():
+            a, _ = nets.actforward(actor, "actor", torch.from_numpy(obs), eps)
+        return a.numpy()
+
+    def step(obs, act):
+        n = len(obs)
+        r0 = cur["row"]
+        noise = g["normal"][:, r0 * D:(r0 + n) * D].reshape(E, n, D)
+        out = ora.step(obs, act, g["scaler_mu"], g["scaler_std"], odyn.term_hopper, m["penalty_coef"], noise,
+                       g["midx"][r0:r0 + n])
+        cur["row"] += n
+        return out
+
+    out, info = odyn.rollout(select_action, step, g["init"], m["horizon"])
+    assert info["num_transitions"] == int(g["counts"].sum())
+    for k in ("obss", "next_obss", "actions", "rewards"):
+        assert rel_err(out[k], g["out|" + k]) < 1e-4, k
+    assert np.array_equal(out["terminals"], g["out|terminals"])
