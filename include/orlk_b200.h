@@ -1,0 +1,222 @@
+/*
+ * orlk_b200.h -- C ABI of the B200-native engine for OfflineRL-Kit's offline
+ * actor-critic gradient step (liborlk_b200.so, built from offlinerl-kit_b200/csrc).
+ *
+ * The reference (zhaoyizhou1123/OfflineRL-Kit) is pure Python on PyTorch: it has
+ * no FFI or operator registry.  The "reference interface each entry point
+ * replaces" is therefore the Python call site whose ATen/cuBLAS work the entry
+ * point takes over; those are cited per function as  file:line  relative to the
+ * reference tree.  INTEGRATION.md shows the ctypes binding a maintainer would
+ * add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in _host (pinned host memory);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success, otherwise a non-zero code (a
+ *     cudaError_t, or ORLK_ERR_*); orlk_last_error() gives the message.  Nothing
+ *     throws and nothing falls back to the CPU;
+ *   - all launchers are asynchronous on `stream` and CUDA-graph capturable.
+ */
+#ifndef ORLK_B200_H
+#define ORLK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORLK_ABI_VERSION 3
+#define ORLK_ERR_BAD_ARG 10001
+#define ORLK_ERR_UNSUPPORTED 10002
+
+/* ------------------------------------------------------------------ runtime */
+int orlk_abi_version(void);
+const char* orlk_last_error(void);
+/* sizeof() of the descriptor structs below, so a binding can verify its mirror */
+int orlk_sizeof_gemm_desc(void);
+int orlk_sizeof_adam_desc(void);
+int orlk_sizeof_adam_group(void);
+int orlk_sizeof_concat_seg(void);
+/* device properties: out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max smem/block optin */
+int orlk_device_info(int device, int* out4);
+
+/* CUDA-graph capture of a launch sequence on `stream` (replaces the ~4 300
+ * per-step ATen launches of one policy.learn). */
+int orlk_graph_begin(void* stream);
+int orlk_graph_end(void* stream, void** graph_exec_out);
+int orlk_graph_launch(void* graph_exec, void* stream);
+int orlk_graph_destroy(void* graph_exec);
+int orlk_stream_sync(void* stream);
+int orlk_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream);
+int orlk_memcpy_d2h_async(void* dst_host, const void* src, size_t bytes, void* stream);
+int orlk_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
+int orlk_memset_async(void* dst, int value, size_t bytes, void* stream);
+/* event timing on `stream`: returns elapsed ms between two recorded events */
+int orlk_event_create(void** ev_out);
+int orlk_event_record(void* ev, void* stream);
+int orlk_event_sync(void* ev);
+int orlk_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out);
+int orlk_event_destroy(void* ev);
+
+/* ------------------------------------------------------------------- replay */
+/* ReplayBuffer device mirror: one row-major table, row = [obs | next_obs | act | rew | term | pad],
+ * row_w floats per row (multiple of 4).  Replaces the five host arrays of buffer/buffer.py:26-30. */
+int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, const float* rew, const float* term,
+                     int64_t n, int obs_dim, int act_dim, float* table, int row_w, int64_t row_offset, void* stream);
+/* ReplayBuffer.sample gather (buffer/buffer.py:100-106): bit-exact copy of rows idx[0..n) into
+ *   obs2  [2n, obs_dim]  rows [0,n) = observations, rows [n,2n) = next_observations
+ *   act   [n, act_dim], rew [n], term [n]. */
+int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx,
+                       int n, float* obs2, float* act, float* rew, float* term, void* stream);
+
+/* --------------------------------------------------------------- dense GEMM */
+/* One problem of a grouped fp32 GEMM launch:  C[M,N] = epi( sum_k A(m,k) * B(k,n) ).
+ * Replaces nn.Linear / einsum forward, dgrad and wgrad GEMMs (nets/mlp.py:22,28;
+ * nets/ensemble_linear.py:35,37 and their autograd backward). */
+enum {
+    ORLK_EPI_NONE = 0,      /* C = acc (+ bias[n])                                    */
+    ORLK_EPI_RELU = 1,      /* C = relu(acc + bias[n])                                */
+    ORLK_EPI_RELU_MASK = 2, /* C = acc * (aux(m,n) > 0)        ReLU backward          */
+    ORLK_EPI_SWISH = 3,     /* z = acc + bias; C = z*sigmoid(z); C2 = z               */
+    ORLK_EPI_DSWISH = 4     /* C = acc * swish'(aux(m,n))      Swish backward, aux=z  */
+};
+enum { ORLK_CFG_BIG = 0, ORLK_CFG_MID = 1, ORLK_CFG_SMALL = 2 }; /* 128x128x16, 64x64x16, 32x32x32 tiles */
+
+typedef struct OrlkGemmDesc {
+    const float* A;
+    const float* B;
+    float* C;
+    float* C2;         /* second output (ORLK_EPI_SWISH) or NULL                       */
+    const float* bias; /* [N] or NULL                                                  */
+    const float* aux;  /* epilogue operand indexed [m*ldaux + n] or NULL               */
+    float* rowsum;     /* optional [M]: sum_k A(m,k), written by the n-tile-0 CTAs     */
+    float* colsum;     /* optional [N]: sum_k B(k,n), written by the m-tile-0 CTAs     */
+    int64_t lda, ldb, ldc, ldaux;
+    int64_t c_split_stride;   /* split s writes C + (split_base+s)*c_split_stride      */
+    int64_t sum_split_stride; /* same for rowsum / colsum                              */
+    int32_t M, N, K;
+    int32_t a_layout; /* 0: A(m,k)=A[m*lda+k]   1: A(m,k)=A[k*lda+m]                  */
+    int32_t b_layout; /* 0: B(k,n)=B[k*ldb+n]   1: B(k,n)=B[n*ldb+k]                  */
+    int32_t epi;
+    int32_t k_splits; /* >=1 ; split s covers k in [s*k_chunk, min(K,(s+1)*k_chunk))  */
+    int32_t k_chunk;  /* multiple of the config's BK                                   */
+    int32_t split_base;
+    int32_t tile_start; /* first linear tile id of this problem in the launch          */
+    int32_t tiles_m, tiles_n;
+} OrlkGemmDesc;
+
+int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, void* stream);
+
+/* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
+ * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).
+ *   fwd :  Y[g][m,n] = b[g][n] + sum_k X[g][m,k] * W[g][n*ldw + k]            (one warp per row)
+ *   dgrad: dX[g][m,k] = (sum_n dY[g][m,n] * W[g][n*ldw+k]) * (mask ? mask[g][m,k] > 0 : 1)
+ * groups g = 0..G-1 are addressed with the *_gs element strides. */
+int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
+                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G, void* stream);
+int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W, int64_t ldw, int64_t w_gs,
+                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, int M, int K,
+                      int NS, int G, void* stream);
+
+/* Row assembly for critic inputs: dst[row_off+m, 0:w1) = src1[(m / rep1), 0:w1); dst[.., w1:w1+w2) = src2[m, 0:w2)
+ * (replaces torch.cat / repeat in critic_module.py:25 and cql.py:142-147). */
+typedef struct OrlkConcatSeg {
+    float* dst;
+    const float* src1;
+    const float* src2;
+    int64_t ld_dst, ld1, ld2;
+    int32_t M, w1, w2, rep1;
+    int32_t row_start; /* prefix sum of M over segments */
+    int32_t pad_;
+} OrlkConcatSeg;
+int orlk_concat_rows(const OrlkConcatSeg* segs_dev, int n_segs, int total_rows, void* stream);
+
+/* ------------------------------------------------------ stochastic policy head */
+/* Philox4x32-10 fill: out[i] ~ N(0,1) for i < n_normal, then U[lo,hi) for the next n_uniform
+ * (replaces the per-step device randn of dist_module.py:39-42 and the CPU uniform_ of cql.py:138-140
+ * in performance mode; parity tests inject noise instead and set *enable = 0). counter[0] selects the
+ * Philox stream offset; orlk_step_end advances it so that graph replays draw fresh numbers. */
+int orlk_philox_fill(float* out, int64_t n_normal, int64_t n_uniform, float lo, float hi, uint64_t seed,
+                     unsigned long long* counter, const int* enable, void* stream);
+
+/* TanhDiagGaussian / SAC actforward (sac.py:66-77, dist_module.py:21-27,39-42,117-127).
+ * head rows are [mu(0:A) | raw_log_sigma(A:2A)];  row m reads head[(head_row_off + m / rep)*ld_head].
+ *   u = mu + exp(clamp(raw,-5,2)) * eps ; a = tanh(u) (eps == NULL -> mode) ; logp as in the reference.
+ * Outputs: act[m*ld_act + i] (may alias into a critic-input row), logp[m],
+ * and optionally xobs: copies obs[(m / rep)*ld_obs + j] into xout[m*ld_x + j], j < obs_dim. */
+int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off, int rep, const float* eps, int M, int A,
+                           float* act, int64_t ld_act, float* logp, const float* obs, int64_t ld_obs, int obs_dim,
+                           float* xout, int64_t ld_x, void* stream);
+/* Backward of the above with eps fixed:
+ *   dA = sum_{j<n_da} dA_j ; dhead[m, 0:A) = dmu, dhead[m, A:2A) = draw (clamp-gated). glp[m] = dLoss/dlogp[m]. */
+int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, const float* act, int64_t ld_act,
+                        const float* dA0, const float* dA1, int64_t ld_da, const float* glp, int M, int A,
+                        float* dhead, int64_t ld_dhead, void* stream);
+
+/* ------------------------------------------------------------------ losses */
+/* scalars block shared by the loss kernels of one learner (device memory, floats):
+ *   [0] log_alpha  [1] alpha (value in use)  [2] cql_log_alpha  [3..] reserved */
+enum { ORLK_SC_LOG_ALPHA = 0, ORLK_SC_ALPHA = 1, ORLK_SC_CQL_LOG_ALPHA = 2, ORLK_SC_COUNT = 8 };
+
+/* Actor loss of SAC / CQL / EDAC (sac.py:111-126, cql.py:93-106, edac.py:96-110) for q[e][b], e < E:
+ *   loss = mean_b(alpha*logp_b - min_e q_eb);  dq[e][b] = -1/B at the arg-min (E==2: ties split, torch.min(a,b);
+ *   E>2: first index, torch.min(dim)); glp[b] = alpha/B.  If auto_alpha: loss_alpha = -mean(log_alpha*(logp+H)),
+ *   one Adam step on log_alpha (group `alpha_group`), alpha <- exp(log_alpha) (clamped to [0,1] if clamp01).
+ * out_losses[0] = actor loss, [1] = alpha loss, [2] = alpha (new). */
+typedef struct OrlkAdamGroup {
+    float lr, beta1, beta2, eps;
+    float tau; /* polyak coefficient for descs with a target            */
+    int32_t step; /* number of optimiser steps already applied             */
+    int32_t pad_[2];
+} OrlkAdamGroup;
+
+int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, int B, float* scalars, int auto_alpha,
+                        int clamp01, float target_entropy, OrlkAdamGroup* groups, int alpha_group, float* alpha_mv,
+                        float* dq, int64_t dq_es, float* glp, float* out_losses, void* stream);
+
+/* CQL critic phase loss (cql.py:108-205) for both critics.
+ *   q[c] : [B + 3R] rows = data | pi | pi_next | random  (c = 0,1; stride q_cs)
+ *   tq[c]: [B] target-critic values on (s', a');  lp_next [B];  lp_pi, lp_pn [R]
+ * Computes the TD target, the 3-way logsumexp per repeat row (the reference's quirk), the optional Lagrange
+ * multiplier step, the per-row upstream gradients dq[c][.] and the losses
+ *   out_losses[0..1] = critic1/2 loss, [2] = cql_alpha loss, [3] = cql_alpha (old, clamped). */
+int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
+                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int R, int A,
+                         float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
+                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream);
+
+/* ---------------------------------------------------------------- optimiser */
+/* Fused (split-K partial reduction) + Adam + polyak over a list of tensors (torch.optim.Adam as constructed in
+ * run_example/run_cql.py:92-94; _sync_weight sac.py:60-64).  For element i of tensor d:
+ *   g = sum_{s<g_splits} grad[s*g_split_stride + i] + wd * p[i]
+ *   m <- m + (g-m)(1-b1);  v <- b2 v + (1-b2) g^2;  p <- p - (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *   tgt <- tgt*(1-tau) + p*tau   (if tgt != NULL),  with t = groups[group].step + 1. */
+typedef struct OrlkAdamDesc {
+    float* p;
+    float* m;
+    float* v;
+    float* tgt;
+    const float* grad;
+    int64_t n;
+    int64_t g_split_stride;
+    int32_t g_splits;
+    int32_t group;
+    float wd;
+    int32_t block_start; /* prefix sum of ceil(n / 1024) */
+    int32_t flags;       /* ORLK_OPT_ADAM | ORLK_OPT_POLYAK */
+    int32_t pad_;
+} OrlkAdamDesc;
+enum { ORLK_OPT_ADAM = 1, ORLK_OPT_POLYAK = 2 };
+int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream);
+/* Last node of a step graph: groups[g].step += 1 for every g with bit g set in mask, and
+ * philox_counter[0] += 1 when philox_counter != NULL. */
+int orlk_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* philox_counter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORLK_B200_H */

@@ -1,0 +1,199 @@
+"""ReplayBuffer with a device-resident mirror and a CUDA gather (reference: offlinerlkit/buffer/buffer.py).
+
+Same constructor, public NumPy attributes and methods as the reference (``add``, ``add_batch``,
+``load_dataset``, ``normalize_obs``, ``sample``, ``sample_all``).  The host arrays stay the source of truth; they are
+mirrored into one row-major fp32 table in HBM, and ``sample`` draws the indices with the SAME
+``np.random.randint`` call as the reference (buffer.py:98, so the index stream is bit-identical), uploads the
+2 KB of int64 indices and launches ``orlk_replay_gather``.  There is no host-side gather and no CPU fallback.
+"""
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+FIELDS = ("observations", "actions", "next_observations", "terminals", "rewards")
+
+
+class Batch(dict):
+    """The dict returned by ``sample``.  The tensors are views of persistent staging memory owned by the buffer
+    (overwritten by the next ``sample`` of the same size); ``stable`` tells the policy engines that they may bind
+    their CUDA graphs to these addresses."""
+    stable = True
+    obs2: torch.Tensor = None      # [2B, O]: observations then next_observations (one GEMM operand for the actor)
+
+
+class _Stage:
+    N_SLOTS = 4
+
+    def __init__(self, rt, B: int, O: int, A: int):
+        dev = rt.device
+        self.idx_host = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(self.N_SLOTS)]
+        self.idx_np = [t.numpy() for t in self.idx_host]
+        self.events: List[Optional[C.c_void_p]] = [None] * self.N_SLOTS
+        self.slot = 0
+        self.idx_dev = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.obs2 = torch.zeros(2 * B, O, dtype=torch.float32, device=dev)
+        self.act = torch.zeros(B, A, dtype=torch.float32, device=dev)
+        self.rew = torch.zeros(B, 1, dtype=torch.float32, device=dev)
+        self.term = torch.zeros(B, 1, dtype=torch.float32, device=dev)
+        self.batch = Batch(observations=self.obs2[:B], actions=self.act, next_observations=self.obs2[B:],
+                           terminals=self.term, rewards=self.rew)
+        self.batch.obs2 = self.obs2
+        self.batch.indices = self.idx_dev
+
+
+class ReplayBuffer:
+    def __init__(self, buffer_size: int, obs_shape: Tuple, obs_dtype: np.dtype, action_dim: int,
+                 action_dtype: np.dtype, device: str = "cpu") -> None:
+        self._max_size = int(buffer_size)
+        self.obs_shape, self.obs_dtype = tuple(obs_shape), obs_dtype
+        self.action_dim, self.action_dtype = int(action_dim), action_dtype
+        self._ptr = 0
+        self._size = 0
+        self.observations = np.zeros((self._max_size,) + self.obs_shape, dtype=obs_dtype)
+        self.next_observations = np.zeros((self._max_size,) + self.obs_shape, dtype=obs_dtype)
+        self.actions = np.zeros((self._max_size, self.action_dim), dtype=action_dtype)
+        self.rewards = np.zeros((self._max_size, 1), dtype=np.float32)
+        self.terminals = np.zeros((self._max_size, 1), dtype=np.float32)
+        self.device = torch.device(device)
+        # device mirror state
+        self._rt = None
+        self._table: Optional[torch.Tensor] = None
+        self._dirty: List[Tuple[int, int]] = []       # host row ranges [lo, hi) not yet mirrored
+        self._stages: Dict[int, _Stage] = {}
+
+    # ------------------------------------------------------------------ host-side API (as the reference)
+    def add(self, obs, next_obs, action, reward, terminal) -> None:
+        i = self._ptr
+        self.observations[i] = np.array(obs).copy()
+        self.next_observations[i] = np.array(next_obs).copy()
+        self.actions[i] = np.array(action).copy()
+        self.rewards[i] = np.array(reward).copy()
+        self.terminals[i] = np.array(terminal).copy()
+        self._mark(i, i + 1)
+        self._ptr = (self._ptr + 1) % self._max_size
+        self._size = min(self._size + 1, self._max_size)
+
+    def add_batch(self, obss, next_obss, actions, rewards, terminals) -> None:
+        n = len(obss)
+        at = np.arange(self._ptr, self._ptr + n) % self._max_size
+        self.observations[at] = np.array(obss).copy()
+        self.next_observations[at] = np.array(next_obss).copy()
+        self.actions[at] = np.array(actions).copy()
+        self.rewards[at] = np.array(rewards).copy()
+        self.terminals[at] = np.array(terminals).copy()
+        if n >= self._max_size:
+            self._mark(0, self._max_size)
+        elif self._ptr + n <= self._max_size:
+            self._mark(self._ptr, self._ptr + n)
+        else:
+            self._mark(self._ptr, self._max_size)
+            self._mark(0, (self._ptr + n) % self._max_size)
+        self._ptr = (self._ptr + n) % self._max_size
+        self._size = min(self._size + n, self._max_size)
+
+    def load_dataset(self, dataset: Dict[str, np.ndarray]) -> None:
+        self.observations = np.array(dataset["observations"], dtype=self.obs_dtype)
+        self.next_observations = np.array(dataset["next_observations"], dtype=self.obs_dtype)
+        self.actions = np.array(dataset["actions"], dtype=self.action_dtype)
+        self.rewards = np.array(dataset["rewards"], dtype=np.float32).reshape(-1, 1)
+        self.terminals = np.array(dataset["terminals"], dtype=np.float32).reshape(-1, 1)
+        self._ptr = self._size = len(self.observations)
+        self._table = None                              # capacity may have changed: rebuild the mirror lazily
+        self._dirty = [(0, self._size)]
+
+    def normalize_obs(self, eps: float = 1e-3) -> Tuple[np.ndarray, np.ndarray]:
+        mean = self.observations.mean(0, keepdims=True)
+        std = self.observations.std(0, keepdims=True) + eps
+        self.observations = (self.observations - mean) / std
+        self.next_observations = (self.next_observations - mean) / std
+        self._dirty = [(0, len(self.observations))]
+        return mean, std
+
+    def sample_all(self) -> Dict[str, np.ndarray]:
+        n = self._size
+        return {"observations": self.observations[:n].copy(), "actions": self.actions[:n].copy(),
+                "next_observations": self.next_observations[:n].copy(), "terminals": self.terminals[:n].copy(),
+                "rewards": self.rewards[:n].copy()}
+
+    # ------------------------------------------------------------------ device mirror
+    def _mark(self, lo: int, hi: int) -> None:
+        if self._dirty and self._dirty[-1][1] == lo:
+            self._dirty[-1] = (self._dirty[-1][0], hi)
+        else:
+            self._dirty.append((lo, hi))
+
+    @property
+    def _obs_dim(self) -> int:
+        return int(np.prod(self.obs_shape))
+
+    @property
+    def row_width(self) -> int:
+        """floats per table row: [obs | next_obs | act | rew | term], padded to a multiple of 4 (16-byte rows)."""
+        return (2 * self._obs_dim + self.action_dim + 2 + 3) // 4 * 4
+
+    def _runtime(self):
+        if self._rt is None:
+            from .engine.core import get_runtime
+            self._rt = get_runtime(self.device)
+        return self._rt
+
+    def _sync_mirror(self) -> None:
+        rt = self._runtime()
+        cap = len(self.observations)
+        if self._table is None or self._table.shape[0] != cap:
+            self._table = torch.zeros(cap, self.row_width, dtype=torch.float32, device=rt.device)
+            self._dirty = [(0, max(self._size, 0))]
+        O, A = self._obs_dim, self.action_dim
+        for lo, hi in self._dirty:
+            if hi <= lo:
+                continue
+            up = lambda a, w: torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.float32).reshape(hi - lo, w)).to(rt.device)
+            o, no, ac = up(self.observations, O), up(self.next_observations, O), up(self.actions, A)
+            rw, tm = up(self.rewards, 1), up(self.terminals, 1)
+            L.call("orlk_replay_pack", o.data_ptr(), no.data_ptr(), ac.data_ptr(), rw.data_ptr(), tm.data_ptr(),
+                   hi - lo, O, A, self._table.data_ptr(), self.row_width, lo, rt.cur)
+            rt.sync()      # the temporaries above are released after this
+        self._dirty = []
+
+    def _stage(self, batch_size: int) -> _Stage:
+        st = self._stages.get(batch_size)
+        if st is None:
+            st = _Stage(self._runtime(), batch_size, self._obs_dim, self.action_dim)
+            self._stages[batch_size] = st
+        return st
+
+    def draw_indices(self, batch_size: int) -> np.ndarray:
+        """buffer.py:98 -- the legacy NumPy global generator, exactly as the reference."""
+        return np.random.randint(0, self._size, size=batch_size)
+
+    def gather(self, indices: np.ndarray) -> Batch:
+        """Device gather of the given host indices into the staging batch of that size."""
+        if self.obs_dtype != np.float32 or self.action_dtype != np.float32:
+            raise L.OrlkError("the device mirror stores fp32 rows; obs/action dtype must be float32")
+        rt = self._runtime()
+        if self._dirty or self._table is None:
+            self._sync_mirror()
+        B = int(len(indices))
+        st = self._stage(B)
+        s = st.slot
+        st.slot = (s + 1) % st.N_SLOTS
+        if st.events[s] is None:
+            ev = C.c_void_p()
+            L.call("orlk_event_create", C.byref(ev))
+            st.events[s] = ev
+        else:
+            L.call("orlk_event_sync", st.events[s])      # the pinned slot's previous upload has finished
+        st.idx_np[s][:] = indices
+        L.call("orlk_memcpy_h2d_async", st.idx_dev.data_ptr(), st.idx_host[s].data_ptr(), 8 * B, rt.cur)
+        L.call("orlk_event_record", st.events[s], rt.cur)
+        L.call("orlk_replay_gather", self._table.data_ptr(), len(self.observations), self.row_width, self._obs_dim,
+               self.action_dim, st.idx_dev.data_ptr(), B, st.obs2.data_ptr(), st.act.data_ptr(), st.rew.data_ptr(),
+               st.term.data_ptr(), rt.cur)
+        return st.batch
+
+    def sample(self, batch_size: int) -> Dict[str, torch.Tensor]:
+        return self.gather(self.draw_indices(batch_size))

@@ -1,0 +1,62 @@
+// Shared helpers for the orlk_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/orlk_b200.h"
+
+namespace orlk {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+inline int check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+#define ORLK_REQUIRE(cond, msg)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            orlk::set_error("bad argument: %s", msg);   \
+            return ORLK_ERR_BAD_ARG;                    \
+        }                                               \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for up to 1024 threads; `red` is a __shared__ float[32]. Result is returned to every thread.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace orlk

@@ -1,0 +1,467 @@
+// Narrow layers, row assembly, the tanh-Gaussian policy head, loss epilogues and the fused optimiser.
+// Everything here is latency-bound elementwise / reduction work on <= 8K rows: warp-shuffle reductions,
+// one CTA for the scalar losses, no atomics (results are run-to-run deterministic).
+#include <math.h>
+#include "orlk_common.cuh"
+using namespace orlk;
+
+namespace {
+
+constexpr int MAX_NS = 16;
+
+// ------------------------------------------------------------------------------------------ skinny layers
+__global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
+                             int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
+                             int64_t y_gs, int M, int K, int NS) {
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const float* x = X + g * x_gs + (int64_t)m * ldx;
+    const float* w = W + g * w_gs;
+    float acc[MAX_NS];
+#pragma unroll
+    for (int n = 0; n < MAX_NS; ++n) acc[n] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float xv = x[k];
+#pragma unroll
+        for (int n = 0; n < MAX_NS; ++n)
+            if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + k), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < MAX_NS; ++n)
+        if (n < NS) acc[n] = warp_sum(acc[n]);
+    if (lane == 0) {
+        float* y = Y + g * y_gs + (int64_t)m * ldy;
+        for (int n = 0; n < NS; ++n) y[n] = acc[n] + (b ? b[g * b_gs + n] : 0.f);
+    }
+}
+
+__global__ void k_skinny_dgrad(const float* __restrict__ dY, int64_t ldy, int64_t y_gs, const float* __restrict__ W,
+                               int64_t ldw, int64_t w_gs, const float* __restrict__ mask, int64_t ldm, int64_t m_gs,
+                               float* __restrict__ dX, int64_t ldx, int64_t x_gs, int M, int K, int NS) {
+    const int g = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)M * K) return;
+    const int m = (int)(e / K), k = (int)(e % K);
+    const float* dy = dY + g * y_gs + (int64_t)m * ldy;
+    const float* w = W + g * w_gs + k;
+    float s = 0.f;
+    for (int n = 0; n < NS; ++n) s = fmaf(dy[n], __ldg(w + (int64_t)n * ldw), s);
+    if (mask != nullptr && !(mask[g * m_gs + (int64_t)m * ldm + k] > 0.f)) s = 0.f;
+    dX[g * x_gs + (int64_t)m * ldx + k] = s;
+}
+
+// ------------------------------------------------------------------------------------------ row assembly
+__global__ void k_concat_rows(const OrlkConcatSeg* __restrict__ segs, int n_segs, int total_rows) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int s = 0;
+    while (s + 1 < n_segs && segs[s + 1].row_start <= row) ++s;
+    const OrlkConcatSeg sg = segs[s];
+    const int m = row - sg.row_start;
+    float* dst = sg.dst + (int64_t)m * sg.ld_dst;
+    const float* a = sg.src1 + (int64_t)(m / sg.rep1) * sg.ld1;
+    const float* b = sg.src2 + (int64_t)m * sg.ld2;
+    for (int j = lane; j < sg.w1 + sg.w2; j += 32) dst[j] = j < sg.w1 ? a[j] : b[j - sg.w1];
+}
+
+// ------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+
+__global__ void k_philox_fill(float* __restrict__ out, int64_t n_normal, int64_t n_uniform, float lo, float hi,
+                              uint64_t seed, const unsigned long long* __restrict__ counter, const int* __restrict__ enable) {
+    if (enable != nullptr && *enable == 0) return;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call = 4 outputs
+    const int64_t n = n_normal + n_uniform;
+    if (q * 4 >= n) return;
+    const unsigned long long ctr = counter ? *counter : 0ull;
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u0 = u01(c[0]), u1 = u01(c[1]), u2 = u01(c[2]), u3 = u01(c[3]);
+    // Box-Muller on (u0,u1) and (u2,u3)
+    const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+    const float nrm[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+    const float uni[4] = {u0, u1, u2, u3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t i = q * 4 + j;
+        if (i < n_normal) out[i] = nrm[j];
+        else if (i < n) out[i] = lo + (hi - lo) * uni[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tanh-Gaussian head
+constexpr int MAX_A = 32;
+constexpr float LOG_SIG_MIN = -5.f, LOG_SIG_MAX = 2.f;
+constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
+
+__global__ void k_tanh_gauss_sample(const float* __restrict__ head, int64_t ld_head, int head_row_off, int rep,
+                                    const float* __restrict__ eps, int M, int A, float* __restrict__ act, int64_t ld_act,
+                                    float* __restrict__ logp, const float* __restrict__ obs, int64_t ld_obs, int obs_dim,
+                                    float* __restrict__ xout, int64_t ld_x) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float* h = head + (int64_t)(head_row_off + m / rep) * ld_head;
+    float lp = 0.f, corr = 0.f;
+    for (int i = 0; i < A; ++i) {
+        const float mu = h[i];
+        const float ls = fminf(fmaxf(h[A + i], LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sigma = expf(ls);
+        const float u = eps ? fmaf(sigma, eps[(int64_t)m * A + i], mu) : mu;
+        const float a = tanhf(u);
+        const float d = u - mu;
+        lp += -(d * d) / (2.f * sigma * sigma) - logf(sigma) - HALF_LOG_2PI;
+        corr += logf((1.f - a * a) + 1e-6f);
+        act[(int64_t)m * ld_act + i] = a;
+    }
+    if (logp) logp[m] = lp - corr;
+    if (xout) {
+        const float* o = obs + (int64_t)(m / rep) * ld_obs;
+        for (int j = 0; j < obs_dim; ++j) xout[(int64_t)m * ld_x + j] = o[j];
+    }
+}
+
+__global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head, const float* __restrict__ eps,
+                                 const float* __restrict__ act, int64_t ld_act, const float* __restrict__ dA0,
+                                 const float* __restrict__ dA1, int64_t ld_da, const float* __restrict__ glp, int M, int A,
+                                 float* __restrict__ dhead, int64_t ld_dhead) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float* h = head + (int64_t)m * ld_head;
+    const float g = glp ? glp[m] : 0.f;
+    for (int i = 0; i < A; ++i) {
+        const float raw = h[A + i];
+        const float ls = fminf(fmaxf(raw, LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sigma = expf(ls);
+        const float e = eps[(int64_t)m * A + i];
+        const float a = act[(int64_t)m * ld_act + i];
+        const float om = 1.f - a * a;
+        float da = dA0 ? dA0[(int64_t)m * ld_da + i] : 0.f;
+        if (dA1) da += dA1[(int64_t)m * ld_da + i];
+        const float t = 2.f * a * om / (om + 1e-6f);   // d logp / d u  (tanh correction only)
+        const float du = da * om + g * t;              // through a = tanh(u) and through logp
+        const float dmu = du;
+        float draw = du * sigma * e - g;               // u = mu + sigma*eps ; -log sigma term of logp
+        if (!(raw >= LOG_SIG_MIN && raw <= LOG_SIG_MAX)) draw = 0.f;
+        dhead[(int64_t)m * ld_dhead + i] = dmu;
+        dhead[(int64_t)m * ld_dhead + A + i] = draw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scalar Adam
+__device__ float scalar_adam(float p, float g, float* mv, const OrlkAdamGroup& grp) {
+    const int t = grp.step + 1;
+    const double bc1 = 1.0 - pow((double)grp.beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)grp.beta2, (double)t);
+    const float step_size = (float)((double)grp.lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    float m = mv[0], v = mv[1];
+    m = m + (g - m) * (1.f - grp.beta1);
+    v = v * grp.beta2 + (1.f - grp.beta2) * g * g;
+    mv[0] = m; mv[1] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + grp.eps;
+    return p - step_size * (m / denom);
+}
+
+// ------------------------------------------------------------------------------------------ actor loss
+__global__ void k_sac_actor_loss(const float* __restrict__ q, int64_t q_es, int E, const float* __restrict__ logp, int B,
+                                 float* __restrict__ scalars, int auto_alpha, int clamp01, float target_entropy,
+                                 const OrlkAdamGroup* __restrict__ groups, int alpha_group, float* __restrict__ alpha_mv,
+                                 float* __restrict__ dq, int64_t dq_es, float* __restrict__ glp, float* __restrict__ out) {
+    __shared__ float red[32];
+    const float alpha = scalars[ORLK_SC_ALPHA];
+    const float invB = 1.f / (float)B;
+    float lsum = 0.f, lpsum = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float mn = q[b];
+        int arg = 0;
+        for (int e = 1; e < E; ++e) {
+            const float v = q[e * q_es + b];
+            if (v < mn) { mn = v; arg = e; }
+        }
+        const float lp = logp[b];
+        lsum += alpha * lp - mn;
+        lpsum += lp;
+        if (E == 2) {   // torch.min(a, b): ties split the gradient evenly
+            const float q0 = q[b], q1 = q[q_es + b];
+            dq[b] = q0 < q1 ? -invB : (q0 == q1 ? -0.5f * invB : 0.f);
+            dq[dq_es + b] = q1 < q0 ? -invB : (q0 == q1 ? -0.5f * invB : 0.f);
+        } else {        // torch.min(dim=0): gradient to the returned (first minimal) index
+            for (int e = 0; e < E; ++e) dq[e * dq_es + b] = (e == arg) ? -invB : 0.f;
+        }
+        glp[b] = alpha * invB;
+    }
+    lsum = block_sum(lsum, red);
+    lpsum = block_sum(lpsum, red);
+    if (threadIdx.x == 0) {
+        out[0] = lsum * invB;
+        float new_alpha = alpha, aloss = 0.f;
+        if (auto_alpha) {
+            const float la = scalars[ORLK_SC_LOG_ALPHA];
+            const float mean_lp = lpsum * invB + target_entropy;
+            aloss = -(la * mean_lp);
+            const float la_new = scalar_adam(la, -mean_lp, alpha_mv, groups[alpha_group]);
+            scalars[ORLK_SC_LOG_ALPHA] = la_new;
+            new_alpha = expf(la_new);
+            if (clamp01) new_alpha = fminf(fmaxf(new_alpha, 0.f), 1.f);
+            scalars[ORLK_SC_ALPHA] = new_alpha;
+        }
+        out[1] = aloss;
+        out[2] = new_alpha;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ CQL critic loss
+__global__ void __launch_bounds__(1024)
+k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __restrict__ tq, int64_t tq_cs,
+                  const float* __restrict__ lp_next, const float* __restrict__ lp_pi, const float* __restrict__ lp_pn,
+                  const float* __restrict__ rew, const float* __restrict__ term, int B, int R, float log_u, float gamma,
+                  float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
+                  const OrlkAdamGroup* __restrict__ groups, int cql_alpha_group, float* __restrict__ cql_alpha_mv,
+                  float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out) {
+    __shared__ float red[32];
+    __shared__ float sh_scale;
+    const float alpha = scalars[ORLK_SC_ALPHA];
+    const float invB = 1.f / (float)B, invR = 1.f / (float)R, invT = 1.f / T;
+    float td[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float nq = fminf(tq[b], tq[tq_cs + b]);
+        if (!det_backup) nq -= alpha * lp_next[b];
+        const float y = rew[b] + gamma * (1.f - term[b]) * nq;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float qq = q[c * q_cs + b];
+            const float df = qq - y;
+            td[c] += df * df;
+            qs[c] += qq;
+        }
+    }
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float l1 = lp_pi[r], l2 = lp_pn[r];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float* qc = q + c * q_cs + B;
+            const float z1 = (qc[r] - l1) * invT, z2 = (qc[R + r] - l2) * invT, z3 = (qc[2 * R + r] - log_u) * invT;
+            const float mx = fmaxf(z1, fmaxf(z2, z3));
+            ls[c] += mx + logf(expf(z1 - mx) + expf(z2 - mx) + expf(z3 - mx));
+        }
+    }
+    float cons[2], tdm[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        tdm[c] = block_sum(td[c], red) * invB;
+        const float qmean = block_sum(qs[c], red) * invB;
+        const float lmean = block_sum(ls[c], red) * invR;
+        cons[c] = lmean * w * T - qmean * w;
+    }
+    if (threadIdx.x == 0) {
+        float scale = 1.f, closs = 0.f, calpha = 0.f;
+        float c0 = cons[0], c1 = cons[1];
+        if (with_lagrange) {
+            const float la = scalars[ORLK_SC_CQL_LOG_ALPHA];
+            const float ex = expf(la);
+            calpha = fminf(fmaxf(ex, 0.f), 1e6f);
+            c0 = calpha * (cons[0] - thr);
+            c1 = calpha * (cons[1] - thr);
+            closs = -(c0 + c1) * 0.5f;
+            const float gate = (ex >= 0.f && ex <= 1e6f) ? 1.f : 0.f;
+            const float g = -0.5f * ((cons[0] - thr) + (cons[1] - thr)) * ex * gate;
+            scalars[ORLK_SC_CQL_LOG_ALPHA] = scalar_adam(la, g, cql_alpha_mv, groups[cql_alpha_group]);
+            scale = calpha;
+        }
+        out[0] = tdm[0] + c0;
+        out[1] = tdm[1] + c1;
+        out[2] = closs;
+        out[3] = calpha;
+        sh_scale = scale;
+    }
+    __syncthreads();
+    const float scale = sh_scale;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float nq = fminf(tq[b], tq[tq_cs + b]);
+        if (!det_backup) nq -= alpha * lp_next[b];
+        const float y = rew[b] + gamma * (1.f - term[b]) * nq;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) dq[c * dq_cs + b] = 2.f * (q[c * q_cs + b] - y) * invB - w * scale * invB;
+    }
+    const float k = scale * w * invR;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float l1 = lp_pi[r], l2 = lp_pn[r];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float* qc = q + c * q_cs + B;
+            float* dc = dq + c * dq_cs + B;
+            const float z1 = (qc[r] - l1) * invT, z2 = (qc[R + r] - l2) * invT, z3 = (qc[2 * R + r] - log_u) * invT;
+            const float mx = fmaxf(z1, fmaxf(z2, z3));
+            const float e1 = expf(z1 - mx), e2 = expf(z2 - mx), e3 = expf(z3 - mx);
+            const float inv = k / (e1 + e2 + e3);
+            dc[r] = e1 * inv;
+            dc[R + r] = e2 * inv;
+            dc[2 * R + r] = e3 * inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ fused Adam + polyak
+constexpr int ADAM_BLOCK_ELEMS = 1024;
+
+__global__ void __launch_bounds__(256)
+k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamGroup* __restrict__ groups) {
+    __shared__ OrlkAdamDesc sd;
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        int p = 0;
+        while (p + 1 < n_descs && descs[p + 1].block_start <= (int)blockIdx.x) ++p;
+        sd = descs[p];
+        const OrlkAdamGroup g = groups[sd.group];
+        const int t = g.step + 1;
+        s_step_size = (float)((double)g.lr / (1.0 - pow((double)g.beta1, (double)t)));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow((double)g.beta2, (double)t));
+    }
+    __syncthreads();
+    const OrlkAdamDesc& d = sd;
+    const OrlkAdamGroup g = groups[d.group];
+    const int64_t base = (int64_t)(blockIdx.x - d.block_start) * ADAM_BLOCK_ELEMS;
+#pragma unroll
+    for (int j = 0; j < ADAM_BLOCK_ELEMS / 256; ++j) {
+        const int64_t i = base + j * 256 + threadIdx.x;
+        if (i >= d.n) continue;
+        float p = d.p[i];
+        if (d.flags & ORLK_OPT_ADAM) {
+            float gr = 0.f;
+            for (int s = 0; s < d.g_splits; ++s) gr += d.grad[(int64_t)s * d.g_split_stride + i];
+            if (d.wd != 0.f) gr = fmaf(d.wd, p, gr);
+            float m = d.m[i], v = d.v[i];
+            m = m + (gr - m) * (1.f - g.beta1);
+            v = v * g.beta2 + (1.f - g.beta2) * gr * gr;
+            d.m[i] = m; d.v[i] = v;
+            const float denom = sqrtf(v) / s_bc2_sqrt + g.eps;
+            p = p - s_step_size * (m / denom);
+            d.p[i] = p;
+        }
+        if ((d.flags & ORLK_OPT_POLYAK) && d.tgt != nullptr) d.tgt[i] = d.tgt[i] * (1.f - g.tau) + p * g.tau;
+    }
+}
+
+__global__ void k_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* counter) {
+    const int g = threadIdx.x;
+    if (g < 32 && (mask >> g) & 1u) groups[g].step += 1;
+    if (g == 0 && counter != nullptr) *counter += 1ull;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
+                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G, void* stream) {
+    ORLK_REQUIRE(NS >= 1 && NS <= MAX_NS, "NS must be in [1,16]");
+    ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
+    const int wpb = 8;
+    dim3 grid((M + wpb - 1) / wpb, G);
+    k_skinny_fwd<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS);
+    return check_launch("k_skinny_fwd");
+}
+
+int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W, int64_t ldw, int64_t w_gs,
+                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, int M, int K,
+                      int NS, int G, void* stream) {
+    ORLK_REQUIRE(NS >= 1 && NS <= MAX_NS, "NS must be in [1,16]");
+    ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
+    const int64_t n = (int64_t)M * K;
+    dim3 grid((unsigned)((n + 255) / 256), G);
+    k_skinny_dgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs, M, K, NS);
+    return check_launch("k_skinny_dgrad");
+}
+
+int orlk_concat_rows(const OrlkConcatSeg* segs_dev, int n_segs, int total_rows, void* stream) {
+    ORLK_REQUIRE(segs_dev != nullptr && n_segs > 0 && total_rows > 0, "segments");
+    const int wpb = 8;
+    k_concat_rows<<<(total_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(segs_dev, n_segs, total_rows);
+    return check_launch("k_concat_rows");
+}
+
+int orlk_philox_fill(float* out, int64_t n_normal, int64_t n_uniform, float lo, float hi, uint64_t seed,
+                     unsigned long long* counter, const int* enable, void* stream) {
+    const int64_t n = n_normal + n_uniform;
+    ORLK_REQUIRE(out != nullptr && n > 0, "sizes");
+    const int64_t calls = (n + 3) / 4;
+    k_philox_fill<<<(unsigned)((calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_normal, n_uniform, lo, hi, seed,
+                                                                                    counter, enable);
+    return check_launch("k_philox_fill");
+}
+
+int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off, int rep, const float* eps, int M, int A,
+                           float* act, int64_t ld_act, float* logp, const float* obs, int64_t ld_obs, int obs_dim,
+                           float* xout, int64_t ld_x, void* stream) {
+    ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && rep >= 1, "sizes");
+    ORLK_REQUIRE(xout == nullptr || obs != nullptr, "xout needs obs");
+    k_tanh_gauss_sample<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, head_row_off, rep, eps, M, A, act,
+                                                                          ld_act, logp, obs, ld_obs, obs_dim, xout, ld_x);
+    return check_launch("k_tanh_gauss_sample");
+}
+
+int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, const float* act, int64_t ld_act,
+                        const float* dA0, const float* dA1, int64_t ld_da, const float* glp, int M, int A, float* dhead,
+                        int64_t ld_dhead, void* stream) {
+    ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && eps != nullptr, "sizes");
+    k_tanh_gauss_bwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, eps, act, ld_act, dA0, dA1, ld_da, glp,
+                                                                       M, A, dhead, ld_dhead);
+    return check_launch("k_tanh_gauss_bwd");
+}
+
+int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, int B, float* scalars, int auto_alpha,
+                        int clamp01, float target_entropy, OrlkAdamGroup* groups, int alpha_group, float* alpha_mv,
+                        float* dq, int64_t dq_es, float* glp, float* out_losses, void* stream) {
+    ORLK_REQUIRE(E >= 1 && B > 0, "sizes");
+    ORLK_REQUIRE(!auto_alpha || (groups != nullptr && alpha_mv != nullptr), "auto alpha needs its Adam state");
+    k_sac_actor_loss<<<1, 256, 0, (cudaStream_t)stream>>>(q, q_es, E, logp, B, scalars, auto_alpha, clamp01, target_entropy,
+                                                         groups, alpha_group, alpha_mv, dq, dq_es, glp, out_losses);
+    return check_launch("k_sac_actor_loss");
+}
+
+int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
+                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int R, int A,
+                         float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
+                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream) {
+    ORLK_REQUIRE(B > 0 && R > 0 && A > 0, "sizes");
+    ORLK_REQUIRE(!with_lagrange || (groups != nullptr && cql_alpha_mv != nullptr), "lagrange needs its Adam state");
+    const float log_u = (float)log(pow(0.5, (double)A));   // cql.py:82: np.log(0.5 ** act_dim)
+    k_cql_critic_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, R, log_u,
+                                                           gamma, cql_weight, temperature, deterministic_backup,
+                                                           with_lagrange, lagrange_threshold, scalars, groups,
+                                                           cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses);
+    return check_launch("k_cql_critic_loss");
+}
+
+int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream) {
+    ORLK_REQUIRE(descs_dev != nullptr && n_descs > 0 && total_blocks > 0 && groups != nullptr, "descs");
+    k_adam_step<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, n_descs, groups);
+    return check_launch("k_adam_step");
+}
+
+int orlk_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* philox_counter, void* stream) {
+    ORLK_REQUIRE(groups != nullptr, "groups");
+    k_step_end<<<1, 32, 0, (cudaStream_t)stream>>>(groups, mask, philox_counter);
+    return check_launch("k_step_end");
+}
+
+}  // extern "C"

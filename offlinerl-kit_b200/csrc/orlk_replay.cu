@@ -1,0 +1,74 @@
+// ReplayBuffer device mirror: row table packing and the index gather of ReplayBuffer.sample
+// (reference: buffer/buffer.py:26-30 storage, :96-106 sample).  Pure copies -> bit-exact.
+#include "orlk_common.cuh"
+using namespace orlk;
+
+// One warp per transition row: lanes stride over the row_w floats of the row.
+__global__ void k_replay_pack(const float* __restrict__ obs, const float* __restrict__ nobs, const float* __restrict__ act,
+                              const float* __restrict__ rew, const float* __restrict__ term, int64_t n, int O, int A,
+                              float* __restrict__ table, int row_w, int64_t row_offset) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < n; r += nwarps) {
+        float* dst = table + (row_offset + r) * row_w;
+        for (int j = lane; j < row_w; j += 32) {
+            float v = 0.f;
+            if (j < O) v = obs[r * O + j];
+            else if (j < 2 * O) v = nobs[r * O + (j - O)];
+            else if (j < 2 * O + A) v = act[r * A + (j - 2 * O)];
+            else if (j == 2 * O + A) v = rew[r];
+            else if (j == 2 * O + A + 1) v = term[r];
+            dst[j] = v;
+        }
+    }
+}
+
+// One warp per sampled index: a coalesced read of the (<= 256 B) table row, scattered into the SoA batch.
+__global__ void k_replay_gather(const float* __restrict__ table, int64_t n_rows, int row_w, int O, int A,
+                                const int64_t* __restrict__ idx, int n, float* __restrict__ obs2, float* __restrict__ act,
+                                float* __restrict__ rew, float* __restrict__ term) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= n) return;
+    int64_t r = idx[warp];
+    if (r < 0) r = 0;
+    if (r >= n_rows) r = n_rows - 1;
+    const float* src = table + r * row_w;
+    const int used = 2 * O + A + 2;
+    for (int j = lane; j < used; j += 32) {
+        const float v = __ldg(src + j);
+        if (j < O) obs2[(int64_t)warp * O + j] = v;
+        else if (j < 2 * O) obs2[((int64_t)n + warp) * O + (j - O)] = v;
+        else if (j < 2 * O + A) act[(int64_t)warp * A + (j - 2 * O)] = v;
+        else if (j == 2 * O + A) rew[warp] = v;
+        else term[warp] = v;
+    }
+}
+
+extern "C" {
+
+int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, const float* rew, const float* term,
+                     int64_t n, int obs_dim, int act_dim, float* table, int row_w, int64_t row_offset, void* stream) {
+    ORLK_REQUIRE(n >= 0 && obs_dim > 0 && act_dim > 0, "sizes");
+    ORLK_REQUIRE(row_w >= 2 * obs_dim + act_dim + 2, "row_w too small");
+    if (n == 0) return 0;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_replay_pack<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, next_obs, act, rew, term, n, obs_dim, act_dim,
+                                                                      table, row_w, row_offset);
+    return check_launch("k_replay_pack");
+}
+
+int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx, int n,
+                       float* obs2, float* act, float* rew, float* term, void* stream) {
+    ORLK_REQUIRE(n >= 0 && n_rows > 0, "sizes");
+    ORLK_REQUIRE(row_w >= 2 * obs_dim + act_dim + 2, "row_w too small");
+    if (n == 0) return 0;
+    const int wpb = 4;  // warps per block: 64 blocks for a 256 batch, spread over SMs
+    k_replay_gather<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(table, n_rows, row_w, obs_dim, act_dim,
+                                                                                idx, n, obs2, act, rew, term);
+    return check_launch("k_replay_gather");
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Runtime plumbing of the C ABI: error text, CUDA-graph capture/replay, copies, events.
+#include <stdarg.h>
+#include <string.h>
+#include "orlk_common.cuh"
+
+namespace orlk {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace orlk
+using namespace orlk;
+
+extern "C" {
+
+int orlk_abi_version(void) { return ORLK_ABI_VERSION; }
+const char* orlk_last_error(void) { return g_err; }
+int orlk_sizeof_gemm_desc(void) { return (int)sizeof(OrlkGemmDesc); }
+int orlk_sizeof_adam_desc(void) { return (int)sizeof(OrlkAdamDesc); }
+int orlk_sizeof_adam_group(void) { return (int)sizeof(OrlkAdamGroup); }
+int orlk_sizeof_concat_seg(void) { return (int)sizeof(OrlkConcatSeg); }
+
+int orlk_device_info(int device, int* out4) {
+    ORLK_REQUIRE(out4 != nullptr, "out4 is NULL");
+    cudaDeviceProp p;
+    int rc = check(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties");
+    if (rc) return rc;
+    out4[0] = p.multiProcessorCount;
+    out4[1] = p.major;
+    out4[2] = p.minor;
+    out4[3] = (int)p.sharedMemPerBlockOptin;
+    return 0;
+}
+
+int orlk_graph_begin(void* stream) {
+    return check(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+}
+
+int orlk_graph_end(void* stream, void** graph_exec_out) {
+    ORLK_REQUIRE(graph_exec_out != nullptr, "graph_exec_out is NULL");
+    cudaGraph_t g = nullptr;
+    int rc = check(cudaStreamEndCapture((cudaStream_t)stream, &g), "cudaStreamEndCapture");
+    if (rc) return rc;
+    cudaGraphExec_t ex = nullptr;
+    rc = check(cudaGraphInstantiate(&ex, g, 0), "cudaGraphInstantiate");
+    cudaGraphDestroy(g);
+    if (rc) return rc;
+    *graph_exec_out = (void*)ex;
+    return 0;
+}
+
+int orlk_graph_launch(void* graph_exec, void* stream) {
+    return check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
+}
+
+int orlk_graph_destroy(void* graph_exec) {
+    return check(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec), "cudaGraphExecDestroy");
+}
+
+int orlk_stream_sync(void* stream) { return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+
+int orlk_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream) {
+    return check(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "memcpy h2d");
+}
+int orlk_memcpy_d2h_async(void* dst_host, const void* src, size_t bytes, void* stream) {
+    return check(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "memcpy d2h");
+}
+int orlk_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream) {
+    return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "memcpy d2d");
+}
+int orlk_memset_async(void* dst, int value, size_t bytes, void* stream) {
+    return check(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream), "memset");
+}
+
+int orlk_event_create(void** ev_out) {
+    ORLK_REQUIRE(ev_out != nullptr, "ev_out is NULL");
+    cudaEvent_t e;
+    int rc = check(cudaEventCreate(&e), "cudaEventCreate");
+    if (rc) return rc;
+    *ev_out = (void*)e;
+    return 0;
+}
+int orlk_event_record(void* ev, void* stream) {
+    return check(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream), "cudaEventRecord");
+}
+int orlk_event_sync(void* ev) { return check(cudaEventSynchronize((cudaEvent_t)ev), "cudaEventSynchronize"); }
+int orlk_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out) {
+    int rc = check(cudaEventSynchronize((cudaEvent_t)ev_stop), "cudaEventSynchronize");
+    if (rc) return rc;
+    return check(cudaEventElapsedTime(ms_out, (cudaEvent_t)ev_start, (cudaEvent_t)ev_stop), "cudaEventElapsedTime");
+}
+int orlk_event_destroy(void* ev) { return check(cudaEventDestroy((cudaEvent_t)ev), "cudaEventDestroy"); }
+
+}  // extern "C"

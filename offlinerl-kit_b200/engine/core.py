@@ -1,0 +1,239 @@
+"""Core host plumbing: device views, GEMM/Adam descriptor tables, launch plans (CUDA graph capture)."""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+NUM_SMS = 148
+
+
+def require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise L.OrlkError(f"offlinerlkit_b200 needs a CUDA device (got {dev}); there is no CPU fallback")
+    L.load()
+    return dev
+
+
+@dataclass
+class Mat:
+    """A row-major fp32 device matrix view: element (r,c) at ptr + 4*(r*ld + c)."""
+    ptr: int
+    rows: int
+    cols: int
+    ld: int
+    keep: object = None     # tensor that owns the memory (kept alive)
+
+    @staticmethod
+    def of(t: torch.Tensor) -> "Mat":
+        assert t.dtype == torch.float32 and t.is_cuda
+        if t.dim() == 1:
+            t = t.view(1, -1)
+        assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+        return Mat(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0) if t.shape[0] > 1 else t.shape[1], t)
+
+    def rows_(self, r0: int, r1: int) -> "Mat":
+        assert 0 <= r0 <= r1 <= self.rows
+        return Mat(self.ptr + 4 * r0 * self.ld, r1 - r0, self.cols, self.ld, self.keep)
+
+    def cols_(self, c0: int, c1: int) -> "Mat":
+        assert 0 <= c0 <= c1 <= self.cols
+        return Mat(self.ptr + 4 * c0, self.rows, c1 - c0, self.ld, self.keep)
+
+
+@dataclass
+class GP:
+    """One GEMM problem C[M,N] = epi(A x B) in the terms of include/orlk_b200.h:OrlkGemmDesc."""
+    A: int
+    lda: int
+    a_layout: int
+    B: int
+    ldb: int
+    b_layout: int
+    C: int
+    ldc: int
+    M: int
+    N: int
+    K: int
+    epi: int = L.EPI_NONE
+    bias: int = 0
+    aux: int = 0
+    ldaux: int = 0
+    C2: int = 0
+    rowsum: int = 0
+    colsum: int = 0
+    k_splits: int = 1
+    split_base: int = 0
+    c_split_stride: int = 0
+    sum_split_stride: int = 0
+
+
+class Runtime:
+    """One CUDA stream + the loaded library + a keep-alive list for descriptor tables."""
+
+    def __init__(self, device):
+        self.device = require_cuda(device)
+        self.lib = L.load()
+        torch.cuda.set_device(self.device)
+        # Launches go to torch's current stream (normally the legacy default stream) so that they are ordered with
+        # the caller's own torch work; graph capture needs a non-default stream, so Plan.capture() temporarily
+        # switches `cur` to a private one.
+        self.capture_stream = torch.cuda.Stream(device=self.device)
+        self.exec_ptr = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.cur = self.exec_ptr
+        self._keep: List[torch.Tensor] = []
+
+    # ---- memory helpers (torch owns device memory: plumbing)
+    def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def upload_bytes(self, raw: bytes) -> torch.Tensor:
+        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self._keep.append(t)
+        return t
+
+    def sync(self) -> None:
+        L.call("orlk_stream_sync", self.cur)
+
+    # ---- launch builders: each returns a zero-argument closure that enqueues on self.stream
+    def gemm(self, problems: Sequence[GP], cfg: int) -> Callable[[], None]:
+        BM, BN, BK = L.CFG_TILES[cfg]
+        arr = (L.GemmDesc * len(problems))()
+        tile = 0
+        for i, p in enumerate(problems):
+            d = arr[i]
+            tiles_m, tiles_n = -(-p.M // BM), -(-p.N // BN)
+            splits = max(1, p.k_splits)
+            chunk = -(-p.K // splits)
+            chunk = -(-chunk // BK) * BK
+            splits = max(1, -(-p.K // chunk))
+            if p.epi != L.EPI_NONE or p.bias:
+                assert splits == 1, "epilogues need the full k range"
+            d.A, d.B, d.C, d.C2 = p.A, p.B, p.C, p.C2 or None
+            d.bias, d.aux, d.rowsum, d.colsum = p.bias or None, p.aux or None, p.rowsum or None, p.colsum or None
+            d.lda, d.ldb, d.ldc, d.ldaux = p.lda, p.ldb, p.ldc, p.ldaux
+            d.c_split_stride, d.sum_split_stride = p.c_split_stride, p.sum_split_stride
+            d.M, d.N, d.K = p.M, p.N, p.K
+            d.a_layout, d.b_layout, d.epi = p.a_layout, p.b_layout, p.epi
+            d.k_splits, d.k_chunk, d.split_base = splits, chunk, p.split_base
+            d.tile_start, d.tiles_m, d.tiles_n = tile, tiles_m, tiles_n
+            tile += tiles_m * tiles_n * splits
+        dev = self.upload_bytes(bytes(arr))
+        n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())
+        return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, self.cur)
+
+    @staticmethod
+    def effective_splits(K: int, want: int, cfg: int) -> int:
+        """Number of k-splits the descriptor builder will actually produce for (K, want)."""
+        BK = L.CFG_TILES[cfg][2]
+        want = max(1, want)
+        chunk = -(-(-(-K // want)) // BK) * BK
+        return max(1, -(-K // chunk))
+
+    def concat(self, segs: Sequence[Tuple[Mat, Mat, int, Mat]]) -> Callable[[], None]:
+        """segs: (dst, src1, rep1, src2): dst[m] = [src1[m // rep1] | src2[m]]."""
+        arr = (L.ConcatSeg * len(segs))()
+        row = 0
+        for i, (dst, s1, rep, s2) in enumerate(segs):
+            sg = arr[i]
+            sg.dst, sg.src1, sg.src2 = dst.ptr, s1.ptr, s2.ptr
+            sg.ld_dst, sg.ld1, sg.ld2 = dst.ld, s1.ld, s2.ld
+            sg.M, sg.w1, sg.w2, sg.rep1, sg.row_start = dst.rows, s1.cols, s2.cols, rep, row
+            assert dst.cols == s1.cols + s2.cols and s2.rows == dst.rows and s1.rows * rep >= dst.rows
+            row += dst.rows
+        dev = self.upload_bytes(bytes(arr))
+        n, total, ptr = len(segs), row, C.c_void_p(dev.data_ptr())
+        return lambda: L.call("orlk_concat_rows", ptr, n, total, self.cur)
+
+    def adam(self, descs: Sequence["AdamT"], groups_ptr: int) -> Callable[[], None]:
+        arr = (L.AdamDesc * len(descs))()
+        blk = 0
+        for i, t in enumerate(descs):
+            d = arr[i]
+            d.p, d.m, d.v, d.tgt, d.grad = t.p, t.m or None, t.v or None, t.tgt or None, t.grad or None
+            d.n, d.g_split_stride, d.g_splits, d.group = t.n, t.g_split_stride, t.g_splits, t.group
+            d.wd, d.block_start, d.flags = t.wd, blk, t.flags
+            blk += -(-t.n // 1024)
+        dev = self.upload_bytes(bytes(arr))
+        n, total, ptr, gp = len(descs), blk, C.c_void_p(dev.data_ptr()), C.c_void_p(groups_ptr)
+        return lambda: L.call("orlk_adam_step", ptr, n, total, gp, self.cur)
+
+
+@dataclass
+class AdamT:
+    p: int
+    n: int
+    group: int
+    m: int = 0
+    v: int = 0
+    tgt: int = 0
+    grad: int = 0
+    g_splits: int = 1
+    g_split_stride: int = 0
+    wd: float = 0.0
+    flags: int = L.OPT_ADAM
+
+
+class Plan:
+    """An ordered list of launches; runs eagerly (debug) or as one captured CUDA graph."""
+
+    def __init__(self, rt: Runtime, name: str = ""):
+        self.rt, self.name = rt, name
+        self.ops: List[Tuple[str, Callable[[], None]]] = []
+        self.graph: Optional[C.c_void_p] = None
+
+    def add(self, label: str, op: Callable[[], None]) -> None:
+        self.ops.append((label, op))
+
+    @property
+    def n_launches(self) -> int:
+        return len(self.ops)
+
+    def run_eager(self) -> None:
+        for _, op in self.ops:
+            op()
+
+    def capture(self) -> None:
+        g = C.c_void_p()
+        rt = self.rt
+        torch.cuda.synchronize(rt.device)
+        rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
+        try:
+            L.call("orlk_graph_begin", rt.cur)
+            try:
+                self.run_eager()
+            finally:
+                L.call("orlk_graph_end", rt.cur, C.byref(g))
+        finally:
+            rt.cur = rt.exec_ptr
+        self.graph = g
+
+    def launch(self) -> None:
+        if self.graph is None:
+            self.capture()
+        L.call("orlk_graph_launch", self.graph, self.rt.cur)
+
+    def __del__(self):
+        try:
+            if self.graph is not None:
+                L.load().orlk_graph_destroy(self.graph)
+        except Exception:
+            pass
+
+
+_RUNTIMES: Dict[str, Runtime] = {}
+
+
+def get_runtime(device) -> Runtime:
+    """One Runtime per CUDA device, shared by buffers, policies and dynamics."""
+    dev = require_cuda(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = f"cuda:{idx}"
+    if key not in _RUNTIMES:
+        _RUNTIMES[key] = Runtime(torch.device(key))
+    return _RUNTIMES[key]

@@ -1,0 +1,248 @@
+"""Shared machinery of the per-algorithm gradient-step engines.
+
+A ``Learner`` owns: the Adam group table (lr / betas / eps / tau / step counters, device resident), the loss block
+(device + pinned host), the noise block (filled by the Philox kernel, or by the caller in parity mode) and the
+staging batch.  Sub-classes build a ``Plan`` (ordered launches) per step variant; ``step()`` replays it as one
+CUDA graph and returns the loss scalars after a single stream synchronisation -- the ``Dict[str, float]``
+contract of ``policy.learn`` (policy/base_policy.py:25-26).
+"""
+import ctypes as C
+import struct
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .core import GP, AdamT, Mat, Plan, Runtime, get_runtime
+from .nets import (GradBuf, Layer, ParamSet, adam_descs, dgrad_problem, fwd_problem, pick_cfg, wgrad_problem,
+                   wgrad_splits)
+
+MAX_GROUPS = 16
+N_LOSS = 32
+
+
+def linears_of(module: nn.Module) -> List[nn.Linear]:
+    return [m for m in module.modules() if isinstance(m, nn.Linear)]
+
+
+def check_plain_mlp(backbone: nn.Module, what: str) -> None:
+    """The engine implements Linear+ReLU stacks without dropout (what the five run scripts build)."""
+    for m in backbone.modules():
+        if isinstance(m, nn.Dropout):
+            raise L.OrlkError(f"{what}: dropout is not supported by the CUDA engine")
+        if isinstance(m, (nn.Tanh, nn.Sigmoid, nn.ELU, nn.LeakyReLU, nn.GELU)):
+            raise L.OrlkError(f"{what}: only ReLU hidden activations are supported, found {type(m).__name__}")
+
+
+def adam_hyper(optim: torch.optim.Optimizer) -> Dict[str, float]:
+    if not isinstance(optim, torch.optim.Adam):
+        raise L.OrlkError(f"the CUDA engine implements torch.optim.Adam only, got {type(optim).__name__}")
+    g = optim.param_groups[0]
+    if g.get("amsgrad", False) or g.get("weight_decay", 0) != 0 or g.get("maximize", False):
+        raise L.OrlkError("Adam options amsgrad / weight_decay / maximize are not supported")
+    b1, b2 = g["betas"]
+    return dict(lr=float(g["lr"]), beta1=float(b1), beta2=float(b2), eps=float(g["eps"]))
+
+
+class Learner:
+    def __init__(self, device):
+        self.rt: Runtime = get_runtime(device)
+        self.dev = self.rt.device
+        self._groups = (L.AdamGroup * MAX_GROUPS)()
+        self._n_groups = 0
+        self._group_optim: Dict[int, torch.optim.Optimizer] = {}
+        self._group_lr: Dict[int, float] = {}
+        self.groups_dev = torch.zeros(MAX_GROUPS * C.sizeof(L.AdamGroup), dtype=torch.uint8, device=self.dev)
+        self._lr_host = torch.zeros(MAX_GROUPS, dtype=torch.float32).pin_memory()
+        self.loss_dev = self.rt.zeros(N_LOSS)
+        self.loss_host = torch.zeros(N_LOSS, dtype=torch.float32).pin_memory()
+        self.loss_np = self.loss_host.numpy()
+        self.scalars = self.rt.zeros(L.SC_COUNT)
+        self.philox_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.noise_enable = torch.ones(1, dtype=torch.int32, device=self.dev)
+        self._noise_enabled_host = True
+        self.plans: Dict[str, Plan] = {}
+        self.use_graph = True
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ Adam groups
+    def add_group(self, optim: Optional[torch.optim.Optimizer], tau: float = 0.0, **hyper) -> int:
+        g = self._n_groups
+        assert g < MAX_GROUPS
+        h = adam_hyper(optim) if optim is not None else hyper
+        e = self._groups[g]
+        e.lr, e.beta1, e.beta2, e.eps, e.tau, e.step = h["lr"], h["beta1"], h["beta2"], h["eps"], tau, 0
+        if optim is not None:
+            self._group_optim[g] = optim
+        self._group_lr[g] = h["lr"]
+        self._n_groups += 1
+        return g
+
+    def push_groups(self) -> None:
+        raw = torch.frombuffer(bytearray(bytes(self._groups)), dtype=torch.uint8)
+        self.groups_dev.copy_(raw.to(self.dev))
+
+    def sync_lr(self) -> None:
+        """lr schedulers mutate ``optim.param_groups`` between epochs (run_iql.py:132-135): re-read and upload."""
+        for g, opt in self._group_optim.items():
+            lr = float(opt.param_groups[0]["lr"])
+            if lr != self._group_lr[g]:
+                self._group_lr[g] = lr
+                self._lr_host[g] = lr
+                L.call("orlk_memcpy_h2d_async", self.groups_dev.data_ptr() + g * C.sizeof(L.AdamGroup),
+                       self._lr_host.data_ptr() + 4 * g, 4, self.rt.cur)
+
+    def group_steps(self) -> List[int]:
+        raw = self.groups_dev.cpu().numpy().tobytes()
+        sz = C.sizeof(L.AdamGroup)
+        return [struct.unpack_from("i", raw, g * sz + 20)[0] for g in range(self._n_groups)]
+
+    @property
+    def groups_ptr(self) -> int:
+        return self.groups_dev.data_ptr()
+
+    # ------------------------------------------------------------------ noise
+    def set_noise_enabled(self, on: bool) -> None:
+        if on != self._noise_enabled_host:
+            self.noise_enable.fill_(1 if on else 0)
+            self._noise_enabled_host = on
+
+    # ------------------------------------------------------------------ plan execution
+    def run(self, key: str) -> np.ndarray:
+        plan = self.plans[key]
+        if self.use_graph:
+            plan.launch()
+        else:
+            plan.run_eager()
+        self.rt.sync()
+        self.steps_done += 1
+        return self.loss_np
+
+    def enqueue(self, key: str) -> None:
+        """Launch a step without waiting for it (used by the device-resident benchmark loop)."""
+        plan = self.plans[key]
+        if self.use_graph:
+            plan.launch()
+        else:
+            plan.run_eager()
+        self.steps_done += 1
+
+    def finish_ops(self, plan: Plan, group_mask: int) -> None:
+        rt = self
+        gp, cp = C.c_void_p(self.groups_ptr), C.c_void_p(self.philox_counter.data_ptr())
+        plan.add("step_end", lambda: L.call("orlk_step_end", gp, group_mask, cp, self.rt.cur))
+        ld, lh = C.c_void_p(self.loss_dev.data_ptr()), C.c_void_p(self.loss_host.data_ptr())
+        plan.add("losses_d2h", lambda: L.call("orlk_memcpy_d2h_async", lh, ld, 4 * N_LOSS, self.rt.cur))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Reusable schedule fragments for ReLU MLP member groups
+# --------------------------------------------------------------------------------------------------------------
+class MlpRun:
+    """Activation / gradient buffers of one forward(+backward) pass of a ParamSet over M rows."""
+
+    def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P"):
+        self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
+        G = ps.G
+        self.H = [rt.zeros(G, M, ps.layers[l].out_dim) for l in range(n_hidden)]
+        self.dZ = [rt.zeros(G, M, ps.layers[l].out_dim) for l in range(n_hidden)] if need_grad else None
+        self.has_head = len(ps.layers) > n_hidden
+        self.NS = ps.layers[n_hidden].out_dim if self.has_head else 0
+        self.out = rt.zeros(G, M, self.NS) if self.has_head else None
+        self.dOut = rt.zeros(G, M, self.NS) if (self.has_head and need_grad) else None
+
+    def h(self, l: int, g: int) -> Mat:
+        return Mat.of(self.H[l][g])
+
+    def dz(self, l: int, g: int) -> Mat:
+        return Mat.of(self.dZ[l][g])
+
+
+def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
+    """Hidden layers as grouped GEMMs (+bias+ReLU fused), then the narrow head as a warp-per-row kernel."""
+    ps, G = run.ps, run.ps.G
+    for l in range(run.nh):
+        probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store)
+                 for g in range(G)]
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(run.M * G, ps.layers[l].out_dim)))
+    if run.has_head:
+        emit_head_forward(rt, plan, run, tag)
+
+
+def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
+    ps, G, l = run.ps, run.ps.G, run.nh
+    lay = ps.layers[l]
+    hin = run.H[l - 1]
+    K = lay.in_dim
+    if lay.layout == "io":
+        assert lay.out_dim == 1, "ensemble heads wider than 1 go through the GEMM path"
+    args = (hin.data_ptr(), K, run.M * K, ps.w(l, 0, run.store), K, lay.w_gs, ps.b(l, 0, run.store), lay.b_gs,
+            run.out.data_ptr(), run.NS, run.M * run.NS, run.M, K, run.NS, G)
+    plan.add(f"{tag}.head", lambda: L.call("orlk_skinny_fwd", *args, rt.cur))
+
+
+def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
+    """dZ[last hidden] = (dOut W_head) * relu'(H[last hidden])."""
+    ps, G, l = run.ps, run.ps.G, run.nh
+    lay = ps.layers[l]
+    K = lay.in_dim
+    hmask = run.H[l - 1]
+    args = (run.dOut.data_ptr(), run.NS, run.M * run.NS, ps.w(l, 0), K, lay.w_gs, hmask.data_ptr(), K, run.M * K,
+            run.dZ[l - 1].data_ptr(), K, run.M * K, run.M, K, run.NS, G)
+    plan.add(f"{tag}.head_dgrad", lambda: L.call("orlk_skinny_dgrad", *args, rt.cur))
+
+
+def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1) -> None:
+    """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to."""
+    ps, G = run.ps, run.ps.G
+    for l in range(run.nh - 1, down_to - 1, -1):
+        probs = [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g))
+                 for g in range(G)]
+        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(run.M * G, ps.layers[l].in_dim)))
+
+
+def wgrad_layout(ps: ParamSet, n_layers: int, M: int) -> List[Tuple[int, int]]:
+    """(tile config, split-K factor) per layer for a weight-gradient reduction over M rows."""
+    out = []
+    for l in range(n_layers):
+        lay = ps.layers[l]
+        out_r, out_c = (lay.out_dim, lay.in_dim) if lay.layout == "oi" else (lay.in_dim, lay.out_dim)
+        cfg = L.CFG_BIG if (out_r >= 128 and out_c >= 128 and M >= 2048) else L.CFG_SMALL
+        BM, BN, _ = L.CFG_TILES[cfg]
+        tiles = (-(-out_r // BM)) * (-(-out_c // BN)) * ps.G
+        out.append((cfg, wgrad_splits(tiles, M, cfg)))
+    return out
+
+
+def make_gradbuf(rt: Runtime, ps: ParamSet, row_counts: Sequence[Tuple[int, int]]) -> GradBuf:
+    """GradBuf with enough split slots for reductions over each (n_layers, M) the ParamSet will see."""
+    slots = 1
+    for n_layers, M in row_counts:
+        slots = max([slots] + [s for _, s in wgrad_layout(ps, n_layers, M)])
+    return GradBuf(rt, ps, slots)
+
+
+def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: GradBuf, groups_ptr: int, tag: str,
+                    polyak: bool) -> None:
+    """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update."""
+    ps, G, M = run.ps, run.ps.G, run.M
+    big, small = [], []
+    n_l = run.nh + (1 if run.has_head else 0)
+    layout = wgrad_layout(ps, n_l, M)
+    splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
+    for l in range(n_l):
+        cfg, s = layout[l]
+        assert s <= gb.n_slots, (s, gb.n_slots)
+        for g in range(G):
+            xin = X[g] if l == 0 else run.h(l - 1, g)
+            dy = run.dz(l, g) if l < run.nh else Mat.of(run.dOut[g])
+            (big if cfg == L.CFG_BIG else small).append(wgrad_problem(ps, gb, l, g, xin, dy, s))
+    if big:
+        plan.add(f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG))
+    if small:
+        plan.add(f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL))
+    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l)), groups_ptr))
+
+

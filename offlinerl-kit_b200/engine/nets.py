@@ -1,0 +1,283 @@
+"""Parameter arenas and launch emitters for dense (MLP / ensemble) networks.
+
+A ``ParamSet`` owns the parameters of G identically-shaped networks ("members": twin critics, or the E members
+of an EnsembleLinear stack), their Adam moments and (optionally) their target copies, each in ONE contiguous
+fp32 device tensor.  The ``nn.Parameter`` objects of the facade modules are re-pointed at views of that tensor,
+so ``state_dict()`` / ``torch.save`` / ``load_state_dict`` keep working unchanged while the
+kernels see ``base + offset``.
+"""
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .core import GP, AdamT, Mat, Plan, Runtime, NUM_SMS
+
+
+@dataclass
+class Layer:
+    """One dense layer of a member group.  ``layout`` is 'oi' (nn.Linear, W[out,in]) or 'io' (EnsembleLinear W[in,out])."""
+    in_dim: int
+    out_dim: int
+    layout: str
+    w_off: int          # offsets (floats) of member 0 inside the ParamSet block
+    b_off: int
+    w_gs: int           # member stride (floats)
+    b_gs: int
+
+    @property
+    def w_numel(self) -> int:
+        return self.in_dim * self.out_dim
+
+
+class ParamSet:
+    def __init__(self, rt: Runtime, name: str):
+        self.rt, self.name = rt, name
+        self.G = 0
+        self.total = 0                    # floats in the parameter tensor
+        self.layers: List[Layer] = []     # hidden layers followed by narrow heads, in forward order
+        self.extra: Dict[str, Tuple[int, int]] = {}   # name -> (offset, numel) of non-layer parameters
+        self.P = self.Mo = self.Vo = self.T = None
+        self.group_ids: List[int] = []     # Adam group index per member (set by the learner)
+
+    # ------------------------------------------------------------------ construction from facade modules
+    @staticmethod
+    def _align(n: int) -> int:
+        return (n + 3) // 4 * 4
+
+    @classmethod
+    def from_linear_members(cls, rt: Runtime, name: str, members: Sequence[Sequence[nn.Linear]],
+                            targets: Optional[Sequence[Sequence[nn.Linear]]] = None,
+                            extra: Optional[Sequence[Dict[str, nn.Parameter]]] = None,
+                            fuse_last: int = 1) -> "ParamSet":
+        """members[g] = the nn.Linear modules of member g in forward order.  The last ``fuse_last`` Linears are
+        narrow heads; when ``fuse_last`` == 2 (dist_net.mu, dist_net.sigma) they are placed back to back so the
+        engine sees one [2A, K] head."""
+        self = cls(rt, name)
+        self.G = len(members)
+        ref = members[0]
+        off = 0
+        n_lin = len(ref)
+        spec = []
+        i = 0
+        while i < n_lin:
+            lin = ref[i]
+            if fuse_last == 2 and i == n_lin - 2:
+                nxt = ref[i + 1]
+                assert nxt.in_features == lin.in_features
+                out = lin.out_features + nxt.out_features
+                w_off = off; off += out * lin.in_features
+                off = cls._align(off)
+                b_off = off; off += out
+                off = cls._align(off)
+                spec.append((lin.in_features, out, w_off, b_off, (i, i + 1)))
+                i += 2
+            else:
+                w_off = off; off += lin.out_features * lin.in_features
+                off = cls._align(off)
+                b_off = off; off += lin.out_features
+                off = cls._align(off)
+                spec.append((lin.in_features, lin.out_features, w_off, b_off, (i,)))
+                i += 1
+        extra_spec = {}
+        if extra is not None:
+            for k, p in extra[0].items():
+                extra_spec[k] = (off, p.numel())
+                off = cls._align(off + p.numel())
+        block = cls._align(off)
+        self.total = block * self.G
+        self.block = block
+        self.layers = [Layer(i_, o_, "oi", w, b, block, block) for (i_, o_, w, b, _) in spec]
+        self.extra = extra_spec
+        self._alloc(targets is not None)
+        for g, lins in enumerate(members):
+            self._adopt_linears(self.P, g, lins, spec)
+            if extra is not None:
+                for k, p in extra[g].items():
+                    o, n = extra_spec[k]
+                    self._adopt(self.P, g * block + o, p)
+        if targets is not None:
+            for g, lins in enumerate(targets):
+                self._adopt_linears(self.T, g, lins, spec)
+        return self
+
+    def _adopt_linears(self, store, g, lins, spec):
+        for (in_f, out_f, w_off, b_off, idxs) in spec:
+            wo, bo = g * self.block + w_off, g * self.block + b_off
+            for j in idxs:
+                lin = lins[j]
+                self._adopt(store, wo, lin.weight)
+                self._adopt(store, bo, lin.bias)
+                wo += lin.weight.numel()
+                bo += lin.bias.numel()
+
+    @classmethod
+    def from_ensemble(cls, rt: Runtime, name: str, layers: Sequence[nn.Module],
+                      targets: Optional[Sequence[nn.Module]] = None,
+                      extra: Optional[Dict[str, nn.Parameter]] = None) -> "ParamSet":
+        """layers = EnsembleLinear-like modules (``weight`` [E,in,out], ``bias`` [E,1,out]) in forward order."""
+        self = cls(rt, name)
+        E = layers[0].weight.shape[0]
+        self.G = E
+        off = 0
+        spec = []
+        for lay in layers:
+            _, i_, o_ = lay.weight.shape
+            w_off = off; off = cls._align(off + E * i_ * o_)
+            b_off = off; off = cls._align(off + E * o_)
+            spec.append((i_, o_, w_off, b_off))
+        extra_spec = {}
+        if extra is not None:
+            for k, p in extra.items():
+                extra_spec[k] = (off, p.numel())
+                off = cls._align(off + p.numel())
+        self.total = self.block = off
+        self.layers = [Layer(i_, o_, "io", w, b, i_ * o_, o_) for (i_, o_, w, b) in spec]
+        self.extra = extra_spec
+        self._alloc(targets is not None)
+        for lay, (i_, o_, w, b) in zip(layers, spec):
+            self._adopt(self.P, w, lay.weight)
+            self._adopt(self.P, b, lay.bias)
+        if extra is not None:
+            for k, p in extra.items():
+                self._adopt(self.P, extra_spec[k][0], p)
+        if targets is not None:
+            for lay, (i_, o_, w, b) in zip(targets, spec):
+                self._adopt(self.T, w, lay.weight)
+                self._adopt(self.T, b, lay.bias)
+        return self
+
+    def _alloc(self, with_target: bool) -> None:
+        self.P = self.rt.zeros(self.total)
+        self.Mo = self.rt.zeros(self.total)
+        self.Vo = self.rt.zeros(self.total)
+        self.T = self.rt.zeros(self.total) if with_target else None
+
+    @staticmethod
+    def _adopt(store: torch.Tensor, off: int, p: torch.Tensor) -> None:
+        """Copy the parameter's current value into the arena and re-point its storage at the arena view."""
+        view = store[off:off + p.numel()].view(p.shape)
+        with torch.no_grad():
+            view.copy_(p.detach().to(store.device, torch.float32))
+        p.data = view
+
+    # ------------------------------------------------------------------ pointers
+    def _ptr(self, store: torch.Tensor, off: int) -> int:
+        return store.data_ptr() + 4 * off
+
+    def w(self, l: int, g: int = 0, store: str = "P") -> int:
+        lay = self.layers[l]
+        return self._ptr(getattr(self, store), lay.w_off + g * lay.w_gs)
+
+    def b(self, l: int, g: int = 0, store: str = "P") -> int:
+        lay = self.layers[l]
+        return self._ptr(getattr(self, store), lay.b_off + g * lay.b_gs)
+
+    def extra_ptr(self, name: str, store: str = "P") -> int:
+        return self._ptr(getattr(self, store), self.extra[name][0])
+
+
+class GradBuf:
+    """Split-K partial gradient storage for one ParamSet: [n_slots, total] floats, zero-initialised.
+
+    Slot s of a tensor lives at ``base + s*total + offset`` so that a single Adam descriptor per tensor can sum
+    ``g_splits`` partials with stride ``total``."""
+
+    def __init__(self, rt: Runtime, ps: ParamSet, n_slots: int):
+        self.ps, self.n_slots = ps, n_slots
+        self.buf = rt.zeros(n_slots * ps.total)
+
+    def ptr(self, off: int) -> int:
+        return self.buf.data_ptr() + 4 * off
+
+    @property
+    def stride(self) -> int:
+        return self.ps.total
+
+
+# ---------------------------------------------------------------------------------------------- emitters
+def pick_cfg(M: int, N: int) -> int:
+    """Tile configuration for an output of M x N (see csrc/orlk_gemm.cu)."""
+    if M * N >= 128 * 128 * 96:
+        return L.CFG_BIG
+    if M * N >= 64 * 64 * 96:
+        return L.CFG_MID
+    return L.CFG_SMALL
+
+
+def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: str = "P", Z: Optional[Mat] = None) -> GP:
+    """Y = act(X W^T + b) for member g of layer l (nn.Linear, mlp.py:22 / EnsembleLinear, ensemble_linear.py:30-41)."""
+    lay = ps.layers[l]
+    assert X.cols == lay.in_dim and Y.cols == lay.out_dim and X.rows == Y.rows, (X, Y, lay)
+    if lay.layout == "oi":
+        b_layout, ldb = 1, lay.in_dim
+    else:
+        b_layout, ldb = 0, lay.out_dim
+    return GP(A=X.ptr, lda=X.ld, a_layout=0, B=ps.w(l, g, store), ldb=ldb, b_layout=b_layout, C=Y.ptr, ldc=Y.ld,
+              M=X.rows, N=lay.out_dim, K=lay.in_dim, epi=epi, bias=ps.b(l, g, store),
+              C2=Z.ptr if Z is not None else 0)
+
+
+def dgrad_problem(ps: ParamSet, l: int, g: int, dY: Mat, dX: Mat, epi: int, aux: Optional[Mat],
+                  col0: int = 0, ncols: Optional[int] = None) -> GP:
+    """dX[:, col0:col0+ncols] = (dY W)[:, col0:...] (x) mask  -- input gradient of layer l for member g."""
+    lay = ps.layers[l]
+    ncols = lay.in_dim - col0 if ncols is None else ncols
+    assert dY.cols == lay.out_dim and dX.cols == ncols and dX.rows == dY.rows
+    if lay.layout == "oi":      # W[out,in]: B(k=o, n=i) = W[o*in + i]
+        Bp, b_layout, ldb = ps.w(l, g) + 4 * col0, 0, lay.in_dim
+    else:                       # W[in,out]: B(k=o, n=i) = W[i*out + o]
+        Bp, b_layout, ldb = ps.w(l, g) + 4 * col0 * lay.out_dim, 1, lay.out_dim
+    return GP(A=dY.ptr, lda=dY.ld, a_layout=0, B=Bp, ldb=ldb, b_layout=b_layout, C=dX.ptr, ldc=dX.ld,
+              M=dY.rows, N=ncols, K=lay.out_dim, epi=epi, aux=aux.ptr if aux is not None else 0,
+              ldaux=aux.ld if aux is not None else 0)
+
+
+def wgrad_problem(ps: ParamSet, gb: GradBuf, l: int, g: int, X: Mat, dY: Mat, k_splits: int, split_base: int = 0,
+                  col0: int = 0, with_bias: bool = True) -> GP:
+    """Partial dW (and db) of layer l, member g, reduced over the rows of X / dY, into GradBuf slots."""
+    lay = ps.layers[l]
+    assert X.rows == dY.rows and dY.cols == lay.out_dim
+    w_off = lay.w_off + g * lay.w_gs
+    b_off = lay.b_off + g * lay.b_gs
+    if lay.layout == "oi":      # dW[o,i] = sum_m dY[m,o] X[m,i]
+        return GP(A=dY.ptr, lda=dY.ld, a_layout=1, B=X.ptr, ldb=X.ld, b_layout=0, C=gb.ptr(w_off + col0), ldc=lay.in_dim,
+                  M=lay.out_dim, N=X.cols, K=X.rows, k_splits=k_splits, split_base=split_base,
+                  c_split_stride=gb.stride, sum_split_stride=gb.stride,
+                  rowsum=gb.ptr(b_off) if with_bias else 0)
+    return GP(A=X.ptr, lda=X.ld, a_layout=1, B=dY.ptr, ldb=dY.ld, b_layout=0, C=gb.ptr(w_off + col0 * lay.out_dim),
+              ldc=lay.out_dim, M=X.cols, N=lay.out_dim, K=X.rows, k_splits=k_splits, split_base=split_base,
+              c_split_stride=gb.stride, sum_split_stride=gb.stride, colsum=gb.ptr(b_off) if with_bias else 0)
+
+
+def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polyak: bool,
+               layers: Optional[Sequence[int]] = None) -> List[AdamT]:
+    """One Adam(+polyak) descriptor per weight / bias tensor (all members of a tensor when they are contiguous)."""
+    out = []
+    idx = range(len(ps.layers)) if layers is None else layers
+    for l in idx:
+        lay, s = ps.layers[l], splits_per_layer[l]
+        contiguous = (lay.w_gs == lay.w_numel)          # ensemble tensors: members back to back
+        for g in ([0] if contiguous else range(ps.G)):
+            nw = lay.w_numel * (ps.G if contiguous else 1)
+            nb = lay.out_dim * (ps.G if contiguous else 1)
+            wo = lay.w_off + (0 if contiguous else g * lay.w_gs)
+            bo = lay.b_off + (0 if contiguous else g * lay.b_gs)
+            for off, n in ((wo, nw), (bo, nb)):
+                out.append(AdamT(p=ps._ptr(ps.P, off), n=n, group=ps.group_ids[g], m=ps._ptr(ps.Mo, off),
+                                 v=ps._ptr(ps.Vo, off), tgt=ps._ptr(ps.T, off) if (polyak and ps.T is not None) else 0,
+                                 grad=gb.ptr(off), g_splits=s, g_split_stride=gb.stride,
+                                 flags=L.OPT_ADAM | (L.OPT_POLYAK if polyak and ps.T is not None else 0)))
+    return out
+
+
+def wgrad_splits(out_tiles: int, K: int, cfg: int, target_ctas: Optional[int] = None) -> int:
+    """Split-K factor so that a wgrad launch fills the machine: ~target_ctas CTAs, chunks >= 2*BK."""
+    BK = L.CFG_TILES[cfg][2]
+    if target_ctas is None:
+        target_ctas = NUM_SMS if cfg == L.CFG_BIG else 2 * NUM_SMS
+    want = max(1, target_ctas // max(1, out_tiles))
+    want = min(want, max(1, K // (2 * BK)))
+    return Runtime.effective_splits(K, want, cfg)

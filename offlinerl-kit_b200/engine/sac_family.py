@@ -1,0 +1,273 @@
+"""Gradient-step engines for the twin-critic / tanh-Gaussian-actor algorithms: CQL and SAC (MOPO's learner).
+
+Schedules follow the reference op order exactly:
+  CQL  (policy/model_free/cql.py:87-207):  actor -> alpha -> [updated actor] TD target + conservative term
+        (3-way logsumexp per repeat row) -> (Lagrange alpha') -> critic1, critic2 -> polyak.
+  SAC  (policy/model_free/sac.py:88-140):  critics -> actor (updated critics) -> alpha (clamped) -> polyak.
+What is *not* reproduced is the reference's wasted work: critic weight gradients in the actor step, actor
+back-propagation from the critic losses, and the actor forward over the 10x repeated rows (the head is
+evaluated once per distinct state and sampled 10 times).
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .core import Mat, Plan
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
+                      emit_wgrad_adam, linears_of, make_gradbuf)
+from .nets import ParamSet, dgrad_problem, pick_cfg
+
+# loss block layout (floats)
+LS_ACTOR, LS_ALPHA_LOSS, LS_ALPHA = 0, 1, 2
+LS_C1, LS_C2, LS_CQL_ALPHA_LOSS, LS_CQL_ALPHA = 4, 5, 6, 7
+
+
+class TwinCriticLearner(Learner):
+    """Common state: actor ParamSet (fused mu|sigma head), twin critic ParamSet with targets, alpha scalars."""
+
+    clamp_alpha = True
+
+    def __init__(self, policy, batch_size: int):
+        actor, c1, c2 = policy.actor, policy.critic1, policy.critic2
+        super().__init__(actor.device)
+        rt = self.rt
+        self.policy, self.B = policy, int(batch_size)
+        check_plain_mlp(actor.backbone, "actor")
+        check_plain_mlp(c1.backbone, "critic")
+        dist = actor.dist_net
+        if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
+            raise L.OrlkError("SAC/CQL engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
+        a_lin = linears_of(actor)
+        self.actor_ps = ParamSet.from_linear_members(rt, "actor", [a_lin], fuse_last=2)
+        self.critic_ps = ParamSet.from_linear_members(
+            rt, "critics", [linears_of(c1), linears_of(c2)],
+            targets=[linears_of(policy.critic1_old), linears_of(policy.critic2_old)], fuse_last=1)
+        self.nh_a = len(self.actor_ps.layers) - 1
+        self.nh_c = len(self.critic_ps.layers) - 1
+        self.O = self.actor_ps.layers[0].in_dim
+        self.A = self.actor_ps.layers[-1].out_dim // 2
+        assert self.critic_ps.layers[0].in_dim == self.O + self.A
+
+        tau = float(policy._tau)
+        self.g_actor = self.add_group(policy.actor_optim)
+        self.g_c1 = self.add_group(policy.critic1_optim, tau=tau)
+        self.g_c2 = self.add_group(policy.critic2_optim, tau=tau)
+        self.actor_ps.group_ids = [self.g_actor]
+        self.critic_ps.group_ids = [self.g_c1, self.g_c2]
+        self.auto_alpha = bool(policy._is_auto_alpha)
+        self.alpha_mv = rt.zeros(2)
+        self.g_alpha = -1
+        if self.auto_alpha:
+            self.g_alpha = self.add_group(policy.alpha_optim)
+            self.target_entropy = float(policy._target_entropy)
+            la = policy._log_alpha
+            with torch.no_grad():
+                self.scalars[L.SC_LOG_ALPHA] = float(la.detach().reshape(-1)[0])
+                self.scalars[L.SC_ALPHA] = float(policy._alpha)
+            la.data = self.scalars[L.SC_LOG_ALPHA:L.SC_LOG_ALPHA + 1].view(la.shape)
+        else:
+            self.target_entropy = 0.0
+            with torch.no_grad():
+                self.scalars[L.SC_ALPHA] = float(policy._alpha)
+        self.gamma = float(policy._gamma)
+
+    # ------------------------------------------------------------------ staging
+    def _make_stage(self) -> None:
+        rt, B, O, A = self.rt, self.B, self.O, self.A
+        self.obs2 = rt.zeros(2 * B, O)
+        self.act = rt.zeros(B, A)
+        self.rew = rt.zeros(B, 1)
+        self.term = rt.zeros(B, 1)
+        self._bound_ptrs = None
+
+    def bind_batch(self, batch) -> None:
+        """Use the replay buffer's persistent staging tensors as graph inputs (zero-copy), or copy a foreign
+        batch into the engine's own staging."""
+        obs2 = getattr(batch, "obs2", None)
+        if obs2 is not None and getattr(batch, "stable", False) and obs2.shape[0] == 2 * self.B:
+            ptrs = (obs2.data_ptr(), batch["actions"].data_ptr(), batch["rewards"].data_ptr(),
+                    batch["terminals"].data_ptr())
+            if self._bound_ptrs is None and not self.plans:
+                self.obs2, self.act, self.rew, self.term = obs2, batch["actions"], batch["rewards"], batch["terminals"]
+                self._bound_ptrs = ptrs
+                return
+            if ptrs == self._bound_ptrs:
+                return
+        B = self.B
+        with torch.no_grad():
+            self.obs2[:B].copy_(torch.as_tensor(batch["observations"], device=self.dev, dtype=torch.float32))
+            self.obs2[B:].copy_(torch.as_tensor(batch["next_observations"], device=self.dev, dtype=torch.float32))
+            self.act.copy_(torch.as_tensor(batch["actions"], device=self.dev, dtype=torch.float32))
+            self.rew.copy_(torch.as_tensor(batch["rewards"], device=self.dev, dtype=torch.float32).view(B, 1))
+            self.term.copy_(torch.as_tensor(batch["terminals"], device=self.dev, dtype=torch.float32).view(B, 1))
+
+    def set_noise(self, noise: Optional[Dict[str, torch.Tensor]]) -> None:
+        """Parity mode: the caller supplies every random draw; otherwise Philox fills them."""
+        if noise is None:
+            self.set_noise_enabled(True)
+            return
+        self.set_noise_enabled(False)
+        with torch.no_grad():
+            for k, buf in self.noise_views.items():
+                buf.copy_(torch.as_tensor(noise[k], device=self.dev, dtype=torch.float32).reshape(buf.shape))
+
+    # ------------------------------------------------------------------ shared fragments
+    def _emit_noise(self, plan: Plan, n_normal: int, n_uniform: int, lo: float, hi: float) -> None:
+        args = (self.noise.data_ptr(), n_normal, n_uniform, lo, hi, int(self.seed), self.philox_counter.data_ptr(),
+                self.noise_enable.data_ptr())
+        plan.add("philox", lambda: L.call("orlk_philox_fill", *args, self.rt.cur))
+
+    def _emit_sample(self, plan: Plan, tag: str, head: torch.Tensor, head_row_off: int, rep: int, eps: torch.Tensor,
+                     M: int, X: Mat, logp: torch.Tensor, obs: Mat) -> None:
+        """a ~ pi(.|s) from head rows -> writes [obs | a] rows of the critic input X and logp."""
+        O, A = self.O, self.A
+        args = (head.data_ptr(), 2 * A, head_row_off, rep, eps.data_ptr(), M, A, X.ptr + 4 * O, X.ld, logp.data_ptr(),
+                obs.ptr, obs.ld, O, X.ptr, X.ld)
+        plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
+
+    def _emit_actor_update(self, plan: Plan, clamp01: bool) -> None:
+        """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)"""
+        rt, B, O, A = self.rt, self.B, self.O, self.A
+        ar, cr = self.run_actor, self.run_critic_a
+        obs = Mat.of(self.obs2).rows_(0, B)
+        emit_forward(rt, plan, ar, [obs], "A.actor")
+        Xa = Mat.of(self.Xa)
+        self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
+        emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
+        q, dq = cr.out, cr.dOut      # [2, B, 1]
+        args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
+                int(clamp01), self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(),
+                dq.data_ptr(), B, self.glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+        plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
+        emit_head_dgrad(rt, plan, cr, "A.critic")
+        emit_hidden_dgrad(rt, plan, cr, "A.critic")
+        # dL/da = sum over the two critics of dZ1 . W1[:, O:O+A]
+        probs = [dgrad_problem(self.critic_ps, 0, g, cr.dz(0, g), Mat.of(self.dA[g]), L.EPI_NONE, None, col0=O, ncols=A)
+                 for g in range(2)]
+        plan.add("A.critic.dact", rt.gemm(probs, L.CFG_SMALL))
+        head = ar.out[0]
+        bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA[0].data_ptr(),
+                 self.dA[1].data_ptr(), A, self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
+        plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
+        emit_head_dgrad(rt, plan, ar, "A.actor")
+        emit_hidden_dgrad(rt, plan, ar, "A.actor")
+        emit_wgrad_adam(rt, plan, ar, [obs], self.gb_actor, self.groups_ptr, "A.actor", polyak=False)
+
+    def _alloc_actor_phase(self) -> None:
+        rt, B, A = self.rt, self.B, self.A
+        self.run_actor = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=True)
+        self.run_critic_a = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True)
+        self.Xa = rt.zeros(B, self.O + A)
+        self.logp_a = rt.zeros(B)
+        self.glp = rt.zeros(B)
+        self.dA = rt.zeros(2, B, A)
+
+    def group_mask(self, *gs: int) -> int:
+        m = 0
+        for g in gs:
+            if g >= 0:
+                m |= 1 << g
+        return m
+
+
+class CQLLearner(TwinCriticLearner):
+    def __init__(self, policy, batch_size: int, seed: int = 0):
+        super().__init__(policy, batch_size)
+        rt, B, O, A = self.rt, self.B, self.O, self.A
+        self.seed = seed
+        self.N = int(policy._num_repeat_actions)
+        self.R = B * self.N
+        self.Mc = B + 3 * self.R
+        if policy._max_q_backup:
+            raise L.OrlkError("CQL max_q_backup=True is not implemented by the CUDA engine")
+        self.with_lagrange = bool(policy._with_lagrange)
+        self.g_cql = -1
+        self.cql_mv = rt.zeros(2)
+        if self.with_lagrange:
+            self.g_cql = self.add_group(policy.cql_alpha_optim)
+            cla = policy.cql_log_alpha
+            with torch.no_grad():
+                self.scalars[L.SC_CQL_LOG_ALPHA] = float(cla.detach().reshape(-1)[0])
+            cla.data = self.scalars[L.SC_CQL_LOG_ALPHA:L.SC_CQL_LOG_ALPHA + 1].view(cla.shape)
+        self.act_lo = float(policy.action_space.low[0])
+        self.act_hi = float(policy.action_space.high[0])
+        self.push_groups()
+        self._make_stage()
+        # noise block: normals first (eps_actor, eps_next, eps_pi, eps_pi_next), then uniforms (rand_act)
+        R = self.R
+        self.n_normal, self.n_uniform = (2 * B + 2 * R) * A, R * A
+        self.noise = rt.zeros(self.n_normal + self.n_uniform)
+        o = 0
+        views = {}
+        for name, rows in (("eps_actor", B), ("eps_next", B), ("eps_pi", R), ("eps_pi_next", R), ("rand_act", R)):
+            views[name] = self.noise[o:o + rows * A].view(rows, A)
+            o += rows * A
+        self.noise_views = views
+        self.eps_actor = views["eps_actor"]
+        self._built = False
+
+    def _build(self) -> None:
+        rt, B, O, A, R, Mc = self.rt, self.B, self.O, self.A, self.R, self.Mc
+        self._alloc_actor_phase()
+        self.run_actor_b = MlpRun(rt, self.actor_ps, 2 * B, self.nh_a, need_grad=False)
+        self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        self.run_critic = MlpRun(rt, self.critic_ps, Mc, self.nh_c, need_grad=True)
+        self.Xt = rt.zeros(B, O + A)
+        self.Xc = rt.zeros(Mc, O + A)
+        self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(B), rt.zeros(R), rt.zeros(R)
+        self.gb_actor = make_gradbuf(rt, self.actor_ps, [(self.nh_a + 1, B)])
+        self.gb_critic = make_gradbuf(rt, self.critic_ps, [(self.nh_c + 1, Mc)])
+
+        plan = Plan(rt, "cql")
+        self._emit_noise(plan, self.n_normal, self.n_uniform, self.act_lo, self.act_hi)
+        self._emit_actor_update(plan, clamp01=False)
+
+        # ---- critic phase with the UPDATED actor (cql.py:108-192)
+        obs2 = Mat.of(self.obs2)
+        obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
+        ab = self.run_actor_b
+        emit_forward(rt, plan, ab, [obs2], "C.actor")
+        head = ab.out[0]
+        Xt, Xc = Mat.of(self.Xt), Mat.of(self.Xc)
+        v = self.noise_views
+        self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
+        self._emit_sample(plan, "C.sample_pi", head, 0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, obs)
+        self._emit_sample(plan, "C.sample_pi_next", head, B, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
+                          self.lp_pn, obs)
+        plan.add("C.concat", rt.concat([(Xc.rows_(0, B), obs, 1, Mat.of(self.act)),
+                                        (Xc.rows_(B + 2 * R, Mc), obs, self.N, Mat.of(v["rand_act"]))]))
+        emit_forward(rt, plan, self.run_target, [Xt, Xt], "C.target")
+        cr = self.run_critic
+        emit_forward(rt, plan, cr, [Xc, Xc], "C.critic")
+        pol = self.policy
+        largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), B, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
+                 self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, R, A, self.gamma,
+                 float(pol._cql_weight), float(pol._temperature), int(bool(pol._deterministic_backup)),
+                 int(self.with_lagrange), float(pol._lagrange_threshold), self.scalars.data_ptr(), self.groups_ptr,
+                 max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1)
+        plan.add("C.loss", lambda: L.call("orlk_cql_critic_loss", *largs, rt.cur))
+        emit_head_dgrad(rt, plan, cr, "C.critic")
+        emit_hidden_dgrad(rt, plan, cr, "C.critic")
+        emit_wgrad_adam(rt, plan, cr, [Xc, Xc], self.gb_critic, self.groups_ptr, "C.critic", polyak=True)
+        self.finish_ops(plan, self.group_mask(self.g_actor, self.g_c1, self.g_c2, self.g_alpha, self.g_cql))
+        self.plans["step"] = plan
+        self._built = True
+
+    def step(self, batch, noise=None) -> Dict[str, float]:
+        self.bind_batch(batch)
+        if not self._built:
+            self._build()
+        self.set_noise(noise)
+        self.sync_lr()
+        out = self.run("step")
+        res = {"loss/actor": float(out[LS_ACTOR]), "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
+        if self.auto_alpha:
+            res["loss/alpha"] = float(out[LS_ALPHA_LOSS])
+            res["alpha"] = float(out[LS_ALPHA])
+        if self.with_lagrange:
+            res["loss/cql_alpha"] = float(out[LS_CQL_ALPHA_LOSS])
+            res["cql_alpha"] = float(out[LS_CQL_ALPHA])
+        return res

@@ -1,0 +1,78 @@
+"""SACPolicy facade (reference: policy/model_free/sac.py:10-140).
+
+Holds the same attributes as the reference class (the run scripts and the trainers only touch those) and
+delegates ``learn`` to the CUDA engine (engine/sac_family.py).  Used directly by MOPO.
+"""
+from copy import deepcopy
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .base_policy import BasePolicy
+
+
+class SACPolicy(BasePolicy):
+    _engine_cls = None      # set below (import cycle-free)
+
+    def __init__(self, actor: nn.Module, critic1: nn.Module, critic2: nn.Module,
+                 actor_optim: torch.optim.Optimizer, critic1_optim: torch.optim.Optimizer,
+                 critic2_optim: torch.optim.Optimizer, tau: float = 0.005, gamma: float = 0.99,
+                 alpha: Union[float, Tuple[float, torch.Tensor, torch.optim.Optimizer]] = 0.2) -> None:
+        super().__init__()
+        self.actor = actor
+        self.critic1, self.critic1_old = critic1, deepcopy(critic1)
+        self.critic2, self.critic2_old = critic2, deepcopy(critic2)
+        self.critic1_old.eval()
+        self.critic2_old.eval()
+        self.actor_optim, self.critic1_optim, self.critic2_optim = actor_optim, critic1_optim, critic2_optim
+        self._tau, self._gamma = tau, gamma
+        self._is_auto_alpha = isinstance(alpha, tuple)
+        if self._is_auto_alpha:
+            self._target_entropy, self._log_alpha, self.alpha_optim = alpha
+            self._alpha = self._log_alpha.detach().exp()
+        else:
+            self._alpha = alpha
+        self._engine = None
+
+    def train(self) -> None:
+        for m in (self.actor, self.critic1, self.critic2):
+            m.train()
+
+    def eval(self) -> None:
+        for m in (self.actor, self.critic1, self.critic2):
+            m.eval()
+
+    # ---- inference (evaluation / rollouts)
+    def actforward(self, obs: torch.Tensor, deterministic: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        dist = self.actor(obs)
+        squashed, raw = dist.mode() if deterministic else dist.rsample()
+        return squashed, dist.log_prob(squashed, raw)
+
+    def select_action(self, obs: np.ndarray, deterministic: bool = False) -> np.ndarray:
+        with torch.no_grad():
+            action, _ = self.actforward(obs, deterministic)
+        return action.cpu().numpy()
+
+    # ---- the gradient step
+    def _make_engine(self, batch_size: int):
+        from ..engine.sac_family import SACLearner
+        return SACLearner(self, batch_size)
+
+    def engine(self, batch_size: int):
+        if self._engine is None:
+            self._engine = self._make_engine(batch_size)
+        elif self._engine.B != batch_size:
+            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
+        return self._engine
+
+    def _after_step(self, out: Dict[str, float]) -> None:
+        if self._is_auto_alpha and "alpha" in out:
+            self._alpha = torch.tensor([out["alpha"]], device=self.actor.device)
+
+    def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
+        eng = self.engine(int(batch["observations"].shape[0]))
+        out = eng.step(batch, noise)
+        self._after_step(out)
+        return out

@@ -1,0 +1,115 @@
+"""Helpers for the GPU parity tests: build facade policies from golden metadata and run golden steps."""
+from typing import Dict
+
+import numpy as np
+import torch
+
+from tests.helpers import Golden, initial_state, assert_stats_close, rel_err
+
+
+class Box:
+    def __init__(self, low, high, shape):
+        self.low = np.full(shape, low, dtype=np.float32)
+        self.high = np.full(shape, high, dtype=np.float32)
+        self.shape = shape
+
+
+def build_policy(meta, device="cuda:0"):
+    from offlinerlkit_b200.nets import MLP
+    from offlinerlkit_b200.modules import ActorProb, Actor, Critic, EnsembleCritic, TanhDiagGaussian, DiagGaussian
+    import offlinerlkit_b200.policy as P
+    algo, O, A, hid, hy = meta["algo"], meta["O"], meta["A"], meta["hidden"], meta.get("hyper", {})
+    adam = lambda m, lr: torch.optim.Adam(m.parameters(), lr=lr)
+
+    def alpha_tuple():
+        la = torch.zeros(1, requires_grad=True, device=device)
+        return (meta["target_entropy"], la, torch.optim.Adam([la], lr=meta["alpha_lr"]))
+
+    def tanh_actor():
+        bb = MLP(O, hid)
+        return ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), device)
+
+    if algo in ("cql", "sac"):
+        actor, c1, c2 = tanh_actor(), Critic(MLP(O + A, hid), device), Critic(MLP(O + A, hid), device)
+        opt = (adam(actor, hy["actor_lr"]), adam(c1, hy["critic_lr"]), adam(c2, hy["critic_lr"]))
+        if algo == "sac":
+            return P.SACPolicy(actor, c1, c2, *opt, tau=hy["tau"], gamma=hy["gamma"], alpha=alpha_tuple())
+        return P.CQLPolicy(actor, c1, c2, *opt, action_space=Box(-1, 1, (A,)), tau=hy["tau"], gamma=hy["gamma"],
+                           alpha=alpha_tuple(), cql_weight=hy["cql_weight"], temperature=hy["temperature"],
+                           max_q_backup=hy["max_q_backup"], deterministic_backup=hy["deterministic_backup"],
+                           with_lagrange=hy["with_lagrange"], lagrange_threshold=hy["lagrange_threshold"],
+                           cql_alpha_lr=hy["cql_alpha_lr"], num_repeart_actions=hy["num_repeat_actions"])
+    if algo == "edac":
+        actor = tanh_actor()
+        critics = EnsembleCritic(O, A, hid, num_ensemble=meta["E"], device=device)
+        return P.EDACPolicy(actor, critics, adam(actor, hy["actor_lr"]), adam(critics, hy["critic_lr"]), tau=hy["tau"],
+                            gamma=hy["gamma"], alpha=alpha_tuple(), max_q_backup=False,
+                            deterministic_backup=hy["deterministic_backup"], eta=hy["eta"])
+    if algo == "iql":
+        bb = MLP(O, hid, dropout_rate=None)
+        actor = ActorProb(bb, DiagGaussian(bb.output_dim, A, unbounded=False, conditioned_sigma=False), device)
+        q1, q2, v = Critic(MLP(O + A, hid), device), Critic(MLP(O + A, hid), device), Critic(MLP(O, hid), device)
+        return P.IQLPolicy(actor, q1, q2, v, adam(actor, hy["actor_lr"]), adam(q1, hy["critic_q_lr"]),
+                           adam(q2, hy["critic_q_lr"]), adam(v, hy["critic_v_lr"]), action_space=Box(-1, 1, (A,)),
+                           tau=hy["tau"], gamma=hy["gamma"], expectile=hy["expectile"], temperature=hy["temperature"])
+    if algo == "td3bc":
+        actor = Actor(MLP(O, hid), A, device=device)
+        c1, c2 = Critic(MLP(O + A, hid), device), Critic(MLP(O + A, hid), device)
+        return P.TD3BCPolicy(actor, c1, c2, adam(actor, hy["actor_lr"]), adam(c1, hy["critic_lr"]),
+                             adam(c2, hy["critic_lr"]), tau=hy["tau"], gamma=hy["gamma"], max_action=hy["max_action"],
+                             policy_noise=hy["policy_noise"], noise_clip=hy["noise_clip"],
+                             update_actor_freq=hy["update_actor_freq"], alpha=hy["alpha"])
+    raise KeyError(algo)
+
+
+def load_state(policy, state: Dict[str, torch.Tensor]) -> None:
+    missing, unexpected = policy.load_state_dict(state, strict=False)
+    assert not unexpected, unexpected
+    assert all("saved_" in k for k in missing), missing
+
+
+def make_buffer(g: Golden, device="cuda:0"):
+    from offlinerlkit_b200.buffer import ReplayBuffer
+    m = g.meta
+    data = g.dataset()
+    buf = ReplayBuffer(m["n_data"], (m["O"],), np.float32, m["A"], np.float32, device=device)
+    buf.load_dataset(data)
+    return buf, data
+
+
+def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0"):
+    """Engine vs golden (= the real reference): index draw + gather bit-exact, then losses and parameters."""
+    m = g.meta
+    policy = build_policy(m, device)
+    load_state(policy, initial_state(m))
+    policy.train()
+    buf, data = make_buffer(g, device)
+    np.random.seed(m["np_seed"])
+    n_steps = n_steps or m["n_steps"]
+    lr_atol = 2.5 * max(v for k, v in m["hyper"].items() if k.endswith("_lr"))
+    for t in range(n_steps):
+        batch = buf.sample(m["B"])
+        torch.cuda.synchronize()
+        assert np.array_equal(batch.indices.cpu().numpy(), g["idx"][t]), "index stream differs from the reference"
+        ref_b = g.batch(t, data)
+        for k, v in ref_b.items():
+            assert torch.equal(batch[k].cpu().reshape(v.shape), v), f"gather not bit-exact: {k}"
+        policy.engine(m["B"]).use_graph = use_graph
+        noise = g.noise(t) if any(k.startswith(f"noise{t}|") for k in g.z.files) else None
+        out = policy.learn(batch, noise=noise) if noise is not None else policy.learn(batch)
+        ref = g.losses(t)
+        if verbose:
+            print(f"step {t}: engine {out}\n        golden {ref}", flush=True)
+        assert out.keys() == ref.keys(), (out.keys(), ref.keys())
+        for k in ref:
+            assert abs(out[k] - ref[k]) <= tol * max(1.0, abs(ref[k])), (t, k, out[k], ref[k])
+        sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
+        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol)
+    post = g.group("post")
+    if post and n_steps == m["n_steps"]:
+        sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
+        for k, v in post.items():
+            if v.dtype.kind == "f" and "saved_" not in k:
+                err = np.abs(sd[k].numpy() - v).max()
+                assert err <= tol * np.abs(v).max() + lr_atol, (k, err)
+    return policy

@@ -1,0 +1,401 @@
+"""GPU: every kernel entry point of the C ABI against a plain PyTorch fp32/fp64 expression of the same op."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from offlinerlkit_b200.engine.core import get_runtime
+    return get_runtime(DEV)
+
+
+def _close(got, ref, rtol=1e-5, atol=1e-5, msg=""):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    err = (got - ref).abs().max().item() if got.numel() else 0.0
+    scale = ref.abs().max().item() if ref.numel() else 1.0
+    assert err <= atol + rtol * scale, f"{msg}: max err {err:.3e} (scale {scale:.3e})"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, epi, splits, with_bias, sums, seed):
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import GP
+    gen = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=gen)
+    B = torch.randn(K, N, generator=gen)
+    bias = torch.randn(N, generator=gen) if with_bias else None
+    aux = torch.randn(M, N, generator=gen)
+    Ad = (A if a_layout == 0 else A.t().contiguous()).to(DEV)
+    Bd = (B if b_layout == 0 else B.t().contiguous()).to(DEV)
+    s_eff = rt.effective_splits(K, splits, cfg)
+    Cd = torch.full((s_eff, M, N), float("nan"), device=DEV)
+    C2 = torch.zeros(M, N, device=DEV)
+    W = max(M, N)
+    rs = torch.full((s_eff, W), float("nan"), device=DEV)
+    cs = torch.full((s_eff, W), float("nan"), device=DEV)
+    p = GP(A=Ad.data_ptr(), lda=Ad.stride(0), a_layout=a_layout, B=Bd.data_ptr(), ldb=Bd.stride(0), b_layout=b_layout,
+           C=Cd.data_ptr(), ldc=N, M=M, N=N, K=K, epi=epi, bias=bias.to(DEV).data_ptr() if with_bias else 0,
+           aux=0, ldaux=N, C2=C2.data_ptr() if epi == L.EPI_SWISH else 0, k_splits=splits, c_split_stride=M * N,
+           sum_split_stride=0)
+    keep = [bias.to(DEV) if with_bias else None]
+    if with_bias:
+        p.bias = keep[0].data_ptr()
+    auxd = aux.to(DEV)
+    if epi in (L.EPI_RELU_MASK, L.EPI_DSWISH):
+        p.aux = auxd.data_ptr()
+    if sums:
+        p.rowsum, p.colsum, p.sum_split_stride = rs.data_ptr(), cs.data_ptr(), W
+    rt.gemm([p], cfg)()
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double()
+    if with_bias:
+        ref = ref + bias.double()
+    got = Cd.sum(0) if epi == L.EPI_NONE else Cd[0]
+    if epi == L.EPI_RELU:
+        ref = ref.clamp(min=0)
+    elif epi == L.EPI_RELU_MASK:
+        ref = ref * (aux > 0)
+    elif epi == L.EPI_SWISH:
+        _close(C2, ref, msg="swish z")
+        ref = ref * torch.sigmoid(ref)
+    elif epi == L.EPI_DSWISH:
+        s = torch.sigmoid(aux.double())
+        ref = ref * (s * (1 + aux.double() * (1 - s)))
+    tag = f"cfg{cfg} {M}x{N}x{K} a{a_layout} b{b_layout} epi{epi} s{splits}"
+    assert not torch.isnan(got).any(), tag + ": NaN = unwritten output"
+    _close(got, ref, rtol=2e-6 * math.sqrt(K) + 1e-6, atol=1e-5, msg=tag)
+    if sums:
+        _close(rs[:, :M].sum(0), A.double().sum(1), rtol=1e-5, atol=1e-4, msg=tag + " rowsum")
+        _close(cs[:, :N].sum(0), B.double().sum(0), rtol=1e-5, atol=1e-4, msg=tag + " colsum")
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_gemm_layouts_and_ragged_shapes(rt, cfg):
+    shapes = [(1, 1, 1), (37, 23, 23), (300, 256, 250), (128, 128, 64), (129, 6, 256), (256, 256, 256), (64, 1, 515)]
+    seed = 0
+    for (M, N, K) in shapes:
+        for a_layout in (0, 1):
+            for b_layout in (0, 1):
+                seed += 1
+                _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, 0, 1, with_bias=bool(seed % 2), sums=False, seed=seed)
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_gemm_epilogues(rt, cfg):
+    for epi in (1, 2, 3, 4):
+        _gemm_case(rt, cfg, 200, 136, 96, 0, 1, epi, 1, with_bias=epi in (1, 3), sums=False, seed=100 + epi)
+        _gemm_case(rt, cfg, 256, 256, 256, 0, 0, epi, 1, with_bias=epi in (1, 3), sums=False, seed=200 + epi)
+
+
+@pytest.mark.parametrize("cfg", [0, 2])
+def test_gemm_split_k_and_sums(rt, cfg):
+    # wgrad shapes: C[out,in] = dY^T X reduced over rows, with bias row/col sums
+    for (M, N, K, splits) in [(256, 256, 7936, 18), (256, 23, 7936, 18), (1, 256, 7936, 9), (12, 256, 256, 4),
+                              (256, 17, 256, 3), (100, 50, 1000, 7)]:
+        _gemm_case(rt, cfg, M, N, K, 1, 0, 0, splits, with_bias=False, sums=True, seed=M + N + K)
+
+
+def test_gemm_grouped_many_problems(rt):
+    from offlinerlkit_b200.engine.core import GP
+    gen = torch.Generator().manual_seed(5)
+    probs, refs, outs, keep = [], [], [], []
+    for i, (M, N, K) in enumerate([(256, 256, 23), (40, 256, 256), (256, 1, 256), (77, 33, 129)] * 3):
+        A, B = torch.randn(M, K, generator=gen).to(DEV), torch.randn(N, K, generator=gen).to(DEV)
+        Cd = torch.zeros(M, N, device=DEV)
+        probs.append(GP(A=A.data_ptr(), lda=K, a_layout=0, B=B.data_ptr(), ldb=K, b_layout=1, C=Cd.data_ptr(), ldc=N,
+                        M=M, N=N, K=K))
+        refs.append(A.double().cpu() @ B.double().cpu().t())
+        outs.append(Cd)
+        keep += [A, B]
+    for cfg in (0, 1, 2):
+        for o in outs:
+            o.zero_()
+        rt.gemm(probs, cfg)()
+        torch.cuda.synchronize()
+        for i, (o, r) in enumerate(zip(outs, refs)):
+            _close(o, r, rtol=1e-5, atol=1e-4, msg=f"grouped cfg{cfg} problem {i}")
+
+
+# ------------------------------------------------------------------------------------------------ narrow layers
+def test_skinny_fwd_and_dgrad(rt):
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(1)
+    for (G, M, K, NS) in [(1, 256, 256, 12), (2, 300, 256, 1), (3, 7, 40, 16), (2, 2560, 200, 6)]:
+        X = torch.randn(G, M, K, generator=gen)
+        W = torch.randn(G, NS, K, generator=gen)
+        b = torch.randn(G, NS, generator=gen)
+        Xd, Wd, bd = X.to(DEV), W.to(DEV), b.to(DEV)
+        Y = torch.zeros(G, M, NS, device=DEV)
+        L.call("orlk_skinny_fwd", Xd.data_ptr(), K, M * K, Wd.data_ptr(), K, NS * K, bd.data_ptr(), NS, Y.data_ptr(), NS,
+               M * NS, M, K, NS, G, rt.cur)
+        ref = torch.einsum("gmk,gnk->gmn", X.double(), W.double()) + b.double()[:, None, :]
+        _close(Y, ref, msg=f"skinny fwd {G,M,K,NS}")
+        dY = torch.randn(G, M, NS, generator=gen)
+        mask = torch.randn(G, M, K, generator=gen)
+        dX = torch.zeros(G, M, K, device=DEV)
+        dYd, md = dY.to(DEV), mask.to(DEV)
+        L.call("orlk_skinny_dgrad", dYd.data_ptr(), NS, M * NS, Wd.data_ptr(), K, NS * K, md.data_ptr(), K, M * K,
+               dX.data_ptr(), K, M * K, M, K, NS, G, rt.cur)
+        ref = torch.einsum("gmn,gnk->gmk", dY.double(), W.double()) * (mask > 0)
+        _close(dX, ref, msg=f"skinny dgrad {G,M,K,NS}")
+
+
+def test_concat_rows(rt):
+    from offlinerlkit_b200.engine.core import Mat
+    obs, act = torch.randn(16, 5, device=DEV), torch.randn(64, 3, device=DEV)
+    act0 = torch.randn(16, 3, device=DEV)
+    X = torch.zeros(80, 8, device=DEV)
+    Xm = Mat.of(X)
+    rt.concat([(Xm.rows_(0, 16), Mat.of(obs), 1, Mat.of(act0)), (Xm.rows_(16, 80), Mat.of(obs), 4, Mat.of(act))])()
+    torch.cuda.synchronize()
+    ref = torch.cat([torch.cat([obs, act0], 1), torch.cat([obs.repeat_interleave(4, 0), act], 1)], 0)
+    assert torch.equal(X, ref)
+
+
+# ------------------------------------------------------------------------------------------------ policy head
+def _head_ref(head, eps, A):
+    mu, raw = head[:, :A], head[:, A:]
+    sigma = raw.clamp(-5, 2).exp()
+    u = mu + sigma * eps if eps is not None else mu
+    a = torch.tanh(u)
+    lp = (-((u - mu) ** 2) / (2 * sigma ** 2) - sigma.log() - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
+    lp = lp - torch.log((1 - a.pow(2)) + 1e-6).sum(-1, keepdim=True)
+    return a, lp
+
+
+def test_tanh_gauss_sample_and_bwd(rt):
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(2)
+    A, O, B, rep = 6, 17, 32, 4
+    M = B * rep
+    head = torch.randn(2 * B, 2 * A, generator=gen) * 2.5      # exercises the clamp on both sides
+    eps = torch.randn(M, A, generator=gen)
+    obs = torch.randn(B, O, generator=gen)
+    hd, ed, od = head.to(DEV), eps.to(DEV), obs.to(DEV)
+    X = torch.zeros(M, O + A, device=DEV)
+    lp = torch.zeros(M, device=DEV)
+    L.call("orlk_tanh_gauss_sample", hd.data_ptr(), 2 * A, B, rep, ed.data_ptr(), M, A, X.data_ptr() + 4 * O, O + A,
+           lp.data_ptr(), od.data_ptr(), O, O, X.data_ptr(), O + A, rt.cur)
+    hrep = head[B:].repeat_interleave(rep, 0).double()
+    a_ref, lp_ref = _head_ref(hrep, eps.double(), A)
+    _close(X[:, O:], a_ref, rtol=1e-5, atol=1e-6, msg="sampled action")
+    _close(lp, lp_ref[:, 0], rtol=1e-5, atol=1e-4, msg="log-prob")
+    assert torch.equal(X[:, :O].cpu(), obs.repeat_interleave(rep, 0))
+    # mode (eps == NULL)
+    L.call("orlk_tanh_gauss_sample", hd.data_ptr(), 2 * A, B, rep, None, M, A, X.data_ptr() + 4 * O, O + A,
+           lp.data_ptr(), None, 0, 0, None, 0, rt.cur)
+    a_ref, lp_ref = _head_ref(hrep, None, A)
+    _close(X[:, O:], a_ref, msg="mode action")
+    _close(lp, lp_ref[:, 0], rtol=1e-5, atol=1e-4, msg="mode log-prob")
+    # backward against autograd (rep = 1)
+    head1 = (torch.randn(B, 2 * A, generator=gen) * 2.5).double().requires_grad_(True)
+    eps1 = torch.randn(B, A, generator=gen)
+    a1, lp1 = _head_ref(head1, eps1.double(), A)
+    dA0, dA1, glp = torch.randn(B, A, generator=gen), torch.randn(B, A, generator=gen), torch.randn(B, generator=gen)
+    loss = (a1 * (dA0 + dA1).double()).sum() + (lp1[:, 0] * glp.double()).sum()
+    loss.backward()
+    h1d, e1d = head1.detach().float().to(DEV), eps1.to(DEV)
+    act = torch.zeros(B, A, device=DEV)
+    lpd = torch.zeros(B, device=DEV)
+    L.call("orlk_tanh_gauss_sample", h1d.data_ptr(), 2 * A, 0, 1, e1d.data_ptr(), B, A, act.data_ptr(), A, lpd.data_ptr(),
+           None, 0, 0, None, 0, rt.cur)
+    dh = torch.zeros(B, 2 * A, device=DEV)
+    d0, d1, gl = dA0.to(DEV), dA1.to(DEV), glp.to(DEV)
+    L.call("orlk_tanh_gauss_bwd", h1d.data_ptr(), 2 * A, e1d.data_ptr(), act.data_ptr(), A, d0.data_ptr(), d1.data_ptr(),
+           A, gl.data_ptr(), B, A, dh.data_ptr(), 2 * A, rt.cur)
+    _close(dh, head1.grad, rtol=2e-4, atol=2e-4, msg="head backward")
+
+
+def test_philox_fill_statistics(rt):
+    from offlinerlkit_b200 import _lib as L
+    n_n, n_u = 400_003, 100_001
+    out = torch.zeros(n_n + n_u, device=DEV)
+    ctr = torch.zeros(1, dtype=torch.int64, device=DEV)
+    en = torch.ones(1, dtype=torch.int32, device=DEV)
+    L.call("orlk_philox_fill", out.data_ptr(), n_n, n_u, -1.0, 1.0, 1234, ctr.data_ptr(), en.data_ptr(), rt.cur)
+    nrm, uni = out[:n_n].double().cpu(), out[n_n:].double().cpu()
+    assert abs(nrm.mean()) < 0.01 and abs(nrm.std() - 1) < 0.01
+    assert abs((nrm ** 4).mean() - 3) < 0.1                      # kurtosis of a Gaussian
+    assert uni.min() >= -1 and uni.max() < 1 and abs(uni.mean()) < 0.01 and abs(uni.var() - 1 / 3) < 0.01
+    first = out.clone()
+    L.call("orlk_philox_fill", out.data_ptr(), n_n, n_u, -1.0, 1.0, 1234, ctr.data_ptr(), en.data_ptr(), rt.cur)
+    assert torch.equal(first, out)                               # same counter -> same stream (reproducible)
+    ctr += 1
+    L.call("orlk_philox_fill", out.data_ptr(), n_n, n_u, -1.0, 1.0, 1234, ctr.data_ptr(), en.data_ptr(), rt.cur)
+    assert not torch.equal(first, out)
+    en.zero_()
+    out.fill_(7.0)
+    L.call("orlk_philox_fill", out.data_ptr(), n_n, n_u, -1.0, 1.0, 1234, ctr.data_ptr(), en.data_ptr(), rt.cur)
+    assert (out == 7.0).all()                                    # disabled: injected noise is left untouched
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def test_adam_polyak_matches_torch(rt):
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import AdamT
+    gen = torch.Generator().manual_seed(3)
+    n, splits = 5000, 3
+    p0 = torch.randn(n, generator=gen)
+    tgt0 = torch.randn(n, generator=gen)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=3e-4)
+    pd, md, vd, td = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), tgt0.to(DEV)
+    groups = (L.AdamGroup * 2)()
+    groups[1].lr, groups[1].beta1, groups[1].beta2, groups[1].eps, groups[1].tau, groups[1].step = 3e-4, 0.9, 0.999, 1e-8, 0.005, 0
+    gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
+    gbuf = torch.zeros(splits, n, device=DEV)
+    tref = tgt0.clone()
+    op = rt.adam([AdamT(p=pd.data_ptr(), n=n, group=1, m=md.data_ptr(), v=vd.data_ptr(), tgt=td.data_ptr(),
+                        grad=gbuf.data_ptr(), g_splits=splits, g_split_stride=n, flags=L.OPT_ADAM | L.OPT_POLYAK)],
+                 gd.data_ptr())
+    for it in range(5):
+        parts = torch.randn(splits, n, generator=gen) * (10.0 ** (it - 3))
+        gbuf.copy_(parts)
+        pt.grad = parts.sum(0)
+        opt.step()
+        tref = tref * (1 - 0.005) + pt.detach() * 0.005
+        op()
+        L.call("orlk_step_end", gd.data_ptr(), 0b10, None, rt.cur)
+        torch.cuda.synchronize()
+        _close(pd, pt.detach(), rtol=1e-6, atol=2e-7, msg=f"adam param it{it}")
+        _close(td, tref, rtol=1e-6, atol=2e-7, msg=f"polyak it{it}")
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_sac_actor_loss_vs_autograd(rt):
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(4)
+    for (E, B, clamp) in [(2, 256, 0), (2, 16, 1), (10, 256, 1)]:
+        q = torch.randn(E, B, generator=gen)
+        q[0, :3] = q[1, :3]                                     # ties
+        logp = torch.randn(B, generator=gen)
+        la0, H = 0.3, -6.0
+        qd = q.clone().double().requires_grad_(True)
+        lpd = logp.clone().double().requires_grad_(True)
+        alpha = math.exp(la0)
+        mn = torch.min(qd[0], qd[1]) if E == 2 else torch.min(qd, 0)[0]
+        loss = (alpha * lpd - mn).mean()
+        loss.backward()
+        la = torch.tensor([la0], requires_grad=True)
+        aopt = torch.optim.Adam([la], lr=1e-2)
+        aloss = -(la * (logp + H)).mean()
+        aloss.backward()
+        aopt.step()
+        new_alpha = la.detach().exp().clamp(0, 1) if clamp else la.detach().exp()
+        sc = torch.zeros(8, device=DEV)
+        sc[0], sc[1] = la0, alpha
+        groups = (L.AdamGroup * 1)()
+        groups[0].lr, groups[0].beta1, groups[0].beta2, groups[0].eps = 1e-2, 0.9, 0.999, 1e-8
+        gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
+        mv = torch.zeros(2, device=DEV)
+        qg, lg = q.to(DEV), logp.to(DEV)
+        dq, glp, out = torch.zeros(E, B, device=DEV), torch.zeros(B, device=DEV), torch.zeros(4, device=DEV)
+        L.call("orlk_sac_actor_loss", qg.data_ptr(), B, E, lg.data_ptr(), B, sc.data_ptr(), 1, clamp, H, gd.data_ptr(), 0,
+               mv.data_ptr(), dq.data_ptr(), B, glp.data_ptr(), out.data_ptr(), rt.cur)
+        torch.cuda.synchronize()
+        _close(out[0], loss, rtol=1e-5, atol=1e-5, msg="actor loss")
+        _close(out[1], aloss, rtol=1e-5, atol=1e-5, msg="alpha loss")
+        _close(out[2], new_alpha[0], rtol=1e-5, msg="alpha")
+        _close(sc[1], new_alpha[0], rtol=1e-5, msg="alpha scalar")
+        _close(dq, qd.grad, rtol=1e-6, atol=1e-9, msg="dq")
+        _close(glp, lpd.grad, rtol=1e-6, atol=1e-9, msg="dlogp")
+
+
+def test_cql_critic_loss_vs_autograd(rt):
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(6)
+    for (B, N, A, det, lag) in [(16, 4, 3, 1, 0), (256, 10, 6, 0, 1), (256, 10, 6, 1, 1)]:
+        R = B * N
+        Mc = B + 3 * R
+        q = torch.randn(2, Mc, generator=gen) * 3
+        tq = torch.randn(2, B, generator=gen)
+        lpn, lpp, lpq = torch.randn(B, generator=gen), torch.randn(R, generator=gen), torch.randn(R, generator=gen)
+        rew, term = torch.randn(B, generator=gen), (torch.rand(B, generator=gen) < 0.1).float()
+        gamma, w, T, thr, alpha, cla0 = 0.99, 5.0, 1.3, 10.0, 0.7, 0.2
+        qd = q.clone().double().requires_grad_(True)
+        nq = torch.min(tq[0], tq[1]).double()
+        if not det:
+            nq = nq - alpha * lpn.double()
+        y = rew.double() + gamma * (1 - term.double()) * nq
+        cla = torch.tensor([cla0], dtype=torch.double, requires_grad=True)
+        losses = []
+        for c in range(2):
+            td = ((qd[c, :B] - y) ** 2).mean()
+            cat = torch.stack([qd[c, B:B + R] - lpp.double(), qd[c, B + R:B + 2 * R] - lpq.double(),
+                               qd[c, B + 2 * R:] - math.log(0.5 ** A)], 1)
+            cons = torch.logsumexp(cat / T, dim=1).mean() * w * T - qd[c, :B].mean() * w
+            if lag:
+                cons = torch.clamp(cla.exp(), 0, 1e6) * (cons - thr)
+            losses.append((td, cons))
+        cql_alpha_loss = -(losses[0][1] + losses[1][1]) * 0.5 if lag else None
+        if lag:
+            g_cla, = torch.autograd.grad(cql_alpha_loss, cla, retain_graph=True)
+        total = [td + cons for td, cons in losses]
+        (total[0] + total[1]).backward()
+        sc = torch.zeros(8, device=DEV)
+        sc[1], sc[2] = alpha, cla0
+        groups = (L.AdamGroup * 1)()
+        groups[0].lr, groups[0].beta1, groups[0].beta2, groups[0].eps = 3e-4, 0.9, 0.999, 1e-8
+        gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
+        mv = torch.zeros(2, device=DEV)
+        dev = lambda t: t.to(DEV)
+        qg, tqg, a1, a2, a3, rg, tg = map(dev, (q, tq, lpn, lpp, lpq, rew, term))
+        dq, out = torch.zeros(2, Mc, device=DEV), torch.zeros(4, device=DEV)
+        L.call("orlk_cql_critic_loss", qg.data_ptr(), Mc, tqg.data_ptr(), B, a1.data_ptr(), a2.data_ptr(), a3.data_ptr(),
+               rg.data_ptr(), tg.data_ptr(), B, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
+               mv.data_ptr(), dq.data_ptr(), Mc, out.data_ptr(), rt.cur)
+        torch.cuda.synchronize()
+        _close(out[0], total[0], rtol=2e-5, atol=1e-4, msg="critic1 loss")
+        _close(out[1], total[1], rtol=2e-5, atol=1e-4, msg="critic2 loss")
+        _close(dq, qd.grad, rtol=2e-5, atol=1e-8, msg="dq")
+        if lag:
+            _close(out[2], cql_alpha_loss, rtol=2e-5, atol=1e-4, msg="cql alpha loss")
+            _close(out[3], cla.detach().exp()[0], rtol=1e-5, msg="cql alpha")
+            # first Adam step moves log-alpha by -lr*sign(g)
+            _close(sc[2], torch.tensor(cla0 - 3e-4 * math.copysign(1.0, g_cla.item())), rtol=1e-4, msg="cql log alpha")
+
+
+# ------------------------------------------------------------------------------------------------ replay
+def test_replay_gather_bit_exact_and_ring(rt):
+    from offlinerlkit_b200.buffer import ReplayBuffer
+    from offlinerlkit_b200.synthetic import make_dataset
+    for (O, A, n) in [(11, 3, 5000), (17, 6, 3001)]:
+        d = make_dataset(n, O, A, seed=1)
+        buf = ReplayBuffer(n, (O,), np.float32, A, np.float32, device=DEV)
+        buf.load_dataset(d)
+        for B in (1, 256, 1000):
+            np.random.seed(B)
+            batch = buf.sample(B)
+            np.random.seed(B)
+            idx = np.random.randint(0, n, size=B)
+            torch.cuda.synchronize()
+            assert np.array_equal(batch.indices.cpu().numpy(), idx)
+            assert np.array_equal(batch["observations"].cpu().numpy(), d["observations"][idx])
+            assert np.array_equal(batch["next_observations"].cpu().numpy(), d["next_observations"][idx])
+            assert np.array_equal(batch["actions"].cpu().numpy(), d["actions"][idx])
+            assert np.array_equal(batch["rewards"].cpu().numpy(), d["rewards"][idx].reshape(-1, 1))
+            assert np.array_equal(batch["terminals"].cpu().numpy(), d["terminals"][idx].reshape(-1, 1))
+    # ring writes (add_batch wrap-around) are mirrored before the next sample
+    buf = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)
+    rng = np.random.default_rng(0)
+    for k in range(5):
+        m = 37
+        buf.add_batch(rng.standard_normal((m, 4), dtype=np.float32), rng.standard_normal((m, 4), dtype=np.float32),
+                      rng.standard_normal((m, 2), dtype=np.float32), rng.standard_normal((m, 1), dtype=np.float32),
+                      (rng.random((m, 1)) < 0.5).astype(np.float32))
+        idx = np.arange(buf._size)
+        b = buf.gather(idx)
+        torch.cuda.synchronize()
+        assert np.array_equal(b["observations"].cpu().numpy(), buf.observations[idx])
+        assert np.array_equal(b["terminals"].cpu().numpy(), buf.terminals[idx])
+    mean, std = buf.normalize_obs()
+    b = buf.gather(np.arange(buf._size))
+    torch.cuda.synchronize()
+    assert np.array_equal(b["next_observations"].cpu().numpy(), buf.next_observations[:buf._size])
