@@ -110,6 +110,31 @@ typedef struct OrlkGemmDesc {
 
 int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, void* stream);
 
+/* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
+ *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.
+ * passes = 1: single TF32 MMA per product ("fast" mode); passes = 3: hi/lo operand split in shared memory and
+ * three MMAs per product (fp32-grade, the parity mode).  Outputs (each optional): row-major C (per k-split slot),
+ * transposed CT[n][m], rowsum[m] = sum_k A[g][m][k] (bias gradients; also per k-split slot).  The struct is read
+ * on the HOST (it is not a device pointer).  Same reference call sites as orlk_gemm_grouped. */
+typedef struct OrlkTcGemm {
+    const float* A; int64_t lda, a_gs;
+    const float* B; int64_t ldb, b_gs;
+    float* C; int64_t ldc, c_gs, c_split_stride;
+    float* CT; int64_t ldct, ct_gs;
+    const float* bias; int64_t bias_gs;
+    const float* aux; int64_t ldaux, aux_gs;
+    float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
+    int32_t M, N, K, G;
+    int32_t epi;      /* ORLK_EPI_NONE | ORLK_EPI_RELU | ORLK_EPI_RELU_MASK */
+    int32_t k_splits; /* as returned by orlk_tc_effective_splits */
+    int32_t passes;   /* 1 or 3 */
+    int32_t pad_;
+} OrlkTcGemm;
+int orlk_tc_init(void);
+int orlk_tc_gemm(const OrlkTcGemm* params_host, void* stream);
+int orlk_tc_effective_splits(int K, int want);
+int orlk_sizeof_tc_gemm(void);
+
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
  * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).
  *   fwd :  Y[g][m,n] = b[g][n] + sum_k X[g][m,k] * W[g][n*ldw + k]            (one warp per row)

@@ -43,6 +43,18 @@ class AdamDesc(C.Structure):
                 ("wd", C.c_float), ("block_start", C.c_int32), ("flags", C.c_int32), ("pad_", C.c_int32)]
 
 
+class TcGemm(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("a_gs", C.c_int64),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("b_gs", C.c_int64),
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("c_gs", C.c_int64), ("c_split_stride", C.c_int64),
+                ("CT", C.c_void_p), ("ldct", C.c_int64), ("ct_gs", C.c_int64),
+                ("bias", C.c_void_p), ("bias_gs", C.c_int64),
+                ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_gs", C.c_int64),
+                ("rowsum", C.c_void_p), ("rowsum_gs", C.c_int64), ("rowsum_split_stride", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("G", C.c_int32),
+                ("epi", C.c_int32), ("k_splits", C.c_int32), ("passes", C.c_int32), ("pad_", C.c_int32)]
+
+
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)
 CFG_BIG, CFG_MID, CFG_SMALL = range(3)
 CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32)}
@@ -65,6 +77,8 @@ _PROTOS = {
     "orlk_replay_pack": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _L, _P],
     "orlk_replay_gather": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _P],
+    "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I],
+    "orlk_sizeof_tc_gemm": [],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
@@ -106,7 +120,8 @@ def load() -> C.CDLL:
     if lib.orlk_abi_version() != ABI_VERSION:
         raise OrlkError(f"ABI mismatch: library {lib.orlk_abi_version()} vs binding {ABI_VERSION}; rebuild")
     for fn, st in (("orlk_sizeof_gemm_desc", GemmDesc), ("orlk_sizeof_adam_desc", AdamDesc),
-                   ("orlk_sizeof_adam_group", AdamGroup), ("orlk_sizeof_concat_seg", ConcatSeg)):
+                   ("orlk_sizeof_adam_group", AdamGroup), ("orlk_sizeof_concat_seg", ConcatSeg),
+                   ("orlk_sizeof_tc_gemm", TcGemm)):
         if getattr(lib, fn)() != C.sizeof(st):
             raise OrlkError(f"struct size mismatch for {st.__name__}: C {getattr(lib, fn)()} vs ctypes {C.sizeof(st)}")
     _lib = lib

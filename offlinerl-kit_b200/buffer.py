@@ -195,5 +195,17 @@ class ReplayBuffer:
                st.term.data_ptr(), rt.cur)
         return st.batch
 
+    def gather_device(self, idx_dev: torch.Tensor) -> Batch:
+        """Gather with indices that already live on the device (int64 [B]); no host traffic at all."""
+        rt = self._runtime()
+        if self._dirty or self._table is None:
+            self._sync_mirror()
+        B = int(idx_dev.shape[0])
+        st = self._stage(B)
+        L.call("orlk_replay_gather", self._table.data_ptr(), len(self.observations), self.row_width, self._obs_dim,
+               self.action_dim, idx_dev.data_ptr(), B, st.obs2.data_ptr(), st.act.data_ptr(), st.rew.data_ptr(),
+               st.term.data_ptr(), rt.cur)
+        return st.batch
+
     def sample(self, batch_size: int) -> Dict[str, torch.Tensor]:
         return self.gather(self.draw_indices(batch_size))

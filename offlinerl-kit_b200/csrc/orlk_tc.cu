@@ -1,0 +1,430 @@
+// Tensor-core GEMM for the wide hidden layers: tcgen05.mma (kind::tf32) with TMEM accumulators, TMA operand
+// staging through an mbarrier ring, warp-specialised roles.  sm_100a only.
+//
+//   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] )          A, B row-major with k contiguous ("K-major")
+//
+// One CTA = one 128-row tile of A x all N (<= 256) columns, for one k-split.  The fp32 accumulator tile lives in
+// TMEM (128 lanes x N columns).  Precision modes:
+//   passes = 1 : one TF32 MMA per product (10-bit mantissa operands, fp32 accumulate)  -- "fast" mode
+//   passes = 3 : operands are split in shared memory into hi = tf32(x) and lo = x - hi and three MMAs
+//                (hi*hi + lo*hi + hi*lo) are accumulated: ~2^-21 relative error per product -- fp32-parity mode.
+// Optional fused outputs: row-major C, transposed C^T (the K-major operand of the next weight-gradient GEMM),
+// bias + ReLU / ReLU-mask epilogues, and row sums of A (bias gradients) computed by the tensor core against a
+// tile of ones.
+//
+// Replaces the 256x256 nn.Linear forward / dgrad / wgrad GEMMs of both critics over the 7936-row CQL critic batch
+// (reference: nets/mlp.py:22 forward; autograd backward of the same layers; cql.py:133-190).
+#include <cuda.h>
+#include "orlk_common.cuh"
+using namespace orlk;
+
+namespace {
+
+constexpr int BM = 128, BN_MAX = 256, BK = 32;          // BK fp32 = 128 bytes = one SWIZZLE_128B row
+constexpr int A_BYTES = BM * BK * 4;                      // 16 KB
+constexpr int B_BYTES = BN_MAX * BK * 4;                  // 32 KB
+constexpr int ONES_BYTES = 16 * BK * 4;                   // 2 KB
+constexpr int TMEM_COLS = 512;
+constexpr int ROWSUM_COL = 256;
+constexpr int NUM_THREADS = 192;                          // warp0 TMA, warp1 MMA, warps2-5 split + epilogue
+
+struct TcParams {
+    float* C; int64_t ldc, c_gs, c_split_stride;
+    float* CT; int64_t ldct, ct_gs;
+    const float* bias; int64_t bias_gs;
+    const float* aux; int64_t ldaux, aux_gs;
+    float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
+    int M, N, K, G, epi, k_splits, slabs_per_split, tiles_m;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+// 8-row groups of 128-byte rows, SBO = 1024 bytes between groups, LBO unused (1), layout_type 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t instr_desc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return v;
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
+__device__ __forceinline__ void split_tf32(float4& v, float4& lo) {
+    float4 hi;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    v = hi;
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    constexpr int STAGES = PASSES == 3 ? 2 : 4;
+    constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ones = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
+    uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
+    uint64_t* splitb = bars + STAGES;       // [STAGES]  hi/lo split done (PASSES == 3)
+    uint64_t* empty = bars + 2 * STAGES;    // [STAGES]  MMAs that read the stage have completed
+    uint64_t* accum = bars + 3 * STAGES;    // accumulator tile complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int idx = blockIdx.x;
+    const int split = idx % p.k_splits;
+    idx /= p.k_splits;
+    const int tile_m = idx % p.tiles_m;
+    const int g = idx / p.tiles_m;
+    const int total_slabs = (p.K + BK - 1) / BK;
+    const int slab0 = split * p.slabs_per_split;
+    const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
+    const bool want_rowsum = p.rowsum != nullptr;
+
+    auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
+    auto b_raw = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES; };
+    auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES + B_BYTES; };
+    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&splitb[s]), 128);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(accum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && want_rowsum) {
+        float* o = reinterpret_cast<float*>(ones);
+        for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        const uint32_t tx_bytes = A_BYTES + (uint32_t)p.N * BK * 4;
+        for (int it = 0; it < nslabs; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+            mbar_expect_tx(smem_u32(&full[s]), tx_bytes);
+            const int k0 = (slab0 + it) * BK;
+            tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, g);
+            tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, 0, g);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        const uint32_t idesc = instr_desc_tf32(BM, p.N);
+        const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
+        const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
+        for (int it = 0; it < nslabs; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(smem_u32(PASSES == 3 ? &splitb[s] : &full[s]), ph);
+            tc_fence_after();
+            const uint64_t ad = smem_desc_sw128(smem_u32(a_raw(s))), bd = smem_desc_sw128(smem_u32(b_raw(s)));
+            const uint64_t adl = smem_desc_sw128(smem_u32(a_lo(s))), bdl = smem_desc_sw128(smem_u32(b_lo(s)));
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {              // UMMA_K = 8 for tf32: 32 bytes along K per instruction
+                const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                const uint64_t koff = (uint64_t)(k * 2);    // +32 bytes in the 16-byte-unit start-address field
+                umma_tf32(tmem_base, ad + koff, bd + koff, idesc, acc);
+                if (PASSES == 3) {
+                    umma_tf32(tmem_base, adl + koff, bd + koff, idesc, 1u);
+                    umma_tf32(tmem_base, ad + koff, bdl + koff, idesc, 1u);
+                }
+                if (want_rowsum) {
+                    umma_tf32(tmem_base + ROWSUM_COL, ad + koff, ones_desc, idesc_rs, acc);
+                    if (PASSES == 3) umma_tf32(tmem_base + ROWSUM_COL, adl + koff, ones_desc, idesc_rs, 1u);
+                }
+            }
+            umma_commit(smem_u32(&empty[s]));               // frees the stage when these MMAs have completed
+        }
+        umma_commit(smem_u32(accum));
+    } else if (warp >= 2) {
+        const int t = threadIdx.x - 64;                     // 0..127
+        if (PASSES == 3) {
+            // -------------------------------------------------------------- operand splitter
+            const int nB4 = p.N * BK / 4;
+            for (int it = 0; it < nslabs; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(smem_u32(&full[s]), ph);
+                float4* ar = reinterpret_cast<float4*>(a_raw(s));
+                float4* al = reinterpret_cast<float4*>(a_lo(s));
+                float4* br = reinterpret_cast<float4*>(b_raw(s));
+                float4* bl = reinterpret_cast<float4*>(b_lo(s));
+#pragma unroll 4
+                for (int i = t; i < A_BYTES / 16; i += 128) {
+                    float4 v = ar[i], lo;
+                    split_tf32(v, lo);
+                    ar[i] = v;
+                    al[i] = lo;
+                }
+#pragma unroll 4
+                for (int i = t; i < nB4; i += 128) {
+                    float4 v = br[i], lo;
+                    split_tf32(v, lo);
+                    br[i] = v;
+                    bl[i] = lo;
+                }
+                fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(smem_u32(&splitb[s]));
+            }
+        }
+        // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+        mbar_wait(smem_u32(accum), 0);
+        tc_fence_after();
+        const int q = warp & 3;                             // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int row = q * 32 + lane;
+        const int m = tile_m * BM + row;
+        const bool row_ok = m < p.M;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* C = p.C ? p.C + (int64_t)g * p.c_gs + (int64_t)split * p.c_split_stride + (int64_t)m * p.ldc : nullptr;
+        float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + m : nullptr;
+        const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_gs : nullptr;
+        const float* aux = p.aux ? p.aux + (int64_t)g * p.aux_gs + (int64_t)m * p.ldaux : nullptr;
+        const bool vec_ok = (p.N % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
+                            (p.c_split_stride % 4 == 0);
+        const bool aux_vec = aux != nullptr && (p.ldaux % 4 == 0) && aligned16(p.aux) && (p.aux_gs % 4 == 0);
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            tmem_wait_ld();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = c0 + j;
+                float val = __uint_as_float(v[j]);
+                if (bias != nullptr && n < p.N) val += __ldg(bias + n);
+                x[j] = val;
+            }
+            if (p.epi == ORLK_EPI_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            } else if (p.epi == ORLK_EPI_RELU_MASK && row_ok) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const int n = c0 + 4 * j4;
+                    if (n >= p.N) break;
+                    float a4[4];
+                    if (aux_vec) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(aux + n));
+                        a4[0] = a.x; a4[1] = a.y; a4[2] = a.z; a4[3] = a.w;
+                    } else {
+                        for (int e = 0; e < 4; ++e) a4[e] = (n + e < p.N) ? __ldg(aux + n + e) : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[4 * j4 + e] = a4[e] > 0.f ? x[4 * j4 + e] : 0.f;
+                }
+            }
+            if (row_ok) {
+                if (C != nullptr) {
+                    if (vec_ok) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            if (c0 + 4 * j4 < p.N)
+                                *reinterpret_cast<float4*>(C + c0 + 4 * j4) =
+                                    make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < p.N) C[c0 + j] = x[j];
+                    }
+                }
+                if (CT != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) CT[(int64_t)(c0 + j) * p.ldct] = x[j];   // coalesced across the warp's rows
+                }
+            }
+        }
+        if (want_rowsum) {
+            const uint32_t r = tmem_ld1(taddr + ROWSUM_COL);
+            tmem_wait_ld();
+            if (row_ok) p.rowsum[(int64_t)g * p.rowsum_gs + (int64_t)split * p.rowsum_split_stride + m] = __uint_as_float(r);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 3-D tensor map over [G][rows][K] fp32 (k contiguous), box = 32 (k) x box_rows x 1, 128-byte swizzle.
+int make_map(CUtensorMap* map, const float* base, int64_t ld, int64_t gs, int rows, int K, int G, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ORLK_ERR_UNSUPPORTED;
+    }
+    if (gs <= 0) gs = (int64_t)rows * ld;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)G};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)gs * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (ld=%lld gs=%lld rows=%d K=%d G=%d)", (int)r, (long long)ld,
+                  (long long)gs, rows, K, G);
+        return ORLK_ERR_BAD_ARG;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int orlk_sizeof_tc_gemm(void) { return (int)sizeof(OrlkTcGemm); }
+
+static size_t tc_smem_bytes(int passes) {
+    const int stages = passes == 3 ? 2 : 4;
+    const int stage_bytes = (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1);
+    return (size_t)stages * stage_bytes + ONES_BYTES + 256 + 1024;
+}
+
+// Opt in to > 48 KB of dynamic shared memory once, outside any stream capture.
+extern "C" int orlk_tc_init(void) {
+    int rc = check(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(1)), "smem attr <1>");
+    if (rc) return rc;
+    return check(cudaFuncSetAttribute(k_tc_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(3)), "smem attr <3>");
+}
+
+extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
+    ORLK_REQUIRE(q != nullptr, "params");
+    ORLK_REQUIRE(q->M > 0 && q->K > 0 && q->G > 0, "sizes");
+    ORLK_REQUIRE(q->N >= 16 && q->N <= BN_MAX && q->N % 16 == 0, "N must be a multiple of 16 in [16,256]");
+    ORLK_REQUIRE(q->passes == 1 || q->passes == 3, "passes must be 1 or 3");
+    ORLK_REQUIRE(q->lda % 4 == 0 && q->ldb % 4 == 0 && q->a_gs % 4 == 0 && q->b_gs % 4 == 0, "operand strides must be multiples of 4 floats");
+    ORLK_REQUIRE(aligned16(q->A) && aligned16(q->B), "operands must be 16-byte aligned");
+    ORLK_REQUIRE(q->epi == ORLK_EPI_NONE || q->epi == ORLK_EPI_RELU || q->epi == ORLK_EPI_RELU_MASK, "epilogue");
+    ORLK_REQUIRE(q->epi != ORLK_EPI_RELU_MASK || q->aux != nullptr, "mask epilogue needs aux");
+    const int total_slabs = (q->K + BK - 1) / BK;
+    int splits = q->k_splits < 1 ? 1 : q->k_splits;
+    int per = (total_slabs + splits - 1) / splits;
+    splits = (total_slabs + per - 1) / per;
+    ORLK_REQUIRE(splits == 1 || (q->epi == ORLK_EPI_NONE && q->bias == nullptr), "split-K needs a linear epilogue");
+    ORLK_REQUIRE(splits == (q->k_splits < 1 ? 1 : q->k_splits), "k_splits must divide the slab count evenly enough (use orlk_tc_effective_splits)");
+
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, q->G, BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, q->N);
+    if (rc) return rc;
+
+    TcParams p;
+    p.C = q->C; p.ldc = q->ldc; p.c_gs = q->c_gs; p.c_split_stride = q->c_split_stride;
+    p.CT = q->CT; p.ldct = q->ldct; p.ct_gs = q->ct_gs;
+    p.bias = q->bias; p.bias_gs = q->bias_gs;
+    p.aux = q->aux; p.ldaux = q->ldaux; p.aux_gs = q->aux_gs;
+    p.rowsum = q->rowsum; p.rowsum_gs = q->rowsum_gs; p.rowsum_split_stride = q->rowsum_split_stride;
+    p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
+    p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
+
+    const size_t smem = tc_smem_bytes(q->passes);
+    const int grid = q->G * p.tiles_m * splits;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (q->passes == 3) k_tc_gemm<3><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+    else k_tc_gemm<1><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+    return check_launch("k_tc_gemm");
+}
+
+// number of k-splits orlk_tc_gemm will accept for (K, want): chunks are whole 32-wide slabs
+extern "C" int orlk_tc_effective_splits(int K, int want) {
+    const int total_slabs = (K + BK - 1) / BK;
+    if (want < 1) want = 1;
+    const int per = (total_slabs + want - 1) / want;
+    return (total_slabs + per - 1) / per;
+}

@@ -10,6 +10,7 @@ import torch
 from .. import _lib as L
 
 NUM_SMS = 148
+_ctypes_pointer = C.pointer      # (the name ``C`` is shadowed by a matrix argument in Runtime.tc_gemm)
 
 
 def require_cuda(device) -> torch.device:
@@ -87,6 +88,7 @@ class Runtime:
         self.exec_ptr = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         self.cur = self.exec_ptr
         self._keep: List[torch.Tensor] = []
+        L.call("orlk_tc_init")
 
     # ---- memory helpers (torch owns device memory: plumbing)
     def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
@@ -126,6 +128,29 @@ class Runtime:
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())
         return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, self.cur)
+
+    def tc_gemm(self, *, A: Mat, a_gs: int, B: Mat, b_gs: int, G: int, passes: int, epi: int = L.EPI_NONE,
+                C: Optional[Mat] = None, c_gs: int = 0, c_split_stride: int = 0, CT: Optional[Mat] = None, ct_gs: int = 0,
+                bias: int = 0, bias_gs: int = 0, aux: Optional[Mat] = None, aux_gs: int = 0, rowsum: int = 0,
+                rowsum_gs: int = 0, rowsum_split_stride: int = 0, k_splits: int = 1) -> Callable[[], None]:
+        """tcgen05 GEMM launch: C[g] = epi(A[g] (M x K) . B[g]^T (N x K)); group strides in floats."""
+        q = L.TcGemm()
+        q.A, q.lda, q.a_gs = A.ptr, A.ld, a_gs
+        q.B, q.ldb, q.b_gs = B.ptr, B.ld, b_gs
+        if C is not None:
+            q.C, q.ldc, q.c_gs, q.c_split_stride = C.ptr, C.ld, c_gs, c_split_stride
+        if CT is not None:
+            q.CT, q.ldct, q.ct_gs = CT.ptr, CT.ld, ct_gs
+        q.bias, q.bias_gs = bias or None, bias_gs
+        if aux is not None:
+            q.aux, q.ldaux, q.aux_gs = aux.ptr, aux.ld, aux_gs
+        q.rowsum, q.rowsum_gs, q.rowsum_split_stride = rowsum or None, rowsum_gs, rowsum_split_stride
+        q.M, q.N, q.K, q.G = A.rows, B.rows, A.cols, G
+        assert A.cols == B.cols
+        q.epi, q.passes = epi, passes
+        q.k_splits = self.lib.orlk_tc_effective_splits(A.cols, k_splits)
+        qp = _ctypes_pointer(q)      # the struct is read on the host at every launch: keep it alive in the closure
+        return lambda: L.call("orlk_tc_gemm", qp, self.cur)
 
     @staticmethod
     def effective_splits(K: int, want: int, cfg: int) -> int:

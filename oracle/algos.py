@@ -31,11 +31,13 @@ def _prefixed(state: Tensors, prefix: str) -> List[str]:
 class _Learner:
     """Parameter store + Adam factories shared by all oracles."""
 
+    device = "cpu"      # class-level default; set ``Cls.device = "cuda"`` before construction to time eager-GPU PyTorch
+
     def __init__(self, state: Tensors, trainable_prefixes: Iterable[str]):
         tp = tuple(trainable_prefixes)
         self.p: Tensors = {}
         for k, v in state.items():
-            t = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).detach().clone()
+            t = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).detach().clone().to(self.device)
             if t.is_floating_point():
                 t = t.float()
             train = any(k.startswith(pre + ".") for pre in tp) and "saved_" not in k and t.is_floating_point()
@@ -79,7 +81,7 @@ class _AutoAlpha:
         if isinstance(alpha, tuple):
             self.auto_alpha = True
             self.target_entropy, log_alpha0, alpha_lr = alpha
-            self.log_alpha = torch.tensor([float(log_alpha0)], requires_grad=True)
+            self.log_alpha = torch.tensor([float(log_alpha0)], requires_grad=True, device=self.device)
             self.alpha_optim = torch.optim.Adam([self.log_alpha], lr=alpha_lr)
             self.alpha = self.log_alpha.detach().exp()
         else:
@@ -172,7 +174,7 @@ class CQLOracle(_Learner, _AutoAlpha):
         self.w, self.T = cql_weight, temperature
         self.max_q_backup, self.det_backup = max_q_backup, deterministic_backup
         self.with_lagrange, self.thr = with_lagrange, lagrange_threshold
-        self.cql_log_alpha = torch.zeros(1, requires_grad=True)                       # cql.py:57
+        self.cql_log_alpha = torch.zeros(1, requires_grad=True, device=self.device)   # cql.py:57
         self.cql_alpha_optim = torch.optim.Adam([self.cql_log_alpha], lr=cql_alpha_lr)  # cql.py:58
         self.N = num_repeat_actions
 
@@ -297,7 +299,7 @@ class EDACOracle(_Learner, _AutoAlpha):
             g = g / (torch.norm(g, p=2, dim=2).unsqueeze(-1) + 1e-10)
             g = g.transpose(0, 1)
             gram = torch.einsum("bik,bjk->bij", g, g)
-            mask = torch.eye(E).unsqueeze(0).repeat(gram.size(0), 1, 1)
+            mask = torch.eye(E, device=gram.device).unsqueeze(0).repeat(gram.size(0), 1, 1)
             gram = (1 - mask) * gram
             grad_loss = torch.mean(torch.sum(gram, dim=(1, 2))) / (E - 1)
             loss = loss + self.eta * grad_loss

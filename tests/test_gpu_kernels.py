@@ -170,6 +170,17 @@ def _head_ref(head, eps, A):
     return a, lp
 
 
+def _lp_from_action(head, eps, a_gpu, A):
+    """log-prob with the tanh correction evaluated in fp32 from the kernel's own action: near |a| = 1 the term
+    log(1 - a^2 + 1e-6) is ill-conditioned in fp32 (for the reference as well), so an fp64 tanh is no oracle there."""
+    mu, raw = head[:, :A].double(), head[:, A:].double()
+    ls = raw.clamp(-5, 2)
+    e = eps.double() if eps is not None else torch.zeros_like(mu)
+    lp = (-(e ** 2) / 2 - ls - 0.5 * math.log(2 * math.pi)).sum(-1)
+    a32 = a_gpu.float().cpu()
+    return lp - torch.log((1 - a32 * a32) + 1e-6).double().sum(-1)
+
+
 def test_tanh_gauss_sample_and_bwd(rt):
     from offlinerlkit_b200 import _lib as L
     gen = torch.Generator().manual_seed(2)
@@ -183,20 +194,24 @@ def test_tanh_gauss_sample_and_bwd(rt):
     lp = torch.zeros(M, device=DEV)
     L.call("orlk_tanh_gauss_sample", hd.data_ptr(), 2 * A, B, rep, ed.data_ptr(), M, A, X.data_ptr() + 4 * O, O + A,
            lp.data_ptr(), od.data_ptr(), O, O, X.data_ptr(), O + A, rt.cur)
-    hrep = head[B:].repeat_interleave(rep, 0).double()
-    a_ref, lp_ref = _head_ref(hrep, eps.double(), A)
+    hrep = head[B:].repeat_interleave(rep, 0)
+    a_ref, _ = _head_ref(hrep.double(), eps.double(), A)
     _close(X[:, O:], a_ref, rtol=1e-5, atol=1e-6, msg="sampled action")
-    _close(lp, lp_ref[:, 0], rtol=1e-5, atol=1e-4, msg="log-prob")
+    _close(lp, _lp_from_action(hrep, eps, X[:, O:], A), rtol=1e-5, atol=1e-4, msg="log-prob")
     assert torch.equal(X[:, :O].cpu(), obs.repeat_interleave(rep, 0))
     # mode (eps == NULL)
     L.call("orlk_tanh_gauss_sample", hd.data_ptr(), 2 * A, B, rep, None, M, A, X.data_ptr() + 4 * O, O + A,
            lp.data_ptr(), None, 0, 0, None, 0, rt.cur)
-    a_ref, lp_ref = _head_ref(hrep, None, A)
+    a_ref, _ = _head_ref(hrep.double(), None, A)
     _close(X[:, O:], a_ref, msg="mode action")
-    _close(lp, lp_ref[:, 0], rtol=1e-5, atol=1e-4, msg="mode log-prob")
-    # backward against autograd (rep = 1)
-    head1 = (torch.randn(B, 2 * A, generator=gen) * 2.5).double().requires_grad_(True)
-    eps1 = torch.randn(B, A, generator=gen)
+    _close(lp, _lp_from_action(hrep, None, X[:, O:], A), rtol=1e-5, atol=1e-4, msg="mode log-prob")
+    # backward against autograd (rep = 1); pre-tanh values kept moderate so that fp32 and fp64 agree,
+    # raw log-sigma still crosses both clamp bounds (gradient gating)
+    h0 = torch.randn(B, 2 * A, generator=gen)
+    h0[:, :A] *= 0.5
+    h0[:, A:] *= 2.5
+    head1 = h0.double().requires_grad_(True)
+    eps1 = torch.randn(B, A, generator=gen) * 0.5 * torch.exp(-h0[:, A:].clamp(-5, 2))
     a1, lp1 = _head_ref(head1, eps1.double(), A)
     dA0, dA1, glp = torch.randn(B, A, generator=gen), torch.randn(B, A, generator=gen), torch.randn(B, generator=gen)
     loss = (a1 * (dA0 + dA1).double()).sum() + (lp1[:, 0] * glp.double()).sum()
@@ -206,6 +221,7 @@ def test_tanh_gauss_sample_and_bwd(rt):
     lpd = torch.zeros(B, device=DEV)
     L.call("orlk_tanh_gauss_sample", h1d.data_ptr(), 2 * A, 0, 1, e1d.data_ptr(), B, A, act.data_ptr(), A, lpd.data_ptr(),
            None, 0, 0, None, 0, rt.cur)
+    _close(lpd, lp1[:, 0], rtol=1e-5, atol=1e-4, msg="log-prob (moderate)")
     dh = torch.zeros(B, 2 * A, device=DEV)
     d0, d1, gl = dA0.to(DEV), dA1.to(DEV), glp.to(DEV)
     L.call("orlk_tanh_gauss_bwd", h1d.data_ptr(), 2 * A, e1d.data_ptr(), act.data_ptr(), A, d0.data_ptr(), d1.data_ptr(),
@@ -399,3 +415,63 @@ def test_replay_gather_bit_exact_and_ring(rt):
     b = buf.gather(np.arange(buf._size))
     torch.cuda.synchronize()
     assert np.array_equal(b["next_observations"].cpu().numpy(), buf.next_observations[:buf._size])
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM
+def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed):
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import Mat
+    gen = torch.Generator().manual_seed(seed)
+    A = torch.randn(G, M, K, generator=gen)
+    B = torch.randn(G, N, K, generator=gen) / math.sqrt(K)
+    bias = torch.randn(G, N, generator=gen)
+    aux = torch.randn(G, M, N, generator=gen)
+    Ad, Bd, bd, auxd = A.to(DEV), B.to(DEV), bias.to(DEV), aux.to(DEV)
+    s_eff = rt.lib.orlk_tc_effective_splits(K, splits)
+    Cd = torch.full((s_eff, G, M, N), float("nan"), device=DEV)
+    CTd = torch.full((G, N, M), float("nan"), device=DEV)
+    rs = torch.full((s_eff, G, M), float("nan"), device=DEV)
+    op = rt.tc_gemm(A=Mat(Ad.data_ptr(), M, K, K), a_gs=M * K, B=Mat(Bd.data_ptr(), N, K, K), b_gs=N * K, G=G,
+                    passes=passes, epi=epi, C=Mat(Cd.data_ptr(), M, N, N), c_gs=M * N, c_split_stride=G * M * N,
+                    CT=Mat(CTd.data_ptr(), N, M, M) if want_ct else None, ct_gs=N * M,
+                    bias=bd.data_ptr() if with_bias else 0, bias_gs=N,
+                    aux=Mat(auxd.data_ptr(), M, N, N) if epi == L.EPI_RELU_MASK else None, aux_gs=M * N,
+                    rowsum=rs.data_ptr() if want_rowsum else 0, rowsum_gs=M, rowsum_split_stride=G * M, k_splits=splits)
+    op()
+    torch.cuda.synchronize()
+    ref = torch.einsum("gmk,gnk->gmn", A.double(), B.double())
+    if with_bias:
+        ref = ref + bias.double()[:, None, :]
+    if epi == L.EPI_RELU:
+        ref = ref.clamp(min=0)
+    elif epi == L.EPI_RELU_MASK:
+        ref = ref * (aux > 0)
+    got = Cd.sum(0) if s_eff > 1 else Cd[0]
+    tag = f"tc G{G} {M}x{N}x{K} passes{passes} epi{epi} splits{s_eff}"
+    assert not torch.isnan(got).any(), tag + ": unwritten output"
+    # 3 passes: fp32-grade.  1 pass: TF32 operands (10-bit mantissa, truncated) -> ~1e-3 of the row scale
+    tol = 3e-6 if passes == 3 else 3e-3
+    scale = (A.double().abs() @ B.double().abs().transpose(1, 2)).max().item()
+    err = (got.double().cpu() - ref).abs().max().item()
+    assert err <= tol * scale, f"{tag}: max err {err:.3e} vs {tol * scale:.3e}"
+    if want_ct:
+        assert torch.equal(CTd, got.transpose(1, 2).contiguous()) or s_eff > 1, tag + " CT"
+    if want_rowsum:
+        rref = A.double().sum(2)
+        rerr = (rs.sum(0).double().cpu() - rref).abs().max().item()
+        assert rerr <= (3e-6 if passes == 3 else 3e-3) * A.abs().sum(2).max().item(), f"{tag} rowsum err {rerr:.3e}"
+    return err / scale
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
+    from offlinerlkit_b200 import _lib as L
+    errs = []
+    errs.append(_tc_case(rt, 1, 128, 256, 32, passes, L.EPI_NONE, 1, False, False, False, 1))     # one slab, one tile
+    errs.append(_tc_case(rt, 1, 128, 256, 256, passes, L.EPI_NONE, 1, False, True, False, 2))
+    errs.append(_tc_case(rt, 2, 300, 256, 256, passes, L.EPI_RELU, 1, True, True, False, 3))       # ragged M, bias+ReLU
+    errs.append(_tc_case(rt, 2, 7936, 256, 256, passes, L.EPI_RELU_MASK, 1, False, True, False, 4))  # critic dgrad
+    errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 16, False, False, True, 5))    # critic wgrad + bias grads
+    errs.append(_tc_case(rt, 3, 200, 64, 96, passes, L.EPI_NONE, 1, True, True, True, 6))          # narrow N, K not /128
+    errs.append(_tc_case(rt, 1, 1000, 208, 224, passes, L.EPI_RELU, 1, True, False, False, 7))     # N = 208 (13 x 16)
+    print(f"passes={passes}: relative errors {['%.2e' % e for e in errs]}")
