@@ -35,7 +35,9 @@ ALPHA_LR = 1e-4
 FLOP_PER_STEP = 13.84e9
 CONFIG = {"workload": "cql_halfcheetah_shaped obs17 act6 hidden256x3 batch256 repeat10 auto-alpha no-lagrange "
                       "buffer1M (configs[1])",
-          "batch": BATCH, "buffer_rows": N_DATA, "precision_mode": "fp32 (FFMA accumulate, parity mode)",
+          "batch": BATCH, "buffer_rows": N_DATA,
+          "precision_mode": "tf32x3 = fp32-grade: 3 TF32 tensor-core MMAs per product on hi/lo split operands, fp32 "
+                            "accumulate (parity-tested at 1e-4); narrow layers in fp32 FFMA",
           "l2": "replay table (176 MB, random rows) is larger than L2; the 6 MB of model state is L2-resident by "
                 "design of the workload; no explicit flush",
           "parallelism": "seed-parallel replicas, one per GPU, no data-path collective"}
@@ -321,17 +323,20 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         Mc = BATCH + 3 * BATCH * N_REPEAT
         flop = {}
         for l in (1, 2):
-            flop[f"C.critic.fwd{l}"] = 2 * 2 * Mc * 256 * 256
-            flop[f"C.critic.dgrad{l}"] = 2 * 2 * Mc * 256 * 256
+            for kind in ("fwd", "dgrad", "wgrad"):
+                flop[f"C.critic.{kind}{l}"] = flop[f"C.critic.{kind}{l}.tc"] = 2 * 2 * Mc * 256 * 256
         flop["C.critic.wgrad_big"] = 2 * 2 * 2 * Mc * 256 * 256
         big = [(lbl, us) for lbl, us in br if lbl in flop]
+        on_tc = any(lbl.endswith(".tc") for lbl, _ in big)
         big_us = sum(us for _, us in big)
         big_flop = sum(flop[lbl] for lbl, _ in big)
         step_us = sum(us for _, us in br)
         achieved = big_flop / (big_us * 1e-6) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "k_gemm_grouped<128,128,16,8,8> (fp32 FFMA; hidden-layer fwd/dgrad/wgrad "
-                                             "of both critics over 7936 rows)",
+        kname = (f"k_tc_gemm<{eng.tc_passes}> (tcgen05.mma kind::tf32, {eng.tc_passes} MMA pass(es) per product, TMEM "
+                 "accumulators, TMA operand ring; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)") if on_tc \
+            else "k_gemm_grouped<128,128,16,8,8> (fp32 FFMA; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)"
+        roof = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} bf16 dense (sustained)", "traffic": None,
                 "launches_per_step": len(big), "us_per_step": big_us, "share_of_step": big_us / step_us,
@@ -339,12 +344,15 @@ def run_engine(args, rank: int, world: int, local_rank: int):
                 "fp32_simt_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
                 "frac_of_fp32_simt_peak": achieved / (148 * 128 * 2 * 1.965e9 / 1e12)}
         top = sorted(br, key=lambda x: -x[1])[:8]
+        if args.full_breakdown:
+            with open(args.full_breakdown, "w") as f:
+                json.dump({"precision": eng.precision, "launch_us": br, "graph_step_us": 1e3 * dev_ms / K}, f, indent=1)
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms / K, "us_per_update": 1e3 * dev_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 8 * BATCH, "d2h_bytes_per_step": 4 * 32,
                         "ms_per_step": e2e_ms / K},
-                "gpu_launches": n_kernels * K, "launches_per_step": n_kernels, "roofline": roof,
+                "gpu_launches": n_kernels * K, "launches_per_step": n_kernels, "roofline": roof, "precision": eng.precision,
                 "launch_breakdown_us": {lbl: round(us, 2) for lbl, us in top}, "eager_step_us": step_us,
                 "last_loss": {k: float(v) for k, v in loss.items()}}
         if world == 1 and not args.no_cpu_baseline:
@@ -376,9 +384,14 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--rows", type=int, default=N_DATA)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=None, choices=["fp32", "tf32x3", "tf32"],
+                    help="GEMM mode of the wide layers (default tf32x3, the fp32-parity tensor-core mode)")
+    ap.add_argument("--full-breakdown", default=None, help="write the per-launch device times (JSON) to this file")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.precision:
+        os.environ["ORLK_PRECISION"] = args.precision
     if args.impl == "reference":
         run_reference(args, rank)
         return

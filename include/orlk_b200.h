@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 3
+#define ORLK_ABI_VERSION 4
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -94,7 +94,8 @@ typedef struct OrlkGemmDesc {
     const float* aux;  /* epilogue operand indexed [m*ldaux + n] or NULL               */
     float* rowsum;     /* optional [M]: sum_k A(m,k), written by the n-tile-0 CTAs     */
     float* colsum;     /* optional [N]: sum_k B(k,n), written by the m-tile-0 CTAs     */
-    int64_t lda, ldb, ldc, ldaux;
+    float* CT;         /* optional transposed copy of the output: CT[n*ldct + m]       */
+    int64_t lda, ldb, ldc, ldaux, ldct;
     int64_t c_split_stride;   /* split s writes C + (split_base+s)*c_split_stride      */
     int64_t sum_split_stride; /* same for rowsum / colsum                              */
     int32_t M, N, K;
@@ -143,8 +144,9 @@ int orlk_sizeof_tc_gemm(void);
 int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
                     int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G, void* stream);
 int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W, int64_t ldw, int64_t w_gs,
-                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, int M, int K,
-                      int NS, int G, void* stream);
+                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, float* dXT,
+                      int64_t ldxt, int64_t xt_gs, int M, int K, int NS, int G, void* stream);
+/*   dXT (optional): transposed copy dXT[g][k*ldxt + m], the K-major operand of the tensor-core weight gradient. */
 
 /* Row assembly for critic inputs: dst[row_off+m, 0:w1) = src1[(m / rep1), 0:w1); dst[.., w1:w1+w2) = src2[m, 0:w2)
  * (replaces torch.cat / repeat in critic_module.py:25 and cql.py:142-147). */
@@ -233,7 +235,8 @@ typedef struct OrlkAdamDesc {
     float wd;
     int32_t block_start; /* prefix sum of ceil(n / 1024) */
     int32_t flags;       /* ORLK_OPT_ADAM | ORLK_OPT_POLYAK */
-    int32_t pad_;
+    int32_t cols;        /* with pT: the tensor is [n/cols, cols] row-major ...                     */
+    float* pT;           /* ... and pT receives its transpose [cols, n/cols] (K-major dgrad operand) */
 } OrlkAdamDesc;
 enum { ORLK_OPT_ADAM = 1, ORLK_OPT_POLYAK = 2 };
 int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream);

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -17,7 +17,8 @@ c_stream = C.c_void_p
 class GemmDesc(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
                 ("bias", C.c_void_p), ("aux", C.c_void_p), ("rowsum", C.c_void_p), ("colsum", C.c_void_p),
-                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64), ("ldaux", C.c_int64),
+                ("CT", C.c_void_p),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64), ("ldaux", C.c_int64), ("ldct", C.c_int64),
                 ("c_split_stride", C.c_int64), ("sum_split_stride", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("a_layout", C.c_int32), ("b_layout", C.c_int32), ("epi", C.c_int32),
@@ -40,7 +41,8 @@ class AdamGroup(C.Structure):
 class AdamDesc(C.Structure):
     _fields_ = [("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("tgt", C.c_void_p), ("grad", C.c_void_p),
                 ("n", C.c_int64), ("g_split_stride", C.c_int64), ("g_splits", C.c_int32), ("group", C.c_int32),
-                ("wd", C.c_float), ("block_start", C.c_int32), ("flags", C.c_int32), ("pad_", C.c_int32)]
+                ("wd", C.c_float), ("block_start", C.c_int32), ("flags", C.c_int32), ("cols", C.c_int32),
+                ("pT", C.c_void_p)]
 
 
 class TcGemm(C.Structure):
@@ -80,7 +82,7 @@ _PROTOS = {
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I],
     "orlk_sizeof_tc_gemm": [],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
-    "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
+    "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
     "orlk_philox_fill": [_P, _L, _L, _F, _F, C.c_uint64, _P, _P, _P],
     "orlk_tanh_gauss_sample": [_P, _L, _I, _I, _P, _I, _I, _P, _L, _P, _P, _L, _I, _P, _L, _P],

@@ -12,7 +12,7 @@ constexpr int MAX_NS = 16;
 // ------------------------------------------------------------------------------------------ skinny layers
 __global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
                              int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
-                             int64_t y_gs, int M, int K, int NS) {
+                             int64_t y_gs, int M, int K, int NS, int vec) {
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -22,11 +22,26 @@ __global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x
     float acc[MAX_NS];
 #pragma unroll
     for (int n = 0; n < MAX_NS; ++n) acc[n] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        const float xv = x[k];
+    if (vec) {      // K % 4 == 0 and 16-byte aligned rows: 128-bit loads, all of a row's loads in flight at once
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int K4 = K >> 2;
+#pragma unroll 2
+        for (int k = lane; k < K4; k += 32) {
+            const float4 xv = x4[k];
 #pragma unroll
-        for (int n = 0; n < MAX_NS; ++n)
-            if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + k), acc[n]);
+            for (int n = 0; n < MAX_NS; ++n)
+                if (n < NS) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * ldw) + k);
+                    acc[n] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[n]))));
+                }
+        }
+    } else {
+        for (int k = lane; k < K; k += 32) {
+            const float xv = x[k];
+#pragma unroll
+            for (int n = 0; n < MAX_NS; ++n)
+                if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + k), acc[n]);
+        }
     }
 #pragma unroll
     for (int n = 0; n < MAX_NS; ++n)
@@ -37,19 +52,42 @@ __global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x
     }
 }
 
+// 32 x 32 (m x k) tile per block of 32 x 8 threads; the optional transposed copy goes through shared memory so
+// that both stores are coalesced.
 __global__ void k_skinny_dgrad(const float* __restrict__ dY, int64_t ldy, int64_t y_gs, const float* __restrict__ W,
                                int64_t ldw, int64_t w_gs, const float* __restrict__ mask, int64_t ldm, int64_t m_gs,
-                               float* __restrict__ dX, int64_t ldx, int64_t x_gs, int M, int K, int NS) {
-    const int g = blockIdx.y;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (int64_t)M * K) return;
-    const int m = (int)(e / K), k = (int)(e % K);
-    const float* dy = dY + g * y_gs + (int64_t)m * ldy;
-    const float* w = W + g * w_gs + k;
-    float s = 0.f;
-    for (int n = 0; n < NS; ++n) s = fmaf(dy[n], __ldg(w + (int64_t)n * ldw), s);
-    if (mask != nullptr && !(mask[g * m_gs + (int64_t)m * ldm + k] > 0.f)) s = 0.f;
-    dX[g * x_gs + (int64_t)m * ldx + k] = s;
+                               float* __restrict__ dX, int64_t ldx, int64_t x_gs, float* __restrict__ dXT, int64_t ldxt,
+                               int64_t xt_gs, int M, int K, int NS) {
+    __shared__ float tile[32][33];
+    const int g = blockIdx.z;
+    const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int k = k0 + tx;
+    float wk[MAX_NS];
+#pragma unroll
+    for (int n = 0; n < MAX_NS; ++n) wk[n] = (n < NS && k < K) ? __ldg(W + g * w_gs + (int64_t)n * ldw + k) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = ty + 8 * r;
+        const int m = m0 + row;
+        float s = 0.f;
+        if (m < M && k < K) {
+            const float* dy = dY + g * y_gs + (int64_t)m * ldy;
+#pragma unroll
+            for (int n = 0; n < MAX_NS; ++n)
+                if (n < NS) s = fmaf(dy[n], wk[n], s);
+            if (mask != nullptr && !(mask[g * m_gs + (int64_t)m * ldm + k] > 0.f)) s = 0.f;
+            dX[g * x_gs + (int64_t)m * ldx + k] = s;
+        }
+        tile[row][tx] = s;
+    }
+    if (dXT == nullptr) return;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int kk = k0 + ty + 8 * r, m = m0 + tx;
+        if (kk < K && m < M) dXT[g * xt_gs + (int64_t)kk * ldxt + m] = tile[tx][ty + 8 * r];
+    }
 }
 
 // ------------------------------------------------------------------------------------------ row assembly
@@ -355,6 +393,10 @@ k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamG
             const float denom = sqrtf(v) / s_bc2_sqrt + g.eps;
             p = p - s_step_size * (m / denom);
             d.p[i] = p;
+            if (d.pT != nullptr) {      // keep the transposed (K-major for dgrad) copy of the weight in sync
+                const int64_t r = i / d.cols, c = i % d.cols;
+                d.pT[c * (d.n / d.cols) + r] = p;
+            }
         }
         if ((d.flags & ORLK_OPT_POLYAK) && d.tgt != nullptr) d.tgt[i] = d.tgt[i] * (1.f - g.tau) + p * g.tau;
     }
@@ -376,18 +418,20 @@ int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, i
     ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
     const int wpb = 8;
     dim3 grid((M + wpb - 1) / wpb, G);
-    k_skinny_fwd<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS);
+    const int vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && (x_gs % 4 == 0) && (w_gs % 4 == 0) && aligned16(X) &&
+                    aligned16(W);
+    k_skinny_fwd<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
     return check_launch("k_skinny_fwd");
 }
 
 int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W, int64_t ldw, int64_t w_gs,
-                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, int M, int K,
-                      int NS, int G, void* stream) {
+                      const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, float* dXT,
+                      int64_t ldxt, int64_t xt_gs, int M, int K, int NS, int G, void* stream) {
     ORLK_REQUIRE(NS >= 1 && NS <= MAX_NS, "NS must be in [1,16]");
     ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
-    const int64_t n = (int64_t)M * K;
-    dim3 grid((unsigned)((n + 255) / 256), G);
-    k_skinny_dgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs, M, K, NS);
+    dim3 grid((K + 31) / 32, (M + 31) / 32, G);
+    k_skinny_dgrad<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs,
+                                                                dXT, ldxt, xt_gs, M, K, NS);
     return check_launch("k_skinny_dgrad");
 }
 

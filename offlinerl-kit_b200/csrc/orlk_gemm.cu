@@ -224,7 +224,9 @@ k_gemm_grouped(const OrlkGemmDesc* __restrict__ descs, int n_descs) {
             if (d.bias != nullptr) v += __ldg(d.bias + n);
             const float ax = has_aux ? __ldg(d.aux + (int64_t)m * d.ldaux + n) : 0.f;
             if (epi == ORLK_EPI_SWISH && d.C2 != nullptr) d.C2[(int64_t)m * d.ldc + n] = v;
-            C[(int64_t)m * d.ldc + n] = epilogue(v, epi, ax);
+            const float r = epilogue(v, epi, ax);
+            C[(int64_t)m * d.ldc + n] = r;
+            if (d.CT != nullptr) d.CT[(int64_t)n * d.ldct + m] = r;
         }
     }
     if (do_rs && tx == 0) {

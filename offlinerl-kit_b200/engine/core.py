@@ -72,6 +72,8 @@ class GP:
     split_base: int = 0
     c_split_stride: int = 0
     sum_split_stride: int = 0
+    CT: int = 0
+    ldct: int = 0
 
 
 class Runtime:
@@ -119,6 +121,7 @@ class Runtime:
             d.A, d.B, d.C, d.C2 = p.A, p.B, p.C, p.C2 or None
             d.bias, d.aux, d.rowsum, d.colsum = p.bias or None, p.aux or None, p.rowsum or None, p.colsum or None
             d.lda, d.ldb, d.ldc, d.ldaux = p.lda, p.ldb, p.ldc, p.ldaux
+            d.CT, d.ldct = p.CT or None, p.ldct
             d.c_split_stride, d.sum_split_stride = p.c_split_stride, p.sum_split_stride
             d.M, d.N, d.K = p.M, p.N, p.K
             d.a_layout, d.b_layout, d.epi = p.a_layout, p.b_layout, p.epi
@@ -183,6 +186,7 @@ class Runtime:
             d.p, d.m, d.v, d.tgt, d.grad = t.p, t.m or None, t.v or None, t.tgt or None, t.grad or None
             d.n, d.g_split_stride, d.g_splits, d.group = t.n, t.g_split_stride, t.g_splits, t.group
             d.wd, d.block_start, d.flags = t.wd, blk, t.flags
+            d.pT, d.cols = t.pT or None, max(t.cols, 1)
             blk += -(-t.n // 1024)
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr, gp = len(descs), blk, C.c_void_p(dev.data_ptr()), C.c_void_p(groups_ptr)
@@ -202,6 +206,8 @@ class AdamT:
     g_split_stride: int = 0
     wd: float = 0.0
     flags: int = L.OPT_ADAM
+    pT: int = 0
+    cols: int = 1
 
 
 class Plan:

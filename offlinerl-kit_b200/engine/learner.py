@@ -7,6 +7,7 @@ CUDA graph and returns the loss scalars after a single stream synchronisation --
 contract of ``policy.learn`` (policy/base_policy.py:25-26).
 """
 import ctypes as C
+import os
 import struct
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -16,11 +17,12 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .core import GP, AdamT, Mat, Plan, Runtime, get_runtime
-from .nets import (GradBuf, Layer, ParamSet, adam_descs, dgrad_problem, fwd_problem, pick_cfg, wgrad_problem,
-                   wgrad_splits)
+from .nets import (GradBuf, Layer, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, fwd_problem, pick_cfg,
+                   tc_ok_dgrad, tc_ok_fwd, tc_ok_wgrad, wgrad_problem, wgrad_splits)
 
 MAX_GROUPS = 16
 N_LOSS = 32
+PRECISIONS = {"fp32": 0, "tf32x3": 3, "tf32": 1}
 
 
 def linears_of(module: nn.Module) -> List[nn.Linear]:
@@ -66,6 +68,12 @@ class Learner:
         self.plans: Dict[str, Plan] = {}
         self.use_graph = True
         self.steps_done = 0
+        # GEMM precision of the wide layers: "fp32" = SIMT FFMA, "tf32x3" = tensor cores with hi/lo operand split
+        # (fp32-grade, default), "tf32" = single-pass TF32 tensor cores (fast mode, looser tolerance)
+        self.precision = os.environ.get("ORLK_PRECISION", "tf32x3")
+        if self.precision not in PRECISIONS:
+            raise L.OrlkError(f"unknown precision {self.precision!r}; choose one of {sorted(PRECISIONS)}")
+        self.param_sets: List[ParamSet] = []
 
     # ------------------------------------------------------------------ Adam groups
     def add_group(self, optim: Optional[torch.optim.Optimizer], tau: float = 0.0, **hyper) -> int:
@@ -109,6 +117,15 @@ class Learner:
             self.noise_enable.fill_(1 if on else 0)
             self._noise_enabled_host = on
 
+    @property
+    def tc_passes(self) -> int:
+        return PRECISIONS[self.precision]
+
+    def refresh(self) -> None:
+        """Host-side writes to the parameters (load_state_dict, custom init) invalidate derived copies."""
+        for ps in self.param_sets:
+            ps.refresh_wt()
+
     # ------------------------------------------------------------------ plan execution
     def run(self, key: str) -> np.ndarray:
         plan = self.plans[key]
@@ -141,17 +158,38 @@ class Learner:
 # Reusable schedule fragments for ReLU MLP member groups
 # --------------------------------------------------------------------------------------------------------------
 class MlpRun:
-    """Activation / gradient buffers of one forward(+backward) pass of a ParamSet over M rows."""
+    """Activation / gradient buffers of one forward(+backward) pass of a ParamSet over M rows.
 
-    def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P"):
+    ``tc_passes`` = 0 runs every GEMM on the SIMT fp32 kernel; 1 / 3 routes eligible wide layers to the tcgen05
+    kernel (TF32, or 3xTF32 fp32-grade).  The tensor-core weight gradient wants K-major operands, i.e. the
+    TRANSPOSED activations / gradients; those are emitted by the producing kernels' epilogues into HT / dZT.
+    """
+
+    def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P",
+                 tc_passes: int = 0):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
+        self.tc = tc_passes if M >= TC_MIN_ROWS else 0
+        self.Mt = (M + 3) // 4 * 4
         G = ps.G
-        self.H = [rt.zeros(G, M, ps.layers[l].out_dim) for l in range(n_hidden)]
-        self.dZ = [rt.zeros(G, M, ps.layers[l].out_dim) for l in range(n_hidden)] if need_grad else None
-        self.has_head = len(ps.layers) > n_hidden
-        self.NS = ps.layers[n_hidden].out_dim if self.has_head else 0
+        lays = ps.layers
+        self.H = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)]
+        self.dZ = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)] if need_grad else None
+        self.has_head = len(lays) > n_hidden
+        self.NS = lays[n_hidden].out_dim if self.has_head else 0
         self.out = rt.zeros(G, M, self.NS) if self.has_head else None
         self.dOut = rt.zeros(G, M, self.NS) if (self.has_head and need_grad) else None
+        # per-layer kernel choice
+        self.tc_fwd = [bool(self.tc) and l >= 1 and tc_ok_fwd(lays[l], M) for l in range(n_hidden)]
+        self.tc_dgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_dgrad(lays[l], M) for l in range(n_hidden)]
+        self.tc_wgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_wgrad(lays[l], M) for l in range(n_hidden)]
+        self.HT = [None] * n_hidden
+        self.dZT = [None] * n_hidden
+        for l in range(n_hidden):
+            if self.tc_wgrad[l]:
+                self.dZT[l] = rt.zeros(G, lays[l].out_dim, self.Mt)
+                self.HT[l - 1] = rt.zeros(G, lays[l - 1].out_dim, self.Mt)
+        if any(self.tc_dgrad):
+            ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
 
     def h(self, l: int, g: int) -> Mat:
         return Mat.of(self.H[l][g])
@@ -159,14 +197,34 @@ class MlpRun:
     def dz(self, l: int, g: int) -> Mat:
         return Mat.of(self.dZ[l][g])
 
+    def ht(self, l: int, g: int) -> Optional[Mat]:
+        return None if self.HT[l] is None else Mat(self.HT[l][g].data_ptr(), self.HT[l].shape[1], self.M, self.Mt)
+
+    def dzt(self, l: int, g: int) -> Optional[Mat]:
+        return None if self.dZT[l] is None else Mat(self.dZT[l][g].data_ptr(), self.dZT[l].shape[1], self.M, self.Mt)
+
+
+def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
+    """Member 0 of a [G, rows, ld] tensor as a Mat (the tensor-core launcher strides over the members itself)."""
+    return Mat(t.data_ptr(), rows, cols, ld, t)
+
 
 def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
-    """Hidden layers as grouped GEMMs (+bias+ReLU fused), then the narrow head as a warp-per-row kernel."""
-    ps, G = run.ps, run.ps.G
+    """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
+    ps, G, M = run.ps, run.ps.G, run.M
     for l in range(run.nh):
-        probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store)
-                 for g in range(G)]
-        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(run.M * G, ps.layers[l].out_dim)))
+        lay = ps.layers[l]
+        if run.tc_fwd[l]:
+            K, N = lay.in_dim, lay.out_dim
+            plan.add(f"{tag}.fwd{l}.tc", rt.tc_gemm(
+                A=_grouped(run.H[l - 1], M, K, K), a_gs=M * K, B=Mat(ps.w(l, 0, run.store), N, K, K), b_gs=lay.w_gs, G=G,
+                passes=run.tc, epi=L.EPI_RELU, C=_grouped(run.H[l], M, N, N), c_gs=M * N,
+                CT=_grouped(run.HT[l], N, M, run.Mt) if run.HT[l] is not None else None, ct_gs=N * run.Mt,
+                bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
+            continue
+        probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store,
+                             YT=run.ht(l, g)) for g in range(G)]
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim)))
     if run.has_head:
         emit_head_forward(rt, plan, run, tag)
 
@@ -184,30 +242,47 @@ def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
 
 
 def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
-    """dZ[last hidden] = (dOut W_head) * relu'(H[last hidden])."""
+    """dZ[last hidden] = (dOut W_head) * relu'(H[last hidden])  (+ its transpose for a tensor-core wgrad)."""
     ps, G, l = run.ps, run.ps.G, run.nh
     lay = ps.layers[l]
     K = lay.in_dim
     hmask = run.H[l - 1]
+    dzt = run.dZT[l - 1]
     args = (run.dOut.data_ptr(), run.NS, run.M * run.NS, ps.w(l, 0), K, lay.w_gs, hmask.data_ptr(), K, run.M * K,
-            run.dZ[l - 1].data_ptr(), K, run.M * K, run.M, K, run.NS, G)
+            run.dZ[l - 1].data_ptr(), K, run.M * K, dzt.data_ptr() if dzt is not None else None, run.Mt, K * run.Mt,
+            run.M, K, run.NS, G)
     plan.add(f"{tag}.head_dgrad", lambda: L.call("orlk_skinny_dgrad", *args, rt.cur))
 
 
 def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1) -> None:
     """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to."""
-    ps, G = run.ps, run.ps.G
+    ps, G, M = run.ps, run.ps.G, run.M
     for l in range(run.nh - 1, down_to - 1, -1):
-        probs = [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g))
-                 for g in range(G)]
-        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(run.M * G, ps.layers[l].in_dim)))
+        lay = ps.layers[l]
+        if run.tc_dgrad[l]:
+            K, N = lay.out_dim, lay.in_dim
+            plan.add(f"{tag}.dgrad{l}.tc", rt.tc_gemm(
+                A=_grouped(run.dZ[l], M, K, K), a_gs=M * K, B=Mat(ps.wt(l, 0), N, K, K), b_gs=lay.w_gs, G=G,
+                passes=run.tc, epi=L.EPI_RELU_MASK, C=_grouped(run.dZ[l - 1], M, N, N), c_gs=M * N,
+                CT=_grouped(run.dZT[l - 1], N, M, run.Mt) if run.dZT[l - 1] is not None else None, ct_gs=N * run.Mt,
+                aux=_grouped(run.H[l - 1], M, N, N), aux_gs=M * N))
+            continue
+        probs = [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g),
+                               dXT=run.dzt(l - 1, g)) for g in range(G)]
+        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim)))
 
 
-def wgrad_layout(ps: ParamSet, n_layers: int, M: int) -> List[Tuple[int, int]]:
-    """(tile config, split-K factor) per layer for a weight-gradient reduction over M rows."""
+TC_WGRAD_SPLITS = 16
+
+
+def wgrad_layout(ps: ParamSet, n_layers: int, M: int, tc_layers: Sequence[bool] = ()) -> List[Tuple[int, int]]:
+    """(tile config or -1 for the tensor-core kernel, split-K factor) per layer for a reduction over M rows."""
     out = []
     for l in range(n_layers):
         lay = ps.layers[l]
+        if l < len(tc_layers) and tc_layers[l]:
+            out.append((-1, L.load().orlk_tc_effective_splits(M, TC_WGRAD_SPLITS)))
+            continue
         out_r, out_c = (lay.out_dim, lay.in_dim) if lay.layout == "oi" else (lay.in_dim, lay.out_dim)
         cfg = L.CFG_BIG if (out_r >= 128 and out_c >= 128 and M >= 2048) else L.CFG_SMALL
         BM, BN, _ = L.CFG_TILES[cfg]
@@ -216,11 +291,12 @@ def wgrad_layout(ps: ParamSet, n_layers: int, M: int) -> List[Tuple[int, int]]:
     return out
 
 
-def make_gradbuf(rt: Runtime, ps: ParamSet, row_counts: Sequence[Tuple[int, int]]) -> GradBuf:
-    """GradBuf with enough split slots for reductions over each (n_layers, M) the ParamSet will see."""
+def make_gradbuf(rt: Runtime, ps: ParamSet, runs: Sequence["MlpRun"]) -> GradBuf:
+    """GradBuf with enough split slots for the weight-gradient reductions of the given passes."""
     slots = 1
-    for n_layers, M in row_counts:
-        slots = max([slots] + [s for _, s in wgrad_layout(ps, n_layers, M)])
+    for run in runs:
+        n_l = run.nh + (1 if run.has_head else 0)
+        slots = max([slots] + [s for _, s in wgrad_layout(ps, n_l, run.M, run.tc_wgrad)])
     return GradBuf(rt, ps, slots)
 
 
@@ -230,11 +306,20 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     ps, G, M = run.ps, run.ps.G, run.M
     big, small = [], []
     n_l = run.nh + (1 if run.has_head else 0)
-    layout = wgrad_layout(ps, n_l, M)
+    layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
     splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
     for l in range(n_l):
         cfg, s = layout[l]
         assert s <= gb.n_slots, (s, gb.n_slots)
+        lay = ps.layers[l]
+        if cfg == -1:
+            # dW[o,i] = sum_m dZ^T[o,m] * H^T[i,m]; bias gradient = row sums of dZ^T (a ones-tile MMA)
+            plan.add(f"{tag}.wgrad{l}.tc", rt.tc_gemm(
+                A=_grouped(run.dZT[l], lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt,
+                B=_grouped(run.HT[l - 1], lay.in_dim, M, run.Mt), b_gs=lay.in_dim * run.Mt, G=G, passes=run.tc,
+                C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
+                rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s))
+            continue
         for g in range(G):
             xin = X[g] if l == 0 else run.h(l - 1, g)
             dy = run.dz(l, g) if l < run.nh else Mat.of(run.dOut[g])
@@ -244,5 +329,3 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     if small:
         plan.add(f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL))
     plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l)), groups_ptr))
-
-

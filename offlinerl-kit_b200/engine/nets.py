@@ -40,6 +40,9 @@ class ParamSet:
         self.layers: List[Layer] = []     # hidden layers followed by narrow heads, in forward order
         self.extra: Dict[str, Tuple[int, int]] = {}   # name -> (offset, numel) of non-layer parameters
         self.P = self.Mo = self.Vo = self.T = None
+        self.WT = None                    # transposed weight copies (K-major operand of the tensor-core dgrad)
+        self.wt_layers: List[int] = []
+        self._wt_version = -1
         self.group_ids: List[int] = []     # Adam group index per member (set by the learner)
 
     # ------------------------------------------------------------------ construction from facade modules
@@ -163,6 +166,36 @@ class ParamSet:
             view.copy_(p.detach().to(store.device, torch.float32))
         p.data = view
 
+    # ------------------------------------------------------------------ transposed weight copies
+    def enable_wt(self, layers: Sequence[int]) -> None:
+        """Maintain WT[l] = W[l]^T ([in, out] row-major) for the given 'oi' layers.  The Adam kernel keeps them in
+        sync after every update (OrlkAdamDesc.pT); ``refresh_wt`` re-derives them after host-side writes."""
+        new = [l for l in layers if l not in self.wt_layers]
+        if not new:
+            return
+        if self.WT is None:
+            self.WT = self.rt.zeros(self.total)
+        self.wt_layers += new
+        self._wt_version = -1
+        self.refresh_wt()
+
+    def refresh_wt(self) -> None:
+        if self.WT is None or self.P._version == self._wt_version:
+            return
+        with torch.no_grad():
+            for l in self.wt_layers:
+                lay = self.layers[l]
+                assert lay.layout == "oi"
+                for g in range(self.G):
+                    o = lay.w_off + g * lay.w_gs
+                    src = self.P[o:o + lay.w_numel].view(lay.out_dim, lay.in_dim)
+                    self.WT[o:o + lay.w_numel].view(lay.in_dim, lay.out_dim).copy_(src.t())
+        self._wt_version = self.P._version
+
+    def wt(self, l: int, g: int = 0) -> int:
+        lay = self.layers[l]
+        return self._ptr(self.WT, lay.w_off + g * lay.w_gs)
+
     # ------------------------------------------------------------------ pointers
     def _ptr(self, store: torch.Tensor, off: int) -> int:
         return store.data_ptr() + 4 * off
@@ -198,6 +231,21 @@ class GradBuf:
 
 
 # ---------------------------------------------------------------------------------------------- emitters
+TC_MIN_ROWS = 1024      # below this the 128-row tiles cannot fill the machine; the SIMT kernel is used instead
+
+
+def tc_ok_fwd(lay: Layer, M: int) -> bool:
+    return lay.layout == "oi" and lay.in_dim % 4 == 0 and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and M >= TC_MIN_ROWS
+
+
+def tc_ok_dgrad(lay: Layer, M: int) -> bool:
+    return lay.layout == "oi" and lay.out_dim % 4 == 0 and lay.in_dim % 16 == 0 and lay.in_dim <= 256 and M >= TC_MIN_ROWS
+
+
+def tc_ok_wgrad(lay: Layer, M: int) -> bool:
+    return lay.layout == "oi" and lay.in_dim % 16 == 0 and lay.in_dim <= 256 and lay.out_dim >= 64 and M >= TC_MIN_ROWS
+
+
 def pick_cfg(M: int, N: int) -> int:
     """Tile configuration for an output of M x N (see csrc/orlk_gemm.cu)."""
     if M * N >= 128 * 128 * 96:
@@ -207,7 +255,8 @@ def pick_cfg(M: int, N: int) -> int:
     return L.CFG_SMALL
 
 
-def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: str = "P", Z: Optional[Mat] = None) -> GP:
+def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: str = "P", Z: Optional[Mat] = None,
+                YT: Optional[Mat] = None) -> GP:
     """Y = act(X W^T + b) for member g of layer l (nn.Linear, mlp.py:22 / EnsembleLinear, ensemble_linear.py:30-41)."""
     lay = ps.layers[l]
     assert X.cols == lay.in_dim and Y.cols == lay.out_dim and X.rows == Y.rows, (X, Y, lay)
@@ -217,11 +266,11 @@ def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: s
         b_layout, ldb = 0, lay.out_dim
     return GP(A=X.ptr, lda=X.ld, a_layout=0, B=ps.w(l, g, store), ldb=ldb, b_layout=b_layout, C=Y.ptr, ldc=Y.ld,
               M=X.rows, N=lay.out_dim, K=lay.in_dim, epi=epi, bias=ps.b(l, g, store),
-              C2=Z.ptr if Z is not None else 0)
+              C2=Z.ptr if Z is not None else 0, CT=YT.ptr if YT is not None else 0, ldct=YT.ld if YT is not None else 0)
 
 
 def dgrad_problem(ps: ParamSet, l: int, g: int, dY: Mat, dX: Mat, epi: int, aux: Optional[Mat],
-                  col0: int = 0, ncols: Optional[int] = None) -> GP:
+                  col0: int = 0, ncols: Optional[int] = None, dXT: Optional[Mat] = None) -> GP:
     """dX[:, col0:col0+ncols] = (dY W)[:, col0:...] (x) mask  -- input gradient of layer l for member g."""
     lay = ps.layers[l]
     ncols = lay.in_dim - col0 if ncols is None else ncols
@@ -232,7 +281,8 @@ def dgrad_problem(ps: ParamSet, l: int, g: int, dY: Mat, dX: Mat, epi: int, aux:
         Bp, b_layout, ldb = ps.w(l, g) + 4 * col0 * lay.out_dim, 1, lay.out_dim
     return GP(A=dY.ptr, lda=dY.ld, a_layout=0, B=Bp, ldb=ldb, b_layout=b_layout, C=dX.ptr, ldc=dX.ld,
               M=dY.rows, N=ncols, K=lay.out_dim, epi=epi, aux=aux.ptr if aux is not None else 0,
-              ldaux=aux.ld if aux is not None else 0)
+              ldaux=aux.ld if aux is not None else 0, CT=dXT.ptr if dXT is not None else 0,
+              ldct=dXT.ld if dXT is not None else 0)
 
 
 def wgrad_problem(ps: ParamSet, gb: GradBuf, l: int, g: int, X: Mat, dY: Mat, k_splits: int, split_base: int = 0,
@@ -265,11 +315,13 @@ def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polya
             nb = lay.out_dim * (ps.G if contiguous else 1)
             wo = lay.w_off + (0 if contiguous else g * lay.w_gs)
             bo = lay.b_off + (0 if contiguous else g * lay.b_gs)
-            for off, n in ((wo, nw), (bo, nb)):
+            for off, n, is_w in ((wo, nw, True), (bo, nb, False)):
+                keep_t = is_w and ps.WT is not None and l in ps.wt_layers and not contiguous
                 out.append(AdamT(p=ps._ptr(ps.P, off), n=n, group=ps.group_ids[g], m=ps._ptr(ps.Mo, off),
                                  v=ps._ptr(ps.Vo, off), tgt=ps._ptr(ps.T, off) if (polyak and ps.T is not None) else 0,
                                  grad=gb.ptr(off), g_splits=s, g_split_stride=gb.stride,
-                                 flags=L.OPT_ADAM | (L.OPT_POLYAK if polyak and ps.T is not None else 0)))
+                                 flags=L.OPT_ADAM | (L.OPT_POLYAK if polyak and ps.T is not None else 0),
+                                 pT=ps._ptr(ps.WT, off) if keep_t else 0, cols=lay.in_dim if keep_t else 1))
     return out
 
 

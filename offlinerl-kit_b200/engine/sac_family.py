@@ -45,6 +45,7 @@ class TwinCriticLearner(Learner):
         self.critic_ps = ParamSet.from_linear_members(
             rt, "critics", [linears_of(c1), linears_of(c2)],
             targets=[linears_of(policy.critic1_old), linears_of(policy.critic2_old)], fuse_last=1)
+        self.param_sets = [self.actor_ps, self.critic_ps]
         self.nh_a = len(self.actor_ps.layers) - 1
         self.nh_c = len(self.critic_ps.layers) - 1
         self.O = self.actor_ps.layers[0].in_dim
@@ -214,12 +215,12 @@ class CQLLearner(TwinCriticLearner):
         self._alloc_actor_phase()
         self.run_actor_b = MlpRun(rt, self.actor_ps, 2 * B, self.nh_a, need_grad=False)
         self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
-        self.run_critic = MlpRun(rt, self.critic_ps, Mc, self.nh_c, need_grad=True)
+        self.run_critic = MlpRun(rt, self.critic_ps, Mc, self.nh_c, need_grad=True, tc_passes=self.tc_passes)
         self.Xt = rt.zeros(B, O + A)
         self.Xc = rt.zeros(Mc, O + A)
         self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(B), rt.zeros(R), rt.zeros(R)
-        self.gb_actor = make_gradbuf(rt, self.actor_ps, [(self.nh_a + 1, B)])
-        self.gb_critic = make_gradbuf(rt, self.critic_ps, [(self.nh_c + 1, Mc)])
+        self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
+        self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
 
         plan = Plan(rt, "cql")
         self._emit_noise(plan, self.n_normal, self.n_uniform, self.act_lo, self.act_hi)
@@ -262,6 +263,7 @@ class CQLLearner(TwinCriticLearner):
             self._build()
         self.set_noise(noise)
         self.sync_lr()
+        self.refresh()
         out = self.run("step")
         res = {"loss/actor": float(out[LS_ACTOR]), "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
         if self.auto_alpha:

@@ -77,7 +77,7 @@ def make_buffer(g: Golden, device="cuda:0"):
     return buf, data
 
 
-def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0"):
+def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0", precision=None):
     """Engine vs golden (= the real reference): index draw + gather bit-exact, then losses and parameters."""
     m = g.meta
     policy = build_policy(m, device)
@@ -94,7 +94,10 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
         ref_b = g.batch(t, data)
         for k, v in ref_b.items():
             assert torch.equal(batch[k].cpu().reshape(v.shape), v), f"gather not bit-exact: {k}"
-        policy.engine(m["B"]).use_graph = use_graph
+        eng = policy.engine(m["B"])
+        eng.use_graph = use_graph
+        if precision is not None and t == 0:
+            eng.precision = precision
         noise = g.noise(t) if any(k.startswith(f"noise{t}|") for k in g.z.files) else None
         out = policy.learn(batch, noise=noise) if noise is not None else policy.learn(batch)
         ref = g.losses(t)

@@ -141,10 +141,16 @@ def test_skinny_fwd_and_dgrad(rt):
         mask = torch.randn(G, M, K, generator=gen)
         dX = torch.zeros(G, M, K, device=DEV)
         dYd, md = dY.to(DEV), mask.to(DEV)
+        dXT = torch.zeros(G, K, M, device=DEV)
         L.call("orlk_skinny_dgrad", dYd.data_ptr(), NS, M * NS, Wd.data_ptr(), K, NS * K, md.data_ptr(), K, M * K,
-               dX.data_ptr(), K, M * K, M, K, NS, G, rt.cur)
+               dX.data_ptr(), K, M * K, dXT.data_ptr(), M, K * M, M, K, NS, G, rt.cur)
         ref = torch.einsum("gmn,gnk->gmk", dY.double(), W.double()) * (mask > 0)
         _close(dX, ref, msg=f"skinny dgrad {G,M,K,NS}")
+        assert torch.equal(dXT, dX.transpose(1, 2).contiguous()), "transposed copy"
+        dX2 = torch.zeros(G, M, K, device=DEV)
+        L.call("orlk_skinny_dgrad", dYd.data_ptr(), NS, M * NS, Wd.data_ptr(), K, NS * K, None, 0, 0,
+               dX2.data_ptr(), K, M * K, None, 0, 0, M, K, NS, G, rt.cur)
+        _close(dX2, torch.einsum("gmn,gnk->gmk", dY.double(), W.double()), msg="skinny dgrad no mask")
 
 
 def test_concat_rows(rt):
