@@ -222,32 +222,41 @@ def run_reference(args, rank: int):
 
 # ------------------------------------------------------------------------------------------------ engine arm
 def per_launch_breakdown(eng, reps: int = 20):
-    """Eager replay of the step's launch list with a CUDA-event pair around every launch (device time per launch)."""
+    """Device time of every launch of the step: each launch is captured alone into a CUDA graph, repeated `reps`
+    times back to back, and that graph is timed with a CUDA-event pair on the launching stream (warm caches, no
+    host launch cost in the measurement)."""
     from offlinerlkit_b200 import _lib as L
     import ctypes as C
     plan = eng.plans["step"]
     rt = eng.rt
-    n = len(plan.ops)
-    evs = []
-    for _ in range(n + 1):
-        e = C.c_void_p()
-        L.call("orlk_event_create", C.byref(e))
-        evs.append(e)
-    tot = np.zeros(n)
-    for r in range(reps + 2):
-        L.call("orlk_event_record", evs[0], rt.cur)
-        for i, (_, op) in enumerate(plan.ops):
-            op()
-            L.call("orlk_event_record", evs[i + 1], rt.cur)
-        rt.sync()
-        if r >= 2:
-            for i in range(n):
-                ms = C.c_float()
-                L.call("orlk_event_elapsed_ms", evs[i], evs[i + 1], C.byref(ms))
-                tot[i] += ms.value
-    for e in evs:
-        L.call("orlk_event_destroy", e)
-    return [(plan.ops[i][0], 1e3 * tot[i] / reps) for i in range(n)]      # microseconds
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    L.call("orlk_event_create", C.byref(e0))
+    L.call("orlk_event_create", C.byref(e1))
+    out = []
+    for label, op in plan.ops:
+        g = C.c_void_p()
+        torch.cuda.synchronize()
+        rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
+        try:
+            L.call("orlk_graph_begin", rt.cur)
+            try:
+                for _ in range(reps):
+                    op()
+            finally:
+                L.call("orlk_graph_end", rt.cur, C.byref(g))
+        finally:
+            rt.cur = rt.exec_ptr
+        L.call("orlk_graph_launch", g, rt.cur)
+        L.call("orlk_event_record", e0, rt.cur)
+        L.call("orlk_graph_launch", g, rt.cur)
+        L.call("orlk_event_record", e1, rt.cur)
+        ms = C.c_float()
+        L.call("orlk_event_elapsed_ms", e0, e1, C.byref(ms))
+        L.call("orlk_graph_destroy", g)
+        out.append((label, 1e3 * ms.value / reps))
+    L.call("orlk_event_destroy", e0)
+    L.call("orlk_event_destroy", e1)
+    return out      # microseconds per launch
 
 
 def run_engine(args, rank: int, world: int, local_rank: int):

@@ -148,6 +148,20 @@ int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W
                       int64_t ldxt, int64_t xt_gs, int M, int K, int NS, int G, void* stream);
 /*   dXT (optional): transposed copy dXT[g][k*ldxt + m], the K-major operand of the tensor-core weight gradient. */
 
+/* Streaming kernels for large row counts where one operand is narrow (<= 32 wide): the first critic / dynamics layer
+ * (K = obs+act inputs) forward, and the weight gradients of that layer and of the narrow heads.
+ *   fwd  : Y[g][m][n] = act(b[g][n] + sum_k X[g][m][k] W[g][n*ldw+k]), K <= 32; optional transposed copy YT[g][n][m]
+ *   wgrad: per 128-row chunk c:  out[g][c][ns*s_ns + kw*s_kw] = sum_m Nar[g][m][ns] * Wide[g][m][kw]  (NS <= 32),
+ *          wide_sum[g][c][kw] = sum_m Wide[g][m][kw],  nar_sum[g][c][ns] = sum_m Nar[g][m][ns]  (both optional);
+ *          the chunks are summed by orlk_adam_step (g_splits = orlk_narrow_wgrad_chunks(M)). */
+int orlk_narrow_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
+                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, float* YT, int64_t ldyt, int64_t yt_gs, int M, int N,
+                    int K, int G, int relu, void* stream);
+int orlk_narrow_wgrad_chunks(int M);
+int orlk_narrow_wgrad(const float* Wide, int64_t ldw, int64_t w_gs, const float* Nar, int64_t ldn, int64_t n_gs, float* out,
+                      int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs, float* wide_sum, int64_t ws_gs, int64_t ws_cs,
+                      float* nar_sum, int64_t ns_gs, int64_t ns_cs, int M, int KW, int NS, int G, void* stream);
+
 /* Row assembly for critic inputs: dst[row_off+m, 0:w1) = src1[(m / rep1), 0:w1); dst[.., w1:w1+w2) = src2[m, 0:w2)
  * (replaces torch.cat / repeat in critic_module.py:25 and cql.py:142-147). */
 typedef struct OrlkConcatSeg {

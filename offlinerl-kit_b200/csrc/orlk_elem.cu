@@ -383,8 +383,18 @@ k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamG
         if (i >= d.n) continue;
         float p = d.p[i];
         if (d.flags & ORLK_OPT_ADAM) {
-            float gr = 0.f;
-            for (int s = 0; s < d.g_splits; ++s) gr += d.grad[(int64_t)s * d.g_split_stride + i];
+            // fixed-order reduction of the split-K partials, four independent chains so the loads overlap
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+            const float* gp = d.grad + i;
+            int s = 0;
+            for (; s + 4 <= d.g_splits; s += 4) {
+                g0 += gp[(int64_t)s * d.g_split_stride];
+                g1 += gp[(int64_t)(s + 1) * d.g_split_stride];
+                g2 += gp[(int64_t)(s + 2) * d.g_split_stride];
+                g3 += gp[(int64_t)(s + 3) * d.g_split_stride];
+            }
+            for (; s < d.g_splits; ++s) g0 += gp[(int64_t)s * d.g_split_stride];
+            float gr = (g0 + g1) + (g2 + g3);
             if (d.wd != 0.f) gr = fmaf(d.wd, p, gr);
             float m = d.m[i], v = d.v[i];
             m = m + (gr - m) * (1.f - g.beta1);

@@ -1,0 +1,137 @@
+// First-layer ("narrow-K") and head ("narrow-N") kernels for large row counts.
+//
+// The first critic layer has K = obs+act = 14..23 inputs and the heads have 1..12 outputs: these are not GEMM
+// shaped (a 128x128x16 tile would be mostly padding), they are bandwidth-bound streaming kernels over the
+// [M, 256] activation / gradient matrices.  One thread owns one of the 256 wide columns, the narrow operand of a
+// row tile sits in shared memory and is broadcast.  Reference call sites: the first nn.Linear of
+// Critic.backbone (critic_module.py:25-26 -> mlp.py:22) forward and weight gradient; Critic.last weight gradient.
+#include "orlk_common.cuh"
+using namespace orlk;
+
+namespace {
+
+constexpr int NK_MAX = 32;     // max narrow dimension
+constexpr int ROWS_FWD = 32;   // rows per block in the forward kernel
+constexpr int ROWS_WG = 128;   // rows per block (= per partial slot) in the weight-gradient kernel
+
+// Y[g][m][n] = act(b[g][n] + sum_k X[g][m][k] * W[g][n*ldw + k]),   K <= 32;  optional YT[g][n][m]
+__global__ void __launch_bounds__(256)
+k_narrow_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw, int64_t w_gs,
+             const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy, int64_t y_gs,
+             float* __restrict__ YT, int64_t ldyt, int64_t yt_gs, int M, int N, int K, int relu) {
+    __shared__ float xs[ROWS_FWD][NK_MAX + 1];
+    const int g = blockIdx.z;
+    const int m0 = blockIdx.x * ROWS_FWD;
+    const int n = blockIdx.y * 256 + threadIdx.x;
+    const float* Xg = X + g * x_gs;
+    for (int i = threadIdx.x; i < ROWS_FWD * K; i += 256) {
+        const int r = i / K, k = i % K;
+        xs[r][k] = (m0 + r < M) ? __ldg(Xg + (int64_t)(m0 + r) * ldx + k) : 0.f;
+    }
+    float w[NK_MAX];
+    const bool n_ok = n < N;
+#pragma unroll
+    for (int k = 0; k < NK_MAX; ++k) w[k] = (n_ok && k < K) ? __ldg(W + g * w_gs + (int64_t)n * ldw + k) : 0.f;
+    const float bias = (n_ok && b != nullptr) ? __ldg(b + g * b_gs + n) : 0.f;
+    __syncthreads();
+    float yt[ROWS_FWD];
+#pragma unroll
+    for (int r = 0; r < ROWS_FWD; ++r) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < NK_MAX; ++k)
+            if (k < K) acc = fmaf(xs[r][k], w[k], acc);
+        if (relu) acc = fmaxf(acc, 0.f);
+        yt[r] = acc;
+        if (n_ok && m0 + r < M) Y[g * y_gs + (int64_t)(m0 + r) * ldy + n] = acc;
+    }
+    if (YT != nullptr && n_ok) {
+        float* dst = YT + g * yt_gs + (int64_t)n * ldyt + m0;
+        if (m0 + ROWS_FWD <= M && (ldyt % 4) == 0 && (yt_gs % 4) == 0 && aligned16(YT)) {
+#pragma unroll
+            for (int r4 = 0; r4 < ROWS_FWD / 4; ++r4)
+                reinterpret_cast<float4*>(dst)[r4] = make_float4(yt[4 * r4], yt[4 * r4 + 1], yt[4 * r4 + 2], yt[4 * r4 + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < ROWS_FWD; ++r)
+                if (m0 + r < M) dst[r] = yt[r];
+        }
+    }
+}
+
+// Partial sums over a 128-row chunk c (blockIdx.x):
+//   out[g][c][ns][kw]  = sum_m Nar[g][m][ns] * Wide[g][m][kw]       (written at  ns*s_ns + kw*s_kw)
+//   wide_sum[g][c][kw] = sum_m Wide[g][m][kw]                         (optional)
+//   nar_sum[g][c][ns]  = sum_m Nar[g][m][ns]                          (optional)
+__global__ void __launch_bounds__(256)
+k_narrow_wgrad(const float* __restrict__ Wide, int64_t ldw, int64_t w_gs, const float* __restrict__ Nar, int64_t ldn,
+               int64_t n_gs, float* __restrict__ out, int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs,
+               float* __restrict__ wide_sum, int64_t ws_gs, int64_t ws_cs, float* __restrict__ nar_sum, int64_t ns_gs,
+               int64_t ns_cs, int M, int KW, int NS) {
+    __shared__ float ns_s[ROWS_WG][NK_MAX + 1];
+    const int g = blockIdx.z, c = blockIdx.x;
+    const int m0 = c * ROWS_WG;
+    const int kw = blockIdx.y * 256 + threadIdx.x;
+    const int rows = min(ROWS_WG, M - m0);
+    const float* Ng = Nar + g * n_gs;
+    for (int i = threadIdx.x; i < ROWS_WG * NS; i += 256) {
+        const int r = i / NS, j = i % NS;
+        ns_s[r][j] = (r < rows) ? __ldg(Ng + (int64_t)(m0 + r) * ldn + j) : 0.f;
+    }
+    __syncthreads();
+    float acc[NK_MAX];
+#pragma unroll
+    for (int j = 0; j < NK_MAX; ++j) acc[j] = 0.f;
+    float cs = 0.f;
+    if (kw < KW) {
+        const float* wp = Wide + g * w_gs + (int64_t)m0 * ldw + kw;
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r) {
+            const float x = __ldg(wp + (int64_t)r * ldw);
+            cs += x;
+#pragma unroll
+            for (int j = 0; j < NK_MAX; ++j)
+                if (j < NS) acc[j] = fmaf(x, ns_s[r][j], acc[j]);
+        }
+        float* o = out + g * o_gs + (int64_t)c * o_cs + (int64_t)kw * s_kw;
+#pragma unroll
+        for (int j = 0; j < NK_MAX; ++j)
+            if (j < NS) o[(int64_t)j * s_ns] = acc[j];
+        if (wide_sum != nullptr) wide_sum[g * ws_gs + (int64_t)c * ws_cs + kw] = cs;
+    }
+    if (nar_sum != nullptr && blockIdx.y == 0 && threadIdx.x < NS) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += ns_s[r][threadIdx.x];
+        nar_sum[g * ns_gs + (int64_t)c * ns_cs + threadIdx.x] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int orlk_narrow_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
+                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, float* YT, int64_t ldyt, int64_t yt_gs, int M, int N,
+                    int K, int G, int relu, void* stream) {
+    ORLK_REQUIRE(K >= 1 && K <= NK_MAX, "K must be in [1,32]");
+    ORLK_REQUIRE(M > 0 && N > 0 && G > 0, "sizes");
+    dim3 grid((M + ROWS_FWD - 1) / ROWS_FWD, (N + 255) / 256, G);
+    k_narrow_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, YT, ldyt, yt_gs, M, N,
+                                                        K, relu);
+    return check_launch("k_narrow_fwd");
+}
+
+int orlk_narrow_wgrad_chunks(int M) { return (M + ROWS_WG - 1) / ROWS_WG; }
+
+int orlk_narrow_wgrad(const float* Wide, int64_t ldw, int64_t w_gs, const float* Nar, int64_t ldn, int64_t n_gs, float* out,
+                      int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs, float* wide_sum, int64_t ws_gs, int64_t ws_cs,
+                      float* nar_sum, int64_t ns_gs, int64_t ns_cs, int M, int KW, int NS, int G, void* stream) {
+    ORLK_REQUIRE(NS >= 1 && NS <= NK_MAX, "NS must be in [1,32]");
+    ORLK_REQUIRE(M > 0 && KW > 0 && G > 0, "sizes");
+    dim3 grid((M + ROWS_WG - 1) / ROWS_WG, (KW + 255) / 256, G);
+    k_narrow_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(Wide, ldw, w_gs, Nar, ldn, n_gs, out, s_ns, s_kw, o_gs, o_cs, wide_sum,
+                                                          ws_gs, ws_cs, nar_sum, ns_gs, ns_cs, M, KW, NS);
+    return check_launch("k_narrow_wgrad");
+}
+
+}  // extern "C"

@@ -26,7 +26,7 @@ constexpr int B_BYTES = BN_MAX * BK * 4;                  // 32 KB
 constexpr int ONES_BYTES = 16 * BK * 4;                   // 2 KB
 constexpr int TMEM_COLS = 512;
 constexpr int ROWSUM_COL = 256;
-constexpr int NUM_THREADS = 192;                          // warp0 TMA, warp1 MMA, warps2-5 split + epilogue
+constexpr int NUM_THREADS = 320;                          // warp0 TMA, warp1 MMA, warps2-5 split + epilogue, warps6-9 mask
 
 struct TcParams {
     float* C; int64_t ldc, c_gs, c_split_stride;
@@ -124,7 +124,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array keeps the address space known to the compiler: LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ones = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
     uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
@@ -132,6 +133,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint64_t* empty = bars + 2 * STAGES;    // [STAGES]  MMAs that read the stage have completed
     uint64_t* accum = bars + 3 * STAGES;    // accumulator tile complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    float* bias_s = reinterpret_cast<float*>(bars + 3 * STAGES + 2);     // [BN_MAX] bias staged once per CTA
+    uint32_t* mask_s = reinterpret_cast<uint32_t*>(bias_s + BN_MAX);     // [BM][BN_MAX/32] ReLU-mask bits of the tile
+    uint64_t* maskbar = reinterpret_cast<uint64_t*>(mask_s + BM * (BN_MAX / 32));   // mask tile complete (128 arrivals)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int idx = blockIdx.x;
@@ -156,6 +160,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_init(smem_u32(&empty[s]), 1);
         }
         mbar_init(smem_u32(accum), 1);
+        mbar_init(smem_u32(maskbar), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -163,10 +168,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                      "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2 && want_rowsum) {
-        float* o = reinterpret_cast<float*>(ones);
-        for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
-        fence_proxy_async();
+    if (warp >= 2 && warp < 6) {
+        if (want_rowsum) {
+            float* o = reinterpret_cast<float*>(ones);
+            for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
+            fence_proxy_async();
+        }
+        const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs : nullptr;
+        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < p.N) ? __ldg(bg + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -214,6 +223,55 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             umma_commit(smem_u32(&empty[s]));               // frees the stage when these MMAs have completed
         }
         umma_commit(smem_u32(accum));
+    } else if (warp >= 6) {
+        // ------------------------------------------------------------------ ReLU-mask builder (overlaps the mainloop)
+        // Each lane loads float4s (512 contiguous bytes per warp instruction, 8 rows in flight); component e of
+        // 128-column group q gives one ballot word:  bit j of mask_s[row][4q+e]  <=>  aux[m][128q + 4j + e] > 0.
+        if (p.epi == ORLK_EPI_RELU_MASK) {
+            const int w = warp - 6;
+            const float* auxg = p.aux + (int64_t)g * p.aux_gs;
+            const bool vec = (p.ldaux % 4 == 0) && (p.aux_gs % 4 == 0) && aligned16(p.aux) && (p.N % 4 == 0);
+            constexpr int RB = 8;                                   // rows per batch
+            for (int r0 = 0; r0 < 32; r0 += RB) {
+                float4 a[RB][2];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int m = tile_m * BM + w * 32 + r0 + rr;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int n = q * 128 + 4 * lane;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < p.M && n < p.N) {
+                            const float* src = auxg + (int64_t)m * p.ldaux + n;
+                            if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
+                            else {
+                                v.x = __ldg(src);
+                                if (n + 1 < p.N) v.y = __ldg(src + 1);
+                                if (n + 2 < p.N) v.z = __ldg(src + 2);
+                                if (n + 3 < p.N) v.w = __ldg(src + 3);
+                            }
+                        }
+                        a[rr][q] = v;
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int row = w * 32 + r0 + rr;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint32_t b0 = __ballot_sync(0xffffffffu, a[rr][q].x > 0.f);
+                        const uint32_t b1 = __ballot_sync(0xffffffffu, a[rr][q].y > 0.f);
+                        const uint32_t b2 = __ballot_sync(0xffffffffu, a[rr][q].z > 0.f);
+                        const uint32_t b3 = __ballot_sync(0xffffffffu, a[rr][q].w > 0.f);
+                        if (lane == 0) {
+                            uint4* dst = reinterpret_cast<uint4*>(mask_s + row * (BN_MAX / 32) + 4 * q);
+                            *dst = make_uint4(b0, b1, b2, b3);
+                        }
+                    }
+                }
+            }
+            mbar_arrive(smem_u32(maskbar));
+        }
     } else if (warp >= 2) {
         const int t = threadIdx.x - 64;                     // 0..127
         if (PASSES == 3) {
@@ -223,29 +281,45 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(smem_u32(&full[s]), ph);
-                float4* ar = reinterpret_cast<float4*>(a_raw(s));
-                float4* al = reinterpret_cast<float4*>(a_lo(s));
-                float4* br = reinterpret_cast<float4*>(b_raw(s));
-                float4* bl = reinterpret_cast<float4*>(b_lo(s));
-#pragma unroll 4
-                for (int i = t; i < A_BYTES / 16; i += 128) {
-                    float4 v = ar[i], lo;
-                    split_tf32(v, lo);
-                    ar[i] = v;
-                    al[i] = lo;
+                float4* __restrict__ ar = reinterpret_cast<float4*>(a_raw(s));
+                float4* __restrict__ al = reinterpret_cast<float4*>(a_lo(s));
+                float4* __restrict__ br = reinterpret_cast<float4*>(b_raw(s));
+                float4* __restrict__ bl = reinterpret_cast<float4*>(b_lo(s));
+                // A: 1024 float4 -> 8 per thread, all loads issued before the first store
+                {
+                    float4 v[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ar[t + 128 * j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        split_tf32(v[j], lo[j]);
+                        ar[t + 128 * j] = v[j];
+                        al[t + 128 * j] = lo[j];
+                    }
                 }
-#pragma unroll 4
-                for (int i = t; i < nB4; i += 128) {
-                    float4 v = br[i], lo;
-                    split_tf32(v, lo);
-                    br[i] = v;
-                    bl[i] = lo;
+                for (int i0 = 0; i0 < nB4; i0 += 128 * 8) {
+                    float4 v[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = i0 + t + 128 * j;
+                        v[j] = i < nB4 ? br[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = i0 + t + 128 * j;
+                        if (i < nB4) {
+                            split_tf32(v[j], lo[j]);
+                            br[i] = v[j];
+                            bl[i] = lo[j];
+                        }
+                    }
                 }
                 fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(smem_u32(&splitb[s]));
             }
         }
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+        if (p.epi == ORLK_EPI_RELU_MASK) mbar_wait(smem_u32(maskbar), 0);
         mbar_wait(smem_u32(accum), 0);
         tc_fence_after();
         const int q = warp & 3;                             // a warp may only touch TMEM lanes 32*(warp%4) .. +31
@@ -255,11 +329,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         float* C = p.C ? p.C + (int64_t)g * p.c_gs + (int64_t)split * p.c_split_stride + (int64_t)m * p.ldc : nullptr;
         float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + m : nullptr;
-        const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_gs : nullptr;
-        const float* aux = p.aux ? p.aux + (int64_t)g * p.aux_gs + (int64_t)m * p.ldaux : nullptr;
         const bool vec_ok = (p.N % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
                             (p.c_split_stride % 4 == 0);
-        const bool aux_vec = aux != nullptr && (p.ldaux % 4 == 0) && aligned16(p.aux) && (p.aux_gs % 4 == 0);
         for (int c0 = 0; c0 < p.N; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
@@ -268,27 +339,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = c0 + j;
-                float val = __uint_as_float(v[j]);
-                if (bias != nullptr && n < p.N) val += __ldg(bias + n);
-                x[j] = val;
+                x[j] = __uint_as_float(v[j]) + bias_s[n < BN_MAX ? n : 0];
             }
             if (p.epi == ORLK_EPI_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-            } else if (p.epi == ORLK_EPI_RELU_MASK && row_ok) {
+            } else if (p.epi == ORLK_EPI_RELU_MASK) {
+                // columns c0 .. c0+31 live in 128-column group q = c0/128 at lanes 8*((c0/32)%4) .. +7
+                const uint4 mb = *reinterpret_cast<const uint4*>(mask_s + row * (BN_MAX / 32) + 4 * (c0 >> 7));
+                const int sh = 8 * ((c0 >> 5) & 3);
+                const uint32_t m0 = mb.x >> sh, m1 = mb.y >> sh, m2 = mb.z >> sh, m3 = mb.w >> sh;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const int n = c0 + 4 * j4;
-                    if (n >= p.N) break;
-                    float a4[4];
-                    if (aux_vec) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(aux + n));
-                        a4[0] = a.x; a4[1] = a.y; a4[2] = a.z; a4[3] = a.w;
-                    } else {
-                        for (int e = 0; e < 4; ++e) a4[e] = (n + e < p.N) ? __ldg(aux + n + e) : 0.f;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) x[4 * j4 + e] = a4[e] > 0.f ? x[4 * j4 + e] : 0.f;
+                for (int jj = 0; jj < 8; ++jj) {
+                    x[4 * jj + 0] = ((m0 >> jj) & 1u) ? x[4 * jj + 0] : 0.f;
+                    x[4 * jj + 1] = ((m1 >> jj) & 1u) ? x[4 * jj + 1] : 0.f;
+                    x[4 * jj + 2] = ((m2 >> jj) & 1u) ? x[4 * jj + 2] : 0.f;
+                    x[4 * jj + 3] = ((m3 >> jj) & 1u) ? x[4 * jj + 3] : 0.f;
                 }
             }
             if (row_ok) {
@@ -372,7 +438,7 @@ extern "C" int orlk_sizeof_tc_gemm(void) { return (int)sizeof(OrlkTcGemm); }
 static size_t tc_smem_bytes(int passes) {
     const int stages = passes == 3 ? 2 : 4;
     const int stage_bytes = (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1);
-    return (size_t)stages * stage_bytes + ONES_BYTES + 256 + 1024;
+    return (size_t)stages * stage_bytes + ONES_BYTES + 256 + BN_MAX * 4 + BM * (BN_MAX / 32) * 4 + 64 + 1024;
 }
 
 // Opt in to > 48 KB of dynamic shared memory once, outside any stream capture.

@@ -190,6 +190,18 @@ class MlpRun:
                 self.HT[l - 1] = rt.zeros(G, lays[l - 1].out_dim, self.Mt)
         if any(self.tc_dgrad):
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
+        # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
+        big = M >= TC_MIN_ROWS
+        self.narrow0 = big and lays[0].layout == "oi" and lays[0].in_dim <= 32 and store == "P"
+        self.narrow_head = big and self.has_head and lays[n_hidden].layout == "oi" and self.NS <= 32
+        self.chunks = L.load().orlk_narrow_wgrad_chunks(M)
+        self.w0_part = self.b0_part = self.hw_part = self.hb_part = None
+        if need_grad and self.narrow0:
+            self.w0_part = rt.zeros(self.chunks, G, lays[0].out_dim, lays[0].in_dim)
+            self.b0_part = rt.zeros(self.chunks, G, lays[0].out_dim)
+        if need_grad and self.narrow_head:
+            self.hw_part = rt.zeros(self.chunks, G, self.NS, lays[n_hidden].in_dim)
+            self.hb_part = rt.zeros(self.chunks, G, self.NS)
 
     def h(self, l: int, g: int) -> Mat:
         return Mat.of(self.H[l][g])
@@ -221,6 +233,13 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
                 passes=run.tc, epi=L.EPI_RELU, C=_grouped(run.H[l], M, N, N), c_gs=M * N,
                 CT=_grouped(run.HT[l], N, M, run.Mt) if run.HT[l] is not None else None, ct_gs=N * run.Mt,
                 bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
+            continue
+        if l == 0 and run.narrow0 and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
+            ht = run.HT[0]
+            args = (X[0].ptr, X[0].ld, 0, ps.w(0, 0, run.store), lay.in_dim, lay.w_gs, ps.b(0, 0, run.store), lay.b_gs,
+                    run.H[0].data_ptr(), lay.out_dim, M * lay.out_dim, ht.data_ptr() if ht is not None else None, run.Mt,
+                    lay.out_dim * run.Mt, M, lay.out_dim, lay.in_dim, G, 1)
+            plan.add(f"{tag}.fwd0.narrow", lambda args=args: L.call("orlk_narrow_fwd", *args, rt.cur))
             continue
         probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store,
                              YT=run.ht(l, g)) for g in range(G)]
@@ -308,10 +327,27 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     n_l = run.nh + (1 if run.has_head else 0)
     layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
     splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
+    grad_src = {}
     for l in range(n_l):
         cfg, s = layout[l]
-        assert s <= gb.n_slots, (s, gb.n_slots)
         lay = ps.layers[l]
+        if l == 0 and run.w0_part is not None and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
+            o, i = lay.out_dim, lay.in_dim
+            args = (run.dZ[0].data_ptr(), o, M * o, X[0].ptr, X[0].ld, 0, run.w0_part.data_ptr(), 1, i, o * i, G * o * i,
+                    run.b0_part.data_ptr(), o, G * o, None, 0, 0, M, o, i, G)
+            plan.add(f"{tag}.wgrad0.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur))
+            grad_src[(0, "w")] = (run.w0_part.data_ptr(), o * i, G * o * i, run.chunks)
+            grad_src[(0, "b")] = (run.b0_part.data_ptr(), o, G * o, run.chunks)
+            continue
+        if l == run.nh and run.hw_part is not None:
+            K, NS = lay.in_dim, run.NS
+            args = (run.H[l - 1].data_ptr(), K, M * K, run.dOut.data_ptr(), NS, M * NS, run.hw_part.data_ptr(), K, 1, NS * K,
+                    G * NS * K, None, 0, 0, run.hb_part.data_ptr(), NS, G * NS, M, K, NS, G)
+            plan.add(f"{tag}.wgrad_head.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur))
+            grad_src[(l, "w")] = (run.hw_part.data_ptr(), NS * K, G * NS * K, run.chunks)
+            grad_src[(l, "b")] = (run.hb_part.data_ptr(), NS, G * NS, run.chunks)
+            continue
+        assert s <= gb.n_slots, (s, gb.n_slots)
         if cfg == -1:
             # dW[o,i] = sum_m dZ^T[o,m] * H^T[i,m]; bias gradient = row sums of dZ^T (a ones-tile MMA)
             plan.add(f"{tag}.wgrad{l}.tc", rt.tc_gemm(
@@ -328,4 +364,4 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
         plan.add(f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG))
     if small:
         plan.add(f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL))
-    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l)), groups_ptr))
+    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l), grad_src=grad_src), groups_ptr))

@@ -303,9 +303,13 @@ def wgrad_problem(ps: ParamSet, gb: GradBuf, l: int, g: int, X: Mat, dY: Mat, k_
 
 
 def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polyak: bool,
-               layers: Optional[Sequence[int]] = None) -> List[AdamT]:
-    """One Adam(+polyak) descriptor per weight / bias tensor (all members of a tensor when they are contiguous)."""
+               layers: Optional[Sequence[int]] = None, grad_src: Optional[Dict] = None) -> List[AdamT]:
+    """One Adam(+polyak) descriptor per weight / bias tensor (all members of a tensor when they are contiguous).
+
+    ``grad_src[(layer, 'w'|'b')] = (ptr of member 0, member stride, split stride, n splits)`` overrides the GradBuf
+    location for tensors whose partial gradients were written elsewhere (the narrow-layer kernels)."""
     out = []
+    grad_src = grad_src or {}
     idx = range(len(ps.layers)) if layers is None else layers
     for l in idx:
         lay, s = ps.layers[l], splits_per_layer[l]
@@ -317,9 +321,14 @@ def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polya
             bo = lay.b_off + (0 if contiguous else g * lay.b_gs)
             for off, n, is_w in ((wo, nw, True), (bo, nb, False)):
                 keep_t = is_w and ps.WT is not None and l in ps.wt_layers and not contiguous
+                src = grad_src.get((l, "w" if is_w else "b"))
+                if src is not None:
+                    gptr, gsplits, gstride = src[0] + 4 * g * src[1], src[3], src[2]
+                else:
+                    gptr, gsplits, gstride = gb.ptr(off), s, gb.stride
                 out.append(AdamT(p=ps._ptr(ps.P, off), n=n, group=ps.group_ids[g], m=ps._ptr(ps.Mo, off),
                                  v=ps._ptr(ps.Vo, off), tgt=ps._ptr(ps.T, off) if (polyak and ps.T is not None) else 0,
-                                 grad=gb.ptr(off), g_splits=s, g_split_stride=gb.stride,
+                                 grad=gptr, g_splits=gsplits, g_split_stride=gstride,
                                  flags=L.OPT_ADAM | (L.OPT_POLYAK if polyak and ps.T is not None else 0),
                                  pT=ps._ptr(ps.WT, off) if keep_t else 0, cols=lay.in_dim if keep_t else 1))
     return out

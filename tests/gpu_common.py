@@ -77,7 +77,8 @@ def make_buffer(g: Golden, device="cuda:0"):
     return buf, data
 
 
-def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0", precision=None):
+def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0", precision=None,
+                     elementwise=True):
     """Engine vs golden (= the real reference): index draw + gather bit-exact, then losses and parameters."""
     m = g.meta
     policy = build_policy(m, device)
@@ -107,7 +108,7 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
         for k in ref:
             assert abs(out[k] - ref[k]) <= tol * max(1.0, abs(ref[k])), (t, k, out[k], ref[k])
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
-        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol)
+        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol if elementwise else 10 * lr_atol)
     post = g.group("post")
     if post and n_steps == m["n_steps"]:
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}

@@ -20,7 +20,9 @@ def test_cql_matches_reference(name, precision):
 def test_cql_fast_mode_tolerance(name):
     """Single-pass TF32 tensor-core mode, reported separately (north_star): losses within 2e-3 relative."""
     from tests.gpu_common import run_golden_steps
-    run_golden_steps(Golden(name), tol=2e-3, verbose=True, precision="tf32")
+    # Adam turns a rounding-level sign flip of a tiny gradient into a 2*lr parameter change, so single elements
+    # are only bounded by a few lr in this mode; losses and per-tensor norms are held to 2e-3.
+    run_golden_steps(Golden(name), tol=2e-3, verbose=True, precision="tf32", elementwise=False)
 
 
 def test_cql_eager_equals_graph():

@@ -481,3 +481,40 @@ def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
     errs.append(_tc_case(rt, 3, 200, 64, 96, passes, L.EPI_NONE, 1, True, True, True, 6))          # narrow N, K not /128
     errs.append(_tc_case(rt, 1, 1000, 208, 224, passes, L.EPI_RELU, 1, True, False, False, 7))     # N = 208 (13 x 16)
     print(f"passes={passes}: relative errors {['%.2e' % e for e in errs]}")
+
+
+# ------------------------------------------------------------------------------------------------ narrow layers (large M)
+def test_narrow_fwd_and_wgrad(rt):
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(9)
+    for (G, M, N, K) in [(2, 7936, 256, 23), (1, 1000, 200, 14), (3, 333, 40, 32)]:
+        X = torch.randn(M, K, generator=gen)
+        W = torch.randn(G, N, K, generator=gen)
+        b = torch.randn(G, N, generator=gen)
+        Xd, Wd, bd = X.to(DEV), W.to(DEV), b.to(DEV)
+        Mt = (M + 3) // 4 * 4
+        Y, YT = torch.zeros(G, M, N, device=DEV), torch.zeros(G, N, Mt, device=DEV)
+        L.call("orlk_narrow_fwd", Xd.data_ptr(), K, 0, Wd.data_ptr(), K, N * K, bd.data_ptr(), N, Y.data_ptr(), N, M * N,
+               YT.data_ptr(), Mt, N * Mt, M, N, K, G, 1, rt.cur)
+        ref = (torch.einsum("mk,gnk->gmn", X.double(), W.double()) + b.double()[:, None, :]).clamp(min=0)
+        _close(Y, ref, msg=f"narrow fwd {G,M,N,K}")
+        assert torch.equal(YT[:, :, :M], Y.transpose(1, 2).contiguous()), "narrow fwd transposed copy"
+        # first-layer weight gradient: dW[g][n][k] = sum_m dZ[g][m][n] X[m][k], db[g][n] = sum_m dZ[g][m][n]
+        dZ = torch.randn(G, M, N, generator=gen)
+        dZd = dZ.to(DEV)
+        ch = rt.lib.orlk_narrow_wgrad_chunks(M)
+        wp, bp = torch.zeros(ch, G, N, K, device=DEV), torch.zeros(ch, G, N, device=DEV)
+        L.call("orlk_narrow_wgrad", dZd.data_ptr(), N, M * N, Xd.data_ptr(), K, 0, wp.data_ptr(), 1, K, N * K, G * N * K,
+               bp.data_ptr(), N, G * N, None, 0, 0, M, N, K, G, rt.cur)
+        _close(wp.sum(0), torch.einsum("gmn,mk->gnk", dZ.double(), X.double()), rtol=1e-5, atol=1e-4, msg="narrow wgrad W0")
+        _close(bp.sum(0), dZ.double().sum(1), rtol=1e-5, atol=1e-4, msg="narrow wgrad b0")
+    # head weight gradient: dW[g][ns][k] = sum_m dOut[g][m][ns] H[g][m][k], db[g][ns] = sum_m dOut[g][m][ns]
+    for (G, M, K, NS) in [(2, 7936, 256, 1), (1, 2000, 256, 12)]:
+        H, dO = torch.randn(G, M, K, generator=gen), torch.randn(G, M, NS, generator=gen)
+        Hd, dOd = H.to(DEV), dO.to(DEV)
+        ch = rt.lib.orlk_narrow_wgrad_chunks(M)
+        wp, bp = torch.zeros(ch, G, NS, K, device=DEV), torch.zeros(ch, G, NS, device=DEV)
+        L.call("orlk_narrow_wgrad", Hd.data_ptr(), K, M * K, dOd.data_ptr(), NS, M * NS, wp.data_ptr(), K, 1, NS * K,
+               G * NS * K, None, 0, 0, bp.data_ptr(), NS, G * NS, M, K, NS, G, rt.cur)
+        _close(wp.sum(0), torch.einsum("gmn,gmk->gnk", dO.double(), H.double()), rtol=1e-5, atol=1e-4, msg="head wgrad W")
+        _close(bp.sum(0), dO.double().sum(1), rtol=1e-5, atol=1e-4, msg="head wgrad b")
