@@ -247,7 +247,7 @@ typedef struct OrlkAdamDesc {
     int32_t g_splits;
     int32_t group;
     float wd;
-    int32_t block_start; /* prefix sum of ceil(n / 1024) */
+    int32_t block_start; /* prefix sum of ceil(n / 256) */
     int32_t flags;       /* ORLK_OPT_ADAM | ORLK_OPT_POLYAK */
     int32_t cols;        /* with pT: the tensor is [n/cols, cols] row-major ...                     */
     float* pT;           /* ... and pT receives its transpose [cols, n/cols] (K-major dgrad operand) */

@@ -10,18 +10,20 @@ namespace {
 constexpr int MAX_NS = 16;
 
 // ------------------------------------------------------------------------------------------ skinny layers
-__global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
-                             int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
-                             int64_t y_gs, int M, int K, int NS, int vec) {
+template <int NST>
+__global__ void __launch_bounds__(256)
+k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
+             int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
+             int64_t y_gs, int M, int K, int NS, int vec) {
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
     const float* x = X + g * x_gs + (int64_t)m * ldx;
     const float* w = W + g * w_gs;
-    float acc[MAX_NS];
+    float acc[NST];
 #pragma unroll
-    for (int n = 0; n < MAX_NS; ++n) acc[n] = 0.f;
+    for (int n = 0; n < NST; ++n) acc[n] = 0.f;
     if (vec) {      // K % 4 == 0 and 16-byte aligned rows: 128-bit loads, all of a row's loads in flight at once
         const float4* x4 = reinterpret_cast<const float4*>(x);
         const int K4 = K >> 2;
@@ -29,7 +31,7 @@ __global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x
         for (int k = lane; k < K4; k += 32) {
             const float4 xv = x4[k];
 #pragma unroll
-            for (int n = 0; n < MAX_NS; ++n)
+            for (int n = 0; n < NST; ++n)
                 if (n < NS) {
                     const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * ldw) + k);
                     acc[n] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[n]))));
@@ -39,16 +41,18 @@ __global__ void k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x
         for (int k = lane; k < K; k += 32) {
             const float xv = x[k];
 #pragma unroll
-            for (int n = 0; n < MAX_NS; ++n)
+            for (int n = 0; n < NST; ++n)
                 if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + k), acc[n]);
         }
     }
 #pragma unroll
-    for (int n = 0; n < MAX_NS; ++n)
+    for (int n = 0; n < NST; ++n)
         if (n < NS) acc[n] = warp_sum(acc[n]);
     if (lane == 0) {
         float* y = Y + g * y_gs + (int64_t)m * ldy;
-        for (int n = 0; n < NS; ++n) y[n] = acc[n] + (b ? b[g * b_gs + n] : 0.f);
+#pragma unroll
+        for (int n = 0; n < NST; ++n)
+            if (n < NS) y[n] = acc[n] + (b ? b[g * b_gs + n] : 0.f);
     }
 }
 
@@ -358,7 +362,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------ fused Adam + polyak
-constexpr int ADAM_BLOCK_ELEMS = 1024;
+constexpr int ADAM_BLOCK_ELEMS = 256;
 
 __global__ void __launch_bounds__(256)
 k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamGroup* __restrict__ groups) {
@@ -430,7 +434,11 @@ int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, i
     dim3 grid((M + wpb - 1) / wpb, G);
     const int vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && (x_gs % 4 == 0) && (w_gs % 4 == 0) && aligned16(X) &&
                     aligned16(W);
-    k_skinny_fwd<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (NS == 1) k_skinny_fwd<1><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 4) k_skinny_fwd<4><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 8) k_skinny_fwd<8><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else k_skinny_fwd<16><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
     return check_launch("k_skinny_fwd");
 }
 

@@ -11,11 +11,11 @@ using namespace orlk;
 namespace {
 
 constexpr int NK_MAX = 32;     // max narrow dimension
-constexpr int ROWS_FWD = 32;   // rows per block in the forward kernel
+constexpr int ROWS_FWD = 16;   // rows per block in the forward kernel
 constexpr int ROWS_WG = 128;   // rows per block (= per partial slot) in the weight-gradient kernel
 
 // Y[g][m][n] = act(b[g][n] + sum_k X[g][m][k] * W[g][n*ldw + k]),   K <= 32;  optional YT[g][n][m]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_narrow_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw, int64_t w_gs,
              const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy, int64_t y_gs,
              float* __restrict__ YT, int64_t ldyt, int64_t yt_gs, int M, int N, int K, int relu) {
@@ -63,18 +63,22 @@ k_narrow_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float
 //   out[g][c][ns][kw]  = sum_m Nar[g][m][ns] * Wide[g][m][kw]       (written at  ns*s_ns + kw*s_kw)
 //   wide_sum[g][c][kw] = sum_m Wide[g][m][kw]                         (optional)
 //   nar_sum[g][c][ns]  = sum_m Nar[g][m][ns]                          (optional)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_narrow_wgrad(const float* __restrict__ Wide, int64_t ldw, int64_t w_gs, const float* __restrict__ Nar, int64_t ldn,
                int64_t n_gs, float* __restrict__ out, int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs,
                float* __restrict__ wide_sum, int64_t ws_gs, int64_t ws_cs, float* __restrict__ nar_sum, int64_t ns_gs,
                int64_t ns_cs, int M, int KW, int NS) {
+    // block = (256 wide columns) x (4 row quarters); the quarters are combined through shared memory
     __shared__ float ns_s[ROWS_WG][NK_MAX + 1];
+    __shared__ float red[3][256];
     const int g = blockIdx.z, c = blockIdx.x;
     const int m0 = c * ROWS_WG;
-    const int kw = blockIdx.y * 256 + threadIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 256 + tx;
+    const int kw = blockIdx.y * 256 + tx;
     const int rows = min(ROWS_WG, M - m0);
     const float* Ng = Nar + g * n_gs;
-    for (int i = threadIdx.x; i < ROWS_WG * NS; i += 256) {
+    for (int i = tid; i < ROWS_WG * NS; i += 1024) {
         const int r = i / NS, j = i % NS;
         ns_s[r][j] = (r < rows) ? __ldg(Ng + (int64_t)(m0 + r) * ldn + j) : 0.f;
     }
@@ -83,26 +87,38 @@ k_narrow_wgrad(const float* __restrict__ Wide, int64_t ldw, int64_t w_gs, const 
 #pragma unroll
     for (int j = 0; j < NK_MAX; ++j) acc[j] = 0.f;
     float cs = 0.f;
+    const int r_lo = ty * (ROWS_WG / 4), r_hi = min(rows, r_lo + ROWS_WG / 4);
     if (kw < KW) {
         const float* wp = Wide + g * w_gs + (int64_t)m0 * ldw + kw;
 #pragma unroll 8
-        for (int r = 0; r < rows; ++r) {
+        for (int r = r_lo; r < r_hi; ++r) {
             const float x = __ldg(wp + (int64_t)r * ldw);
             cs += x;
 #pragma unroll
             for (int j = 0; j < NK_MAX; ++j)
                 if (j < NS) acc[j] = fmaf(x, ns_s[r][j], acc[j]);
         }
-        float* o = out + g * o_gs + (int64_t)c * o_cs + (int64_t)kw * s_kw;
-#pragma unroll
-        for (int j = 0; j < NK_MAX; ++j)
-            if (j < NS) o[(int64_t)j * s_ns] = acc[j];
-        if (wide_sum != nullptr) wide_sum[g * ws_gs + (int64_t)c * ws_cs + kw] = cs;
     }
-    if (nar_sum != nullptr && blockIdx.y == 0 && threadIdx.x < NS) {
+    // combine the four row quarters in a fixed order (deterministic)
+    float* o = out + g * o_gs + (int64_t)c * o_cs + (int64_t)kw * s_kw;
+    for (int j = 0; j <= NS; ++j) {
+        float v = cs;
+#pragma unroll
+        for (int jj = 0; jj < NK_MAX; ++jj)
+            if (j < NS && jj == j) v = acc[jj];
+        __syncthreads();
+        if (ty > 0) red[ty - 1][tx] = v;
+        __syncthreads();
+        if (ty == 0 && kw < KW) {
+            v = ((v + red[0][tx]) + red[1][tx]) + red[2][tx];
+            if (j < NS) o[(int64_t)j * s_ns] = v;
+            else if (wide_sum != nullptr) wide_sum[g * ws_gs + (int64_t)c * ws_cs + kw] = v;
+        }
+    }
+    if (nar_sum != nullptr && blockIdx.y == 0 && tid < NS) {
         float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += ns_s[r][threadIdx.x];
-        nar_sum[g * ns_gs + (int64_t)c * ns_cs + threadIdx.x] = s;
+        for (int r = 0; r < rows; ++r) s += ns_s[r][tid];
+        nar_sum[g * ns_gs + (int64_t)c * ns_cs + tid] = s;
     }
 }
 
@@ -129,7 +145,7 @@ int orlk_narrow_wgrad(const float* Wide, int64_t ldw, int64_t w_gs, const float*
     ORLK_REQUIRE(NS >= 1 && NS <= NK_MAX, "NS must be in [1,32]");
     ORLK_REQUIRE(M > 0 && KW > 0 && G > 0, "sizes");
     dim3 grid((M + ROWS_WG - 1) / ROWS_WG, (KW + 255) / 256, G);
-    k_narrow_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(Wide, ldw, w_gs, Nar, ldn, n_gs, out, s_ns, s_kw, o_gs, o_cs, wide_sum,
+    k_narrow_wgrad<<<grid, dim3(256, 4), 0, (cudaStream_t)stream>>>(Wide, ldw, w_gs, Nar, ldn, n_gs, out, s_ns, s_kw, o_gs, o_cs, wide_sum,
                                                           ws_gs, ws_cs, nar_sum, ns_gs, ns_cs, M, KW, NS);
     return check_launch("k_narrow_wgrad");
 }
