@@ -230,6 +230,30 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
                          float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream);
 
+/* Generic TD loss (sac.py:93-108, td3bc.py:87-104, iql.py:101-115, edac.py:124-134):
+ *   y = r + gamma (1-d) [ min_{e2<E2} tq[e2] - (use_alpha ? alpha * lp_next : 0) ]
+ *   out_losses[e] = mean_b (q[e][b]-y)^2,  *out_sum = sum_e (optional),  dq[e][b] = 2 (q[e][b]-y)/B,  y_out optional. */
+int orlk_td_loss(const float* q, int64_t q_es, int E, const float* tq, int64_t tq_es, int E2, const float* lp_next,
+                 const float* scalars, int use_alpha, const float* rew, const float* term, int B, float gamma, float* dq,
+                 int64_t dq_es, float* y_out, float* out_losses, float* out_sum, void* stream);
+/* IQL expectile value loss (iql.py:82-98): q = min(tq[0], tq[1]); writes dv[b], qmin[b], out_loss[0]. */
+int orlk_iql_v_loss(const float* tq, int64_t tq_es, const float* v, int B, float expectile, float* dv, float* qmin,
+                    float* out_loss, void* stream);
+/* IQL advantage-weighted actor loss (iql.py:118-130; bounded DiagGaussian with state-independent sigma,
+ * dist_module.py:65-76): z = pre-tanh mu head [B,A]; writes dz [B,A], dsigma [A] (gradient of sigma_param), loss. */
+int orlk_iql_actor_loss(const float* z, int64_t ldz, const float* sigma_param, const float* act, int64_t lda, const float* qmin,
+                        const float* v, int B, int A, float temperature, float max_mu, float* dz, int64_t lddz, float* dsigma,
+                        float* out_loss, void* stream);
+/* Deterministic actor head (actor_module.py:46-50) with TD3 target-policy smoothing (td3bc.py:90-91) when eps != NULL. */
+int orlk_det_actor_fwd(const float* z, int64_t ldz, const float* eps, int M, int A, float max_action, float policy_noise,
+                       float noise_clip, float* act, int64_t ld_act, const float* obs, int64_t ld_obs, int obs_dim, float* xout,
+                       int64_t ld_x, void* stream);
+/* TD3+BC actor loss (td3bc.py:107-112): writes dq[b] = -lambda/B, dabc[b,i] = 2(a-a_data)/(B A), out_loss[0]. */
+int orlk_td3bc_actor_loss(const float* q, const float* a, int64_t lda, const float* a_data, int64_t ldd, int B, int A,
+                          float bc_alpha, float* dq, float* dabc, int64_t ldg, float* out_loss, void* stream);
+int orlk_det_actor_bwd(const float* a, int64_t lda, const float* dA0, int64_t ld0, const float* dA1, int64_t ld1, int M, int A,
+                       float max_action, float* dz, int64_t lddz, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 /* Fused (split-K partial reduction) + Adam + polyak over a list of tensors (torch.optim.Adam as constructed in
  * run_example/run_cql.py:92-94; _sync_weight sac.py:60-64).  For element i of tensor d:

@@ -93,6 +93,12 @@ _PROTOS = {
     "orlk_sac_actor_loss": [_P, _L, _I, _P, _I, _P, _I, _I, _F, _P, _I, _P, _P, _L, _P, _P, _P],
     "orlk_cql_critic_loss": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _I, _F, _P, _P, _I, _P,
                              _P, _L, _P, _P],
+    "orlk_td_loss": [_P, _L, _I, _P, _L, _I, _P, _P, _I, _P, _P, _I, _F, _P, _L, _P, _P, _P, _P],
+    "orlk_iql_v_loss": [_P, _L, _P, _I, _F, _P, _P, _P, _P],
+    "orlk_iql_actor_loss": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _F, _F, _P, _L, _P, _P, _P],
+    "orlk_det_actor_fwd": [_P, _L, _P, _I, _I, _F, _F, _F, _P, _L, _P, _L, _I, _P, _L, _P],
+    "orlk_td3bc_actor_loss": [_P, _P, _L, _P, _L, _I, _I, _F, _P, _P, _L, _P, _P],
+    "orlk_det_actor_bwd": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _P, _L, _P],
     "orlk_adam_step": [_P, _I, _I, _P, _P],
     "orlk_step_end": [_P, C.c_uint, _P, _P],
 }

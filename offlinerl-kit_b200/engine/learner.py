@@ -166,11 +166,11 @@ class MlpRun:
     """
 
     def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P",
-                 tc_passes: int = 0):
+                 tc_passes: int = 0, members: Optional[int] = None):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
         self.tc = tc_passes if M >= TC_MIN_ROWS else 0
         self.Mt = (M + 3) // 4 * 4
-        G = ps.G
+        self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
         lays = ps.layers
         self.H = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)]
         self.dZ = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)] if need_grad else None
@@ -223,7 +223,7 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
 
 def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
     """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
-    ps, G, M = run.ps, run.ps.G, run.M
+    ps, G, M = run.ps, run.G, run.M
     for l in range(run.nh):
         lay = ps.layers[l]
         if run.tc_fwd[l]:
@@ -249,7 +249,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
 
 
 def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
-    ps, G, l = run.ps, run.ps.G, run.nh
+    ps, G, l = run.ps, run.G, run.nh
     lay = ps.layers[l]
     hin = run.H[l - 1]
     K = lay.in_dim
@@ -262,7 +262,7 @@ def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
 
 def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     """dZ[last hidden] = (dOut W_head) * relu'(H[last hidden])  (+ its transpose for a tensor-core wgrad)."""
-    ps, G, l = run.ps, run.ps.G, run.nh
+    ps, G, l = run.ps, run.G, run.nh
     lay = ps.layers[l]
     K = lay.in_dim
     hmask = run.H[l - 1]
@@ -275,7 +275,7 @@ def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
 
 def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1) -> None:
     """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to."""
-    ps, G, M = run.ps, run.ps.G, run.M
+    ps, G, M = run.ps, run.G, run.M
     for l in range(run.nh - 1, down_to - 1, -1):
         lay = ps.layers[l]
         if run.tc_dgrad[l]:
@@ -310,6 +310,11 @@ def wgrad_layout(ps: ParamSet, n_layers: int, M: int, tc_layers: Sequence[bool] 
     return out
 
 
+def polyak_descs(ps: ParamSet) -> List[AdamT]:
+    """Target-only update tgt <- (1-tau) tgt + tau p over the whole ParamSet (one descriptor per member block)."""
+    return [AdamT(p=ps._ptr(ps.P, 0), n=ps.total, group=ps.group_ids[0], tgt=ps._ptr(ps.T, 0), flags=L.OPT_POLYAK)]
+
+
 def make_gradbuf(rt: Runtime, ps: ParamSet, runs: Sequence["MlpRun"]) -> GradBuf:
     """GradBuf with enough split slots for the weight-gradient reductions of the given passes."""
     slots = 1
@@ -322,7 +327,7 @@ def make_gradbuf(rt: Runtime, ps: ParamSet, runs: Sequence["MlpRun"]) -> GradBuf
 def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: GradBuf, groups_ptr: int, tag: str,
                     polyak: bool) -> None:
     """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update."""
-    ps, G, M = run.ps, run.ps.G, run.M
+    ps, G, M = run.ps, run.G, run.M
     big, small = [], []
     n_l = run.nh + (1 if run.has_head else 0)
     layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
@@ -364,4 +369,5 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
         plan.add(f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG))
     if small:
         plan.add(f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL))
-    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l), grad_src=grad_src), groups_ptr))
+    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l), grad_src=grad_src,
+                                               members=range(G)), groups_ptr))

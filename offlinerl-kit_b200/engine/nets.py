@@ -303,7 +303,8 @@ def wgrad_problem(ps: ParamSet, gb: GradBuf, l: int, g: int, X: Mat, dY: Mat, k_
 
 
 def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polyak: bool,
-               layers: Optional[Sequence[int]] = None, grad_src: Optional[Dict] = None) -> List[AdamT]:
+               layers: Optional[Sequence[int]] = None, grad_src: Optional[Dict] = None,
+               members: Optional[Sequence[int]] = None) -> List[AdamT]:
     """One Adam(+polyak) descriptor per weight / bias tensor (all members of a tensor when they are contiguous).
 
     ``grad_src[(layer, 'w'|'b')] = (ptr of member 0, member stride, split stride, n splits)`` overrides the GradBuf
@@ -314,7 +315,7 @@ def adam_descs(ps: ParamSet, gb: GradBuf, splits_per_layer: Sequence[int], polya
     for l in idx:
         lay, s = ps.layers[l], splits_per_layer[l]
         contiguous = (lay.w_gs == lay.w_numel)          # ensemble tensors: members back to back
-        for g in ([0] if contiguous else range(ps.G)):
+        for g in ([0] if contiguous else (members if members is not None else range(ps.G))):
             nw = lay.w_numel * (ps.G if contiguous else 1)
             nb = lay.out_dim * (ps.G if contiguous else 1)
             wo = lay.w_off + (0 if contiguous else g * lay.w_gs)

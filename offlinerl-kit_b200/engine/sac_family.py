@@ -273,3 +273,71 @@ class CQLLearner(TwinCriticLearner):
             res["loss/cql_alpha"] = float(out[LS_CQL_ALPHA_LOSS])
             res["cql_alpha"] = float(out[LS_CQL_ALPHA])
         return res
+
+
+class SACLearner(TwinCriticLearner):
+    """policy/model_free/sac.py:88-140 (MOPO's learner): critics -> actor (with the updated critics) -> alpha -> polyak.
+
+    The polyak update is fused into the critics' Adam launch: the target networks are last read by the TD target
+    earlier in the same step, so updating them right after the critic step is equivalent to the reference's
+    end-of-step ``_sync_weight``."""
+
+    def __init__(self, policy, batch_size: int, seed: int = 0):
+        super().__init__(policy, batch_size)
+        rt, B, A = self.rt, self.B, self.A
+        self.seed = seed
+        self.push_groups()
+        self._make_stage()
+        self.n_normal = 2 * B * A
+        self.noise = rt.zeros(self.n_normal)
+        self.noise_views = {"eps_next": self.noise[:B * A].view(B, A), "eps_actor": self.noise[B * A:].view(B, A)}
+        self.eps_actor = self.noise_views["eps_actor"]
+        self._built = False
+
+    def _build(self) -> None:
+        rt, B, O, A = self.rt, self.B, self.O, self.A
+        self._alloc_actor_phase()
+        self.run_actor_n = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=False)
+        self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        self.run_critic = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True)
+        self.Xd, self.Xt = rt.zeros(B, O + A), rt.zeros(B, O + A)
+        self.lp_next = rt.zeros(B)
+        self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
+        self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
+        plan = Plan(rt, "sac")
+        self._emit_noise(plan, self.n_normal, 0, 0.0, 1.0)
+        obs2 = Mat.of(self.obs2)
+        obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
+        Xd, Xt = Mat.of(self.Xd), Mat.of(self.Xt)
+        plan.add("Q.concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
+        cr = self.run_critic
+        emit_forward(rt, plan, cr, [Xd, Xd], "Q.critic")
+        an = self.run_actor_n
+        emit_forward(rt, plan, an, [nobs], "Q.actor_next")
+        self._emit_sample(plan, "Q.sample_next", an.out[0], 0, 1, self.noise_views["eps_next"], B, Xt, self.lp_next, nobs)
+        emit_forward(rt, plan, self.run_target, [Xt, Xt], "Q.target")
+        targs = (cr.out.data_ptr(), B, 2, self.run_target.out.data_ptr(), B, 2, self.lp_next.data_ptr(),
+                 self.scalars.data_ptr(), 1, self.rew.data_ptr(), self.term.data_ptr(), B, self.gamma, cr.dOut.data_ptr(), B,
+                 None, self.loss_dev.data_ptr() + 4 * LS_C1, None)
+        plan.add("Q.loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+        emit_head_dgrad(rt, plan, cr, "Q.critic")
+        emit_hidden_dgrad(rt, plan, cr, "Q.critic")
+        emit_wgrad_adam(rt, plan, cr, [Xd, Xd], self.gb_critic, self.groups_ptr, "Q.critic", polyak=True)
+        self._emit_actor_update(plan, clamp01=True)
+        self.finish_ops(plan, self.group_mask(self.g_actor, self.g_c1, self.g_c2, self.g_alpha))
+        self.plans["step"] = plan
+        self._built = True
+
+    def step(self, batch, noise=None) -> Dict[str, float]:
+        self.bind_batch(batch)
+        if not self._built:
+            self._build()
+        self.set_noise(noise)
+        self.sync_lr()
+        self.refresh()
+        out = self.run("step")
+        res = {"loss/actor": float(out[LS_ACTOR]), "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
+        if self.auto_alpha:
+            res["loss/alpha"] = float(out[LS_ALPHA_LOSS])
+            res["alpha"] = float(out[LS_ALPHA])
+        return res

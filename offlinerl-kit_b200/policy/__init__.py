@@ -1,5 +1,7 @@
 from .base_policy import BasePolicy
 from .sac import SACPolicy
 from .cql import CQLPolicy
+from .td3bc import TD3BCPolicy
+from .iql import IQLPolicy
 
-__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy"]
+__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy", "TD3BCPolicy", "IQLPolicy"]
