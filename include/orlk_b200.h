@@ -254,6 +254,34 @@ int orlk_td3bc_actor_loss(const float* q, const float* a, int64_t lda, const flo
 int orlk_det_actor_bwd(const float* a, int64_t lda, const float* dA0, int64_t ld0, const float* dA1, int64_t ld1, int M, int A,
                        float max_action, float* dz, int64_t lddz, void* stream);
 
+/* ------------------------------------------------------- MOPO ensemble dynamics */
+/* scaler.transform on [obs | act] (utils/scaler.py:25-31): X[s] = ([obs[s] | act[s]] - mu) / std. */
+int orlk_dyn_input(const float* obs, int64_t ld_obs, const float* act, int64_t ld_act, const float* mu, const float* sd, int S,
+                   int O, int A, float* X, int64_t ldx, void* stream);
+/* Per-member bootstrap batch: dst[e][r][0:w) = src[idx[e*idx_ld + r0 + r]][0:w) (ensemble_dynamics.py:134,144,186-187). */
+int orlk_gather_rows(const float* src, int64_t ld_src, int w, const int64_t* idx, int64_t idx_ld, int64_t r0, int E, int R,
+                     float* dst, int64_t ld_dst, int64_t dst_es, void* stream);
+/* partial[c] = scale * sum of squares of chunk c (4096 elements): the weight-decay term of the reported loss. */
+int orlk_sumsq_chunks(int64_t n);
+int orlk_sumsq(const float* x, int64_t n, float scale, float* partial, void* stream);
+/* Gaussian NLL + soft-clamped logvar (ensemble_dynamics.py:193-201, dynamics_module.py:19-29): out [E][Bn][2D] = mean|raw,
+ * y [E][Bn][D].  Writes dout (same shape as out), dmax[D], dmin[D] (incl. the +-coef terms) and out_loss[0]. */
+int orlk_dyn_nll(const float* out, const float* y, int E, int Bn, int D, const float* max_lv, const float* min_lv, float coef,
+                 const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss, void* stream);
+/* Holdout MSE of the mean head per member (ensemble_dynamics.py:210-217); y [Bn][D] is shared by the members. */
+int orlk_dyn_val_mse(const float* out, const float* y, int E, int Bn, int D, float* mse, void* stream);
+/* Imagination epilogue (ensemble_dynamics.py:43-77): term_kind 0 halfcheetah, 1 hopper, 2 walker2d, 3 never
+ * (utils/termination_fns.py).  Reference-stream mode: noise [E][S][D] float64 and midx [S] are the reference's two
+ * NumPy draws.  Device mode (noise == NULL / midx == NULL): noise32 [S][D] normals for the chosen member and
+ * pick_u [S] uniforms in [0,1) selecting elites[floor(u * n_elites)]. */
+int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, const float* min_lv, const float* obs,
+                  int64_t ld_obs, const double* noise, const int* midx, const float* noise32, const float* pick_u,
+                  const int* elites, int n_elites, int term_kind, float penalty_coef, float* next_obs, float* reward,
+                  float* raw_reward, float* penalty, unsigned char* terminal, void* stream);
+/* Stable compaction of rows with drop[i] == 0 (mopo.py:69-73); *count_out = number of survivors. */
+int orlk_compact_rows(const unsigned char* drop, int S, const float* src, int64_t ld_src, int w, float* dst, int64_t ld_dst,
+                      int* count_out, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 /* Fused (split-K partial reduction) + Adam + polyak over a list of tensors (torch.optim.Adam as constructed in
  * run_example/run_cql.py:92-94; _sync_weight sac.py:60-64).  For element i of tensor d:

@@ -99,6 +99,13 @@ _PROTOS = {
     "orlk_det_actor_fwd": [_P, _L, _P, _I, _I, _F, _F, _F, _P, _L, _P, _L, _I, _P, _L, _P],
     "orlk_td3bc_actor_loss": [_P, _P, _L, _P, _L, _I, _I, _F, _P, _P, _L, _P, _P],
     "orlk_det_actor_bwd": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _P, _L, _P],
+    "orlk_dyn_input": [_P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _L, _P],
+    "orlk_gather_rows": [_P, _L, _I, _P, _L, _L, _I, _I, _P, _L, _L, _P],
+    "orlk_sumsq_chunks": [_L], "orlk_sumsq": [_P, _L, _F, _P, _P],
+    "orlk_dyn_nll": [_P, _P, _I, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P],
+    "orlk_dyn_val_mse": [_P, _P, _I, _I, _I, _P, _P],
+    "orlk_dyn_step": [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P],
+    "orlk_compact_rows": [_P, _I, _P, _L, _I, _P, _L, _P, _P],
     "orlk_adam_step": [_P, _I, _I, _P, _P],
     "orlk_step_end": [_P, C.c_uint, _P, _P],
 }

@@ -1,0 +1,177 @@
+"""BaseDynamics / EnsembleDynamics facades (reference: dynamics/base_dynamics.py:8-23, dynamics/ensemble_dynamics.py).
+
+Same constructor and methods as the reference (``step``, ``train``, ``learn``, ``validate``, ``select_elites``, ``save``,
+``load``, ``format_samples_for_training``); all model arithmetic runs in engine/dynamics.py on the device.  ``train``
+keeps the (scaled) training set, the targets and the per-member bootstrap index matrix resident in HBM and gathers
+each mini-batch with a kernel, instead of the reference's > 1 GB host fancy-index per epoch.
+"""
+import os
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .utils.scaler import StandardScaler
+
+
+class BaseDynamics:
+    def __init__(self, model: nn.Module, optim: torch.optim.Optimizer) -> None:
+        self.model, self.optim = model, optim
+
+    def step(self, obs: np.ndarray, action: np.ndarray):
+        raise NotImplementedError
+
+
+class EnsembleDynamics(BaseDynamics):
+    def __init__(self, model: nn.Module, optim: torch.optim.Optimizer, scaler: StandardScaler,
+                 terminal_fn: Callable[[np.ndarray, np.ndarray, np.ndarray], np.ndarray], penalty_coef: float = 0.0,
+                 uncertainty_mode: str = "aleatoric") -> None:
+        super().__init__(model, optim)
+        self.scaler, self.terminal_fn = scaler, terminal_fn
+        self._penalty_coef, self._uncertainty_mode = penalty_coef, uncertainty_mode
+        if uncertainty_mode != "aleatoric":
+            raise L.OrlkError("only uncertainty_mode='aleatoric' (MOPO) is implemented by the CUDA engine")
+        self._engine = None
+        self._scaler_dev = None
+        self.rng = "numpy"       # "numpy": the reference's two host draws per step; "device": Philox on the GPU
+
+    # ------------------------------------------------------------------ engine plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine.dynamics import DynamicsEngine
+            self._engine = DynamicsEngine(self.model, self.optim)
+        return self._engine
+
+    def _dev(self, a, dtype=torch.float32) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(a)).to(device=self.engine.dev, dtype=dtype)
+
+    def _scaler_tensors(self):
+        key = (id(self.scaler.mu), id(self.scaler.std))
+        if self._scaler_dev is None or self._scaler_dev[0] != key:
+            self._scaler_dev = (key, self._dev(np.asarray(self.scaler.mu, np.float32).reshape(-1)),
+                                self._dev(np.asarray(self.scaler.std, np.float32).reshape(-1)))
+        return self._scaler_dev[1], self._scaler_dev[2]
+
+    # ------------------------------------------------------------------ imagination
+    def step_device(self, obs: torch.Tensor, act: torch.Tensor, noise64=None, midx=None):
+        """One imagined step on device tensors -> (next_obs, reward, terminal(uint8), raw_reward, penalty) on the device."""
+        eng = self.engine
+        S = obs.shape[0]
+        mu, sd = self._scaler_tensors()
+        kind = getattr(self.terminal_fn, "device_kind", None)
+        n32 = pick = elites = None
+        if noise64 is None:
+            if self.rng == "numpy":           # ensemble_dynamics.py:48 and dynamics_module.py:118, in that order
+                noise64 = self._dev(np.random.normal(size=(eng.E, S, eng.D)), torch.float64)
+                midx = self._dev(self.model.random_elite_idxs(S), torch.int32)
+            else:
+                buf = torch.empty(S * eng.D + S, dtype=torch.float32, device=eng.dev)
+                L.call("orlk_philox_fill", buf.data_ptr(), S * eng.D, S, 0.0, 1.0, 0x5eed, eng.philox_counter.data_ptr(), None,
+                       eng.rt.cur)
+                L.call("orlk_step_end", eng.groups_ptr, 0, eng.philox_counter.data_ptr(), eng.rt.cur)
+                n32, pick = buf[:S * eng.D], buf[S * eng.D:]
+                elites = self.model.elites.data.to(device=eng.dev, dtype=torch.int32)
+        out = eng.imagine(obs, act, mu, sd, 3 if kind is None else kind, self._penalty_coef, noise64, midx, n32, pick, elites)
+        return out
+
+    @torch.no_grad()
+    def step(self, obs: np.ndarray, action: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, Dict]:
+        obs_d, act_d = self._dev(obs), self._dev(action)
+        nobs, rew, term, raw, pen = self.step_device(obs_d, act_d)
+        self.engine.rt.sync()
+        next_obs, reward = nobs.cpu().numpy(), rew.cpu().numpy()
+        if getattr(self.terminal_fn, "device_kind", None) is None:
+            terminal = self.terminal_fn(obs, action, next_obs)       # unknown predicate: evaluate it on the host
+        else:
+            terminal = term.cpu().numpy().astype(bool)
+        info = {"raw_reward": raw.cpu().numpy()}
+        if self._penalty_coef:
+            info["penalty"] = pen.cpu().numpy()
+        return next_obs, reward, terminal, info
+
+    # ------------------------------------------------------------------ training
+    def format_samples_for_training(self, data: Dict) -> Tuple[np.ndarray, np.ndarray]:
+        inputs = np.concatenate((data["observations"], data["actions"]), axis=-1)
+        targets = np.concatenate((data["next_observations"] - data["observations"], data["rewards"]), axis=-1)
+        return inputs, targets
+
+    def train(self, data: Dict, logger, max_epochs: Optional[float] = None, max_epochs_since_update: int = 5,
+              batch_size: int = 256, holdout_ratio: float = 0.2, logvar_loss_coef: float = 0.01) -> None:
+        inputs, targets = self.format_samples_for_training(data)
+        data_size = inputs.shape[0]
+        holdout_size = min(int(data_size * holdout_ratio), 1000)
+        train_size = data_size - holdout_size
+        train_split, holdout_split = torch.utils.data.random_split(range(data_size), (train_size, holdout_size))
+        train_inputs, train_targets = inputs[train_split.indices], targets[train_split.indices]
+        holdout_inputs, holdout_targets = inputs[holdout_split.indices], targets[holdout_split.indices]
+        self.scaler.fit(train_inputs)
+        E = self.model.num_ensemble
+        x_dev, y_dev = self._dev(self.scaler.transform(train_inputs)), self._dev(train_targets)
+        hx_dev, hy_dev = self._dev(self.scaler.transform(holdout_inputs)), self._dev(holdout_targets)
+        holdout_losses = [1e10 for _ in range(E)]
+        data_idxes = np.random.randint(train_size, size=[E, train_size])
+
+        def shuffle_rows(arr):
+            order = np.argsort(np.random.uniform(size=arr.shape), axis=-1)
+            return arr[np.arange(arr.shape[0])[:, None], order]
+
+        epoch = cnt = 0
+        logger.log("Training dynamics:")
+        while True:
+            epoch += 1
+            idx_dev = torch.as_tensor(data_idxes, dtype=torch.int64).to(self.engine.dev)
+            train_loss = self.engine.learn(x_dev, y_dev, idx_dev, batch_size, logvar_loss_coef)
+            new_holdout_losses = self.engine.validate(hx_dev, hy_dev)
+            holdout_loss = (np.sort(new_holdout_losses)[:self.model.num_elites]).mean()
+            logger.logkv("loss/dynamics_train_loss", train_loss)
+            logger.logkv("loss/dynamics_holdout_loss", holdout_loss)
+            logger.set_timestep(epoch)
+            logger.dumpkvs(exclude=["policy_training_progress"])
+            data_idxes = shuffle_rows(data_idxes)
+            improved = []
+            for i, (new, old) in enumerate(zip(new_holdout_losses, holdout_losses)):
+                if (old - new) / old > 0.01:
+                    improved.append(i)
+                    holdout_losses[i] = new
+            if improved:
+                self.model.update_save(improved)
+                cnt = 0
+            else:
+                cnt += 1
+            if cnt >= max_epochs_since_update or (max_epochs and epoch >= max_epochs):
+                break
+        elites = self.select_elites(holdout_losses)
+        self.model.set_elites(elites)
+        self.model.load_save()
+        self.save(logger.model_dir)
+        self.model.eval()
+        logger.log("elites:{} , holdout loss: {}".format(elites, (np.sort(holdout_losses)[:self.model.num_elites]).mean()))
+
+    def learn(self, inputs: np.ndarray, targets: np.ndarray, batch_size: int = 256, logvar_loss_coef: float = 0.01) -> float:
+        """Reference signature: inputs [E, n, in], targets [E, n, out] already gathered per member."""
+        self.model.train()
+        E, n = inputs.shape[0], inputs.shape[1]
+        x = self._dev(np.asarray(inputs, np.float32).reshape(E * n, -1))
+        y = self._dev(np.asarray(targets, np.float32).reshape(E * n, -1))
+        idx = (torch.arange(E, device=x.device).view(E, 1) * n + torch.arange(n, device=x.device).view(1, n)).contiguous()
+        return self.engine.learn(x, y, idx, batch_size, logvar_loss_coef)
+
+    @torch.no_grad()
+    def validate(self, inputs: np.ndarray, targets: np.ndarray) -> List[float]:
+        self.model.eval()
+        return self.engine.validate(self._dev(inputs), self._dev(targets))
+
+    def select_elites(self, metrics: List) -> List[int]:
+        order = sorted(range(len(metrics)), key=lambda i: metrics[i])
+        return order[:self.model.num_elites]
+
+    def save(self, save_path: str) -> None:
+        torch.save(self.model.state_dict(), os.path.join(save_path, "dynamics.pth"))
+        self.scaler.save_scaler(save_path)
+
+    def load(self, load_path: str) -> None:
+        self.model.load_state_dict(torch.load(os.path.join(load_path, "dynamics.pth"), map_location=self.model.device))
+        self.scaler.load_scaler(load_path)

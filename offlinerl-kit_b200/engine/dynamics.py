@@ -1,0 +1,211 @@
+"""Device engine for the MOPO ensemble dynamics model: training step, holdout validation and one-step imagination.
+
+Reference: dynamics/ensemble_dynamics.py (learn :178-208, validate :210-217, step :28-79) on
+modules/dynamics_module.py:32-119 (E x [in -> hidden x n Swish -> 2*(obs+1)], learned log-variance bounds).
+The E members live in one ParamSet ('io' layout, members contiguous per tensor); every layer of every member is
+one problem of a grouped GEMM launch; Swish and its derivative are GEMM epilogues.
+"""
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .core import AdamT, GP, Mat, Plan, Runtime, get_runtime
+from .learner import Learner, N_LOSS
+from .nets import GradBuf, ParamSet, adam_descs, dgrad_problem, fwd_problem, pick_cfg, wgrad_problem, wgrad_splits
+
+
+class DynRun:
+    """Buffers of one forward (+backward) pass of the ensemble over M rows per member."""
+
+    def __init__(self, rt: Runtime, ps: ParamSet, M: int, need_grad: bool):
+        self.ps, self.M = ps, M
+        E, nl = ps.G, len(ps.layers)
+        self.nh = nl - 1
+        self.H = [rt.zeros(E, M, ps.layers[l].out_dim) for l in range(self.nh)]
+        self.Z = [rt.zeros(E, M, ps.layers[l].out_dim) for l in range(self.nh)] if need_grad else None
+        self.OUT = rt.zeros(E, M, ps.layers[-1].out_dim)
+        self.dZ = [rt.zeros(E, M, ps.layers[l].out_dim) for l in range(self.nh)] if need_grad else None
+        self.dOUT = rt.zeros(E, M, ps.layers[-1].out_dim) if need_grad else None
+
+
+def emit_dyn_forward(rt: Runtime, plan: Plan, run: DynRun, X: Callable[[int], Mat], tag: str) -> None:
+    ps, E, M = run.ps, run.ps.G, run.M
+    for l in range(run.nh + 1):
+        last = l == run.nh
+        probs = []
+        for e in range(E):
+            xin = X(e) if l == 0 else Mat.of(run.H[l - 1][e])
+            yout = Mat.of(run.OUT[e]) if last else Mat.of(run.H[l][e])
+            z = Mat.of(run.Z[l][e]) if (not last and run.Z is not None) else None
+            probs.append(fwd_problem(ps, l, e, xin, yout, L.EPI_NONE if last else L.EPI_SWISH, Z=z))
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * E, ps.layers[l].out_dim)))
+
+
+class DynamicsEngine(Learner):
+    def __init__(self, model, optim):
+        super().__init__(model.device)
+        rt = self.rt
+        self.model = model
+        layers = list(model.backbones) + [model.output_layer]
+        self.ps = ParamSet.from_ensemble(rt, "dynamics", layers,
+                                         extra={"max_logvar": model.max_logvar, "min_logvar": model.min_logvar})
+        self.E = self.ps.G
+        self.in_dim = self.ps.layers[0].in_dim
+        self.D = self.ps.layers[-1].out_dim // 2
+        self.wd = [float(getattr(lay, "weight_decay", 0.0)) for lay in layers]
+        self.g = self.add_group(optim)
+        self.ps.group_ids = [self.g]
+        self.push_groups()
+        self._learn_plans: Dict[int, Tuple[Plan, dict]] = {}
+        self._fwd_runs: Dict[int, Tuple[DynRun, Plan, torch.Tensor]] = {}
+        n_dec = sum(self.rt.lib.orlk_sumsq_chunks(self.E * lay.w_numel) for lay in self.ps.layers)
+        self.decay_partials = rt.zeros(max(n_dec, 1))
+        self.n_decay = n_dec
+        self.dmax, self.dmin = rt.zeros(self.D), rt.zeros(self.D)
+
+    # ------------------------------------------------------------------ training step
+    def _learn_plan(self, Bn: int):
+        if Bn in self._learn_plans:
+            return self._learn_plans[Bn]
+        rt, ps, E, D = self.rt, self.ps, self.E, self.D
+        run = DynRun(rt, ps, Bn, need_grad=True)
+        X = rt.zeros(E, Bn, self.in_dim)
+        Y = rt.zeros(E, Bn, D)
+        nl = len(ps.layers)
+        cfgs, splits = [], []
+        for l in range(nl):
+            lay = ps.layers[l]
+            cfg = L.CFG_SMALL
+            BM, BN, _ = L.CFG_TILES[cfg]
+            tiles = (-(-lay.in_dim // BM)) * (-(-lay.out_dim // BN)) * E
+            splits.append(wgrad_splits(tiles, Bn, cfg))
+            cfgs.append(cfg)
+        gb = GradBuf(rt, ps, max(splits))
+        plan = Plan(rt, f"dyn.learn{Bn}")
+        emit_dyn_forward(rt, plan, run, lambda e: Mat.of(X[e]), "D")
+        # weight-decay term of the reported loss: sum_l wd_l * 0.5 * sum W_l^2
+        off = 0
+        for l, lay in enumerate(ps.layers):
+            n = E * lay.w_numel
+            args = (ps._ptr(ps.P, lay.w_off), n, 0.5 * self.wd[l], self.decay_partials.data_ptr() + 4 * off)
+            plan.add(f"D.decay{l}", lambda args=args: L.call("orlk_sumsq", *args, rt.cur))
+            off += rt.lib.orlk_sumsq_chunks(n)
+        self._coef_dev = rt.zeros(1)
+        largs = [run.OUT.data_ptr(), Y.data_ptr(), E, Bn, D, ps.extra_ptr("max_logvar"), ps.extra_ptr("min_logvar"), 0.01,
+                 self.decay_partials.data_ptr(), self.n_decay, run.dOUT.data_ptr(), self.dmax.data_ptr(), self.dmin.data_ptr(),
+                 self.loss_dev.data_ptr()]
+        state = {"coef": 0.01}
+
+        def loss_op():
+            largs[7] = state["coef"]
+            L.call("orlk_dyn_nll", *largs, rt.cur)
+        plan.add("D.loss", loss_op)
+        # backward: dH_last = (dOUT W_out^T) * swish'(Z_last), then down the stack
+        for l in range(run.nh, 0, -1):
+            probs = []
+            for e in range(E):
+                dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
+                probs.append(dgrad_problem(ps, l, e, dy, Mat.of(run.dZ[l - 1][e]), L.EPI_DSWISH, Mat.of(run.Z[l - 1][e])))
+            plan.add(f"D.dgrad{l}", rt.gemm(probs, pick_cfg(Bn * E, ps.layers[l].in_dim)))
+        probs = []
+        for l in range(nl):
+            for e in range(E):
+                xin = Mat.of(X[e]) if l == 0 else Mat.of(run.H[l - 1][e])
+                dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
+                probs.append(wgrad_problem(ps, gb, l, e, xin, dy, splits[l]))
+        plan.add("D.wgrad", rt.gemm(probs, L.CFG_SMALL))
+        descs = adam_descs(ps, gb, splits, polyak=False)
+        # weight decay enters the gradient as wd_l * W_l (d/dW of wd * 0.5 * sum W^2); biases are not decayed
+        k = 0
+        for l in range(nl):
+            descs[k].wd = self.wd[l]
+            k += 2
+        for name, gbuf in (("max_logvar", self.dmax), ("min_logvar", self.dmin)):
+            o = ps.extra[name][0]
+            descs.append(AdamT(p=ps._ptr(ps.P, o), n=D, group=self.g, m=ps._ptr(ps.Mo, o), v=ps._ptr(ps.Vo, o),
+                               grad=gbuf.data_ptr(), g_splits=1, g_split_stride=D))
+        plan.add("D.adam", rt.adam(descs, self.groups_ptr))
+        gp = C.c_void_p(self.groups_ptr)
+        plan.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
+        self._learn_plans[Bn] = (plan, dict(X=X, Y=Y, run=run, state=state))
+        return self._learn_plans[Bn]
+
+    def learn(self, src_x: torch.Tensor, src_y: torch.Tensor, idx: torch.Tensor, batch_size: int, coef: float) -> float:
+        """One pass over idx [E, n] (row ids into src_x [N,in] / src_y [N,D]) in mini-batches of ``batch_size``."""
+        rt, E = self.rt, self.E
+        n = idx.shape[1]
+        nb = -(-n // batch_size)
+        losses = torch.zeros(nb, dtype=torch.float32, device=self.dev)
+        self.sync_lr()
+        for b in range(nb):
+            r0 = b * batch_size
+            Bn = min(batch_size, n - r0)
+            plan, st = self._learn_plan(Bn)
+            st["state"]["coef"] = float(coef)
+            X, Y = st["X"], st["Y"]
+            L.call("orlk_gather_rows", src_x.data_ptr(), src_x.stride(0), self.in_dim, idx.data_ptr(), idx.stride(0), r0, E, Bn,
+                   X.data_ptr(), self.in_dim, Bn * self.in_dim, rt.cur)
+            L.call("orlk_gather_rows", src_y.data_ptr(), src_y.stride(0), self.D, idx.data_ptr(), idx.stride(0), r0, E, Bn,
+                   Y.data_ptr(), self.D, Bn * self.D, rt.cur)
+            if self.use_graph and abs(coef - 0.01) < 1e-12:
+                plan.launch()
+            else:
+                plan.run_eager()       # (a non-default logvar coefficient is a launch argument, not graph state)
+            L.call("orlk_memcpy_d2d_async", losses.data_ptr() + 4 * b, self.loss_dev.data_ptr(), 4, rt.cur)
+        return float(losses.cpu().numpy().astype(np.float64).mean())
+
+    # ------------------------------------------------------------------ inference
+    def _forward(self, x: torch.Tensor) -> DynRun:
+        """Ensemble forward on a shared [S, in] device input (already scaled)."""
+        S = x.shape[0]
+        self._forward_alloc(S)
+        run, plan, xbuf = self._fwd_runs[S]
+        if x.data_ptr() != xbuf.data_ptr():
+            xbuf.copy_(x)
+        plan.run_eager()
+        return run
+
+    def input_buffer(self, S: int) -> torch.Tensor:
+        self._forward_alloc(S)
+        return self._fwd_runs[S][2]
+
+    def _forward_alloc(self, S: int) -> None:
+        if S not in self._fwd_runs:
+            if len(self._fwd_runs) > 8:
+                self._fwd_runs.clear()
+            run = DynRun(self.rt, self.ps, S, need_grad=False)
+            xbuf = self.rt.zeros(S, self.in_dim)
+            plan = Plan(self.rt, f"dyn.fwd{S}")
+            xm = Mat.of(xbuf)
+            emit_dyn_forward(self.rt, plan, run, lambda e: xm, "F")
+            self._fwd_runs[S] = (run, plan, xbuf)
+
+    def validate(self, x: torch.Tensor, y: torch.Tensor) -> List[float]:
+        run = self._forward(x)
+        mse = torch.zeros(self.E, dtype=torch.float32, device=self.dev)
+        L.call("orlk_dyn_val_mse", run.OUT.data_ptr(), y.data_ptr(), self.E, x.shape[0], self.D, mse.data_ptr(), self.rt.cur)
+        return list(mse.cpu().numpy())
+
+    def imagine(self, obs: torch.Tensor, act: torch.Tensor, mu: torch.Tensor, sd: torch.Tensor, term_kind: int,
+                penalty_coef: float, noise64: Optional[torch.Tensor], midx: Optional[torch.Tensor],
+                noise32: Optional[torch.Tensor], pick_u: Optional[torch.Tensor], elites: Optional[torch.Tensor]):
+        """One imagined transition for S device-resident states; returns device tensors."""
+        rt, S, O = self.rt, obs.shape[0], obs.shape[1]
+        A = act.shape[1]
+        self._forward_alloc(S)
+        xbuf = self._fwd_runs[S][2]
+        L.call("orlk_dyn_input", obs.data_ptr(), obs.stride(0), act.data_ptr(), act.stride(0), mu.data_ptr(), sd.data_ptr(), S,
+               O, A, xbuf.data_ptr(), self.in_dim, rt.cur)
+        run = self._forward(xbuf)
+        nobs = torch.empty(S, O, dtype=torch.float32, device=self.dev)
+        rew, raw, pen = (torch.empty(S, 1, dtype=torch.float32, device=self.dev) for _ in range(3))
+        term = torch.empty(S, 1, dtype=torch.uint8, device=self.dev)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        L.call("orlk_dyn_step", run.OUT.data_ptr(), self.E, S, self.D, self.ps.extra_ptr("max_logvar"),
+               self.ps.extra_ptr("min_logvar"), obs.data_ptr(), obs.stride(0), ptr(noise64), ptr(midx), ptr(noise32), ptr(pick_u),
+               ptr(elites), int(elites.numel()) if elites is not None else 0, term_kind, float(penalty_coef), nobs.data_ptr(),
+               rew.data_ptr(), raw.data_ptr(), pen.data_ptr(), term.data_ptr(), rt.cur)
+        return nobs, rew, term, raw, pen

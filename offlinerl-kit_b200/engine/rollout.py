@@ -1,0 +1,96 @@
+"""Device-resident model rollouts for MOPO (reference: policy/model_based/mopo.py:45-79 + sac.py:79-86 +
+dynamics/ensemble_dynamics.py:28-79).  The reference ping-pongs every imagined step through the host (50 MB of model
+outputs per step, 6.3 M float64 normals on one core); here only the survivor count (4 bytes) crosses per step and the
+transitions are copied out once at the end."""
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .core import Mat, Plan, get_runtime
+from .learner import MlpRun, emit_forward, linears_of
+from .nets import ParamSet
+
+
+class RolloutEngine:
+    def __init__(self, policy):
+        self.policy = policy
+        self.dyn = policy.dynamics
+        self.rt = get_runtime(policy.actor.device)
+        self.dev = self.rt.device
+        eng = getattr(policy, "_engine", None)
+        self._own_ps = None
+        if eng is not None:
+            self.actor_ps = eng.actor_ps            # share the learner's arena: the rollout sees the trained weights
+        else:
+            self._own_ps = self.actor_ps = ParamSet.from_linear_members(self.rt, "actor", [linears_of(policy.actor)], fuse_last=2)
+        self.nh = len(self.actor_ps.layers) - 1
+        self.O = self.actor_ps.layers[0].in_dim
+        self.A = self.actor_ps.layers[-1].out_dim // 2
+        self._plans: Dict[int, tuple] = {}
+        self.count_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.philox_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.tc_passes = getattr(eng, "tc_passes", 3) if eng is not None else 3
+
+    def _actor_plan(self, S: int):
+        if S not in self._plans:
+            if len(self._plans) > 8:
+                self._plans.clear()
+            run = MlpRun(self.rt, self.actor_ps, S, self.nh, need_grad=False, tc_passes=self.tc_passes)
+            obs = torch.zeros(S, self.O, dtype=torch.float32, device=self.dev)
+            plan = Plan(self.rt, f"rollout.actor{S}")
+            emit_forward(self.rt, plan, run, [Mat.of(obs)], "R.actor")
+            self._plans[S] = (run, plan, obs)
+        return self._plans[S]
+
+    def run(self, init_obss: np.ndarray, length: int, noise: Optional[Dict[str, List[np.ndarray]]] = None):
+        rt, O, A = self.rt, self.O, self.A
+        dyn = self.dyn
+        E, D = dyn.engine.E, dyn.engine.D
+        if getattr(dyn.terminal_fn, "device_kind", None) is None:
+            raise L.OrlkError("device rollouts need a termination function with a device_kind (utils/termination_fns.py)")
+        eng = getattr(self.policy, "_engine", None)
+        if eng is not None and eng.actor_ps is not self.actor_ps:
+            # the learner was created after this engine and has re-homed the actor's parameters in its own arena
+            self.actor_ps = eng.actor_ps
+            self.tc_passes = eng.tc_passes
+            self._plans.clear()
+        self.actor_ps.refresh_wt()
+        cur = torch.as_tensor(init_obss, dtype=torch.float32).to(self.dev).contiguous()
+        outs = {k: [] for k in ("obss", "next_obss", "actions", "rewards", "terminals")}
+        n_total, t = 0, 0
+        for t in range(length):
+            S = cur.shape[0]
+            run, plan, obs_buf = self._actor_plan(S)
+            obs_buf.copy_(cur)
+            plan.run_eager()
+            if noise is not None:
+                eps = torch.as_tensor(noise["eps"][t], dtype=torch.float32).to(self.dev).contiguous()
+            else:
+                eps = torch.empty(S, A, dtype=torch.float32, device=self.dev)
+                L.call("orlk_philox_fill", eps.data_ptr(), S * A, 0, 0.0, 1.0, 0xac7, self.philox_counter.data_ptr(), None, rt.cur)
+                L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
+            act = torch.empty(S, A, dtype=torch.float32, device=self.dev)
+            L.call("orlk_tanh_gauss_sample", run.out.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), S, A, act.data_ptr(), A, None, None,
+                   0, 0, None, 0, rt.cur)
+            n64 = midx = None
+            if noise is not None:
+                n64 = torch.as_tensor(noise["normal"][t], dtype=torch.float64).to(self.dev).contiguous()
+                midx = torch.as_tensor(noise["midx"][t], dtype=torch.int32).to(self.dev).contiguous()
+            nobs, rew, term, raw, pen = dyn.step_device(obs_buf, act, n64, midx)
+            for k, v in zip(outs, (obs_buf.clone(), nobs, act, rew, term)):
+                outs[k].append(v)
+            n_total += S
+            nxt = torch.empty_like(nobs)
+            L.call("orlk_compact_rows", term.data_ptr(), S, nobs.data_ptr(), O, O, nxt.data_ptr(), O, self.count_dev.data_ptr(),
+                   rt.cur)
+            rt.sync()
+            alive = int(self.count_dev.item())
+            if alive == 0:
+                break
+            cur = nxt[:alive]
+        res = {k: torch.cat(v, 0).cpu().numpy() for k, v in outs.items()}
+        res["terminals"] = res["terminals"].astype(bool)
+        return res, {"num_transitions": n_total, "reward_mean": float(res["rewards"].astype(np.float64).mean())}

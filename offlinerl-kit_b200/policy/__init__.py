@@ -3,5 +3,6 @@ from .sac import SACPolicy
 from .cql import CQLPolicy
 from .td3bc import TD3BCPolicy
 from .iql import IQLPolicy
+from .mopo import MOPOPolicy
 
-__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy", "TD3BCPolicy", "IQLPolicy"]
+__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy", "TD3BCPolicy", "IQLPolicy", "MOPOPolicy"]

@@ -1,0 +1,90 @@
+"""GPU: MOPO ensemble dynamics (learn / validate / step) and MOPOPolicy.rollout vs golden vectors from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import Golden, initial_state, assert_stats_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def _build_dynamics(m, state, mu, std, term):
+    from offlinerlkit_b200.modules import EnsembleDynamicsModel
+    from offlinerlkit_b200.dynamics import EnsembleDynamics
+    from offlinerlkit_b200.utils.scaler import StandardScaler
+    from offlinerlkit_b200.utils import termination_fns as T
+    model = EnsembleDynamicsModel(m["O"], m["A"], m["hidden"] if "hidden" in m and m["algo"] == "dynamics" else m["dyn_hidden"],
+                                  num_ensemble=m["E"], num_elites=m["n_elites"], weight_decays=m["weight_decays"], device=DEV)
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    assert not unexpected
+    optim = torch.optim.Adam(model.parameters(), lr=m.get("lr", 1e-3))
+    fn = {"halfcheetah": T.termination_fn_halfcheetah, "hopper": T.termination_fn_hopper, "walker2d": T.termination_fn_walker2d}[m["term"]]
+    return EnsembleDynamics(model, optim, StandardScaler(mu, std), fn, penalty_coef=m["penalty_coef"])
+
+
+@pytest.mark.parametrize("name", ["dynamics_small", "dynamics_hc"])
+def test_dynamics_learn_validate_step(name):
+    from offlinerlkit_b200.synthetic import make_dataset
+    g = Golden(name)
+    m = g.meta
+    d = make_dataset(m["n_data"], m["O"], m["A"], seed=m["data_seed"])
+    x = np.concatenate([d["observations"], d["actions"]], axis=-1)
+    y = np.concatenate([d["next_observations"] - d["observations"], d["rewards"].reshape(-1, 1)], axis=-1)
+    mu, std = g["scaler_mu"], g["scaler_std"]
+    xs = (x - mu) / std
+    dyn = _build_dynamics(m, initial_state(m), mu, std, m["term"])
+    boot = g["boot"]
+    loss = dyn.learn(xs[boot], y[boot], batch_size=m["B"])
+    assert loss == pytest.approx(float(g["learn_loss"]), rel=TOL)
+    sd = {k: v.detach().cpu() for k, v in dyn.model.state_dict().items()}
+    assert_stats_close(sd, g.group("stats"), tol=TOL, lr_atol=2.5 * m["lr"])
+    val = dyn.validate(xs[:m["holdout"]], y[:m["holdout"]])
+    assert rel_err(val, g["val"]) < TOL
+    # imagination step: the facade consumes np.random exactly like the reference (normal then choice)
+    np.random.seed(11)
+    nobs, rew, term, info = dyn.step(g["step_obs"], g["step_act"])
+    assert rel_err(nobs, g["step_next_obs"]) < TOL and rel_err(rew, g["step_reward"]) < TOL
+    assert np.array_equal(term, g["step_terminal"])
+    assert rel_err(info["penalty"], g["step_penalty"]) < TOL and rel_err(info["raw_reward"], g["step_raw_reward"]) < TOL
+    # device-side noise: same distribution, different stream -> only sanity-check shapes / finiteness / penalty
+    dyn.rng = "device"
+    nobs2, rew2, term2, info2 = dyn.step(g["step_obs"], g["step_act"])
+    assert nobs2.shape == nobs.shape and np.isfinite(nobs2).all()
+    assert rel_err(info2["penalty"], g["step_penalty"]) < TOL
+
+
+def test_mopo_rollout_matches_reference():
+    from offlinerlkit_b200.nets import MLP
+    from offlinerlkit_b200.modules import ActorProb, Critic, TanhDiagGaussian
+    from offlinerlkit_b200.policy import MOPOPolicy
+    g = Golden("rollout_small")
+    m = g.meta
+    O, A, hid = m["O"], m["A"], m["hidden"]
+    dyn_state = {k: torch.from_numpy(v) for k, v in g.group("dyn").items()}
+    dyn = _build_dynamics(m, dyn_state, g["scaler_mu"], g["scaler_std"], m["term"])
+    bb = MLP(O, hid)
+    actor = ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), DEV)
+    actor.load_state_dict({k: torch.from_numpy(v) for k, v in g.group("actor").items()})
+    c1, c2 = Critic(MLP(O + A, hid), DEV), Critic(MLP(O + A, hid), DEV)
+    adam = lambda mod: torch.optim.Adam(mod.parameters(), lr=1e-4)
+    pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2)
+    counts, E, D = g["counts"], m["E"], O + 1
+    eps, nrm, mid, r = [], [], [], 0
+    for c in counts:
+        eps.append(g["eps"][r:r + c])
+        nrm.append(g["normal"][:, r * D:(r + c) * D].reshape(E, c, D))
+        mid.append(g["midx"][r:r + c])
+        r += c
+    out, info = pol.rollout(g["init"], m["horizon"], noise={"eps": eps, "normal": nrm, "midx": mid})
+    assert info["num_transitions"] == int(counts.sum())
+    for k in ("obss", "next_obss", "actions", "rewards"):
+        assert out[k].shape == g["out|" + k].shape, k
+        assert rel_err(out[k], g["out|" + k]) < 2e-4, k
+    assert np.array_equal(out["terminals"], g["out|terminals"])
+    assert info["reward_mean"] == pytest.approx(float(g["reward_mean"]), rel=1e-4)
+    # performance mode (device noise): runs, keeps the output contract
+    out2, info2 = pol.rollout(g["init"], m["horizon"])
+    assert set(out2) == {"obss", "next_obss", "actions", "rewards", "terminals"} and out2["terminals"].dtype == bool
+    assert len(out2["obss"]) == info2["num_transitions"]
