@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 4
+#define ORLK_ABI_VERSION 5
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -192,10 +192,15 @@ int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off,
                            float* act, int64_t ld_act, float* logp, const float* obs, int64_t ld_obs, int obs_dim,
                            float* xout, int64_t ld_x, void* stream);
 /* Backward of the above with eps fixed:
- *   dA = sum_{j<n_da} dA_j ; dhead[m, 0:A) = dmu, dhead[m, A:2A) = draw (clamp-gated). glp[m] = dLoss/dlogp[m]. */
+ *   dL/da = sum_{j<n_da} dA[j*da_gs + m*ld_da + i] (one slab per critic / ensemble member);
+ *   dhead[m, 0:A) = dmu, dhead[m, A:2A) = draw (clamp-gated). glp[m] = dLoss/dlogp[m]. */
 int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, const float* act, int64_t ld_act,
-                        const float* dA0, const float* dA1, int64_t ld_da, const float* glp, int M, int A,
+                        const float* dA, int n_da, int64_t da_gs, int64_t ld_da, const float* glp, int M, int A,
                         float* dhead, int64_t ld_dhead, void* stream);
+/* EDAC ensemble-diversity term (edac.py:136-149): g [E][B][A] = dQ_e/da; ghat = g / (|g| + 1e-10);
+ *   G = mean_b sum_{i != j} <ghat_i, ghat_j> / (E-1);  writes gbar [E][B][A] = eta * dG/dg and out_loss[0] = eta * G. */
+int orlk_edac_div(const float* g, int E, int B, int A, float eta, float* gbar, float* scratch /* ceil(B/256) floats */,
+                  float* out_loss, void* stream);
 
 /* ------------------------------------------------------------------ losses */
 /* scalars block shared by the loss kernels of one learner (device memory, floats):

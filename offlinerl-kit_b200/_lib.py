@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -89,7 +89,8 @@ _PROTOS = {
     "orlk_narrow_wgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_philox_fill": [_P, _L, _L, _F, _F, C.c_uint64, _P, _P, _P],
     "orlk_tanh_gauss_sample": [_P, _L, _I, _I, _P, _I, _I, _P, _L, _P, _P, _L, _I, _P, _L, _P],
-    "orlk_tanh_gauss_bwd": [_P, _L, _P, _P, _L, _P, _P, _L, _P, _I, _I, _P, _L, _P],
+    "orlk_tanh_gauss_bwd": [_P, _L, _P, _P, _L, _P, _I, _L, _L, _P, _I, _I, _P, _L, _P],
+    "orlk_edac_div": [_P, _I, _I, _I, _F, _P, _P, _P, _P],
     "orlk_sac_actor_loss": [_P, _L, _I, _P, _I, _P, _I, _I, _F, _P, _I, _P, _P, _L, _P, _P, _P],
     "orlk_cql_critic_loss": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _I, _F, _P, _P, _I, _P,
                              _P, _L, _P, _P],

@@ -181,8 +181,8 @@ __global__ void k_tanh_gauss_sample(const float* __restrict__ head, int64_t ld_h
 }
 
 __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head, const float* __restrict__ eps,
-                                 const float* __restrict__ act, int64_t ld_act, const float* __restrict__ dA0,
-                                 const float* __restrict__ dA1, int64_t ld_da, const float* __restrict__ glp, int M, int A,
+                                 const float* __restrict__ act, int64_t ld_act, const float* __restrict__ dA, int n_da,
+                                 int64_t da_gs, int64_t ld_da, const float* __restrict__ glp, int M, int A,
                                  float* __restrict__ dhead, int64_t ld_dhead) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -195,8 +195,8 @@ __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head
         const float e = eps[(int64_t)m * A + i];
         const float a = act[(int64_t)m * ld_act + i];
         const float om = 1.f - a * a;
-        float da = dA0 ? dA0[(int64_t)m * ld_da + i] : 0.f;
-        if (dA1) da += dA1[(int64_t)m * ld_da + i];
+        float da = 0.f;
+        for (int j = 0; j < n_da; ++j) da += dA[j * da_gs + (int64_t)m * ld_da + i];    // sum over the critics / members
         const float t = 2.f * a * om / (om + 1e-6f);   // d logp / d u  (tanh correction only)
         const float du = da * om + g * t;              // through a = tanh(u) and through logp
         const float dmu = du;
@@ -481,11 +481,12 @@ int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off,
 }
 
 int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, const float* act, int64_t ld_act,
-                        const float* dA0, const float* dA1, int64_t ld_da, const float* glp, int M, int A, float* dhead,
+                        const float* dA, int n_da, int64_t da_gs, int64_t ld_da, const float* glp, int M, int A, float* dhead,
                         int64_t ld_dhead, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && eps != nullptr, "sizes");
-    k_tanh_gauss_bwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, eps, act, ld_act, dA0, dA1, ld_da, glp,
-                                                                       M, A, dhead, ld_dhead);
+    ORLK_REQUIRE(n_da == 0 || dA != nullptr, "dA");
+    k_tanh_gauss_bwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, eps, act, ld_act, dA, n_da, da_gs, ld_da,
+                                                                       glp, M, A, dhead, ld_dhead);
     return check_launch("k_tanh_gauss_bwd");
 }
 

@@ -167,6 +167,55 @@ __global__ void k_det_actor_bwd(const float* __restrict__ a, int64_t lda, const 
     }
 }
 
+// EDAC diversity loss and its gradient w.r.t. the input gradients g.  One thread per sample.
+__global__ void __launch_bounds__(256)
+k_edac_div(const float* __restrict__ g, int E, int B, int A, float eta, float* __restrict__ gbar, float* __restrict__ partial) {
+    __shared__ float red[32];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    float Gb = 0.f;
+    if (b < B) {
+        float S[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) S[i] = 0.f;
+        float sumsq = 0.f;
+        for (int e = 0; e < E; ++e) {
+            const float* ge = g + ((int64_t)e * B + b) * A;
+            float n2 = 0.f;
+            for (int i = 0; i < A; ++i) n2 += ge[i] * ge[i];
+            const float inv = 1.f / (sqrtf(n2) + 1e-10f);
+            for (int i = 0; i < A; ++i) {
+                const float h = ge[i] * inv;
+                S[i] += h;
+                sumsq += h * h;
+            }
+        }
+        float s2 = 0.f;
+        for (int i = 0; i < A; ++i) s2 += S[i] * S[i];
+        Gb = (s2 - sumsq) / (float)(E - 1);
+        const float c = 2.f * eta / ((float)B * (float)(E - 1));
+        for (int e = 0; e < E; ++e) {
+            const float* ge = g + ((int64_t)e * B + b) * A;
+            float* ob = gbar + ((int64_t)e * B + b) * A;
+            float n2 = 0.f;
+            for (int i = 0; i < A; ++i) n2 += ge[i] * ge[i];
+            const float n = sqrtf(n2), d = n + 1e-10f;
+            // hbar_i = c (S_i - ghat_i);  gbar = hbar/d - g <g,hbar> / (n d^2)
+            float dot = 0.f;
+            for (int i = 0; i < A; ++i) dot += ge[i] * (c * (S[i] - ge[i] / d));
+            const float k = n > 0.f ? dot / (n * d * d) : 0.f;
+            for (int i = 0; i < A; ++i) ob[i] = c * (S[i] - ge[i] / d) / d - ge[i] * k;
+        }
+    }
+    Gb = block_sum(Gb, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = Gb;
+}
+
+__global__ void k_edac_div_final(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    out[0] = s * scale;
+}
+
 }  // namespace
 
 extern "C" {
@@ -212,6 +261,15 @@ int orlk_td3bc_actor_loss(const float* q, const float* a, int64_t lda, const flo
     ORLK_REQUIRE(B > 0 && A > 0, "sizes");
     k_td3bc_actor_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(q, a, lda, a_data, ldd, B, A, bc_alpha, dq, dabc, ldg, out_loss);
     return check_launch("k_td3bc_actor_loss");
+}
+
+int orlk_edac_div(const float* g, int E, int B, int A, float eta, float* gbar, float* scratch, float* out_loss, void* stream) {
+    ORLK_REQUIRE(E >= 2 && B > 0 && A > 0 && A <= 32, "sizes");
+    ORLK_REQUIRE(scratch != nullptr, "scratch (ceil(B/256) floats)");
+    const int blocks = (B + 255) / 256;
+    k_edac_div<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, E, B, A, eta, gbar, scratch);
+    k_edac_div_final<<<1, 1, 0, (cudaStream_t)stream>>>(scratch, blocks, eta / (float)B, out_loss);
+    return check_launch("k_edac_div");
 }
 
 int orlk_det_actor_bwd(const float* a, int64_t lda, const float* dA0, int64_t ld0, const float* dA1, int64_t ld1, int M, int A,

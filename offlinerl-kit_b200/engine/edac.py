@@ -1,0 +1,209 @@
+"""Gradient-step engine for EDAC (policy/model_free/edac.py:88-166).
+
+E critics live in one 'io' ParamSet (EnsembleLinear layout, members contiguous).  The ensemble-diversity term needs
+d/dW of a function of the INPUT gradients dQ_e/da; instead of autograd's double backward (``create_graph=True``) the
+closed form of SURVEY.md appendix A.4 is scheduled explicitly:
+  1. g-chain   : an ordinary backward pass with upstream 1 over the saved ReLU masks -> v_l and g = dQ/da
+  2. orlk_edac_div : loss eta*G and gbar = eta * dG/dg
+  3. second chain  : ubar_1 = m_1 * (gbar W1a), ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1})  (forward-like masked GEMMs)
+                     dW1a += gbar^T v_1, dW_{l+1} += ubar_l^T v_{l+1}, dw_head += sum_b ubar_L      (wgrad GEMMs)
+The diversity weight gradients go to extra split-K slots of the same GradBuf, so one fused Adam+polyak launch sums
+the TD part and the diversity part.
+"""
+import ctypes as C
+from typing import Dict
+
+import torch
+
+from .. import _lib as L
+from .core import GP, Mat, Plan
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
+                      make_gradbuf, wgrad_layout)
+from .nets import GradBuf, ParamSet, adam_descs, dgrad_problem, pick_cfg, wgrad_problem
+from .sac_family import LS_ACTOR, LS_ALPHA, LS_ALPHA_LOSS
+from .td3_iql import _BatchMixin
+
+LS_TD_SUM, LS_DIV = 9, 10
+
+
+class EDACLearner(_BatchMixin, Learner):
+    def __init__(self, policy, batch_size: int, seed: int = 0):
+        actor = policy.actor
+        super().__init__(actor.device)
+        rt = self.rt
+        self.policy, self.B, self.seed = policy, int(batch_size), seed
+        check_plain_mlp(actor.backbone, "actor")
+        if policy._max_q_backup:
+            raise L.OrlkError("EDAC max_q_backup=True is not implemented by the CUDA engine")
+        dist = actor.dist_net
+        if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
+            raise L.OrlkError("EDAC engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
+        lin = lambda m: [x for x in m.model if hasattr(x, "num_ensemble")]
+        for mod in policy.critics.model:
+            if not hasattr(mod, "num_ensemble") and not isinstance(mod, torch.nn.ReLU):
+                raise L.OrlkError(f"EnsembleCritic: only ReLU activations are supported, found {type(mod).__name__}")
+        self.actor_ps = ParamSet.from_linear_members(rt, "actor", [linears_of(actor)], fuse_last=2)
+        self.critic_ps = ParamSet.from_ensemble(rt, "critics", lin(policy.critics), targets=lin(policy.critics_old))
+        self.param_sets = [self.actor_ps, self.critic_ps]
+        self.E = self.critic_ps.G
+        self.nh_a, self.nh_c = len(self.actor_ps.layers) - 1, len(self.critic_ps.layers) - 1
+        self.O = self.actor_ps.layers[0].in_dim
+        self.A = self.actor_ps.layers[-1].out_dim // 2
+        self.g_actor = self.add_group(policy.actor_optim)
+        self.g_c = self.add_group(policy.critics_optim, tau=float(policy._tau))
+        self.actor_ps.group_ids, self.critic_ps.group_ids = [self.g_actor], [self.g_c]
+        self.auto_alpha = bool(policy._is_auto_alpha)
+        self.alpha_mv = rt.zeros(2)
+        self.g_alpha, self.target_entropy = -1, 0.0
+        with torch.no_grad():
+            self.scalars[L.SC_ALPHA] = float(policy._alpha)
+        if self.auto_alpha:
+            self.g_alpha = self.add_group(policy.alpha_optim)
+            self.target_entropy = float(policy._target_entropy)
+            la = policy._log_alpha
+            with torch.no_grad():
+                self.scalars[L.SC_LOG_ALPHA] = float(la.detach().reshape(-1)[0])
+            la.data = self.scalars[L.SC_LOG_ALPHA:L.SC_LOG_ALPHA + 1].view(la.shape)
+        self.eta = float(policy._eta)
+        self.push_groups()
+        self._make_stage()
+        B, A = self.B, self.A
+        self.noise = rt.zeros(2 * B * A)
+        self.noise_views = {"eps_actor": self.noise[:B * A].view(B, A), "eps_next": self.noise[B * A:].view(B, A)}
+        self._built = False
+
+    def _sample(self, plan, tag, head, eps, X: Mat, logp, obs: Mat):
+        O, A, B = self.O, self.A, self.B
+        args = (head.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), B, A, X.ptr + 4 * O, X.ld, logp.data_ptr(), obs.ptr, obs.ld, O,
+                X.ptr, X.ld)
+        plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
+
+    def _build(self) -> None:
+        rt, B, O, A, E, pol = self.rt, self.B, self.O, self.A, self.E, self.policy
+        cps, aps = self.critic_ps, self.actor_ps
+        nh = self.nh_c
+        run_a = MlpRun(rt, aps, B, self.nh_a, need_grad=True)
+        run_ca = MlpRun(rt, cps, B, nh, need_grad=True)                       # Q_e(s, a~pi) in the actor phase
+        run_an = MlpRun(rt, aps, B, self.nh_a, need_grad=False)
+        run_t = MlpRun(rt, cps, B, nh, need_grad=False, store="T")
+        run_c = MlpRun(rt, cps, B, nh, need_grad=True)                        # Q_e(s, a_data): TD backward
+        run_g = MlpRun(rt, cps, B, nh, need_grad=True, share_forward=run_c)   # same activations: input-gradient chain
+        Xa, Xt, Xd = rt.zeros(B, O + A), rt.zeros(B, O + A), rt.zeros(B, O + A)
+        logp_a, lp_next, glp = rt.zeros(B), rt.zeros(B), rt.zeros(B)
+        dA = rt.zeros(E, B, A)
+        gin, gbar = rt.zeros(E, B, A), rt.zeros(E, B, A)
+        ones = torch.ones(B, 1, dtype=torch.float32, device=self.dev)
+        ubar = [rt.zeros(E, B, cps.layers[l].out_dim) for l in range(nh)]
+        div_scratch = rt.zeros((B + 255) // 256)
+        self._keep = [run_a, run_ca, run_an, run_t, run_c, run_g, Xa, Xt, Xd, logp_a, lp_next, glp, dA, gin, gbar, ones, ubar,
+                      div_scratch]
+        gb_a = make_gradbuf(rt, aps, [run_a])
+        td_layout = wgrad_layout(cps, nh + 1, B)
+        s_td = max(s for _, s in td_layout)
+        gb_c = GradBuf(rt, cps, s_td + 1)              # slots [0, s_td): TD part; slot s_td: diversity part
+        obs2 = Mat.of(self.obs2)
+        obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
+        mXa, mXt, mXd = Mat.of(Xa), Mat.of(Xt), Mat.of(Xd)
+        plan = Plan(rt, "edac")
+        nargs = (self.noise.data_ptr(), 2 * B * A, 0, 0.0, 1.0, int(self.seed), self.philox_counter.data_ptr(),
+                 self.noise_enable.data_ptr())
+        plan.add("philox", lambda: L.call("orlk_philox_fill", *nargs, rt.cur))
+
+        # ---- actor: L = -mean min_e Q_e(s, a) + alpha mean logp      (edac.py:96-110)
+        emit_forward(rt, plan, run_a, [obs], "A.actor")
+        self._sample(plan, "A.sample", run_a.out[0], self.noise_views["eps_actor"], mXa, logp_a, obs)
+        emit_forward(rt, plan, run_ca, [mXa] * E, "A.critics")
+        largs = (run_ca.out.data_ptr(), B, E, logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha), 1,
+                 self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(), run_ca.dOut.data_ptr(), B,
+                 glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+        plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *largs, rt.cur))
+        emit_head_dgrad(rt, plan, run_ca, "A.critics")
+        emit_hidden_dgrad(rt, plan, run_ca, "A.critics")
+        plan.add("A.critics.dact", rt.gemm([dgrad_problem(cps, 0, e, run_ca.dz(0, e), Mat.of(dA[e]), L.EPI_NONE, None, col0=O,
+                                                          ncols=A) for e in range(E)], L.CFG_SMALL))
+        bargs = (run_a.out.data_ptr(), 2 * A, self.noise_views["eps_actor"].data_ptr(), mXa.ptr + 4 * O, mXa.ld, dA.data_ptr(), E,
+                 B * A, A, glp.data_ptr(), B, A, run_a.dOut.data_ptr(), 2 * A)
+        plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
+        emit_head_dgrad(rt, plan, run_a, "A.actor")
+        emit_hidden_dgrad(rt, plan, run_a, "A.actor")
+        from .learner import emit_wgrad_adam
+        emit_wgrad_adam(rt, plan, run_a, [obs], gb_a, self.groups_ptr, "A.actor", polyak=False)
+
+        # ---- critics: TD to min_e Q'_e(s', a') - alpha logp'  +  eta * diversity      (edac.py:112-155)
+        emit_forward(rt, plan, run_an, [nobs], "C.actor_next")
+        self._sample(plan, "C.sample_next", run_an.out[0], self.noise_views["eps_next"], mXt, lp_next, nobs)
+        emit_forward(rt, plan, run_t, [mXt] * E, "C.target")
+        plan.add("C.concat", rt.concat([(mXd, obs, 1, Mat.of(self.act))]))
+        emit_forward(rt, plan, run_c, [mXd] * E, "C.critics")
+        use_alpha = 0 if pol._deterministic_backup else 1
+        targs = (run_c.out.data_ptr(), B, E, run_t.out.data_ptr(), B, E, lp_next.data_ptr(), self.scalars.data_ptr(), use_alpha,
+                 self.rew.data_ptr(), self.term.data_ptr(), B, float(pol._gamma), run_c.dOut.data_ptr(), B, None,
+                 self.loss_dev.data_ptr() + 4 * 12, self.loss_dev.data_ptr() + 4 * LS_TD_SUM)
+        plan.add("C.td_loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+        emit_head_dgrad(rt, plan, run_c, "C.critics")
+        emit_hidden_dgrad(rt, plan, run_c, "C.critics")
+        probs = []
+        for l in range(nh + 1):
+            for e in range(E):
+                xin = mXd if l == 0 else run_c.h(l - 1, e)
+                dy = run_c.dz(l, e) if l < nh else Mat.of(run_c.dOut[e])
+                probs.append(wgrad_problem(cps, gb_c, l, e, xin, dy, td_layout[l][1]))
+        plan.add("C.critics.wgrad_td", rt.gemm(probs, L.CFG_SMALL))
+        if self.eta > 0:
+            # 1. input-gradient chain (upstream 1)
+            run_g.dOut.fill_(1.0)
+            emit_head_dgrad(rt, plan, run_g, "G.chain")
+            emit_hidden_dgrad(rt, plan, run_g, "G.chain")
+            plan.add("G.dact", rt.gemm([dgrad_problem(cps, 0, e, run_g.dz(0, e), Mat.of(gin[e]), L.EPI_NONE, None, col0=O, ncols=A)
+                                        for e in range(E)], L.CFG_SMALL))
+            # 2. loss and gbar
+            dargs = (gin.data_ptr(), E, B, A, self.eta, gbar.data_ptr(), div_scratch.data_ptr(),
+                     self.loss_dev.data_ptr() + 4 * LS_DIV)
+            plan.add("G.div", lambda: L.call("orlk_edac_div", *dargs, rt.cur))
+            # 3. second chain + weight gradients into slot s_td
+            wprobs = [wgrad_problem(cps, gb_c, 0, e, Mat.of(gbar[e]), run_g.dz(0, e), 1, split_base=s_td, col0=O, with_bias=False)
+                      for e in range(E)]
+            for l in range(nh):
+                lay = cps.layers[l]
+                fprobs = []
+                for e in range(E):
+                    if l == 0:      # ubar_1 = m_1 * (gbar W1a),  W1a = rows O.. of W1 [in, out]
+                        fprobs.append(GP(A=gbar[e].data_ptr(), lda=A, a_layout=0, B=cps.w(0, e) + 4 * O * lay.out_dim,
+                                         ldb=lay.out_dim, b_layout=0, C=ubar[0][e].data_ptr(), ldc=lay.out_dim, M=B,
+                                         N=lay.out_dim, K=A, epi=L.EPI_RELU_MASK, aux=run_c.H[0][e].data_ptr(), ldaux=lay.out_dim))
+                    else:           # ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1})
+                        fprobs.append(GP(A=ubar[l - 1][e].data_ptr(), lda=lay.in_dim, a_layout=0, B=cps.w(l, e), ldb=lay.out_dim,
+                                         b_layout=0, C=ubar[l][e].data_ptr(), ldc=lay.out_dim, M=B, N=lay.out_dim, K=lay.in_dim,
+                                         epi=L.EPI_RELU_MASK, aux=run_c.H[l][e].data_ptr(), ldaux=lay.out_dim))
+                plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim)))
+                for e in range(E):
+                    if l + 1 < nh:  # dW_{l+1} += ubar_l^T v_{l+1}
+                        wprobs.append(wgrad_problem(cps, gb_c, l + 1, e, Mat.of(ubar[l][e]), run_g.dz(l + 1, e), 1,
+                                                    split_base=s_td, with_bias=False))
+                    else:           # dw_head += sum_b ubar_L
+                        wprobs.append(wgrad_problem(cps, gb_c, nh, e, Mat.of(ubar[l][e]), Mat.of(ones), 1, split_base=s_td,
+                                                    with_bias=False))
+                if l + 1 < nh:
+                    continue
+            plan.add("G.wgrad_div", rt.gemm(wprobs, L.CFG_SMALL))
+        splits = [s_td + 1] * (nh + 1)
+        plan.add("C.critics.adam", rt.adam(adam_descs(cps, gb_c, splits, polyak=True), self.groups_ptr))
+        mask = (1 << self.g_actor) | (1 << self.g_c) | ((1 << self.g_alpha) if self.g_alpha >= 0 else 0)
+        self.finish_ops(plan, mask)
+        self.plans["step"] = plan
+        self._built = True
+
+    def step(self, batch, noise=None) -> Dict[str, float]:
+        self.bind_batch(batch)
+        if not self._built:
+            self._build()
+        self.set_noise(noise)
+        self.sync_lr()
+        self.refresh()
+        out = self.run("step")
+        res = {"loss/actor": float(out[LS_ACTOR]),
+               "loss/critics": float(out[LS_TD_SUM]) + (float(out[LS_DIV]) if self.eta > 0 else 0.0)}
+        if self.auto_alpha:
+            res["loss/alpha"] = float(out[LS_ALPHA_LOSS])
+            res["alpha"] = float(out[LS_ALPHA])
+        return res

@@ -166,17 +166,18 @@ class MlpRun:
     """
 
     def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P",
-                 tc_passes: int = 0, members: Optional[int] = None):
+                 tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
         self.tc = tc_passes if M >= TC_MIN_ROWS else 0
         self.Mt = (M + 3) // 4 * 4
         self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
         lays = ps.layers
-        self.H = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)]
+        # ``share_forward``: a second gradient chain over the SAME activations (EDAC's input-gradient pass)
+        self.H = share_forward.H if share_forward is not None else [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)]
         self.dZ = [rt.zeros(G, M, lays[l].out_dim) for l in range(n_hidden)] if need_grad else None
         self.has_head = len(lays) > n_hidden
         self.NS = lays[n_hidden].out_dim if self.has_head else 0
-        self.out = rt.zeros(G, M, self.NS) if self.has_head else None
+        self.out = (share_forward.out if share_forward is not None else rt.zeros(G, M, self.NS)) if self.has_head else None
         self.dOut = rt.zeros(G, M, self.NS) if (self.has_head and need_grad) else None
         # per-layer kernel choice
         self.tc_fwd = [bool(self.tc) and l >= 1 and tc_ok_fwd(lays[l], M) for l in range(n_hidden)]

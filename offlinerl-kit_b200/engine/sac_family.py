@@ -150,8 +150,8 @@ class TwinCriticLearner(Learner):
                  for g in range(2)]
         plan.add("A.critic.dact", rt.gemm(probs, L.CFG_SMALL))
         head = ar.out[0]
-        bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA[0].data_ptr(),
-                 self.dA[1].data_ptr(), A, self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
+        bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), 2, B * A, A,
+                 self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
         plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
         emit_head_dgrad(rt, plan, ar, "A.actor")
         emit_hidden_dgrad(rt, plan, ar, "A.actor")

@@ -4,5 +4,6 @@ from .cql import CQLPolicy
 from .td3bc import TD3BCPolicy
 from .iql import IQLPolicy
 from .mopo import MOPOPolicy
+from .edac import EDACPolicy
 
-__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy", "TD3BCPolicy", "IQLPolicy", "MOPOPolicy"]
+__all__ = ["BasePolicy", "SACPolicy", "CQLPolicy", "TD3BCPolicy", "IQLPolicy", "MOPOPolicy", "EDACPolicy"]

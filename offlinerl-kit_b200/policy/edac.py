@@ -1,0 +1,63 @@
+"""EDACPolicy facade (reference: policy/model_free/edac.py:11-166); ``learn`` runs engine/edac.py:EDACLearner."""
+from copy import deepcopy
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .base_policy import BasePolicy
+
+
+class EDACPolicy(BasePolicy):
+    def __init__(self, actor: nn.Module, critics: nn.Module, actor_optim: torch.optim.Optimizer,
+                 critics_optim: torch.optim.Optimizer, tau: float = 0.005, gamma: float = 0.99,
+                 alpha: Union[float, Tuple[float, torch.Tensor, torch.optim.Optimizer]] = 0.2, max_q_backup: bool = False,
+                 deterministic_backup: bool = True, eta: float = 1.0) -> None:
+        super().__init__()
+        self.actor = actor
+        self.critics, self.critics_old = critics, deepcopy(critics)
+        self.critics_old.eval()
+        self.actor_optim, self.critics_optim = actor_optim, critics_optim
+        self._tau, self._gamma = tau, gamma
+        self._is_auto_alpha = isinstance(alpha, tuple)
+        if self._is_auto_alpha:
+            self._target_entropy, self._log_alpha, self.alpha_optim = alpha
+            self._alpha = self._log_alpha.detach().exp()
+        else:
+            self._alpha = alpha
+        self._max_q_backup, self._deterministic_backup, self._eta = max_q_backup, deterministic_backup, eta
+        self._num_critics = self.critics._num_ensemble
+        self._engine = None
+
+    def train(self) -> None:
+        self.actor.train()
+        self.critics.train()
+
+    def eval(self) -> None:
+        self.actor.eval()
+        self.critics.eval()
+
+    def actforward(self, obs: torch.Tensor, deterministic: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        dist = self.actor(obs)
+        squashed, raw = dist.mode() if deterministic else dist.rsample()
+        return squashed, dist.log_prob(squashed, raw)
+
+    def select_action(self, obs: np.ndarray, deterministic: bool = False) -> np.ndarray:
+        with torch.no_grad():
+            action, _ = self.actforward(obs, deterministic)
+        return action.cpu().numpy()
+
+    def engine(self, batch_size: int):
+        if self._engine is None:
+            from ..engine.edac import EDACLearner
+            self._engine = EDACLearner(self, batch_size)
+        elif self._engine.B != batch_size:
+            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
+        return self._engine
+
+    def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
+        out = self.engine(int(batch["observations"].shape[0])).step(batch, noise)
+        if self._is_auto_alpha:
+            self._alpha = torch.tensor([out["alpha"]], device=self.actor.device)
+        return out

@@ -24,3 +24,10 @@ def test_td3bc_matches_reference(name):
     """td3bc_small runs 4 steps: the actor / polyak phase only runs on steps 0 and 2 (td3bc.py:107-116)."""
     from tests.gpu_common import run_golden_steps
     run_golden_steps(Golden(name), tol=TOL, verbose=True)
+
+
+@pytest.mark.parametrize("name", ["edac_small", "edac_hc"])
+def test_edac_matches_reference(name):
+    """Ensemble critics + the input-gradient diversity loss (hand-derived double backward) vs the reference's autograd."""
+    from tests.gpu_common import run_golden_steps
+    run_golden_steps(Golden(name), tol=TOL, verbose=True)

@@ -229,8 +229,8 @@ def test_tanh_gauss_sample_and_bwd(rt):
            None, 0, 0, None, 0, rt.cur)
     _close(lpd, lp1[:, 0], rtol=1e-5, atol=1e-4, msg="log-prob (moderate)")
     dh = torch.zeros(B, 2 * A, device=DEV)
-    d0, d1, gl = dA0.to(DEV), dA1.to(DEV), glp.to(DEV)
-    L.call("orlk_tanh_gauss_bwd", h1d.data_ptr(), 2 * A, e1d.data_ptr(), act.data_ptr(), A, d0.data_ptr(), d1.data_ptr(),
+    d01, gl = torch.stack([dA0, dA1]).to(DEV), glp.to(DEV)
+    L.call("orlk_tanh_gauss_bwd", h1d.data_ptr(), 2 * A, e1d.data_ptr(), act.data_ptr(), A, d01.data_ptr(), 2, B * A,
            A, gl.data_ptr(), B, A, dh.data_ptr(), 2 * A, rt.cur)
     _close(dh, head1.grad, rtol=2e-4, atol=2e-4, msg="head backward")
 
