@@ -217,6 +217,9 @@ class Plan:
         self.rt, self.name = rt, name
         self.ops: List[Tuple[str, Callable[[], None]]] = []
         self.graph: Optional[C.c_void_p] = None
+        # The launch closures hold raw device pointers: every tensor they address must be referenced from here (or
+        # from the owning learner) for as long as the plan can run.
+        self.keep: List[object] = []
 
     def add(self, label: str, op: Callable[[], None]) -> None:
         self.ops.append((label, op))

@@ -93,7 +93,6 @@ class DynamicsEngine(Learner):
             args = (ps._ptr(ps.P, lay.w_off), n, 0.5 * self.wd[l], self.decay_partials.data_ptr() + 4 * off)
             plan.add(f"D.decay{l}", lambda args=args: L.call("orlk_sumsq", *args, rt.cur))
             off += rt.lib.orlk_sumsq_chunks(n)
-        self._coef_dev = rt.zeros(1)
         largs = [run.OUT.data_ptr(), Y.data_ptr(), E, Bn, D, ps.extra_ptr("max_logvar"), ps.extra_ptr("min_logvar"), 0.01,
                  self.decay_partials.data_ptr(), self.n_decay, run.dOUT.data_ptr(), self.dmax.data_ptr(), self.dmin.data_ptr(),
                  self.loss_dev.data_ptr()]
@@ -130,6 +129,7 @@ class DynamicsEngine(Learner):
         plan.add("D.adam", rt.adam(descs, self.groups_ptr))
         gp = C.c_void_p(self.groups_ptr)
         plan.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
+        plan.keep += [gb, run, X, Y]
         self._learn_plans[Bn] = (plan, dict(X=X, Y=Y, run=run, state=state))
         return self._learn_plans[Bn]
 

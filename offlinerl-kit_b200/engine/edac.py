@@ -190,6 +190,7 @@ class EDACLearner(_BatchMixin, Learner):
         plan.add("C.critics.adam", rt.adam(adam_descs(cps, gb_c, splits, polyak=True), self.groups_ptr))
         mask = (1 << self.g_actor) | (1 << self.g_c) | ((1 << self.g_alpha) if self.g_alpha >= 0 else 0)
         self.finish_ops(plan, mask)
+        plan.keep.append(dict(locals()))       # runs, GradBufs, scratch: everything the closures point into
         self.plans["step"] = plan
         self._built = True
 

@@ -84,6 +84,7 @@ class Learner:
         e.lr, e.beta1, e.beta2, e.eps, e.tau, e.step = h["lr"], h["beta1"], h["beta2"], h["eps"], tau, 0
         if optim is not None:
             self._group_optim[g] = optim
+            optim._opt_called = True      # the engine applies this optimiser's steps; keeps lr_scheduler's order check quiet
         self._group_lr[g] = h["lr"]
         self._n_groups += 1
         return g
@@ -225,6 +226,7 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
 def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
     """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
     ps, G, M = run.ps, run.G, run.M
+    plan.keep += [run, [x.keep for x in X]]
     for l in range(run.nh):
         lay = ps.layers[l]
         if run.tc_fwd[l]:
@@ -329,6 +331,7 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
                     polyak: bool) -> None:
     """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update."""
     ps, G, M = run.ps, run.G, run.M
+    plan.keep += [run, gb, [x.keep for x in X]]
     big, small = [], []
     n_l = run.nh + (1 if run.has_head else 0)
     layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
