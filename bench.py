@@ -264,11 +264,11 @@ def run_engine(args, rank: int, world: int, local_rank: int):
     from offlinerlkit_b200 import _lib as L
     device = f"cuda:{local_rank}"
     torch.cuda.set_device(local_rank)
-    dist_on = world > 1
+    from offlinerlkit_b200 import parallel
+    dist_on = parallel.init("nccl", torch.device(device))
     if dist_on:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(device))
-    policy, buf = build_engine(device, seed=rank, n_data=args.rows)
+    policy, buf = build_engine(device, seed=parallel.seed_for_rank(0, rank), n_data=args.rows)
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- warm-up through the public API (uploads the table, builds and captures the step graph)
@@ -318,10 +318,7 @@ def run_engine(args, rank: int, world: int, local_rank: int):
     e2e_ms = max(ms.value, 1e3 * e2e_wall)
     clocks = sampler.stop()
 
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
-    if dist_on:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = times.tolist()
+    dev_ms, e2e_ms = parallel.reduce_scalars([dev_ms, e2e_ms], "max", device)      # the slowest rank bounds the job
     value = world * K / (dev_ms * 1e-3)
     e2e = world * K / (e2e_ms * 1e-3)
 

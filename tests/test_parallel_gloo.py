@@ -1,0 +1,66 @@
+"""CPU, world_size 2 over gloo: the replica-mode bookkeeping (timing reduction, seeds, member partition)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from offlinerlkit_b200 import parallel
+    assert parallel.init("gloo")
+    # rank 1 is slower: the whole-job rate is bounded by it
+    elapsed = 100.0 if rank == 0 else 250.0
+    rate = parallel.aggregate_rate(steps_per_rank=500, elapsed_ms=elapsed)
+    sums = parallel.reduce_scalars([float(rank + 1), 2.0], "sum")
+    import torch.distributed as dist
+    # replica determinism contract: every rank derives its own seed; same seed -> same index stream on any rank
+    import numpy as np
+    np.random.seed(parallel.seed_for_rank(7, rank))
+    idx = torch.from_numpy(np.random.randint(0, 1000, size=8))
+    gathered = [torch.zeros_like(idx) for _ in range(world)]
+    dist.all_gather(gathered, idx)
+    q.put((rank, rate, sums, [g.tolist() for g in gathered]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replica_bookkeeping_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import numpy as np
+    for rank, rate, sums, gathered in res:
+        assert rate == pytest.approx(2 * 500 / 0.250)            # all ranks agree: total steps / slowest rank
+        assert sums == [3.0, 4.0]
+        for r in range(2):                                        # rank r's stream == a single-process run with seed 7+r
+            np.random.seed(7 + r)
+            assert gathered[r] == np.random.randint(0, 1000, size=8).tolist()
+    assert res[0][3][0] != res[0][3][1]
+
+
+def test_member_partition():
+    from offlinerlkit_b200.parallel import partition_members
+    assert [len(p) for p in partition_members(10, 4)] == [3, 3, 2, 2]
+    assert [len(p) for p in partition_members(10, 8)] == [2, 2, 1, 1, 1, 1, 1, 1]
+    assert sum(partition_members(7, 8), []) == list(range(7)) and partition_members(7, 8)[7] == []
