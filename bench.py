@@ -207,6 +207,8 @@ def run_reference(args, rank: int):
     so `oracle/_ref` does not exist).  Rank 0 only."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     threads = torch.get_num_threads()
     rate, done, dt = time_oracle("cpu", args.steps, min(args.warmup, 5), budget_s=150.0, n_data=args.rows)
     sample = (f"{done} consecutive gradient steps of the same workload (requested {args.steps}; capped at 150 s of "
@@ -362,6 +364,7 @@ def run_engine(args, rank: int, world: int, local_rank: int):
                 "launch_breakdown_us": {lbl: round(us, 2) for lbl, us in top}, "eager_step_us": step_us,
                 "last_loss": {k: float(v) for k, v in loss.items()}}
         if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(max(1, os.cpu_count() or 1))
             threads = torch.get_num_threads()
             rate, done, dt = time_oracle("cpu", 200, 3, budget_s=20.0, n_data=min(args.rows, 200_000))
             line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
