@@ -16,6 +16,23 @@ def env_rank() -> tuple:
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
+class _StdoutToStderr:
+    """NCCL announces its version on stdout when the first communicator is created; callers that promise ONE JSON line
+    on stdout route the file descriptor to stderr for the duration of the rendezvous."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        import sys
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def init(backend: str, device: torch.device = None) -> bool:
     """Join the process group described by the torchrun environment; returns False for a single process."""
     rank, world, _ = env_rank()
@@ -23,7 +40,12 @@ def init(backend: str, device: torch.device = None) -> bool:
         return False
     if not dist.is_initialized():
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
-        dist.init_process_group(backend, **kw)
+        with _StdoutToStderr():
+            dist.init_process_group(backend, **kw)
+            t = torch.zeros(1, device=device if backend == "nccl" else "cpu")
+            dist.all_reduce(t)                  # creates the communicator now, inside the redirected region
+            if backend == "nccl":
+                torch.cuda.synchronize(device)
     return True
 
 
