@@ -235,7 +235,7 @@ def per_launch_breakdown(eng, reps: int = 20):
     L.call("orlk_event_create", C.byref(e0))
     L.call("orlk_event_create", C.byref(e1))
     out = []
-    for label, op in plan.ops:
+    for label, op in plan.flat_ops:
         g = C.c_void_p()
         torch.cuda.synchronize()
         rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
@@ -278,7 +278,7 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         loss = policy.learn(buf.sample(BATCH))
     eng = policy._engine
     rt = eng.rt
-    n_kernels = sum(1 for lbl, _ in eng.plans["step"].ops if lbl != "losses_d2h") + 1      # + the gather kernel
+    n_kernels = sum(1 for lbl, _ in eng.plans["step"].flat_ops if lbl != "losses_d2h") + 1      # + the gather kernel
 
     def barrier():
         if dist_on:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 5
+#define ORLK_ABI_VERSION 7
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -50,6 +50,12 @@ int orlk_graph_end(void* stream, void** graph_exec_out);
 int orlk_graph_launch(void* graph_exec, void* stream);
 int orlk_graph_destroy(void* graph_exec);
 int orlk_stream_sync(void* stream);
+/* side streams + ordering events: independent launches of a step (e.g. the weight gradients of different layers)
+ * are forked onto side streams inside the captured graph and joined before the optimiser */
+int orlk_stream_create(void** stream_out);
+int orlk_stream_destroy(void* stream);
+int orlk_stream_wait_event(void* stream, void* ev);
+int orlk_event_create_notiming(void** ev_out);
 int orlk_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream);
 int orlk_memcpy_d2h_async(void* dst_host, const void* src, size_t bytes, void* stream);
 int orlk_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
@@ -83,7 +89,8 @@ enum {
     ORLK_EPI_SWISH = 3,     /* z = acc + bias; C = z*sigmoid(z); C2 = z               */
     ORLK_EPI_DSWISH = 4     /* C = acc * swish'(aux(m,n))      Swish backward, aux=z  */
 };
-enum { ORLK_CFG_BIG = 0, ORLK_CFG_MID = 1, ORLK_CFG_SMALL = 2 }; /* 128x128x16, 64x64x16, 32x32x32 tiles */
+/* tile configurations: 128x128x16, 64x64x16, 32x32x32, and 32x32x256 with 4 k-parallel thread groups (small-M layers) */
+enum { ORLK_CFG_BIG = 0, ORLK_CFG_MID = 1, ORLK_CFG_SMALL = 2, ORLK_CFG_KPAR = 3 };
 
 typedef struct OrlkGemmDesc {
     const float* A;
@@ -109,7 +116,11 @@ typedef struct OrlkGemmDesc {
     int32_t tiles_m, tiles_n;
 } OrlkGemmDesc;
 
-int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, void* stream);
+int orlk_gemm_init(void); /* once per process, outside stream capture (shared-memory opt-in) */
+/* a_layout / b_layout: the operand layouts shared by ALL problems of the launch (the kernel is specialised on them;
+ * the per-problem fields of the descriptors must agree). */
+int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, int a_layout, int b_layout,
+                      void* stream);
 
 /* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
  *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.
@@ -138,11 +149,13 @@ int orlk_sizeof_tc_gemm(void);
 
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
  * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).
- *   fwd :  Y[g][m,n] = b[g][n] + sum_k X[g][m,k] * W[g][n*ldw + k]            (one warp per row)
+ *   fwd :  Y[g][m,n] = b[g][n] + sum_k X[g][m,k] * W[g][n*ldw + k*w_sk]       (one warp per row; w_sk = 1 for a
+ *          row-major [N,K] weight, w_sk = leading dimension to read a column block of a [K, .] matrix, e.g. dQ/da)
  *   dgrad: dX[g][m,k] = (sum_n dY[g][m,n] * W[g][n*ldw+k]) * (mask ? mask[g][m,k] > 0 : 1)
  * groups g = 0..G-1 are addressed with the *_gs element strides. */
-int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
-                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G, void* stream);
+int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_sk, int64_t w_gs,
+                    const float* b, int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G,
+                    void* stream);
 int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W, int64_t ldw, int64_t w_gs,
                       const float* mask, int64_t ldm, int64_t m_gs, float* dX, int64_t ldx, int64_t x_gs, float* dXT,
                       int64_t ldxt, int64_t xt_gs, int M, int K, int NS, int G, void* stream);

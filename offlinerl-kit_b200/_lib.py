@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -58,8 +58,8 @@ class TcGemm(C.Structure):
 
 
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)
-CFG_BIG, CFG_MID, CFG_SMALL = range(3)
-CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32)}
+CFG_BIG, CFG_MID, CFG_SMALL, CFG_KPAR = range(4)
+CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32), CFG_KPAR: (32, 32, 256)}
 OPT_ADAM, OPT_POLYAK = 1, 2
 SC_LOG_ALPHA, SC_ALPHA, SC_CQL_LOG_ALPHA, SC_COUNT = 0, 1, 2, 8
 
@@ -72,16 +72,18 @@ _PROTOS = {
     "orlk_device_info": [_I, C.POINTER(C.c_int)],
     "orlk_graph_begin": [_P], "orlk_graph_end": [_P, C.POINTER(C.c_void_p)], "orlk_graph_launch": [_P, _P],
     "orlk_graph_destroy": [_P], "orlk_stream_sync": [_P],
+    "orlk_stream_create": [C.POINTER(C.c_void_p)], "orlk_stream_destroy": [_P], "orlk_stream_wait_event": [_P, _P],
+    "orlk_event_create_notiming": [C.POINTER(C.c_void_p)],
     "orlk_memcpy_h2d_async": [_P, _P, C.c_size_t, _P], "orlk_memcpy_d2h_async": [_P, _P, C.c_size_t, _P],
     "orlk_memcpy_d2d_async": [_P, _P, C.c_size_t, _P], "orlk_memset_async": [_P, _I, C.c_size_t, _P],
     "orlk_event_create": [C.POINTER(C.c_void_p)], "orlk_event_record": [_P, _P], "orlk_event_sync": [_P],
     "orlk_event_elapsed_ms": [_P, _P, C.POINTER(C.c_float)], "orlk_event_destroy": [_P],
     "orlk_replay_pack": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _L, _P],
     "orlk_replay_gather": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
-    "orlk_gemm_grouped": [_P, _I, _I, _I, _P],
+    "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I],
     "orlk_sizeof_tc_gemm": [],
-    "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
+    "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
     "orlk_narrow_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P],

@@ -13,7 +13,7 @@ constexpr int MAX_NS = 16;
 template <int NST>
 __global__ void __launch_bounds__(256)
 k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
-             int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
+             int64_t w_sk, int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
              int64_t y_gs, int M, int K, int NS, int vec) {
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -42,7 +42,7 @@ k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float
             const float xv = x[k];
 #pragma unroll
             for (int n = 0; n < NST; ++n)
-                if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + k), acc[n]);
+                if (n < NS) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * ldw + (int64_t)k * w_sk), acc[n]);
         }
     }
 #pragma unroll
@@ -426,19 +426,20 @@ __global__ void k_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned lo
 
 extern "C" {
 
-int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_gs, const float* b,
-                    int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G, void* stream) {
+int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, int64_t ldw, int64_t w_sk, int64_t w_gs,
+                    const float* b, int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, int M, int K, int NS, int G,
+                    void* stream) {
     ORLK_REQUIRE(NS >= 1 && NS <= MAX_NS, "NS must be in [1,16]");
     ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
     const int wpb = 8;
     dim3 grid((M + wpb - 1) / wpb, G);
-    const int vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && (x_gs % 4 == 0) && (w_gs % 4 == 0) && aligned16(X) &&
-                    aligned16(W);
+    const int vec = (w_sk == 1) && (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && (x_gs % 4 == 0) && (w_gs % 4 == 0) &&
+                    aligned16(X) && aligned16(W);
     cudaStream_t s = (cudaStream_t)stream;
-    if (NS == 1) k_skinny_fwd<1><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else if (NS <= 4) k_skinny_fwd<4><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else if (NS <= 8) k_skinny_fwd<8><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else k_skinny_fwd<16><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    if (NS == 1) k_skinny_fwd<1><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 4) k_skinny_fwd<4><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 8) k_skinny_fwd<8><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else k_skinny_fwd<16><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
     return check_launch("k_skinny_fwd");
 }
 

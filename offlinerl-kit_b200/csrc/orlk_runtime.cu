@@ -60,6 +60,27 @@ int orlk_graph_destroy(void* graph_exec) {
     return check(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec), "cudaGraphExecDestroy");
 }
 
+int orlk_stream_create(void** stream_out) {
+    ORLK_REQUIRE(stream_out != nullptr, "stream_out is NULL");
+    cudaStream_t s;
+    int rc = check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc) return rc;
+    *stream_out = (void*)s;
+    return 0;
+}
+int orlk_stream_destroy(void* stream) { return check(cudaStreamDestroy((cudaStream_t)stream), "cudaStreamDestroy"); }
+int orlk_stream_wait_event(void* stream, void* ev) {
+    return check(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent");
+}
+int orlk_event_create_notiming(void** ev_out) {
+    ORLK_REQUIRE(ev_out != nullptr, "ev_out is NULL");
+    cudaEvent_t e;
+    int rc = check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc) return rc;
+    *ev_out = (void*)e;
+    return 0;
+}
+
 int orlk_stream_sync(void* stream) { return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
 int orlk_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream) {

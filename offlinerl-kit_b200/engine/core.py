@@ -91,6 +91,7 @@ class Runtime:
         self.cur = self.exec_ptr
         self._keep: List[torch.Tensor] = []
         L.call("orlk_tc_init")
+        L.call("orlk_gemm_init")
 
     # ---- memory helpers (torch owns device memory: plumbing)
     def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
@@ -106,6 +107,17 @@ class Runtime:
 
     # ---- launch builders: each returns a zero-argument closure that enqueues on self.stream
     def gemm(self, problems: Sequence[GP], cfg: int) -> Callable[[], None]:
+        """Grouped fp32 GEMM launch(es): the kernel is specialised on the operand layouts, so problems are bucketed
+        by (a_layout, b_layout) -- one launch per bucket (normally a single one)."""
+        buckets: Dict[Tuple[int, int], List[GP]] = {}
+        for p in problems:
+            buckets.setdefault((p.a_layout, p.b_layout), []).append(p)
+        ops = [self._gemm_bucket(ps, cfg, key) for key, ps in buckets.items()]
+        if len(ops) == 1:
+            return ops[0]
+        return lambda: [op() for op in ops] and None
+
+    def _gemm_bucket(self, problems: Sequence[GP], cfg: int, layouts: Tuple[int, int]) -> Callable[[], None]:
         BM, BN, BK = L.CFG_TILES[cfg]
         arr = (L.GemmDesc * len(problems))()
         tile = 0
@@ -130,7 +142,8 @@ class Runtime:
             tile += tiles_m * tiles_n * splits
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())
-        return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, self.cur)
+        al, bl = layouts
+        return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, al, bl, self.cur)
 
     def tc_gemm(self, *, A: Mat, a_gs: int, B: Mat, b_gs: int, G: int, passes: int, epi: int = L.EPI_NONE,
                 C: Optional[Mat] = None, c_gs: int = 0, c_split_stride: int = 0, CT: Optional[Mat] = None, ct_gs: int = 0,
@@ -211,7 +224,14 @@ class AdamT:
 
 
 class Plan:
-    """An ordered list of launches; runs eagerly (debug) or as one captured CUDA graph."""
+    """An ordered list of launches; runs eagerly (debug) or as one captured CUDA graph.
+
+    ``fork()`` / ``branch(k)`` / ``join()`` mark launches that are independent of each other: branch k > 0 runs on a
+    side stream that waits for everything issued before the fork, and ``join`` makes the main stream wait for all
+    branches.  Under stream capture this becomes parallel branches of the graph (the GPU runs e.g. the weight
+    gradients of different layers concurrently instead of one partially filled launch after another)."""
+
+    N_SIDE = 3
 
     def __init__(self, rt: Runtime, name: str = ""):
         self.rt, self.name = rt, name
@@ -220,13 +240,67 @@ class Plan:
         # The launch closures hold raw device pointers: every tensor they address must be referenced from here (or
         # from the owning learner) for as long as the plan can run.
         self.keep: List[object] = []
+        self._branch = 0
+        self._side = None
+        self._ev_fork = None
+        self._ev_join = None
+        self.flat_ops: List[Tuple[str, Callable[[], None]]] = []      # every launch, branch-agnostic (profiling)
 
     def add(self, label: str, op: Callable[[], None]) -> None:
-        self.ops.append((label, op))
+        b = self._branch
+        self.flat_ops.append((label, op))
+        if b == 0:
+            self.ops.append((label, op))
+        else:
+            self.ops.append((label, lambda op=op, b=b: self._on_side(b, op)))
+
+    # ---- parallel sections
+    def _ensure_side(self) -> None:
+        if self._side is None:
+            self._side, self._ev_join = [], []
+            for _ in range(self.N_SIDE):
+                st, ev = C.c_void_p(), C.c_void_p()
+                L.call("orlk_stream_create", C.byref(st))
+                L.call("orlk_event_create_notiming", C.byref(ev))
+                self._side.append(st)
+                self._ev_join.append(ev)
+            self._ev_fork = C.c_void_p()
+            L.call("orlk_event_create_notiming", C.byref(self._ev_fork))
+
+    def _on_side(self, b: int, op: Callable[[], None]) -> None:
+        rt = self.rt
+        main = rt.cur
+        rt.cur = self._side[b - 1]
+        try:
+            op()
+        finally:
+            rt.cur = main
+
+    def fork(self) -> None:
+        self._ensure_side()
+
+        def op():
+            L.call("orlk_event_record", self._ev_fork, self.rt.cur)
+            for st in self._side:
+                L.call("orlk_stream_wait_event", st, self._ev_fork)
+        self.ops.append(("fork", op))
+        self._branch = 0
+
+    def branch(self, k: int) -> None:
+        assert 0 <= k <= self.N_SIDE
+        self._branch = k
+
+    def join(self) -> None:
+        def op():
+            for st, ev in zip(self._side, self._ev_join):
+                L.call("orlk_event_record", ev, st)
+                L.call("orlk_stream_wait_event", self.rt.cur, ev)
+        self.ops.append(("join", op))
+        self._branch = 0
 
     @property
     def n_launches(self) -> int:
-        return len(self.ops)
+        return sum(1 for lbl, _ in self.ops if lbl not in ("fork", "join"))
 
     def run_eager(self) -> None:
         for _, op in self.ops:

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib as L
 from .core import GP, Mat, Plan
-from .learner import (Learner, MlpRun, check_plain_mlp, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
                       make_gradbuf, wgrad_layout)
 from .nets import GradBuf, ParamSet, adam_descs, dgrad_problem, pick_cfg, wgrad_problem
 from .sac_family import LS_ACTOR, LS_ALPHA, LS_ALPHA_LOSS
@@ -119,8 +119,7 @@ class EDACLearner(_BatchMixin, Learner):
         plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *largs, rt.cur))
         emit_head_dgrad(rt, plan, run_ca, "A.critics")
         emit_hidden_dgrad(rt, plan, run_ca, "A.critics")
-        plan.add("A.critics.dact", rt.gemm([dgrad_problem(cps, 0, e, run_ca.dz(0, e), Mat.of(dA[e]), L.EPI_NONE, None, col0=O,
-                                                          ncols=A) for e in range(E)], L.CFG_SMALL))
+        emit_dact(rt, plan, run_ca, dA, O, A, "A.critics")
         bargs = (run_a.out.data_ptr(), 2 * A, self.noise_views["eps_actor"].data_ptr(), mXa.ptr + 4 * O, mXa.ld, dA.data_ptr(), E,
                  B * A, A, glp.data_ptr(), B, A, run_a.dOut.data_ptr(), 2 * A)
         plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
@@ -154,8 +153,7 @@ class EDACLearner(_BatchMixin, Learner):
             run_g.dOut.fill_(1.0)
             emit_head_dgrad(rt, plan, run_g, "G.chain")
             emit_hidden_dgrad(rt, plan, run_g, "G.chain")
-            plan.add("G.dact", rt.gemm([dgrad_problem(cps, 0, e, run_g.dz(0, e), Mat.of(gin[e]), L.EPI_NONE, None, col0=O, ncols=A)
-                                        for e in range(E)], L.CFG_SMALL))
+            emit_dact(rt, plan, run_g, gin, O, A, "G")
             # 2. loss and gbar
             dargs = (gin.data_ptr(), E, B, A, self.eta, gbar.data_ptr(), div_scratch.data_ptr(),
                      self.loss_dev.data_ptr() + 4 * LS_DIV)

@@ -193,15 +193,16 @@ class MlpRun:
         if any(self.tc_dgrad):
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
         # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
-        big = M >= TC_MIN_ROWS
-        self.narrow0 = big and lays[0].layout == "oi" and lays[0].in_dim <= 32 and store == "P"
-        self.narrow_head = big and self.has_head and lays[n_hidden].layout == "oi" and self.NS <= 32
+        # streaming kernels for the narrow first layer (K <= 32) and the narrow head's weight gradient
+        self.narrow0 = lays[0].layout == "oi" and lays[0].in_dim <= 32
+        self.narrow_head = self.has_head and lays[n_hidden].layout == "oi" and self.NS <= 32 and M >= 128
         self.chunks = L.load().orlk_narrow_wgrad_chunks(M)
         self.w0_part = self.b0_part = self.hw_part = self.hb_part = None
-        if need_grad and self.narrow0:
+        big = M >= TC_MIN_ROWS          # the chunked weight-gradient kernels only pay off for long reductions
+        if need_grad and self.narrow0 and big:
             self.w0_part = rt.zeros(self.chunks, G, lays[0].out_dim, lays[0].in_dim)
             self.b0_part = rt.zeros(self.chunks, G, lays[0].out_dim)
-        if need_grad and self.narrow_head:
+        if need_grad and self.narrow_head and big:
             self.hw_part = rt.zeros(self.chunks, G, self.NS, lays[n_hidden].in_dim)
             self.hb_part = rt.zeros(self.chunks, G, self.NS)
 
@@ -258,7 +259,7 @@ def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     K = lay.in_dim
     if lay.layout == "io":
         assert lay.out_dim == 1, "ensemble heads wider than 1 go through the GEMM path"
-    args = (hin.data_ptr(), K, run.M * K, ps.w(l, 0, run.store), K, lay.w_gs, ps.b(l, 0, run.store), lay.b_gs,
+    args = (hin.data_ptr(), K, run.M * K, ps.w(l, 0, run.store), K, 1, lay.w_gs, ps.b(l, 0, run.store), lay.b_gs,
             run.out.data_ptr(), run.NS, run.M * run.NS, run.M, K, run.NS, G)
     plan.add(f"{tag}.head", lambda: L.call("orlk_skinny_fwd", *args, rt.cur))
 
@@ -294,7 +295,21 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
         plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim)))
 
 
-TC_WGRAD_SPLITS = 16
+def emit_dact(rt: Runtime, plan: Plan, run: MlpRun, dA: torch.Tensor, col0: int, ncols: int, tag: str) -> None:
+    """dL/d(input columns col0 .. col0+ncols) of the first layer: dA[g] = dZ0[g] . W0[:, cols]  (a narrow product)."""
+    ps, G, M = run.ps, run.G, run.M
+    lay = ps.layers[0]
+    K = lay.out_dim
+    if lay.layout == "oi":      # W0[o][i]: element (n=a, k=o) at W0 + (col0+a) + o*in
+        w, ldw, w_sk = ps.w(0, 0) + 4 * col0, 1, lay.in_dim
+    else:                       # W0[i][o]: element (n=a, k=o) at W0 + (col0+a)*out + o
+        w, ldw, w_sk = ps.w(0, 0) + 4 * col0 * lay.out_dim, lay.out_dim, 1
+    args = (run.dZ[0].data_ptr(), K, M * K, w, ldw, w_sk, lay.w_gs, None, 0, dA.data_ptr(), ncols, M * ncols, M, K, ncols, G)
+    plan.add(f"{tag}.dact", lambda: L.call("orlk_skinny_fwd", *args, rt.cur))
+    plan.keep.append(dA)
+
+
+TC_WGRAD_SPLITS = 31
 
 
 def wgrad_layout(ps: ParamSet, n_layers: int, M: int, tc_layers: Sequence[bool] = ()) -> List[Tuple[int, int]]:
@@ -337,6 +352,7 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
     splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
     grad_src = {}
+    launches: List[Tuple[str, Callable[[], None]]] = []       # mutually independent: run on parallel graph branches
     for l in range(n_l):
         cfg, s = layout[l]
         lay = ps.layers[l]
@@ -344,7 +360,7 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
             o, i = lay.out_dim, lay.in_dim
             args = (run.dZ[0].data_ptr(), o, M * o, X[0].ptr, X[0].ld, 0, run.w0_part.data_ptr(), 1, i, o * i, G * o * i,
                     run.b0_part.data_ptr(), o, G * o, None, 0, 0, M, o, i, G)
-            plan.add(f"{tag}.wgrad0.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur))
+            launches.append((f"{tag}.wgrad0.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur)))
             grad_src[(0, "w")] = (run.w0_part.data_ptr(), o * i, G * o * i, run.chunks)
             grad_src[(0, "b")] = (run.b0_part.data_ptr(), o, G * o, run.chunks)
             continue
@@ -352,26 +368,35 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
             K, NS = lay.in_dim, run.NS
             args = (run.H[l - 1].data_ptr(), K, M * K, run.dOut.data_ptr(), NS, M * NS, run.hw_part.data_ptr(), K, 1, NS * K,
                     G * NS * K, None, 0, 0, run.hb_part.data_ptr(), NS, G * NS, M, K, NS, G)
-            plan.add(f"{tag}.wgrad_head.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur))
+            launches.append((f"{tag}.wgrad_head.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur)))
             grad_src[(l, "w")] = (run.hw_part.data_ptr(), NS * K, G * NS * K, run.chunks)
             grad_src[(l, "b")] = (run.hb_part.data_ptr(), NS, G * NS, run.chunks)
             continue
         assert s <= gb.n_slots, (s, gb.n_slots)
         if cfg == -1:
             # dW[o,i] = sum_m dZ^T[o,m] * H^T[i,m]; bias gradient = row sums of dZ^T (a ones-tile MMA)
-            plan.add(f"{tag}.wgrad{l}.tc", rt.tc_gemm(
+            launches.append((f"{tag}.wgrad{l}.tc", rt.tc_gemm(
                 A=_grouped(run.dZT[l], lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt,
                 B=_grouped(run.HT[l - 1], lay.in_dim, M, run.Mt), b_gs=lay.in_dim * run.Mt, G=G, passes=run.tc,
                 C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
-                rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s))
+                rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s)))
             continue
         for g in range(G):
             xin = X[g] if l == 0 else run.h(l - 1, g)
             dy = run.dz(l, g) if l < run.nh else Mat.of(run.dOut[g])
             (big if cfg == L.CFG_BIG else small).append(wgrad_problem(ps, gb, l, g, xin, dy, s))
     if big:
-        plan.add(f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG))
+        launches.append((f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG)))
     if small:
-        plan.add(f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL))
+        launches.append((f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL)))
+    if len(launches) > 1:
+        plan.fork()
+        for i, (label, op) in enumerate(launches):
+            plan.branch(i % (Plan.N_SIDE + 1))
+            plan.add(label, op)
+        plan.join()
+    else:
+        for label, op in launches:
+            plan.add(label, op)
     plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l), grad_src=grad_src,
                                                members=range(G)), groups_ptr))

@@ -252,7 +252,7 @@ def pick_cfg(M: int, N: int) -> int:
         return L.CFG_BIG
     if M * N >= 64 * 64 * 96:
         return L.CFG_MID
-    return L.CFG_SMALL
+    return L.CFG_KPAR      # small layers are latency-bound: whole-K slabs, 4 k-parallel groups per 32 x 32 tile
 
 
 def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: str = "P", Z: Optional[Mat] = None,

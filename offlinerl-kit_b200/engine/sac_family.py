@@ -16,7 +16,7 @@ import torch
 
 from .. import _lib as L
 from .core import Mat, Plan
-from .learner import (Learner, MlpRun, check_plain_mlp, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
                       emit_wgrad_adam, linears_of, make_gradbuf)
 from .nets import ParamSet, dgrad_problem, pick_cfg
 
@@ -146,9 +146,7 @@ class TwinCriticLearner(Learner):
         emit_head_dgrad(rt, plan, cr, "A.critic")
         emit_hidden_dgrad(rt, plan, cr, "A.critic")
         # dL/da = sum over the two critics of dZ1 . W1[:, O:O+A]
-        probs = [dgrad_problem(self.critic_ps, 0, g, cr.dz(0, g), Mat.of(self.dA[g]), L.EPI_NONE, None, col0=O, ncols=A)
-                 for g in range(2)]
-        plan.add("A.critic.dact", rt.gemm(probs, L.CFG_SMALL))
+        emit_dact(rt, plan, cr, self.dA, O, A, "A.critic")
         head = ar.out[0]
         bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), 2, B * A, A,
                  self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
@@ -240,9 +238,14 @@ class CQLLearner(TwinCriticLearner):
                           self.lp_pn, obs)
         plan.add("C.concat", rt.concat([(Xc.rows_(0, B), obs, 1, Mat.of(self.act)),
                                         (Xc.rows_(B + 2 * R, Mc), obs, self.N, Mat.of(v["rand_act"]))]))
-        emit_forward(rt, plan, self.run_target, [Xt, Xt], "C.target")
+        # the target critics on (s', a') and the online critics on the 7936-row batch are independent: two branches
         cr = self.run_critic
+        plan.fork()
+        plan.branch(1)
+        emit_forward(rt, plan, self.run_target, [Xt, Xt], "C.target")
+        plan.branch(0)
         emit_forward(rt, plan, cr, [Xc, Xc], "C.critic")
+        plan.join()
         pol = self.policy
         largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), B, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
                  self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, R, A, self.gamma,

@@ -7,7 +7,7 @@ import torch
 
 from .. import _lib as L
 from .core import AdamT, Mat, Plan
-from .learner import (Learner, MlpRun, check_plain_mlp, emit_forward, emit_head_dgrad, emit_hidden_dgrad, emit_wgrad_adam,
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, emit_wgrad_adam,
                       linears_of, make_gradbuf, polyak_descs)
 from .nets import ParamSet, dgrad_problem
 
@@ -132,8 +132,7 @@ class TD3BCLearner(_BatchMixin, Learner):
             plan.add("P.loss", lambda: L.call("orlk_td3bc_actor_loss", *largs, rt.cur))
             emit_head_dgrad(rt, plan, q1, "P.q1")
             emit_hidden_dgrad(rt, plan, q1, "P.q1")
-            plan.add("P.q1.dact", rt.gemm([dgrad_problem(self.critic_ps, 0, 0, q1.dz(0, 0), Mat.of(self.dA), L.EPI_NONE, None,
-                                                         col0=O, ncols=A)], L.CFG_SMALL))
+            emit_dact(rt, plan, q1, self.dA, O, A, "P.q1")
             bargs = (Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), A, self.dabc.data_ptr(), A, B, A, max_a, ar.dOut.data_ptr(), A)
             plan.add("P.head_bwd", lambda: L.call("orlk_det_actor_bwd", *bargs, rt.cur))
             emit_head_dgrad(rt, plan, ar, "P.actor")

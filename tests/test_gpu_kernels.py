@@ -76,7 +76,7 @@ def _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, epi, splits, with_bias, sum
         _close(cs[:, :N].sum(0), B.double().sum(0), rtol=1e-5, atol=1e-4, msg=tag + " colsum")
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_gemm_layouts_and_ragged_shapes(rt, cfg):
     shapes = [(1, 1, 1), (37, 23, 23), (300, 256, 250), (128, 128, 64), (129, 6, 256), (256, 256, 256), (64, 1, 515)]
     seed = 0
@@ -87,14 +87,14 @@ def test_gemm_layouts_and_ragged_shapes(rt, cfg):
                 _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, 0, 1, with_bias=bool(seed % 2), sums=False, seed=seed)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_gemm_epilogues(rt, cfg):
     for epi in (1, 2, 3, 4):
         _gemm_case(rt, cfg, 200, 136, 96, 0, 1, epi, 1, with_bias=epi in (1, 3), sums=False, seed=100 + epi)
         _gemm_case(rt, cfg, 256, 256, 256, 0, 0, epi, 1, with_bias=epi in (1, 3), sums=False, seed=200 + epi)
 
 
-@pytest.mark.parametrize("cfg", [0, 2])
+@pytest.mark.parametrize("cfg", [0, 2, 3])
 def test_gemm_split_k_and_sums(rt, cfg):
     # wgrad shapes: C[out,in] = dY^T X reduced over rows, with bias row/col sums
     for (M, N, K, splits) in [(256, 256, 7936, 18), (256, 23, 7936, 18), (1, 256, 7936, 9), (12, 256, 256, 4),
@@ -114,7 +114,7 @@ def test_gemm_grouped_many_problems(rt):
         refs.append(A.double().cpu() @ B.double().cpu().t())
         outs.append(Cd)
         keep += [A, B]
-    for cfg in (0, 1, 2):
+    for cfg in (0, 1, 2, 3):
         for o in outs:
             o.zero_()
         rt.gemm(probs, cfg)()
@@ -133,8 +133,15 @@ def test_skinny_fwd_and_dgrad(rt):
         b = torch.randn(G, NS, generator=gen)
         Xd, Wd, bd = X.to(DEV), W.to(DEV), b.to(DEV)
         Y = torch.zeros(G, M, NS, device=DEV)
-        L.call("orlk_skinny_fwd", Xd.data_ptr(), K, M * K, Wd.data_ptr(), K, NS * K, bd.data_ptr(), NS, Y.data_ptr(), NS,
+        L.call("orlk_skinny_fwd", Xd.data_ptr(), K, M * K, Wd.data_ptr(), K, 1, NS * K, bd.data_ptr(), NS, Y.data_ptr(), NS,
                M * NS, M, K, NS, G, rt.cur)
+        # strided weight access (a column block of a [K, ld] matrix): Y = X @ Wk[:, c0:c0+NS]
+        Wk = torch.randn(G, K, NS + 5, generator=gen)
+        Wkd = Wk.to(DEV)
+        Y2 = torch.zeros(G, M, NS, device=DEV)
+        L.call("orlk_skinny_fwd", Xd.data_ptr(), K, M * K, Wkd.data_ptr() + 4 * 3, 1, NS + 5, K * (NS + 5), None, 0,
+               Y2.data_ptr(), NS, M * NS, M, K, NS, G, rt.cur)
+        _close(Y2, torch.einsum("gmk,gkn->gmn", X.double(), Wk.double()[:, :, 3:3 + NS]), msg=f"skinny fwd strided {G,M,K,NS}")
         ref = torch.einsum("gmk,gnk->gmn", X.double(), W.double()) + b.double()[:, None, :]
         _close(Y, ref, msg=f"skinny fwd {G,M,K,NS}")
         dY = torch.randn(G, M, NS, generator=gen)
