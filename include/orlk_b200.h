@@ -171,6 +171,7 @@ int orlk_narrow_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, i
                     int64_t b_gs, float* Y, int64_t ldy, int64_t y_gs, float* YT, int64_t ldyt, int64_t yt_gs, int M, int N,
                     int K, int G, int relu, void* stream);
 int orlk_narrow_wgrad_chunks(int M);
+int orlk_narrow_init(void); /* once per process, outside stream capture */
 int orlk_narrow_wgrad(const float* Wide, int64_t ldw, int64_t w_gs, const float* Nar, int64_t ldn, int64_t n_gs, float* out,
                       int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs, float* wide_sum, int64_t ws_gs, int64_t ws_cs,
                       float* nar_sum, int64_t ns_gs, int64_t ns_cs, int M, int KW, int NS, int G, void* stream);

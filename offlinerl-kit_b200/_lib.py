@@ -87,7 +87,7 @@ _PROTOS = {
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
     "orlk_narrow_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P],
-    "orlk_narrow_wgrad_chunks": [_I],
+    "orlk_narrow_wgrad_chunks": [_I], "orlk_narrow_init": [],
     "orlk_narrow_wgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_philox_fill": [_P, _L, _L, _F, _F, C.c_uint64, _P, _P, _P],
     "orlk_tanh_gauss_sample": [_P, _L, _I, _I, _P, _I, _I, _P, _L, _P, _P, _L, _I, _P, _L, _P],

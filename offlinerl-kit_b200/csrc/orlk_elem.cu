@@ -63,34 +63,43 @@ __global__ void k_skinny_dgrad(const float* __restrict__ dY, int64_t ldy, int64_
                                float* __restrict__ dX, int64_t ldx, int64_t x_gs, float* __restrict__ dXT, int64_t ldxt,
                                int64_t xt_gs, int M, int K, int NS) {
     __shared__ float tile[32][33];
+    __shared__ float dys[32][MAX_NS];
     const int g = blockIdx.z;
-    const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int m0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int k = k0 + tx;
-    float wk[MAX_NS];
-#pragma unroll
-    for (int n = 0; n < MAX_NS; ++n) wk[n] = (n < NS && k < K) ? __ldg(W + g * w_gs + (int64_t)n * ldw + k) : 0.f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int row = ty + 8 * r;
-        const int m = m0 + row;
-        float s = 0.f;
-        if (m < M && k < K) {
-            const float* dy = dY + g * y_gs + (int64_t)m * ldy;
-#pragma unroll
-            for (int n = 0; n < MAX_NS; ++n)
-                if (n < NS) s = fmaf(dy[n], wk[n], s);
-            if (mask != nullptr && !(mask[g * m_gs + (int64_t)m * ldm + k] > 0.f)) s = 0.f;
-            dX[g * x_gs + (int64_t)m * ldx + k] = s;
-        }
-        tile[row][tx] = s;
+    for (int i = ty * 32 + tx; i < 32 * NS; i += 256) {
+        const int r = i / NS, n = i % NS;
+        dys[r][n] = (m0 + r < M) ? dY[g * y_gs + (int64_t)(m0 + r) * ldy + n] : 0.f;
     }
-    if (dXT == nullptr) return;
     __syncthreads();
+    for (int k0 = blockIdx.x * 32; k0 < K; k0 += gridDim.x * 32) {
+        const int k = k0 + tx;
+        float wk[MAX_NS];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int kk = k0 + ty + 8 * r, m = m0 + tx;
-        if (kk < K && m < M) dXT[g * xt_gs + (int64_t)kk * ldxt + m] = tile[tx][ty + 8 * r];
+        for (int n = 0; n < MAX_NS; ++n) wk[n] = (n < NS && k < K) ? __ldg(W + g * w_gs + (int64_t)n * ldw + k) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            const int m = m0 + row;
+            float s = 0.f;
+            if (m < M && k < K) {
+#pragma unroll
+                for (int n = 0; n < MAX_NS; ++n)
+                    if (n < NS) s = fmaf(dys[row][n], wk[n], s);
+                if (mask != nullptr && !(mask[g * m_gs + (int64_t)m * ldm + k] > 0.f)) s = 0.f;
+                dX[g * x_gs + (int64_t)m * ldx + k] = s;
+            }
+            tile[row][tx] = s;
+        }
+        if (dXT != nullptr) {
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int kk = k0 + ty + 8 * r, m = m0 + tx;
+                if (kk < K && m < M) dXT[g * xt_gs + (int64_t)kk * ldxt + m] = tile[tx][ty + 8 * r];
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -448,7 +457,10 @@ int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W
                       int64_t ldxt, int64_t xt_gs, int M, int K, int NS, int G, void* stream) {
     ORLK_REQUIRE(NS >= 1 && NS <= MAX_NS, "NS must be in [1,16]");
     ORLK_REQUIRE(M > 0 && K > 0 && G > 0, "sizes");
-    dim3 grid((K + 31) / 32, (M + 31) / 32, G);
+    // one block per 32-row strip when there are plenty of strips, otherwise also split the k range across blocks
+    const int strips = (M + 31) / 32;
+    const int kblocks = strips * G >= 592 ? 1 : (K + 31) / 32;
+    dim3 grid(kblocks, strips, G);
     k_skinny_dgrad<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs,
                                                                 dXT, ldxt, xt_gs, M, K, NS);
     return check_launch("k_skinny_dgrad");

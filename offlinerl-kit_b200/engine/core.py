@@ -92,6 +92,7 @@ class Runtime:
         self._keep: List[torch.Tensor] = []
         L.call("orlk_tc_init")
         L.call("orlk_gemm_init")
+        L.call("orlk_narrow_init")
 
     # ---- memory helpers (torch owns device memory: plumbing)
     def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
