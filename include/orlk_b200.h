@@ -140,7 +140,8 @@ typedef struct OrlkTcGemm {
     int32_t epi;      /* ORLK_EPI_NONE | ORLK_EPI_RELU | ORLK_EPI_RELU_MASK */
     int32_t k_splits; /* as returned by orlk_tc_effective_splits */
     int32_t passes;   /* 1 or 3 */
-    int32_t pad_;
+    int32_t n_tile;   /* output columns per CTA (multiple of 16 dividing N); 0 = N.  Small-M layers use 32 so that
+                         (M/128) x (N/32) CTAs share the work */
 } OrlkTcGemm;
 int orlk_tc_init(void);
 int orlk_tc_gemm(const OrlkTcGemm* params_host, void* stream);

@@ -54,7 +54,7 @@ class TcGemm(C.Structure):
                 ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_gs", C.c_int64),
                 ("rowsum", C.c_void_p), ("rowsum_gs", C.c_int64), ("rowsum_split_stride", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("G", C.c_int32),
-                ("epi", C.c_int32), ("k_splits", C.c_int32), ("passes", C.c_int32), ("pad_", C.c_int32)]
+                ("epi", C.c_int32), ("k_splits", C.c_int32), ("passes", C.c_int32), ("n_tile", C.c_int32)]
 
 
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)

@@ -6,7 +6,7 @@
 // One CTA = one 128-row tile of A x all N (<= 256) columns, for one k-split.  The fp32 accumulator tile lives in
 // TMEM (128 lanes x N columns).  Precision modes:
 //   passes = 1 : one TF32 MMA per product (10-bit mantissa operands, fp32 accumulate)  -- "fast" mode
-//   passes = 3 : operands are split in shared memory into hi = tf32(x) and lo = x - hi and three MMAs
+//   passes = 3 : lo = x - tf32_trunc(x) is written next to each raw tile in shared memory and three MMAs
 //                (hi*hi + lo*hi + hi*lo) are accumulated: ~2^-21 relative error per product -- fp32-parity mode.
 // Optional fused outputs: row-major C, transposed C^T (the K-major operand of the next weight-gradient GEMM),
 // bias + ReLU / ReLU-mask epilogues, and row sums of A (bias gradients) computed by the tensor core against a
@@ -15,6 +15,7 @@
 // Replaces the 256x256 nn.Linear forward / dgrad / wgrad GEMMs of both critics over the 7936-row CQL critic batch
 // (reference: nets/mlp.py:22 forward; autograd backward of the same layers; cql.py:133-190).
 #include <cuda.h>
+#include <stdlib.h>
 #include "orlk_common.cuh"
 using namespace orlk;
 
@@ -26,6 +27,8 @@ constexpr int B_BYTES = BN_MAX * BK * 4;                  // 32 KB
 constexpr int ONES_BYTES = 16 * BK * 4;                   // 2 KB
 constexpr int TMEM_COLS = 512;
 constexpr int ROWSUM_COL = 256;
+constexpr int MAX_STAGES = 8;
+constexpr int FIXED_SMEM = 8192;                          // ones tile, barriers, staged bias, mask bits
 constexpr int NUM_THREADS = 320;                          // warp0 TMA, warp1 MMA, warps2-5 split + epilogue, warps6-9 mask
 
 struct TcParams {
@@ -34,7 +37,8 @@ struct TcParams {
     const float* bias; int64_t bias_gs;
     const float* aux; int64_t ldaux, aux_gs;
     float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
-    int M, N, K, G, epi, k_splits, slabs_per_split, tiles_m;
+    int M, N, K, G, epi, k_splits, slabs_per_split, tiles_m, tiles_n, NT;   // NT = output columns per CTA (n-tile)
+    int stages, stage_bytes;   // depth of the TMA ring and bytes per stage (depend on NT and the precision mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,52 +110,57 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
-__device__ __forceinline__ void split_tf32(float4& v, float4& lo) {
-    float4 hi;
-    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-    v = hi;
+// The tensor core reads an fp32 word as TF32 by IGNORING the 13 low mantissa bits (measured: a kernel that rewrites
+// hi = x & 0xFFFFE000 in shared memory and one that leaves x untouched give bit-identical results, while
+// lo = x - cvt.rna.tf32(x) is off by 2^-11).  So the raw tile already is the "hi" operand and only
+// lo = x - trunc_tf32(x) (exact in fp32) has to be written.
+__device__ __forceinline__ float4 lo_tf32(const float4& v) {
+    return make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
+                       v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                       v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u),
+                       v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
 }
 
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    constexpr int STAGES = PASSES == 3 ? 2 : 4;
-    constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment
     // (offset arithmetic on the __shared__ array keeps the address space known to the compiler: LDS/STS, not generic)
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* ones = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
-    uint64_t* full = bars;                  // [STAGES]  TMA bytes landed
-    uint64_t* splitb = bars + STAGES;       // [STAGES]  hi/lo split done (PASSES == 3)
-    uint64_t* empty = bars + 2 * STAGES;    // [STAGES]  MMAs that read the stage have completed
-    uint64_t* accum = bars + 3 * STAGES;    // accumulator tile complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
-    float* bias_s = reinterpret_cast<float*>(bars + 3 * STAGES + 2);     // [BN_MAX] bias staged once per CTA
+    uint8_t* fixed = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ones = fixed;                                               // [16 x 32] fp32 ones (bias-gradient MMA)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fixed + ONES_BYTES);
+    uint64_t* full = bars;                          // [MAX_STAGES]  TMA bytes landed
+    uint64_t* splitb = bars + MAX_STAGES;           // [MAX_STAGES]  hi/lo split done (PASSES == 3)
+    uint64_t* empty = bars + 2 * MAX_STAGES;        // [MAX_STAGES]  MMAs that read the stage have completed
+    uint64_t* accum = bars + 3 * MAX_STAGES;        // accumulator tile complete
+    uint64_t* maskbar = bars + 3 * MAX_STAGES + 1;  // mask tile complete (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 2);
+    float* bias_s = reinterpret_cast<float*>(fixed + ONES_BYTES + 256);  // [BN_MAX] bias staged once per CTA
     uint32_t* mask_s = reinterpret_cast<uint32_t*>(bias_s + BN_MAX);     // [BM][BN_MAX/32] ReLU-mask bits of the tile
-    uint64_t* maskbar = reinterpret_cast<uint64_t*>(mask_s + BM * (BN_MAX / 32));   // mask tile complete (128 arrivals)
+    uint8_t* smem = fixed + FIXED_SMEM;                                  // the operand ring
+    const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int idx = blockIdx.x;
     const int split = idx % p.k_splits;
     idx /= p.k_splits;
+    const int tile_n = idx % p.tiles_n;
+    idx /= p.tiles_n;
     const int tile_m = idx % p.tiles_m;
     const int g = idx / p.tiles_m;
+    const int NT = p.NT;                       // this CTA owns output columns [n0, n0 + NT)
+    const int n0 = tile_n * NT;
     const int total_slabs = (p.K + BK - 1) / BK;
     const int slab0 = split * p.slabs_per_split;
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
-    const bool want_rowsum = p.rowsum != nullptr;
+    const bool want_rowsum = p.rowsum != nullptr && tile_n == 0;
 
+    const int b_bytes = NT * BK * 4;
     auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
     auto b_raw = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES; };
-    auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES + B_BYTES; };
-    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+    auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES + b_bytes; };
+    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + b_bytes; };
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -174,8 +183,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
             fence_proxy_async();
         }
-        const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs : nullptr;
-        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < p.N) ? __ldg(bg + i) : 0.f;
+        const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs + n0 : nullptr;
+        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < NT) ? __ldg(bg + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -184,7 +193,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
-        const uint32_t tx_bytes = A_BYTES + (uint32_t)p.N * BK * 4;
+        const uint32_t tx_bytes = A_BYTES + (uint32_t)NT * BK * 4;
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -192,11 +201,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_expect_tx(smem_u32(&full[s]), tx_bytes);
             const int k0 = (slab0 + it) * BK;
             tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, g);
-            tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, 0, g);
+            tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        const uint32_t idesc = instr_desc_tf32(BM, p.N);
+        const uint32_t idesc = instr_desc_tf32(BM, NT);
         const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
         const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
         for (int it = 0; it < nslabs; ++it) {
@@ -229,8 +238,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // 128-column group q gives one ballot word:  bit j of mask_s[row][4q+e]  <=>  aux[m][128q + 4j + e] > 0.
         if (p.epi == ORLK_EPI_RELU_MASK) {
             const int w = warp - 6;
-            const float* auxg = p.aux + (int64_t)g * p.aux_gs;
-            const bool vec = (p.ldaux % 4 == 0) && (p.aux_gs % 4 == 0) && aligned16(p.aux) && (p.N % 4 == 0);
+            const float* auxg = p.aux + (int64_t)g * p.aux_gs + n0;
+            const bool vec = (p.ldaux % 4 == 0) && (p.aux_gs % 4 == 0) && aligned16(p.aux) && (NT % 4 == 0);
             constexpr int RB = 8;                                   // rows per batch
             for (int r0 = 0; r0 < 32; r0 += RB) {
                 float4 a[RB][2];
@@ -241,14 +250,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int q = 0; q < 2; ++q) {
                         const int n = q * 128 + 4 * lane;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < p.M && n < p.N) {
+                        if (m < p.M && n < NT) {
                             const float* src = auxg + (int64_t)m * p.ldaux + n;
                             if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
                             else {
                                 v.x = __ldg(src);
-                                if (n + 1 < p.N) v.y = __ldg(src + 1);
-                                if (n + 2 < p.N) v.z = __ldg(src + 2);
-                                if (n + 3 < p.N) v.w = __ldg(src + 3);
+                                if (n + 1 < NT) v.y = __ldg(src + 1);
+                                if (n + 2 < NT) v.z = __ldg(src + 2);
+                                if (n + 3 < NT) v.w = __ldg(src + 3);
                             }
                         }
                         a[rr][q] = v;
@@ -276,7 +285,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int t = threadIdx.x - 64;                     // 0..127
         if (PASSES == 3) {
             // -------------------------------------------------------------- operand splitter
-            const int nB4 = p.N * BK / 4;
+            const int nB4 = NT * BK / 4;
             for (int it = 0; it < nslabs; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -287,18 +296,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 float4* __restrict__ bl = reinterpret_cast<float4*>(b_lo(s));
                 // A: 1024 float4 -> 8 per thread, all loads issued before the first store
                 {
-                    float4 v[8], lo[8];
+                    float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = ar[t + 128 * j];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        split_tf32(v[j], lo[j]);
-                        ar[t + 128 * j] = v[j];
-                        al[t + 128 * j] = lo[j];
-                    }
+                    for (int j = 0; j < 8; ++j) al[t + 128 * j] = lo_tf32(v[j]);
                 }
                 for (int i0 = 0; i0 < nB4; i0 += 128 * 8) {
-                    float4 v[8], lo[8];
+                    float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int i = i0 + t + 128 * j;
@@ -307,11 +312,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int i = i0 + t + 128 * j;
-                        if (i < nB4) {
-                            split_tf32(v[j], lo[j]);
-                            br[i] = v[j];
-                            bl[i] = lo[j];
-                        }
+                        if (i < nB4) bl[i] = lo_tf32(v[j]);
                     }
                 }
                 fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
@@ -327,11 +328,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int m = tile_m * BM + row;
         const bool row_ok = m < p.M;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* C = p.C ? p.C + (int64_t)g * p.c_gs + (int64_t)split * p.c_split_stride + (int64_t)m * p.ldc : nullptr;
-        float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + m : nullptr;
-        const bool vec_ok = (p.N % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
+        float* C = p.C ? p.C + (int64_t)g * p.c_gs + (int64_t)split * p.c_split_stride + (int64_t)m * p.ldc + n0 : nullptr;
+        float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + (int64_t)n0 * p.ldct + m : nullptr;
+        const bool vec_ok = (NT % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
                             (p.c_split_stride % 4 == 0);
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
+        for (int c0 = 0; c0 < NT; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
             tmem_wait_ld();
@@ -362,19 +363,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (vec_ok) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
-                            if (c0 + 4 * j4 < p.N)
+                            if (c0 + 4 * j4 < NT)
                                 *reinterpret_cast<float4*>(C + c0 + 4 * j4) =
                                     make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c0 + j < p.N) C[c0 + j] = x[j];
+                            if (c0 + j < NT) C[c0 + j] = x[j];
                     }
                 }
                 if (CT != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < p.N) CT[(int64_t)(c0 + j) * p.ldct] = x[j];   // coalesced across the warp's rows
+                        if (c0 + j < NT) CT[(int64_t)(c0 + j) * p.ldct] = x[j];    // coalesced across the warp's rows
                 }
             }
         }
@@ -435,17 +436,20 @@ int make_map(CUtensorMap* map, const float* base, int64_t ld, int64_t gs, int ro
 
 extern "C" int orlk_sizeof_tc_gemm(void) { return (int)sizeof(OrlkTcGemm); }
 
-static size_t tc_smem_bytes(int passes) {
-    const int stages = passes == 3 ? 2 : 4;
-    const int stage_bytes = (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1);
-    return (size_t)stages * stage_bytes + ONES_BYTES + 256 + BN_MAX * 4 + BM * (BN_MAX / 32) * 4 + 64 + 1024;
+constexpr int MAX_DYN_SMEM = 227 * 1024;
+
+// ring geometry for (n-tile, precision): as many stages as fit next to the fixed region, at most MAX_STAGES
+static void tc_ring(int NT, int passes, int* stages, int* stage_bytes) {
+    *stage_bytes = (A_BYTES + NT * BK * 4) * (passes == 3 ? 2 : 1);
+    int n = (MAX_DYN_SMEM - 1024 - FIXED_SMEM) / *stage_bytes;
+    *stages = n > MAX_STAGES ? MAX_STAGES : (n < 1 ? 1 : n);
 }
 
-// Opt in to > 48 KB of dynamic shared memory once, outside any stream capture.
+// Opt in to the full 227 KB of dynamic shared memory once, outside any stream capture.
 extern "C" int orlk_tc_init(void) {
-    int rc = check(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(1)), "smem attr <1>");
+    int rc = check(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM), "smem attr <1>");
     if (rc) return rc;
-    return check(cudaFuncSetAttribute(k_tc_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(3)), "smem attr <3>");
+    return check(cudaFuncSetAttribute(k_tc_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM), "smem attr <3>");
 }
 
 extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
@@ -467,7 +471,9 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, q->G, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, q->N);
+    const int NT = (q->n_tile > 0) ? q->n_tile : q->N;
+    ORLK_REQUIRE(NT >= 16 && NT <= BN_MAX && NT % 16 == 0 && q->N % NT == 0, "n_tile must be a multiple of 16 that divides N");
+    rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
     if (rc) return rc;
 
     TcParams p;
@@ -478,9 +484,11 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.rowsum = q->rowsum; p.rowsum_gs = q->rowsum_gs; p.rowsum_split_stride = q->rowsum_split_stride;
     p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
     p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
+    p.NT = NT; p.tiles_n = q->N / NT;
 
-    const size_t smem = tc_smem_bytes(q->passes);
-    const int grid = q->G * p.tiles_m * splits;
+    tc_ring(NT, q->passes, &p.stages, &p.stage_bytes);
+    const size_t smem = 1024 + FIXED_SMEM + (size_t)p.stages * p.stage_bytes;
+    const int grid = q->G * p.tiles_m * p.tiles_n * splits;
     cudaStream_t s = (cudaStream_t)stream;
     if (q->passes == 3) k_tc_gemm<3><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
     else k_tc_gemm<1><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);

@@ -82,12 +82,12 @@ class EDACLearner(_BatchMixin, Learner):
         rt, B, O, A, E, pol = self.rt, self.B, self.O, self.A, self.E, self.policy
         cps, aps = self.critic_ps, self.actor_ps
         nh = self.nh_c
-        run_a = MlpRun(rt, aps, B, self.nh_a, need_grad=True)
-        run_ca = MlpRun(rt, cps, B, nh, need_grad=True)                       # Q_e(s, a~pi) in the actor phase
-        run_an = MlpRun(rt, aps, B, self.nh_a, need_grad=False)
-        run_t = MlpRun(rt, cps, B, nh, need_grad=False, store="T")
-        run_c = MlpRun(rt, cps, B, nh, need_grad=True)                        # Q_e(s, a_data): TD backward
-        run_g = MlpRun(rt, cps, B, nh, need_grad=True, share_forward=run_c)   # same activations: input-gradient chain
+        run_a = self.mlp_run(aps, B, self.nh_a, need_grad=True)
+        run_ca = self.mlp_run(cps, B, nh, need_grad=True)                       # Q_e(s, a~pi) in the actor phase
+        run_an = self.mlp_run(aps, B, self.nh_a, need_grad=False)
+        run_t = self.mlp_run(cps, B, nh, need_grad=False, store="T")
+        run_c = self.mlp_run(cps, B, nh, need_grad=True)                        # Q_e(s, a_data): TD backward
+        run_g = self.mlp_run(cps, B, nh, need_grad=True, share_forward=run_c)   # same activations: input-gradient chain
         Xa, Xt, Xd = rt.zeros(B, O + A), rt.zeros(B, O + A), rt.zeros(B, O + A)
         logp_a, lp_next, glp = rt.zeros(B), rt.zeros(B), rt.zeros(B)
         dA = rt.zeros(E, B, A)

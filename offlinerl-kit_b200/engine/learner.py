@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .core import GP, AdamT, Mat, Plan, Runtime, get_runtime
-from .nets import (GradBuf, Layer, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, fwd_problem, pick_cfg,
+from .nets import (GradBuf, Layer, ParamSet, TC_MIN_ROWS, TC_MIN_ROWS_FWD, tc_n_tile, adam_descs, dgrad_problem, fwd_problem, pick_cfg,
                    tc_ok_dgrad, tc_ok_fwd, tc_ok_wgrad, wgrad_problem, wgrad_splits)
 
 MAX_GROUPS = 16
@@ -122,6 +122,11 @@ class Learner:
     def tc_passes(self) -> int:
         return PRECISIONS[self.precision]
 
+    def mlp_run(self, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, **kw) -> "MlpRun":
+        """MlpRun with this learner's precision mode (tensor-core passes for the eligible wide layers)."""
+        kw.setdefault("tc_passes", self.tc_passes)
+        return MlpRun(self.rt, ps, M, n_hidden, need_grad, **kw)
+
     def refresh(self) -> None:
         """Host-side writes to the parameters (load_state_dict, custom init) invalidate derived copies."""
         for ps in self.param_sets:
@@ -169,7 +174,7 @@ class MlpRun:
     def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P",
                  tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
-        self.tc = tc_passes if M >= TC_MIN_ROWS else 0
+        self.tc = tc_passes if M >= TC_MIN_ROWS_FWD else 0
         self.Mt = (M + 3) // 4 * 4
         self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
         lays = ps.layers
@@ -234,7 +239,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
             K, N = lay.in_dim, lay.out_dim
             plan.add(f"{tag}.fwd{l}.tc", rt.tc_gemm(
                 A=_grouped(run.H[l - 1], M, K, K), a_gs=M * K, B=Mat(ps.w(l, 0, run.store), N, K, K), b_gs=lay.w_gs, G=G,
-                passes=run.tc, epi=L.EPI_RELU, C=_grouped(run.H[l], M, N, N), c_gs=M * N,
+                passes=run.tc, n_tile=tc_n_tile(M, N), epi=L.EPI_RELU, C=_grouped(run.H[l], M, N, N), c_gs=M * N,
                 CT=_grouped(run.HT[l], N, M, run.Mt) if run.HT[l] is not None else None, ct_gs=N * run.Mt,
                 bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
             continue
@@ -286,7 +291,7 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
             K, N = lay.out_dim, lay.in_dim
             plan.add(f"{tag}.dgrad{l}.tc", rt.tc_gemm(
                 A=_grouped(run.dZ[l], M, K, K), a_gs=M * K, B=Mat(ps.wt(l, 0), N, K, K), b_gs=lay.w_gs, G=G,
-                passes=run.tc, epi=L.EPI_RELU_MASK, C=_grouped(run.dZ[l - 1], M, N, N), c_gs=M * N,
+                passes=run.tc, n_tile=tc_n_tile(M, N), epi=L.EPI_RELU_MASK, C=_grouped(run.dZ[l - 1], M, N, N), c_gs=M * N,
                 CT=_grouped(run.dZT[l - 1], N, M, run.Mt) if run.dZT[l - 1] is not None else None, ct_gs=N * run.Mt,
                 aux=_grouped(run.H[l - 1], M, N, N), aux_gs=M * N))
             continue

@@ -231,15 +231,21 @@ class GradBuf:
 
 
 # ---------------------------------------------------------------------------------------------- emitters
-TC_MIN_ROWS = 1024      # below this the 128-row tiles cannot fill the machine; the SIMT kernel is used instead
+TC_MIN_ROWS = 1024      # weight gradients: below this the reduction is too short for the tensor-core kernel
+TC_MIN_ROWS_FWD = 128   # forward / dgrad: small row counts tile the OUTPUT columns (32 per CTA) to get enough CTAs
+
+
+def tc_n_tile(M: int, N: int) -> int:
+    """Output columns per CTA: everything for large M (one 128 x N accumulator), 32-column strips for small M."""
+    return 0 if M >= TC_MIN_ROWS or N % 32 != 0 else 32
 
 
 def tc_ok_fwd(lay: Layer, M: int) -> bool:
-    return lay.layout == "oi" and lay.in_dim % 4 == 0 and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and M >= TC_MIN_ROWS
+    return lay.layout == "oi" and lay.in_dim % 4 == 0 and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and M >= TC_MIN_ROWS_FWD
 
 
 def tc_ok_dgrad(lay: Layer, M: int) -> bool:
-    return lay.layout == "oi" and lay.out_dim % 4 == 0 and lay.in_dim % 16 == 0 and lay.in_dim <= 256 and M >= TC_MIN_ROWS
+    return lay.layout == "oi" and lay.out_dim % 4 == 0 and lay.in_dim % 16 == 0 and lay.in_dim <= 256 and M >= TC_MIN_ROWS_FWD
 
 
 def tc_ok_wgrad(lay: Layer, M: int) -> bool:

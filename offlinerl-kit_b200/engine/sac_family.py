@@ -157,8 +157,8 @@ class TwinCriticLearner(Learner):
 
     def _alloc_actor_phase(self) -> None:
         rt, B, A = self.rt, self.B, self.A
-        self.run_actor = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=True)
-        self.run_critic_a = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True)
+        self.run_actor = self.mlp_run(self.actor_ps, B, self.nh_a, need_grad=True)
+        self.run_critic_a = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=True)
         self.Xa = rt.zeros(B, self.O + A)
         self.logp_a = rt.zeros(B)
         self.glp = rt.zeros(B)
@@ -211,9 +211,9 @@ class CQLLearner(TwinCriticLearner):
     def _build(self) -> None:
         rt, B, O, A, R, Mc = self.rt, self.B, self.O, self.A, self.R, self.Mc
         self._alloc_actor_phase()
-        self.run_actor_b = MlpRun(rt, self.actor_ps, 2 * B, self.nh_a, need_grad=False)
-        self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
-        self.run_critic = MlpRun(rt, self.critic_ps, Mc, self.nh_c, need_grad=True, tc_passes=self.tc_passes)
+        self.run_actor_b = self.mlp_run(self.actor_ps, 2 * B, self.nh_a, need_grad=False)
+        self.run_target = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        self.run_critic = self.mlp_run(self.critic_ps, Mc, self.nh_c, need_grad=True)
         self.Xt = rt.zeros(B, O + A)
         self.Xc = rt.zeros(Mc, O + A)
         self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(B), rt.zeros(R), rt.zeros(R)
@@ -300,9 +300,9 @@ class SACLearner(TwinCriticLearner):
     def _build(self) -> None:
         rt, B, O, A = self.rt, self.B, self.O, self.A
         self._alloc_actor_phase()
-        self.run_actor_n = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=False)
-        self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
-        self.run_critic = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True)
+        self.run_actor_n = self.mlp_run(self.actor_ps, B, self.nh_a, need_grad=False)
+        self.run_target = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        self.run_critic = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=True)
         self.Xd, self.Xt = rt.zeros(B, O + A), rt.zeros(B, O + A)
         self.lp_next = rt.zeros(B)
         self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])

@@ -87,11 +87,11 @@ class TD3BCLearner(_BatchMixin, Learner):
     def _build(self) -> None:
         rt, B, O, A, pol = self.rt, self.B, self.O, self.A, self.policy
         max_a = float(pol._max_action)
-        self.run_actor_t = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=False, store="T")
-        self.run_target = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=False, store="T")
-        self.run_critic = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True)
-        self.run_actor = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=True)
-        self.run_q1 = MlpRun(rt, self.critic_ps, B, self.nh_c, need_grad=True, members=1)
+        self.run_actor_t = self.mlp_run(self.actor_ps, B, self.nh_a, need_grad=False, store="T")
+        self.run_target = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        self.run_critic = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=True)
+        self.run_actor = self.mlp_run(self.actor_ps, B, self.nh_a, need_grad=True)
+        self.run_q1 = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=True, members=1)
         self.Xd, self.Xt, self.Xa = rt.zeros(B, O + A), rt.zeros(B, O + A), rt.zeros(B, O + A)
         self.dA, self.dabc = rt.zeros(B, A), rt.zeros(B, A)
         self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
@@ -204,11 +204,11 @@ class IQLLearner(_BatchMixin, Learner):
 
     def _build(self) -> None:
         rt, B, O, A, pol = self.rt, self.B, self.O, self.A, self.policy
-        self.run_qt = MlpRun(rt, self.q_ps, B, self.nh_q, need_grad=False, store="T")
-        self.run_v = MlpRun(rt, self.v_ps, B, self.nh_v, need_grad=True)
-        self.run_q = MlpRun(rt, self.q_ps, B, self.nh_q, need_grad=True)
-        self.run_v2 = MlpRun(rt, self.v_ps, 2 * B, self.nh_v, need_grad=False)
-        self.run_actor = MlpRun(rt, self.actor_ps, B, self.nh_a, need_grad=True)
+        self.run_qt = self.mlp_run(self.q_ps, B, self.nh_q, need_grad=False, store="T")
+        self.run_v = self.mlp_run(self.v_ps, B, self.nh_v, need_grad=True)
+        self.run_q = self.mlp_run(self.q_ps, B, self.nh_q, need_grad=True)
+        self.run_v2 = self.mlp_run(self.v_ps, 2 * B, self.nh_v, need_grad=False)
+        self.run_actor = self.mlp_run(self.actor_ps, B, self.nh_a, need_grad=True)
         self.Xd = rt.zeros(B, O + A)
         self.qmin = rt.zeros(B)
         self.dsigma = rt.zeros(A)

@@ -70,3 +70,20 @@ for k, v in out.items():
     print(f"{k:32s} {v:8.2f} us")
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)
+
+# ---- small-M study: where do ~10 us per layer go?
+print("small-M (G=2, M=256, N=256, n_tile=32):")
+As = torch.randn(2, 256, 256, device="cuda")
+Bs = torch.randn(2, 256, 256, device="cuda")
+Cs = torch.zeros(2, 256, 256, device="cuda")
+for passes in (1, 3):
+    for K in (32, 256):
+        for nt in (32, 64, 256):
+            for outs in ("none", "C"):
+                kw = dict(C=Mat(Cs.data_ptr(), 256, 256, 256), c_gs=256 * 256) if outs == "C" else {}
+                op = rt.tc_gemm(A=Mat(As.data_ptr(), 256, K, 256), a_gs=256 * 256, B=Mat(Bs.data_ptr(), 256, K, 256), b_gs=256 * 256,
+                                G=2, passes=passes, n_tile=nt, **kw)
+                print(f"  p{passes} K={K:3d} n_tile={nt:3d} out={outs:4s} {timeit(op):7.2f} us")
+# an empty-ish kernel for the launch floor
+e = torch.zeros(1, device="cuda")
+print("  launch floor (philox 4 elements):", timeit(lambda: L.call("orlk_philox_fill", e.data_ptr(), 1, 0, 0.0, 1.0, 1, None, None, rt.cur)))

@@ -431,7 +431,7 @@ def test_replay_gather_bit_exact_and_ring(rt):
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
-def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed):
+def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed, n_tile=0):
     from offlinerlkit_b200 import _lib as L
     from offlinerlkit_b200.engine.core import Mat
     gen = torch.Generator().manual_seed(seed)
@@ -449,7 +449,8 @@ def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsu
                     CT=Mat(CTd.data_ptr(), N, M, M) if want_ct else None, ct_gs=N * M,
                     bias=bd.data_ptr() if with_bias else 0, bias_gs=N,
                     aux=Mat(auxd.data_ptr(), M, N, N) if epi == L.EPI_RELU_MASK else None, aux_gs=M * N,
-                    rowsum=rs.data_ptr() if want_rowsum else 0, rowsum_gs=M, rowsum_split_stride=G * M, k_splits=splits)
+                    rowsum=rs.data_ptr() if want_rowsum else 0, rowsum_gs=M, rowsum_split_stride=G * M, k_splits=splits,
+                    n_tile=n_tile)
     op()
     torch.cuda.synchronize()
     ref = torch.einsum("gmk,gnk->gmn", A.double(), B.double())
@@ -487,6 +488,10 @@ def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
     errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 16, False, False, True, 5))    # critic wgrad + bias grads
     errs.append(_tc_case(rt, 3, 200, 64, 96, passes, L.EPI_NONE, 1, True, True, True, 6))          # narrow N, K not /128
     errs.append(_tc_case(rt, 1, 1000, 208, 224, passes, L.EPI_RELU, 1, True, False, False, 7))     # N = 208 (13 x 16)
+    # small-M layers: the output columns are tiled 32 per CTA
+    errs.append(_tc_case(rt, 2, 256, 256, 256, passes, L.EPI_RELU, 1, True, True, False, 8, n_tile=32))
+    errs.append(_tc_case(rt, 2, 512, 256, 256, passes, L.EPI_RELU_MASK, 1, False, True, False, 9, n_tile=32))
+    errs.append(_tc_case(rt, 1, 200, 192, 64, passes, L.EPI_NONE, 1, True, False, True, 10, n_tile=64))
     print(f"passes={passes}: relative errors {['%.2e' % e for e in errs]}")
 
 
