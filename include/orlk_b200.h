@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 7
+#define ORLK_ABI_VERSION 8
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -146,6 +146,10 @@ typedef struct OrlkTcGemm {
 int orlk_tc_init(void);
 int orlk_tc_gemm(const OrlkTcGemm* params_host, void* stream);
 int orlk_tc_effective_splits(int K, int want);
+/* Profiling aid: when dev_buf is non-NULL every CTA of later orlk_tc_gemm launches writes 16 %globaltimer stamps
+ * (ns) to dev_buf[16 * blockIdx.x ..]: 0 start, 1 predecessor complete, 2 prologue done, 3 first tile landed,
+ * 4 first MMA issued, 5 last MMA issued, 6 accumulator ready, 7 epilogue stores issued, 8..15 k-slab 0..7 landed.  NULL turns it off. */
+int orlk_tc_set_trace(void* dev_buf);
 int orlk_sizeof_tc_gemm(void);
 
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;

@@ -34,6 +34,35 @@ inline int check(cudaError_t e, const char* what) {
         }                                               \
     } while (0)
 
+// Programmatic dependent launch.  Every kernel of the library is launched with the stream-serialisation attribute and
+// starts with pdl_enter(): it lets the NEXT kernel of the stream be scheduled right away (its CTAs become resident and
+// run their own prologue) and then blocks until the PREVIOUS kernel has completed and its writes are visible.  Because
+// every kernel waits on its predecessor before touching global memory, ordering stays transitive along the stream; what
+// is hidden is the ~1-2 us launch + prologue latency between dependent graph nodes.  ORLK_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -16,6 +16,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __global__ void k_dyn_input(const float* __restrict__ obs, int64_t ld_obs, const float* __restrict__ act, int64_t ld_act,
                             const float* __restrict__ mu, const float* __restrict__ sd, int S, int O, int A,
                             float* __restrict__ X, int64_t ldx) {
+    orlk::pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int W = O + A;
     if (i >= (int64_t)S * W) return;
@@ -27,6 +28,7 @@ __global__ void k_dyn_input(const float* __restrict__ obs, int64_t ld_obs, const
 // dst[e][r][:] = src[idx[e*idx_ld + r0 + r]][:]   (per-member bootstrap batch, ensemble_dynamics.py:134,144,186-187)
 __global__ void k_gather_rows(const float* __restrict__ src, int64_t ld_src, int w, const int64_t* __restrict__ idx,
                               int64_t idx_ld, int64_t r0, int E, int R, float* __restrict__ dst, int64_t ld_dst, int64_t dst_es) {
+    orlk::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (int64_t)E * R) return;
@@ -40,6 +42,7 @@ __global__ void k_gather_rows(const float* __restrict__ src, int64_t ld_src, int
 // sum of squares of [n] floats in 4096-element chunks (weight-decay term of the reported loss)
 __global__ void __launch_bounds__(256)
 k_sumsq(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ partial) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const int64_t base = (int64_t)blockIdx.x * 4096;
     float s = 0.f;
@@ -58,6 +61,7 @@ __global__ void __launch_bounds__(1024)
 k_dyn_nll(const float* __restrict__ out, const float* __restrict__ y, int E, int Bn, int D, const float* __restrict__ max_lv,
           const float* __restrict__ min_lv, float coef, const float* __restrict__ decay_partials, int n_decay,
           float* __restrict__ dout, float* __restrict__ dmax, float* __restrict__ dmin, float* __restrict__ out_loss) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const float inv = 1.f / ((float)Bn * (float)D);
     float loss = 0.f;
@@ -110,6 +114,7 @@ k_dyn_nll(const float* __restrict__ out, const float* __restrict__ y, int E, int
 // per-member holdout MSE of the mean head (ensemble_dynamics.py:210-217): one CTA per member
 __global__ void __launch_bounds__(256)
 k_dyn_val_mse(const float* __restrict__ out, const float* __restrict__ y, int Bn, int D, float* __restrict__ mse) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const int e = blockIdx.x;
     float s = 0.f;
@@ -150,6 +155,7 @@ __global__ void k_dyn_step(const float* __restrict__ out, int E, int S, int D, c
                            float penalty_coef,
                            float* __restrict__ next_obs, float* __restrict__ reward, float* __restrict__ raw_reward,
                            float* __restrict__ penalty, unsigned char* __restrict__ terminal) {
+    orlk::pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int O = D - 1;
@@ -186,6 +192,7 @@ __global__ void k_dyn_step(const float* __restrict__ out, int E, int S, int D, c
 __global__ void __launch_bounds__(1024)
 k_compact_rows(const unsigned char* __restrict__ drop, int S, const float* __restrict__ src, int64_t ld_src, int w,
                float* __restrict__ dst, int64_t ld_dst, int* __restrict__ count_out) {
+    orlk::pdl_enter();
     __shared__ int sums[1024];
     const int per = (S + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = min(S, lo + per);
@@ -218,7 +225,7 @@ int orlk_dyn_input(const float* obs, int64_t ld_obs, const float* act, int64_t l
                    int O, int A, float* X, int64_t ldx, void* stream) {
     ORLK_REQUIRE(S > 0 && O > 0 && A > 0, "sizes");
     const int64_t n = (int64_t)S * (O + A);
-    k_dyn_input<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, ld_obs, act, ld_act, mu, sd, S, O, A, X, ldx);
+    orlk::launch(k_dyn_input, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, obs, ld_obs, act, ld_act, mu, sd, S, O, A, X, ldx);
     return check_launch("k_dyn_input");
 }
 
@@ -226,7 +233,7 @@ int orlk_gather_rows(const float* src, int64_t ld_src, int w, const int64_t* idx
                      float* dst, int64_t ld_dst, int64_t dst_es, void* stream) {
     ORLK_REQUIRE(E > 0 && R > 0 && w > 0, "sizes");
     const int64_t rows = (int64_t)E * R;
-    k_gather_rows<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(src, ld_src, w, idx, idx_ld, r0, E, R, dst, ld_dst,
+    orlk::launch(k_gather_rows, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, src, ld_src, w, idx, idx_ld, r0, E, R, dst, ld_dst,
                                                                              dst_es);
     return check_launch("k_gather_rows");
 }
@@ -235,21 +242,21 @@ int orlk_sumsq_chunks(int64_t n) { return (int)((n + 4095) / 4096); }
 
 int orlk_sumsq(const float* x, int64_t n, float scale, float* partial, void* stream) {
     ORLK_REQUIRE(n > 0, "sizes");
-    k_sumsq<<<orlk_sumsq_chunks(n), 256, 0, (cudaStream_t)stream>>>(x, n, scale, partial);
+    orlk::launch(k_sumsq, orlk_sumsq_chunks(n), 256, 0, (cudaStream_t)stream, x, n, scale, partial);
     return check_launch("k_sumsq");
 }
 
 int orlk_dyn_nll(const float* out, const float* y, int E, int Bn, int D, const float* max_lv, const float* min_lv, float coef,
                  const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss, void* stream) {
     ORLK_REQUIRE(E > 0 && Bn > 0 && D > 0 && D <= 64, "sizes (D <= 64)");
-    k_dyn_nll<<<1, 1024, 0, (cudaStream_t)stream>>>(out, y, E, Bn, D, max_lv, min_lv, coef, decay_partials, n_decay, dout, dmax,
+    orlk::launch(k_dyn_nll, 1, 1024, 0, (cudaStream_t)stream, out, y, E, Bn, D, max_lv, min_lv, coef, decay_partials, n_decay, dout, dmax,
                                                    dmin, out_loss);
     return check_launch("k_dyn_nll");
 }
 
 int orlk_dyn_val_mse(const float* out, const float* y, int E, int Bn, int D, float* mse, void* stream) {
     ORLK_REQUIRE(E > 0 && Bn > 0 && D > 0, "sizes");
-    k_dyn_val_mse<<<E, 256, 0, (cudaStream_t)stream>>>(out, y, Bn, D, mse);
+    orlk::launch(k_dyn_val_mse, E, 256, 0, (cudaStream_t)stream, out, y, Bn, D, mse);
     return check_launch("k_dyn_val_mse");
 }
 
@@ -261,7 +268,7 @@ int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, co
     ORLK_REQUIRE(term_kind >= 0 && term_kind <= 3, "termination kind");
     ORLK_REQUIRE(noise != nullptr || noise32 != nullptr, "noise");
     ORLK_REQUIRE(midx != nullptr || (pick_u != nullptr && elites != nullptr && n_elites > 0), "elite selection");
-    k_dyn_step<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(out, E, S, D, max_lv, min_lv, obs, ld_obs, noise, midx, noise32,
+    orlk::launch(k_dyn_step, (S + 127) / 128, 128, 0, (cudaStream_t)stream, out, E, S, D, max_lv, min_lv, obs, ld_obs, noise, midx, noise32,
                                                                  pick_u, elites, n_elites, term_kind, penalty_coef, next_obs, reward,
                                                                  raw_reward, penalty, terminal);
     return check_launch("k_dyn_step");
@@ -270,7 +277,7 @@ int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, co
 int orlk_compact_rows(const unsigned char* drop, int S, const float* src, int64_t ld_src, int w, float* dst, int64_t ld_dst,
                       int* count_out, void* stream) {
     ORLK_REQUIRE(S > 0 && w > 0, "sizes");
-    k_compact_rows<<<1, 1024, 0, (cudaStream_t)stream>>>(drop, S, src, ld_src, w, dst, ld_dst, count_out);
+    orlk::launch(k_compact_rows, 1, 1024, 0, (cudaStream_t)stream, drop, S, src, ld_src, w, dst, ld_dst, count_out);
     return check_launch("k_compact_rows");
 }
 

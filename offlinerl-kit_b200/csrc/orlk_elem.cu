@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 k_skinny_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw,
              int64_t w_sk, int64_t w_gs, const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy,
              int64_t y_gs, int M, int K, int NS, int vec) {
+    orlk::pdl_enter();
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -62,6 +63,7 @@ __global__ void k_skinny_dgrad(const float* __restrict__ dY, int64_t ldy, int64_
                                int64_t ldw, int64_t w_gs, const float* __restrict__ mask, int64_t ldm, int64_t m_gs,
                                float* __restrict__ dX, int64_t ldx, int64_t x_gs, float* __restrict__ dXT, int64_t ldxt,
                                int64_t xt_gs, int M, int K, int NS) {
+    orlk::pdl_enter();
     __shared__ float tile[32][33];
     __shared__ float dys[32][MAX_NS];
     const int g = blockIdx.z;
@@ -105,6 +107,7 @@ __global__ void k_skinny_dgrad(const float* __restrict__ dY, int64_t ldy, int64_
 
 // ------------------------------------------------------------------------------------------ row assembly
 __global__ void k_concat_rows(const OrlkConcatSeg* __restrict__ segs, int n_segs, int total_rows) {
+    orlk::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= total_rows) return;
@@ -135,6 +138,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 __global__ void k_philox_fill(float* __restrict__ out, int64_t n_normal, int64_t n_uniform, float lo, float hi,
                               uint64_t seed, const unsigned long long* __restrict__ counter, const int* __restrict__ enable) {
+    orlk::pdl_enter();
     if (enable != nullptr && *enable == 0) return;
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call = 4 outputs
     const int64_t n = n_normal + n_uniform;
@@ -167,6 +171,7 @@ __global__ void k_tanh_gauss_sample(const float* __restrict__ head, int64_t ld_h
                                     const float* __restrict__ eps, int M, int A, float* __restrict__ act, int64_t ld_act,
                                     float* __restrict__ logp, const float* __restrict__ obs, int64_t ld_obs, int obs_dim,
                                     float* __restrict__ xout, int64_t ld_x) {
+    orlk::pdl_enter();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     const float* h = head + (int64_t)(head_row_off + m / rep) * ld_head;
@@ -193,6 +198,7 @@ __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head
                                  const float* __restrict__ act, int64_t ld_act, const float* __restrict__ dA, int n_da,
                                  int64_t da_gs, int64_t ld_da, const float* __restrict__ glp, int M, int A,
                                  float* __restrict__ dhead, int64_t ld_dhead) {
+    orlk::pdl_enter();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     const float* h = head + (int64_t)m * ld_head;
@@ -236,6 +242,7 @@ __global__ void k_sac_actor_loss(const float* __restrict__ q, int64_t q_es, int 
                                  float* __restrict__ scalars, int auto_alpha, int clamp01, float target_entropy,
                                  const OrlkAdamGroup* __restrict__ groups, int alpha_group, float* __restrict__ alpha_mv,
                                  float* __restrict__ dq, int64_t dq_es, float* __restrict__ glp, float* __restrict__ out) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const float alpha = scalars[ORLK_SC_ALPHA];
     const float invB = 1.f / (float)B;
@@ -287,6 +294,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
                   float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
                   const OrlkAdamGroup* __restrict__ groups, int cql_alpha_group, float* __restrict__ cql_alpha_mv,
                   float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     __shared__ float sh_scale;
     const float alpha = scalars[ORLK_SC_ALPHA];
@@ -375,6 +383,7 @@ constexpr int ADAM_BLOCK_ELEMS = 256;
 
 __global__ void __launch_bounds__(256)
 k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamGroup* __restrict__ groups) {
+    orlk::pdl_enter();
     __shared__ OrlkAdamDesc sd;
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
@@ -426,6 +435,7 @@ k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamG
 }
 
 __global__ void k_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* counter) {
+    orlk::pdl_enter();
     const int g = threadIdx.x;
     if (g < 32 && (mask >> g) & 1u) groups[g].step += 1;
     if (g == 0 && counter != nullptr) *counter += 1ull;
@@ -445,10 +455,10 @@ int orlk_skinny_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, i
     const int vec = (w_sk == 1) && (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && (x_gs % 4 == 0) && (w_gs % 4 == 0) &&
                     aligned16(X) && aligned16(W);
     cudaStream_t s = (cudaStream_t)stream;
-    if (NS == 1) k_skinny_fwd<1><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else if (NS <= 4) k_skinny_fwd<4><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else if (NS <= 8) k_skinny_fwd<8><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
-    else k_skinny_fwd<16><<<grid, wpb * 32, 0, s>>>(X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    if (NS == 1) orlk::launch(k_skinny_fwd<1>, grid, wpb * 32, 0, s, X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 4) orlk::launch(k_skinny_fwd<4>, grid, wpb * 32, 0, s, X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else if (NS <= 8) orlk::launch(k_skinny_fwd<8>, grid, wpb * 32, 0, s, X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
+    else orlk::launch(k_skinny_fwd<16>, grid, wpb * 32, 0, s, X, ldx, x_gs, W, ldw, w_sk, w_gs, b, b_gs, Y, ldy, y_gs, M, K, NS, vec);
     return check_launch("k_skinny_fwd");
 }
 
@@ -461,7 +471,7 @@ int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W
     const int strips = (M + 31) / 32;
     const int kblocks = strips * G >= 592 ? 1 : (K + 31) / 32;
     dim3 grid(kblocks, strips, G);
-    k_skinny_dgrad<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs,
+    orlk::launch(k_skinny_dgrad, grid, dim3(32, 8), 0, (cudaStream_t)stream, dY, ldy, y_gs, W, ldw, w_gs, mask, ldm, m_gs, dX, ldx, x_gs,
                                                                 dXT, ldxt, xt_gs, M, K, NS);
     return check_launch("k_skinny_dgrad");
 }
@@ -469,7 +479,7 @@ int orlk_skinny_dgrad(const float* dY, int64_t ldy, int64_t y_gs, const float* W
 int orlk_concat_rows(const OrlkConcatSeg* segs_dev, int n_segs, int total_rows, void* stream) {
     ORLK_REQUIRE(segs_dev != nullptr && n_segs > 0 && total_rows > 0, "segments");
     const int wpb = 8;
-    k_concat_rows<<<(total_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(segs_dev, n_segs, total_rows);
+    orlk::launch(k_concat_rows, (total_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream, segs_dev, n_segs, total_rows);
     return check_launch("k_concat_rows");
 }
 
@@ -478,7 +488,7 @@ int orlk_philox_fill(float* out, int64_t n_normal, int64_t n_uniform, float lo, 
     const int64_t n = n_normal + n_uniform;
     ORLK_REQUIRE(out != nullptr && n > 0, "sizes");
     const int64_t calls = (n + 3) / 4;
-    k_philox_fill<<<(unsigned)((calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_normal, n_uniform, lo, hi, seed,
+    orlk::launch(k_philox_fill, (unsigned)((calls + 255) / 256), 256, 0, (cudaStream_t)stream, out, n_normal, n_uniform, lo, hi, seed,
                                                                                     counter, enable);
     return check_launch("k_philox_fill");
 }
@@ -488,7 +498,7 @@ int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off,
                            float* xout, int64_t ld_x, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && rep >= 1, "sizes");
     ORLK_REQUIRE(xout == nullptr || obs != nullptr, "xout needs obs");
-    k_tanh_gauss_sample<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, head_row_off, rep, eps, M, A, act,
+    orlk::launch(k_tanh_gauss_sample, (M + 127) / 128, 128, 0, (cudaStream_t)stream, head, ld_head, head_row_off, rep, eps, M, A, act,
                                                                           ld_act, logp, obs, ld_obs, obs_dim, xout, ld_x);
     return check_launch("k_tanh_gauss_sample");
 }
@@ -498,7 +508,7 @@ int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, co
                         int64_t ld_dhead, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && eps != nullptr, "sizes");
     ORLK_REQUIRE(n_da == 0 || dA != nullptr, "dA");
-    k_tanh_gauss_bwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(head, ld_head, eps, act, ld_act, dA, n_da, da_gs, ld_da,
+    orlk::launch(k_tanh_gauss_bwd, (M + 127) / 128, 128, 0, (cudaStream_t)stream, head, ld_head, eps, act, ld_act, dA, n_da, da_gs, ld_da,
                                                                        glp, M, A, dhead, ld_dhead);
     return check_launch("k_tanh_gauss_bwd");
 }
@@ -508,7 +518,7 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
                         float* dq, int64_t dq_es, float* glp, float* out_losses, void* stream) {
     ORLK_REQUIRE(E >= 1 && B > 0, "sizes");
     ORLK_REQUIRE(!auto_alpha || (groups != nullptr && alpha_mv != nullptr), "auto alpha needs its Adam state");
-    k_sac_actor_loss<<<1, 256, 0, (cudaStream_t)stream>>>(q, q_es, E, logp, B, scalars, auto_alpha, clamp01, target_entropy,
+    orlk::launch(k_sac_actor_loss, 1, 256, 0, (cudaStream_t)stream, q, q_es, E, logp, B, scalars, auto_alpha, clamp01, target_entropy,
                                                          groups, alpha_group, alpha_mv, dq, dq_es, glp, out_losses);
     return check_launch("k_sac_actor_loss");
 }
@@ -521,7 +531,7 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
     ORLK_REQUIRE(B > 0 && R > 0 && A > 0, "sizes");
     ORLK_REQUIRE(!with_lagrange || (groups != nullptr && cql_alpha_mv != nullptr), "lagrange needs its Adam state");
     const float log_u = (float)log(pow(0.5, (double)A));   // cql.py:82: np.log(0.5 ** act_dim)
-    k_cql_critic_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, R, log_u,
+    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, R, log_u,
                                                            gamma, cql_weight, temperature, deterministic_backup,
                                                            with_lagrange, lagrange_threshold, scalars, groups,
                                                            cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses);
@@ -530,13 +540,13 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
 
 int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream) {
     ORLK_REQUIRE(descs_dev != nullptr && n_descs > 0 && total_blocks > 0 && groups != nullptr, "descs");
-    k_adam_step<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, n_descs, groups);
+    orlk::launch(k_adam_step, total_blocks, 256, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
     return check_launch("k_adam_step");
 }
 
 int orlk_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* philox_counter, void* stream) {
     ORLK_REQUIRE(groups != nullptr, "groups");
-    k_step_end<<<1, 32, 0, (cudaStream_t)stream>>>(groups, mask, philox_counter);
+    orlk::launch(k_step_end, 1, 32, 0, (cudaStream_t)stream, groups, mask, philox_counter);
     return check_launch("k_step_end");
 }
 

@@ -112,6 +112,7 @@ __device__ __forceinline__ float epilogue(float v, int epi, float aux) {
 template <int BM, int BN, int BK, int TM, int TN, int KG, int NBUF, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(KG * (BM / TM) * (BN / TN), (KG > 1 ? 1 : (BM >= 128 ? 2 : 3)))
 k_gemm_grouped(const OrlkGemmDesc* __restrict__ descs, int n_descs) {
+    orlk::pdl_enter();
     constexpr int NTG = (BM / TM) * (BN / TN);      // threads per k-group
     constexpr int NT = KG * NTG;
     constexpr int TX = BN / TN;
@@ -288,10 +289,10 @@ int launch_cfg(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int 
     constexpr int NT = KG * (BM / TM) * (BN / TN);
     constexpr size_t smem = gemm_smem_bytes<BM, BN, BK, NBUF>();
     const bool a_kc = a_layout == 0, b_kc = b_layout == 1;
-    if (a_kc && b_kc) k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, true, true><<<total_tiles, NT, smem, s>>>(descs_dev, n_descs);
-    else if (a_kc) k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, true, false><<<total_tiles, NT, smem, s>>>(descs_dev, n_descs);
-    else if (b_kc) k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, false, true><<<total_tiles, NT, smem, s>>>(descs_dev, n_descs);
-    else k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, false, false><<<total_tiles, NT, smem, s>>>(descs_dev, n_descs);
+    if (a_kc && b_kc) orlk::launch(k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, true, true>, total_tiles, NT, smem, s, descs_dev, n_descs);
+    else if (a_kc) orlk::launch(k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, true, false>, total_tiles, NT, smem, s, descs_dev, n_descs);
+    else if (b_kc) orlk::launch(k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, false, true>, total_tiles, NT, smem, s, descs_dev, n_descs);
+    else orlk::launch(k_gemm_grouped<BM, BN, BK, TM, TN, KG, NBUF, false, false>, total_tiles, NT, smem, s, descs_dev, n_descs);
     return check_launch("k_gemm_grouped");
 }
 

@@ -16,6 +16,7 @@ k_td_loss(const float* __restrict__ q, int64_t q_es, int E, const float* __restr
           const float* __restrict__ lp_next, const float* __restrict__ scalars, int use_alpha, const float* __restrict__ rew,
           const float* __restrict__ term, int B, float gamma, float* __restrict__ dq, int64_t dq_es, float* __restrict__ y_out,
           float* __restrict__ out_losses, float* __restrict__ out_sum) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const float alpha = use_alpha ? scalars[ORLK_SC_ALPHA] : 0.f;
     const float invB = 1.f / (float)B;
@@ -46,6 +47,7 @@ k_td_loss(const float* __restrict__ q, int64_t q_es, int E, const float* __restr
 __global__ void __launch_bounds__(1024)
 k_iql_v_loss(const float* __restrict__ tq, int64_t tq_es, const float* __restrict__ v, int B, float expectile,
              float* __restrict__ dv, float* __restrict__ qmin, float* __restrict__ out_loss) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const float invB = 1.f / (float)B;
     float s = 0.f;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(1024)
 k_iql_actor_loss(const float* __restrict__ z, int64_t ldz, const float* __restrict__ sigma_param, const float* __restrict__ act,
                  int64_t lda, const float* __restrict__ qmin, const float* __restrict__ v, int B, int A, float temp,
                  float max_mu, float* __restrict__ dz, int64_t lddz, float* __restrict__ dsigma, float* __restrict__ out_loss) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const float invB = 1.f / (float)B;
     float loss = 0.f;
@@ -112,6 +115,7 @@ __global__ void k_det_actor_fwd(const float* __restrict__ z, int64_t ldz, const 
                                 float max_action, float policy_noise, float noise_clip, float* __restrict__ act, int64_t ld_act,
                                 const float* __restrict__ obs, int64_t ld_obs, int obs_dim, float* __restrict__ xout,
                                 int64_t ld_x) {
+    orlk::pdl_enter();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     for (int i = 0; i < A; ++i) {
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(1024)
 k_td3bc_actor_loss(const float* __restrict__ q, const float* __restrict__ a, int64_t lda, const float* __restrict__ a_data,
                    int64_t ldd, int B, int A, float bc_alpha, float* __restrict__ dq, float* __restrict__ dabc, int64_t ldg,
                    float* __restrict__ out_loss) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     float sabs = 0.f, sq = 0.f, sbc = 0.f;
     const float invB = 1.f / (float)B, invBA = 1.f / ((float)B * (float)A);
@@ -157,6 +162,7 @@ k_td3bc_actor_loss(const float* __restrict__ q, const float* __restrict__ a, int
 __global__ void k_det_actor_bwd(const float* __restrict__ a, int64_t lda, const float* __restrict__ dA0, int64_t ld0,
                                 const float* __restrict__ dA1, int64_t ld1, int M, int A, float max_action,
                                 float* __restrict__ dz, int64_t lddz) {
+    orlk::pdl_enter();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     for (int i = 0; i < A; ++i) {
@@ -170,6 +176,7 @@ __global__ void k_det_actor_bwd(const float* __restrict__ a, int64_t lda, const 
 // EDAC diversity loss and its gradient w.r.t. the input gradients g.  One thread per sample.
 __global__ void __launch_bounds__(256)
 k_edac_div(const float* __restrict__ g, int E, int B, int A, float eta, float* __restrict__ gbar, float* __restrict__ partial) {
+    orlk::pdl_enter();
     __shared__ float red[32];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     float Gb = 0.f;
@@ -211,6 +218,7 @@ k_edac_div(const float* __restrict__ g, int E, int B, int A, float eta, float* _
 }
 
 __global__ void k_edac_div_final(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+    orlk::pdl_enter();
     float s = 0.f;
     for (int i = 0; i < n; ++i) s += partial[i];
     out[0] = s * scale;
@@ -225,7 +233,7 @@ int orlk_td_loss(const float* q, int64_t q_es, int E, const float* tq, int64_t t
                  int64_t dq_es, float* y_out, float* out_losses, float* out_sum, void* stream) {
     ORLK_REQUIRE(E >= 1 && E2 >= 1 && B > 0, "sizes");
     ORLK_REQUIRE(!use_alpha || (lp_next != nullptr && scalars != nullptr), "alpha term needs lp_next and scalars");
-    k_td_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(q, q_es, E, tq, tq_es, E2, lp_next, scalars, use_alpha, rew, term, B, gamma,
+    orlk::launch(k_td_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_es, E, tq, tq_es, E2, lp_next, scalars, use_alpha, rew, term, B, gamma,
                                                    dq, dq_es, y_out, out_losses, out_sum);
     return check_launch("k_td_loss");
 }
@@ -233,7 +241,7 @@ int orlk_td_loss(const float* q, int64_t q_es, int E, const float* tq, int64_t t
 int orlk_iql_v_loss(const float* tq, int64_t tq_es, const float* v, int B, float expectile, float* dv, float* qmin,
                     float* out_loss, void* stream) {
     ORLK_REQUIRE(B > 0, "sizes");
-    k_iql_v_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(tq, tq_es, v, B, expectile, dv, qmin, out_loss);
+    orlk::launch(k_iql_v_loss, 1, 1024, 0, (cudaStream_t)stream, tq, tq_es, v, B, expectile, dv, qmin, out_loss);
     return check_launch("k_iql_v_loss");
 }
 
@@ -241,7 +249,7 @@ int orlk_iql_actor_loss(const float* z, int64_t ldz, const float* sigma_param, c
                         const float* v, int B, int A, float temperature, float max_mu, float* dz, int64_t lddz, float* dsigma,
                         float* out_loss, void* stream) {
     ORLK_REQUIRE(B > 0 && A > 0 && A <= 32, "sizes");
-    k_iql_actor_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(z, ldz, sigma_param, act, lda, qmin, v, B, A, temperature, max_mu, dz,
+    orlk::launch(k_iql_actor_loss, 1, 1024, 0, (cudaStream_t)stream, z, ldz, sigma_param, act, lda, qmin, v, B, A, temperature, max_mu, dz,
                                                           lddz, dsigma, out_loss);
     return check_launch("k_iql_actor_loss");
 }
@@ -251,7 +259,7 @@ int orlk_det_actor_fwd(const float* z, int64_t ldz, const float* eps, int M, int
                        int64_t ld_x, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0, "sizes");
     ORLK_REQUIRE(xout == nullptr || obs != nullptr, "xout needs obs");
-    k_det_actor_fwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, ldz, eps, M, A, max_action, policy_noise, noise_clip, act,
+    orlk::launch(k_det_actor_fwd, (M + 127) / 128, 128, 0, (cudaStream_t)stream, z, ldz, eps, M, A, max_action, policy_noise, noise_clip, act,
                                                                       ld_act, obs, ld_obs, obs_dim, xout, ld_x);
     return check_launch("k_det_actor_fwd");
 }
@@ -259,7 +267,7 @@ int orlk_det_actor_fwd(const float* z, int64_t ldz, const float* eps, int M, int
 int orlk_td3bc_actor_loss(const float* q, const float* a, int64_t lda, const float* a_data, int64_t ldd, int B, int A,
                           float bc_alpha, float* dq, float* dabc, int64_t ldg, float* out_loss, void* stream) {
     ORLK_REQUIRE(B > 0 && A > 0, "sizes");
-    k_td3bc_actor_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(q, a, lda, a_data, ldd, B, A, bc_alpha, dq, dabc, ldg, out_loss);
+    orlk::launch(k_td3bc_actor_loss, 1, 1024, 0, (cudaStream_t)stream, q, a, lda, a_data, ldd, B, A, bc_alpha, dq, dabc, ldg, out_loss);
     return check_launch("k_td3bc_actor_loss");
 }
 
@@ -267,15 +275,15 @@ int orlk_edac_div(const float* g, int E, int B, int A, float eta, float* gbar, f
     ORLK_REQUIRE(E >= 2 && B > 0 && A > 0 && A <= 32, "sizes");
     ORLK_REQUIRE(scratch != nullptr, "scratch (ceil(B/256) floats)");
     const int blocks = (B + 255) / 256;
-    k_edac_div<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, E, B, A, eta, gbar, scratch);
-    k_edac_div_final<<<1, 1, 0, (cudaStream_t)stream>>>(scratch, blocks, eta / (float)B, out_loss);
+    orlk::launch(k_edac_div, blocks, 256, 0, (cudaStream_t)stream, g, E, B, A, eta, gbar, scratch);
+    orlk::launch(k_edac_div_final, 1, 1, 0, (cudaStream_t)stream, scratch, blocks, eta / (float)B, out_loss);
     return check_launch("k_edac_div");
 }
 
 int orlk_det_actor_bwd(const float* a, int64_t lda, const float* dA0, int64_t ld0, const float* dA1, int64_t ld1, int M, int A,
                        float max_action, float* dz, int64_t lddz, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0 && dA0 != nullptr, "sizes");
-    k_det_actor_bwd<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, lda, dA0, ld0, dA1, ld1, M, A, max_action, dz, lddz);
+    orlk::launch(k_det_actor_bwd, (M + 127) / 128, 128, 0, (cudaStream_t)stream, a, lda, dA0, ld0, dA1, ld1, M, A, max_action, dz, lddz);
     return check_launch("k_det_actor_bwd");
 }
 

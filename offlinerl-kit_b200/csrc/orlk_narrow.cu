@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256, 2)
 k_narrow_fwd(const float* __restrict__ X, int64_t ldx, int64_t x_gs, const float* __restrict__ W, int64_t ldw, int64_t w_gs,
              const float* __restrict__ b, int64_t b_gs, float* __restrict__ Y, int64_t ldy, int64_t y_gs,
              float* __restrict__ YT, int64_t ldyt, int64_t yt_gs, int M, int N, int K, int relu) {
+    orlk::pdl_enter();
     __shared__ __align__(16) float xs[ROWS_FWD * SUB_FWD][XLD];
     const int g = blockIdx.z;
     const int mb = blockIdx.x * ROWS_FWD * SUB_FWD;
@@ -80,6 +81,7 @@ k_narrow_wgrad(const float* __restrict__ Wide, int64_t ldw, int64_t w_gs, const 
                int64_t n_gs, float* __restrict__ out, int64_t s_ns, int64_t s_kw, int64_t o_gs, int64_t o_cs,
                float* __restrict__ wide_sum, int64_t ws_gs, int64_t ws_cs, float* __restrict__ nar_sum, int64_t ns_gs,
                int64_t ns_cs, int M, int KW, int NS) {
+    orlk::pdl_enter();
     // block = (256 wide columns) x (4 row quarters); the quarters are combined through shared memory in one shot
     extern __shared__ float dsm[];
     float (*ns_s)[XLD] = reinterpret_cast<float (*)[XLD]>(dsm);                             // [ROWS_WG][36], zero padded
@@ -160,7 +162,7 @@ int orlk_narrow_fwd(const float* X, int64_t ldx, int64_t x_gs, const float* W, i
     ORLK_REQUIRE(K >= 1 && K <= NK_MAX, "K must be in [1,32]");
     ORLK_REQUIRE(M > 0 && N > 0 && G > 0, "sizes");
     dim3 grid((M + ROWS_FWD * SUB_FWD - 1) / (ROWS_FWD * SUB_FWD), (N + 255) / 256, G);
-    k_narrow_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, YT, ldyt, yt_gs, M, N,
+    orlk::launch(k_narrow_fwd, grid, 256, 0, (cudaStream_t)stream, X, ldx, x_gs, W, ldw, w_gs, b, b_gs, Y, ldy, y_gs, YT, ldyt, yt_gs, M, N,
                                                         K, relu);
     return check_launch("k_narrow_fwd");
 }
@@ -180,7 +182,7 @@ int orlk_narrow_wgrad(const float* Wide, int64_t ldw, int64_t w_gs, const float*
     ORLK_REQUIRE(M > 0 && KW > 0 && G > 0, "sizes");
     dim3 grid((M + ROWS_WG - 1) / ROWS_WG, (KW + 255) / 256, G);
     const size_t smem = sizeof(float) * (ROWS_WG * XLD + 3 * (NS + 1) * 256);
-    k_narrow_wgrad<<<grid, dim3(256, 4), smem, (cudaStream_t)stream>>>(Wide, ldw, w_gs, Nar, ldn, n_gs, out, s_ns, s_kw, o_gs, o_cs, wide_sum,
+    orlk::launch(k_narrow_wgrad, grid, dim3(256, 4), smem, (cudaStream_t)stream, Wide, ldw, w_gs, Nar, ldn, n_gs, out, s_ns, s_kw, o_gs, o_cs, wide_sum,
                                                           ws_gs, ws_cs, nar_sum, ns_gs, ns_cs, M, KW, NS);
     return check_launch("k_narrow_wgrad");
 }

@@ -7,6 +7,7 @@ using namespace orlk;
 __global__ void k_replay_pack(const float* __restrict__ obs, const float* __restrict__ nobs, const float* __restrict__ act,
                               const float* __restrict__ rew, const float* __restrict__ term, int64_t n, int O, int A,
                               float* __restrict__ table, int row_w, int64_t row_offset) {
+    orlk::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -28,6 +29,7 @@ __global__ void k_replay_pack(const float* __restrict__ obs, const float* __rest
 __global__ void k_replay_gather(const float* __restrict__ table, int64_t n_rows, int row_w, int O, int A,
                                 const int64_t* __restrict__ idx, int n, float* __restrict__ obs2, float* __restrict__ act,
                                 float* __restrict__ rew, float* __restrict__ term) {
+    orlk::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (warp >= n) return;
@@ -55,7 +57,7 @@ int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, 
     if (n == 0) return 0;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k_replay_pack<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, next_obs, act, rew, term, n, obs_dim, act_dim,
+    orlk::launch(k_replay_pack, (unsigned)blocks, 256, 0, (cudaStream_t)stream, obs, next_obs, act, rew, term, n, obs_dim, act_dim,
                                                                       table, row_w, row_offset);
     return check_launch("k_replay_pack");
 }
@@ -66,7 +68,7 @@ int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_di
     ORLK_REQUIRE(row_w >= 2 * obs_dim + act_dim + 2, "row_w too small");
     if (n == 0) return 0;
     const int wpb = 4;  // warps per block: 64 blocks for a 256 batch, spread over SMs
-    k_replay_gather<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(table, n_rows, row_w, obs_dim, act_dim,
+    orlk::launch(k_replay_gather, (n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream, table, n_rows, row_w, obs_dim, act_dim,
                                                                                 idx, n, obs2, act, rew, term);
     return check_launch("k_replay_gather");
 }

@@ -1,5 +1,6 @@
 // Runtime plumbing of the C ABI: error text, CUDA-graph capture/replay, copies, events.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "orlk_common.cuh"
 
@@ -10,6 +11,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("ORLK_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
 }
 }  // namespace orlk
 using namespace orlk;
@@ -44,6 +53,19 @@ int orlk_graph_end(void* stream, void** graph_exec_out) {
     cudaGraph_t g = nullptr;
     int rc = check(cudaStreamEndCapture((cudaStream_t)stream, &g), "cudaStreamEndCapture");
     if (rc) return rc;
+    if (getenv("ORLK_GRAPH_DEBUG")) {
+        size_t n_nodes = 0, n_edges = 0;
+        cudaGraphGetNodes(g, nullptr, &n_nodes);
+        cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &n_edges);
+        cudaGraphNode_t* from = (cudaGraphNode_t*)malloc(sizeof(cudaGraphNode_t) * (n_edges + 1));
+        cudaGraphNode_t* to = (cudaGraphNode_t*)malloc(sizeof(cudaGraphNode_t) * (n_edges + 1));
+        cudaGraphEdgeData* ed = (cudaGraphEdgeData*)malloc(sizeof(cudaGraphEdgeData) * (n_edges + 1));
+        size_t prog = 0;
+        if (cudaGraphGetEdges_v2(g, from, to, ed, &n_edges) == cudaSuccess)
+            for (size_t i = 0; i < n_edges; ++i) prog += ed[i].type == cudaGraphDependencyTypeProgrammatic;
+        fprintf(stderr, "[orlk] graph: %zu nodes, %zu edges, %zu programmatic\n", n_nodes, n_edges, prog);
+        free(from); free(to); free(ed);
+    }
     cudaGraphExec_t ex = nullptr;
     rc = check(cudaGraphInstantiate(&ex, g, 0), "cudaGraphInstantiate");
     cudaGraphDestroy(g);

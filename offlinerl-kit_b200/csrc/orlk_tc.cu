@@ -16,6 +16,7 @@
 // (reference: nets/mlp.py:22 forward; autograd backward of the same layers; cql.py:133-190).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "orlk_common.cuh"
 using namespace orlk;
 
@@ -39,7 +40,20 @@ struct TcParams {
     float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
     int M, N, K, G, epi, k_splits, slabs_per_split, tiles_m, tiles_n, NT;   // NT = output columns per CTA (n-tile)
     int stages, stage_bytes;   // depth of the TMA ring and bytes per stage (depend on NT and the precision mode)
+    int c_tma;                 // C leaves through TMA stores (tmC valid)
+    int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
+    unsigned long long* trace; // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_STAMP(slot)                                                       \
+    do {                                                                     \
+        if (p.trace != nullptr) p.trace[(int64_t)blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+    } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,6 +81,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// One lane of a converged warp.  Issuing TMA / tcgen05 instructions under elect.sync inside a warp-uniform branch lets
+// the compiler keep descriptors and addresses in uniform registers; under a plain `lane == 0` test it wraps every
+// UTCHMMA in an R2UR "waterfall" loop (~70 ns per instruction, measured).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -123,7 +154,8 @@ __device__ __forceinline__ float4 lo_tf32(const float4& v) {
 
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmC, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment
     // (offset arithmetic on the __shared__ array keeps the address space known to the compiler: LDS/STS, not generic)
@@ -141,7 +173,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint8_t* smem = fixed + FIXED_SMEM;                                  // the operand ring
     const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);    // provably warp-uniform
+    const int lane = threadIdx.x & 31;
     int idx = blockIdx.x;
     const int split = idx % p.k_splits;
     idx /= p.k_splits;
@@ -162,6 +195,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES + b_bytes; };
     auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + b_bytes; };
 
+    // Prologue that touches no global data: runs while the previous kernel of the stream is still finishing.
+    orlk::pdl_trigger();
+    if (threadIdx.x == 0) TC_STAMP(0);
+    if (threadIdx.x == 32) {                   // descriptor fetch off the critical path (~0.3 us on first use)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
@@ -177,21 +218,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                      "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp >= 2 && warp < 6 && want_rowsum) {
+        float* o = reinterpret_cast<float*>(ones);
+        for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
+        fence_proxy_async();
+    }
+    orlk::pdl_wait();                          // operands, bias and aux come from earlier kernels
+    if (threadIdx.x == 0) TC_STAMP(1);
     if (warp >= 2 && warp < 6) {
-        if (want_rowsum) {
-            float* o = reinterpret_cast<float*>(ones);
-            for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) o[i] = 1.0f;
-            fence_proxy_async();
-        }
         const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs + n0 : nullptr;
         for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < NT) ? __ldg(bg + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    if (threadIdx.x == 0) TC_STAMP(2);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      if (elect_one()) {
         // ------------------------------------------------------------------ TMA producer
         const uint32_t tx_bytes = A_BYTES + (uint32_t)NT * BK * 4;
         for (int it = 0; it < nslabs; ++it) {
@@ -202,17 +247,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int k0 = (slab0 + it) * BK;
             tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, g);
             tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
+            if (p.trace_mode == 1 && it < 8) TC_STAMP(8 + it);
         }
-    } else if (warp == 1 && lane == 0) {
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         const uint32_t idesc = instr_desc_tf32(BM, NT);
         const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
         const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
+        if (p.trace != nullptr && p.trace_mode == 2 && nslabs <= STAGES) {   // experiment: issue only once all slabs landed
+            for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32(PASSES == 3 ? &splitb[it] : &full[it]), 0);
+            TC_STAMP(3);
+        }
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(PASSES == 3 ? &splitb[s] : &full[s]), ph);
             tc_fence_after();
+            if (it == 0) TC_STAMP(4);
+            if (it == nslabs - 1) TC_STAMP(5);
+            if (PASSES == 1 && p.trace_mode == 0 && it < 8) TC_STAMP(8 + it);
+            if (p.trace_mode == 3 && it == 1) TC_STAMP(8);
+            const uint32_t x1 = (p.trace_mode == 3 && NT <= 128) ? NT : 0, x2 = 2 * x1;   // experiment: 3 accumulators
             const uint64_t ad = smem_desc_sw128(smem_u32(a_raw(s))), bd = smem_desc_sw128(smem_u32(b_raw(s)));
             const uint64_t adl = smem_desc_sw128(smem_u32(a_lo(s))), bdl = smem_desc_sw128(smem_u32(b_lo(s)));
 #pragma unroll
@@ -221,21 +278,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint64_t koff = (uint64_t)(k * 2);    // +32 bytes in the 16-byte-unit start-address field
                 umma_tf32(tmem_base, ad + koff, bd + koff, idesc, acc);
                 if (PASSES == 3) {
-                    umma_tf32(tmem_base, adl + koff, bd + koff, idesc, 1u);
-                    umma_tf32(tmem_base, ad + koff, bdl + koff, idesc, 1u);
+                    umma_tf32(tmem_base + x1, adl + koff, bd + koff, idesc, x1 ? acc : 1u);
+                    umma_tf32(tmem_base + x2, ad + koff, bdl + koff, idesc, x1 ? acc : 1u);
                 }
                 if (want_rowsum) {
                     umma_tf32(tmem_base + ROWSUM_COL, ad + koff, ones_desc, idesc_rs, acc);
                     if (PASSES == 3) umma_tf32(tmem_base + ROWSUM_COL, adl + koff, ones_desc, idesc_rs, 1u);
                 }
             }
+            if (p.trace_mode == 3 && it == 1) TC_STAMP(9);
             umma_commit(smem_u32(&empty[s]));               // frees the stage when these MMAs have completed
+            if (p.trace_mode == 3 && it == 1) TC_STAMP(10);
         }
         umma_commit(smem_u32(accum));
+      }
     } else if (warp >= 6) {
         // ------------------------------------------------------------------ ReLU-mask builder (overlaps the mainloop)
         // Each lane loads float4s (512 contiguous bytes per warp instruction, 8 rows in flight); component e of
         // 128-column group q gives one ballot word:  bit j of mask_s[row][4q+e]  <=>  aux[m][128q + 4j + e] > 0.
+        if (p.trace != nullptr && p.trace_mode == 2 && warp == 6 && lane == 0) {     // experiment: landing observer
+            for (int it = 0; it < nslabs && it < 8; ++it) {
+                mbar_wait(smem_u32(&full[it % STAGES]), (it / STAGES) & 1);
+                TC_STAMP(8 + it);
+            }
+        }
         if (p.epi == ORLK_EPI_RELU_MASK) {
             const int w = warp - 6;
             const float* auxg = p.aux + (int64_t)g * p.aux_gs + n0;
@@ -290,6 +356,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(smem_u32(&full[s]), ph);
+                if (t == 0 && it == 0) TC_STAMP(3);
+                if (t == 0 && p.trace_mode == 0 && it < 8) TC_STAMP(8 + it);
+                const bool st4 = (t == 0 && p.trace_mode == 4 && it == 1);
+                if (st4) TC_STAMP(8);
                 float4* __restrict__ ar = reinterpret_cast<float4*>(a_raw(s));
                 float4* __restrict__ al = reinterpret_cast<float4*>(a_lo(s));
                 float4* __restrict__ br = reinterpret_cast<float4*>(b_raw(s));
@@ -302,6 +372,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                     for (int j = 0; j < 8; ++j) al[t + 128 * j] = lo_tf32(v[j]);
                 }
+                if (st4) TC_STAMP(9);
                 for (int i0 = 0; i0 < nB4; i0 += 128 * 8) {
                     float4 v[8];
 #pragma unroll
@@ -315,15 +386,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         if (i < nB4) bl[i] = lo_tf32(v[j]);
                     }
                 }
+                if (st4) TC_STAMP(10);
                 fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
+                if (st4) TC_STAMP(11);
                 mbar_arrive(smem_u32(&splitb[s]));
+                if (st4) TC_STAMP(12);
             }
         }
+    }
+    if (warp >= 2) {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+        // Eight warps: warp w may only touch TMEM lanes 32*(w%4) .. +31, so quadrant q is shared by warps 2+q' and 6+q''
+        // which take alternate 32-column chunks.  A lane owns one accumulator ROW, so:
+        //  * C (row-major) is parked in the now idle operand ring as 32x32 SWIZZLE_128B tiles and leaves through TMA
+        //    stores (direct stores put 32 different lines in every instruction: measured 6 us for a 128x256 tile);
+        //  * CT (transposed) is written directly, a warp instruction covering 32 consecutive floats of one CT row.
+        const int t = threadIdx.x - 64;
         if (p.epi == ORLK_EPI_RELU_MASK) mbar_wait(smem_u32(maskbar), 0);
         mbar_wait(smem_u32(accum), 0);
         tc_fence_after();
-        const int q = warp & 3;                             // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        if (t == 0) TC_STAMP(6);
+        const int q = warp & 3;
+        const int half = warp >= 6 ? 1 : 0;
         const int row = q * 32 + lane;
         const int m = tile_m * BM + row;
         const bool row_ok = m < p.M;
@@ -332,21 +416,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + (int64_t)n0 * p.ldct + m : nullptr;
         const bool vec_ok = (NT % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
                             (p.c_split_stride % 4 == 0);
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+        const bool c_tma = p.c_tma != 0;
+        bool issued = false;
+        for (int c0 = 32 * half; c0 < NT; c0 += 64) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
             tmem_wait_ld();
             float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = c0 + j;
-                x[j] = __uint_as_float(v[j]) + bias_s[n < BN_MAX ? n : 0];
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j4);
+                x[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b4.x;
+                x[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+                x[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z;
+                x[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
             }
             if (p.epi == ORLK_EPI_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
             } else if (p.epi == ORLK_EPI_RELU_MASK) {
-                // columns c0 .. c0+31 live in 128-column group q = c0/128 at lanes 8*((c0/32)%4) .. +7
+                // columns c0 .. c0+31 live in 128-column group c0/128 at bits 8*((c0/32)%4) .. +7
                 const uint4 mb = *reinterpret_cast<const uint4*>(mask_s + row * (BN_MAX / 32) + 4 * (c0 >> 7));
                 const int sh = 8 * ((c0 >> 5) & 3);
                 const uint32_t m0 = mb.x >> sh, m1 = mb.y >> sh, m2 = mb.z >> sh, m3 = mb.w >> sh;
@@ -358,33 +447,47 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     x[4 * jj + 3] = ((m3 >> jj) & 1u) ? x[4 * jj + 3] : 0.f;
                 }
             }
-            if (row_ok) {
-                if (C != nullptr) {
-                    if (vec_ok) {
+            if (c_tma) {
+                // tile (q, c0/32): 32 rows x 128 bytes, 16-byte chunk j of row r at position j ^ (r & 7)
+                uint8_t* tile = smem + (size_t)(q * ((NT + 31) >> 5) + (c0 >> 5)) * 4096;
+                float4* trow = reinterpret_cast<float4*>(tile + lane * 128);
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            if (c0 + 4 * j4 < NT)
-                                *reinterpret_cast<float4*>(C + c0 + 4 * j4) =
-                                    make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < NT) C[c0 + j] = x[j];
-                    }
+                for (int j4 = 0; j4 < 8; ++j4)
+                    trow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_4d(&tmC, smem_u32(tile), n0 + c0, tile_m * BM + q * 32, g, split);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (CT != nullptr) {
+                issued = true;
+            } else if (row_ok && C != nullptr) {
+                if (vec_ok) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (c0 + 4 * j4 < NT)
+                            *reinterpret_cast<float4*>(C + c0 + 4 * j4) =
+                                make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < NT) CT[(int64_t)(c0 + j) * p.ldct] = x[j];    // coalesced across the warp's rows
+                        if (c0 + j < NT) C[c0 + j] = x[j];
                 }
             }
+            if (row_ok && CT != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < NT) CT[(int64_t)(c0 + j) * p.ldct] = x[j];
+            }
         }
-        if (want_rowsum) {
+        if (want_rowsum && half == 0) {
             const uint32_t r = tmem_ld1(taddr + ROWSUM_COL);
             tmem_wait_ld();
             if (row_ok) p.rowsum[(int64_t)g * p.rowsum_gs + (int64_t)split * p.rowsum_split_stride + m] = __uint_as_float(r);
         }
+        if (issued) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tiles must outlive the stores
     }
+    if (threadIdx.x == 64) TC_STAMP(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -432,9 +535,38 @@ int make_map(CUtensorMap* map, const float* base, int64_t ld, int64_t gs, int ro
     return 0;
 }
 
+// 4-D tensor map over the row-major output [splits][G][M][N] (n contiguous), box = 32 (n) x 32 (m), 128-byte swizzle.
+int make_map_c(CUtensorMap* map, float* base, int64_t ldc, int64_t gs, int64_t ss, int M, int N, int G, int S) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ORLK_ERR_UNSUPPORTED;
+    }
+    if (gs <= 0) gs = (int64_t)M * ldc;
+    if (ss <= 0) ss = (int64_t)G * gs;
+    cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)G, (cuuint64_t)S};
+    cuuint64_t strides[3] = {(cuuint64_t)ldc * 4, (cuuint64_t)gs * 4, (cuuint64_t)ss * 4};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (C) failed with CUresult %d (ldc=%lld gs=%lld ss=%lld M=%d N=%d G=%d S=%d)", (int)r,
+                  (long long)ldc, (long long)gs, (long long)ss, M, N, G, S);
+        return ORLK_ERR_BAD_ARG;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int orlk_sizeof_tc_gemm(void) { return (int)sizeof(OrlkTcGemm); }
+
+static unsigned long long* g_tc_trace = nullptr;
+extern "C" int orlk_tc_set_trace(void* dev_buf) {
+    g_tc_trace = (unsigned long long*)dev_buf;
+    return 0;
+}
 
 constexpr int MAX_DYN_SMEM = 227 * 1024;
 
@@ -485,13 +617,24 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
     p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
     p.NT = NT; p.tiles_n = q->N / NT;
+    p.trace = g_tc_trace;
+    { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }
 
     tc_ring(NT, q->passes, &p.stages, &p.stage_bytes);
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    p.c_tma = 0;
+    if (q->C != nullptr && NT % 32 == 0 && q->ldc % 4 == 0 && aligned16(q->C) && q->c_gs % 4 == 0 && q->c_split_stride % 4 == 0 &&
+        (int64_t)NT * 512 <= (int64_t)p.stages * p.stage_bytes) {
+        rc = make_map_c(&tmC, q->C, q->ldc, q->c_gs, q->c_split_stride, q->M, q->N, q->G, splits);
+        if (rc) return rc;
+        p.c_tma = 1;
+    }
     const size_t smem = 1024 + FIXED_SMEM + (size_t)p.stages * p.stage_bytes;
     const int grid = q->G * p.tiles_m * p.tiles_n * splits;
     cudaStream_t s = (cudaStream_t)stream;
-    if (q->passes == 3) k_tc_gemm<3><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
-    else k_tc_gemm<1><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+    if (q->passes == 3) orlk::launch(k_tc_gemm<3>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
+    else orlk::launch(k_tc_gemm<1>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
     return check_launch("k_tc_gemm");
 }
 
