@@ -90,7 +90,7 @@ enum {
     ORLK_EPI_DSWISH = 4     /* C = acc * swish'(aux(m,n))      Swish backward, aux=z  */
 };
 /* tile configurations: 128x128x16, 64x64x16, 32x32x32, and 32x32x256 with 4 k-parallel thread groups (small-M layers) */
-enum { ORLK_CFG_BIG = 0, ORLK_CFG_MID = 1, ORLK_CFG_SMALL = 2, ORLK_CFG_KPAR = 3 };
+enum { ORLK_CFG_BIG = 0, ORLK_CFG_MID = 1, ORLK_CFG_SMALL = 2, ORLK_CFG_KPAR = 3, ORLK_CFG_TINY = 4 /* orlk_gemm_tiny only */ };
 
 typedef struct OrlkGemmDesc {
     const float* A;
@@ -121,6 +121,11 @@ int orlk_gemm_init(void); /* once per process, outside stream capture (shared-me
  * the per-problem fields of the descriptors must agree). */
 int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, int a_layout, int b_layout,
                       void* stream);
+/* Small-row variant (M of a few hundred, latency-bound layers): same descriptor and math, 32 x 16 output tiles
+ * (ORLK_CFG_TINY), the whole k extent of both operand tiles fetched in one cp.async burst, four k-parallel thread
+ * groups.  descs_host is a HOST array of 1..16 problems with k_splits == 1 (it travels in the kernel parameters). */
+int orlk_gemm_tiny_init(void); /* once per process, outside stream capture */
+int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles, int a_layout, int b_layout, void* stream);
 
 /* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
  *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.

@@ -58,8 +58,8 @@ class TcGemm(C.Structure):
 
 
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)
-CFG_BIG, CFG_MID, CFG_SMALL, CFG_KPAR = range(4)
-CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32), CFG_KPAR: (32, 32, 256)}
+CFG_BIG, CFG_MID, CFG_SMALL, CFG_KPAR, CFG_TINY = range(5)
+CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32), CFG_KPAR: (32, 32, 256), CFG_TINY: (32, 16, 256)}
 OPT_ADAM, OPT_POLYAK = 1, 2
 SC_LOG_ALPHA, SC_ALPHA, SC_CQL_LOG_ALPHA, SC_COUNT = 0, 1, 2, 8
 
@@ -81,6 +81,7 @@ _PROTOS = {
     "orlk_replay_pack": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _L, _P],
     "orlk_replay_gather": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
+    "orlk_gemm_tiny": [_P, _I, _I, _I, _I, _P], "orlk_gemm_tiny_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],
     "orlk_sizeof_tc_gemm": [],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],

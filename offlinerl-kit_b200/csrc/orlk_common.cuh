@@ -47,9 +47,12 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 bool pdl_enabled();
+// First launch of each kernel: pin its shared-memory carveout (ORLK_CARVEOUT=percent, default: leave the driver's choice).
+void prepare_kernel(const void* fn);
 
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    prepare_kernel(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;

@@ -20,6 +20,20 @@ bool pdl_enabled() {
     }
     return on == 1;
 }
+void prepare_kernel(const void* fn) {
+    static const void* seen[256];
+    static int n_seen = 0;
+    static int carve = -2;
+    if (carve == -2) {
+        const char* e = getenv("ORLK_CARVEOUT");
+        carve = e ? atoi(e) : -1;
+    }
+    if (carve < 0) return;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == fn) return;
+    if (n_seen < 256) seen[n_seen++] = fn;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+}
 }  // namespace orlk
 using namespace orlk;
 

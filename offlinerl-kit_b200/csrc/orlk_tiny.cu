@@ -1,0 +1,275 @@
+// Latency-oriented fp32 GEMM for the small-row passes (M of a few hundred: actor / target / policy-improvement chains).
+//
+// Those layers are ~17 MFLOP each: what they cost is the dependent chain  launch -> operand fetch -> k loop -> store.
+// So this kernel (a) takes its problem list BY VALUE in the kernel parameters (no descriptor fetch from global memory),
+// (b) cuts the output into 32 x 16 tiles so that a 256 x 256 layer spreads over 128 SMs, (c) fetches the whole k extent
+// of both operand tiles (up to 256 k at a time) with one burst of 16-byte cp.async copies in the operands' OWN layout -
+// no register staging, no transposition, (d) splits k over four thread groups that are summed through shared memory,
+// and (e) applies the epilogue with all 256 threads on the reduced tile so C and CT both leave in coalesced rows.
+// Same math and the same descriptor as orlk_gemm_grouped (ascending-k FFMA inside each k group, fixed-order group sum).
+// Replaces nn.Linear forward / autograd dgrad / wgrad for small batches (nets/mlp.py:22,28).
+#include "orlk_common.cuh"
+using namespace orlk;
+
+namespace {
+
+constexpr int TM = 32;            // tile rows
+constexpr int TN = 16;            // tile columns
+constexpr int KC = 256;           // k extent staged per pass
+constexpr int KP = KC + 4;        // row pitch (floats) of a k-contiguous operand tile: 260 % 32 == 4 -> rows sit 16 bytes apart in the banks
+constexpr int NTHR = 256;
+constexpr int KG = 4;             // k groups
+constexpr int MAXP = 16;          // problems per launch (kernel-parameter space: 16 x 176 bytes)
+
+struct TinyArgs {
+    OrlkGemmDesc d[MAXP];
+    int n;
+};
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// Stage rows [t0, t0+BT) x k [k0, k0+kc) of an operand.  KCONT: operand(t,k) = base[t*ld + k] -> S[t][KP];
+// otherwise operand(t,k) = base[k*ld + t] -> S[k][BT].  Everything outside the matrix is zero-filled.
+template <int BT, bool KCONT>
+__device__ __forceinline__ void stage(float* S, const float* __restrict__ base, int64_t ld, int t0, int T, int k0, int kc,
+                                      int kend, int tid) {
+    const bool vec = aligned16(base) && (ld % 4) == 0;
+    const int kc4 = (kc + 3) >> 2;                      // 4-k blocks in this pass (a ragged last block is zero-padded)
+    if (KCONT) {
+        if (vec) {
+            for (int q = tid; q < BT * kc4; q += NTHR) {
+                const int r = q / kc4, c = q - r * kc4;
+                const int t = t0 + r, k = k0 + 4 * c;
+                int bytes = (t < T) ? 4 * min(4, kend - k) : 0;
+                const float* src = base + (int64_t)min(t, T - 1) * ld + (bytes > 0 ? k : 0);
+                cp_async16(S + r * KP + 4 * c, src, bytes > 0 ? bytes : 0);
+            }
+        } else {
+            for (int q = tid; q < BT * kc4 * 4; q += NTHR) {
+                const int r = q / (kc4 * 4), kk = q - r * (kc4 * 4);
+                const int t = t0 + r, k = k0 + kk;
+                S[r * KP + kk] = (t < T && k < kend) ? __ldg(base + (int64_t)t * ld + k) : 0.f;
+            }
+        }
+    } else {
+        constexpr int C4 = BT / 4;
+        if (vec) {
+            for (int q = tid; q < kc4 * 4 * C4; q += NTHR) {
+                const int kk = q / C4, c = q - kk * C4;
+                const int k = k0 + kk, t = t0 + 4 * c;
+                int bytes = (k < kend) ? 4 * min(4, T - t) : 0;
+                const float* src = base + (int64_t)min(k, kend - 1) * ld + (bytes > 0 ? t : 0);
+                cp_async16(S + kk * BT + 4 * c, src, bytes > 0 ? bytes : 0);
+            }
+        } else {
+            for (int q = tid; q < kc4 * 4 * BT; q += NTHR) {
+                const int kk = q / BT, r = q - kk * BT;
+                const int k = k0 + kk, t = t0 + r;
+                S[kk * BT + r] = (t < T && k < kend) ? __ldg(base + (int64_t)k * ld + t) : 0.f;
+            }
+        }
+    }
+}
+
+// A_KC: A(m,k) = A[m*lda + k] (a_layout 0); B_KC: B(k,n) = B[n*ldb + k] (b_layout 1).
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(NTHR, 2)
+k_tiny_gemm(const __grid_constant__ TinyArgs P) {
+    orlk::pdl_enter();
+    extern __shared__ float4 smem_f4[];
+    float* As = reinterpret_cast<float*>(smem_f4);                  // A_KC ? [TM][KP] : [KC][TM]
+    float* Bs = As + (A_KC ? TM * KP : KC * TM);                    // B_KC ? [TN][KP] : [KC][TN]
+
+    const int tid = threadIdx.x;
+    int p = 0;
+    while (p + 1 < P.n && P.d[p + 1].tile_start <= (int)blockIdx.x) ++p;
+    const OrlkGemmDesc& d = P.d[p];
+    const int t = blockIdx.x - d.tile_start;
+    const int tm = t / d.tiles_n, tn = t - tm * d.tiles_n;
+    const int m0 = tm * TM, n0 = tn * TN;
+    const int M = d.M, N = d.N, K = d.K;
+
+    const int kg = tid >> 6, tg = tid & 63;
+    const int tx = tg & 7, ty = tg >> 3;                // 8 x 8 threads per k group, micro-tile 4 (m) x 2 (n)
+    float acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f}, cs[2] = {0.f, 0.f};
+    const bool do_rs = d.rowsum != nullptr && tn == 0;
+    const bool do_cs = d.colsum != nullptr && tm == 0;
+
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = min(KC, K - k0);
+        if (k0 > 0) __syncthreads();                    // the previous pass is done with the tiles
+        stage<TM, A_KC>(As, d.A, d.lda, m0, M, k0, kc, K, tid);
+        stage<TN, B_KC>(Bs, d.B, d.ldb, n0, N, k0, kc, K, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int nblk = (kc + 3) >> 2, per = (nblk + KG - 1) / KG;
+        const int b_lo = kg * per, b_hi = min(nblk, b_lo + per);
+#pragma unroll 2
+        for (int blk = b_lo; blk < b_hi; ++blk) {
+            const int k = 4 * blk;
+            float a[4][4], b[4][2];                     // a[i][e] = A(m_i, k+e), b[e][j] = B(k+e, n_j)
+            if (A_KC) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {           // rows ty + 8i: the 4 rows a warp touches are 16 bytes apart in the banks
+                    const float4 v = *reinterpret_cast<const float4*>(As + (ty + 8 * i) * KP + k);
+                    a[i][0] = v.x; a[i][1] = v.y; a[i][2] = v.z; a[i][3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {           // rows 4ty .. 4ty+3
+                    const float4 v = *reinterpret_cast<const float4*>(As + (k + e) * TM + 4 * ty);
+                    a[0][e] = v.x; a[1][e] = v.y; a[2][e] = v.z; a[3][e] = v.w;
+                }
+            }
+            if (B_KC) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {           // columns tx + 8j
+                    const float4 v = *reinterpret_cast<const float4*>(Bs + (tx + 8 * j) * KP + k);
+                    b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {           // columns 2tx, 2tx+1
+                    const float2 v = *reinterpret_cast<const float2*>(Bs + (k + e) * TN + 2 * tx);
+                    b[e][0] = v.x; b[e][1] = v.y;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(a[i][e], b[e][0], acc[i][0]);
+                    acc[i][1] = fmaf(a[i][e], b[e][1], acc[i][1]);
+                }
+            if (do_rs) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rs[i] += a[i][e];
+            }
+            if (do_cs) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { cs[0] += b[e][0]; cs[1] += b[e][1]; }
+            }
+        }
+    }
+
+    // ---- k-group partial tiles -> shared memory (the operand tiles are dead), then all threads finish the tile
+    __syncthreads();
+    float* red = As;                                    // [KG][TM][TN + 1]
+    float* rsum = red + KG * TM * (TN + 1);             // [KG][TM]
+    float* csum = rsum + KG * TM;                       // [KG][TN]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = A_KC ? ty + 8 * i : 4 * ty + i;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = B_KC ? tx + 8 * j : 2 * tx + j;
+            red[(kg * TM + r) * (TN + 1) + c] = acc[i][j];
+        }
+        if (do_rs && tx == 0) rsum[kg * TM + r] = rs[i];
+    }
+    if (do_cs && ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) csum[kg * TN + (B_KC ? tx + 8 * j : 2 * tx + j)] = cs[j];
+    }
+    __syncthreads();
+
+    const int slot = d.split_base;
+    const int epi = d.epi;
+    float* __restrict__ Cg = d.C != nullptr ? d.C + (int64_t)slot * d.c_split_stride : nullptr;
+    // pass 1: consecutive threads -> consecutive n (row-major C, C2, bias, aux are read / written in 64-byte rows);
+    // the finished value is parked in red[0] for the transposed pass
+    for (int e = tid; e < TM * TN; e += NTHR) {
+        const int r = e / TN, c = e - r * TN;
+        const int m = m0 + r, n = n0 + c;
+        float v = red[r * (TN + 1) + c] + red[(TM + r) * (TN + 1) + c] + red[(2 * TM + r) * (TN + 1) + c] +
+                  red[(3 * TM + r) * (TN + 1) + c];
+        if (m < M && n < N) {
+            if (d.bias != nullptr) v += __ldg(d.bias + n);
+            const float ax = d.aux != nullptr ? __ldg(d.aux + (int64_t)m * d.ldaux + n) : 0.f;
+            if (epi == ORLK_EPI_SWISH && d.C2 != nullptr) d.C2[(int64_t)m * d.ldc + n] = v;
+            switch (epi) {
+                case ORLK_EPI_RELU: v = fmaxf(v, 0.f); break;
+                case ORLK_EPI_RELU_MASK: v = ax > 0.f ? v : 0.f; break;
+                case ORLK_EPI_SWISH: v = v / (1.f + expf(-v)); break;
+                case ORLK_EPI_DSWISH: {
+                    const float s = 1.f / (1.f + expf(-ax));
+                    v = v * (s * (1.f + ax * (1.f - s)));
+                    break;
+                }
+                default: break;
+            }
+            if (Cg != nullptr) Cg[(int64_t)m * d.ldc + n] = v;
+        }
+        red[r * (TN + 1) + c] = v;
+    }
+    if (d.CT != nullptr) {
+        __syncthreads();
+        // pass 2: consecutive threads -> consecutive m (CT rows)
+        for (int e = tid; e < TM * TN; e += NTHR) {
+            const int c = e / TM, r = e - c * TM;
+            const int m = m0 + r, n = n0 + c;
+            if (m < M && n < N) d.CT[(int64_t)n * d.ldct + m] = red[r * (TN + 1) + c];
+        }
+    }
+    if (do_rs && tid < TM && m0 + tid < M)
+        d.rowsum[(int64_t)slot * d.sum_split_stride + m0 + tid] =
+            rsum[tid] + rsum[TM + tid] + rsum[2 * TM + tid] + rsum[3 * TM + tid];
+    if (do_cs && tid < TN && n0 + tid < N)
+        d.colsum[(int64_t)slot * d.sum_split_stride + n0 + tid] =
+            csum[tid] + csum[TN + tid] + csum[2 * TN + tid] + csum[3 * TN + tid];
+}
+
+template <bool A_KC, bool B_KC>
+constexpr size_t tiny_smem() {
+    return sizeof(float) * ((A_KC ? TM * KP : KC * TM) + (B_KC ? TN * KP : KC * TN));
+}
+
+template <bool A_KC, bool B_KC>
+int tiny_launch(const TinyArgs& args, int total_tiles, cudaStream_t s) {
+    orlk::launch(k_tiny_gemm<A_KC, B_KC>, total_tiles, NTHR, tiny_smem<A_KC, B_KC>(), s, args);
+    return check_launch("k_tiny_gemm");
+}
+
+}  // namespace
+
+// Set the shared-memory opt-in of all four layout variants once, outside stream capture.
+extern "C" int orlk_gemm_tiny_init(void) {
+    int rc = check(cudaFuncSetAttribute(k_tiny_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiny_smem<true, true>()), "tiny smem attr");
+    if (rc) return rc;
+    rc = check(cudaFuncSetAttribute(k_tiny_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiny_smem<true, false>()), "tiny smem attr");
+    if (rc) return rc;
+    rc = check(cudaFuncSetAttribute(k_tiny_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiny_smem<false, true>()), "tiny smem attr");
+    if (rc) return rc;
+    return check(cudaFuncSetAttribute(k_tiny_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiny_smem<false, false>()), "tiny smem attr");
+}
+
+// descs_host: HOST array (copied into the kernel parameters); tiles are 32 x 16, k_splits must be 1.
+extern "C" int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles, int a_layout, int b_layout,
+                              void* stream) {
+    ORLK_REQUIRE(descs_host != nullptr && n_descs > 0 && n_descs <= MAXP, "1..16 problems per launch");
+    ORLK_REQUIRE(total_tiles > 0, "total_tiles");
+    TinyArgs args;
+    args.n = n_descs;
+    for (int i = 0; i < n_descs; ++i) {
+        const OrlkGemmDesc& d = descs_host[i];
+        ORLK_REQUIRE(d.k_splits <= 1, "the small-row kernel does not split k");
+        ORLK_REQUIRE(d.a_layout == a_layout && d.b_layout == b_layout, "operand layouts must match the launch");
+        ORLK_REQUIRE(d.tiles_m == (d.M + TM - 1) / TM && d.tiles_n == (d.N + TN - 1) / TN, "tiles must be 32 x 16");
+        args.d[i] = d;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool a_kc = a_layout == 0, b_kc = b_layout == 1;
+    if (a_kc && b_kc) return tiny_launch<true, true>(args, total_tiles, s);
+    if (a_kc) return tiny_launch<true, false>(args, total_tiles, s);
+    if (b_kc) return tiny_launch<false, true>(args, total_tiles, s);
+    return tiny_launch<false, false>(args, total_tiles, s);
+}

@@ -92,6 +92,7 @@ class Runtime:
         self._keep: List[torch.Tensor] = []
         L.call("orlk_tc_init")
         L.call("orlk_gemm_init")
+        L.call("orlk_gemm_tiny_init")
         L.call("orlk_narrow_init")
 
     # ---- memory helpers (torch owns device memory: plumbing)
@@ -141,9 +142,23 @@ class Runtime:
             d.k_splits, d.k_chunk, d.split_base = splits, chunk, p.split_base
             d.tile_start, d.tiles_m, d.tiles_n = tile, tiles_m, tiles_n
             tile += tiles_m * tiles_n * splits
+        al, bl = layouts
+        if cfg == L.CFG_TINY:
+            # the small-row kernel takes its problems by value in the kernel parameters, at most 16 per launch
+            ops = []
+            for i0 in range(0, len(problems), 16):
+                n = min(16, len(problems) - i0)
+                sub = (L.GemmDesc * n)()
+                base = arr[i0].tile_start
+                for i in range(n):
+                    C.memmove(C.byref(sub[i]), C.byref(arr[i0 + i]), C.sizeof(L.GemmDesc))
+                    assert sub[i].k_splits == 1, "the small-row kernel does not split k"
+                    sub[i].tile_start -= base
+                tiles = (arr[i0 + n].tile_start if i0 + n < len(problems) else tile) - base
+                ops.append(lambda sub=sub, n=n, tiles=tiles: L.call("orlk_gemm_tiny", sub, n, tiles, al, bl, self.cur))
+            return ops[0] if len(ops) == 1 else (lambda: [op() for op in ops] and None)
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())
-        al, bl = layouts
         return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, al, bl, self.cur)
 
     def tc_gemm(self, *, A: Mat, a_gs: int, B: Mat, b_gs: int, G: int, passes: int, epi: int = L.EPI_NONE,

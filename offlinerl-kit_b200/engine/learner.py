@@ -326,6 +326,9 @@ def wgrad_layout(ps: ParamSet, n_layers: int, M: int, tc_layers: Sequence[bool] 
             out.append((-1, L.load().orlk_tc_effective_splits(M, TC_WGRAD_SPLITS)))
             continue
         out_r, out_c = (lay.out_dim, lay.in_dim) if lay.layout == "oi" else (lay.in_dim, lay.out_dim)
+        if M < TC_MIN_ROWS:        # short reductions: whole-k tiles, no split-K partials for Adam to re-read
+            out.append((L.CFG_TINY, 1))
+            continue
         cfg = L.CFG_BIG if (out_r >= 128 and out_c >= 128 and M >= 2048) else L.CFG_SMALL
         BM, BN, _ = L.CFG_TILES[cfg]
         tiles = (-(-out_r // BM)) * (-(-out_c // BN)) * ps.G
@@ -352,7 +355,7 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update."""
     ps, G, M = run.ps, run.G, run.M
     plan.keep += [run, gb, [x.keep for x in X]]
-    big, small = [], []
+    big, small, tiny = [], [], []
     n_l = run.nh + (1 if run.has_head else 0)
     layout = wgrad_layout(ps, n_l, M, run.tc_wgrad)
     splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
@@ -389,11 +392,13 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
         for g in range(G):
             xin = X[g] if l == 0 else run.h(l - 1, g)
             dy = run.dz(l, g) if l < run.nh else Mat.of(run.dOut[g])
-            (big if cfg == L.CFG_BIG else small).append(wgrad_problem(ps, gb, l, g, xin, dy, s))
+            {L.CFG_BIG: big, L.CFG_SMALL: small, L.CFG_TINY: tiny}[cfg].append(wgrad_problem(ps, gb, l, g, xin, dy, s))
     if big:
         launches.append((f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG)))
     if small:
         launches.append((f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL)))
+    if tiny:
+        launches.append((f"{tag}.wgrad_tiny", rt.gemm(tiny, L.CFG_TINY)))
     if len(launches) > 1:
         plan.fork()
         for i, (label, op) in enumerate(launches):

@@ -6,6 +6,7 @@ fp32 device tensor.  The ``nn.Parameter`` objects of the facade modules are re-p
 so ``state_dict()`` / ``torch.save`` / ``load_state_dict`` keep working unchanged while the
 kernels see ``base + offset``.
 """
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -232,7 +233,9 @@ class GradBuf:
 
 # ---------------------------------------------------------------------------------------------- emitters
 TC_MIN_ROWS = 1024      # weight gradients: below this the reduction is too short for the tensor-core kernel
-TC_MIN_ROWS_FWD = 128   # forward / dgrad: small row counts tile the OUTPUT columns (32 per CTA) to get enough CTAs
+# forward / dgrad: below this the layer is latency-bound and goes to the small-row fp32 kernel (csrc/orlk_tiny.cu);
+# ORLK_TC_MIN_ROWS_FWD=128 restores the n-tiled tensor-core path for those layers
+TC_MIN_ROWS_FWD = int(os.environ.get("ORLK_TC_MIN_ROWS_FWD", "1024"))
 
 
 def tc_n_tile(M: int, N: int) -> int:
@@ -258,7 +261,7 @@ def pick_cfg(M: int, N: int) -> int:
         return L.CFG_BIG
     if M * N >= 64 * 64 * 96:
         return L.CFG_MID
-    return L.CFG_KPAR      # small layers are latency-bound: whole-K slabs, 4 k-parallel groups per 32 x 32 tile
+    return L.CFG_TINY      # small layers are latency-bound: 32 x 16 tiles, whole-k cp.async burst, 4 k-parallel groups
 
 
 def fwd_problem(ps: ParamSet, l: int, g: int, X: Mat, Y: Mat, epi: int, store: str = "P", Z: Optional[Mat] = None,

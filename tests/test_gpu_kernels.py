@@ -76,7 +76,7 @@ def _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, epi, splits, with_bias, sum
         _close(cs[:, :N].sum(0), B.double().sum(0), rtol=1e-5, atol=1e-4, msg=tag + " colsum")
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_gemm_layouts_and_ragged_shapes(rt, cfg):
     shapes = [(1, 1, 1), (37, 23, 23), (300, 256, 250), (128, 128, 64), (129, 6, 256), (256, 256, 256), (64, 1, 515)]
     seed = 0
@@ -87,7 +87,7 @@ def test_gemm_layouts_and_ragged_shapes(rt, cfg):
                 _gemm_case(rt, cfg, M, N, K, a_layout, b_layout, 0, 1, with_bias=bool(seed % 2), sums=False, seed=seed)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_gemm_epilogues(rt, cfg):
     for epi in (1, 2, 3, 4):
         _gemm_case(rt, cfg, 200, 136, 96, 0, 1, epi, 1, with_bias=epi in (1, 3), sums=False, seed=100 + epi)
@@ -102,11 +102,18 @@ def test_gemm_split_k_and_sums(rt, cfg):
         _gemm_case(rt, cfg, M, N, K, 1, 0, 0, splits, with_bias=False, sums=True, seed=M + N + K)
 
 
+def test_gemm_small_row_kernel_sums_and_long_k(rt):
+    # the small-row kernel (cfg 4) never splits k: whole reductions, several 256-wide passes, bias row/col sums
+    for (M, N, K) in [(256, 256, 256), (256, 23, 256), (12, 256, 256), (256, 17, 700), (100, 50, 1000), (1, 256, 515)]:
+        _gemm_case(rt, 4, M, N, K, 1, 0, 0, 1, with_bias=False, sums=True, seed=M + N + K)
+        _gemm_case(rt, 4, M, N, K, 0, 1, 0, 1, with_bias=True, sums=True, seed=M + N + K + 1)
+
+
 def test_gemm_grouped_many_problems(rt):
     from offlinerlkit_b200.engine.core import GP
     gen = torch.Generator().manual_seed(5)
     probs, refs, outs, keep = [], [], [], []
-    for i, (M, N, K) in enumerate([(256, 256, 23), (40, 256, 256), (256, 1, 256), (77, 33, 129)] * 3):
+    for i, (M, N, K) in enumerate([(256, 256, 23), (40, 256, 256), (256, 1, 256), (77, 33, 129)] * 5):
         A, B = torch.randn(M, K, generator=gen).to(DEV), torch.randn(N, K, generator=gen).to(DEV)
         Cd = torch.zeros(M, N, device=DEV)
         probs.append(GP(A=A.data_ptr(), lda=K, a_layout=0, B=B.data_ptr(), ldb=K, b_layout=1, C=Cd.data_ptr(), ldc=N,
@@ -114,7 +121,7 @@ def test_gemm_grouped_many_problems(rt):
         refs.append(A.double().cpu() @ B.double().cpu().t())
         outs.append(Cd)
         keep += [A, B]
-    for cfg in (0, 1, 2, 3):
+    for cfg in (0, 1, 2, 3, 4):     # 20 problems: cfg 4 travels in kernel parameters, 16 problems per launch
         for o in outs:
             o.zero_()
         rt.gemm(probs, cfg)()
