@@ -47,6 +47,9 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 bool pdl_enabled();
+// Profiling aid shared by the GEMM kernels (orlk_tc_set_trace): device buffer for per-CTA clock stamps, or NULL.
+unsigned long long* trace_buffer();
+void set_trace_buffer(unsigned long long* p);
 // First launch of each kernel: pin its shared-memory carveout (ORLK_CARVEOUT=percent, default: leave the driver's choice).
 void prepare_kernel(const void* fn);
 

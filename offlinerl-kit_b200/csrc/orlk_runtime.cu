@@ -20,6 +20,10 @@ bool pdl_enabled() {
     }
     return on == 1;
 }
+static unsigned long long* g_trace = nullptr;
+unsigned long long* trace_buffer() { return g_trace; }
+void set_trace_buffer(unsigned long long* p) { g_trace = p; }
+
 void prepare_kernel(const void* fn) {
     static const void* seen[256];
     static int n_seen = 0;

@@ -562,9 +562,8 @@ int make_map_c(CUtensorMap* map, float* base, int64_t ldc, int64_t gs, int64_t s
 
 extern "C" int orlk_sizeof_tc_gemm(void) { return (int)sizeof(OrlkTcGemm); }
 
-static unsigned long long* g_tc_trace = nullptr;
 extern "C" int orlk_tc_set_trace(void* dev_buf) {
-    g_tc_trace = (unsigned long long*)dev_buf;
+    orlk::set_trace_buffer((unsigned long long*)dev_buf);
     return 0;
 }
 
@@ -617,7 +616,7 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
     p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
     p.NT = NT; p.tiles_n = q->N / NT;
-    p.trace = g_tc_trace;
+    p.trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }
 
     tc_ring(NT, q->passes, &p.stages, &p.stage_bytes);

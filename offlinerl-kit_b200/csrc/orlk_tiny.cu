@@ -17,39 +17,69 @@ constexpr int TM = 32;            // tile rows
 constexpr int TN = 16;            // tile columns
 constexpr int KC = 256;           // k extent staged per pass
 constexpr int KP = KC + 4;        // row pitch (floats) of a k-contiguous operand tile: 260 % 32 == 4 -> rows sit 16 bytes apart in the banks
-constexpr int NTHR = 256;
-constexpr int KG = 4;             // k groups
+constexpr int NTHR = 512;
+constexpr int KG = 8;             // k groups of 64 threads; group g owns the g-th eighth of every staged k extent
 constexpr int MAXP = 16;          // problems per launch (kernel-parameter space: 16 x 176 bytes)
+static_assert(TM * TN == NTHR, "the epilogue gives every thread one element of the tile");
 
 struct TinyArgs {
     OrlkGemmDesc d[MAXP];
     int n;
+    unsigned long long* trace;    // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
 };
+#define TINY_STAMP(slot)                                                                                      \
+    do {                                                                                                      \
+        if (P.trace != nullptr && threadIdx.x == 0) P.trace[(int64_t)blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
+// Named barrier 1 + g over the 64 threads of k group g (literal ids, so that the kernel reserves 9 barriers, not 16).
+__device__ __forceinline__ void group_sync(int g) {
+    switch (g) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+        case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+        case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+        case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+    }
+}
 
-// Stage rows [t0, t0+BT) x k [k0, k0+kc) of an operand.  KCONT: operand(t,k) = base[t*ld + k] -> S[t][KP];
-// otherwise operand(t,k) = base[k*ld + t] -> S[k][BT].  Everything outside the matrix is zero-filled.
+// One k group (64 threads, tg = 0..63) stages ITS OWN share of an operand tile: rows [t0, t0+BT) x 4-k blocks
+// [b_lo, b_hi) (relative to k0), 16-byte cp.async copies in the operand's own layout.  KCONT: operand(t,k) =
+// base[t*ld + k] -> S[t][KP]; otherwise operand(t,k) = base[k*ld + t] -> S[k][BT].  Outside the matrix: zeros.
 template <int BT, bool KCONT>
-__device__ __forceinline__ void stage(float* S, const float* __restrict__ base, int64_t ld, int t0, int T, int k0, int kc,
-                                      int kend, int tid) {
-    const bool vec = aligned16(base) && (ld % 4) == 0;
-    const int kc4 = (kc + 3) >> 2;                      // 4-k blocks in this pass (a ragged last block is zero-padded)
+__device__ __forceinline__ void stage(float* S, const float* __restrict__ base, int64_t ld, bool vec, int t0, int T, int k0,
+                                      int b_lo, int b_hi, int kend, int tg) {
+    const int nb = b_hi - b_lo;
+    if (nb <= 0) return;
     if (KCONT) {
         if (vec) {
-            for (int q = tid; q < BT * kc4; q += NTHR) {
-                const int r = q / kc4, c = q - r * kc4;
-                const int t = t0 + r, k = k0 + 4 * c;
-                int bytes = (t < T) ? 4 * min(4, kend - k) : 0;
-                const float* src = base + (int64_t)min(t, T - 1) * ld + (bytes > 0 ? k : 0);
-                cp_async16(S + r * KP + 4 * c, src, bytes > 0 ? bytes : 0);
+            if (nb == 8) {                              // the common case (256 k per pass): shifts instead of divisions
+#pragma unroll
+                for (int i = 0; i < BT * 8 / 64; ++i) {
+                    const int idx = tg + 64 * i;
+                    const int r = idx >> 3, c = b_lo + (idx & 7);
+                    const int t = t0 + r, k = k0 + 4 * c;
+                    const int bytes = (t < T) ? 4 * min(4, kend - k) : 0;
+                    cp_async16(S + r * KP + 4 * c, base + (int64_t)min(t, T - 1) * ld + k, bytes);
+                }
+            } else {
+                for (int idx = tg; idx < BT * nb; idx += 64) {
+                    const int r = idx / nb, c = b_lo + (idx - r * nb);
+                    const int t = t0 + r, k = k0 + 4 * c;
+                    const int bytes = (t < T) ? 4 * min(4, kend - k) : 0;
+                    cp_async16(S + r * KP + 4 * c, base + (int64_t)min(t, T - 1) * ld + k, bytes);
+                }
             }
         } else {
-            for (int q = tid; q < BT * kc4 * 4; q += NTHR) {
-                const int r = q / (kc4 * 4), kk = q - r * (kc4 * 4);
+            for (int q = tg; q < BT * nb * 4; q += 64) {
+                const int r = q / (nb * 4), kk = 4 * b_lo + (q - r * (nb * 4));
                 const int t = t0 + r, k = k0 + kk;
                 S[r * KP + kk] = (t < T && k < kend) ? __ldg(base + (int64_t)t * ld + k) : 0.f;
             }
@@ -57,16 +87,17 @@ __device__ __forceinline__ void stage(float* S, const float* __restrict__ base, 
     } else {
         constexpr int C4 = BT / 4;
         if (vec) {
-            for (int q = tid; q < kc4 * 4 * C4; q += NTHR) {
-                const int kk = q / C4, c = q - kk * C4;
+            for (int idx = tg; idx < 4 * nb * C4; idx += 64) {
+                const int kr = idx / C4, c = idx - kr * C4;
+                const int kk = 4 * b_lo + kr;
                 const int k = k0 + kk, t = t0 + 4 * c;
-                int bytes = (k < kend) ? 4 * min(4, T - t) : 0;
-                const float* src = base + (int64_t)min(k, kend - 1) * ld + (bytes > 0 ? t : 0);
-                cp_async16(S + kk * BT + 4 * c, src, bytes > 0 ? bytes : 0);
+                const int bytes = (k < kend && t < T) ? 4 * min(4, T - t) : 0;
+                cp_async16(S + kk * BT + 4 * c, base + (int64_t)min(k, kend - 1) * ld + (t < T ? t : 0), bytes);
             }
         } else {
-            for (int q = tid; q < kc4 * 4 * BT; q += NTHR) {
-                const int kk = q / BT, r = q - kk * BT;
+            for (int q = tg; q < 4 * nb * BT; q += 64) {
+                const int kr = q / BT, r = q - kr * BT;
+                const int kk = 4 * b_lo + kr;
                 const int k = k0 + kk, t = t0 + r;
                 S[kk * BT + r] = (t < T && k < kend) ? __ldg(base + (int64_t)k * ld + t) : 0.f;
             }
@@ -78,7 +109,7 @@ __device__ __forceinline__ void stage(float* S, const float* __restrict__ base, 
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(NTHR, 2)
 k_tiny_gemm(const __grid_constant__ TinyArgs P) {
-    orlk::pdl_enter();
+    TINY_STAMP(0);
     extern __shared__ float4 smem_f4[];
     float* As = reinterpret_cast<float*>(smem_f4);                  // A_KC ? [TM][KP] : [KC][TM]
     float* Bs = As + (A_KC ? TM * KP : KC * TM);                    // B_KC ? [TN][KP] : [KC][TN]
@@ -91,6 +122,16 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     const int tm = t / d.tiles_n, tn = t - tm * d.tiles_n;
     const int m0 = tm * TM, n0 = tn * TN;
     const int M = d.M, N = d.N, K = d.K;
+    const bool vecA = aligned16(d.A) && (d.lda % 4) == 0, vecB = aligned16(d.B) && (d.ldb % 4) == 0;
+    orlk::pdl_enter();                                  // nothing above touched global data
+    TINY_STAMP(1);
+
+    // this thread's element of the tile in the epilogue: fetch its bias / aux operands now, off the critical path
+    const int er = tid / TN, ec = tid - er * TN;
+    const int em = m0 + er, en = n0 + ec;
+    const bool e_ok = em < M && en < N;
+    const float e_bias = (e_ok && d.bias != nullptr) ? __ldg(d.bias + en) : 0.f;
+    const float e_aux = (e_ok && d.aux != nullptr) ? __ldg(d.aux + (int64_t)em * d.ldaux + en) : 0.f;
 
     const int kg = tid >> 6, tg = tid & 63;
     const int tx = tg & 7, ty = tg >> 3;                // 8 x 8 threads per k group, micro-tile 4 (m) x 2 (n)
@@ -104,13 +145,16 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     for (int k0 = 0; k0 < K; k0 += KC) {
         const int kc = min(KC, K - k0);
         if (k0 > 0) __syncthreads();                    // the previous pass is done with the tiles
-        stage<TM, A_KC>(As, d.A, d.lda, m0, M, k0, kc, K, tid);
-        stage<TN, B_KC>(Bs, d.B, d.ldb, n0, N, k0, kc, K, tid);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
         const int nblk = (kc + 3) >> 2, per = (nblk + KG - 1) / KG;
-        const int b_lo = kg * per, b_hi = min(nblk, b_lo + per);
+        const int b_lo = min(nblk, kg * per), b_hi = min(nblk, b_lo + per);
+        // every k group fetches and waits for its own eighth of the two tiles: the groups never wait for each other
+        stage<TM, A_KC>(As, d.A, d.lda, vecA, m0, M, k0, b_lo, b_hi, K, tg);
+        stage<TN, B_KC>(Bs, d.B, d.ldb, vecB, n0, N, k0, b_lo, b_hi, K, tg);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (k0 == 0) TINY_STAMP(2);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        group_sync(kg);                                 // named barrier of this group's two warps
+        if (k0 == 0) TINY_STAMP(3);
 #pragma unroll 2
         for (int blk = b_lo; blk < b_hi; ++blk) {
             const int k = 4 * blk;
@@ -161,7 +205,8 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
         }
     }
 
-    // ---- k-group partial tiles -> shared memory (the operand tiles are dead), then all threads finish the tile
+    // ---- k-group partial tiles -> shared memory (the operand tiles are dead), then every thread finishes one element
+    TINY_STAMP(4);
     __syncthreads();
     float* red = As;                                    // [KG][TM][TN + 1]
     float* rsum = red + KG * TM * (TN + 1);             // [KG][TM]
@@ -181,51 +226,51 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
         for (int j = 0; j < 2; ++j) csum[kg * TN + (B_KC ? tx + 8 * j : 2 * tx + j)] = cs[j];
     }
     __syncthreads();
+    TINY_STAMP(5);
 
     const int slot = d.split_base;
     const int epi = d.epi;
-    float* __restrict__ Cg = d.C != nullptr ? d.C + (int64_t)slot * d.c_split_stride : nullptr;
-    // pass 1: consecutive threads -> consecutive n (row-major C, C2, bias, aux are read / written in 64-byte rows);
-    // the finished value is parked in red[0] for the transposed pass
-    for (int e = tid; e < TM * TN; e += NTHR) {
-        const int r = e / TN, c = e - r * TN;
-        const int m = m0 + r, n = n0 + c;
-        float v = red[r * (TN + 1) + c] + red[(TM + r) * (TN + 1) + c] + red[(2 * TM + r) * (TN + 1) + c] +
-                  red[(3 * TM + r) * (TN + 1) + c];
-        if (m < M && n < N) {
-            if (d.bias != nullptr) v += __ldg(d.bias + n);
-            const float ax = d.aux != nullptr ? __ldg(d.aux + (int64_t)m * d.ldaux + n) : 0.f;
-            if (epi == ORLK_EPI_SWISH && d.C2 != nullptr) d.C2[(int64_t)m * d.ldc + n] = v;
-            switch (epi) {
-                case ORLK_EPI_RELU: v = fmaxf(v, 0.f); break;
-                case ORLK_EPI_RELU_MASK: v = ax > 0.f ? v : 0.f; break;
-                case ORLK_EPI_SWISH: v = v / (1.f + expf(-v)); break;
-                case ORLK_EPI_DSWISH: {
-                    const float s = 1.f / (1.f + expf(-ax));
-                    v = v * (s * (1.f + ax * (1.f - s)));
-                    break;
-                }
-                default: break;
+    // consecutive threads -> consecutive n: row-major C / C2 leave in 64-byte rows
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < KG; ++g) v += red[(g * TM + er) * (TN + 1) + ec];      // fixed order: bit-reproducible
+    if (e_ok) {
+        v += e_bias;
+        if (epi == ORLK_EPI_SWISH && d.C2 != nullptr) d.C2[(int64_t)em * d.ldc + en] = v;
+        switch (epi) {
+            case ORLK_EPI_RELU: v = fmaxf(v, 0.f); break;
+            case ORLK_EPI_RELU_MASK: v = e_aux > 0.f ? v : 0.f; break;
+            case ORLK_EPI_SWISH: v = v / (1.f + expf(-v)); break;
+            case ORLK_EPI_DSWISH: {
+                const float sg = 1.f / (1.f + expf(-e_aux));
+                v = v * (sg * (1.f + e_aux * (1.f - sg)));
+                break;
             }
-            if (Cg != nullptr) Cg[(int64_t)m * d.ldc + n] = v;
+            default: break;
         }
-        red[r * (TN + 1) + c] = v;
+        if (d.C != nullptr) d.C[(int64_t)slot * d.c_split_stride + (int64_t)em * d.ldc + en] = v;
     }
     if (d.CT != nullptr) {
+        __syncthreads();                                // everyone has read its partials
+        red[er * (TN + 1) + ec] = v;
         __syncthreads();
-        // pass 2: consecutive threads -> consecutive m (CT rows)
-        for (int e = tid; e < TM * TN; e += NTHR) {
-            const int c = e / TM, r = e - c * TM;
-            const int m = m0 + r, n = n0 + c;
-            if (m < M && n < N) d.CT[(int64_t)n * d.ldct + m] = red[r * (TN + 1) + c];
-        }
+        // consecutive threads -> consecutive m: CT leaves in 128-byte rows
+        const int c = tid / TM, r = tid - c * TM;
+        if (m0 + r < M && n0 + c < N) d.CT[(int64_t)(n0 + c) * d.ldct + m0 + r] = red[r * (TN + 1) + c];
     }
-    if (do_rs && tid < TM && m0 + tid < M)
-        d.rowsum[(int64_t)slot * d.sum_split_stride + m0 + tid] =
-            rsum[tid] + rsum[TM + tid] + rsum[2 * TM + tid] + rsum[3 * TM + tid];
-    if (do_cs && tid < TN && n0 + tid < N)
-        d.colsum[(int64_t)slot * d.sum_split_stride + n0 + tid] =
-            csum[tid] + csum[TN + tid] + csum[2 * TN + tid] + csum[3 * TN + tid];
+    TINY_STAMP(6);
+    if (do_rs && tid < TM && m0 + tid < M) {
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < KG; ++g) sum += rsum[g * TM + tid];
+        d.rowsum[(int64_t)slot * d.sum_split_stride + m0 + tid] = sum;
+    }
+    if (do_cs && tid < TN && n0 + tid < N) {
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < KG; ++g) sum += csum[g * TN + tid];
+        d.colsum[(int64_t)slot * d.sum_split_stride + n0 + tid] = sum;
+    }
 }
 
 template <bool A_KC, bool B_KC>
@@ -259,6 +304,7 @@ extern "C" int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int t
     ORLK_REQUIRE(total_tiles > 0, "total_tiles");
     TinyArgs args;
     args.n = n_descs;
+    args.trace = orlk::trace_buffer();
     for (int i = 0; i < n_descs; ++i) {
         const OrlkGemmDesc& d = descs_host[i];
         ORLK_REQUIRE(d.k_splits <= 1, "the small-row kernel does not split k");
