@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 8
+#define ORLK_ABI_VERSION 9
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -147,6 +147,14 @@ typedef struct OrlkTcGemm {
     int32_t passes;   /* 1 or 3 */
     int32_t n_tile;   /* output columns per CTA (multiple of 16 dividing N); 0 = N.  Small-M layers use 32 so that
                          (M/128) x (N/32) CTAs share the work */
+    /* Rank-1 operand generator (both NULL = off).  When set, the kernel does not multiply A itself but
+     *   A'[g][m][k] = gen_row[g][m] * gen_col[g][k] * (A[g][m][k] > 0),
+     * built in shared memory from the A tile TMA just delivered.  This is the gradient that flows back through a
+     * scalar head into the last ReLU layer: dZ[m][k] = dq[m] * w_head[k] * relu'(H[m][k]) (dgrad: A = H, gen_row = dq,
+     * gen_col = w_head) and its transpose (wgrad: A = H^T, gen_row = w_head, gen_col = dq), so dZ never exists in
+     * global memory (autograd of modules/critic_module.py:25-33's last Linear).  Requires K % 4 == 0. */
+    const float* gen_row; int64_t gen_row_gs;
+    const float* gen_col; int64_t gen_col_gs;
 } OrlkTcGemm;
 int orlk_tc_init(void);
 int orlk_tc_gemm(const OrlkTcGemm* params_host, void* stream);

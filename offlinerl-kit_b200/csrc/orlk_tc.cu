@@ -40,6 +40,8 @@ struct TcParams {
     float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
     int M, N, K, G, epi, k_splits, slabs_per_split, tiles_m, tiles_n, NT;   // NT = output columns per CTA (n-tile)
     int stages, stage_bytes;   // depth of the TMA ring and bytes per stage (depend on NT and the precision mode)
+    const float* gen_row; int64_t gen_row_gs;   // rank-1 operand generator (see OrlkTcGemm), NULL = off
+    const float* gen_col; int64_t gen_col_gs;
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
     unsigned long long* trace; // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
@@ -188,6 +190,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int slab0 = split * p.slabs_per_split;
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
     const bool want_rowsum = p.rowsum != nullptr && tile_n == 0;
+    const bool gen = p.gen_row != nullptr;
 
     const int b_bytes = NT * BK * 4;
     auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
@@ -257,13 +260,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
         const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
         if (p.trace != nullptr && p.trace_mode == 2 && nslabs <= STAGES) {   // experiment: issue only once all slabs landed
-            for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32(PASSES == 3 ? &splitb[it] : &full[it]), 0);
+            for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32((PASSES == 3 || gen) ? &splitb[it] : &full[it]), 0);
             TC_STAMP(3);
         }
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(smem_u32(PASSES == 3 ? &splitb[s] : &full[s]), ph);
+            mbar_wait(smem_u32((PASSES == 3 || gen) ? &splitb[s] : &full[s]), ph);
             tc_fence_after();
             if (it == 0) TC_STAMP(4);
             if (it == nslabs - 1) TC_STAMP(5);
@@ -349,9 +352,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp >= 2) {
         const int t = threadIdx.x - 64;                     // 0..127
-        if (PASSES == 3) {
-            // -------------------------------------------------------------- operand splitter
+        if (PASSES == 3 || gen) {
+            // -------------------------------------------------------------- operand splitter (+ rank-1 generator)
             const int nB4 = NT * BK / 4;
+            // float4 number t + 128 j of the swizzled A tile sits in row t/8 + 16 j at chunk position t%8, i.e. it holds
+            // k = 4c .. 4c+3 of that row with c = (t%8) ^ ((t/8) & 7) - the same c for all eight j.  So the generator
+            // needs eight row factors (fixed for the whole CTA) and one float4 of column factors per k-slab.
+            float grow[8];
+            const int gc = (t & 7) ^ ((t >> 3) & 7);
+            const float* gcol = nullptr;
+            if (gen) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = tile_m * BM + (t >> 3) + 16 * j;
+                    grow[j] = m < p.M ? __ldg(p.gen_row + (int64_t)g * p.gen_row_gs + m) : 0.f;
+                }
+                gcol = p.gen_col + (int64_t)g * p.gen_col_gs + 4 * gc;
+            }
             for (int it = 0; it < nslabs; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -369,11 +386,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = ar[t + 128 * j];
+                    if (gen) {
+                        const int k = (slab0 + it) * BK + 4 * gc;
+                        const float4 cv = k < p.K ? __ldg(reinterpret_cast<const float4*>(gcol + (int64_t)(slab0 + it) * BK))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) al[t + 128 * j] = lo_tf32(v[j]);
+                        for (int j = 0; j < 8; ++j) {
+                            v[j].x = v[j].x > 0.f ? grow[j] * cv.x : 0.f;
+                            v[j].y = v[j].y > 0.f ? grow[j] * cv.y : 0.f;
+                            v[j].z = v[j].z > 0.f ? grow[j] * cv.z : 0.f;
+                            v[j].w = v[j].w > 0.f ? grow[j] * cv.w : 0.f;
+                            ar[t + 128 * j] = v[j];
+                        }
+                    }
+                    if (PASSES == 3) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) al[t + 128 * j] = lo_tf32(v[j]);
+                    }
                 }
                 if (st4) TC_STAMP(9);
-                for (int i0 = 0; i0 < nB4; i0 += 128 * 8) {
+                for (int i0 = 0; PASSES == 3 && i0 < nB4; i0 += 128 * 8) {
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -616,6 +648,10 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
     p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
     p.NT = NT; p.tiles_n = q->N / NT;
+    ORLK_REQUIRE((q->gen_row == nullptr) == (q->gen_col == nullptr), "gen_row and gen_col go together");
+    ORLK_REQUIRE(q->gen_row == nullptr || (q->K % 4 == 0 && aligned16(q->gen_col) && q->gen_col_gs % 4 == 0),
+                 "the operand generator needs K % 4 == 0 and 16-byte aligned column factors");
+    p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;
     p.trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }
 

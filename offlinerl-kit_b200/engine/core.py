@@ -164,7 +164,8 @@ class Runtime:
     def tc_gemm(self, *, A: Mat, a_gs: int, B: Mat, b_gs: int, G: int, passes: int, epi: int = L.EPI_NONE,
                 C: Optional[Mat] = None, c_gs: int = 0, c_split_stride: int = 0, CT: Optional[Mat] = None, ct_gs: int = 0,
                 bias: int = 0, bias_gs: int = 0, aux: Optional[Mat] = None, aux_gs: int = 0, rowsum: int = 0,
-                rowsum_gs: int = 0, rowsum_split_stride: int = 0, k_splits: int = 1, n_tile: int = 0) -> Callable[[], None]:
+                rowsum_gs: int = 0, rowsum_split_stride: int = 0, k_splits: int = 1, n_tile: int = 0,
+                gen_row: int = 0, gen_row_gs: int = 0, gen_col: int = 0, gen_col_gs: int = 0) -> Callable[[], None]:
         """tcgen05 GEMM launch: C[g] = epi(A[g] (M x K) . B[g]^T (N x K)); group strides in floats."""
         q = L.TcGemm()
         q.A, q.lda, q.a_gs = A.ptr, A.ld, a_gs
@@ -180,6 +181,7 @@ class Runtime:
         q.M, q.N, q.K, q.G = A.rows, B.rows, A.cols, G
         assert A.cols == B.cols
         q.epi, q.passes, q.n_tile = epi, passes, n_tile
+        q.gen_row, q.gen_row_gs, q.gen_col, q.gen_col_gs = gen_row or None, gen_row_gs, gen_col or None, gen_col_gs
         q.k_splits = self.lib.orlk_tc_effective_splits(A.cols, k_splits)
         qp = _ctypes_pointer(q)      # the struct is read on the host at every launch: keep it alive in the closure
         return lambda: L.call("orlk_tc_gemm", qp, self.cur)

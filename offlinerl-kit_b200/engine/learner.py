@@ -195,6 +195,18 @@ class MlpRun:
             if self.tc_wgrad[l]:
                 self.dZT[l] = rt.zeros(G, lays[l].out_dim, self.Mt)
                 self.HT[l - 1] = rt.zeros(G, lays[l - 1].out_dim, self.Mt)
+        # Scalar head over a tensor-core last hidden layer: dZ[last] = dOut (x) w_head * relu'(H[last]) is rank-1 times a
+        # mask, so the dgrad / wgrad GEMMs that consume it build it in shared memory from H / H^T (orlk_tc_gemm's
+        # operand generator) and the head_dgrad launch with its two 16 MB outputs disappears.
+        last = n_hidden - 1
+        self.fuse_head_bwd = (need_grad and self.has_head and self.NS == 1 and n_hidden >= 2 and share_forward is None
+                              and self.tc_dgrad[last] and self.tc_wgrad[last] and lays[n_hidden].layout == "oi"
+                              and lays[last].out_dim % 4 == 0 and self.Mt == M
+                              and lays[n_hidden].w_off % 4 == 0 and lays[n_hidden].w_gs % 4 == 0
+                              and os.environ.get("ORLK_FUSE_HEAD_BWD", "1") != "0")
+        if self.fuse_head_bwd:
+            self.HT[last] = rt.zeros(G, lays[last].out_dim, self.Mt)
+            self.dZT[last] = None           # never materialised
         if any(self.tc_dgrad):
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
         # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
@@ -272,6 +284,8 @@ def emit_head_forward(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
 def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     """dZ[last hidden] = (dOut W_head) * relu'(H[last hidden])  (+ its transpose for a tensor-core wgrad)."""
     ps, G, l = run.ps, run.G, run.nh
+    if run.fuse_head_bwd:
+        return                  # folded into the consumers' operand generator
     lay = ps.layers[l]
     K = lay.in_dim
     hmask = run.H[l - 1]
@@ -289,8 +303,14 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
         lay = ps.layers[l]
         if run.tc_dgrad[l]:
             K, N = lay.out_dim, lay.in_dim
+            gen = {}
+            a_src = run.dZ[l]
+            if run.fuse_head_bwd and l == run.nh - 1:
+                head = ps.layers[run.nh]
+                a_src = run.H[l]            # the generator turns relu(H) into dOut[m] * w_head[k] * (H > 0)
+                gen = dict(gen_row=run.dOut.data_ptr(), gen_row_gs=M, gen_col=ps.w(run.nh, 0), gen_col_gs=head.w_gs)
             plan.add(f"{tag}.dgrad{l}.tc", rt.tc_gemm(
-                A=_grouped(run.dZ[l], M, K, K), a_gs=M * K, B=Mat(ps.wt(l, 0), N, K, K), b_gs=lay.w_gs, G=G,
+                A=_grouped(a_src, M, K, K), a_gs=M * K, B=Mat(ps.wt(l, 0), N, K, K), b_gs=lay.w_gs, G=G, **gen,
                 passes=run.tc, n_tile=tc_n_tile(M, N), epi=L.EPI_RELU_MASK, C=_grouped(run.dZ[l - 1], M, N, N), c_gs=M * N,
                 CT=_grouped(run.dZT[l - 1], N, M, run.Mt) if run.dZT[l - 1] is not None else None, ct_gs=N * run.Mt,
                 aux=_grouped(run.H[l - 1], M, N, N), aux_gs=M * N))
@@ -383,8 +403,14 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
         assert s <= gb.n_slots, (s, gb.n_slots)
         if cfg == -1:
             # dW[o,i] = sum_m dZ^T[o,m] * H^T[i,m]; bias gradient = row sums of dZ^T (a ones-tile MMA)
+            gen = {}
+            a_src = run.dZT[l]
+            if run.fuse_head_bwd and l == run.nh - 1:
+                head = ps.layers[run.nh]
+                a_src = run.HT[l]           # dZ^T[o][m] = w_head[o] * dOut[m] * (H^T[o][m] > 0)
+                gen = dict(gen_row=ps.w(run.nh, 0), gen_row_gs=head.w_gs, gen_col=run.dOut.data_ptr(), gen_col_gs=M)
             launches.append((f"{tag}.wgrad{l}.tc", rt.tc_gemm(
-                A=_grouped(run.dZT[l], lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt,
+                A=_grouped(a_src, lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt, **gen,
                 B=_grouped(run.HT[l - 1], lay.in_dim, M, run.Mt), b_gs=lay.in_dim * run.Mt, G=G, passes=run.tc,
                 C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
                 rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s)))
