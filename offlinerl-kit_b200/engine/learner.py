@@ -241,6 +241,10 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
     return Mat(t.data_ptr(), rows, cols, ld, t)
 
 
+# the streaming first-layer kernel pays off for long row counts; short passes take the small-row GEMM (one k pass)
+NARROW_MIN_ROWS = int(os.environ.get("ORLK_NARROW_MIN_ROWS", "1024"))
+
+
 def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
     """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
     ps, G, M = run.ps, run.G, run.M
@@ -255,7 +259,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
                 CT=_grouped(run.HT[l], N, M, run.Mt) if run.HT[l] is not None else None, ct_gs=N * run.Mt,
                 bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
             continue
-        if l == 0 and run.narrow0 and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
+        if l == 0 and run.narrow0 and M >= NARROW_MIN_ROWS and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
             ht = run.HT[0]
             args = (X[0].ptr, X[0].ld, 0, ps.w(0, 0, run.store), lay.in_dim, lay.w_gs, ps.b(0, 0, run.store), lay.b_gs,
                     run.H[0].data_ptr(), lay.out_dim, M * lay.out_dim, ht.data_ptr() if ht is not None else None, run.Mt,
