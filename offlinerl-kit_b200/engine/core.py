@@ -316,6 +316,37 @@ class Plan:
         self.ops.append(("join", op))
         self._branch = 0
 
+    # ---- a detached launch: runs on its own stream after everything issued so far, joined by join_detached()
+    @property
+    def has_detached(self) -> bool:
+        return getattr(self, "_aux", None) is not None
+
+    def detach(self, label: str, op: Callable[[], None]) -> None:
+        if not self.has_detached:
+            self._aux, self._ev_aux_fork, self._ev_aux_join = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            L.call("orlk_stream_create", C.byref(self._aux))
+            L.call("orlk_event_create_notiming", C.byref(self._ev_aux_fork))
+            L.call("orlk_event_create_notiming", C.byref(self._ev_aux_join))
+
+        def run():
+            rt = self.rt
+            L.call("orlk_event_record", self._ev_aux_fork, rt.cur)
+            L.call("orlk_stream_wait_event", self._aux, self._ev_aux_fork)
+            main = rt.cur
+            rt.cur = self._aux
+            try:
+                op()
+            finally:
+                rt.cur = main
+        self.flat_ops.append((label, op))
+        self.ops.append((label, run))
+
+    def join_detached(self) -> None:
+        def op():
+            L.call("orlk_event_record", self._ev_aux_join, self._aux)
+            L.call("orlk_stream_wait_event", self.rt.cur, self._ev_aux_join)
+        self.ops.append(("join", op))
+
     @property
     def n_launches(self) -> int:
         return sum(1 for lbl, _ in self.ops if lbl not in ("fork", "join"))

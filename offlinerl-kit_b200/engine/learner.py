@@ -152,12 +152,19 @@ class Learner:
             plan.run_eager()
         self.steps_done += 1
 
+    def emit_loss_readback(self, plan: Plan) -> None:
+        """Copy the loss block to pinned host memory on a detached branch (call once no later launch writes it)."""
+        ld, lh = C.c_void_p(self.loss_dev.data_ptr()), C.c_void_p(self.loss_host.data_ptr())
+        plan.detach("losses_d2h", lambda: L.call("orlk_memcpy_d2h_async", lh, ld, 4 * N_LOSS, self.rt.cur))
+
     def finish_ops(self, plan: Plan, group_mask: int) -> None:
-        rt = self
         gp, cp = C.c_void_p(self.groups_ptr), C.c_void_p(self.philox_counter.data_ptr())
         plan.add("step_end", lambda: L.call("orlk_step_end", gp, group_mask, cp, self.rt.cur))
-        ld, lh = C.c_void_p(self.loss_dev.data_ptr()), C.c_void_p(self.loss_host.data_ptr())
-        plan.add("losses_d2h", lambda: L.call("orlk_memcpy_d2h_async", lh, ld, 4 * N_LOSS, self.rt.cur))
+        if plan.has_detached:
+            plan.join_detached()
+        else:
+            self.emit_loss_readback(plan)
+            plan.join_detached()
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -116,10 +116,15 @@ class TwinCriticLearner(Learner):
                 buf.copy_(torch.as_tensor(noise[k], device=self.dev, dtype=torch.float32).reshape(buf.shape))
 
     # ------------------------------------------------------------------ shared fragments
-    def _emit_noise(self, plan: Plan, n_normal: int, n_uniform: int, lo: float, hi: float) -> None:
+    def _emit_noise(self, plan: Plan, n_normal: int, n_uniform: int, lo: float, hi: float, defer: bool = False):
+        """The step's noise block.  ``defer``: return the launch instead of adding it, so that the caller can put it on
+        a branch parallel to work that does not consume noise."""
         args = (self.noise.data_ptr(), n_normal, n_uniform, lo, hi, int(self.seed), self.philox_counter.data_ptr(),
                 self.noise_enable.data_ptr())
-        plan.add("philox", lambda: L.call("orlk_philox_fill", *args, self.rt.cur))
+        op = ("philox", lambda: L.call("orlk_philox_fill", *args, self.rt.cur))
+        if defer:
+            return op
+        plan.add(*op)
 
     def _emit_sample(self, plan: Plan, tag: str, head: torch.Tensor, head_row_off: int, rep: int, eps: torch.Tensor,
                      M: int, X: Mat, logp: torch.Tensor, obs: Mat) -> None:
@@ -129,12 +134,21 @@ class TwinCriticLearner(Learner):
                 obs.ptr, obs.ld, O, X.ptr, X.ld)
         plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
 
-    def _emit_actor_update(self, plan: Plan, clamp01: bool) -> None:
-        """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)"""
+    def _emit_actor_update(self, plan: Plan, clamp01: bool, beside_forward=None) -> None:
+        """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)
+        ``beside_forward``: a (label, launch) that is independent of the actor forward (the noise fill) and runs on a
+        parallel branch next to it."""
         rt, B, O, A = self.rt, self.B, self.O, self.A
         ar, cr = self.run_actor, self.run_critic_a
         obs = Mat.of(self.obs2).rows_(0, B)
+        if beside_forward is not None:
+            plan.fork()
+            plan.branch(1)
+            plan.add(*beside_forward)
+            plan.branch(0)
         emit_forward(rt, plan, ar, [obs], "A.actor")
+        if beside_forward is not None:
+            plan.join()
         Xa = Mat.of(self.Xa)
         self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
         emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
@@ -221,8 +235,8 @@ class CQLLearner(TwinCriticLearner):
         self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
 
         plan = Plan(rt, "cql")
-        self._emit_noise(plan, self.n_normal, self.n_uniform, self.act_lo, self.act_hi)
-        self._emit_actor_update(plan, clamp01=False)
+        noise = self._emit_noise(plan, self.n_normal, self.n_uniform, self.act_lo, self.act_hi, defer=True)
+        self._emit_actor_update(plan, clamp01=False, beside_forward=noise)
 
         # ---- critic phase with the UPDATED actor (cql.py:108-192)
         obs2 = Mat.of(self.obs2)
@@ -232,12 +246,19 @@ class CQLLearner(TwinCriticLearner):
         head = ab.out[0]
         Xt, Xc = Mat.of(self.Xt), Mat.of(self.Xc)
         v = self.noise_views
+        # the three samplers and the concat write disjoint row blocks of Xt / Xc: four parallel branches
+        plan.fork()
+        plan.branch(1)
         self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
+        plan.branch(2)
         self._emit_sample(plan, "C.sample_pi", head, 0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, obs)
+        plan.branch(3)
         self._emit_sample(plan, "C.sample_pi_next", head, B, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
                           self.lp_pn, obs)
+        plan.branch(0)
         plan.add("C.concat", rt.concat([(Xc.rows_(0, B), obs, 1, Mat.of(self.act)),
                                         (Xc.rows_(B + 2 * R, Mc), obs, self.N, Mat.of(v["rand_act"]))]))
+        plan.join()
         # the target critics on (s', a') and the online critics on the 7936-row batch are independent: two branches
         cr = self.run_critic
         plan.fork()
@@ -253,6 +274,7 @@ class CQLLearner(TwinCriticLearner):
                  int(self.with_lagrange), float(pol._lagrange_threshold), self.scalars.data_ptr(), self.groups_ptr,
                  max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1)
         plan.add("C.loss", lambda: L.call("orlk_cql_critic_loss", *largs, rt.cur))
+        self.emit_loss_readback(plan)       # every loss scalar is final: the copy overlaps the backward pass
         emit_head_dgrad(rt, plan, cr, "C.critic")
         emit_hidden_dgrad(rt, plan, cr, "C.critic")
         emit_wgrad_adam(rt, plan, cr, [Xc, Xc], self.gb_critic, self.groups_ptr, "C.critic", polyak=True)
