@@ -48,6 +48,7 @@ int orlk_device_info(int device, int* out4);
 int orlk_graph_begin(void* stream);
 int orlk_graph_end(void* stream, void** graph_exec_out);
 int orlk_graph_launch(void* graph_exec, void* stream);
+int orlk_graph_launch_sync(void* graph_exec, void* stream); /* launch, then wait for the stream */
 int orlk_graph_destroy(void* graph_exec);
 int orlk_stream_sync(void* stream);
 /* side streams + ordering events: independent launches of a step (e.g. the weight gradients of different layers)
@@ -77,6 +78,13 @@ int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, 
  *   act   [n, act_dim], rew [n], term [n]. */
 int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx,
                        int n, float* obs2, float* act, float* rew, float* term, void* stream);
+
+/* The whole of ReplayBuffer.sample (buffer/buffer.py:97-106) in one host call: waits for slot_event if event_armed
+ * (the previous upload out of this pinned slot), copies idx_host[0..n) into idx_pinned, uploads it to idx_dev,
+ * records slot_event and launches orlk_replay_gather. */
+int orlk_replay_sample(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx_host,
+                       int64_t* idx_pinned, int64_t* idx_dev, void* slot_event, int event_armed, int n, float* obs2,
+                       float* act, float* rew, float* term, void* stream);
 
 /* --------------------------------------------------------------- dense GEMM */
 /* One problem of a grouped fp32 GEMM launch:  C[M,N] = epi( sum_k A(m,k) * B(k,n) ).

@@ -72,7 +72,7 @@ _PROTOS = {
     "orlk_sizeof_gemm_desc": [], "orlk_sizeof_adam_desc": [], "orlk_sizeof_adam_group": [], "orlk_sizeof_concat_seg": [],
     "orlk_device_info": [_I, C.POINTER(C.c_int)],
     "orlk_graph_begin": [_P], "orlk_graph_end": [_P, C.POINTER(C.c_void_p)], "orlk_graph_launch": [_P, _P],
-    "orlk_graph_destroy": [_P], "orlk_stream_sync": [_P],
+    "orlk_graph_destroy": [_P], "orlk_stream_sync": [_P], "orlk_graph_launch_sync": [_P, _P],
     "orlk_stream_create": [C.POINTER(C.c_void_p)], "orlk_stream_destroy": [_P], "orlk_stream_wait_event": [_P, _P],
     "orlk_event_create_notiming": [C.POINTER(C.c_void_p)],
     "orlk_memcpy_h2d_async": [_P, _P, C.c_size_t, _P], "orlk_memcpy_d2h_async": [_P, _P, C.c_size_t, _P],
@@ -81,6 +81,7 @@ _PROTOS = {
     "orlk_event_elapsed_ms": [_P, _P, C.POINTER(C.c_float)], "orlk_event_destroy": [_P],
     "orlk_replay_pack": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _L, _P],
     "orlk_replay_gather": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "orlk_replay_sample": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
     "orlk_gemm_tiny": [_P, _I, _I, _I, _I, _P], "orlk_gemm_tiny_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],

@@ -32,7 +32,12 @@ class _Stage:
         dev = rt.device
         self.idx_host = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(self.N_SLOTS)]
         self.idx_np = [t.numpy() for t in self.idx_host]
-        self.events: List[Optional[C.c_void_p]] = [None] * self.N_SLOTS
+        self.events: List[C.c_void_p] = []
+        for _ in range(self.N_SLOTS):
+            ev = C.c_void_p()
+            L.call("orlk_event_create", C.byref(ev))
+            self.events.append(ev)
+        self.armed = [0] * self.N_SLOTS            # the slot's event has been recorded at least once
         self.slot = 0
         self.idx_dev = torch.zeros(B, dtype=torch.int64, device=dev)
         self.obs2 = torch.zeros(2 * B, O, dtype=torch.float32, device=dev)
@@ -43,6 +48,11 @@ class _Stage:
                            terminals=self.term, rewards=self.rew)
         self.batch.obs2 = self.obs2
         self.batch.indices = self.idx_dev
+        self.batch.token = self                    # identity of the staging memory (engines bind their graphs to it)
+        # constant tail of the orlk_replay_sample argument list
+        self.out_args = (self.obs2.data_ptr(), self.act.data_ptr(), self.rew.data_ptr(), self.term.data_ptr())
+        self.pinned_ptrs = [t.data_ptr() for t in self.idx_host]
+        self.idx_dev_ptr = self.idx_dev.data_ptr()
 
 
 class ReplayBuffer:
@@ -158,6 +168,9 @@ class ReplayBuffer:
                    hi - lo, O, A, self._table.data_ptr(), self.row_width, lo, rt.cur)
             rt.sync()      # the temporaries above are released after this
         self._dirty = []
+        # cached scalars of the per-sample host call
+        self._table_ptr, self._table_rows, self._row_w, self._O = self._table.data_ptr(), cap, self.row_width, O
+        self._sample_fn = L.load().orlk_replay_sample
 
     def _stage(self, batch_size: int) -> _Stage:
         st = self._stages.get(batch_size)
@@ -174,25 +187,20 @@ class ReplayBuffer:
         """Device gather of the given host indices into the staging batch of that size."""
         if self.obs_dtype != np.float32 or self.action_dtype != np.float32:
             raise L.OrlkError("the device mirror stores fp32 rows; obs/action dtype must be float32")
-        rt = self._runtime()
+        rt = self._rt or self._runtime()
         if self._dirty or self._table is None:
             self._sync_mirror()
-        B = int(len(indices))
-        st = self._stage(B)
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        B = idx.shape[0]
+        st = self._stages.get(B) or self._stage(B)
         s = st.slot
         st.slot = (s + 1) % st.N_SLOTS
-        if st.events[s] is None:
-            ev = C.c_void_p()
-            L.call("orlk_event_create", C.byref(ev))
-            st.events[s] = ev
-        else:
-            L.call("orlk_event_sync", st.events[s])      # the pinned slot's previous upload has finished
-        st.idx_np[s][:] = indices
-        L.call("orlk_memcpy_h2d_async", st.idx_dev.data_ptr(), st.idx_host[s].data_ptr(), 8 * B, rt.cur)
-        L.call("orlk_event_record", st.events[s], rt.cur)
-        L.call("orlk_replay_gather", self._table.data_ptr(), len(self.observations), self.row_width, self._obs_dim,
-               self.action_dim, st.idx_dev.data_ptr(), B, st.obs2.data_ptr(), st.act.data_ptr(), st.rew.data_ptr(),
-               st.term.data_ptr(), rt.cur)
+        # one host call: wait for the slot's previous upload, refill the pinned slot, upload, re-arm, gather
+        rc = self._sample_fn(self._table_ptr, self._table_rows, self._row_w, self._O, self.action_dim, idx.ctypes.data,
+                             st.pinned_ptrs[s], st.idx_dev_ptr, st.events[s], st.armed[s], B, *st.out_args, rt.cur)
+        if rc:
+            L.check(rc, "orlk_replay_sample")
+        st.armed[s] = 1
         return st.batch
 
     def gather_device(self, idx_dev: torch.Tensor) -> Batch:

@@ -1,5 +1,6 @@
 // ReplayBuffer device mirror: row table packing and the index gather of ReplayBuffer.sample
 // (reference: buffer/buffer.py:26-30 storage, :96-106 sample).  Pure copies -> bit-exact.
+#include <string.h>
 #include "orlk_common.cuh"
 using namespace orlk;
 
@@ -71,6 +72,27 @@ int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_di
     orlk::launch(k_replay_gather, (n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream, table, n_rows, row_w, obs_dim, act_dim,
                                                                                 idx, n, obs2, act, rew, term);
     return check_launch("k_replay_gather");
+}
+
+// ReplayBuffer.sample in ONE host call (the public-API step is host-latency sensitive: every ctypes round trip shows):
+// wait until the pinned slot's previous upload has finished, copy the freshly drawn indices into it, upload, re-arm
+// the slot's event, gather.
+int orlk_replay_sample(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx_host,
+                       int64_t* idx_pinned, int64_t* idx_dev, void* slot_event, int event_armed, int n, float* obs2,
+                       float* act, float* rew, float* term, void* stream) {
+    ORLK_REQUIRE(n > 0 && n_rows > 0, "sizes");
+    ORLK_REQUIRE(idx_host != nullptr && idx_pinned != nullptr && idx_dev != nullptr && slot_event != nullptr, "index buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (event_armed) {
+        int rc = check(cudaEventSynchronize((cudaEvent_t)slot_event), "cudaEventSynchronize");
+        if (rc) return rc;
+    }
+    memcpy(idx_pinned, idx_host, sizeof(int64_t) * (size_t)n);
+    int rc = check(cudaMemcpyAsync(idx_dev, idx_pinned, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, s), "index upload");
+    if (rc) return rc;
+    rc = check(cudaEventRecord((cudaEvent_t)slot_event, s), "cudaEventRecord");
+    if (rc) return rc;
+    return orlk_replay_gather(table, n_rows, row_w, obs_dim, act_dim, idx_dev, n, obs2, act, rew, term, stream);
 }
 
 }  // extern "C"

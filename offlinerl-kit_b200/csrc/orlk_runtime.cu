@@ -96,6 +96,12 @@ int orlk_graph_launch(void* graph_exec, void* stream) {
     return check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
 }
 
+int orlk_graph_launch_sync(void* graph_exec, void* stream) {
+    int rc = check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
+    if (rc) return rc;
+    return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+
 int orlk_graph_destroy(void* graph_exec) {
     return check(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec), "cudaGraphExecDestroy");
 }

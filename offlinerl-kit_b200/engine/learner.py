@@ -74,6 +74,7 @@ class Learner:
         if self.precision not in PRECISIONS:
             raise L.OrlkError(f"unknown precision {self.precision!r}; choose one of {sorted(PRECISIONS)}")
         self.param_sets: List[ParamSet] = []
+        self._launch_sync = L.load().orlk_graph_launch_sync
 
     # ------------------------------------------------------------------ Adam groups
     def add_group(self, optim: Optional[torch.optim.Optimizer], tau: float = 0.0, **hyper) -> int:
@@ -96,8 +97,9 @@ class Learner:
     def sync_lr(self) -> None:
         """lr schedulers mutate ``optim.param_groups`` between epochs (run_iql.py:132-135): re-read and upload."""
         for g, opt in self._group_optim.items():
-            lr = float(opt.param_groups[0]["lr"])
+            lr = opt.param_groups[0]["lr"]
             if lr != self._group_lr[g]:
+                lr = float(lr)
                 self._group_lr[g] = lr
                 self._lr_host[g] = lr
                 L.call("orlk_memcpy_h2d_async", self.groups_dev.data_ptr() + g * C.sizeof(L.AdamGroup),
@@ -133,15 +135,20 @@ class Learner:
             ps.refresh_wt()
 
     # ------------------------------------------------------------------ plan execution
-    def run(self, key: str) -> np.ndarray:
+    def run(self, key: str) -> List[float]:
+        """Replay the step and wait for it; returns the loss block as Python floats."""
         plan = self.plans[key]
         if self.use_graph:
-            plan.launch()
+            if plan.graph is None:
+                plan.capture()
+            rc = self._launch_sync(plan.graph, self.rt.cur)      # launch + stream sync in one host call
+            if rc:
+                L.check(rc, "orlk_graph_launch_sync")
         else:
             plan.run_eager()
-        self.rt.sync()
+            self.rt.sync()
         self.steps_done += 1
-        return self.loss_np
+        return self.loss_np.tolist()
 
     def enqueue(self, key: str) -> None:
         """Launch a step without waiting for it (used by the device-resident benchmark loop)."""

@@ -69,7 +69,25 @@ class SACPolicy(BasePolicy):
 
     def _after_step(self, out: Dict[str, float]) -> None:
         if self._is_auto_alpha and "alpha" in out:
-            self._alpha = torch.tensor([out["alpha"]], device=self.actor.device)
+            self._alpha_value = out["alpha"]        # the tensor form is rebuilt on demand (see the _alpha property)
+            self._alpha_tensor = None
+
+    # ``_alpha`` is a tensor in the reference (sac.py:43-49); building a device tensor per step costs more host time
+    # than the rest of ``learn``, so the engine keeps the float and the tensor is materialised when somebody reads it.
+    @property
+    def _alpha(self):
+        if self._alpha_tensor is None:
+            self._alpha_tensor = torch.tensor([self._alpha_value], device=self.actor.device)
+        return self._alpha_tensor
+
+    @_alpha.setter
+    def _alpha(self, value) -> None:
+        if torch.is_tensor(value):
+            self._alpha_tensor, self._alpha_value = value, None
+        else:
+            self._alpha_tensor, self._alpha_value = None, float(value)
+            if not self._is_auto_alpha:
+                self._alpha_tensor = value      # a plain float alpha stays a float, as in the reference
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         eng = self.engine(int(batch["observations"].shape[0]))
