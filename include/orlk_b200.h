@@ -137,6 +137,9 @@ int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles,
 
 /* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
  *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.
+ * a_gs == 0 shares one A between all groups (twin critics on the same batch).  A needs 16-byte aligned rows (TMA);
+ * B may have any row pitch when K <= 32 (the obs+act wide first layer: its single B tile is then staged by the
+ * kernel's own warps instead of TMA).
  * passes = 1: single TF32 MMA per product ("fast" mode); passes = 3: hi/lo operand split in shared memory and
  * three MMAs per product (fp32-grade, the parity mode).  Outputs (each optional): row-major C (per k-split slot),
  * transposed CT[n][m], rowsum[m] = sum_k A[g][m][k] (bias gradients; also per k-split slot).  The struct is read

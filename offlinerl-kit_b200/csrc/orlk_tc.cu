@@ -42,6 +42,9 @@ struct TcParams {
     int stages, stage_bytes;   // depth of the TMA ring and bytes per stage (depend on NT and the precision mode)
     const float* gen_row; int64_t gen_row_gs;   // rank-1 operand generator (see OrlkTcGemm), NULL = off
     const float* gen_col; int64_t gen_col_gs;
+    const float* Bm; int64_t ldbm, bm_gs;       // B_MANUAL: B rows are not TMA-able (pitch not a multiple of 16 bytes);
+    int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
+    int a_shared;                               // one A for all groups (a_gs == 0): the A map has a single group plane
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
     unsigned long long* trace; // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
@@ -191,6 +194,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
     const bool want_rowsum = p.rowsum != nullptr && tile_n == 0;
     const bool gen = p.gen_row != nullptr;
+    const bool split_runs = PASSES == 3 || gen || p.b_manual != 0;     // the splitter warps process every stage
 
     const int b_bytes = NT * BK * 4;
     auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
@@ -203,7 +207,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (threadIdx.x == 0) TC_STAMP(0);
     if (threadIdx.x == 32) {                   // descriptor fetch off the critical path (~0.3 us on first use)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (!p.b_manual) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     }
     if (warp == 1 && lane == 0) {
@@ -241,15 +245,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0) {
       if (elect_one()) {
         // ------------------------------------------------------------------ TMA producer
-        const uint32_t tx_bytes = A_BYTES + (uint32_t)NT * BK * 4;
+        const uint32_t tx_bytes = A_BYTES + (p.b_manual ? 0u : (uint32_t)NT * BK * 4);
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(&empty[s]), ph ^ 1);
             mbar_expect_tx(smem_u32(&full[s]), tx_bytes);
             const int k0 = (slab0 + it) * BK;
-            tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, g);
-            tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
+            tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, p.a_shared ? 0 : g);
+            if (!p.b_manual) tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
             if (p.trace_mode == 1 && it < 8) TC_STAMP(8 + it);
         }
       }
@@ -260,13 +264,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
         const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
         if (p.trace != nullptr && p.trace_mode == 2 && nslabs <= STAGES) {   // experiment: issue only once all slabs landed
-            for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32((PASSES == 3 || gen) ? &splitb[it] : &full[it]), 0);
+            for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32(split_runs ? &splitb[it] : &full[it]), 0);
             TC_STAMP(3);
         }
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(smem_u32((PASSES == 3 || gen) ? &splitb[s] : &full[s]), ph);
+            mbar_wait(smem_u32(split_runs ? &splitb[s] : &full[s]), ph);
             tc_fence_after();
             if (it == 0) TC_STAMP(4);
             if (it == nslabs - 1) TC_STAMP(5);
@@ -352,7 +356,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp >= 2) {
         const int t = threadIdx.x - 64;                     // 0..127
-        if (PASSES == 3 || gen) {
+        if (split_runs) {
             // -------------------------------------------------------------- operand splitter (+ rank-1 generator)
             const int nB4 = NT * BK / 4;
             // float4 number t + 128 j of the swizzled A tile sits in row t/8 + 16 j at chunk position t%8, i.e. it holds
@@ -405,7 +409,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                 }
                 if (st4) TC_STAMP(9);
-                for (int i0 = 0; PASSES == 3 && i0 < nB4; i0 += 128 * 8) {
+                if (p.b_manual) {
+                    // B tile by hand (a single k-slab): element (n, k) of the K-major SWIZZLE_128B tile lives at
+                    // n * 128 bytes + 16 * ((k / 4) ^ (n & 7)) + 4 * (k % 4); k >= K and n >= N are zeros
+                    const float* Bg = p.Bm + (int64_t)g * p.bm_gs + (int64_t)n0 * p.ldbm;
+                    float* brf = reinterpret_cast<float*>(br);
+                    float* blf = reinterpret_cast<float*>(bl);
+                    for (int idx = t; idx < NT * BK; idx += 128) {
+                        const int n = idx >> 5, k = idx & 31;
+                        const float v = (k < p.K && n0 + n < p.N) ? __ldg(Bg + (int64_t)n * p.ldbm + k) : 0.f;
+                        const int off = n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+                        brf[off] = v;
+                        if (PASSES == 3) blf[off] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                    }
+                }
+                for (int i0 = 0; PASSES == 3 && !p.b_manual && i0 < nB4; i0 += 128 * 8) {
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -620,8 +638,10 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE(q->M > 0 && q->K > 0 && q->G > 0, "sizes");
     ORLK_REQUIRE(q->N >= 16 && q->N <= BN_MAX && q->N % 16 == 0, "N must be a multiple of 16 in [16,256]");
     ORLK_REQUIRE(q->passes == 1 || q->passes == 3, "passes must be 1 or 3");
-    ORLK_REQUIRE(q->lda % 4 == 0 && q->ldb % 4 == 0 && q->a_gs % 4 == 0 && q->b_gs % 4 == 0, "operand strides must be multiples of 4 floats");
-    ORLK_REQUIRE(aligned16(q->A) && aligned16(q->B), "operands must be 16-byte aligned");
+    ORLK_REQUIRE(q->lda % 4 == 0 && q->a_gs % 4 == 0 && aligned16(q->A), "A must be 16-byte aligned with strides that are multiples of 4 floats");
+    // B rows that TMA cannot address (the K = obs+act wide first-layer weights, pitch 23 floats) are staged by hand
+    const bool b_manual = q->ldb % 4 != 0 || q->b_gs % 4 != 0 || !aligned16(q->B);
+    ORLK_REQUIRE(!b_manual || q->K <= BK, "B must be 16-byte aligned with strides that are multiples of 4 floats unless K <= 32");
     ORLK_REQUIRE(q->epi == ORLK_EPI_NONE || q->epi == ORLK_EPI_RELU || q->epi == ORLK_EPI_RELU_MASK, "epilogue");
     ORLK_REQUIRE(q->epi != ORLK_EPI_RELU_MASK || q->aux != nullptr, "mask epilogue needs aux");
     const int total_slabs = (q->K + BK - 1) / BK;
@@ -632,12 +652,16 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE(splits == (q->k_splits < 1 ? 1 : q->k_splits), "k_splits must divide the slab count evenly enough (use orlk_tc_effective_splits)");
 
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, q->G, BM);
+    const bool a_shared = q->a_gs == 0 && q->G > 1;
+    int rc = make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G, BM);
     if (rc) return rc;
     const int NT = (q->n_tile > 0) ? q->n_tile : q->N;
     ORLK_REQUIRE(NT >= 16 && NT <= BN_MAX && NT % 16 == 0 && q->N % NT == 0, "n_tile must be a multiple of 16 that divides N");
-    rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
-    if (rc) return rc;
+    if (b_manual) memset(&tmB, 0, sizeof(tmB));
+    else {
+        rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
+        if (rc) return rc;
+    }
 
     TcParams p;
     p.C = q->C; p.ldc = q->ldc; p.c_gs = q->c_gs; p.c_split_stride = q->c_split_stride;
@@ -651,6 +675,7 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE((q->gen_row == nullptr) == (q->gen_col == nullptr), "gen_row and gen_col go together");
     ORLK_REQUIRE(q->gen_row == nullptr || (q->K % 4 == 0 && aligned16(q->gen_col) && q->gen_col_gs % 4 == 0),
                  "the operand generator needs K % 4 == 0 and 16-byte aligned column factors");
+    p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0;
     p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;
     p.trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }

@@ -273,7 +273,19 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
                 CT=_grouped(run.HT[l], N, M, run.Mt) if run.HT[l] is not None else None, ct_gs=N * run.Mt,
                 bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
             continue
-        if l == 0 and run.narrow0 and M >= NARROW_MIN_ROWS and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
+        same_x = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
+        if (l == 0 and run.tc and run.narrow0 and M >= TC_MIN_ROWS and same_x and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0
+                and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and os.environ.get("ORLK_TC_FWD0", "1") != "0"):
+            # obs+act wide first layer on the tensor cores: one zero-padded k-slab, the kernel is all epilogue
+            K, N = lay.in_dim, lay.out_dim
+            plan.add(f"{tag}.fwd0.tc", rt.tc_gemm(
+                A=Mat(X[0].ptr, M, K, X[0].ld), a_gs=0, B=Mat(ps.w(0, 0, run.store), N, K, K), b_gs=lay.w_gs, G=G,
+                passes=3,       # raw observations: always fp32-grade (a single k-slab, the extra MMAs are free)
+                epi=L.EPI_RELU, C=_grouped(run.H[0], M, N, N), c_gs=M * N,
+                CT=_grouped(run.HT[0], N, M, run.Mt) if run.HT[0] is not None else None, ct_gs=N * run.Mt,
+                bias=ps.b(0, 0, run.store), bias_gs=lay.b_gs))
+            continue
+        if l == 0 and run.narrow0 and M >= NARROW_MIN_ROWS and same_x:
             ht = run.HT[0]
             args = (X[0].ptr, X[0].ld, 0, ps.w(0, 0, run.store), lay.in_dim, lay.w_gs, ps.b(0, 0, run.store), lay.b_gs,
                     run.H[0].data_ptr(), lay.out_dim, M * lay.out_dim, ht.data_ptr() if ht is not None else None, run.Mt,

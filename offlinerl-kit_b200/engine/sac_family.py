@@ -235,7 +235,7 @@ class CQLLearner(TwinCriticLearner):
         self.run_target = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=False, store="T")
         self.run_critic = self.mlp_run(self.critic_ps, Mc, self.nh_c, need_grad=True)
         self.Xt = rt.zeros(B, O + A)
-        self.Xc = rt.zeros(Mc, O + A)
+        self.Xc = rt.zeros(Mc, (O + A + 3) // 4 * 4)[:, :O + A]      # 16-byte aligned rows: a TMA operand of the first layer
         self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(B), rt.zeros(R), rt.zeros(R)
         self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
         self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
