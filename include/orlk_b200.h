@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 9
+#define ORLK_ABI_VERSION 10
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -166,6 +166,10 @@ typedef struct OrlkTcGemm {
      * global memory (autograd of modules/critic_module.py:25-33's last Linear).  Requires K % 4 == 0. */
     const float* gen_row; int64_t gen_row_gs;
     const float* gen_col; int64_t gen_col_gs;
+    /* MN-major operands: a_mn != 0 means A is stored [g][k][m] (m contiguous, lda = pitch of a k row) instead of
+     * [g][m][k]; likewise b_mn for B as [g][k][n].  This is how the weight gradient dW[o][i] = sum_m dZ[m][o] H[m][i]
+     * reads the row-major activations / gradients directly (no transposed copies).  b_mn needs n_tile % 32 == 0. */
+    int32_t a_mn, b_mn;
 } OrlkTcGemm;
 int orlk_tc_init(void);
 int orlk_tc_gemm(const OrlkTcGemm* params_host, void* stream);

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -55,7 +55,8 @@ class TcGemm(C.Structure):
                 ("rowsum", C.c_void_p), ("rowsum_gs", C.c_int64), ("rowsum_split_stride", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("G", C.c_int32),
                 ("epi", C.c_int32), ("k_splits", C.c_int32), ("passes", C.c_int32), ("n_tile", C.c_int32),
-                ("gen_row", C.c_void_p), ("gen_row_gs", C.c_int64), ("gen_col", C.c_void_p), ("gen_col_gs", C.c_int64)]
+                ("gen_row", C.c_void_p), ("gen_row_gs", C.c_int64), ("gen_col", C.c_void_p), ("gen_col_gs", C.c_int64),
+                ("a_mn", C.c_int32), ("b_mn", C.c_int32)]
 
 
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)

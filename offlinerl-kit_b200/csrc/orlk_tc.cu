@@ -45,6 +45,7 @@ struct TcParams {
     const float* Bm; int64_t ldbm, bm_gs;       // B_MANUAL: B rows are not TMA-able (pitch not a multiple of 16 bytes);
     int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
     int a_shared;                               // one A for all groups (a_gs == 0): the A map has a single group plane
+    int a_mn, b_mn;            // operand stored [k][m] / [k][n] (MN-major) instead of [m][k] / [n][k]
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
     unsigned long long* trace; // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
@@ -114,6 +115,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+// MN-major TF32 operands: the only shared-memory layout the tensor core accepts is SWIZZLE_128B with 32-byte atoms
+// (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout";
+// cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 4 k-rows of 128 bytes).  A tile is stored [k][32 mn-elements]:
+// 128-byte rows along M or N, the 32-byte chunk c of row r at chunk position c ^ (r & 3)  (what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), one 4 KB block per 32 mn-elements.  Canonical form in 16-byte units:
+// ((8,n),(4,k)) : ((1,LBO),(8,SBO))  ->  LBO = bytes between mn blocks (4096), SBO = bytes between 4-row k groups (512).
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
 __device__ __forceinline__ uint32_t instr_desc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -252,16 +263,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_wait(smem_u32(&empty[s]), ph ^ 1);
             mbar_expect_tx(smem_u32(&full[s]), tx_bytes);
             const int k0 = (slab0 + it) * BK;
-            tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, p.a_shared ? 0 : g);
-            if (!p.b_manual) tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
+            if (p.a_mn) {       // MN-major: one 32 (m) x 32 (k) box per 4 KB block
+#pragma unroll
+                for (int b = 0; b < BM / 32; ++b)
+                    tma_load_3d(smem_u32(a_raw(s)) + b * 4096, &tmA, smem_u32(&full[s]), tile_m * BM + 32 * b, k0, p.a_shared ? 0 : g);
+            } else tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, p.a_shared ? 0 : g);
+            if (p.b_mn) {
+                for (int b = 0; b < NT / 32; ++b)
+                    tma_load_3d(smem_u32(b_raw(s)) + b * 4096, &tmB, smem_u32(&full[s]), n0 + 32 * b, k0, g);
+            } else if (!p.b_manual) tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
             if (p.trace_mode == 1 && it < 8) TC_STAMP(8 + it);
         }
       }
     } else if (warp == 1) {
       if (elect_one()) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        const uint32_t idesc = instr_desc_tf32(BM, NT);
-        const uint32_t idesc_rs = instr_desc_tf32(BM, 16);
+        const uint32_t majors = (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);     // a_major / b_major bits
+        const uint32_t idesc = instr_desc_tf32(BM, NT) | majors;
+        const uint32_t idesc_rs = instr_desc_tf32(BM, 16) | (p.a_mn ? (1u << 15) : 0u);       // the ones tile is K-major
+        // start-address step per UMMA_K = 8: 32 bytes along a K-major row, one 1024-byte k group of an MN-major tile
+        const uint64_t a_kstep = p.a_mn ? 64u : 2u, b_kstep = p.b_mn ? 64u : 2u;
         const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
         if (p.trace != nullptr && p.trace_mode == 2 && nslabs <= STAGES) {   // experiment: issue only once all slabs landed
             for (int it = 0; it < nslabs; ++it) mbar_wait(smem_u32(split_runs ? &splitb[it] : &full[it]), 0);
@@ -275,27 +296,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (it == 0) TC_STAMP(4);
             if (it == nslabs - 1) TC_STAMP(5);
             if (PASSES == 1 && p.trace_mode == 0 && it < 8) TC_STAMP(8 + it);
-            if (p.trace_mode == 3 && it == 1) TC_STAMP(8);
-            const uint32_t x1 = (p.trace_mode == 3 && NT <= 128) ? NT : 0, x2 = 2 * x1;   // experiment: 3 accumulators
-            const uint64_t ad = smem_desc_sw128(smem_u32(a_raw(s))), bd = smem_desc_sw128(smem_u32(b_raw(s)));
-            const uint64_t adl = smem_desc_sw128(smem_u32(a_lo(s))), bdl = smem_desc_sw128(smem_u32(b_lo(s)));
+            const uint64_t ad = p.a_mn ? smem_desc_sw128_mn(smem_u32(a_raw(s))) : smem_desc_sw128(smem_u32(a_raw(s)));
+            const uint64_t bd = p.b_mn ? smem_desc_sw128_mn(smem_u32(b_raw(s))) : smem_desc_sw128(smem_u32(b_raw(s)));
+            const uint64_t adl = p.a_mn ? smem_desc_sw128_mn(smem_u32(a_lo(s))) : smem_desc_sw128(smem_u32(a_lo(s)));
+            const uint64_t bdl = p.b_mn ? smem_desc_sw128_mn(smem_u32(b_lo(s))) : smem_desc_sw128(smem_u32(b_lo(s)));
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {              // UMMA_K = 8 for tf32: 32 bytes along K per instruction
+            for (int k = 0; k < BK / 8; ++k) {              // UMMA_K = 8 for tf32
                 const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-                const uint64_t koff = (uint64_t)(k * 2);    // +32 bytes in the 16-byte-unit start-address field
-                umma_tf32(tmem_base, ad + koff, bd + koff, idesc, acc);
+                const uint64_t ka = (uint64_t)k * a_kstep, kb = (uint64_t)k * b_kstep;
+                umma_tf32(tmem_base, ad + ka, bd + kb, idesc, acc);
                 if (PASSES == 3) {
-                    umma_tf32(tmem_base + x1, adl + koff, bd + koff, idesc, x1 ? acc : 1u);
-                    umma_tf32(tmem_base + x2, ad + koff, bdl + koff, idesc, x1 ? acc : 1u);
+                    umma_tf32(tmem_base, adl + ka, bd + kb, idesc, 1u);
+                    umma_tf32(tmem_base, ad + ka, bdl + kb, idesc, 1u);
                 }
                 if (want_rowsum) {
-                    umma_tf32(tmem_base + ROWSUM_COL, ad + koff, ones_desc, idesc_rs, acc);
-                    if (PASSES == 3) umma_tf32(tmem_base + ROWSUM_COL, adl + koff, ones_desc, idesc_rs, 1u);
+                    umma_tf32(tmem_base + ROWSUM_COL, ad + ka, ones_desc, idesc_rs, acc);
+                    if (PASSES == 3) umma_tf32(tmem_base + ROWSUM_COL, adl + ka, ones_desc, idesc_rs, 1u);
                 }
             }
-            if (p.trace_mode == 3 && it == 1) TC_STAMP(9);
             umma_commit(smem_u32(&empty[s]));               // frees the stage when these MMAs have completed
-            if (p.trace_mode == 3 && it == 1) TC_STAMP(10);
         }
         umma_commit(smem_u32(accum));
       }
@@ -362,16 +381,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             // float4 number t + 128 j of the swizzled A tile sits in row t/8 + 16 j at chunk position t%8, i.e. it holds
             // k = 4c .. 4c+3 of that row with c = (t%8) ^ ((t/8) & 7) - the same c for all eight j.  So the generator
             // needs eight row factors (fixed for the whole CTA) and one float4 of column factors per k-slab.
+            // MN-major A ([k][32 m] blocks of 256 float4): float4 t + 128 j is block j/2, k-row t/8 + 16 (j%2), m-chunk c.
+            // There the ROW factors (per m) are four float4s fixed for the CTA and the column factors are two scalars
+            // (k rows t/8 and t/8 + 16) per slab.
             float grow[8];
-            const int gc = (t & 7) ^ ((t >> 3) & 7);
+            float4 growv[4];
+            const int gc = p.a_mn ? 2 * (((t & 7) >> 1) ^ ((t >> 3) & 3)) + (t & 1)       // 32-byte atoms, rows mod 4
+                                  : (t & 7) ^ ((t >> 3) & 7);
             const float* gcol = nullptr;
-            if (gen) {
+            if (gen && !p.a_mn) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int m = tile_m * BM + (t >> 3) + 16 * j;
                     grow[j] = m < p.M ? __ldg(p.gen_row + (int64_t)g * p.gen_row_gs + m) : 0.f;
                 }
                 gcol = p.gen_col + (int64_t)g * p.gen_col_gs + 4 * gc;
+            }
+            if (gen && p.a_mn) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int m = tile_m * BM + 32 * b + 4 * gc;
+                    const float* gr = p.gen_row + (int64_t)g * p.gen_row_gs + m;
+                    growv[b] = make_float4(m < p.M ? __ldg(gr) : 0.f, m + 1 < p.M ? __ldg(gr + 1) : 0.f,
+                                           m + 2 < p.M ? __ldg(gr + 2) : 0.f, m + 3 < p.M ? __ldg(gr + 3) : 0.f);
+                }
+                gcol = p.gen_col + (int64_t)g * p.gen_col_gs;
             }
             for (int it = 0; it < nslabs; ++it) {
                 const int s = it % STAGES;
@@ -390,7 +424,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = ar[t + 128 * j];
-                    if (gen) {
+                    if (gen && p.a_mn) {
+                        const int k = (slab0 + it) * BK + (t >> 3);
+                        const float c0 = k < p.K ? __ldg(gcol + k) : 0.f, c1 = k + 16 < p.K ? __ldg(gcol + k + 16) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float cf = (j & 1) ? c1 : c0;
+                            const float4 rv = growv[j >> 1];
+                            v[j].x = v[j].x > 0.f ? rv.x * cf : 0.f;
+                            v[j].y = v[j].y > 0.f ? rv.y * cf : 0.f;
+                            v[j].z = v[j].z > 0.f ? rv.z * cf : 0.f;
+                            v[j].w = v[j].w > 0.f ? rv.w * cf : 0.f;
+                            ar[t + 128 * j] = v[j];
+                        }
+                    } else if (gen) {
                         const int k = (slab0 + it) * BK + 4 * gc;
                         const float4 cv = k < p.K ? __ldg(reinterpret_cast<const float4*>(gcol + (int64_t)(slab0 + it) * BK))
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -410,17 +457,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 if (st4) TC_STAMP(9);
                 if (p.b_manual) {
-                    // B tile by hand (a single k-slab): element (n, k) of the K-major SWIZZLE_128B tile lives at
-                    // n * 128 bytes + 16 * ((k / 4) ^ (n & 7)) + 4 * (k % 4); k >= K and n >= N are zeros
+                    // B tile by hand (a single k-slab): 16-byte chunk c (k = 4c .. 4c+3) of row n of the K-major
+                    // SWIZZLE_128B tile lives at n * 128 bytes + 16 * (c ^ (n & 7)); k >= K and n >= N are zeros
                     const float* Bg = p.Bm + (int64_t)g * p.bm_gs + (int64_t)n0 * p.ldbm;
-                    float* brf = reinterpret_cast<float*>(br);
-                    float* blf = reinterpret_cast<float*>(bl);
-                    for (int idx = t; idx < NT * BK; idx += 128) {
-                        const int n = idx >> 5, k = idx & 31;
-                        const float v = (k < p.K && n0 + n < p.N) ? __ldg(Bg + (int64_t)n * p.ldbm + k) : 0.f;
-                        const int off = n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
-                        brf[off] = v;
-                        if (PASSES == 3) blf[off] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                    for (int n = t; n < NT; n += 128) {
+                        const float* row = Bg + (int64_t)n * p.ldbm;
+                        const bool n_ok = n0 + n < p.N;
+#pragma unroll
+                        for (int c = 0; c < BK / 4; ++c) {
+                            float4 v;
+                            v.x = (n_ok && 4 * c + 0 < p.K) ? __ldg(row + 4 * c + 0) : 0.f;
+                            v.y = (n_ok && 4 * c + 1 < p.K) ? __ldg(row + 4 * c + 1) : 0.f;
+                            v.z = (n_ok && 4 * c + 2 < p.K) ? __ldg(row + 4 * c + 2) : 0.f;
+                            v.w = (n_ok && 4 * c + 3 < p.K) ? __ldg(row + 4 * c + 3) : 0.f;
+                            br[n * 8 + (c ^ (n & 7))] = v;
+                            if (PASSES == 3) bl[n * 8 + (c ^ (n & 7))] = lo_tf32(v);
+                        }
                     }
                 }
                 for (int i0 = 0; PASSES == 3 && !p.b_manual && i0 < nB4; i0 += 128 * 8) {
@@ -585,6 +637,30 @@ int make_map(CUtensorMap* map, const float* base, int64_t ld, int64_t gs, int ro
     return 0;
 }
 
+// 3-D tensor map over an MN-major operand [G][K][MN] fp32 (mn contiguous), box = 32 (mn) x 32 (k) x 1, 128-byte swizzle
+// with 32-byte atoms.
+int make_map_mn(CUtensorMap* map, const float* base, int64_t ld, int64_t gs, int MN, int K, int G) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ORLK_ERR_UNSUPPORTED;
+    }
+    if (gs <= 0) gs = (int64_t)K * ld;
+    cuuint64_t dims[3] = {(cuuint64_t)MN, (cuuint64_t)K, (cuuint64_t)G};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)gs * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)BK, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (MN-major) failed with CUresult %d (ld=%lld gs=%lld MN=%d K=%d G=%d)", (int)r,
+                  (long long)ld, (long long)gs, MN, K, G);
+        return ORLK_ERR_BAD_ARG;
+    }
+    return 0;
+}
+
 // 4-D tensor map over the row-major output [splits][G][M][N] (n contiguous), box = 32 (n) x 32 (m), 128-byte swizzle.
 int make_map_c(CUtensorMap* map, float* base, int64_t ldc, int64_t gs, int64_t ss, int M, int N, int G, int S) {
     EncodeTiledFn enc = get_encode();
@@ -653,13 +729,16 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
 
     CUtensorMap tmA, tmB;
     const bool a_shared = q->a_gs == 0 && q->G > 1;
-    int rc = make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G, BM);
+    int rc = q->a_mn ? make_map_mn(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G)
+                     : make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G, BM);
     if (rc) return rc;
     const int NT = (q->n_tile > 0) ? q->n_tile : q->N;
     ORLK_REQUIRE(NT >= 16 && NT <= BN_MAX && NT % 16 == 0 && q->N % NT == 0, "n_tile must be a multiple of 16 that divides N");
+    ORLK_REQUIRE(!q->b_mn || (NT % 32 == 0 && !b_manual), "an MN-major B needs 32-column n-tiles and 16-byte aligned rows");
     if (b_manual) memset(&tmB, 0, sizeof(tmB));
     else {
-        rc = make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
+        rc = q->b_mn ? make_map_mn(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G)
+                     : make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
         if (rc) return rc;
     }
 
@@ -675,6 +754,7 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE((q->gen_row == nullptr) == (q->gen_col == nullptr), "gen_row and gen_col go together");
     ORLK_REQUIRE(q->gen_row == nullptr || (q->K % 4 == 0 && aligned16(q->gen_col) && q->gen_col_gs % 4 == 0),
                  "the operand generator needs K % 4 == 0 and 16-byte aligned column factors");
+    p.a_mn = q->a_mn ? 1 : 0; p.b_mn = q->b_mn ? 1 : 0;
     p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0;
     p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;
     p.trace = orlk::trace_buffer();

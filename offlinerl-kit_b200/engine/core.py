@@ -165,8 +165,10 @@ class Runtime:
                 C: Optional[Mat] = None, c_gs: int = 0, c_split_stride: int = 0, CT: Optional[Mat] = None, ct_gs: int = 0,
                 bias: int = 0, bias_gs: int = 0, aux: Optional[Mat] = None, aux_gs: int = 0, rowsum: int = 0,
                 rowsum_gs: int = 0, rowsum_split_stride: int = 0, k_splits: int = 1, n_tile: int = 0,
-                gen_row: int = 0, gen_row_gs: int = 0, gen_col: int = 0, gen_col_gs: int = 0) -> Callable[[], None]:
-        """tcgen05 GEMM launch: C[g] = epi(A[g] (M x K) . B[g]^T (N x K)); group strides in floats."""
+                gen_row: int = 0, gen_row_gs: int = 0, gen_col: int = 0, gen_col_gs: int = 0,
+                a_mn: bool = False, b_mn: bool = False) -> Callable[[], None]:
+        """tcgen05 GEMM launch: C[g] = epi(A[g] (M x K) . B[g]^T (N x K)); group strides in floats.
+        ``a_mn`` / ``b_mn``: the Mat describes the operand as STORED, [K rows][M or N columns]."""
         q = L.TcGemm()
         q.A, q.lda, q.a_gs = A.ptr, A.ld, a_gs
         q.B, q.ldb, q.b_gs = B.ptr, B.ld, b_gs
@@ -178,11 +180,14 @@ class Runtime:
         if aux is not None:
             q.aux, q.ldaux, q.aux_gs = aux.ptr, aux.ld, aux_gs
         q.rowsum, q.rowsum_gs, q.rowsum_split_stride = rowsum or None, rowsum_gs, rowsum_split_stride
-        q.M, q.N, q.K, q.G = A.rows, B.rows, A.cols, G
-        assert A.cols == B.cols
+        q.a_mn, q.b_mn = int(a_mn), int(b_mn)
+        Ma, Ka = (A.cols, A.rows) if a_mn else (A.rows, A.cols)
+        Nb, Kb = (B.cols, B.rows) if b_mn else (B.rows, B.cols)
+        assert Ka == Kb, (Ka, Kb)
+        q.M, q.N, q.K, q.G = Ma, Nb, Ka, G
         q.epi, q.passes, q.n_tile = epi, passes, n_tile
         q.gen_row, q.gen_row_gs, q.gen_col, q.gen_col_gs = gen_row or None, gen_row_gs, gen_col or None, gen_col_gs
-        q.k_splits = self.lib.orlk_tc_effective_splits(A.cols, k_splits)
+        q.k_splits = self.lib.orlk_tc_effective_splits(Ka, k_splits)
         qp = _ctypes_pointer(q)      # the struct is read on the host at every launch: keep it alive in the closure
         return lambda: L.call("orlk_tc_gemm", qp, self.cur)
 

@@ -203,10 +203,15 @@ class MlpRun:
         self.tc_fwd = [bool(self.tc) and l >= 1 and tc_ok_fwd(lays[l], M) for l in range(n_hidden)]
         self.tc_dgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_dgrad(lays[l], M) for l in range(n_hidden)]
         self.tc_wgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_wgrad(lays[l], M) for l in range(n_hidden)]
+        # The tensor-core weight gradient dW[o][i] = sum_m dZ[m][o] H[m][i] reads the ROW-MAJOR gradients / activations
+        # as MN-major operands (orlk_tc_gemm a_mn / b_mn); only layers whose input width is not a multiple of 32 still
+        # need the transposed copies HT / dZT written by the producing kernels' epilogues.
+        self.wgrad_mn = [self.tc_wgrad[l] and lays[l].in_dim % 32 == 0 and lays[l].out_dim % 4 == 0
+                         and os.environ.get("ORLK_WGRAD_MN", "1") != "0" for l in range(n_hidden)]
         self.HT = [None] * n_hidden
         self.dZT = [None] * n_hidden
         for l in range(n_hidden):
-            if self.tc_wgrad[l]:
+            if self.tc_wgrad[l] and not self.wgrad_mn[l]:
                 self.dZT[l] = rt.zeros(G, lays[l].out_dim, self.Mt)
                 self.HT[l - 1] = rt.zeros(G, lays[l - 1].out_dim, self.Mt)
         # Scalar head over a tensor-core last hidden layer: dZ[last] = dOut (x) w_head * relu'(H[last]) is rank-1 times a
@@ -219,7 +224,8 @@ class MlpRun:
                               and lays[n_hidden].w_off % 4 == 0 and lays[n_hidden].w_gs % 4 == 0
                               and os.environ.get("ORLK_FUSE_HEAD_BWD", "1") != "0")
         if self.fuse_head_bwd:
-            self.HT[last] = rt.zeros(G, lays[last].out_dim, self.Mt)
+            if not self.wgrad_mn[last]:
+                self.HT[last] = rt.zeros(G, lays[last].out_dim, self.Mt)
             self.dZT[last] = None           # never materialised
         if any(self.tc_dgrad):
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
@@ -434,14 +440,20 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
         if cfg == -1:
             # dW[o,i] = sum_m dZ^T[o,m] * H^T[i,m]; bias gradient = row sums of dZ^T (a ones-tile MMA)
             gen = {}
-            a_src = run.dZT[l]
-            if run.fuse_head_bwd and l == run.nh - 1:
+            fused = run.fuse_head_bwd and l == run.nh - 1
+            if fused:       # dZ^T[o][m] = w_head[o] * dOut[m] * (H[m][o] > 0), built inside the kernel
                 head = ps.layers[run.nh]
-                a_src = run.HT[l]           # dZ^T[o][m] = w_head[o] * dOut[m] * (H^T[o][m] > 0)
                 gen = dict(gen_row=ps.w(run.nh, 0), gen_row_gs=head.w_gs, gen_col=run.dOut.data_ptr(), gen_col_gs=M)
+            if run.wgrad_mn[l]:
+                a_src = run.H[l] if fused else run.dZ[l]
+                operands = dict(A=_grouped(a_src, M, lay.out_dim, lay.out_dim), a_gs=M * lay.out_dim, a_mn=True,
+                                B=_grouped(run.H[l - 1], M, lay.in_dim, lay.in_dim), b_gs=M * lay.in_dim, b_mn=True)
+            else:
+                a_src = run.HT[l] if fused else run.dZT[l]
+                operands = dict(A=_grouped(a_src, lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt,
+                                B=_grouped(run.HT[l - 1], lay.in_dim, M, run.Mt), b_gs=lay.in_dim * run.Mt)
             launches.append((f"{tag}.wgrad{l}.tc", rt.tc_gemm(
-                A=_grouped(a_src, lay.out_dim, M, run.Mt), a_gs=lay.out_dim * run.Mt, **gen,
-                B=_grouped(run.HT[l - 1], lay.in_dim, M, run.Mt), b_gs=lay.in_dim * run.Mt, G=G, passes=run.tc,
+                **operands, **gen, G=G, passes=run.tc,
                 C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
                 rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s)))
             continue

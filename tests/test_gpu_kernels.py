@@ -438,7 +438,9 @@ def test_replay_gather_bit_exact_and_ring(rt):
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
-def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed, n_tile=0):
+def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed, n_tile=0, a_mn=False, b_mn=False,
+             gen_mode=False):
+    """gen_mode: the kernel multiplies A' = row[m] * col[k] * (A > 0) instead of A (the fused scalar-head backward)."""
     from offlinerlkit_b200 import _lib as L
     from offlinerlkit_b200.engine.core import Mat
     gen = torch.Generator().manual_seed(seed)
@@ -446,12 +448,23 @@ def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsu
     B = torch.randn(G, N, K, generator=gen) / math.sqrt(K)
     bias = torch.randn(G, N, generator=gen)
     aux = torch.randn(G, M, N, generator=gen)
+    grow, gcol = torch.randn(G, M, generator=gen), torch.randn(G, K, generator=gen)
     Ad, Bd, bd, auxd = A.to(DEV), B.to(DEV), bias.to(DEV), aux.to(DEV)
+    growd, gcold = grow.to(DEV), gcol.to(DEV)
+    if a_mn:
+        Ad = Ad.transpose(1, 2).contiguous()        # stored [G][K][M]
+    if b_mn:
+        Bd = Bd.transpose(1, 2).contiguous()        # stored [G][K][N]
+    Amat = Mat(Ad.data_ptr(), K, M, M) if a_mn else Mat(Ad.data_ptr(), M, K, K)
+    Bmat = Mat(Bd.data_ptr(), K, N, N) if b_mn else Mat(Bd.data_ptr(), N, K, K)
+    gkw = dict(gen_row=growd.data_ptr(), gen_row_gs=M, gen_col=gcold.data_ptr(), gen_col_gs=K) if gen_mode else {}
+    if gen_mode:
+        A = grow[:, :, None] * gcol[:, None, :] * (A > 0)
     s_eff = rt.lib.orlk_tc_effective_splits(K, splits)
     Cd = torch.full((s_eff, G, M, N), float("nan"), device=DEV)
     CTd = torch.full((G, N, M), float("nan"), device=DEV)
     rs = torch.full((s_eff, G, M), float("nan"), device=DEV)
-    op = rt.tc_gemm(A=Mat(Ad.data_ptr(), M, K, K), a_gs=M * K, B=Mat(Bd.data_ptr(), N, K, K), b_gs=N * K, G=G,
+    op = rt.tc_gemm(A=Amat, a_gs=M * K, B=Bmat, b_gs=N * K, G=G, a_mn=a_mn, b_mn=b_mn, **gkw,
                     passes=passes, epi=epi, C=Mat(Cd.data_ptr(), M, N, N), c_gs=M * N, c_split_stride=G * M * N,
                     CT=Mat(CTd.data_ptr(), N, M, M) if want_ct else None, ct_gs=N * M,
                     bias=bd.data_ptr() if with_bias else 0, bias_gs=N,
@@ -499,7 +512,41 @@ def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
     errs.append(_tc_case(rt, 2, 256, 256, 256, passes, L.EPI_RELU, 1, True, True, False, 8, n_tile=32))
     errs.append(_tc_case(rt, 2, 512, 256, 256, passes, L.EPI_RELU_MASK, 1, False, True, False, 9, n_tile=32))
     errs.append(_tc_case(rt, 1, 200, 192, 64, passes, L.EPI_NONE, 1, True, False, True, 10, n_tile=64))
+    # MN-major operands (the weight gradient reads row-major activations / gradients as they are)
+    errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 11, a_mn=True, b_mn=True))
+    errs.append(_tc_case(rt, 1, 200, 96, 300, passes, L.EPI_NONE, 1, False, False, True, 12, a_mn=True, b_mn=True, n_tile=32))
+    errs.append(_tc_case(rt, 2, 300, 256, 256, passes, L.EPI_RELU, 1, True, False, False, 13, a_mn=True))
+    errs.append(_tc_case(rt, 2, 300, 256, 256, passes, L.EPI_NONE, 1, False, False, False, 14, b_mn=True))
+    # rank-1 operand generator (scalar-head backward folded into dgrad / wgrad), both operand orders
+    errs.append(_tc_case(rt, 2, 7936, 256, 256, passes, L.EPI_RELU_MASK, 1, False, True, False, 15, gen_mode=True))
+    errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 16, gen_mode=True))
+    errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 17, gen_mode=True, a_mn=True,
+                         b_mn=True))
+    # first-layer shape: K = 23 with unaligned weight rows (staged by the kernel's own warps), A shared by the groups
+    errs.append(_tc_first_layer_case(rt, passes))
     print(f"passes={passes}: relative errors {['%.2e' % e for e in errs]}")
+
+
+def _tc_first_layer_case(rt, passes):
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import Mat
+    gen = torch.Generator().manual_seed(77)
+    G, M, N, K = 2, 1000, 256, 23
+    X = torch.randn(M, K, generator=gen)
+    W = torch.randn(G, N, K, generator=gen) / math.sqrt(K)
+    b = torch.randn(G, N, generator=gen)
+    Xd = torch.zeros(M, 24, device=DEV)
+    Xd[:, :K] = X.to(DEV)
+    Wd, bd = W.to(DEV), b.to(DEV)
+    Cd = torch.full((G, M, N), float("nan"), device=DEV)
+    rt.tc_gemm(A=Mat(Xd.data_ptr(), M, K, 24), a_gs=0, B=Mat(Wd.data_ptr(), N, K, K), b_gs=N * K, G=G, passes=passes,
+               epi=L.EPI_RELU, C=Mat(Cd.data_ptr(), M, N, N), c_gs=M * N, bias=bd.data_ptr(), bias_gs=N)()
+    torch.cuda.synchronize()
+    ref = (torch.einsum("mk,gnk->gmn", X.double(), W.double()) + b.double()[:, None, :]).clamp(min=0)
+    scale = (X.double().abs() @ W.double().abs().transpose(1, 2)).max().item()
+    err = (Cd.double().cpu() - ref).abs().max().item()
+    assert err <= (3e-6 if passes == 3 else 3e-3) * scale, f"first layer on tensor cores: err {err:.3e}"
+    return err / scale
 
 
 # ------------------------------------------------------------------------------------------------ narrow layers (large M)
