@@ -44,7 +44,7 @@ struct TcParams {
     const float* gen_col; int64_t gen_col_gs;
     const float* Bm; int64_t ldbm, bm_gs;       // B_MANUAL: B rows are not TMA-able (pitch not a multiple of 16 bytes);
     int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
-    int a_shared;                               // one A for all groups (a_gs == 0): the A map has a single group plane
+    int a_shared, b_shared;                     // one A / B for all groups (group stride 0): that map has a single plane
     int a_mn, b_mn;            // operand stored [k][m] / [k][n] (MN-major) instead of [m][k] / [n][k]
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
@@ -200,6 +200,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int g = idx / p.tiles_m;
     const int NT = p.NT;                       // this CTA owns output columns [n0, n0 + NT)
     const int n0 = tile_n * NT;
+    const int n_lim = min(NT, p.N - n0);       // valid output columns of this tile (N need not be a multiple of NT)
     const int total_slabs = (p.K + BK - 1) / BK;
     const int slab0 = split * p.slabs_per_split;
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
@@ -245,7 +246,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (threadIdx.x == 0) TC_STAMP(1);
     if (warp >= 2 && warp < 6) {
         const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs + n0 : nullptr;
-        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < NT) ? __ldg(bg + i) : 0.f;
+        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < n_lim) ? __ldg(bg + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -270,8 +271,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else tma_load_3d(smem_u32(a_raw(s)), &tmA, smem_u32(&full[s]), k0, tile_m * BM, p.a_shared ? 0 : g);
             if (p.b_mn) {
                 for (int b = 0; b < NT / 32; ++b)
-                    tma_load_3d(smem_u32(b_raw(s)) + b * 4096, &tmB, smem_u32(&full[s]), n0 + 32 * b, k0, g);
-            } else if (!p.b_manual) tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, g);
+                    tma_load_3d(smem_u32(b_raw(s)) + b * 4096, &tmB, smem_u32(&full[s]), n0 + 32 * b, k0, p.b_shared ? 0 : g);
+            } else if (!p.b_manual) tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, p.b_shared ? 0 : g);
             if (p.trace_mode == 1 && it < 8) TC_STAMP(8 + it);
         }
       }
@@ -331,7 +332,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.epi == ORLK_EPI_RELU_MASK) {
             const int w = warp - 6;
             const float* auxg = p.aux + (int64_t)g * p.aux_gs + n0;
-            const bool vec = (p.ldaux % 4 == 0) && (p.aux_gs % 4 == 0) && aligned16(p.aux) && (NT % 4 == 0);
+            const bool vec = (p.ldaux % 4 == 0) && (p.aux_gs % 4 == 0) && aligned16(p.aux) && (n_lim % 4 == 0);
             constexpr int RB = 8;                                   // rows per batch
             for (int r0 = 0; r0 < 32; r0 += RB) {
                 float4 a[RB][2];
@@ -342,14 +343,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int q = 0; q < 2; ++q) {
                         const int n = q * 128 + 4 * lane;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < p.M && n < NT) {
+                        if (m < p.M && n < n_lim) {
                             const float* src = auxg + (int64_t)m * p.ldaux + n;
                             if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
                             else {
                                 v.x = __ldg(src);
-                                if (n + 1 < NT) v.y = __ldg(src + 1);
-                                if (n + 2 < NT) v.z = __ldg(src + 2);
-                                if (n + 3 < NT) v.w = __ldg(src + 3);
+                                if (n + 1 < n_lim) v.y = __ldg(src + 1);
+                                if (n + 2 < n_lim) v.z = __ldg(src + 2);
+                                if (n + 3 < n_lim) v.w = __ldg(src + 3);
                             }
                         }
                         a[rr][q] = v;
@@ -516,11 +517,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         float* C = p.C ? p.C + (int64_t)g * p.c_gs + (int64_t)split * p.c_split_stride + (int64_t)m * p.ldc + n0 : nullptr;
         float* CT = p.CT ? p.CT + (int64_t)g * p.ct_gs + (int64_t)n0 * p.ldct + m : nullptr;
-        const bool vec_ok = (NT % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
+        const bool vec_ok = (n_lim % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.C) && (p.c_gs % 4 == 0) &&
                             (p.c_split_stride % 4 == 0);
         const bool c_tma = p.c_tma != 0;
         bool issued = false;
-        for (int c0 = 32 * half; c0 < NT; c0 += 64) {
+        for (int c0 = 32 * half; c0 < n_lim; c0 += 64) {
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
             tmem_wait_ld();
@@ -567,19 +568,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (vec_ok) {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
-                        if (c0 + 4 * j4 < NT)
+                        if (c0 + 4 * j4 + 3 < n_lim)
                             *reinterpret_cast<float4*>(C + c0 + 4 * j4) =
                                 make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < NT) C[c0 + j] = x[j];
+                        if (c0 + j < n_lim) C[c0 + j] = x[j];
                 }
             }
             if (row_ok && CT != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (c0 + j < NT) CT[(int64_t)(c0 + j) * p.ldct] = x[j];
+                    if (c0 + j < n_lim) CT[(int64_t)(c0 + j) * p.ldct] = x[j];
             }
         }
         if (want_rowsum && half == 0) {
@@ -712,7 +713,7 @@ extern "C" int orlk_tc_init(void) {
 extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE(q != nullptr, "params");
     ORLK_REQUIRE(q->M > 0 && q->K > 0 && q->G > 0, "sizes");
-    ORLK_REQUIRE(q->N >= 16 && q->N <= BN_MAX && q->N % 16 == 0, "N must be a multiple of 16 in [16,256]");
+    ORLK_REQUIRE(q->N >= 1 && q->N <= BN_MAX, "N must be in [1,256]");
     ORLK_REQUIRE(q->passes == 1 || q->passes == 3, "passes must be 1 or 3");
     ORLK_REQUIRE(q->lda % 4 == 0 && q->a_gs % 4 == 0 && aligned16(q->A), "A must be 16-byte aligned with strides that are multiples of 4 floats");
     // B rows that TMA cannot address (the K = obs+act wide first-layer weights, pitch 23 floats) are staged by hand
@@ -728,17 +729,18 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE(splits == (q->k_splits < 1 ? 1 : q->k_splits), "k_splits must divide the slab count evenly enough (use orlk_tc_effective_splits)");
 
     CUtensorMap tmA, tmB;
-    const bool a_shared = q->a_gs == 0 && q->G > 1;
+    const bool a_shared = q->a_gs == 0 && q->G > 1, b_shared = q->b_gs == 0 && q->G > 1;
     int rc = q->a_mn ? make_map_mn(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G)
                      : make_map(&tmA, q->A, q->lda, q->a_gs, q->M, q->K, a_shared ? 1 : q->G, BM);
     if (rc) return rc;
-    const int NT = (q->n_tile > 0) ? q->n_tile : q->N;
-    ORLK_REQUIRE(NT >= 16 && NT <= BN_MAX && NT % 16 == 0 && q->N % NT == 0, "n_tile must be a multiple of 16 that divides N");
+    // the MMA is always NT (a multiple of 16) columns wide; columns past N are zero operand rows and are not stored
+    const int NT = (q->n_tile > 0) ? q->n_tile : (q->N + 15) / 16 * 16;
+    ORLK_REQUIRE(NT >= 16 && NT <= BN_MAX && NT % 16 == 0, "n_tile must be a multiple of 16 in [16,256]");
     ORLK_REQUIRE(!q->b_mn || (NT % 32 == 0 && !b_manual), "an MN-major B needs 32-column n-tiles and 16-byte aligned rows");
     if (b_manual) memset(&tmB, 0, sizeof(tmB));
     else {
-        rc = q->b_mn ? make_map_mn(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G)
-                     : make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, q->G, NT);
+        rc = q->b_mn ? make_map_mn(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, b_shared ? 1 : q->G)
+                     : make_map(&tmB, q->B, q->ldb, q->b_gs, q->N, q->K, b_shared ? 1 : q->G, NT);
         if (rc) return rc;
     }
 
@@ -750,12 +752,12 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.rowsum = q->rowsum; p.rowsum_gs = q->rowsum_gs; p.rowsum_split_stride = q->rowsum_split_stride;
     p.M = q->M; p.N = q->N; p.K = q->K; p.G = q->G; p.epi = q->epi;
     p.k_splits = splits; p.slabs_per_split = per; p.tiles_m = (q->M + BM - 1) / BM;
-    p.NT = NT; p.tiles_n = q->N / NT;
+    p.NT = NT; p.tiles_n = (q->N + NT - 1) / NT;
     ORLK_REQUIRE((q->gen_row == nullptr) == (q->gen_col == nullptr), "gen_row and gen_col go together");
     ORLK_REQUIRE(q->gen_row == nullptr || (q->K % 4 == 0 && aligned16(q->gen_col) && q->gen_col_gs % 4 == 0),
                  "the operand generator needs K % 4 == 0 and 16-byte aligned column factors");
     p.a_mn = q->a_mn ? 1 : 0; p.b_mn = q->b_mn ? 1 : 0;
-    p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0;
+    p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0; p.b_shared = b_shared ? 1 : 0;
     p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;
     p.trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }
@@ -764,7 +766,7 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
     p.c_tma = 0;
-    if (q->C != nullptr && NT % 32 == 0 && q->ldc % 4 == 0 && aligned16(q->C) && q->c_gs % 4 == 0 && q->c_split_stride % 4 == 0 &&
+    if (q->C != nullptr && NT % 32 == 0 && q->N % 4 == 0 && q->ldc % 4 == 0 && aligned16(q->C) && q->c_gs % 4 == 0 && q->c_split_stride % 4 == 0 &&
         (int64_t)NT * 512 <= (int64_t)p.stages * p.stage_bytes) {
         rc = make_map_c(&tmC, q->C, q->ldc, q->c_gs, q->c_split_stride, q->M, q->N, q->G, splits);
         if (rc) return rc;

@@ -420,7 +420,21 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     for l in range(n_l):
         cfg, s = layout[l]
         lay = ps.layers[l]
-        if l == 0 and run.w0_part is not None and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X):
+        same_x = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
+        if (l == 0 and run.tc and run.narrow0 and M >= TC_MIN_ROWS and same_x and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0
+                and lay.out_dim % 4 == 0 and os.environ.get("ORLK_TC_WGRAD0", "1") != "0"):
+            # dW0[o][i] = sum_m dZ0[m][o] X[m][i] on the tensor cores: both operands row-major as they are (MN-major
+            # tiles), one X shared by the members, 32-column n-tile with the columns past in_dim zero
+            s0 = L.load().orlk_tc_effective_splits(M, TC_WGRAD_SPLITS)
+            assert s0 <= gb.n_slots, (s0, gb.n_slots)
+            splits[0] = s0
+            launches.append((f"{tag}.wgrad0.tc", rt.tc_gemm(
+                A=_grouped(run.dZ[0], M, lay.out_dim, lay.out_dim), a_gs=M * lay.out_dim, a_mn=True,
+                B=Mat(X[0].ptr, M, lay.in_dim, X[0].ld), b_gs=0, b_mn=True, n_tile=32, G=G, passes=3,
+                C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
+                rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s0)))
+            continue
+        if l == 0 and run.w0_part is not None and same_x:
             o, i = lay.out_dim, lay.in_dim
             args = (run.dZ[0].data_ptr(), o, M * o, X[0].ptr, X[0].ld, 0, run.w0_part.data_ptr(), 1, i, o * i, G * o * i,
                     run.b0_part.data_ptr(), o, G * o, None, 0, 0, M, o, i, G)

@@ -522,9 +522,39 @@ def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
     errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 16, gen_mode=True))
     errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 17, gen_mode=True, a_mn=True,
                          b_mn=True))
+    # first-layer weight gradient: N = 23 columns inside a 32-column tile, operands MN-major, B shared by the groups
+    errs.append(_tc_wgrad0_case(rt, passes))
     # first-layer shape: K = 23 with unaligned weight rows (staged by the kernel's own warps), A shared by the groups
     errs.append(_tc_first_layer_case(rt, passes))
     print(f"passes={passes}: relative errors {['%.2e' % e for e in errs]}")
+
+
+def _tc_wgrad0_case(rt, passes):
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import Mat
+    gen = torch.Generator().manual_seed(78)
+    G, Mb, O, I = 2, 7936, 256, 23
+    dZ = torch.randn(G, Mb, O, generator=gen) / math.sqrt(Mb)
+    X = torch.randn(Mb, I, generator=gen)
+    Xd = torch.zeros(Mb, 24, device=DEV)
+    Xd[:, :I] = X.to(DEV)
+    dZd = dZ.to(DEV)
+    s_eff = rt.lib.orlk_tc_effective_splits(Mb, 31)
+    Cd = torch.full((s_eff, G, O, I), float("nan"), device=DEV)
+    rs = torch.full((s_eff, G, O), float("nan"), device=DEV)
+    rt.tc_gemm(A=Mat(dZd.data_ptr(), Mb, O, O), a_gs=Mb * O, a_mn=True, B=Mat(Xd.data_ptr(), Mb, I, 24), b_gs=0, b_mn=True,
+               n_tile=32, G=G, passes=passes, C=Mat(Cd.data_ptr(), O, I, I), c_gs=O * I, c_split_stride=G * O * I,
+               rowsum=rs.data_ptr(), rowsum_gs=O, rowsum_split_stride=G * O, k_splits=31)()
+    torch.cuda.synchronize()
+    ref = torch.einsum("gmo,mi->goi", dZ.double(), X.double())
+    got = Cd.sum(0).double().cpu()
+    assert not torch.isnan(got).any(), "first-layer wgrad: unwritten output"
+    scale = torch.einsum("gmo,mi->goi", dZ.double().abs(), X.double().abs()).max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= (3e-6 if passes == 3 else 3e-3) * scale, f"first-layer wgrad on tensor cores: err {err:.3e} scale {scale:.3e}"
+    rerr = (rs.sum(0).double().cpu() - dZ.double().sum(1)).abs().max().item()
+    assert rerr <= (3e-6 if passes == 3 else 3e-3) * dZ.abs().sum(1).max().item(), f"first-layer wgrad bias sums: {rerr:.3e}"
+    return err / scale
 
 
 def _tc_first_layer_case(rt, passes):
