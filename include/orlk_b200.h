@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 10
+#define ORLK_ABI_VERSION 11
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -130,10 +130,13 @@ int orlk_gemm_init(void); /* once per process, outside stream capture (shared-me
 int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tiles, int cfg, int a_layout, int b_layout,
                       void* stream);
 /* Small-row variant (M of a few hundred, latency-bound layers): same descriptor and math, 32 x 16 output tiles
- * (ORLK_CFG_TINY), the whole k extent of both operand tiles fetched in one cp.async burst, four k-parallel thread
- * groups.  descs_host is a HOST array of 1..16 problems with k_splits == 1 (it travels in the kernel parameters). */
+ * (ORLK_CFG_TINY), 512 threads in 8 k-groups that each fetch their own share of the operand tiles with cp.async and sync
+ * only among themselves.  passes: 0 = fp32 FFMA, 3 = 3xTF32 warp-level tensor-core MMAs on hi/lo split operands
+ * (fp32-grade), 1 = single-pass TF32; launches that ask for row / column sums always take the FFMA kernel.
+ * descs_host is a HOST array of 1..16 problems with k_splits == 1 (it travels in the kernel parameters). */
 int orlk_gemm_tiny_init(void); /* once per process, outside stream capture */
-int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles, int a_layout, int b_layout, void* stream);
+int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles, int a_layout, int b_layout, int passes,
+                   void* stream);
 
 /* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
  *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.

@@ -54,6 +54,23 @@ void set_trace_buffer(unsigned long long* p);
 void prepare_kernel(const void* fn);
 
 template <typename... KArgs, typename... Args>
+inline void launch_opt(bool allow_pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+    prepare_kernel(reinterpret_cast<const void*>(kernel));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (allow_pdl && pdl_enabled()) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     prepare_kernel(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg{};

@@ -108,18 +108,19 @@ class Runtime:
         L.call("orlk_stream_sync", self.cur)
 
     # ---- launch builders: each returns a zero-argument closure that enqueues on self.stream
-    def gemm(self, problems: Sequence[GP], cfg: int) -> Callable[[], None]:
+    def gemm(self, problems: Sequence[GP], cfg: int, passes: int = 0) -> Callable[[], None]:
         """Grouped fp32 GEMM launch(es): the kernel is specialised on the operand layouts, so problems are bucketed
-        by (a_layout, b_layout) -- one launch per bucket (normally a single one)."""
+        by (a_layout, b_layout) -- one launch per bucket (normally a single one).  ``passes`` (CFG_TINY only):
+        0 = fp32 FFMA, 3 = 3xTF32 tensor-core MMAs (fp32-grade), 1 = single-pass TF32."""
         buckets: Dict[Tuple[int, int], List[GP]] = {}
         for p in problems:
             buckets.setdefault((p.a_layout, p.b_layout), []).append(p)
-        ops = [self._gemm_bucket(ps, cfg, key) for key, ps in buckets.items()]
+        ops = [self._gemm_bucket(ps, cfg, key, passes) for key, ps in buckets.items()]
         if len(ops) == 1:
             return ops[0]
         return lambda: [op() for op in ops] and None
 
-    def _gemm_bucket(self, problems: Sequence[GP], cfg: int, layouts: Tuple[int, int]) -> Callable[[], None]:
+    def _gemm_bucket(self, problems: Sequence[GP], cfg: int, layouts: Tuple[int, int], passes: int = 0) -> Callable[[], None]:
         BM, BN, BK = L.CFG_TILES[cfg]
         arr = (L.GemmDesc * len(problems))()
         tile = 0
@@ -155,7 +156,7 @@ class Runtime:
                     assert sub[i].k_splits == 1, "the small-row kernel does not split k"
                     sub[i].tile_start -= base
                 tiles = (arr[i0 + n].tile_start if i0 + n < len(problems) else tile) - base
-                ops.append(lambda sub=sub, n=n, tiles=tiles: L.call("orlk_gemm_tiny", sub, n, tiles, al, bl, self.cur))
+                ops.append(lambda sub=sub, n=n, tiles=tiles: L.call("orlk_gemm_tiny", sub, n, tiles, al, bl, passes, self.cur))
             return ops[0] if len(ops) == 1 else (lambda: [op() for op in ops] and None)
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())

@@ -189,6 +189,7 @@ class MlpRun:
                  tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
         self.tc = tc_passes if M >= TC_MIN_ROWS_FWD else 0
+        self.passes = tc_passes          # arithmetic of the small-row kernel: 0 fp32 FFMA, 3 = 3xTF32 MMAs, 1 = TF32
         self.Mt = (M + 3) // 4 * 4
         self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
         lays = ps.layers
@@ -300,7 +301,8 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
             continue
         probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store,
                              YT=run.ht(l, g)) for g in range(G)]
-        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim)))
+        # (the first layer sees raw observations: fp32-grade even in the single-pass mode)
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim), passes=(3 if (l == 0 and run.passes) else run.passes)))
     if run.has_head:
         emit_head_forward(rt, plan, run, tag)
 
@@ -353,7 +355,7 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
             continue
         probs = [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g),
                                dXT=run.dzt(l - 1, g)) for g in range(G)]
-        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim)))
+        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim), passes=run.passes))
 
 
 def emit_dact(rt: Runtime, plan: Plan, run: MlpRun, dA: torch.Tensor, col0: int, ncols: int, tag: str) -> None:

@@ -14,7 +14,7 @@ rt = get_runtime("cuda:0")
 NAMES = ["start", "prev_done", "issued", "landed", "k_loop", "reduced", "stored"]
 
 
-def trace(M, N, K, a_layout, b_layout, G=1, epi=0):
+def trace(M, N, K, a_layout, b_layout, G=1, epi=0, passes=0):
     keep, probs = [], []
     for g in range(G):
         A = torch.randn(M, K, device="cuda") if a_layout == 0 else torch.randn(K, M, device="cuda")
@@ -28,7 +28,7 @@ def trace(M, N, K, a_layout, b_layout, G=1, epi=0):
     buf = torch.zeros(4096 * 16, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     L.call("orlk_tc_set_trace", buf.data_ptr())
-    op = rt.gemm(probs, L.CFG_TINY)
+    op = rt.gemm(probs, L.CFG_TINY, passes=passes)
     g = C.c_void_p()
     rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
     L.call("orlk_graph_begin", rt.cur)
@@ -45,15 +45,14 @@ def trace(M, N, K, a_layout, b_layout, G=1, epi=0):
     rel = t - t[:, 1:2]
     med = rel.median(dim=0).values
     mx = rel.max(dim=0).values
-    print(f"M={M} N={N} K={K} a{a_layout} b{b_layout} G={G} ctas={n_cta}")
+    print(f"M={M} N={N} K={K} a{a_layout} b{b_layout} G={G} passes={passes} ctas={n_cta}")
     print("   median " + "  ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, med.tolist())))
     print("   max    " + "  ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, mx.tolist())))
     L.call("orlk_graph_destroy", g)
 
 
-trace(256, 256, 256, 0, 1)          # forward (A k-contiguous, W [out][in])
-trace(256, 256, 256, 0, 0)          # dgrad (W [k][n])
-trace(256, 256, 256, 1, 0)          # wgrad
-trace(256, 256, 256, 0, 1, G=2)
-trace(512, 256, 256, 0, 1)
-trace(256, 256, 23, 0, 1)
+for passes in (0, 3):
+    trace(256, 256, 256, 0, 1, passes=passes)          # forward (A k-contiguous, W [out][in])
+    trace(256, 256, 256, 0, 0, passes=passes)          # dgrad (W [k][n])
+    trace(256, 256, 256, 0, 1, G=2, passes=passes)
+    trace(256, 256, 4, 0, 1, passes=passes)
