@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 11
+#define ORLK_ABI_VERSION 12
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -137,6 +137,16 @@ int orlk_gemm_grouped(const OrlkGemmDesc* descs_dev, int n_descs, int total_tile
 int orlk_gemm_tiny_init(void); /* once per process, outside stream capture */
 int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles, int a_layout, int b_layout, int passes,
                    void* stream);
+
+/* Fused small-row layer chain: ONE launch runs n_stages dependent GEMM stages (stage s+1 multiplies what stage s
+ * wrote: A of s+1 == C of s) for n_chains independent chains with the same M (twin critics).  A thread-block cluster of
+ * 8 CTAs owns a 32-row strip for the whole chain (one 32 x 32 column tile per CTA and stage, cluster barrier between
+ * stages), arithmetic as orlk_gemm_tiny's tensor-core variant (passes 1 or 3; passes_stage0 for the first stage, which
+ * may see raw observations).  descs_host[chain * n_stages + stage] is a
+ * HOST array of at most 16 descriptors: a_layout 0, K <= 256, N <= 256, no split-K / sums / transposed copy.
+ * Replaces the per-layer launches of an MLP forward (nets/mlp.py:22,28) or its autograd input-gradient pass. */
+int orlk_gemm_chain_init(void); /* once per process, outside stream capture */
+int orlk_gemm_chain(const OrlkGemmDesc* descs_host, int n_chains, int n_stages, int passes, int passes_stage0, void* stream);
 
 /* Tensor-core GEMM (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand ring) for the wide hidden layers:
  *   C[g][m][n] = epi( sum_k A[g][m][k] * B[g][n][k] ),   A and B row-major with k contiguous, N <= 256, N % 16 == 0.

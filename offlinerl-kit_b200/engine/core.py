@@ -93,6 +93,7 @@ class Runtime:
         L.call("orlk_tc_init")
         L.call("orlk_gemm_init")
         L.call("orlk_gemm_tiny_init")
+        L.call("orlk_gemm_chain_init")
         L.call("orlk_narrow_init")
 
     # ---- memory helpers (torch owns device memory: plumbing)
@@ -161,6 +162,26 @@ class Runtime:
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr = len(problems), tile, C.c_void_p(dev.data_ptr())
         return lambda: L.call("orlk_gemm_grouped", ptr, n, total, cfg, al, bl, self.cur)
+
+    def gemm_chain(self, chains: Sequence[Sequence[GP]], passes: int, passes0: Optional[int] = None) -> Callable[[], None]:
+        """One launch for whole small-row layer chains (csrc/orlk_chain.cu): ``chains[c][s]`` is stage s of chain c, the
+        A operand of stage s+1 is the C output of stage s; all chains have the same number of stages and rows."""
+        n_chains, n_stages = len(chains), len(chains[0])
+        assert all(len(c) == n_stages for c in chains) and n_chains * n_stages <= 16
+        arr = (L.GemmDesc * (n_chains * n_stages))()
+        for c, chain in enumerate(chains):
+            for s_, p in enumerate(chain):
+                d = arr[c * n_stages + s_]
+                assert p.a_layout == 0 and p.k_splits <= 1 and not p.rowsum and not p.colsum and not p.CT, p
+                assert s_ == 0 or (p.A == chain[s_ - 1].C and p.K == chain[s_ - 1].N), "stage input must be the previous output"
+                d.A, d.B, d.C, d.C2 = p.A, p.B, p.C, p.C2 or None
+                d.bias, d.aux = p.bias or None, p.aux or None
+                d.lda, d.ldb, d.ldc, d.ldaux = p.lda, p.ldb, p.ldc, p.ldaux
+                d.M, d.N, d.K = p.M, p.N, p.K
+                d.a_layout, d.b_layout, d.epi = p.a_layout, p.b_layout, p.epi
+                d.k_splits, d.k_chunk = 1, p.K
+        p0 = passes if passes0 is None else passes0
+        return lambda: L.call("orlk_gemm_chain", arr, n_chains, n_stages, passes, p0, self.cur)
 
     def tc_gemm(self, *, A: Mat, a_gs: int, B: Mat, b_gs: int, G: int, passes: int, epi: int = L.EPI_NONE,
                 C: Optional[Mat] = None, c_gs: int = 0, c_split_stride: int = 0, CT: Optional[Mat] = None, ct_gs: int = 0,

@@ -189,7 +189,11 @@ class MlpRun:
                  tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
         self.tc = tc_passes if M >= TC_MIN_ROWS_FWD else 0
-        self.passes = tc_passes          # arithmetic of the small-row kernel: 0 fp32 FFMA, 3 = 3xTF32 MMAs, 1 = TF32
+        # arithmetic of the small-row kernel: 0 = fp32 FFMA (default: exact fp32, and as fast in the step because those
+        # launches are bound by launch / prologue latency, not by the k loop), 3 = 3xTF32 MMAs, 1 = TF32 (ORLK_TINY_MMA=1)
+        self.passes = tc_passes if os.environ.get("ORLK_TINY_MMA", "0") == "1" else 0
+        if os.environ.get("ORLK_CHAIN", "0") == "1":
+            self.passes = tc_passes
         self.Mt = (M + 3) // 4 * 4
         self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
         lays = ps.layers
@@ -262,6 +266,16 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
     return Mat(t.data_ptr(), rows, cols, ld, t)
 
 
+def chainable(run: "MlpRun", with_head: bool) -> bool:
+    """Small-row pass whose layers all fit the fused chain kernel (csrc/orlk_chain.cu)."""
+    lays = run.ps.layers[:run.nh + (1 if with_head else 0)]
+    # Off by default: measured 6.6 us per stage against ~6 us for the per-layer launches (profiles/chain_trace.py): with
+    # 4 CTAs per strip the legacy mma.sync rate (~1/16 of an SMSP issue slot per m16n8k8) makes the stage compute 3.2 us
+    # and the scalar DSMEM pushes cost 2.5 us.  Kept (and unit-tested) as the base for a 16-CTA-cluster version.
+    return (run.passes != 0 and run.M < TC_MIN_ROWS and len(lays) <= 8 and os.environ.get("ORLK_CHAIN", "0") == "1"
+            and all(lay.layout == "oi" and lay.in_dim <= 256 and lay.out_dim <= 256 for lay in lays))
+
+
 # the streaming first-layer kernel pays off for long row counts; short passes take the small-row GEMM (one k pass)
 NARROW_MIN_ROWS = int(os.environ.get("ORLK_NARROW_MIN_ROWS", "1024"))
 
@@ -270,6 +284,20 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
     """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
     ps, G, M = run.ps, run.G, run.M
     plan.keep += [run, [x.keep for x in X]]
+    if chainable(run, with_head=run.has_head) and all(h is None for h in run.HT):
+        # the whole pass (hidden layers + head) as fused chain launches: one cluster per 32-row strip and member
+        n_st = run.nh + (1 if run.has_head else 0)
+        chains = []
+        for g in range(G):
+            st = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store)
+                  for l in range(run.nh)]
+            if run.has_head:
+                st.append(fwd_problem(ps, run.nh, g, run.h(run.nh - 1, g), Mat.of(run.out[g]), L.EPI_NONE, run.store))
+            chains.append(st)
+        per = max(1, 16 // n_st)
+        for c0 in range(0, G, per):
+            plan.add(f"{tag}.fwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes, passes0=3))
+        return
     for l in range(run.nh):
         lay = ps.layers[l]
         if run.tc_fwd[l]:
@@ -324,6 +352,9 @@ def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     ps, G, l = run.ps, run.G, run.nh
     if run.fuse_head_bwd:
         return                  # folded into the consumers' operand generator
+    if chainable(run, with_head=True) and all(t is None for t in run.dZT):
+        run.pending_head_dgrad = True       # becomes the first stage of the chain emitted by emit_hidden_dgrad
+        return
     lay = ps.layers[l]
     K = lay.in_dim
     hmask = run.H[l - 1]
@@ -334,9 +365,30 @@ def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     plan.add(f"{tag}.head_dgrad", lambda: L.call("orlk_skinny_dgrad", *args, rt.cur))
 
 
-def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1) -> None:
-    """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to."""
+def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1, dact=None) -> None:
+    """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to.  ``dact = (dA, col0, ncols)`` appends
+    dA[g] = dZ[0][g] . W0[:, col0:col0+ncols] (the gradient w.r.t. some input columns, emit_dact) to the pass."""
     ps, G, M = run.ps, run.G, run.M
+    if getattr(run, "pending_head_dgrad", False):
+        run.pending_head_dgrad = False
+        chains = []
+        for g in range(G):
+            st = [dgrad_problem(ps, run.nh, g, Mat.of(run.dOut[g]), run.dz(run.nh - 1, g), L.EPI_RELU_MASK, run.h(run.nh - 1, g))]
+            st += [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g))
+                   for l in range(run.nh - 1, down_to - 1, -1)]
+            if dact is not None:
+                assert down_to == 1
+                dA, col0, ncols = dact
+                st.append(dgrad_problem(ps, 0, g, run.dz(0, g), Mat.of(dA[g]), L.EPI_NONE, None, col0=col0, ncols=ncols))
+            chains.append(st)
+        if dact is not None:
+            plan.keep.append(dact[0])
+        per = max(1, 16 // len(chains[0]))
+        for c0 in range(0, G, per):
+            plan.add(f"{tag}.bwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes))
+        return
+    if dact is not None:
+        raise L.OrlkError("emit_hidden_dgrad(dact=...) needs the fused chain path; call emit_dact instead")
     for l in range(run.nh - 1, down_to - 1, -1):
         lay = ps.layers[l]
         if run.tc_dgrad[l]:

@@ -164,9 +164,12 @@ class TwinCriticLearner(Learner):
                 dq.data_ptr(), B, self.glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
         plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
         emit_head_dgrad(rt, plan, cr, "A.critic")
-        emit_hidden_dgrad(rt, plan, cr, "A.critic")
         # dL/da = sum over the two critics of dZ1 . W1[:, O:O+A]
-        emit_dact(rt, plan, cr, self.dA, O, A, "A.critic")
+        if getattr(cr, "pending_head_dgrad", False):       # fused chain: head dgrad, hidden dgrads and d/da in one launch
+            emit_hidden_dgrad(rt, plan, cr, "A.critic", dact=(self.dA, O, A))
+        else:
+            emit_hidden_dgrad(rt, plan, cr, "A.critic")
+            emit_dact(rt, plan, cr, self.dA, O, A, "A.critic")
         head = ar.out[0]
         bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), 2, B * A, A,
                  self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)

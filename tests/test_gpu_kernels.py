@@ -120,6 +120,68 @@ def test_gemm_small_row_kernel_tensor_core_variant(rt, passes):
         _gemm_case(rt, 4, 256, 256, 256, 0, 0, epi, 1, with_bias=epi in (1, 3), sums=False, seed=700 + epi, passes=passes)
 
 
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_chain_forward_and_backward(rt, passes):
+    """The fused chain launch against the same layers in fp64: a 23 -> 256 -> 256 -> 256 -> 12 forward (bias + ReLU, no
+    activation on the head) and the matching input-gradient chain (ReLU masks), two independent chains, ragged M."""
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200.engine.core import GP
+    gen = torch.Generator().manual_seed(31)
+    G, M, dims = 2, 200, [23, 256, 256, 256, 12]
+    X = torch.randn(G, M, dims[0], generator=gen)
+    Ws = [torch.randn(G, dims[i + 1], dims[i], generator=gen) / math.sqrt(dims[i]) for i in range(4)]
+    bs = [torch.randn(G, dims[i + 1], generator=gen) * 0.1 for i in range(4)]
+    Xd, Wd, bd = X.to(DEV), [w.to(DEV) for w in Ws], [b.to(DEV) for b in bs]
+    H = [torch.full((G, M, dims[i + 1]), float("nan"), device=DEV) for i in range(4)]
+    chains = []
+    for g in range(G):
+        st = []
+        for i in range(4):
+            src = Xd[g] if i == 0 else H[i - 1][g]
+            st.append(GP(A=src.data_ptr(), lda=dims[i], a_layout=0, B=Wd[i][g].data_ptr(), ldb=dims[i], b_layout=1,
+                         C=H[i][g].data_ptr(), ldc=dims[i + 1], M=M, N=dims[i + 1], K=dims[i], epi=L.EPI_RELU if i < 3 else L.EPI_NONE,
+                         bias=bd[i][g].data_ptr()))
+        chains.append(st)
+    rt.gemm_chain(chains, passes)()
+    torch.cuda.synchronize()
+    tol = dict(rtol=3e-6, atol=3e-5) if passes == 3 else dict(rtol=5e-3, atol=5e-2)
+    ref = X.double()
+    refs = []
+    for i in range(4):
+        ref = torch.einsum("gmk,gnk->gmn", ref, Ws[i].double()) + bs[i].double()[:, None, :]
+        if i < 3:
+            ref = ref.clamp(min=0)
+        refs.append(ref)
+        assert not torch.isnan(H[i]).any(), f"chain fwd stage {i}: unwritten output"
+        _close(H[i], ref, msg=f"chain fwd stage {i} passes {passes}", **tol)
+    # backward: dOut [M,12] -> dZ2 = (dOut W3) * (H2 > 0) -> dZ1 -> dZ0, then d/d(input columns 17..22) without a mask
+    dOut = torch.randn(G, M, 12, generator=gen)
+    dOd = dOut.to(DEV)
+    Hm = [r.float().to(DEV) for r in refs[:3]]          # exact masks from the reference activations
+    dZ = [torch.full((G, M, 256), float("nan"), device=DEV) for _ in range(3)]
+    dA = torch.full((G, M, 6), float("nan"), device=DEV)
+    chains = []
+    for g in range(G):
+        st, src, kdim = [], dOd[g], 12
+        for i in (3, 2, 1):
+            st.append(GP(A=src.data_ptr(), lda=kdim, a_layout=0, B=Wd[i][g].data_ptr(), ldb=dims[i], b_layout=0,
+                         C=dZ[i - 1][g].data_ptr(), ldc=256, M=M, N=256, K=kdim, epi=L.EPI_RELU_MASK, aux=Hm[i - 1][g].data_ptr(),
+                         ldaux=256))
+            src, kdim = dZ[i - 1][g], 256
+        st.append(GP(A=dZ[0][g].data_ptr(), lda=256, a_layout=0, B=Wd[0][g].data_ptr() + 4 * 17, ldb=23, b_layout=0,
+                     C=dA[g].data_ptr(), ldc=6, M=M, N=6, K=256, epi=L.EPI_NONE))
+        chains.append(st)
+    rt.gemm_chain(chains, passes)()
+    torch.cuda.synchronize()
+    gref = dOut.double()
+    for i in (3, 2, 1):
+        gref = torch.einsum("gmo,goi->gmi", gref, Ws[i].double()) * (refs[i - 1] > 0)
+        assert not torch.isnan(dZ[i - 1]).any(), f"chain bwd stage {i}: unwritten output"
+        _close(dZ[i - 1], gref, msg=f"chain bwd dZ{i - 1} passes {passes}", **tol)
+    gA = torch.einsum("gmo,goi->gmi", gref, Ws[0].double()[:, :, 17:23])
+    _close(dA, gA, msg=f"chain bwd d/da passes {passes}", **tol)
+
+
 def test_gemm_small_row_kernel_sums_and_long_k(rt):
     # the small-row kernel (cfg 4) never splits k: whole reductions, several 256-wide passes, bias row/col sums
     for (M, N, K) in [(256, 256, 256), (256, 23, 256), (12, 256, 256), (256, 17, 700), (100, 50, 1000), (1, 256, 515)]:
