@@ -79,3 +79,54 @@ def partition_members(n_members: int, world: int) -> List[List[int]]:
         out.append(list(range(start, start + n)))
         start += n
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# State-sharded model rollouts (SURVEY.md section 8e, MOPO rollouts, variant B)
+# --------------------------------------------------------------------------------------------------------------
+def shard_rows(n_rows: int, rank: int, world: int) -> tuple:
+    """[lo, hi) of the contiguous, as-even-as-possible share of ``n_rows`` for ``rank`` (50 000 over 8 -> 6 250 each)."""
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _gather_ragged(arr, device) -> "np.ndarray":
+    """All-gather of per-rank arrays that differ in their first dimension (rollouts drop terminated states), in rank
+    order.  One size exchange + one padded all-gather per array."""
+    import numpy as np
+    world = dist.get_world_size()
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    n_max = max(sizes + [1])
+    pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0).cpu().numpy()
+
+
+def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cpu"):
+    """``MOPOPolicy.rollout`` (policy/model_based/mopo.py:45-79) with the start states split over the ranks.
+
+    Every rank holds the full dynamics ensemble and the actor (replicated after training), imagines the whole horizon
+    for its own contiguous share of ``init_obss`` with no communication, and the resulting transitions are all-gathered
+    in rank order, so every rank ends up with the same fake-buffer batch.  ``rollout_fn(obs, length) -> (dict, info)`` is
+    the single-GPU rollout.  The random streams differ per rank, so the result is distributed like - not bit-equal to -
+    a single-GPU rollout of all states.  Single process: plain call."""
+    import numpy as np
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rollout_fn(init_obss, rollout_length)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_rows(len(init_obss), rank, world)
+    local, info = rollout_fn(init_obss[lo:hi], rollout_length)
+    out = {k: _gather_ragged(v, device) for k, v in local.items()}
+    n_local = float(len(next(iter(local.values())))) if local else 0.0
+    n_tot, r_sum = reduce_scalars([n_local, float(info.get("reward_mean", 0.0)) * n_local], "sum", device)
+    merged = dict(info)
+    merged["num_transitions"] = int(n_tot)
+    merged["reward_mean"] = r_sum / max(n_tot, 1.0)
+    return out, merged

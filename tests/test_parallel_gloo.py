@@ -64,3 +64,67 @@ def test_member_partition():
     assert [len(p) for p in partition_members(10, 4)] == [3, 3, 2, 2]
     assert [len(p) for p in partition_members(10, 8)] == [2, 2, 1, 1, 1, 1, 1, 1]
     assert sum(partition_members(7, 8), []) == list(range(7)) and partition_members(7, 8)[7] == []
+
+
+def _fake_rollout(obs, length):
+    """Stand-in for MOPOPolicy.rollout with its ragged output: every step keeps the states whose first coordinate is
+    below a threshold that shrinks with the step (deterministic, so the sharded result can be checked exactly)."""
+    import numpy as np
+    rows = {"obss": [], "next_obss": [], "actions": [], "rewards": [], "terminals": []}
+    cur = obs
+    for t in range(length):
+        nxt = cur * 0.5
+        rows["obss"].append(cur)
+        rows["next_obss"].append(nxt)
+        rows["actions"].append(cur[:, :2] + t)
+        rows["rewards"].append(cur[:, :1] * 2.0)
+        rows["terminals"].append((cur[:, :1] > 0.5).astype(np.float32))
+        cur = nxt[nxt[:, 0] <= 0.5 / (t + 1)]
+        if len(cur) == 0:
+            break
+    out = {k: np.concatenate(v, 0) for k, v in rows.items()}
+    return out, {"num_transitions": len(out["obss"]), "reward_mean": float(out["rewards"].mean())}
+
+
+def _rollout_worker(rank: int, world: int, port: int, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    from offlinerlkit_b200 import parallel
+    import torch.distributed as dist
+    assert parallel.init("gloo")
+    obs = np.random.default_rng(3).random((101, 4), dtype=np.float32)       # 101 rows: uneven 51 / 50 split
+    out, info = parallel.rollout_state_sharded(_fake_rollout, obs, 3)
+    q.put((rank, {k: v.tolist() for k, v in out.items()}, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_state_sharded_rollout_world2():
+    """Two ranks imagine disjoint shares of the start states and all-gather ragged transition arrays: both ranks end up
+    with rank 0's transitions followed by rank 1's, i.e. what the two single-process rollouts of the shares produce."""
+    import numpy as np
+    from offlinerlkit_b200.parallel import shard_rows
+    assert [shard_rows(50000, r, 8) for r in (0, 7)] == [(0, 6250), (43750, 50000)]
+    assert [shard_rows(101, r, 2) for r in (0, 1)] == [(0, 51), (51, 101)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rollout_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    obs = np.random.default_rng(3).random((101, 4), dtype=np.float32)
+    parts = [_fake_rollout(obs[lo:hi], 3) for lo, hi in ((0, 51), (51, 101))]
+    expect = {k: np.concatenate([p[0][k] for p in parts], 0) for k in parts[0][0]}
+    n = sum(p[1]["num_transitions"] for p in parts)
+    rmean = sum(p[1]["reward_mean"] * p[1]["num_transitions"] for p in parts) / n
+    for rank, out, info in res:
+        for k, v in expect.items():
+            assert np.array_equal(np.asarray(out[k], dtype=np.float32), v), (rank, k)
+        assert info["num_transitions"] == n and info["reward_mean"] == pytest.approx(rmean, rel=1e-6)
