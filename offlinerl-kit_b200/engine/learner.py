@@ -471,6 +471,8 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     splits = [s for _, s in layout] + [1] * (len(ps.layers) - n_l)
     grad_src = {}
     launches: List[Tuple[str, Callable[[], None]]] = []       # mutually independent: run on parallel graph branches
+    launch_layers: List[List[int]] = []                       # the layers whose gradients each launch produces
+    grouped_layers = {L.CFG_BIG: [], L.CFG_SMALL: [], L.CFG_TINY: []}
     for l in range(n_l):
         cfg, s = layout[l]
         lay = ps.layers[l]
@@ -487,12 +489,14 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
                 B=Mat(X[0].ptr, M, lay.in_dim, X[0].ld), b_gs=0, b_mn=True, n_tile=32, G=G, passes=3,
                 C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
                 rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s0)))
+            launch_layers.append([0])
             continue
         if l == 0 and run.w0_part is not None and same_x:
             o, i = lay.out_dim, lay.in_dim
             args = (run.dZ[0].data_ptr(), o, M * o, X[0].ptr, X[0].ld, 0, run.w0_part.data_ptr(), 1, i, o * i, G * o * i,
                     run.b0_part.data_ptr(), o, G * o, None, 0, 0, M, o, i, G)
             launches.append((f"{tag}.wgrad0.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur)))
+            launch_layers.append([0])
             grad_src[(0, "w")] = (run.w0_part.data_ptr(), o * i, G * o * i, run.chunks)
             grad_src[(0, "b")] = (run.b0_part.data_ptr(), o, G * o, run.chunks)
             continue
@@ -501,6 +505,7 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
             args = (run.H[l - 1].data_ptr(), K, M * K, run.dOut.data_ptr(), NS, M * NS, run.hw_part.data_ptr(), K, 1, NS * K,
                     G * NS * K, None, 0, 0, run.hb_part.data_ptr(), NS, G * NS, M, K, NS, G)
             launches.append((f"{tag}.wgrad_head.narrow", lambda args=args: L.call("orlk_narrow_wgrad", *args, rt.cur)))
+            launch_layers.append([l])
             grad_src[(l, "w")] = (run.hw_part.data_ptr(), NS * K, G * NS * K, run.chunks)
             grad_src[(l, "b")] = (run.hb_part.data_ptr(), NS, G * NS, run.chunks)
             continue
@@ -524,25 +529,36 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
                 **operands, **gen, G=G, passes=run.tc,
                 C=Mat(gb.ptr(lay.w_off), lay.out_dim, lay.in_dim, lay.in_dim), c_gs=lay.w_gs, c_split_stride=gb.stride,
                 rowsum=gb.ptr(lay.b_off), rowsum_gs=lay.b_gs, rowsum_split_stride=gb.stride, k_splits=s)))
+            launch_layers.append([l])
             continue
         for g in range(G):
             xin = X[g] if l == 0 else run.h(l - 1, g)
             dy = run.dz(l, g) if l < run.nh else Mat.of(run.dOut[g])
             {L.CFG_BIG: big, L.CFG_SMALL: small, L.CFG_TINY: tiny}[cfg].append(wgrad_problem(ps, gb, l, g, xin, dy, s))
+        grouped_layers[cfg].append(l)
     if big:
         launches.append((f"{tag}.wgrad_big", rt.gemm(big, L.CFG_BIG)))
+        launch_layers.append(grouped_layers[L.CFG_BIG])
     if small:
         launches.append((f"{tag}.wgrad_small", rt.gemm(small, L.CFG_SMALL)))
+        launch_layers.append(grouped_layers[L.CFG_SMALL])
     if tiny:
         launches.append((f"{tag}.wgrad_tiny", rt.gemm(tiny, L.CFG_TINY)))
+        launch_layers.append(grouped_layers[L.CFG_TINY])
+
+    def adam_for(layers):
+        return rt.adam(adam_descs(ps, gb, splits, polyak, layers=layers, grad_src=grad_src, members=range(G)), groups_ptr)
+
     if len(launches) > 1:
+        # each branch: one weight-gradient launch and right behind it the Adam(+polyak) update of exactly those layers, so
+        # the bandwidth-bound optimiser work of one layer overlaps the tensor-core work of the others
         plan.fork()
         for i, (label, op) in enumerate(launches):
             plan.branch(i % (Plan.N_SIDE + 1))
             plan.add(label, op)
+            plan.add(f"{tag}.adam{i}", adam_for(sorted(set(launch_layers[i]))))
         plan.join()
     else:
         for label, op in launches:
             plan.add(label, op)
-    plan.add(f"{tag}.adam", rt.adam(adam_descs(ps, gb, splits, polyak, layers=range(n_l), grad_src=grad_src,
-                                               members=range(G)), groups_ptr))
+        plan.add(f"{tag}.adam", adam_for(range(n_l)))
