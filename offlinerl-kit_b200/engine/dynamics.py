@@ -41,7 +41,7 @@ def emit_dyn_forward(rt: Runtime, plan: Plan, run: DynRun, X: Callable[[int], Ma
             yout = Mat.of(run.OUT[e]) if last else Mat.of(run.H[l][e])
             z = Mat.of(run.Z[l][e]) if (not last and run.Z is not None) else None
             probs.append(fwd_problem(ps, l, e, xin, yout, L.EPI_NONE if last else L.EPI_SWISH, Z=z))
-        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * E, ps.layers[l].out_dim)))
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * E, ps.layers[l].out_dim, rows_per_problem=M)))
 
 
 class DynamicsEngine(Learner):
@@ -108,7 +108,7 @@ class DynamicsEngine(Learner):
             for e in range(E):
                 dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
                 probs.append(dgrad_problem(ps, l, e, dy, Mat.of(run.dZ[l - 1][e]), L.EPI_DSWISH, Mat.of(run.Z[l - 1][e])))
-            plan.add(f"D.dgrad{l}", rt.gemm(probs, pick_cfg(Bn * E, ps.layers[l].in_dim)))
+            plan.add(f"D.dgrad{l}", rt.gemm(probs, pick_cfg(Bn * E, ps.layers[l].in_dim, rows_per_problem=Bn)))
         probs = []
         for l in range(nl):
             for e in range(E):

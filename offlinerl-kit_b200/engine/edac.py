@@ -19,7 +19,7 @@ from .. import _lib as L
 from .core import GP, Mat, Plan
 from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
                       make_gradbuf, wgrad_layout)
-from .nets import GradBuf, ParamSet, adam_descs, dgrad_problem, pick_cfg, wgrad_problem
+from .nets import GradBuf, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, pick_cfg, wgrad_problem
 from .sac_family import LS_ACTOR, LS_ALPHA, LS_ALPHA_LOSS
 from .td3_iql import _BatchMixin
 
@@ -147,7 +147,7 @@ class EDACLearner(_BatchMixin, Learner):
                 xin = mXd if l == 0 else run_c.h(l - 1, e)
                 dy = run_c.dz(l, e) if l < nh else Mat.of(run_c.dOut[e])
                 probs.append(wgrad_problem(cps, gb_c, l, e, xin, dy, td_layout[l][1]))
-        plan.add("C.critics.wgrad_td", rt.gemm(probs, L.CFG_SMALL))
+        plan.add("C.critics.wgrad_td", rt.gemm(probs, L.CFG_TINY if (B < TC_MIN_ROWS and s_td == 1) else L.CFG_SMALL))
         if self.eta > 0:
             # 1. input-gradient chain (upstream 1)
             run_g.dOut.fill_(1.0)
@@ -173,7 +173,7 @@ class EDACLearner(_BatchMixin, Learner):
                         fprobs.append(GP(A=ubar[l - 1][e].data_ptr(), lda=lay.in_dim, a_layout=0, B=cps.w(l, e), ldb=lay.out_dim,
                                          b_layout=0, C=ubar[l][e].data_ptr(), ldc=lay.out_dim, M=B, N=lay.out_dim, K=lay.in_dim,
                                          epi=L.EPI_RELU_MASK, aux=run_c.H[l][e].data_ptr(), ldaux=lay.out_dim))
-                plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim)))
+                plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim, rows_per_problem=B)))
                 for e in range(E):
                     if l + 1 < nh:  # dW_{l+1} += ubar_l^T v_{l+1}
                         wprobs.append(wgrad_problem(cps, gb_c, l + 1, e, Mat.of(ubar[l][e]), run_g.dz(l + 1, e), 1,
@@ -183,7 +183,7 @@ class EDACLearner(_BatchMixin, Learner):
                                                     with_bias=False))
                 if l + 1 < nh:
                     continue
-            plan.add("G.wgrad_div", rt.gemm(wprobs, L.CFG_SMALL))
+            plan.add("G.wgrad_div", rt.gemm(wprobs, L.CFG_TINY if B < TC_MIN_ROWS else L.CFG_SMALL))
         splits = [s_td + 1] * (nh + 1)
         plan.add("C.critics.adam", rt.adam(adam_descs(cps, gb_c, splits, polyak=True), self.groups_ptr))
         mask = (1 << self.g_actor) | (1 << self.g_c) | ((1 << self.g_alpha) if self.g_alpha >= 0 else 0)

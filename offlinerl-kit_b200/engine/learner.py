@@ -330,7 +330,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
         probs = [fwd_problem(ps, l, g, X[g] if l == 0 else run.h(l - 1, g), run.h(l, g), L.EPI_RELU, run.store,
                              YT=run.ht(l, g)) for g in range(G)]
         # (the first layer sees raw observations: fp32-grade even in the single-pass mode)
-        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim), passes=(3 if (l == 0 and run.passes) else run.passes)))
+        plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim, rows_per_problem=M), passes=(3 if (l == 0 and run.passes) else run.passes)))
     if run.has_head:
         emit_head_forward(rt, plan, run, tag)
 
@@ -407,7 +407,7 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
             continue
         probs = [dgrad_problem(ps, l, g, run.dz(l, g), run.dz(l - 1, g), L.EPI_RELU_MASK, run.h(l - 1, g),
                                dXT=run.dzt(l - 1, g)) for g in range(G)]
-        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim), passes=run.passes))
+        plan.add(f"{tag}.dgrad{l}", rt.gemm(probs, pick_cfg(M * G, lay.in_dim, rows_per_problem=M), passes=run.passes))
 
 
 def emit_dact(rt: Runtime, plan: Plan, run: MlpRun, dA: torch.Tensor, col0: int, ncols: int, tag: str) -> None:
