@@ -232,10 +232,12 @@ class GradBuf:
 
 
 # ---------------------------------------------------------------------------------------------- emitters
-TC_MIN_ROWS = 1024      # weight gradients: below this the reduction is too short for the tensor-core kernel
+# below this many rows a pass runs on the small-row kernel: a 1024-row layer is only 8 (x members) 128-row tensor-core
+# tiles - 17-20 us on a handful of SMs against ~9 us as 512 small tiles (IQL at batch 1024)
+TC_MIN_ROWS = int(os.environ.get("ORLK_TC_MIN_ROWS", "2048"))
 # forward / dgrad: below this the layer is latency-bound and goes to the small-row fp32 kernel (csrc/orlk_tiny.cu);
 # ORLK_TC_MIN_ROWS_FWD=128 restores the n-tiled tensor-core path for those layers
-TC_MIN_ROWS_FWD = int(os.environ.get("ORLK_TC_MIN_ROWS_FWD", "1024"))
+TC_MIN_ROWS_FWD = int(os.environ.get("ORLK_TC_MIN_ROWS_FWD", str(TC_MIN_ROWS)))
 
 
 def tc_n_tile(M: int, N: int) -> int:
