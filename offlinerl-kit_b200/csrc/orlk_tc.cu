@@ -28,6 +28,7 @@ constexpr int B_BYTES = BN_MAX * BK * 4;                  // 32 KB
 constexpr int ONES_BYTES = 16 * BK * 4;                   // 2 KB
 constexpr int TMEM_COLS = 512;
 constexpr int ROWSUM_COL = 256;
+constexpr int ATM_COL = 288;                              // A-from-TMEM mode: per stage [hi 32 cols | lo 32 cols] from here
 constexpr int MAX_STAGES = 8;
 constexpr int FIXED_SMEM = 8192;                          // ones tile, barriers, staged bias, mask bits
 constexpr int NUM_THREADS = 320;                          // warp0 TMA, warp1 MMA, warps2-5 split + epilogue, warps6-9 mask
@@ -46,6 +47,7 @@ struct TcParams {
     int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
     int a_shared, b_shared;                     // one A / B for all groups (group stride 0): that map has a single plane
     int a_mn, b_mn;            // operand stored [k][m] / [k][n] (MN-major) instead of [m][k] / [n][k]
+    int a_tmem;                // the splitter moves A (and its lo part) into tensor memory; the MMAs read A from there
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
     unsigned long long* trace; // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
@@ -136,6 +138,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row m, column = k), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+        "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
+        "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
+        "f"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -206,7 +227,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
     const bool want_rowsum = p.rowsum != nullptr && tile_n == 0;
     const bool gen = p.gen_row != nullptr;
-    const bool split_runs = PASSES == 3 || gen || p.b_manual != 0;     // the splitter warps process every stage
+    const bool split_runs = PASSES == 3 || gen || p.b_manual != 0 || p.a_tmem != 0;     // the splitter warps process every stage
+    constexpr int ATM_STRIDE = PASSES == 3 ? 64 : 32;
 
     const int b_bytes = NT * BK * 4;
     auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
@@ -297,6 +319,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (it == 0) TC_STAMP(4);
             if (it == nslabs - 1) TC_STAMP(5);
             if (PASSES == 1 && p.trace_mode == 0 && it < 8) TC_STAMP(8 + it);
+            if (p.a_tmem) {
+                const uint32_t at = tmem_base + ATM_COL + s * ATM_STRIDE;
+                const uint64_t bd = p.b_mn ? smem_desc_sw128_mn(smem_u32(b_raw(s))) : smem_desc_sw128(smem_u32(b_raw(s)));
+                const uint64_t bdl = p.b_mn ? smem_desc_sw128_mn(smem_u32(b_lo(s))) : smem_desc_sw128(smem_u32(b_lo(s)));
+                const uint32_t idesc_ts = instr_desc_tf32(BM, NT) | (p.b_mn ? (1u << 16) : 0u);      // A from TMEM is never transposed
+                const uint32_t idesc_rs_ts = instr_desc_tf32(BM, 16);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                    const uint64_t kb = (uint64_t)k * b_kstep;
+                    umma_tf32_ts(tmem_base, at + 8 * k, bd + kb, idesc_ts, acc);
+                    if (PASSES == 3) {
+                        umma_tf32_ts(tmem_base, at + 32 + 8 * k, bd + kb, idesc_ts, 1u);
+                        umma_tf32_ts(tmem_base, at + 8 * k, bdl + kb, idesc_ts, 1u);
+                    }
+                    if (want_rowsum) {
+                        umma_tf32_ts(tmem_base + ROWSUM_COL, at + 8 * k, ones_desc, idesc_rs_ts, acc);
+                        if (PASSES == 3) umma_tf32_ts(tmem_base + ROWSUM_COL, at + 32 + 8 * k, ones_desc, idesc_rs_ts, 1u);
+                    }
+                }
+                umma_commit(smem_u32(&empty[s]));
+                continue;
+            }
             const uint64_t ad = p.a_mn ? smem_desc_sw128_mn(smem_u32(a_raw(s))) : smem_desc_sw128(smem_u32(a_raw(s)));
             const uint64_t bd = p.b_mn ? smem_desc_sw128_mn(smem_u32(b_raw(s))) : smem_desc_sw128(smem_u32(b_raw(s)));
             const uint64_t adl = p.a_mn ? smem_desc_sw128_mn(smem_u32(a_lo(s))) : smem_desc_sw128(smem_u32(a_lo(s)));
@@ -420,8 +465,51 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 float4* __restrict__ al = reinterpret_cast<float4*>(a_lo(s));
                 float4* __restrict__ br = reinterpret_cast<float4*>(b_raw(s));
                 float4* __restrict__ bl = reinterpret_cast<float4*>(b_lo(s));
+                if (p.a_tmem) {
+                    // A-from-TMEM: thread -> one ROW m of the tile (warp w owns TMEM lanes 32 (w % 4) .. +31); it reads
+                    // the row's 32 k values out of the swizzled tile, optionally turns them into the rank-1 gradient,
+                    // and stores them (and their lo parts) into the stage's TMEM columns
+                    const int row = 32 * (warp & 3) + lane;
+                    const float* af = reinterpret_cast<const float*>(a_raw(s));
+                    float x[32];
+                    if (p.a_mn) {       // [k][32 m] blocks of 4 KB, 32-byte chunk c of row k at position c ^ (k & 3)
+                        const float* blk = af + (row >> 5) * 1024;
+                        const int c32 = (row & 31) >> 3, e = row & 7;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) x[k] = blk[k * 32 + ((c32 ^ (k & 3)) << 3) + e];
+                    } else {            // [128 m][32 k], 16-byte chunk c of row m at position c ^ (m & 7)
+                        const float4* r4 = reinterpret_cast<const float4*>(af + row * 32);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 q = r4[c ^ (row & 7)];
+                            x[4 * c] = q.x; x[4 * c + 1] = q.y; x[4 * c + 2] = q.z; x[4 * c + 3] = q.w;
+                        }
+                    }
+                    if (gen) {
+                        const int m = tile_m * BM + row;
+                        const float gr = m < p.M ? __ldg(p.gen_row + (int64_t)g * p.gen_row_gs + m) : 0.f;
+                        const float* gcl = p.gen_col + (int64_t)g * p.gen_col_gs + (int64_t)(slab0 + it) * BK;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int k = (slab0 + it) * BK + 4 * c;
+                            const float4 cv = k < p.K ? __ldg(reinterpret_cast<const float4*>(gcl) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            x[4 * c] = x[4 * c] > 0.f ? gr * cv.x : 0.f;
+                            x[4 * c + 1] = x[4 * c + 1] > 0.f ? gr * cv.y : 0.f;
+                            x[4 * c + 2] = x[4 * c + 2] > 0.f ? gr * cv.z : 0.f;
+                            x[4 * c + 3] = x[4 * c + 3] > 0.f ? gr * cv.w : 0.f;
+                        }
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + ATM_COL + s * ATM_STRIDE;
+                    tmem_st32(ta, x);
+                    if (PASSES == 3) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) x[k] = x[k] - __uint_as_float(__float_as_uint(x[k]) & 0xFFFFE000u);
+                        tmem_st32(ta + 32, x);
+                    }
+                    tmem_wait_st();
+                }
                 // A: 1024 float4 -> 8 per thread, all loads issued before the first store
-                {
+                if (!p.a_tmem) {
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = ar[t + 128 * j];
@@ -490,6 +578,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                 }
                 if (st4) TC_STAMP(10);
+                if (p.a_tmem) tc_fence_before();            // TMEM stores ordered before the MMA issuer's reads
                 fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
                 if (st4) TC_STAMP(11);
                 mbar_arrive(smem_u32(&splitb[s]));
@@ -757,12 +846,21 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     ORLK_REQUIRE(q->gen_row == nullptr || (q->K % 4 == 0 && aligned16(q->gen_col) && q->gen_col_gs % 4 == 0),
                  "the operand generator needs K % 4 == 0 and 16-byte aligned column factors");
     p.a_mn = q->a_mn ? 1 : 0; p.b_mn = q->b_mn ? 1 : 0;
+    {
+        static int a_tmem = -1;
+        if (a_tmem < 0) { const char* e = getenv("ORLK_TC_A_TMEM"); a_tmem = e ? atoi(e) : 0; }
+        p.a_tmem = a_tmem;
+    }
     p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0; p.b_shared = b_shared ? 1 : 0;
     p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;
     p.trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_TC_TRACE_MODE"); p.trace_mode = e ? atoi(e) : 0; }
 
     tc_ring(NT, q->passes, &p.stages, &p.stage_bytes);
+    if (p.a_tmem) {     // the A stages live in the TMEM columns behind the accumulator: 512 - 288 columns
+        const int max_st = (TMEM_COLS - ATM_COL) / (q->passes == 3 ? 64 : 32);
+        if (p.stages > max_st) p.stages = max_st;
+    }
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
     p.c_tma = 0;
