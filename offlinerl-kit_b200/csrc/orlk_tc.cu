@@ -189,6 +189,23 @@ __device__ __forceinline__ float4 lo_tf32(const float4& v) {
                        v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
 }
 
+// lo = x - trunc_tf32(x) for float4s [i_lo, i_hi) of a raw operand tile, by 128 threads (t = 0..127)
+__device__ __forceinline__ void split_range(const float4* __restrict__ raw, float4* __restrict__ lo, int i_lo, int i_hi, int t) {
+    for (int i0 = i_lo; i0 < i_hi; i0 += 128 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + t + 128 * j;
+            v[j] = i < i_hi ? raw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + t + 128 * j;
+            if (i < i_hi) lo[i] = lo_tf32(v[j]);
+        }
+    }
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -227,6 +244,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int nslabs = min(p.slabs_per_split, total_slabs - slab0);
     const bool want_rowsum = p.rowsum != nullptr && tile_n == 0;
     const bool gen = p.gen_row != nullptr;
+    const int y_from = (p.epi == ORLK_EPI_RELU_MASK) ? p.stages : 0;   // first k-slab the mask warps help to split
     const bool split_runs = PASSES == 3 || gen || p.b_manual != 0 || p.a_tmem != 0;     // the splitter warps process every stage
     constexpr int ATM_STRIDE = PASSES == 3 ? 64 : 32;
 
@@ -247,7 +265,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&splitb[s]), 128);
+            mbar_init(smem_u32(&splitb[s]), (PASSES == 3 && !p.b_manual) ? 256 : 128);     // both warp groups split B
             mbar_init(smem_u32(&empty[s]), 1);
         }
         mbar_init(smem_u32(accum), 1);
@@ -374,6 +392,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 TC_STAMP(8 + it);
             }
         }
+        if (PASSES == 3 && !p.b_manual) {       // their arrivals for the slabs they do not split (first phase of those stages)
+            for (int it = 0; it < y_from && it < nslabs; ++it) mbar_arrive(smem_u32(&splitb[it]));
+        }
         if (p.epi == ORLK_EPI_RELU_MASK) {
             const int w = warp - 6;
             const float* auxg = p.aux + (int64_t)g * p.aux_gs + n0;
@@ -419,11 +440,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             mbar_arrive(smem_u32(maskbar));
         }
+        if (PASSES == 3 && !p.b_manual) {
+            // second splitter group: the larger share of every B tile (the operand split is what paces the mainloop:
+            // one group of four warps needs ~1.1 us per k-slab for A + B, the tensor core 0.85 us)
+            const int ty = threadIdx.x - 192;               // 0..127
+            const int nB4 = NT * BK / 4, nBx = (nB4 / 4) & ~511;
+            for (int it = y_from; it < nslabs; ++it) {
+                const int s = it % STAGES;
+                mbar_wait(smem_u32(&full[s]), (it / STAGES) & 1);
+                split_range(reinterpret_cast<const float4*>(b_raw(s)), reinterpret_cast<float4*>(b_lo(s)), nBx, nB4, ty);
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&splitb[s]));
+            }
+        }
     } else if (warp >= 2) {
         const int t = threadIdx.x - 64;                     // 0..127
         if (split_runs) {
             // -------------------------------------------------------------- operand splitter (+ rank-1 generator)
             const int nB4 = NT * BK / 4;
+            const int nBx = (nB4 / 4) & ~511;               // this group's share of B: it also has all of A to do
             // float4 number t + 128 j of the swizzled A tile sits in row t/8 + 16 j at chunk position t%8, i.e. it holds
             // k = 4c .. 4c+3 of that row with c = (t%8) ^ ((t/8) & 7) - the same c for all eight j.  So the generator
             // needs eight row factors (fixed for the whole CTA) and one float4 of column factors per k-slab.
@@ -564,19 +599,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     }
                 }
-                for (int i0 = 0; PASSES == 3 && !p.b_manual && i0 < nB4; i0 += 128 * 8) {
-                    float4 v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = i0 + t + 128 * j;
-                        v[j] = i < nB4 ? br[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = i0 + t + 128 * j;
-                        if (i < nB4) bl[i] = lo_tf32(v[j]);
-                    }
-                }
+                // the mask warps take [nBx, nB4) - except for the first y_from slabs of a launch whose mask they are building
+                if (PASSES == 3 && !p.b_manual) split_range(br, bl, 0, it < y_from ? nB4 : nBx, t);
                 if (st4) TC_STAMP(10);
                 if (p.a_tmem) tc_fence_before();            // TMEM stores ordered before the MMA issuer's reads
                 fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
@@ -848,7 +872,7 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     p.a_mn = q->a_mn ? 1 : 0; p.b_mn = q->b_mn ? 1 : 0;
     {
         static int a_tmem = -1;
-        if (a_tmem < 0) { const char* e = getenv("ORLK_TC_A_TMEM"); a_tmem = e ? atoi(e) : 0; }
+        if (a_tmem < 0) { const char* e = getenv("ORLK_TC_A_TMEM"); a_tmem = e ? atoi(e) : 1; }
         p.a_tmem = a_tmem;
     }
     p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0; p.b_shared = b_shared ? 1 : 0;
