@@ -20,9 +20,50 @@ FIELDS = ("observations", "actions", "next_observations", "terminals", "rewards"
 class Batch(dict):
     """The dict returned by ``sample``.  The tensors are views of persistent staging memory owned by the buffer
     (overwritten by the next ``sample`` of the same size); ``stable`` tells the policy engines that they may bind
-    their CUDA graphs to these addresses."""
+    their CUDA graphs to these addresses.
+
+    The gather is LAZY: ``sample`` only draws the indices into pinned host memory.  A policy engine whose step graph is
+    bound to this staging memory runs the index upload and the gather as the first two nodes of that graph (one launch
+    for the whole step); any other access to the tensors materialises them first, so the batch always reads as the
+    reference's dict of tensors."""
     stable = True
-    obs2: torch.Tensor = None      # [2B, O]: observations then next_observations (one GEMM operand for the actor)
+
+    def _materialise(self) -> None:
+        st = self.__dict__.get("token")
+        if st is not None and st.pending:
+            st.materialise()
+
+    def __getitem__(self, k):
+        self._materialise()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._materialise()
+        return dict.get(self, k, default)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    @property
+    def obs2(self) -> torch.Tensor:
+        """[2B, O]: observations then next_observations (one GEMM operand for the actor)."""
+        self._materialise()
+        return self.__dict__["_obs2"]
+
+    @property
+    def indices(self) -> torch.Tensor:
+        """The sampled row indices on the device (int64 [B])."""
+        self._materialise()
+        return self.__dict__["_indices"]
+
+    @property
+    def batch_size(self) -> int:
+        return int(self.__dict__["_obs2"].shape[0]) // 2
 
 
 class _Stage:
@@ -46,13 +87,40 @@ class _Stage:
         self.term = torch.zeros(B, 1, dtype=torch.float32, device=dev)
         self.batch = Batch(observations=self.obs2[:B], actions=self.act, next_observations=self.obs2[B:],
                            terminals=self.term, rewards=self.rew)
-        self.batch.obs2 = self.obs2
-        self.batch.indices = self.idx_dev
+        self.batch.__dict__["_obs2"] = self.obs2
+        self.batch.__dict__["_indices"] = self.idx_dev
         self.batch.token = self                    # identity of the staging memory (engines bind their graphs to it)
+        # lazy gather: the indices of the latest sample wait in one pinned buffer until somebody needs the rows
+        self.rt = rt
+        self.pending = False
+        self.idx_pin = torch.empty(B, dtype=torch.int64).pin_memory()
+        self.idx_pin_np = self.idx_pin.numpy()
+        self.idx_pin_ptr = self.idx_pin.data_ptr()
+        self.pin_event = C.c_void_p()
+        L.call("orlk_event_create", C.byref(self.pin_event))
+        self.pin_armed = False
+        self.gather_args = None                    # (table, rows, row_w, O, A) of the owning buffer, set by gather()
         # constant tail of the orlk_replay_sample argument list
         self.out_args = (self.obs2.data_ptr(), self.act.data_ptr(), self.rew.data_ptr(), self.term.data_ptr())
         self.pinned_ptrs = [t.data_ptr() for t in self.idx_host]
         self.idx_dev_ptr = self.idx_dev.data_ptr()
+
+
+    # ---- lazy gather
+    def upload_op(self):
+        """Index upload out of the pinned buffer (a graph node of the engines' fused step, or eager)."""
+        L.call("orlk_memcpy_h2d_async", self.idx_dev_ptr, self.idx_pin_ptr, 8 * self.idx_dev.shape[0], self.rt.cur)
+
+    def gather_op(self):
+        tp, rows, row_w, O, A = self.gather_args
+        L.call("orlk_replay_gather", tp, rows, row_w, O, A, self.idx_dev_ptr, self.idx_dev.shape[0], *self.out_args, self.rt.cur)
+
+    def materialise(self) -> None:
+        self.pending = False
+        self.upload_op()
+        L.call("orlk_event_record", self.pin_event, self.rt.cur)
+        self.pin_armed = True
+        self.gather_op()
 
 
 class ReplayBuffer:
@@ -193,14 +261,12 @@ class ReplayBuffer:
         idx = np.ascontiguousarray(indices, dtype=np.int64)
         B = idx.shape[0]
         st = self._stages.get(B) or self._stage(B)
-        s = st.slot
-        st.slot = (s + 1) % st.N_SLOTS
-        # one host call: wait for the slot's previous upload, refill the pinned slot, upload, re-arm, gather
-        rc = self._sample_fn(self._table_ptr, self._table_rows, self._row_w, self._O, self.action_dim, idx.ctypes.data,
-                             st.pinned_ptrs[s], st.idx_dev_ptr, st.events[s], st.armed[s], B, *st.out_args, rt.cur)
-        if rc:
-            L.check(rc, "orlk_replay_sample")
-        st.armed[s] = 1
+        if st.pin_armed:            # an eager upload out of the pinned buffer may still be queued
+            L.call("orlk_event_sync", st.pin_event)
+            st.pin_armed = False
+        st.idx_pin_np[:] = idx
+        st.gather_args = (self._table_ptr, self._table_rows, self._row_w, self._O, self.action_dim)
+        st.pending = True           # the rows are gathered by the first consumer (Batch docstring)
         return st.batch
 
     def gather_device(self, idx_dev: torch.Tensor) -> Batch:
@@ -210,6 +276,7 @@ class ReplayBuffer:
             self._sync_mirror()
         B = int(idx_dev.shape[0])
         st = self._stage(B)
+        st.pending = False
         L.call("orlk_replay_gather", self._table.data_ptr(), len(self.observations), self.row_width, self._obs_dim,
                self.action_dim, idx_dev.data_ptr(), B, st.obs2.data_ptr(), st.act.data_ptr(), st.rew.data_ptr(),
                st.term.data_ptr(), rt.cur)

@@ -138,6 +138,13 @@ class Learner:
     def run(self, key: str) -> List[float]:
         """Replay the step and wait for it; returns the loss block as Python floats."""
         plan = self.plans[key]
+        tok = getattr(self, "_bound_token", None)
+        if tok is not None and getattr(tok, "pending", False):
+            if self.use_graph:      # index upload + gather ride in front of the step, inside the same graph launch
+                plan = self._with_gather(key, plan, tok)
+                tok.pending = False
+            else:
+                tok.materialise()
         if self.use_graph:
             if plan.graph is None:
                 plan.capture()
@@ -150,8 +157,25 @@ class Learner:
         self.steps_done += 1
         return self.loss_np.tolist()
 
+    def _with_gather(self, key: str, plan: Plan, tok) -> Plan:
+        """The step plan with the replay buffer's pending index upload and row gather as its first two launches."""
+        cache = self.__dict__.setdefault("_gather_plans", {})
+        k = (key, id(tok), tok.gather_args)
+        p2 = cache.get(k)
+        if p2 is None:
+            p2 = Plan(self.rt, getattr(plan, "name", key) + "+gather")
+            head = [("idx_h2d", tok.upload_op), ("gather", tok.gather_op)]
+            p2.ops = head + list(plan.ops)
+            p2.flat_ops = head + list(plan.flat_ops)
+            p2.keep = list(plan.keep) + [tok, plan]
+            cache[k] = p2
+        return p2
+
     def enqueue(self, key: str) -> None:
         """Launch a step without waiting for it (used by the device-resident benchmark loop)."""
+        tok = getattr(self, "_bound_token", None)
+        if tok is not None and getattr(tok, "pending", False):
+            tok.materialise()
         plan = self.plans[key]
         if self.use_graph:
             plan.launch()

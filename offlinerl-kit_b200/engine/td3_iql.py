@@ -24,16 +24,22 @@ class _BatchMixin:
         self.rew = rt.zeros(B, 1)
         self.term = rt.zeros(B, 1)
         self._bound_ptrs = None
+        self._bound_token = None
 
     def bind_batch(self, batch) -> None:
+        tok = getattr(batch, "token", None)
+        if tok is not None and tok is self._bound_token:
+            return              # the buffer's staging memory this engine's graphs are already bound to (gather stays lazy)
         obs2 = getattr(batch, "obs2", None)
         if obs2 is not None and getattr(batch, "stable", False) and obs2.shape[0] == 2 * self.B:
             ptrs = (obs2.data_ptr(), batch["actions"].data_ptr(), batch["rewards"].data_ptr(), batch["terminals"].data_ptr())
             if self._bound_ptrs is None and not self.plans:
                 self.obs2, self.act, self.rew, self.term = obs2, batch["actions"], batch["rewards"], batch["terminals"]
                 self._bound_ptrs = ptrs
+                self._bound_token = tok
                 return
             if ptrs == self._bound_ptrs:
+                self._bound_token = tok
                 return
         B = self.B
         f32 = lambda x: torch.as_tensor(x, device=self.dev, dtype=torch.float32)

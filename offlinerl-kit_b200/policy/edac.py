@@ -57,7 +57,7 @@ class EDACPolicy(BasePolicy):
         return self._engine
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
-        out = self.engine(int(batch["observations"].shape[0])).step(batch, noise)
+        out = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)
         if self._is_auto_alpha:
             self._alpha = torch.tensor([out["alpha"]], device=self.actor.device)
         return out

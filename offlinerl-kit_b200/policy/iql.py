@@ -52,4 +52,4 @@ class IQLPolicy(BasePolicy):
         return self._engine
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
-        return self.engine(int(batch["observations"].shape[0])).step(batch, noise)
+        return self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

@@ -90,7 +90,7 @@ class SACPolicy(BasePolicy):
                 self._alpha_tensor = value      # a plain float alpha stays a float, as in the reference
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
-        eng = self.engine(int(batch["observations"].shape[0]))
+        eng = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0])))
         out = eng.step(batch, noise)
         self._after_step(out)
         return out

@@ -56,4 +56,4 @@ class TD3BCPolicy(BasePolicy):
         return self._engine
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
-        return self.engine(int(batch["observations"].shape[0])).step(batch, noise)
+        return self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

@@ -34,3 +34,48 @@ def test_cql_eager_equals_graph():
     p2 = run_golden_steps(g, tol=TOL, use_graph=False)
     for (k, a), (_, b) in zip(p1.state_dict().items(), p2.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("name", ["cql_hc", "td3bc_walker", "iql_walker"])
+def test_lazy_gather_inside_step_graph_equals_eager_gather(name):
+    """``sample`` only draws indices; the engine whose graph is bound to the buffer's staging memory runs the index upload
+    and the row gather as the first nodes of the step graph.  Touching the batch first (eager gather) must give the
+    same losses and parameters bit for bit, and a batch that was never read must still hold the sampled rows afterwards."""
+    import numpy as np
+    import torch
+    from tests.gpu_common import build_policy, make_buffer
+    g = Golden(name)
+    m = g.meta
+
+    def run(touch):
+        torch.manual_seed(1)
+        np.random.seed(1)
+        pol = build_policy(m)
+        pol.train()
+        buf, data = make_buffer(g)
+        np.random.seed(5)
+        losses = []
+        for t in range(6):
+            b = buf.sample(m["B"])
+            if touch or t == 0:
+                _ = b["observations"]               # materialises (t == 0: the first step binds the engine eagerly anyway)
+            else:
+                assert b.token.pending              # nothing has gathered yet
+            losses.append(pol.learn(b))
+            assert not b.token.pending
+        return pol, buf, data, losses, b
+
+    torch.cuda.manual_seed_all(3)
+    p1, buf1, data, l1, b1 = run(touch=True)
+    p2, buf2, _, l2, b2 = run(touch=False)
+    # the Philox noise stream depends only on (seed, step counter): both runs draw the same noise
+    for a, b in zip(l1, l2):
+        assert a == b, (a, b)
+    for (k, x), (_, y) in zip(p1.state_dict().items(), p2.state_dict().items()):
+        assert torch.equal(x, y), k
+    np.random.seed(5)
+    for _ in range(5):
+        np.random.randint(0, buf2._size, size=m["B"])
+    idx = np.random.randint(0, buf2._size, size=m["B"])
+    assert np.array_equal(b2["observations"].cpu().numpy(), data["observations"][idx])
+    assert np.array_equal(b2.indices.cpu().numpy(), idx)
