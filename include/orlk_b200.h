@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 12
+#define ORLK_ABI_VERSION 13
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -254,6 +254,14 @@ int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off,
 /* Backward of the above with eps fixed:
  *   dL/da = sum_{j<n_da} dA[j*da_gs + m*ld_da + i] (one slab per critic / ensemble member);
  *   dhead[m, 0:A) = dmu, dhead[m, A:2A) = draw (clamp-gated). glp[m] = dLoss/dlogp[m]. */
+/* Entry of the actor's backward pass in one launch (sac.py:111-119 / cql.py:93-99 autograd): per row m
+ *   dL/da[m] = sum_{c<n_c} dZ0[c][m][:] . W0[c][:, col0:col0+A]   (W0[c] is [Kc][ld_w0], the critics' first layers),
+ *   dhead[m] = backward of orlk_tanh_gauss_sample (as orlk_tanh_gauss_bwd),
+ *   dZlast[m][n] = (dhead[m][:] . Wh[:, n]) * (Hlast[m][n] > 0)     (Wh is the actor head [2A][Ka]).
+ * Replaces orlk_skinny_fwd (d/da) + orlk_tanh_gauss_bwd + orlk_skinny_dgrad. */
+int orlk_actor_bwd_entry(const float* dZ0, int64_t dz_gs, int Kc, int n_c, const float* W0, int64_t w0_gs, int ld_w0, int col0,
+                         const float* head, const float* eps, const float* act, int64_t ld_act, const float* glp, int M, int A,
+                         float* dhead, const float* Wh, int Ka, const float* Hlast, float* dZlast, void* stream);
 int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, const float* act, int64_t ld_act,
                         const float* dA, int n_da, int64_t da_gs, int64_t ld_da, const float* glp, int M, int A,
                         float* dhead, int64_t ld_dhead, void* stream);

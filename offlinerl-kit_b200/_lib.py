@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -85,6 +85,7 @@ _PROTOS = {
     "orlk_replay_sample": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
     "orlk_gemm_tiny": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_tiny_init": [],
+    "orlk_actor_bwd_entry": [_P, _L, _I, _I, _P, _L, _I, _I, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _P, _P, _P],
     "orlk_gemm_chain": [_P, _I, _I, _I, _I, _P], "orlk_gemm_chain_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],
     "orlk_sizeof_tc_gemm": [],

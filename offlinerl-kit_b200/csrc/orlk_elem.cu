@@ -222,6 +222,106 @@ __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head
     }
 }
 
+// Entry of the actor's backward pass in one launch (policy improvement step of SAC / CQL / MOPO), one warp per row m:
+//   dL/da[m]      = sum_c dZ0_c[m][:] . W0_c[:, O:O+A]            (gradient of the critics w.r.t. the sampled action)
+//   dhead[m]      = tanh-Gaussian backward                          (same maths as k_tanh_gauss_bwd)
+//   dZlast[m][n]  = (dhead[m][:] . Wh[:, n]) * (Hlast[m][n] > 0)   (through the actor's head into its last hidden layer)
+// i.e. the skinny d/da product, the sampler backward and the head dgrad, which otherwise are three 3-4 us launches.
+template <int AM>       // AM >= A: compile-time bound of the action dimension (8 or 32)
+__global__ void __launch_bounds__(256)
+k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c, const float* __restrict__ W0, int64_t w0_gs,
+                  int ld_w0, int col0, const float* __restrict__ head, const float* __restrict__ eps,
+                  const float* __restrict__ act, int64_t ld_act, const float* __restrict__ glp, int M, int A,
+                  float* __restrict__ dhead, const float* __restrict__ Wh, int Ka, const float* __restrict__ Hlast,
+                  float* __restrict__ dZlast) {
+    orlk::pdl_enter();
+    extern __shared__ float sm[];
+    float* w0s = sm;                                    // [n_c][Kc][A]   action columns of the critics' first layers
+    float* whs = sm + (size_t)n_c * Kc * A;             // [2A][Ka]       the actor's head
+    for (int ck = threadIdx.x; ck < n_c * Kc; ck += blockDim.x) {      // one (critic, k) pair: A consecutive floats
+        const int c = ck / Kc, k = ck - c * Kc;
+        const float* src = W0 + c * w0_gs + (int64_t)k * ld_w0 + col0;
+#pragma unroll
+        for (int a = 0; a < AM; ++a)
+            if (a < A) w0s[ck * A + a] = __ldg(src + a);
+    }
+    if (aligned16(Wh) && ((2 * A * Ka) & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(Wh);
+        float4* d4 = reinterpret_cast<float4*>(whs);        // whs offset n_c*Kc*A floats: 16-byte aligned when that is a multiple of 4
+        if ((((size_t)n_c * Kc * A) & 3) == 0) {
+            for (int i = threadIdx.x; i < (2 * A * Ka) >> 2; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < 2 * A * Ka; i += blockDim.x) whs[i] = __ldg(Wh + i);
+        }
+    } else {
+        for (int i = threadIdx.x; i < 2 * A * Ka; i += blockDim.x) whs[i] = __ldg(Wh + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    // ---- d/da: lanes split k, then a warp sum per action dimension
+    float da[AM];
+#pragma unroll
+    for (int a = 0; a < AM; ++a) da[a] = 0.f;
+    for (int c = 0; c < n_c; ++c) {
+        const float* z = dZ0 + c * dz_gs + (int64_t)m * Kc;
+        const float* w = w0s + (size_t)c * Kc * A;
+        for (int k = lane; k < Kc; k += 32) {
+            const float zv = __ldg(z + k);
+#pragma unroll
+            for (int a = 0; a < AM; ++a)
+                if (a < A) da[a] = fmaf(zv, w[k * A + a], da[a]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < AM; ++a)
+        if (a < A) da[a] = warp_sum(da[a]);
+    // ---- sampler backward: lane i < A owns action dimension i
+    float dmu = 0.f, draw = 0.f;
+    if (lane < A) {
+        const int i = lane;
+        const float* h = head + (int64_t)m * 2 * A;
+        const float g = glp ? glp[m] : 0.f;
+        const float raw = h[A + i];
+        const float ls = fminf(fmaxf(raw, LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sigma = expf(ls);
+        const float e = eps[(int64_t)m * A + i];
+        const float a = act[(int64_t)m * ld_act + i];
+        const float om = 1.f - a * a;
+        float dai = 0.f;
+#pragma unroll
+        for (int q = 0; q < AM; ++q)
+            if (q == i) dai = da[q];
+        const float t = 2.f * a * om / (om + 1e-6f);
+        const float du = dai * om + g * t;
+        dmu = du;
+        draw = du * sigma * e - g;
+        if (!(raw >= LOG_SIG_MIN && raw <= LOG_SIG_MAX)) draw = 0.f;
+        dhead[(int64_t)m * 2 * A + i] = dmu;
+        dhead[(int64_t)m * 2 * A + A + i] = draw;
+    }
+    // ---- head dgrad: every lane needs all 2A head gradients
+    float acc[8];
+    for (int n0 = 0; n0 < Ka; n0 += 256) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float gm = __shfl_sync(0xffffffffu, dmu, j), gr = __shfl_sync(0xffffffffu, draw, j);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = n0 + lane + 32 * q;
+                if (n < Ka) acc[q] = fmaf(gm, whs[j * Ka + n], fmaf(gr, whs[(A + j) * Ka + n], acc[q]));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int n = n0 + lane + 32 * q;
+            if (n < Ka) dZlast[(int64_t)m * Ka + n] = __ldg(Hlast + (int64_t)m * Ka + n) > 0.f ? acc[q] : 0.f;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ scalar Adam
 __device__ float scalar_adam(float p, float g, float* mv, const OrlkAdamGroup& grp) {
     const int t = grp.step + 1;
@@ -511,6 +611,22 @@ int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, co
     orlk::launch(k_tanh_gauss_bwd, (M + 127) / 128, 128, 0, (cudaStream_t)stream, head, ld_head, eps, act, ld_act, dA, n_da, da_gs, ld_da,
                                                                        glp, M, A, dhead, ld_dhead);
     return check_launch("k_tanh_gauss_bwd");
+}
+
+int orlk_actor_bwd_entry(const float* dZ0, int64_t dz_gs, int Kc, int n_c, const float* W0, int64_t w0_gs, int ld_w0, int col0,
+                         const float* head, const float* eps, const float* act, int64_t ld_act, const float* glp, int M, int A,
+                         float* dhead, const float* Wh, int Ka, const float* Hlast, float* dZlast, void* stream) {
+    ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && Kc > 0 && Ka > 0 && n_c > 0, "sizes");
+    ORLK_REQUIRE(dZ0 && W0 && head && eps && act && dhead && Wh && Hlast && dZlast, "pointers");
+    const size_t smem = sizeof(float) * ((size_t)n_c * Kc * A + (size_t)2 * A * Ka);
+    ORLK_REQUIRE(smem <= 48 * 1024, "first-layer action columns + head must fit 48 KB of shared memory");
+    if (A <= 8)
+        orlk::launch(k_actor_bwd_entry<8>, (M + 7) / 8, 256, smem, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0, col0,
+                     head, eps, act, ld_act, glp, M, A, dhead, Wh, Ka, Hlast, dZlast);
+    else
+        orlk::launch(k_actor_bwd_entry<MAX_A>, (M + 7) / 8, 256, smem, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0,
+                     col0, head, eps, act, ld_act, glp, M, A, dhead, Wh, Ka, Hlast, dZlast);
+    return check_launch("k_actor_bwd_entry");
 }
 
 int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, int B, float* scalars, int auto_alpha,

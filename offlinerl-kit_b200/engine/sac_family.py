@@ -9,6 +9,7 @@ back-propagation from the critic losses, and the actor forward over the 10x repe
 evaluated once per distinct state and sampled 10 times).
 """
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -18,7 +19,7 @@ from .. import _lib as L
 from .core import Mat, Plan
 from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
                       emit_wgrad_adam, linears_of, make_gradbuf)
-from .nets import ParamSet, dgrad_problem, pick_cfg
+from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem, pick_cfg
 
 # loss block layout (floats)
 LS_ACTOR, LS_ALPHA_LOSS, LS_ALPHA = 0, 1, 2
@@ -164,17 +165,30 @@ class TwinCriticLearner(Learner):
                 dq.data_ptr(), B, self.glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
         plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
         emit_head_dgrad(rt, plan, cr, "A.critic")
-        # dL/da = sum over the two critics of dZ1 . W1[:, O:O+A]
-        if getattr(cr, "pending_head_dgrad", False):       # fused chain: head dgrad, hidden dgrads and d/da in one launch
-            emit_hidden_dgrad(rt, plan, cr, "A.critic", dact=(self.dA, O, A))
-        else:
-            emit_hidden_dgrad(rt, plan, cr, "A.critic")
-            emit_dact(rt, plan, cr, self.dA, O, A, "A.critic")
         head = ar.out[0]
-        bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), 2, B * A, A,
-                 self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
-        plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
-        emit_head_dgrad(rt, plan, ar, "A.actor")
+        c0, ah = cr.ps.layers[0], ar.ps.layers[ar.nh]
+        fuse_entry = (not getattr(cr, "pending_head_dgrad", False) and c0.layout == "oi" and ah.layout == "oi" and ar.G == 1
+                      and B < TC_MIN_ROWS and ar.dZT[ar.nh - 1] is None
+                      and 4 * (cr.G * c0.out_dim * A + 2 * A * ah.in_dim) <= 48 * 1024
+                      and os.environ.get("ORLK_FUSE_ACTOR_BWD", "1") != "0")
+        if fuse_entry:
+            # d/da through the critics' first layers, the sampler backward and the actor's head dgrad in ONE launch
+            emit_hidden_dgrad(rt, plan, cr, "A.critic")
+            eargs = (cr.dZ[0].data_ptr(), B * c0.out_dim, c0.out_dim, cr.G, cr.ps.w(0, 0), c0.w_gs, c0.in_dim, O,
+                     head.data_ptr(), self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.glp.data_ptr(), B, A,
+                     ar.dOut.data_ptr(), ar.ps.w(ar.nh, 0), ah.in_dim, ar.H[ar.nh - 1].data_ptr(), ar.dZ[ar.nh - 1].data_ptr())
+            plan.add("A.actor.bwd_entry", lambda: L.call("orlk_actor_bwd_entry", *eargs, rt.cur))
+        else:
+            # dL/da = sum over the two critics of dZ1 . W1[:, O:O+A]
+            if getattr(cr, "pending_head_dgrad", False):       # fused chain: head dgrad, hidden dgrads and d/da in one launch
+                emit_hidden_dgrad(rt, plan, cr, "A.critic", dact=(self.dA, O, A))
+            else:
+                emit_hidden_dgrad(rt, plan, cr, "A.critic")
+                emit_dact(rt, plan, cr, self.dA, O, A, "A.critic")
+            bargs = (head.data_ptr(), 2 * A, self.eps_actor.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.dA.data_ptr(), 2, B * A, A,
+                     self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
+            plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
+            emit_head_dgrad(rt, plan, ar, "A.actor")
         emit_hidden_dgrad(rt, plan, ar, "A.actor")
         emit_wgrad_adam(rt, plan, ar, [obs], self.gb_actor, self.groups_ptr, "A.actor", polyak=False)
 
