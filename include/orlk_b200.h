@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 13
+#define ORLK_ABI_VERSION 14
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -254,6 +254,22 @@ int orlk_tanh_gauss_sample(const float* head, int64_t ld_head, int head_row_off,
 /* Backward of the above with eps fixed:
  *   dL/da = sum_{j<n_da} dA[j*da_gs + m*ld_da + i] (one slab per critic / ensemble member);
  *   dhead[m, 0:A) = dmu, dhead[m, A:2A) = draw (clamp-gated). glp[m] = dLoss/dlogp[m]. */
+/* Actor head + reparameterised sampling in one launch (ActorProb.forward + TanhNormal.rsample / log_prob,
+ * modules/actor_module.py + dist_module.py; cql.py:108-140 uses one head pass three times):
+ *   head[m] = X[m] . W^T + b  (2A outputs: mu | raw log-std), then for every use whose head-row range [r0, r1) contains m and
+ *   every repeat r < rep:  o = (m - r0) * rep + r,  a = tanh(mu + sigma * eps[o]),  act[o], logp[o], xout[o] = [obs[m - r0] | .]
+ * (xout row o gets the obs_dim observation columns; act usually points at column obs_dim of the same row). */
+typedef struct OrlkSampleUse {
+    int32_t r0, r1, rep, obs_dim;
+    const float* eps;     /* [rows * rep, A] or NULL (deterministic: a = tanh(mu)) */
+    float* act; int64_t ld_act;
+    float* logp;          /* [rows * rep] or NULL */
+    const float* obs; int64_t ld_obs;
+    float* xout; int64_t ld_x;
+} OrlkSampleUse;
+int orlk_sizeof_sample_use(void);
+int orlk_head_sample(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b, float* head, int M, int K, int A,
+                     const OrlkSampleUse* uses_host, int n_uses, void* stream);
 /* Entry of the actor's backward pass in one launch (sac.py:111-119 / cql.py:93-99 autograd): per row m
  *   dL/da[m] = sum_{c<n_c} dZ0[c][m][:] . W0[c][:, col0:col0+A]   (W0[c] is [Kc][ld_w0], the critics' first layers),
  *   dhead[m] = backward of orlk_tanh_gauss_sample (as orlk_tanh_gauss_bwd),

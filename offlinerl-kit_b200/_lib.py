@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -43,6 +43,12 @@ class AdamDesc(C.Structure):
                 ("n", C.c_int64), ("g_split_stride", C.c_int64), ("g_splits", C.c_int32), ("group", C.c_int32),
                 ("wd", C.c_float), ("block_start", C.c_int32), ("flags", C.c_int32), ("cols", C.c_int32),
                 ("pT", C.c_void_p)]
+
+
+class SampleUse(C.Structure):
+    _fields_ = [("r0", C.c_int32), ("r1", C.c_int32), ("rep", C.c_int32), ("obs_dim", C.c_int32),
+                ("eps", C.c_void_p), ("act", C.c_void_p), ("ld_act", C.c_int64), ("logp", C.c_void_p),
+                ("obs", C.c_void_p), ("ld_obs", C.c_int64), ("xout", C.c_void_p), ("ld_x", C.c_int64)]
 
 
 class TcGemm(C.Structure):
@@ -85,6 +91,7 @@ _PROTOS = {
     "orlk_replay_sample": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
     "orlk_gemm_tiny": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_tiny_init": [],
+    "orlk_head_sample": [_P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _I, _P], "orlk_sizeof_sample_use": [],
     "orlk_actor_bwd_entry": [_P, _L, _I, _I, _P, _L, _I, _I, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _P, _P, _P],
     "orlk_gemm_chain": [_P, _I, _I, _I, _I, _P], "orlk_gemm_chain_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],
@@ -148,7 +155,7 @@ def load() -> C.CDLL:
         raise OrlkError(f"ABI mismatch: library {lib.orlk_abi_version()} vs binding {ABI_VERSION}; rebuild")
     for fn, st in (("orlk_sizeof_gemm_desc", GemmDesc), ("orlk_sizeof_adam_desc", AdamDesc),
                    ("orlk_sizeof_adam_group", AdamGroup), ("orlk_sizeof_concat_seg", ConcatSeg),
-                   ("orlk_sizeof_tc_gemm", TcGemm)):
+                   ("orlk_sizeof_tc_gemm", TcGemm), ("orlk_sizeof_sample_use", SampleUse)):
         if getattr(lib, fn)() != C.sizeof(st):
             raise OrlkError(f"struct size mismatch for {st.__name__}: C {getattr(lib, fn)()} vs ctypes {C.sizeof(st)}")
     _lib = lib

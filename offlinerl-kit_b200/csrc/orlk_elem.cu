@@ -222,6 +222,86 @@ __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head
     }
 }
 
+// Actor head + reparameterised sampling in one launch, one warp per head row m:
+//   head[m] = X[m] . Wh^T + bh   (mu | log-std raw, 2A outputs), then for every use u whose row range contains m and every
+//   repeat r:  a = tanh(mu + sigma * eps[o]),  logp[o],  X_out[o] = [obs[j] | a]   with j = m - r0, o = j * rep + r
+// (exactly k_skinny_fwd followed by k_tanh_gauss_sample per use; CQL's critic phase has three uses of one head pass).
+struct SampleUses {
+    OrlkSampleUse u[4];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
+              float* __restrict__ head, int M, int K, int A, const __grid_constant__ SampleUses U) {
+    orlk::pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const int NS = 2 * A;
+    float acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    const float4* x4 = reinterpret_cast<const float4*>(X + (int64_t)m * ldx);
+    const int K4 = K >> 2;
+#pragma unroll 2
+    for (int k = lane; k < K4; k += 32) {
+        const float4 xv = x4[k];
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            if (n < NS) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw) + k);
+                acc[n] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[n]))));
+            }
+    }
+    float mu = 0.f, raw = 0.f;                          // lane i < A keeps its own action dimension
+#pragma unroll
+    for (int n = 0; n < 16; ++n)
+        if (n < NS) {
+            const float v = warp_sum(acc[n]) + (b ? __ldg(b + n) : 0.f);
+            if (n == lane) mu = v;
+            if (n == lane + A) raw = v;
+            if (lane == 0) head[(int64_t)m * NS + n] = v;
+        }
+    // four repeats per pass: lane = 8 * (repeat within the pass) + action dimension (A <= 8)
+    const int gi = lane & 7, gr = lane >> 3;
+    const float mu_i = __shfl_sync(0xffffffffu, mu, gi), raw_i = __shfl_sync(0xffffffffu, raw, gi);
+    const float ls = fminf(fmaxf(raw_i, LOG_SIG_MIN), LOG_SIG_MAX);
+    const float sigma = expf(ls);
+    const float lsig = logf(sigma);
+    for (int q = 0; q < U.n; ++q) {
+        const OrlkSampleUse& u = U.u[q];
+        if (m < u.r0 || m >= u.r1) continue;            // warp-uniform
+        const int j = m - u.r0;
+        const float* ob = u.xout ? u.obs + (int64_t)j * u.ld_obs : nullptr;
+        for (int r0 = 0; r0 < u.rep; r0 += 4) {
+            const int r = r0 + gr;
+            const bool on = r < u.rep && gi < A;
+            const int64_t o = (int64_t)j * u.rep + r;
+            float t = 0.f;
+            if (on) {
+                const float uu = u.eps ? fmaf(sigma, u.eps[o * A + gi], mu_i) : mu_i;
+                const float a = tanhf(uu);
+                const float d = uu - mu_i;
+                t = -(d * d) / (2.f * sigma * sigma) - lsig - HALF_LOG_2PI - logf((1.f - a * a) + 1e-6f);
+                u.act[o * u.ld_act + gi] = a;
+            }
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            if (gi == 0 && r < u.rep && u.logp) u.logp[o] = t;
+            if (u.xout) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    if (r0 + rr >= u.rep) break;
+                    float* xo = u.xout + ((int64_t)j * u.rep + r0 + rr) * u.ld_x;
+                    for (int c = lane; c < u.obs_dim; c += 32) xo[c] = ob[c];
+                }
+            }
+        }
+    }
+}
+
 // Entry of the actor's backward pass in one launch (policy improvement step of SAC / CQL / MOPO), one warp per row m:
 //   dL/da[m]      = sum_c dZ0_c[m][:] . W0_c[:, O:O+A]            (gradient of the critics w.r.t. the sampled action)
 //   dhead[m]      = tanh-Gaussian backward                          (same maths as k_tanh_gauss_bwd)
@@ -611,6 +691,22 @@ int orlk_tanh_gauss_bwd(const float* head, int64_t ld_head, const float* eps, co
     orlk::launch(k_tanh_gauss_bwd, (M + 127) / 128, 128, 0, (cudaStream_t)stream, head, ld_head, eps, act, ld_act, dA, n_da, da_gs, ld_da,
                                                                        glp, M, A, dhead, ld_dhead);
     return check_launch("k_tanh_gauss_bwd");
+}
+
+int orlk_head_sample(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b, float* head, int M, int K, int A,
+                     const OrlkSampleUse* uses_host, int n_uses, void* stream) {
+    ORLK_REQUIRE(M > 0 && K > 0 && K % 4 == 0 && A > 0 && A <= 8, "sizes (K % 4 == 0, A <= 8)");
+    ORLK_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0 && aligned16(X) && aligned16(W), "16-byte aligned rows");
+    ORLK_REQUIRE(uses_host != nullptr && n_uses >= 1 && n_uses <= 4 && head != nullptr, "1..4 uses");
+    SampleUses U;
+    U.n = n_uses;
+    for (int i = 0; i < n_uses; ++i) {
+        ORLK_REQUIRE(uses_host[i].rep >= 1 && uses_host[i].act != nullptr && (uses_host[i].xout == nullptr || uses_host[i].obs != nullptr),
+                     "use");
+        U.u[i] = uses_host[i];
+    }
+    orlk::launch(k_head_sample, (M + 7) / 8, 256, 0, (cudaStream_t)stream, X, ldx, W, ldw, b, head, M, K, A, U);
+    return check_launch("k_head_sample");
 }
 
 int orlk_actor_bwd_entry(const float* dZ0, int64_t dz_gs, int Kc, int n_c, const float* W0, int64_t w0_gs, int ld_w0, int col0,

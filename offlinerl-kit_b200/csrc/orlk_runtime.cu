@@ -49,6 +49,7 @@ int orlk_sizeof_gemm_desc(void) { return (int)sizeof(OrlkGemmDesc); }
 int orlk_sizeof_adam_desc(void) { return (int)sizeof(OrlkAdamDesc); }
 int orlk_sizeof_adam_group(void) { return (int)sizeof(OrlkAdamGroup); }
 int orlk_sizeof_concat_seg(void) { return (int)sizeof(OrlkConcatSeg); }
+int orlk_sizeof_sample_use(void) { return (int)sizeof(OrlkSampleUse); }
 
 int orlk_device_info(int device, int* out4) {
     ORLK_REQUIRE(out4 != nullptr, "out4 is NULL");

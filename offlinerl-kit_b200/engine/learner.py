@@ -304,11 +304,12 @@ def chainable(run: "MlpRun", with_head: bool) -> bool:
 NARROW_MIN_ROWS = int(os.environ.get("ORLK_NARROW_MIN_ROWS", "1024"))
 
 
-def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str) -> None:
-    """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row)."""
+def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: str, skip_head: bool = False) -> None:
+    """Hidden layers (+bias+ReLU fused) as tcgen05 or grouped SIMT GEMMs, then the narrow head (warp per row).
+    ``skip_head``: the caller evaluates the head itself (fused with the sampler, orlk_head_sample)."""
     ps, G, M = run.ps, run.G, run.M
     plan.keep += [run, [x.keep for x in X]]
-    if chainable(run, with_head=run.has_head) and all(h is None for h in run.HT):
+    if not skip_head and chainable(run, with_head=run.has_head) and all(h is None for h in run.HT):
         # the whole pass (hidden layers + head) as fused chain launches: one cluster per 32-row strip and member
         n_st = run.nh + (1 if run.has_head else 0)
         chains = []
@@ -355,7 +356,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
                              YT=run.ht(l, g)) for g in range(G)]
         # (the first layer sees raw observations: fp32-grade even in the single-pass mode)
         plan.add(f"{tag}.fwd{l}", rt.gemm(probs, pick_cfg(M * G, lay.out_dim, rows_per_problem=M), passes=(3 if (l == 0 and run.passes) else run.passes)))
-    if run.has_head:
+    if run.has_head and not skip_head:
         emit_head_forward(rt, plan, run, tag)
 
 

@@ -141,6 +141,27 @@ class TwinCriticLearner(Learner):
                 obs.ptr, obs.ld, O, X.ptr, X.ld)
         plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
 
+    def _can_fuse_head_sample(self, run: MlpRun) -> bool:
+        head = run.ps.layers[run.nh]
+        return (run.has_head and head.layout == "oi" and run.G == 1 and self.A <= 8 and head.in_dim % 4 == 0
+                and run.M < TC_MIN_ROWS and os.environ.get("ORLK_FUSE_HEAD_SAMPLE", "1") != "0")
+
+    def _emit_head_sample(self, plan: Plan, tag: str, run: MlpRun, uses) -> None:
+        """Actor head + all the samplers that read it, one launch.  uses: (head_row0, head_row1, rep, eps, X, logp, obs)."""
+        O, A = self.O, self.A
+        head = run.ps.layers[run.nh]
+        arr = (L.SampleUse * len(uses))()
+        for i, (r0, r1, rep, eps, X, logp, obs) in enumerate(uses):
+            u = arr[i]
+            u.r0, u.r1, u.rep, u.obs_dim = r0, r1, rep, O
+            u.eps, u.act, u.ld_act, u.logp = eps.data_ptr(), X.ptr + 4 * O, X.ld, logp.data_ptr()
+            u.obs, u.ld_obs, u.xout, u.ld_x = obs.ptr, obs.ld, X.ptr, X.ld
+        hin = run.H[run.nh - 1]
+        args = (hin.data_ptr(), head.in_dim, run.ps.w(run.nh, 0, run.store), head.in_dim, run.ps.b(run.nh, 0, run.store),
+                run.out.data_ptr(), run.M, head.in_dim, A, arr, len(uses))
+        plan.keep.append(arr)
+        plan.add(tag, lambda: L.call("orlk_head_sample", *args, self.rt.cur))
+
     def _emit_actor_update(self, plan: Plan, clamp01: bool, beside_forward=None) -> None:
         """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)
         ``beside_forward``: a (label, launch) that is independent of the actor forward (the noise fill) and runs on a
@@ -153,11 +174,15 @@ class TwinCriticLearner(Learner):
             plan.branch(1)
             plan.add(*beside_forward)
             plan.branch(0)
-        emit_forward(rt, plan, ar, [obs], "A.actor")
+        fuse_hs = self._can_fuse_head_sample(ar)
+        emit_forward(rt, plan, ar, [obs], "A.actor", skip_head=fuse_hs)
         if beside_forward is not None:
             plan.join()
         Xa = Mat.of(self.Xa)
-        self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
+        if fuse_hs:
+            self._emit_head_sample(plan, "A.actor.head_sample", ar, [(0, B, 1, self.eps_actor, Xa, self.logp_a, obs)])
+        else:
+            self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
         emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
         q, dq = cr.out, cr.dOut      # [2, B, 1]
         args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
@@ -265,19 +290,26 @@ class CQLLearner(TwinCriticLearner):
         obs2 = Mat.of(self.obs2)
         obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
         ab = self.run_actor_b
-        emit_forward(rt, plan, ab, [obs2], "C.actor")
+        fuse_hs = self._can_fuse_head_sample(ab)
+        emit_forward(rt, plan, ab, [obs2], "C.actor", skip_head=fuse_hs)
         head = ab.out[0]
         Xt, Xc = Mat.of(self.Xt), Mat.of(self.Xc)
         v = self.noise_views
-        # the three samplers and the concat write disjoint row blocks of Xt / Xc: four parallel branches
+        # the samplers and the concat write disjoint row blocks of Xt / Xc: parallel branches
         plan.fork()
         plan.branch(1)
-        self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
-        plan.branch(2)
-        self._emit_sample(plan, "C.sample_pi", head, 0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, obs)
-        plan.branch(3)
-        self._emit_sample(plan, "C.sample_pi_next", head, B, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
-                          self.lp_pn, obs)
+        if fuse_hs:     # one head pass feeds a'(s'), N x a(s) and N x a(s'): head + three samplers in one launch
+            self._emit_head_sample(plan, "C.actor.head_sample", ab, [
+                (B, 2 * B, 1, v["eps_next"], Xt, self.lp_next, nobs),
+                (0, B, self.N, v["eps_pi"], Xc.rows_(B, B + R), self.lp_pi, obs),
+                (B, 2 * B, self.N, v["eps_pi_next"], Xc.rows_(B + R, B + 2 * R), self.lp_pn, obs)])
+        else:
+            self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
+            plan.branch(2)
+            self._emit_sample(plan, "C.sample_pi", head, 0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, obs)
+            plan.branch(3)
+            self._emit_sample(plan, "C.sample_pi_next", head, B, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
+                              self.lp_pn, obs)
         plan.branch(0)
         plan.add("C.concat", rt.concat([(Xc.rows_(0, B), obs, 1, Mat.of(self.act)),
                                         (Xc.rows_(B + 2 * R, Mc), obs, self.N, Mat.of(v["rand_act"]))]))
