@@ -42,8 +42,13 @@ inline int check(cudaError_t e, const char* what) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
+#ifdef ORLK_PDL_WAIT_FIRST
+    pdl_wait();
+    pdl_trigger();
+#else
     pdl_trigger();
     pdl_wait();
+#endif
 }
 
 bool pdl_enabled();

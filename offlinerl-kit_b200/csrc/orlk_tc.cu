@@ -47,6 +47,7 @@ struct TcParams {
     int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
     int a_shared, b_shared;                     // one A / B for all groups (group stride 0): that map has a single plane
     int a_mn, b_mn;            // operand stored [k][m] / [k][n] (MN-major) instead of [m][k] / [n][k]
+    int late_trigger;          // programmatic launch of the next kernel after the mainloop instead of at kernel start
     int a_tmem;                // the splitter moves A (and its lo part) into tensor memory; the MMAs read A from there
     int c_tma;                 // C leaves through TMA stores (tmC valid)
     int trace_mode;            // 0: slots 8..15 = k-slab landed, 1: slots 8..15 = TMA for k-slab issued
@@ -255,7 +256,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + b_bytes; };
 
     // Prologue that touches no global data: runs while the previous kernel of the stream is still finishing.
-    orlk::pdl_trigger();
+    if (!p.late_trigger) orlk::pdl_trigger();
     if (threadIdx.x == 0) TC_STAMP(0);
     if (threadIdx.x == 32) {                   // descriptor fetch off the critical path (~0.3 us on first use)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -610,6 +611,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     }
+    if (warp < 2 && p.late_trigger) orlk::pdl_trigger();
     if (warp >= 2) {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
         // Eight warps: warp w may only touch TMEM lanes 32*(w%4) .. +31, so quadrant q is shared by warps 2+q' and 6+q''
@@ -621,6 +623,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.epi == ORLK_EPI_RELU_MASK) mbar_wait(smem_u32(maskbar), 0);
         mbar_wait(smem_u32(accum), 0);
         tc_fence_after();
+        if (p.late_trigger) orlk::pdl_trigger();        // mainloop done: only the epilogue is left of this CTA
         if (t == 0) TC_STAMP(6);
         const int q = warp & 3;
         const int half = warp >= 6 ? 1 : 0;
@@ -874,6 +877,9 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
         static int a_tmem = -1;
         if (a_tmem < 0) { const char* e = getenv("ORLK_TC_A_TMEM"); a_tmem = e ? atoi(e) : 1; }
         p.a_tmem = a_tmem;
+        static int late = -1;
+        if (late < 0) { const char* e = getenv("ORLK_TC_LATE_TRIGGER"); late = e ? atoi(e) : 1; }
+        p.late_trigger = late;
     }
     p.Bm = q->B; p.ldbm = q->ldb; p.bm_gs = q->b_gs; p.b_manual = b_manual ? 1 : 0; p.a_shared = a_shared ? 1 : 0; p.b_shared = b_shared ? 1 : 0;
     p.gen_row = q->gen_row; p.gen_row_gs = q->gen_row_gs; p.gen_col = q->gen_col; p.gen_col_gs = q->gen_col_gs;

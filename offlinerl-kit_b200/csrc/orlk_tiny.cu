@@ -28,6 +28,9 @@ static_assert(TM * TN == NTHR, "the epilogue gives every thread one element of t
 struct TinyArgs {
     OrlkGemmDesc d[MAXP];
     int n;
+    int late_trigger;             // let the next kernel of the stream in after the k loop instead of at the start: its CTAs
+                                  // then do not sit on this kernel's SMs while it stages and multiplies (measured: 306 ->
+                                  // 295 us per CQL step); ORLK_TINY_LATE_TRIGGER=0 restores the early trigger
     int passes;                   // MMA variant: 3 = hi/lo split operands, three TF32 MMAs per product (fp32-grade); 1 = plain TF32
     unsigned long long* trace;    // profiling aid (orlk_tc_set_trace): 16 clock stamps per CTA, NULL in normal operation
 };
@@ -139,7 +142,7 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     const int m0 = tm * TM, n0 = tn * TN;
     const int M = d.M, N = d.N, K = d.K;
     const bool vecA = aligned16(d.A) && (d.lda % 4) == 0, vecB = aligned16(d.B) && (d.ldb % 4) == 0;
-    orlk::pdl_enter();                                  // nothing above touched global data
+    if (P.late_trigger) orlk::pdl_wait(); else orlk::pdl_enter();      // nothing above touched global data
     TINY_STAMP(1);
 
     // this thread's element of the tile in the epilogue: fetch its bias / aux operands now, off the critical path
@@ -302,6 +305,7 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     }
 
     // ---- k-group partial tiles -> shared memory (the operand tiles are dead), then every thread finishes one element
+    if (P.late_trigger) orlk::pdl_trigger();
     TINY_STAMP(4);
     __syncthreads();
     constexpr int NRED = MMA ? NTHR / 32 : KG;          // partial tiles: one per warp (MMA) or per k group (FFMA)
@@ -430,6 +434,7 @@ extern "C" int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int t
     TinyArgs args;
     args.n = n_descs;
     args.passes = passes;
+    { static int lt = -1; if (lt < 0) { const char* e = getenv("ORLK_TINY_LATE_TRIGGER"); lt = e ? atoi(e) : 1; } args.late_trigger = lt; }
     args.trace = orlk::trace_buffer();
     bool mma = passes != 0;
     for (int i = 0; i < n_descs; ++i) {
