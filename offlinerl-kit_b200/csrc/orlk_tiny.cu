@@ -305,7 +305,7 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     }
 
     // ---- k-group partial tiles -> shared memory (the operand tiles are dead), then every thread finishes one element
-    if (P.late_trigger) orlk::pdl_trigger();
+    if (P.late_trigger == 1) orlk::pdl_trigger();
     TINY_STAMP(4);
     __syncthreads();
     constexpr int NRED = MMA ? NTHR / 32 : KG;          // partial tiles: one per warp (MMA) or per k group (FFMA)
@@ -341,6 +341,7 @@ k_tiny_gemm(const __grid_constant__ TinyArgs P) {
     }
     __syncthreads();
     TINY_STAMP(5);
+    if (P.late_trigger == 2) orlk::pdl_trigger();
 
     const int slot = d.split_base;
     const int epi = d.epi;
