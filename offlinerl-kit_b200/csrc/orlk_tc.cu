@@ -47,6 +47,8 @@ struct TcParams {
     int b_manual;                               //   K <= 32 then, and the splitter warps fill the single B tile themselves
     int a_shared, b_shared;                     // one A / B for all groups (group stride 0): that map has a single plane
     int a_mn, b_mn;            // operand stored [k][m] / [k][n] (MN-major) instead of [m][k] / [n][k]
+    int r3;                    // 3-pass + A-from-TMEM: ONE A buffer (it is dead as soon as the splitter has moved it to TMEM)
+                               // and a THREE-stage ring of [B | B lo]: the 2-stage ring was bound by its own chain latency
     int late_trigger;          // programmatic launch of the next kernel after the mainloop instead of at kernel start
     int a_tmem;                // the splitter moves A (and its lo part) into tensor memory; the MMAs read A from there
     int c_tma;                 // C leaves through TMA stores (tmC valid)
@@ -222,7 +224,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint64_t* empty = bars + 2 * MAX_STAGES;        // [MAX_STAGES]  MMAs that read the stage have completed
     uint64_t* accum = bars + 3 * MAX_STAGES;        // accumulator tile complete
     uint64_t* maskbar = bars + 3 * MAX_STAGES + 1;  // mask tile complete (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 2);
+    uint64_t* a_full = bars + 3 * MAX_STAGES + 2;   // r3: the A tile of the current slab has landed
+    uint64_t* a_free = bars + 3 * MAX_STAGES + 3;   // r3: the splitter has moved it to TMEM (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
     float* bias_s = reinterpret_cast<float*>(fixed + ONES_BYTES + 256);  // [BN_MAX] bias staged once per CTA
     uint32_t* mask_s = reinterpret_cast<uint32_t*>(bias_s + BN_MAX);     // [BM][BN_MAX/32] ReLU-mask bits of the tile
     uint8_t* smem = fixed + FIXED_SMEM;                                  // the operand ring
@@ -250,10 +254,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     constexpr int ATM_STRIDE = PASSES == 3 ? 64 : 32;
 
     const int b_bytes = NT * BK * 4;
-    auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
-    auto b_raw = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES; };
+    const bool r3 = p.r3 != 0;                 // ring layout: [A buffer] [stage 0: B | B lo] [stage 1] [stage 2]
+    auto a_raw = [&](int s) { return r3 ? smem : smem + s * STAGE_BYTES; };
+    auto b_raw = [&](int s) { return r3 ? smem + A_BYTES + s * STAGE_BYTES : smem + s * STAGE_BYTES + A_BYTES; };
     auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES + b_bytes; };
-    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * A_BYTES + b_bytes; };
+    auto b_lo = [&](int s) { return r3 ? smem + A_BYTES + s * STAGE_BYTES + b_bytes : smem + s * STAGE_BYTES + 2 * A_BYTES + b_bytes; };
 
     // Prologue that touches no global data: runs while the previous kernel of the stream is still finishing.
     if (!p.late_trigger) orlk::pdl_trigger();
@@ -270,6 +275,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_init(smem_u32(&empty[s]), 1);
         }
         mbar_init(smem_u32(accum), 1);
+        mbar_init(smem_u32(a_full), 1);
+        mbar_init(smem_u32(a_free), 128);
         mbar_init(smem_u32(maskbar), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -298,13 +305,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0) {
       if (elect_one()) {
         // ------------------------------------------------------------------ TMA producer
-        const uint32_t tx_bytes = A_BYTES + (p.b_manual ? 0u : (uint32_t)NT * BK * 4);
+        const uint32_t tx_bytes = (r3 ? 0u : (uint32_t)A_BYTES) + (p.b_manual ? 0u : (uint32_t)NT * BK * 4);
         for (int it = 0; it < nslabs; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(&empty[s]), ph ^ 1);
             mbar_expect_tx(smem_u32(&full[s]), tx_bytes);
             const int k0 = (slab0 + it) * BK;
+            if (r3) {           // B of this slab first (its stage is free), then A once the splitter is done with the previous A
+                if (p.b_mn) {
+                    for (int b = 0; b < NT / 32; ++b)
+                        tma_load_3d(smem_u32(b_raw(s)) + b * 4096, &tmB, smem_u32(&full[s]), n0 + 32 * b, k0, p.b_shared ? 0 : g);
+                } else tma_load_3d(smem_u32(b_raw(s)), &tmB, smem_u32(&full[s]), k0, n0, p.b_shared ? 0 : g);
+                mbar_wait(smem_u32(a_free), (it & 1) ^ 1);
+                mbar_expect_tx(smem_u32(a_full), A_BYTES);
+                if (p.a_mn) {
+#pragma unroll
+                    for (int b = 0; b < BM / 32; ++b)
+                        tma_load_3d(smem_u32(a_raw(0)) + b * 4096, &tmA, smem_u32(a_full), tile_m * BM + 32 * b, k0, p.a_shared ? 0 : g);
+                } else tma_load_3d(smem_u32(a_raw(0)), &tmA, smem_u32(a_full), k0, tile_m * BM, p.a_shared ? 0 : g);
+                continue;
+            }
             if (p.a_mn) {       // MN-major: one 32 (m) x 32 (k) box per 4 KB block
 #pragma unroll
                 for (int b = 0; b < BM / 32; ++b)
@@ -492,7 +513,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int it = 0; it < nslabs; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(smem_u32(&full[s]), ph);
+                mbar_wait(smem_u32(r3 ? a_full : &full[s]), r3 ? (uint32_t)(it & 1) : ph);
                 if (t == 0 && it == 0) TC_STAMP(3);
                 if (t == 0 && p.trace_mode == 0 && it < 8) TC_STAMP(8 + it);
                 const bool st4 = (t == 0 && p.trace_mode == 4 && it == 1);
@@ -543,6 +564,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         tmem_st32(ta + 32, x);
                     }
                     tmem_wait_st();
+                    if (r3) {       // the A buffer may be refilled; B of this slab is a separate barrier
+                        mbar_arrive(smem_u32(a_free));
+                        mbar_wait(smem_u32(&full[s]), ph);
+                    }
                 }
                 // A: 1024 float4 -> 8 per thread, all loads issued before the first store
                 if (!p.a_tmem) {
@@ -891,16 +916,27 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
         const int max_st = (TMEM_COLS - ATM_COL) / (q->passes == 3 ? 64 : 32);
         if (p.stages > max_st) p.stages = max_st;
     }
+    size_t ring_bytes = (size_t)p.stages * p.stage_bytes;
+    {
+        static int r3 = -1;
+        if (r3 < 0) { const char* e = getenv("ORLK_TC_R3"); r3 = e ? atoi(e) : 1; }
+        p.r3 = (r3 && q->passes == 3 && p.a_tmem && !b_manual) ? 1 : 0;
+    }
+    if (p.r3) {         // one A buffer + three [B | B lo] stages
+        p.stages = 3;
+        p.stage_bytes = 2 * NT * BK * 4;
+        ring_bytes = A_BYTES + (size_t)p.stages * p.stage_bytes;
+    }
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
     p.c_tma = 0;
     if (q->C != nullptr && NT % 32 == 0 && q->N % 4 == 0 && q->ldc % 4 == 0 && aligned16(q->C) && q->c_gs % 4 == 0 && q->c_split_stride % 4 == 0 &&
-        (int64_t)NT * 512 <= (int64_t)p.stages * p.stage_bytes) {
+        (int64_t)NT * 512 <= (int64_t)ring_bytes) {
         rc = make_map_c(&tmC, q->C, q->ldc, q->c_gs, q->c_split_stride, q->M, q->N, q->G, splits);
         if (rc) return rc;
         p.c_tma = 1;
     }
-    const size_t smem = 1024 + FIXED_SMEM + (size_t)p.stages * p.stage_bytes;
+    const size_t smem = 1024 + FIXED_SMEM + ring_bytes;
     const int grid = q->G * p.tiles_m * p.tiles_n * splits;
     cudaStream_t s = (cudaStream_t)stream;
     if (q->passes == 3) orlk::launch(k_tc_gemm<3>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
