@@ -292,10 +292,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     orlk::pdl_wait();                          // operands, bias and aux come from earlier kernels
     if (threadIdx.x == 0) TC_STAMP(1);
-    if (warp >= 2 && warp < 6) {
-        const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs + n0 : nullptr;
-        for (int i = threadIdx.x - 64; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < n_lim) ? __ldg(bg + i) : 0.f;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -477,6 +473,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp >= 2) {
         const int t = threadIdx.x - 64;                     // 0..127
+        {   // bias of this tile -> shared memory (read again only in the epilogue, behind a barrier of the eight warps;
+            // staged here and not before the CTA-wide sync so that the first TMA does not wait for this global load)
+            const float* bg = p.bias ? p.bias + (int64_t)g * p.bias_gs + n0 : nullptr;
+            for (int i = t; i < BN_MAX; i += 128) bias_s[i] = (bg != nullptr && i < n_lim) ? __ldg(bg + i) : 0.f;
+        }
         if (split_runs) {
             // -------------------------------------------------------------- operand splitter (+ rank-1 generator)
             const int nB4 = NT * BK / 4;
@@ -648,6 +649,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.epi == ORLK_EPI_RELU_MASK) mbar_wait(smem_u32(maskbar), 0);
         mbar_wait(smem_u32(accum), 0);
         tc_fence_after();
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: bias_s (and mask_s) complete
         if (p.late_trigger) orlk::pdl_trigger();        // mainloop done: only the epilogue is left of this CTA
         if (t == 0) TC_STAMP(6);
         const int q = warp & 3;
