@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 14
+#define ORLK_ABI_VERSION 15
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -307,15 +307,17 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
                         int clamp01, float target_entropy, OrlkAdamGroup* groups, int alpha_group, float* alpha_mv,
                         float* dq, int64_t dq_es, float* glp, float* out_losses, void* stream);
 
-/* CQL critic phase loss (cql.py:108-205) for both critics.
+/* CQL critic phase loss (cql.py:108-205) for both critics; also COMBO's (combo.py:133-208), whose TD rows are the
+ * real+fake mix (B), whose `- w * mean Q` term runs over the first n_qmean (= real) rows only (combo.py:196-203) and
+ * whose R conservative rows come from the mix or from the fake rows alone (rho_s, combo.py:162-166).  CQL: n_qmean = B.
  *   q[c] : [B + 3R] rows = data | pi | pi_next | random  (c = 0,1; stride q_cs)
  *   tq[c]: [B] target-critic values on (s', a');  lp_next [B];  lp_pi, lp_pn [R]
  * Computes the TD target, the 3-way logsumexp per repeat row (the reference's quirk), the optional Lagrange
  * multiplier step, the per-row upstream gradients dq[c][.] and the losses
  *   out_losses[0..1] = critic1/2 loss, [2] = cql_alpha loss, [3] = cql_alpha (old, clamped). */
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
-                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int R, int A,
-                         float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
+                         int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
                          float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream);
 

@@ -470,15 +470,15 @@ __global__ void k_sac_actor_loss(const float* __restrict__ q, int64_t q_es, int 
 __global__ void __launch_bounds__(1024)
 k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __restrict__ tq, int64_t tq_cs,
                   const float* __restrict__ lp_next, const float* __restrict__ lp_pi, const float* __restrict__ lp_pn,
-                  const float* __restrict__ rew, const float* __restrict__ term, int B, int R, float log_u, float gamma,
-                  float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
+                  const float* __restrict__ rew, const float* __restrict__ term, int B, int n_qmean, int R, float log_u,
+                  float gamma, float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
                   const OrlkAdamGroup* __restrict__ groups, int cql_alpha_group, float* __restrict__ cql_alpha_mv,
                   float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out) {
     orlk::pdl_enter();
     __shared__ float red[32];
     __shared__ float sh_scale;
     const float alpha = scalars[ORLK_SC_ALPHA];
-    const float invB = 1.f / (float)B, invR = 1.f / (float)R, invT = 1.f / T;
+    const float invB = 1.f / (float)B, invQ = 1.f / (float)n_qmean, invR = 1.f / (float)R, invT = 1.f / T;
     float td[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float nq = fminf(tq[b], tq[tq_cs + b]);
@@ -489,7 +489,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
             const float qq = q[c * q_cs + b];
             const float df = qq - y;
             td[c] += df * df;
-            qs[c] += qq;
+            if (b < n_qmean) qs[c] += qq;
         }
     }
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -506,7 +506,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         tdm[c] = block_sum(td[c], red) * invB;
-        const float qmean = block_sum(qs[c], red) * invB;
+        const float qmean = block_sum(qs[c], red) * invQ;
         const float lmean = block_sum(ls[c], red) * invR;
         cons[c] = lmean * w * T - qmean * w;
     }
@@ -538,7 +538,8 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
         if (!det_backup) nq -= alpha * lp_next[b];
         const float y = rew[b] + gamma * (1.f - term[b]) * nq;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) dq[c * dq_cs + b] = 2.f * (q[c * q_cs + b] - y) * invB - w * scale * invB;
+        for (int c = 0; c < 2; ++c)
+            dq[c * dq_cs + b] = 2.f * (q[c * q_cs + b] - y) * invB - (b < n_qmean ? w * scale * invQ : 0.f);
     }
     const float k = scale * w * invR;
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -736,15 +737,15 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
 }
 
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
-                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int R, int A,
-                         float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
+                         int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
                          float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream) {
-    ORLK_REQUIRE(B > 0 && R > 0 && A > 0, "sizes");
+    ORLK_REQUIRE(B > 0 && R > 0 && A > 0 && n_qmean > 0 && n_qmean <= B, "sizes");
     ORLK_REQUIRE(!with_lagrange || (groups != nullptr && cql_alpha_mv != nullptr), "lagrange needs its Adam state");
     const float log_u = (float)log(pow(0.5, (double)A));   // cql.py:82: np.log(0.5 ** act_dim)
-    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, R, log_u,
-                                                           gamma, cql_weight, temperature, deterministic_backup,
+    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, n_qmean, R,
+                                                           log_u, gamma, cql_weight, temperature, deterministic_backup,
                                                            with_lagrange, lagrange_threshold, scalars, groups,
                                                            cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses);
     return check_launch("k_cql_critic_loss");

@@ -1,5 +1,5 @@
-"""Device-resident model rollouts for MOPO (reference: policy/model_based/mopo.py:45-79 + sac.py:79-86 +
-dynamics/ensemble_dynamics.py:28-79).  The reference ping-pongs every imagined step through the host (50 MB of model
+"""Device-resident model rollouts for MOPO and COMBO (reference: policy/model_based/mopo.py:45-79, combo.py:67-107 +
+sac.py:79-86 + dynamics/ensemble_dynamics.py:28-79).  The reference ping-pongs every imagined step through the host (50 MB of model
 outputs per step, 6.3 M float64 normals on one core); here only the survivor count (4 bytes) crosses per step and the
 transitions are copied out once at the end."""
 import ctypes as C
@@ -15,8 +15,10 @@ from .nets import ParamSet
 
 
 class RolloutEngine:
-    def __init__(self, policy):
+    def __init__(self, policy, uniform=None):
+        """uniform: (low, high) -- COMBO's uniform_rollout: actions are uniform draws instead of the actor's samples."""
         self.policy = policy
+        self.uniform = uniform
         self.dyn = policy.dynamics
         self.rt = get_runtime(policy.actor.device)
         self.dev = self.rt.device
@@ -63,18 +65,30 @@ class RolloutEngine:
         n_total, t = 0, 0
         for t in range(length):
             S = cur.shape[0]
-            run, plan, obs_buf = self._actor_plan(S)
-            obs_buf.copy_(cur)
-            plan.run_eager()
-            if noise is not None:
-                eps = torch.as_tensor(noise["eps"][t], dtype=torch.float32).to(self.dev).contiguous()
+            if self.uniform is not None:
+                # combo.py:81-86: a ~ U(low, high), no actor pass
+                obs_buf = cur.clone()
+                if noise is not None:
+                    act = torch.as_tensor(noise["actions"][t], dtype=torch.float32).to(self.dev).contiguous()
+                else:
+                    act = torch.empty(S, A, dtype=torch.float32, device=self.dev)
+                    L.call("orlk_philox_fill", act.data_ptr(), 0, S * A, self.uniform[0], self.uniform[1], 0xac7,
+                           self.philox_counter.data_ptr(), None, rt.cur)
+                    L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
             else:
-                eps = torch.empty(S, A, dtype=torch.float32, device=self.dev)
-                L.call("orlk_philox_fill", eps.data_ptr(), S * A, 0, 0.0, 1.0, 0xac7, self.philox_counter.data_ptr(), None, rt.cur)
-                L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
-            act = torch.empty(S, A, dtype=torch.float32, device=self.dev)
-            L.call("orlk_tanh_gauss_sample", run.out.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), S, A, act.data_ptr(), A, None, None,
-                   0, 0, None, 0, rt.cur)
+                run, plan, obs_buf = self._actor_plan(S)
+                obs_buf.copy_(cur)
+                plan.run_eager()
+                if noise is not None:
+                    eps = torch.as_tensor(noise["eps"][t], dtype=torch.float32).to(self.dev).contiguous()
+                else:
+                    eps = torch.empty(S, A, dtype=torch.float32, device=self.dev)
+                    L.call("orlk_philox_fill", eps.data_ptr(), S * A, 0, 0.0, 1.0, 0xac7, self.philox_counter.data_ptr(), None,
+                           rt.cur)
+                    L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
+                act = torch.empty(S, A, dtype=torch.float32, device=self.dev)
+                L.call("orlk_tanh_gauss_sample", run.out.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), S, A, act.data_ptr(), A, None,
+                       None, 0, 0, None, 0, rt.cur)
             n64 = midx = None
             if noise is not None:
                 n64 = torch.as_tensor(noise["normal"][t], dtype=torch.float64).to(self.dev).contiguous()

@@ -235,12 +235,22 @@ class TwinCriticLearner(Learner):
 
 
 class CQLLearner(TwinCriticLearner):
-    def __init__(self, policy, batch_size: int, seed: int = 0):
+    """CQL, and COMBO's learner (policy/model_based/combo.py:109-243), which is the same step over the real+fake mix
+    with two row ranges narrowed: ``n_real`` -- the leading rows whose Q enters the ``- w * mean Q`` term
+    (combo.py:196-203) -- and ``cons_rows`` -- the rows the 3 x N conservative samples are drawn for (all of the mix,
+    or the fake rows alone with rho_s="model", combo.py:162-166)."""
+
+    def __init__(self, policy, batch_size: int, seed: int = 0, n_real: Optional[int] = None, cons_rows=None):
         super().__init__(policy, batch_size)
         rt, B, O, A = self.rt, self.B, self.O, self.A
         self.seed = seed
         self.N = int(policy._num_repeat_actions)
-        self.R = B * self.N
+        self.n_real = B if n_real is None else int(n_real)
+        self.c0, self.c1 = (0, B) if cons_rows is None else (int(cons_rows[0]), int(cons_rows[1]))
+        if not (0 < self.n_real <= B and 0 <= self.c0 < self.c1 <= B):
+            raise L.OrlkError("COMBO row split out of range")
+        self.Bc = self.c1 - self.c0
+        self.R = self.Bc * self.N
         self.Mc = B + 3 * self.R
         if policy._max_q_backup:
             raise L.OrlkError("CQL max_q_backup=True is not implemented by the CUDA engine")
@@ -289,6 +299,8 @@ class CQLLearner(TwinCriticLearner):
         # ---- critic phase with the UPDATED actor (cql.py:108-192)
         obs2 = Mat.of(self.obs2)
         obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
+        c0, c1 = self.c0, self.c1
+        cobs = obs.rows_(c0, c1)        # the states of the conservative term
         ab = self.run_actor_b
         fuse_hs = self._can_fuse_head_sample(ab)
         emit_forward(rt, plan, ab, [obs2], "C.actor", skip_head=fuse_hs)
@@ -301,18 +313,18 @@ class CQLLearner(TwinCriticLearner):
         if fuse_hs:     # one head pass feeds a'(s'), N x a(s) and N x a(s'): head + three samplers in one launch
             self._emit_head_sample(plan, "C.actor.head_sample", ab, [
                 (B, 2 * B, 1, v["eps_next"], Xt, self.lp_next, nobs),
-                (0, B, self.N, v["eps_pi"], Xc.rows_(B, B + R), self.lp_pi, obs),
-                (B, 2 * B, self.N, v["eps_pi_next"], Xc.rows_(B + R, B + 2 * R), self.lp_pn, obs)])
+                (c0, c1, self.N, v["eps_pi"], Xc.rows_(B, B + R), self.lp_pi, cobs),
+                (B + c0, B + c1, self.N, v["eps_pi_next"], Xc.rows_(B + R, B + 2 * R), self.lp_pn, cobs)])
         else:
             self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
             plan.branch(2)
-            self._emit_sample(plan, "C.sample_pi", head, 0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, obs)
+            self._emit_sample(plan, "C.sample_pi", head, c0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, cobs)
             plan.branch(3)
-            self._emit_sample(plan, "C.sample_pi_next", head, B, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
-                              self.lp_pn, obs)
+            self._emit_sample(plan, "C.sample_pi_next", head, B + c0, self.N, v["eps_pi_next"], R, Xc.rows_(B + R, B + 2 * R),
+                              self.lp_pn, cobs)
         plan.branch(0)
         plan.add("C.concat", rt.concat([(Xc.rows_(0, B), obs, 1, Mat.of(self.act)),
-                                        (Xc.rows_(B + 2 * R, Mc), obs, self.N, Mat.of(v["rand_act"]))]))
+                                        (Xc.rows_(B + 2 * R, Mc), cobs, self.N, Mat.of(v["rand_act"]))]))
         plan.join()
         # the target critics on (s', a') and the online critics on the 7936-row batch are independent: two branches
         cr = self.run_critic
@@ -324,7 +336,7 @@ class CQLLearner(TwinCriticLearner):
         plan.join()
         pol = self.policy
         largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), B, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
-                 self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, R, A, self.gamma,
+                 self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, self.n_real, R, A, self.gamma,
                  float(pol._cql_weight), float(pol._temperature), int(bool(pol._deterministic_backup)),
                  int(self.with_lagrange), float(pol._lagrange_threshold), self.scalars.data_ptr(), self.groups_ptr,
                  max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1)

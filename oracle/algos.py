@@ -179,6 +179,11 @@ class CQLOracle(_Learner, _AutoAlpha):
         self.N = num_repeat_actions
 
     def step(self, batch: Tensors, noise: Tensors) -> Dict[str, float]:
+        return self._step(batch, noise, batch, None)
+
+    def _step(self, batch: Tensors, noise: Tensors, cons: Tensors, real) -> Dict[str, float]:
+        """batch: the TD / actor rows; cons: the rows the conservative samples are drawn for; real: the rows of the
+        conservative data term when they are not ``batch`` itself (COMBO)."""
         p, N = self.p, self.N
         obs, act, nobs = batch["observations"], batch["actions"], batch["next_observations"]
         rew, term = batch["rewards"], batch["terminals"]
@@ -192,7 +197,7 @@ class CQLOracle(_Learner, _AutoAlpha):
         self._apply(self.actor_optim, actor_loss)
         alpha_loss = self._alpha_update(lp)                                            # cql.py:100-106
 
-        rep = lambda x: x.unsqueeze(1).repeat(1, N, 1).view(B * N, x.shape[-1])       # cql.py:142-147
+        rep = lambda x: x.unsqueeze(1).repeat(1, N, 1).view(x.shape[0] * N, x.shape[-1])   # cql.py:142-147
         # TD target, cql.py:108-132
         with torch.no_grad():
             if self.max_q_backup:
@@ -213,7 +218,7 @@ class CQLOracle(_Learner, _AutoAlpha):
 
         # conservative term, cql.py:138-168
         rand_act = noise["rand_act"]
-        tobs, tnobs = rep(obs), rep(nobs)
+        tobs, tnobs = rep(cons["observations"]), rep(cons["next_observations"])
         a_pi, lp_pi = nets.actforward(p, "actor", tobs, noise["eps_pi"])             # calc_pi_values :62-72
         v1_pi = nets.critic(p, "critic1", tobs, a_pi) - lp_pi.detach()
         v2_pi = nets.critic(p, "critic2", tobs, a_pi) - lp_pi.detach()
@@ -225,6 +230,9 @@ class CQLOracle(_Learner, _AutoAlpha):
         v2_r = nets.critic(p, "critic2", tobs, rand_act) - log_u
         cat1 = torch.cat([v1_pi, v1_pn, v1_r], 1)                                     # [B*N, 3]  (:160-161)
         cat2 = torch.cat([v2_pi, v2_pn, v2_r], 1)
+        if real is not None:                                                          # combo.py:196-197
+            q1 = nets.critic(p, "critic1", real["observations"], real["actions"])
+            q2 = nets.critic(p, "critic2", real["observations"], real["actions"])
         cons1 = torch.logsumexp(cat1 / self.T, dim=1).mean() * self.w * self.T - q1.mean() * self.w
         cons2 = torch.logsumexp(cat2 / self.T, dim=1).mean() * self.w * self.T - q2.mean() * self.w
 
@@ -255,6 +263,25 @@ class CQLOracle(_Learner, _AutoAlpha):
             out["cql_alpha"] = cql_alpha.item()
         self.losses = out
         return out
+
+
+class COMBOOracle(CQLOracle):
+    """policy/model_based/combo.py:109-243: the CQL step over the real+fake mix (combo.py:110-112).
+
+    Differences from cql.py, all kept: the conservative samples are drawn for the mix rows, or for the fake rows only
+    when ``rho_s == "model"`` (combo.py:162-166); the data term of the conservative loss is a fresh critic pass over
+    the real rows (combo.py:196-203).  The discarded ``reshape`` (combo.py:183-187) is the same quirk as CQL's.
+    noise: as CQLOracle, with ``eps_actor`` / ``eps_next`` over the mix rows and ``rand_act`` / ``eps_pi`` /
+    ``eps_pi_next`` over (conservative rows) * N."""
+
+    def __init__(self, state, rho_s="mix", **kw):
+        super().__init__(state, **kw)
+        self.rho_s = rho_s
+
+    def step(self, batch, noise: Tensors) -> Dict[str, float]:
+        real, fake = batch["real"], batch["fake"]
+        mix = {k: torch.cat([real[k], fake[k]], 0) for k in real.keys()}
+        return self._step(mix, noise, fake if self.rho_s == "model" else mix, real)
 
 
 class EDACOracle(_Learner, _AutoAlpha):

@@ -31,7 +31,7 @@ from offlinerlkit.nets import MLP
 from offlinerlkit.modules import (ActorProb, Actor, Critic, EnsembleCritic, TanhDiagGaussian, DiagGaussian,
                                   EnsembleDynamicsModel)
 from offlinerlkit.buffer import ReplayBuffer
-from offlinerlkit.policy import CQLPolicy, EDACPolicy, IQLPolicy, TD3BCPolicy, SACPolicy, MOPOPolicy
+from offlinerlkit.policy import CQLPolicy, EDACPolicy, IQLPolicy, TD3BCPolicy, SACPolicy, MOPOPolicy, COMBOPolicy
 from offlinerlkit.dynamics import EnsembleDynamics
 from offlinerlkit.utils.scaler import StandardScaler
 from offlinerlkit.utils.termination_fns import (termination_fn_halfcheetah, termination_fn_hopper,
@@ -172,6 +172,64 @@ def gen_cql(name, O, A, hidden, B, N, n_steps, with_lagrange, full_state, det_ba
     meta = dict(algo="cql", O=O, A=A, hidden=hidden, B=B, N=N, n_steps=n_steps, n_data=n_data, data_seed=0,
                 param_seeds={"actor": 100, "critic1": 101, "critic2": 102}, alpha_lr=alpha_lr,
                 target_entropy=target_entropy, hyper=hyper, np_seed=seed)
+    save(name, store, meta, full_state)
+
+
+def gen_combo(name, O, A, hidden, n_real, n_fake, N, n_steps, rho_s, with_lagrange, full_state, det_backup=True,
+              n_data=4096, seed=0):
+    """COMBOPolicy.learn (combo.py:109-243) on {"real": ..., "fake": ...} batches; the fake rows are draws from a second
+    synthetic dataset (what the model buffer holds is irrelevant to the step's arithmetic)."""
+    data, fdata = make_dataset(n_data, O, A, seed=0), make_dataset(n_data, O, A, seed=7)
+    torch.manual_seed(seed)
+    actor, c1, c2 = build_sac_like(O, A, hidden)
+    for i, m in enumerate((actor, c1, c2)):
+        overwrite_params(m, 100 + i)
+    hyper = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, cql_weight=5.0, temperature=1.0,
+                 max_q_backup=False, deterministic_backup=det_backup, with_lagrange=with_lagrange,
+                 lagrange_threshold=10.0, cql_alpha_lr=3e-4, num_repeat_actions=N)
+    alpha_lr, target_entropy = 1e-4, -A
+    log_alpha = torch.zeros(1, requires_grad=True)
+    pol = COMBOPolicy(None, actor, c1, c2,
+                      torch.optim.Adam(actor.parameters(), lr=hyper["actor_lr"]),
+                      torch.optim.Adam(c1.parameters(), lr=hyper["critic_lr"]),
+                      torch.optim.Adam(c2.parameters(), lr=hyper["critic_lr"]),
+                      action_space=gym.spaces.Box(-1, 1, (A,)), tau=hyper["tau"], gamma=hyper["gamma"],
+                      alpha=(target_entropy, log_alpha, torch.optim.Adam([log_alpha], lr=alpha_lr)),
+                      cql_weight=hyper["cql_weight"], temperature=hyper["temperature"],
+                      max_q_backup=False, deterministic_backup=det_backup, with_lagrange=with_lagrange,
+                      lagrange_threshold=hyper["lagrange_threshold"], cql_alpha_lr=hyper["cql_alpha_lr"],
+                      num_repeart_actions=N, uniform_rollout=False, rho_s=rho_s)
+    pol.train()
+    pre = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    ora = algos.COMBOOracle(pre, rho_s=rho_s, alpha=(target_entropy, 0.0, alpha_lr), **hyper)
+    idx, batches = draw_batches(data, n_steps, n_real, seed=seed)
+    fidx, fbatches = draw_batches(fdata, n_steps, n_fake, seed=seed + 1)
+    store = {"idx": idx, "fake_idx": fidx}
+    B = n_real + n_fake
+    R = (n_fake if rho_s == "model" else B) * N
+    for t in range(n_steps):
+        both = {"real": batches[t], "fake": fbatches[t]}
+        torch.manual_seed(1000 + t)
+        ref_loss = pol.learn(both)
+        torch.manual_seed(1000 + t)
+        noise = {"eps_actor": torch.randn(B, A), "eps_next": torch.randn(B, A),
+                 "rand_act": torch.FloatTensor(R, A).uniform_(-1.0, 1.0),
+                 "eps_pi": torch.randn(R, A), "eps_pi_next": torch.randn(R, A)}
+        ora_loss = ora.step(both, noise)
+        check_losses(ref_loss, ora_loss, f"{name} step {t}")
+        check_state(pol.state_dict(), ora.state_dict(), f"{name} step {t}")
+        pack(store, f"noise{t}", noise)
+        pack(store, f"loss{t}", {k: np.float64(v) for k, v in ref_loss.items()})
+        if t == 0 and full_state:
+            pack(store, "grads0", ora.grads)
+        pack(store, f"stats{t}", tensor_stats(pol.state_dict()))
+    store["log_alpha_final"] = log_alpha.detach().numpy()
+    store["cql_log_alpha_final"] = pol.cql_log_alpha.detach().numpy()
+    if full_state:
+        pack(store, "post", pol.state_dict())
+    meta = dict(algo="combo", O=O, A=A, hidden=hidden, B=B, n_real=n_real, n_fake=n_fake, N=N, rho_s=rho_s, n_steps=n_steps,
+                n_data=n_data, data_seed=0, fake_data_seed=7, param_seeds={"actor": 100, "critic1": 101, "critic2": 102},
+                alpha_lr=alpha_lr, target_entropy=target_entropy, hyper=hyper, np_seed=seed)
     save(name, store, meta, full_state)
 
 
@@ -401,8 +459,9 @@ def gen_dynamics(name, O, A, hidden, E, n_elites, B, n_batches, S, full_state, t
     save(name, store, meta, full_state)
 
 
-def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="hopper"):
-    """MOPOPolicy.rollout (mopo.py:45-79): compaction order and per-step RNG consumption."""
+def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="hopper", uniform=False):
+    """MOPOPolicy.rollout (mopo.py:45-79): compaction order and per-step RNG consumption.
+    uniform: COMBOPolicy.rollout with uniform_rollout=True (combo.py:67-107) -- NumPy uniform actions, no actor."""
     wds = [2.5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4][:len(dyn_hidden)] + [1e-4]
     model = EnsembleDynamicsModel(O, A, dyn_hidden, num_ensemble=E, num_elites=n_elites, weight_decays=wds, device="cpu")
     overwrite_params(model, 160)
@@ -421,9 +480,13 @@ def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="h
     actor, c1, c2 = build_sac_like(O, A, hidden)
     for i, m in enumerate((actor, c1, c2)):
         overwrite_params(m, 161 + i)
-    pol = MOPOPolicy(dyn, actor, c1, c2, torch.optim.Adam(actor.parameters(), lr=1e-4),
-                     torch.optim.Adam(c1.parameters(), lr=3e-4), torch.optim.Adam(c2.parameters(), lr=3e-4),
-                     alpha=0.2)
+    opts = (torch.optim.Adam(actor.parameters(), lr=1e-4), torch.optim.Adam(c1.parameters(), lr=3e-4),
+            torch.optim.Adam(c2.parameters(), lr=3e-4))
+    if uniform:
+        pol = COMBOPolicy(dyn, actor, c1, c2, *opts, action_space=gym.spaces.Box(-1, 1, (A,)), alpha=0.2,
+                          uniform_rollout=True)
+    else:
+        pol = MOPOPolicy(dyn, actor, c1, c2, *opts, alpha=0.2)
     init = data["observations"][:S].copy()
     init[:, 0] = 1.0 + 0.3 * init[:, 0]       # heights around the hopper/walker2d thresholds -> some terminate
     init[:, 1] = 0.1 * init[:, 1]
@@ -437,7 +500,10 @@ def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="h
     counts, eps_l, nrm_l, mid_l = [], [], [], []
     n_done, S_t = 0, S
     while n_done < len(out["obss"]):
-        eps_l.append(torch.randn(S_t, A).numpy())
+        if uniform:
+            eps_l.append(np.random.uniform(-1.0, 1.0, size=(S_t, A)))       # combo.py:82-86
+        else:
+            eps_l.append(torch.randn(S_t, A).numpy())
         nrm_l.append(np.random.normal(size=(E, S_t, O + 1)))
         mid_l.append(np.random.choice(model.elites.data.cpu().numpy(), size=S_t))
         counts.append(S_t)
@@ -445,15 +511,17 @@ def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="h
         n_done += S_t
         S_t = int((~term_t).sum())
     assert n_done == len(out["obss"]) == info["num_transitions"], (n_done, len(out["obss"]))
+    if uniform:
+        assert np.array_equal(np.concatenate(eps_l), out["actions"]), "uniform action stream differs from the reference"
     store = {"init": init, "counts": np.asarray(counts), "scaler_mu": dyn.scaler.mu, "scaler_std": dyn.scaler.std,
-             "eps": np.concatenate(eps_l), "normal": np.concatenate([n.reshape(E, -1) for n in nrm_l], axis=1),
+             ("uniform_actions" if uniform else "eps"): np.concatenate(eps_l), "normal": np.concatenate([n.reshape(E, -1) for n in nrm_l], axis=1),
              "midx": np.concatenate(mid_l), "reward_mean": np.float64(info["reward_mean"])}
     for k, v in out.items():
         store["out|" + k] = v
     pack(store, "dyn", model.state_dict())
     pack(store, "actor", actor.state_dict())
     meta = dict(algo="rollout", O=O, A=A, hidden=hidden, dyn_hidden=dyn_hidden, E=E, n_elites=n_elites, S=S,
-                horizon=horizon, term=term, penalty_coef=0.5, weight_decays=wds)
+                horizon=horizon, term=term, penalty_coef=0.5, weight_decays=wds, uniform=uniform)
     save(name, store, meta, True)
 
 
@@ -472,6 +540,14 @@ if __name__ == "__main__":
             full_state=False)
     run(gen_cql, "cql_hopper", O=11, A=3, hidden=[256, 256, 256], B=256, N=10, n_steps=1, with_lagrange=False,
             full_state=False)
+    run(gen_combo, "combo_small_mix", n_real=10, n_fake=6, N=4, n_steps=3, rho_s="mix", with_lagrange=False, full_state=True,
+        **small)
+    run(gen_combo, "combo_small_model", n_real=9, n_fake=15, N=4, n_steps=3, rho_s="model", with_lagrange=True,
+        full_state=True, det_backup=False, **small)
+    run(gen_combo, "combo_hc", O=17, A=6, hidden=[256, 256, 256], n_real=128, n_fake=128, N=10, n_steps=2, rho_s="mix",
+        with_lagrange=False, full_state=False)
+    run(gen_combo, "combo_hc_model", O=17, A=6, hidden=[256, 256, 256], n_real=128, n_fake=128, N=10, n_steps=1,
+        rho_s="model", with_lagrange=True, full_state=False)
     run(gen_sac, "sac_small", O=5, A=3, hidden=[32, 32], B=16, n_steps=3, full_state=True)
     run(gen_sac, "sac_hc", O=17, A=6, hidden=[256, 256], B=256, n_steps=2, full_state=False)
     run(gen_edac, "edac_small", O=5, A=3, hidden=[32, 32, 32], E=4, B=16, n_steps=3, full_state=True)
@@ -487,3 +563,5 @@ if __name__ == "__main__":
                  full_state=False, term="halfcheetah")
     run(gen_rollout, "rollout_small", O=5, A=3, hidden=[32, 32], dyn_hidden=[24, 24, 24, 24], E=3, n_elites=2, S=48,
                 horizon=4, term="hopper")
+    run(gen_rollout, "combo_rollout_uniform", O=5, A=3, hidden=[32, 32], dyn_hidden=[24, 24, 24, 24], E=3, n_elites=2, S=48,
+                horizon=4, term="hopper", uniform=True)

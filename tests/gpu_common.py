@@ -29,16 +29,20 @@ def build_policy(meta, device="cuda:0"):
         bb = MLP(O, hid)
         return ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), device)
 
-    if algo in ("cql", "sac"):
+    if algo in ("cql", "sac", "combo"):
         actor, c1, c2 = tanh_actor(), Critic(MLP(O + A, hid), device), Critic(MLP(O + A, hid), device)
         opt = (adam(actor, hy["actor_lr"]), adam(c1, hy["critic_lr"]), adam(c2, hy["critic_lr"]))
         if algo == "sac":
             return P.SACPolicy(actor, c1, c2, *opt, tau=hy["tau"], gamma=hy["gamma"], alpha=alpha_tuple())
-        return P.CQLPolicy(actor, c1, c2, *opt, action_space=Box(-1, 1, (A,)), tau=hy["tau"], gamma=hy["gamma"],
-                           alpha=alpha_tuple(), cql_weight=hy["cql_weight"], temperature=hy["temperature"],
-                           max_q_backup=hy["max_q_backup"], deterministic_backup=hy["deterministic_backup"],
-                           with_lagrange=hy["with_lagrange"], lagrange_threshold=hy["lagrange_threshold"],
-                           cql_alpha_lr=hy["cql_alpha_lr"], num_repeart_actions=hy["num_repeat_actions"])
+        cql_kw = dict(action_space=Box(-1, 1, (A,)), tau=hy["tau"], gamma=hy["gamma"],
+                      alpha=alpha_tuple(), cql_weight=hy["cql_weight"], temperature=hy["temperature"],
+                      max_q_backup=hy["max_q_backup"], deterministic_backup=hy["deterministic_backup"],
+                      with_lagrange=hy["with_lagrange"], lagrange_threshold=hy["lagrange_threshold"],
+                      cql_alpha_lr=hy["cql_alpha_lr"], num_repeart_actions=hy["num_repeat_actions"])
+        if algo == "combo":
+            return P.COMBOPolicy(meta.get("dynamics"), actor, c1, c2, *opt, uniform_rollout=False, rho_s=meta["rho_s"],
+                                 **cql_kw)
+        return P.CQLPolicy(actor, c1, c2, *opt, **cql_kw)
     if algo == "edac":
         actor = tanh_actor()
         critics = EnsembleCritic(O, A, hid, num_ensemble=meta["E"], device=device)
@@ -111,6 +115,60 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
         assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol if elementwise else 10 * lr_atol)
     post = g.group("post")
     if post and n_steps == m["n_steps"]:
+        sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
+        for k, v in post.items():
+            if v.dtype.kind == "f" and "saved_" not in k:
+                err = np.abs(sd[k].numpy() - v).max()
+                assert err <= tol * np.abs(v).max() + lr_atol, (k, err)
+    return policy
+
+
+def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", precision=None):
+    """COMBOPolicy.learn on {"real", "fake"} batches sampled from two facade buffers (as MBPolicyTrainer does) vs the
+    golden run of the real reference: both index streams and gathers bit-exact, then losses and parameters."""
+    from offlinerlkit_b200.buffer import ReplayBuffer
+    m = g.meta
+    policy = build_policy(m, device)
+    load_state(policy, initial_state(m))
+    policy.train()
+    datasets = (g.dataset(), g.fake_dataset())
+    bufs = []
+    for d in datasets:
+        b = ReplayBuffer(m["n_data"], (m["O"],), np.float32, m["A"], np.float32, device=device)
+        b.load_dataset(d)
+        bufs.append(b)
+    states = []
+    for off in (0, 1):          # make_golden.gen_combo: the real stream runs under np_seed, the fake one under np_seed + 1
+        np.random.seed(m["np_seed"] + off)
+        states.append(np.random.get_state())
+    lr_atol = 2.5 * max(v for k, v in m["hyper"].items() if k.endswith("_lr"))
+    sizes, keys = (m["n_real"], m["n_fake"]), ("idx", "fake_idx")
+    for t in range(m["n_steps"]):
+        parts = []
+        for i in range(2):
+            np.random.set_state(states[i])
+            parts.append(bufs[i].sample(sizes[i]))
+            states[i] = np.random.get_state()
+            torch.cuda.synchronize()
+            assert np.array_equal(parts[i].indices.cpu().numpy(), g[keys[i]][t]), "index stream differs from the reference"
+        ref_b = g.batch(t, datasets[0])
+        for part, name in zip(parts, ("real", "fake")):
+            for k, v in ref_b[name].items():
+                assert torch.equal(part[k].cpu().reshape(v.shape), v), f"gather not bit-exact: {name}.{k}"
+        if precision is not None and t == 0:
+            policy._split = sizes
+            policy.engine(m["B"]).precision = precision
+        out = policy.learn({"real": parts[0], "fake": parts[1]}, noise=g.noise(t))
+        ref = g.losses(t)
+        if verbose:
+            print(f"step {t}: engine {out}\n        golden {ref}", flush=True)
+        assert out.keys() == ref.keys(), (out.keys(), ref.keys())
+        for k in ref:
+            assert abs(out[k] - ref[k]) <= tol * max(1.0, abs(ref[k])), (t, k, out[k], ref[k])
+        sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
+        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol)
+    post = g.group("post")
+    if post:
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
         for k, v in post.items():
             if v.dtype.kind == "f" and "saved_" not in k:

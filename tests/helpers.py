@@ -31,10 +31,22 @@ class Golden:
         d["terminals"] = d["terminals"].reshape(-1, 1)
         return d
 
+    def fake_dataset(self):
+        """COMBO goldens: the second synthetic dataset the model-buffer rows are drawn from."""
+        m = self.meta
+        d = make_dataset(m["n_data"], m["O"], m["A"], seed=m["fake_data_seed"])
+        d["rewards"] = d["rewards"].reshape(-1, 1)
+        d["terminals"] = d["terminals"].reshape(-1, 1)
+        return d
+
     def batch(self, t: int, data=None) -> Dict[str, torch.Tensor]:
         data = data or self.dataset()
         idx = self.z["idx"][t]
-        return {k: torch.from_numpy(data[k][idx]) for k in FIELDS}
+        real = {k: torch.from_numpy(data[k][idx]) for k in FIELDS}
+        if self.meta["algo"] != "combo":
+            return real
+        fdata, fidx = self.fake_dataset(), self.z["fake_idx"][t]
+        return {"real": real, "fake": {k: torch.from_numpy(fdata[k][fidx]) for k in FIELDS}}
 
     def noise(self, t: int) -> Dict[str, torch.Tensor]:
         return {k: torch.from_numpy(v) for k, v in self.group(f"noise{t}").items()}
@@ -108,7 +120,7 @@ def initial_state(meta) -> Dict[str, torch.Tensor]:
     algo, O, A, hid = meta["algo"], meta["O"], meta["A"], meta["hidden"]
     ps = meta.get("param_seeds", {})
     st = {}
-    if algo in ("cql", "sac"):
+    if algo in ("cql", "sac", "combo"):
         st.update(recipe_state(actorprob_shapes(O, A, hid), ps["actor"], "actor"))
         for c in ("critic1", "critic2"):
             cs = recipe_state(critic_shapes(O + A, hid), ps[c], c)

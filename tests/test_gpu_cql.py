@@ -16,6 +16,15 @@ def test_cql_matches_reference(name, precision):
     run_golden_steps(Golden(name), tol=TOL, verbose=True, precision=precision)
 
 
+@pytest.mark.parametrize("name", ["combo_small_mix", "combo_small_model", "combo_hc", "combo_hc_model"])
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_combo_matches_reference(name, precision):
+    """COMBOPolicy.learn (combo.py:109-243): the CQL step graph over the real+fake mix, with the conservative rows
+    taken from the mix or from the model rows (rho_s) and its data term over the real rows."""
+    from tests.gpu_common import run_combo_golden_steps
+    run_combo_golden_steps(Golden(name), tol=TOL, verbose=True, precision=precision)
+
+
 @pytest.mark.parametrize("name", ["cql_hc", "cql_hc_lagrange"])
 def test_cql_fast_mode_tolerance(name):
     """Single-pass TF32 tensor-core mode, reported separately (north_star): losses within 2e-3 relative."""

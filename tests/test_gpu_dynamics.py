@@ -55,12 +55,16 @@ def test_dynamics_learn_validate_step(name):
     assert rel_err(info2["penalty"], g["step_penalty"]) < TOL
 
 
-def test_mopo_rollout_matches_reference():
+@pytest.mark.parametrize("name", ["rollout_small", "combo_rollout_uniform"])
+def test_mopo_rollout_matches_reference(name):
+    """MOPOPolicy.rollout, and COMBOPolicy.rollout with uniform_rollout=True (combo.py:67-107)."""
     from offlinerlkit_b200.nets import MLP
     from offlinerlkit_b200.modules import ActorProb, Critic, TanhDiagGaussian
-    from offlinerlkit_b200.policy import MOPOPolicy
-    g = Golden("rollout_small")
+    from offlinerlkit_b200.policy import MOPOPolicy, COMBOPolicy
+    from tests.gpu_common import Box
+    g = Golden(name)
     m = g.meta
+    uniform = bool(m.get("uniform"))
     O, A, hid = m["O"], m["A"], m["hidden"]
     dyn_state = {k: torch.from_numpy(v) for k, v in g.group("dyn").items()}
     dyn = _build_dynamics(m, dyn_state, g["scaler_mu"], g["scaler_std"], m["term"])
@@ -69,15 +73,19 @@ def test_mopo_rollout_matches_reference():
     actor.load_state_dict({k: torch.from_numpy(v) for k, v in g.group("actor").items()})
     c1, c2 = Critic(MLP(O + A, hid), DEV), Critic(MLP(O + A, hid), DEV)
     adam = lambda mod: torch.optim.Adam(mod.parameters(), lr=1e-4)
-    pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2)
+    if uniform:
+        pol = COMBOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), action_space=Box(-1, 1, (A,)), alpha=0.2,
+                          uniform_rollout=True)
+    else:
+        pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2)
     counts, E, D = g["counts"], m["E"], O + 1
     eps, nrm, mid, r = [], [], [], 0
     for c in counts:
-        eps.append(g["eps"][r:r + c])
+        eps.append(g["uniform_actions" if uniform else "eps"][r:r + c])
         nrm.append(g["normal"][:, r * D:(r + c) * D].reshape(E, c, D))
         mid.append(g["midx"][r:r + c])
         r += c
-    out, info = pol.rollout(g["init"], m["horizon"], noise={"eps": eps, "normal": nrm, "midx": mid})
+    out, info = pol.rollout(g["init"], m["horizon"], noise={("actions" if uniform else "eps"): eps, "normal": nrm, "midx": mid})
     assert info["num_transitions"] == int(counts.sum())
     for k in ("obss", "next_obss", "actions", "rewards"):
         assert out[k].shape == g["out|" + k].shape, k
@@ -88,3 +96,5 @@ def test_mopo_rollout_matches_reference():
     out2, info2 = pol.rollout(g["init"], m["horizon"])
     assert set(out2) == {"obss", "next_obss", "actions", "rewards", "terminals"} and out2["terminals"].dtype == bool
     assert len(out2["obss"]) == info2["num_transitions"]
+    if uniform:
+        assert np.abs(out2["actions"]).max() <= 1.0 and abs(float(out2["actions"].mean())) < 0.2

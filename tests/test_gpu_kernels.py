@@ -427,8 +427,11 @@ def test_sac_actor_loss_vs_autograd(rt):
 def test_cql_critic_loss_vs_autograd(rt):
     from offlinerlkit_b200 import _lib as L
     gen = torch.Generator().manual_seed(6)
-    for (B, N, A, det, lag) in [(16, 4, 3, 1, 0), (256, 10, 6, 0, 1), (256, 10, 6, 1, 1)]:
-        R = B * N
+    # (B, rows feeding the conservative term, rows in the `- w mean Q` term): CQL has all three equal; COMBO's
+    # rho_s="mix" has nq = real rows, rho_s="model" additionally draws the conservative rows from the fake half
+    for (B, N, A, det, lag, Bc, nq_rows) in [(16, 4, 3, 1, 0, 16, 16), (256, 10, 6, 0, 1, 256, 256), (256, 10, 6, 1, 1, 256, 256),
+                                             (256, 10, 6, 1, 1, 256, 128), (256, 10, 6, 0, 0, 128, 128), (24, 4, 3, 1, 1, 15, 9)]:
+        R = Bc * N
         Mc = B + 3 * R
         q = torch.randn(2, Mc, generator=gen) * 3
         tq = torch.randn(2, B, generator=gen)
@@ -446,7 +449,7 @@ def test_cql_critic_loss_vs_autograd(rt):
             td = ((qd[c, :B] - y) ** 2).mean()
             cat = torch.stack([qd[c, B:B + R] - lpp.double(), qd[c, B + R:B + 2 * R] - lpq.double(),
                                qd[c, B + 2 * R:] - math.log(0.5 ** A)], 1)
-            cons = torch.logsumexp(cat / T, dim=1).mean() * w * T - qd[c, :B].mean() * w
+            cons = torch.logsumexp(cat / T, dim=1).mean() * w * T - qd[c, :nq_rows].mean() * w
             if lag:
                 cons = torch.clamp(cla.exp(), 0, 1e6) * (cons - thr)
             losses.append((td, cons))
@@ -465,7 +468,7 @@ def test_cql_critic_loss_vs_autograd(rt):
         qg, tqg, a1, a2, a3, rg, tg = map(dev, (q, tq, lpn, lpp, lpq, rew, term))
         dq, out = torch.zeros(2, Mc, device=DEV), torch.zeros(4, device=DEV)
         L.call("orlk_cql_critic_loss", qg.data_ptr(), Mc, tqg.data_ptr(), B, a1.data_ptr(), a2.data_ptr(), a3.data_ptr(),
-               rg.data_ptr(), tg.data_ptr(), B, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
+               rg.data_ptr(), tg.data_ptr(), B, nq_rows, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
                mv.data_ptr(), dq.data_ptr(), Mc, out.data_ptr(), rt.cur)
         torch.cuda.synchronize()
         _close(out[0], total[0], rtol=2e-5, atol=1e-4, msg="critic1 loss")

@@ -54,11 +54,15 @@ def test_mf_trainer_runs_cql(tmp_path):
     assert policy._engine._group_lr[policy._engine.g_actor] == pytest.approx(0.5 * m["hyper"]["actor_lr"])
 
 
-def test_mb_trainer_runs_mopo(tmp_path):
+@pytest.mark.parametrize("algo", ["mopo", "combo", "combo_uniform_model"])
+def test_mb_trainer_runs_mopo(tmp_path, algo):
+    """run_example/run_mopo.py and run_combo.py in miniature: dynamics.train -> MBPolicyTrainer (rollouts into the fake
+    buffer, policy.learn on {"real", "fake"} batches)."""
     from offlinerlkit_b200.nets import MLP
     from offlinerlkit_b200.modules import ActorProb, Critic, TanhDiagGaussian, EnsembleDynamicsModel
-    from offlinerlkit_b200.policy import MOPOPolicy
+    from offlinerlkit_b200.policy import MOPOPolicy, COMBOPolicy
     from offlinerlkit_b200.dynamics import EnsembleDynamics
+    from tests.gpu_common import Box
     from offlinerlkit_b200.buffer import ReplayBuffer
     from offlinerlkit_b200.policy_trainer import MBPolicyTrainer
     from offlinerlkit_b200.utils.logger import Logger
@@ -76,8 +80,14 @@ def test_mb_trainer_runs_mopo(tmp_path):
     model = EnsembleDynamicsModel(O, A, [24, 24], num_ensemble=3, num_elites=2, weight_decays=[2.5e-5, 5e-5, 7.5e-5], device=DEV)
     dyn = EnsembleDynamics(model, adam(model, 1e-3), StandardScaler(), get_termination_fn("halfcheetah-medium-v2"), penalty_coef=0.5)
     la = torch.zeros(1, requires_grad=True, device=DEV)
-    pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor, 1e-4), adam(c1, 3e-4), adam(c2, 3e-4),
-                     alpha=(-A, la, torch.optim.Adam([la], lr=1e-4)))
+    opt = (adam(actor, 1e-4), adam(c1, 3e-4), adam(c2, 3e-4))
+    if algo == "mopo":
+        pol = MOPOPolicy(dyn, actor, c1, c2, *opt, alpha=(-A, la, torch.optim.Adam([la], lr=1e-4)))
+    else:
+        pol = COMBOPolicy(dyn, actor, c1, c2, *opt, action_space=Box(-1, 1, (A,)),
+                          alpha=(-A, la, torch.optim.Adam([la], lr=1e-4)), cql_weight=5.0, with_lagrange=False,
+                          num_repeart_actions=4, uniform_rollout=algo.endswith("uniform_model"),
+                          rho_s="model" if algo.endswith("model") else "mix")
     real = ReplayBuffer(2000, (O,), np.float32, A, np.float32, device=DEV)
     real.load_dataset(data)
     fake = ReplayBuffer(64 * 2 * 5, (O,), np.float32, A, np.float32, device=DEV)

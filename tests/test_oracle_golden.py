@@ -36,6 +36,13 @@ def test_cql(name):
     _run(g, algos.CQLOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
 
 
+@pytest.mark.parametrize("name", ["combo_small_mix", "combo_small_model", "combo_hc", "combo_hc_model"])
+def test_combo(name):
+    """combo.py:109-243 on real+fake batches, both rho_s settings, with and without the Lagrange multiplier."""
+    g = Golden(name)
+    _run(g, algos.COMBOOracle(initial_state(g.meta), rho_s=g.meta["rho_s"], alpha=_alpha(g.meta), **g.meta["hyper"]))
+
+
 @pytest.mark.parametrize("name", ["sac_small", "sac_hc"])
 def test_sac(name):
     g = Golden(name)
@@ -104,10 +111,11 @@ def test_dynamics(name):
     assert rel_err(info["penalty"], g["step_penalty"]) < TOL
 
 
-def test_rollout_compaction():
-    """mopo.py:45-79: stable survivor compaction and per-step draw order, replayed with stored noise."""
+@pytest.mark.parametrize("name", ["rollout_small", "combo_rollout_uniform"])
+def test_rollout_compaction(name):
+    """mopo.py:45-79 / combo.py:67-107: stable survivor compaction and per-step draw order, replayed with stored noise."""
     from oracle import nets
-    g = Golden("rollout_small")
+    g = Golden(name)
     m = g.meta
     dyn_state = {k: torch.from_numpy(v) for k, v in g.group("dyn").items()}
     actor = {"actor." + k: torch.from_numpy(v) for k, v in g.group("actor").items()}
@@ -117,6 +125,8 @@ def test_rollout_compaction():
 
     def select_action(obs):
         n = len(obs)
+        if m.get("uniform"):        # combo.py:82-86: uniform actions, no actor pass
+            return g["uniform_actions"][cur["row"]:cur["row"] + n]
         eps = torch.from_numpy(g["eps"][cur["row"]:cur["row"] + n])
         with torch.no_grad():
             a, _ = nets.actforward(actor, "actor", torch.from_numpy(obs), eps)
