@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 15
+#define ORLK_ABI_VERSION 16
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -78,6 +78,12 @@ int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, 
  *   act   [n, act_dim], rew [n], term [n]. */
 int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx,
                        int n, float* obs2, float* act, float* rew, float* term, void* stream);
+
+/* The same gather with separate destinations for observations and next_observations, so that the draws of several
+ * buffers land in consecutive row blocks of one batch: the real + model-buffer mix of the model-based policies
+ * (mopo.py:81-84, combo.py:110-112 -- there a torch.cat of two sampled dicts). */
+int orlk_replay_gather_into(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx,
+                            int n, float* obs, float* next_obs, float* act, float* rew, float* term, void* stream);
 
 /* The whole of ReplayBuffer.sample (buffer/buffer.py:97-106) in one host call: waits for slot_event if event_armed
  * (the previous upload out of this pinned slot), copies idx_host[0..n) into idx_pinned, uploads it to idx_dev,

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -88,6 +88,7 @@ _PROTOS = {
     "orlk_event_elapsed_ms": [_P, _P, C.POINTER(C.c_float)], "orlk_event_destroy": [_P],
     "orlk_replay_pack": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _L, _P],
     "orlk_replay_gather": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "orlk_replay_gather_into": [_P, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "orlk_replay_sample": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "orlk_gemm_grouped": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_init": [],
     "orlk_gemm_tiny": [_P, _I, _I, _I, _I, _I, _P], "orlk_gemm_tiny_init": [],

@@ -28,8 +28,8 @@ __global__ void k_replay_pack(const float* __restrict__ obs, const float* __rest
 
 // One warp per sampled index: a coalesced read of the (<= 256 B) table row, scattered into the SoA batch.
 __global__ void k_replay_gather(const float* __restrict__ table, int64_t n_rows, int row_w, int O, int A,
-                                const int64_t* __restrict__ idx, int n, float* __restrict__ obs2, float* __restrict__ act,
-                                float* __restrict__ rew, float* __restrict__ term) {
+                                const int64_t* __restrict__ idx, int n, float* __restrict__ obs, float* __restrict__ nobs,
+                                float* __restrict__ act, float* __restrict__ rew, float* __restrict__ term) {
     orlk::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,8 +41,8 @@ __global__ void k_replay_gather(const float* __restrict__ table, int64_t n_rows,
     const int used = 2 * O + A + 2;
     for (int j = lane; j < used; j += 32) {
         const float v = __ldg(src + j);
-        if (j < O) obs2[(int64_t)warp * O + j] = v;
-        else if (j < 2 * O) obs2[((int64_t)n + warp) * O + (j - O)] = v;
+        if (j < O) obs[(int64_t)warp * O + j] = v;
+        else if (j < 2 * O) nobs[(int64_t)warp * O + (j - O)] = v;
         else if (j < 2 * O + A) act[(int64_t)warp * A + (j - 2 * O)] = v;
         else if (j == 2 * O + A) rew[warp] = v;
         else term[warp] = v;
@@ -63,15 +63,21 @@ int orlk_replay_pack(const float* obs, const float* next_obs, const float* act, 
     return check_launch("k_replay_pack");
 }
 
-int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx, int n,
-                       float* obs2, float* act, float* rew, float* term, void* stream) {
+int orlk_replay_gather_into(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx,
+                            int n, float* obs, float* next_obs, float* act, float* rew, float* term, void* stream) {
     ORLK_REQUIRE(n >= 0 && n_rows > 0, "sizes");
     ORLK_REQUIRE(row_w >= 2 * obs_dim + act_dim + 2, "row_w too small");
     if (n == 0) return 0;
     const int wpb = 4;  // warps per block: 64 blocks for a 256 batch, spread over SMs
     orlk::launch(k_replay_gather, (n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream, table, n_rows, row_w, obs_dim, act_dim,
-                                                                                idx, n, obs2, act, rew, term);
+                                                                                idx, n, obs, next_obs, act, rew, term);
     return check_launch("k_replay_gather");
+}
+
+int orlk_replay_gather(const float* table, int64_t n_rows, int row_w, int obs_dim, int act_dim, const int64_t* idx, int n,
+                       float* obs2, float* act, float* rew, float* term, void* stream) {
+    return orlk_replay_gather_into(table, n_rows, row_w, obs_dim, act_dim, idx, n, obs2, obs2 + (int64_t)n * obs_dim, act, rew,
+                                   term, stream);
 }
 
 // ReplayBuffer.sample in ONE host call (the public-API step is host-latency sensitive: every ctypes round trip shows):

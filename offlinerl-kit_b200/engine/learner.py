@@ -139,7 +139,20 @@ class Learner:
         """Replay the step and wait for it; returns the loss block as Python floats."""
         plan = self.plans[key]
         tok = getattr(self, "_bound_token", None)
-        if tok is not None and getattr(tok, "pending", False):
+        srcs = getattr(self, "_sources", None)
+        if srcs:
+            # several buffers feed one batch (real + model rows): their uploads and gathers ride in front of the step when
+            # every draw is still pending, else the rows are gathered eagerly from the indices already on the device
+            if self.use_graph and all(t.pending for t, _ in srcs):
+                plan = self._with_gather_parts(key, plan, srcs)
+            else:
+                for t, off in srcs:
+                    if t.pending:
+                        t.upload_op()
+                        L.call("orlk_event_record", t.pin_event, self.rt.cur)
+                        t.pin_armed = True
+                    self.gather_part_op(t, off)()
+        elif tok is not None and getattr(tok, "pending", False):
             if self.use_graph:      # index upload + gather ride in front of the step, inside the same graph launch
                 plan = self._with_gather(key, plan, tok)
                 tok.pending = False
@@ -170,6 +183,27 @@ class Learner:
             p2.keep = list(plan.keep) + [tok, plan]
             cache[k] = p2
         return p2
+
+    def _with_gather_parts(self, key: str, plan: Plan, srcs) -> Plan:
+        """The step plan behind the pending index uploads and row gathers of all its source buffers."""
+        cache = self.__dict__.setdefault("_gather_plans", {})
+        k = (key,) + tuple((id(t), t.gather_args, off) for t, off in srcs)
+        p2 = cache.get(k)
+        if p2 is None:
+            p2 = Plan(self.rt, getattr(plan, "name", key) + "+gather")
+            head = []
+            for i, (t, off) in enumerate(srcs):
+                head += [(f"idx_h2d{i}", t.upload_op), (f"gather{i}", self.gather_part_op(t, off))]
+            p2.ops = head + list(plan.ops)
+            p2.flat_ops = head + list(plan.flat_ops)
+            p2.keep = list(plan.keep) + [t for t, _ in srcs] + [plan]
+            cache[k] = p2
+        return p2
+
+    def gather_part_op(self, tok, row_off: int):
+        """Launch closure: rows of ``tok``'s buffer at its uploaded indices -> rows [row_off, row_off + n) of this
+        engine's batch staging.  Engines that accept multi-buffer batches implement it."""
+        raise NotImplementedError
 
     def enqueue(self, key: str) -> None:
         """Launch a step without waiting for it (used by the device-resident benchmark loop)."""

@@ -85,10 +85,40 @@ class TwinCriticLearner(Learner):
         self.term = rt.zeros(B, 1)
         self._bound_ptrs = None
         self._bound_token = None
+        self._sources = None
+
+    def bind_parts(self, parts) -> None:
+        """Batches of several replay buffers (MBPolicyTrainer's real + model draws) as consecutive row blocks of the
+        step's batch: the engine gathers each buffer's rows straight into its own staging, inside the step graph."""
+        toks = tuple(p.token for p in parts)
+        if self._sources is not None and tuple(t for t, _ in self._sources) == toks:
+            return
+        sizes = [int(t.idx_dev.shape[0]) for t in toks]
+        if sum(sizes) != self.B:
+            raise L.OrlkError(f"the step graph was built for batch size {self.B}, got parts {sizes}")
+        offs = [sum(sizes[:i]) for i in range(len(sizes))]
+        self._sources = list(zip(toks, offs))
+        self._bound_token = None
+
+    def gather_part_op(self, tok, row_off: int):
+        B, O, A = self.B, self.O, self.A
+        n = int(tok.idx_dev.shape[0])
+        dst = (self.obs2.data_ptr() + 4 * row_off * O, self.obs2.data_ptr() + 4 * (B + row_off) * O,
+               self.act.data_ptr() + 4 * row_off * A, self.rew.data_ptr() + 4 * row_off, self.term.data_ptr() + 4 * row_off)
+        def op():
+            tp, rows, row_w, o_dim, a_dim = tok.gather_args
+            if o_dim != O or a_dim != A:
+                raise L.OrlkError("replay buffer row layout does not match the policy's observation / action sizes")
+            L.call("orlk_replay_gather_into", tp, rows, row_w, o_dim, a_dim, tok.idx_dev_ptr, n, *dst, self.rt.cur)
+        return op
 
     def bind_batch(self, batch) -> None:
         """Use the replay buffer's persistent staging tensors as graph inputs (zero-copy), or copy a foreign
         batch into the engine's own staging."""
+        if isinstance(batch, (list, tuple)):
+            self.bind_parts(batch)
+            return
+        self._sources = None
         tok = getattr(batch, "token", None)
         if tok is not None and tok is self._bound_token:
             return              # the buffer's staging memory this engine's graphs are already bound to

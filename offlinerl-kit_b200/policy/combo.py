@@ -53,12 +53,12 @@ class COMBOPolicy(CQLPolicy):
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
         real, fake = batch["real"], batch["fake"]
-        split = (int(real["observations"].shape[0]), int(fake["observations"].shape[0]))
+        size = lambda b: getattr(b, "batch_size", None) or int(b["observations"].shape[0])   # no gather forced
+        split = (size(real), size(fake))
         if self._split is None:
             if split[0] == 0 or (self._rho_s == "model" and split[1] == 0):
                 raise ValueError("COMBO needs real rows (and model rows with rho_s='model') in every batch")
             self._split = split
         elif split != self._split:
             raise RuntimeError(f"the step graph was built for a {self._split} real/fake split, got {split}")
-        mix = {k: torch.cat([real[k], fake[k]], 0) for k in real.keys()}
-        return super().learn(mix, noise)
+        return self._learn_mixed(real, fake, noise)

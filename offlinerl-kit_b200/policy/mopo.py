@@ -28,6 +28,4 @@ class MOPOPolicy(SACPolicy):
         return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise)
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
-        real, fake = batch["real"], batch["fake"]
-        mix = {k: torch.cat([real[k], fake[k]], 0) for k in real.keys()}
-        return super().learn(mix, noise)
+        return self._learn_mixed(batch["real"], batch["fake"], noise)

@@ -89,6 +89,19 @@ class SACPolicy(BasePolicy):
             if not self._is_auto_alpha:
                 self._alpha_tensor = value      # a plain float alpha stays a float, as in the reference
 
+    def _learn_mixed(self, real, fake, noise=None) -> Dict[str, float]:
+        """The model-based policies' step on real + model-buffer rows (mopo.py:81-84, combo.py:110-112).  Draws of two
+        device-mirrored buffers are gathered straight into the step's batch inside the step graph; anything else is
+        concatenated as the reference does."""
+        tr, tf = getattr(real, "token", None), getattr(fake, "token", None)
+        if tr is not None and tf is not None and tr is not tf:
+            eng = self.engine(real.batch_size + fake.batch_size)
+            out = eng.step([real, fake], noise)
+            self._after_step(out)
+            return out
+        mix = {k: torch.cat([real[k], fake[k]], 0) for k in real.keys()}
+        return SACPolicy.learn(self, mix, noise)
+
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         eng = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0])))
         out = eng.step(batch, noise)

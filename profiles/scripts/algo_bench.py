@@ -15,7 +15,7 @@ from tests.gpu_common import build_policy, make_buffer
 from tests.helpers import Golden
 
 out = {}
-for name in ("cql_hc", "sac_hc", "edac_hc", "iql_walker", "iql_walker_b1024", "td3bc_walker"):
+for name in ("cql_hc", "combo_hc", "combo_hc_model", "sac_hc", "edac_hc", "iql_walker", "iql_walker_b1024", "td3bc_walker"):
     g = Golden(name)
     m = g.meta
     torch.manual_seed(0)
@@ -24,13 +24,18 @@ for name in ("cql_hc", "sac_hc", "edac_hc", "iql_walker", "iql_walker_b1024", "t
     pol.train()
     buf, _ = make_buffer(g)
     B = m["B"]
+    if m["algo"] == "combo":        # MBPolicyTrainer's loop: one draw from the real buffer, one from the model buffer
+        fbuf, _ = make_buffer(g)
+        draw = lambda: {"real": buf.sample(m["n_real"]), "fake": fbuf.sample(m["n_fake"])}
+    else:
+        draw = lambda: buf.sample(B)
     for _ in range(30):
-        loss = pol.learn(buf.sample(B))
+        loss = pol.learn(draw())
     torch.cuda.synchronize()
     N = 1000
     t0 = time.perf_counter()
     for _ in range(N):
-        loss = pol.learn(buf.sample(B))
+        loss = pol.learn(draw())
     e2e = N / (time.perf_counter() - t0)
     eng = pol._engine
     key = "step" if "step" in eng.plans else sorted(eng.plans)[0]

@@ -123,9 +123,12 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
     return policy
 
 
-def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", precision=None):
+def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", precision=None, mode="checked"):
     """COMBOPolicy.learn on {"real", "fake"} batches sampled from two facade buffers (as MBPolicyTrainer does) vs the
-    golden run of the real reference: both index streams and gathers bit-exact, then losses and parameters."""
+    golden run of the real reference: both index streams and gathers bit-exact, then losses and parameters.
+    mode: "checked" reads the sampled rows first (the draws are materialised, the engine re-gathers them eagerly);
+    "lazy" hands the untouched draws over, so both index uploads and gathers run inside the step graph;
+    "concat" passes plain tensor dicts, which the policy concatenates as the reference does."""
     from offlinerlkit_b200.buffer import ReplayBuffer
     m = g.meta
     policy = build_policy(m, device)
@@ -149,12 +152,16 @@ def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", 
             np.random.set_state(states[i])
             parts.append(bufs[i].sample(sizes[i]))
             states[i] = np.random.get_state()
-            torch.cuda.synchronize()
-            assert np.array_equal(parts[i].indices.cpu().numpy(), g[keys[i]][t]), "index stream differs from the reference"
-        ref_b = g.batch(t, datasets[0])
-        for part, name in zip(parts, ("real", "fake")):
-            for k, v in ref_b[name].items():
-                assert torch.equal(part[k].cpu().reshape(v.shape), v), f"gather not bit-exact: {name}.{k}"
+            if mode != "lazy":
+                torch.cuda.synchronize()
+                assert np.array_equal(parts[i].indices.cpu().numpy(), g[keys[i]][t]), "index stream differs from the reference"
+        if mode != "lazy":
+            ref_b = g.batch(t, datasets[0])
+            for part, name in zip(parts, ("real", "fake")):
+                for k, v in ref_b[name].items():
+                    assert torch.equal(part[k].cpu().reshape(v.shape), v), f"gather not bit-exact: {name}.{k}"
+        if mode == "concat":
+            parts = [{k: v.clone() for k, v in part.items()} for part in parts]
         if precision is not None and t == 0:
             policy._split = sizes
             policy.engine(m["B"]).precision = precision

@@ -25,6 +25,20 @@ def test_combo_matches_reference(name, precision):
     run_combo_golden_steps(Golden(name), tol=TOL, verbose=True, precision=precision)
 
 
+@pytest.mark.parametrize("name", ["combo_small_model", "combo_hc"])
+def test_combo_batch_paths_agree(name):
+    """The real and model-buffer draws reach the step three ways: gathered inside the step graph (untouched draws),
+    re-gathered eagerly (draws somebody has read), or concatenated from plain tensors (the reference's torch.cat).
+    All three must give the same parameters bit for bit."""
+    import torch
+    from tests.gpu_common import run_combo_golden_steps
+    g = Golden(name)
+    pols = [run_combo_golden_steps(g, tol=TOL, mode=m) for m in ("lazy", "checked", "concat")]
+    for other in pols[1:]:
+        for (k, a), (_, b) in zip(pols[0].state_dict().items(), other.state_dict().items()):
+            assert torch.equal(a, b), k
+
+
 @pytest.mark.parametrize("name", ["cql_hc", "cql_hc_lagrange"])
 def test_cql_fast_mode_tolerance(name):
     """Single-pass TF32 tensor-core mode, reported separately (north_star): losses within 2e-3 relative."""
