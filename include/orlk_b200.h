@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 16
+#define ORLK_ABI_VERSION 18
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -317,13 +317,15 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
  * real+fake mix (B), whose `- w * mean Q` term runs over the first n_qmean (= real) rows only (combo.py:196-203) and
  * whose R conservative rows come from the mix or from the fake rows alone (rho_s, combo.py:162-166).  CQL: n_qmean = B.
  *   q[c] : [B + 3R] rows = data | pi | pi_next | random  (c = 0,1; stride q_cs)
- *   tq[c]: [B] target-critic values on (s', a');  lp_next [B];  lp_pi, lp_pn [R]
+ *   tq[c]: [B * tq_rep] target-critic values on (s', a');  lp_next [B];  lp_pi, lp_pn [R]
+ *   tq_rep = 1, or N with max_q_backup (cql.py:109-120): row b's N sampled next actions are consecutive, each target
+ *   critic is maximised over them before the min over critics, and lp_next is not used.
  * Computes the TD target, the 3-way logsumexp per repeat row (the reference's quirk), the optional Lagrange
  * multiplier step, the per-row upstream gradients dq[c][.] and the losses
  *   out_losses[0..1] = critic1/2 loss, [2] = cql_alpha loss, [3] = cql_alpha (old, clamped). */
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
                          const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
-                         int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         int tq_rep, int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
                          float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream);
 
@@ -333,6 +335,9 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
 int orlk_td_loss(const float* q, int64_t q_es, int E, const float* tq, int64_t tq_es, int E2, const float* lp_next,
                  const float* scalars, int use_alpha, const float* rew, const float* term, int B, float gamma, float* dq,
                  int64_t dq_es, float* y_out, float* out_losses, float* out_sum, void* stream);
+/* out[g][b] = max over r < rep of x[g][b * rep + r]: EDAC's max_q_backup (edac.py:113-122) keeps, per target critic, the
+ * best of `rep` sampled next actions; the result feeds orlk_td_loss as tq with use_alpha = 0. */
+int orlk_segment_max(const float* x, int64_t x_gs, int G, int B, int rep, float* out, int64_t out_gs, void* stream);
 /* IQL expectile value loss (iql.py:82-98): q = min(tq[0], tq[1]); writes dv[b], qmin[b], out_loss[0]. */
 int orlk_iql_v_loss(const float* tq, int64_t tq_es, const float* v, int B, float expectile, float* dv, float* qmin,
                     float* out_loss, void* stream);

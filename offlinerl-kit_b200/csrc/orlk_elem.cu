@@ -467,11 +467,29 @@ __global__ void k_sac_actor_loss(const float* __restrict__ q, int64_t q_es, int 
 }
 
 // ------------------------------------------------------------------------------------------ CQL critic loss
+// Bootstrap value of row b.  tq_rep == 1: min over the two target critics at (s', a'), minus alpha * log pi(a'|s') unless
+// the backup is deterministic (cql.py:121-132).  tq_rep == N > 1 (max_q_backup, cql.py:109-120): each target critic is
+// maximised over N sampled next actions first, and no entropy term is subtracted.
+__device__ __forceinline__ float next_q(const float* __restrict__ tq, int64_t tq_cs, const float* __restrict__ lp_next, int b,
+                                        int tq_rep, int det_backup, float alpha) {
+    if (tq_rep <= 1) {
+        float nq = fminf(tq[b], tq[tq_cs + b]);
+        if (!det_backup) nq -= alpha * lp_next[b];
+        return nq;
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int r = 0; r < tq_rep; ++r) {
+        m0 = fmaxf(m0, tq[(int64_t)b * tq_rep + r]);
+        m1 = fmaxf(m1, tq[tq_cs + (int64_t)b * tq_rep + r]);
+    }
+    return fminf(m0, m1);
+}
+
 __global__ void __launch_bounds__(1024)
 k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __restrict__ tq, int64_t tq_cs,
                   const float* __restrict__ lp_next, const float* __restrict__ lp_pi, const float* __restrict__ lp_pn,
-                  const float* __restrict__ rew, const float* __restrict__ term, int B, int n_qmean, int R, float log_u,
-                  float gamma, float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
+                  const float* __restrict__ rew, const float* __restrict__ term, int B, int n_qmean, int tq_rep, int R,
+                  float log_u, float gamma, float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
                   const OrlkAdamGroup* __restrict__ groups, int cql_alpha_group, float* __restrict__ cql_alpha_mv,
                   float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out) {
     orlk::pdl_enter();
@@ -481,8 +499,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
     const float invB = 1.f / (float)B, invQ = 1.f / (float)n_qmean, invR = 1.f / (float)R, invT = 1.f / T;
     float td[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        float nq = fminf(tq[b], tq[tq_cs + b]);
-        if (!det_backup) nq -= alpha * lp_next[b];
+        const float nq = next_q(tq, tq_cs, lp_next, b, tq_rep, det_backup, alpha);
         const float y = rew[b] + gamma * (1.f - term[b]) * nq;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -534,8 +551,7 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
     __syncthreads();
     const float scale = sh_scale;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        float nq = fminf(tq[b], tq[tq_cs + b]);
-        if (!det_backup) nq -= alpha * lp_next[b];
+        const float nq = next_q(tq, tq_cs, lp_next, b, tq_rep, det_backup, alpha);
         const float y = rew[b] + gamma * (1.f - term[b]) * nq;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -738,14 +754,15 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
 
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
                          const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
-                         int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
+                         int tq_rep, int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
                          float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream) {
-    ORLK_REQUIRE(B > 0 && R > 0 && A > 0 && n_qmean > 0 && n_qmean <= B, "sizes");
+    ORLK_REQUIRE(B > 0 && R > 0 && A > 0 && n_qmean > 0 && n_qmean <= B && tq_rep >= 1, "sizes");
+    ORLK_REQUIRE(tq_rep > 1 || deterministic_backup || lp_next != nullptr, "the entropy backup needs lp_next");
     ORLK_REQUIRE(!with_lagrange || (groups != nullptr && cql_alpha_mv != nullptr), "lagrange needs its Adam state");
     const float log_u = (float)log(pow(0.5, (double)A));   // cql.py:82: np.log(0.5 ** act_dim)
-    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, n_qmean, R,
-                                                           log_u, gamma, cql_weight, temperature, deterministic_backup,
+    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, n_qmean, tq_rep,
+                                                           R, log_u, gamma, cql_weight, temperature, deterministic_backup,
                                                            with_lagrange, lagrange_threshold, scalars, groups,
                                                            cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses);
     return check_launch("k_cql_critic_loss");

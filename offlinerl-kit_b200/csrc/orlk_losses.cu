@@ -224,9 +224,28 @@ __global__ void k_edac_div_final(const float* __restrict__ partial, int n, float
     out[0] = s * scale;
 }
 
+// out[g][b] = max_{r < rep} x[g][b * rep + r]   (max_q_backup: the best of `rep` sampled next actions per row)
+__global__ void k_segment_max(const float* __restrict__ x, int64_t x_gs, int G, int B, int rep, float* __restrict__ out,
+                              int64_t out_gs) {
+    orlk::pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * B) return;
+    const int g = i / B, b = i - g * B;
+    const float* src = x + g * x_gs + (int64_t)b * rep;
+    float m = -INFINITY;
+    for (int r = 0; r < rep; ++r) m = fmaxf(m, src[r]);
+    out[g * out_gs + b] = m;
+}
+
 }  // namespace
 
 extern "C" {
+
+int orlk_segment_max(const float* x, int64_t x_gs, int G, int B, int rep, float* out, int64_t out_gs, void* stream) {
+    ORLK_REQUIRE(x != nullptr && out != nullptr && G >= 1 && B > 0 && rep >= 1, "sizes");
+    orlk::launch(k_segment_max, (G * B + 255) / 256, 256, 0, (cudaStream_t)stream, x, x_gs, G, B, rep, out, out_gs);
+    return check_launch("k_segment_max");
+}
 
 int orlk_td_loss(const float* q, int64_t q_es, int E, const float* tq, int64_t tq_es, int E2, const float* lp_next,
                  const float* scalars, int use_alpha, const float* rew, const float* term, int B, float gamma, float* dq,

@@ -33,8 +33,9 @@ class EDACLearner(_BatchMixin, Learner):
         rt = self.rt
         self.policy, self.B, self.seed = policy, int(batch_size), seed
         check_plain_mlp(actor.backbone, "actor")
-        if policy._max_q_backup:
-            raise L.OrlkError("EDAC max_q_backup=True is not implemented by the CUDA engine")
+        # max_q_backup (edac.py:113-122): 10 sampled next actions per row (the count is a literal there), each target
+        # critic maximised over them, no entropy term
+        self.n_next = 10 if policy._max_q_backup else 1
         dist = actor.dist_net
         if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
             raise L.OrlkError("EDAC engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
@@ -68,14 +69,15 @@ class EDACLearner(_BatchMixin, Learner):
         self.push_groups()
         self._make_stage()
         B, A = self.B, self.A
-        self.noise = rt.zeros(2 * B * A)
-        self.noise_views = {"eps_actor": self.noise[:B * A].view(B, A), "eps_next": self.noise[B * A:].view(B, A)}
+        self.noise = rt.zeros((1 + self.n_next) * B * A)
+        self.noise_views = {"eps_actor": self.noise[:B * A].view(B, A),
+                            "eps_next": self.noise[B * A:].view(self.n_next * B, A)}
         self._built = False
 
-    def _sample(self, plan, tag, head, eps, X: Mat, logp, obs: Mat):
+    def _sample(self, plan, tag, head, eps, X: Mat, logp, obs: Mat, rep: int = 1):
         O, A, B = self.O, self.A, self.B
-        args = (head.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), B, A, X.ptr + 4 * O, X.ld, logp.data_ptr(), obs.ptr, obs.ld, O,
-                X.ptr, X.ld)
+        args = (head.data_ptr(), 2 * A, 0, rep, eps.data_ptr(), B * rep, A, X.ptr + 4 * O, X.ld, logp.data_ptr(), obs.ptr, obs.ld,
+                O, X.ptr, X.ld)
         plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
 
     def _build(self) -> None:
@@ -85,18 +87,20 @@ class EDACLearner(_BatchMixin, Learner):
         run_a = self.mlp_run(aps, B, self.nh_a, need_grad=True)
         run_ca = self.mlp_run(cps, B, nh, need_grad=True)                       # Q_e(s, a~pi) in the actor phase
         run_an = self.mlp_run(aps, B, self.nh_a, need_grad=False)
-        run_t = self.mlp_run(cps, B, nh, need_grad=False, store="T")
+        Bt = B * self.n_next
+        run_t = self.mlp_run(cps, Bt, nh, need_grad=False, store="T")
         run_c = self.mlp_run(cps, B, nh, need_grad=True)                        # Q_e(s, a_data): TD backward
         run_g = self.mlp_run(cps, B, nh, need_grad=True, share_forward=run_c)   # same activations: input-gradient chain
-        Xa, Xt, Xd = rt.zeros(B, O + A), rt.zeros(B, O + A), rt.zeros(B, O + A)
-        logp_a, lp_next, glp = rt.zeros(B), rt.zeros(B), rt.zeros(B)
+        Xa, Xt, Xd = rt.zeros(B, O + A), rt.zeros(Bt, O + A), rt.zeros(B, O + A)
+        logp_a, lp_next, glp = rt.zeros(B), rt.zeros(Bt), rt.zeros(B)
+        tq_best = rt.zeros(E, B) if self.n_next > 1 else None
         dA = rt.zeros(E, B, A)
         gin, gbar = rt.zeros(E, B, A), rt.zeros(E, B, A)
         ones = torch.ones(B, 1, dtype=torch.float32, device=self.dev)
         ubar = [rt.zeros(E, B, cps.layers[l].out_dim) for l in range(nh)]
         div_scratch = rt.zeros((B + 255) // 256)
         self._keep = [run_a, run_ca, run_an, run_t, run_c, run_g, Xa, Xt, Xd, logp_a, lp_next, glp, dA, gin, gbar, ones, ubar,
-                      div_scratch]
+                      div_scratch, tq_best]
         gb_a = make_gradbuf(rt, aps, [run_a])
         td_layout = wgrad_layout(cps, nh + 1, B)
         s_td = max(s for _, s in td_layout)
@@ -105,7 +109,7 @@ class EDACLearner(_BatchMixin, Learner):
         obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
         mXa, mXt, mXd = Mat.of(Xa), Mat.of(Xt), Mat.of(Xd)
         plan = Plan(rt, "edac")
-        nargs = (self.noise.data_ptr(), 2 * B * A, 0, 0.0, 1.0, int(self.seed), self.philox_counter.data_ptr(),
+        nargs = (self.noise.data_ptr(), (1 + self.n_next) * B * A, 0, 0.0, 1.0, int(self.seed), self.philox_counter.data_ptr(),
                  self.noise_enable.data_ptr())
         plan.add("philox", lambda: L.call("orlk_philox_fill", *nargs, rt.cur))
 
@@ -130,12 +134,17 @@ class EDACLearner(_BatchMixin, Learner):
 
         # ---- critics: TD to min_e Q'_e(s', a') - alpha logp'  +  eta * diversity      (edac.py:112-155)
         emit_forward(rt, plan, run_an, [nobs], "C.actor_next")
-        self._sample(plan, "C.sample_next", run_an.out[0], self.noise_views["eps_next"], mXt, lp_next, nobs)
+        self._sample(plan, "C.sample_next", run_an.out[0], self.noise_views["eps_next"], mXt, lp_next, nobs, rep=self.n_next)
         emit_forward(rt, plan, run_t, [mXt] * E, "C.target")
+        tq = run_t.out
+        if self.n_next > 1:
+            margs = (run_t.out.data_ptr(), Bt, E, B, self.n_next, tq_best.data_ptr(), B)
+            plan.add("C.target_max", lambda: L.call("orlk_segment_max", *margs, rt.cur))
+            tq = tq_best
         plan.add("C.concat", rt.concat([(mXd, obs, 1, Mat.of(self.act))]))
         emit_forward(rt, plan, run_c, [mXd] * E, "C.critics")
-        use_alpha = 0 if pol._deterministic_backup else 1
-        targs = (run_c.out.data_ptr(), B, E, run_t.out.data_ptr(), B, E, lp_next.data_ptr(), self.scalars.data_ptr(), use_alpha,
+        use_alpha = 0 if (pol._deterministic_backup or self.n_next > 1) else 1
+        targs = (run_c.out.data_ptr(), B, E, tq.data_ptr(), B, E, lp_next.data_ptr(), self.scalars.data_ptr(), use_alpha,
                  self.rew.data_ptr(), self.term.data_ptr(), B, float(pol._gamma), run_c.dOut.data_ptr(), B, None,
                  self.loss_dev.data_ptr() + 4 * 12, self.loss_dev.data_ptr() + 4 * LS_TD_SUM)
         plan.add("C.td_loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))

@@ -282,8 +282,9 @@ class CQLLearner(TwinCriticLearner):
         self.Bc = self.c1 - self.c0
         self.R = self.Bc * self.N
         self.Mc = B + 3 * self.R
-        if policy._max_q_backup:
-            raise L.OrlkError("CQL max_q_backup=True is not implemented by the CUDA engine")
+        # max_q_backup (cql.py:109-120): N next actions per row, each target critic maximised over them
+        self.max_q_backup = bool(policy._max_q_backup)
+        self.Rt = B * self.N if self.max_q_backup else B        # rows through the target critics
         self.with_lagrange = bool(policy._with_lagrange)
         self.g_cql = -1
         self.cql_mv = rt.zeros(2)
@@ -299,11 +300,11 @@ class CQLLearner(TwinCriticLearner):
         self._make_stage()
         # noise block: normals first (eps_actor, eps_next, eps_pi, eps_pi_next), then uniforms (rand_act)
         R = self.R
-        self.n_normal, self.n_uniform = (2 * B + 2 * R) * A, R * A
+        self.n_normal, self.n_uniform = (B + self.Rt + 2 * R) * A, R * A
         self.noise = rt.zeros(self.n_normal + self.n_uniform)
         o = 0
         views = {}
-        for name, rows in (("eps_actor", B), ("eps_next", B), ("eps_pi", R), ("eps_pi_next", R), ("rand_act", R)):
+        for name, rows in (("eps_actor", B), ("eps_next", self.Rt), ("eps_pi", R), ("eps_pi_next", R), ("rand_act", R)):
             views[name] = self.noise[o:o + rows * A].view(rows, A)
             o += rows * A
         self.noise_views = views
@@ -314,11 +315,12 @@ class CQLLearner(TwinCriticLearner):
         rt, B, O, A, R, Mc = self.rt, self.B, self.O, self.A, self.R, self.Mc
         self._alloc_actor_phase()
         self.run_actor_b = self.mlp_run(self.actor_ps, 2 * B, self.nh_a, need_grad=False)
-        self.run_target = self.mlp_run(self.critic_ps, B, self.nh_c, need_grad=False, store="T")
+        Rt, n_next = self.Rt, (self.N if self.max_q_backup else 1)
+        self.run_target = self.mlp_run(self.critic_ps, Rt, self.nh_c, need_grad=False, store="T")
         self.run_critic = self.mlp_run(self.critic_ps, Mc, self.nh_c, need_grad=True)
-        self.Xt = rt.zeros(B, O + A)
+        self.Xt = rt.zeros(Rt, (O + A + 3) // 4 * 4)[:, :O + A]
         self.Xc = rt.zeros(Mc, (O + A + 3) // 4 * 4)[:, :O + A]      # 16-byte aligned rows: a TMA operand of the first layer
-        self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(B), rt.zeros(R), rt.zeros(R)
+        self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(Rt), rt.zeros(R), rt.zeros(R)
         self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
         self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
 
@@ -342,11 +344,11 @@ class CQLLearner(TwinCriticLearner):
         plan.branch(1)
         if fuse_hs:     # one head pass feeds a'(s'), N x a(s) and N x a(s'): head + three samplers in one launch
             self._emit_head_sample(plan, "C.actor.head_sample", ab, [
-                (B, 2 * B, 1, v["eps_next"], Xt, self.lp_next, nobs),
+                (B, 2 * B, n_next, v["eps_next"], Xt, self.lp_next, nobs),
                 (c0, c1, self.N, v["eps_pi"], Xc.rows_(B, B + R), self.lp_pi, cobs),
                 (B + c0, B + c1, self.N, v["eps_pi_next"], Xc.rows_(B + R, B + 2 * R), self.lp_pn, cobs)])
         else:
-            self._emit_sample(plan, "C.sample_next", head, B, 1, v["eps_next"], B, Xt, self.lp_next, nobs)
+            self._emit_sample(plan, "C.sample_next", head, B, n_next, v["eps_next"], Rt, Xt, self.lp_next, nobs)
             plan.branch(2)
             self._emit_sample(plan, "C.sample_pi", head, c0, self.N, v["eps_pi"], R, Xc.rows_(B, B + R), self.lp_pi, cobs)
             plan.branch(3)
@@ -365,8 +367,8 @@ class CQLLearner(TwinCriticLearner):
         emit_forward(rt, plan, cr, [Xc, Xc], "C.critic")
         plan.join()
         pol = self.policy
-        largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), B, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
-                 self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, self.n_real, R, A, self.gamma,
+        largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), Rt, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
+                 self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, self.n_real, n_next, R, A, self.gamma,
                  float(pol._cql_weight), float(pol._temperature), int(bool(pol._deterministic_backup)),
                  int(self.with_lagrange), float(pol._lagrange_threshold), self.scalars.data_ptr(), self.groups_ptr,
                  max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1)

@@ -285,13 +285,14 @@ class COMBOOracle(CQLOracle):
 
 
 class EDACOracle(_Learner, _AutoAlpha):
-    """policy/model_free/edac.py:88-166.  noise: ``eps_actor`` [B,A] (:96), ``eps_next`` [B,A] (:125)."""
+    """policy/model_free/edac.py:88-166.  noise: ``eps_actor`` [B,A] (:96), ``eps_next`` [B,A] (:125), or
+    [B*10,A] with max_q_backup (:117; the repeat count 10 is hard-coded there)."""
 
     def __init__(self, state, actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, alpha=0.2,
-                 deterministic_backup=True, eta=1.0):
+                 deterministic_backup=True, eta=1.0, max_q_backup=False):
         super().__init__(state, ("actor", "critics"))
         self.tau, self.gamma, self.eta = tau, gamma, eta
-        self.det_backup = deterministic_backup
+        self.det_backup, self.max_q_backup = deterministic_backup, max_q_backup
         self.actor_optim = self._adam("actor", actor_lr)
         self.critics_optim = self._adam("critics", critic_lr)
         self._init_alpha(alpha, clamp01=True)
@@ -311,10 +312,16 @@ class EDACOracle(_Learner, _AutoAlpha):
         alpha_loss = self._alpha_update(lp)
 
         with torch.no_grad():
-            na, nlp = nets.actforward(p, "actor", nobs, noise["eps_next"])
-            nq = nets.ensemble_critic(p, "critics_old", nobs, na).min(0)[0]
-            if not self.det_backup:
-                nq = nq - self.alpha * nlp
+            if self.max_q_backup:                                                     # :113-122
+                B = obs.shape[0]
+                tn = nobs.unsqueeze(1).repeat(1, 10, 1).view(B * 10, nobs.shape[-1])
+                ta, _ = nets.actforward(p, "actor", tn, noise["eps_next"])
+                nq = nets.ensemble_critic(p, "critics_old", tn, ta).view(E, B, 10, 1).max(2)[0].view(E, B, 1).min(0)[0]
+            else:
+                na, nlp = nets.actforward(p, "actor", nobs, noise["eps_next"])
+                nq = nets.ensemble_critic(p, "critics_old", nobs, na).min(0)[0]
+                if not self.det_backup:
+                    nq = nq - self.alpha * nlp
         target = rew + self.gamma * (1 - term) * nq
         qs = nets.ensemble_critic(p, "critics", obs, act)
         loss = (qs - target.unsqueeze(0)).pow(2).mean(dim=(1, 2)).sum()

@@ -123,14 +123,15 @@ def build_sac_like(O, A, hidden, device="cpu"):
     return ActorProb(actor_backbone, dist, device), Critic(c1b, device), Critic(c2b, device)
 
 
-def gen_cql(name, O, A, hidden, B, N, n_steps, with_lagrange, full_state, det_backup=True, n_data=4096, seed=0):
+def gen_cql(name, O, A, hidden, B, N, n_steps, with_lagrange, full_state, det_backup=True, n_data=4096, seed=0,
+            max_q_backup=False):
     data = make_dataset(n_data, O, A, seed=0)
     torch.manual_seed(seed)
     actor, c1, c2 = build_sac_like(O, A, hidden)
     for i, m in enumerate((actor, c1, c2)):
         overwrite_params(m, 100 + i)
     hyper = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, cql_weight=5.0, temperature=1.0,
-                 max_q_backup=False, deterministic_backup=det_backup, with_lagrange=with_lagrange,
+                 max_q_backup=max_q_backup, deterministic_backup=det_backup, with_lagrange=with_lagrange,
                  lagrange_threshold=10.0, cql_alpha_lr=3e-4, num_repeat_actions=N)
     alpha_lr, target_entropy = 1e-4, -A
     log_alpha = torch.zeros(1, requires_grad=True)
@@ -141,7 +142,7 @@ def gen_cql(name, O, A, hidden, B, N, n_steps, with_lagrange, full_state, det_ba
                     action_space=gym.spaces.Box(-1, 1, (A,)), tau=hyper["tau"], gamma=hyper["gamma"],
                     alpha=(target_entropy, log_alpha, torch.optim.Adam([log_alpha], lr=alpha_lr)),
                     cql_weight=hyper["cql_weight"], temperature=hyper["temperature"],
-                    max_q_backup=False, deterministic_backup=det_backup, with_lagrange=with_lagrange,
+                    max_q_backup=max_q_backup, deterministic_backup=det_backup, with_lagrange=with_lagrange,
                     lagrange_threshold=hyper["lagrange_threshold"], cql_alpha_lr=hyper["cql_alpha_lr"],
                     num_repeart_actions=N)
     pol.train()
@@ -154,7 +155,7 @@ def gen_cql(name, O, A, hidden, B, N, n_steps, with_lagrange, full_state, det_ba
         torch.manual_seed(1000 + t)
         ref_loss = pol.learn(batches[t])
         torch.manual_seed(1000 + t)
-        noise = {"eps_actor": torch.randn(B, A), "eps_next": torch.randn(B, A),
+        noise = {"eps_actor": torch.randn(B, A), "eps_next": torch.randn(R if max_q_backup else B, A),
                  "rand_act": torch.FloatTensor(R, A).uniform_(-1.0, 1.0),
                  "eps_pi": torch.randn(R, A), "eps_pi_next": torch.randn(R, A)}
         ora_loss = ora.step(batches[t], noise)
@@ -274,7 +275,7 @@ def gen_sac(name, O, A, hidden, B, n_steps, full_state, n_data=4096, seed=0):
     save(name, store, meta, full_state)
 
 
-def gen_edac(name, O, A, hidden, E, B, n_steps, full_state, eta=1.0, n_data=4096, seed=0):
+def gen_edac(name, O, A, hidden, E, B, n_steps, full_state, eta=1.0, n_data=4096, seed=0, max_q_backup=False):
     data = make_dataset(n_data, O, A, seed=0)
     actor_backbone = MLP(input_dim=O, hidden_dims=hidden)
     dist = TanhDiagGaussian(latent_dim=actor_backbone.output_dim, output_dim=A, unbounded=True, conditioned_sigma=True)
@@ -282,14 +283,14 @@ def gen_edac(name, O, A, hidden, E, B, n_steps, full_state, eta=1.0, n_data=4096
     critics = EnsembleCritic(O, A, hidden, num_ensemble=E, device="cpu")
     overwrite_params(actor, 120)
     overwrite_params(critics, 121)
-    hyper = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, deterministic_backup=False, eta=eta)
+    hyper = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, deterministic_backup=False, eta=eta, max_q_backup=max_q_backup)
     alpha_lr, target_entropy = 1e-4, -A
     log_alpha = torch.zeros(1, requires_grad=True)
     pol = EDACPolicy(actor, critics, torch.optim.Adam(actor.parameters(), lr=hyper["actor_lr"]),
                      torch.optim.Adam(critics.parameters(), lr=hyper["critic_lr"]),
                      tau=hyper["tau"], gamma=hyper["gamma"],
                      alpha=(target_entropy, log_alpha, torch.optim.Adam([log_alpha], lr=alpha_lr)),
-                     max_q_backup=False, deterministic_backup=False, eta=eta)
+                     max_q_backup=max_q_backup, deterministic_backup=False, eta=eta)
     pol.train()
     pre = {k: v.detach().clone() for k, v in pol.state_dict().items()}
     ora = algos.EDACOracle(pre, alpha=(target_entropy, 0.0, alpha_lr), **hyper)
@@ -299,7 +300,7 @@ def gen_edac(name, O, A, hidden, E, B, n_steps, full_state, eta=1.0, n_data=4096
         torch.manual_seed(3000 + t)
         ref_loss = pol.learn({k: v.clone() for k, v in batches[t].items()})
         torch.manual_seed(3000 + t)
-        noise = {"eps_actor": torch.randn(B, A), "eps_next": torch.randn(B, A)}
+        noise = {"eps_actor": torch.randn(B, A), "eps_next": torch.randn(B * 10 if max_q_backup else B, A)}
         ora_loss = ora.step(batches[t], noise)
         check_losses(ref_loss, ora_loss, f"{name} step {t}")
         check_state(pol.state_dict(), ora.state_dict(), f"{name} step {t}")
@@ -538,6 +539,9 @@ if __name__ == "__main__":
     run(gen_cql, "cql_hc", O=17, A=6, hidden=[256, 256, 256], B=256, N=10, n_steps=2, with_lagrange=False, full_state=False)
     run(gen_cql, "cql_hc_lagrange", O=17, A=6, hidden=[256, 256, 256], B=256, N=10, n_steps=2, with_lagrange=True,
             full_state=False)
+    run(gen_cql, "cql_small_maxq", B=16, N=4, n_steps=3, with_lagrange=True, full_state=True, max_q_backup=True, **small)
+    run(gen_cql, "cql_hc_maxq", O=17, A=6, hidden=[256, 256, 256], B=256, N=10, n_steps=2, with_lagrange=False,
+        full_state=False, max_q_backup=True)
     run(gen_cql, "cql_hopper", O=11, A=3, hidden=[256, 256, 256], B=256, N=10, n_steps=1, with_lagrange=False,
             full_state=False)
     run(gen_combo, "combo_small_mix", n_real=10, n_fake=6, N=4, n_steps=3, rho_s="mix", with_lagrange=False, full_state=True,
@@ -551,6 +555,7 @@ if __name__ == "__main__":
     run(gen_sac, "sac_small", O=5, A=3, hidden=[32, 32], B=16, n_steps=3, full_state=True)
     run(gen_sac, "sac_hc", O=17, A=6, hidden=[256, 256], B=256, n_steps=2, full_state=False)
     run(gen_edac, "edac_small", O=5, A=3, hidden=[32, 32, 32], E=4, B=16, n_steps=3, full_state=True)
+    run(gen_edac, "edac_small_maxq", O=5, A=3, hidden=[32, 32, 32], E=4, B=16, n_steps=3, full_state=True, max_q_backup=True)
     run(gen_edac, "edac_hc", O=17, A=6, hidden=[256, 256, 256], E=10, B=256, n_steps=1, full_state=False)
     run(gen_iql, "iql_small", O=5, A=3, hidden=[32, 32], B=16, n_steps=3, full_state=True)
     run(gen_iql, "iql_walker", O=17, A=6, hidden=[256, 256], B=256, n_steps=2, full_state=False)

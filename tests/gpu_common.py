@@ -47,7 +47,7 @@ def build_policy(meta, device="cuda:0"):
         actor = tanh_actor()
         critics = EnsembleCritic(O, A, hid, num_ensemble=meta["E"], device=device)
         return P.EDACPolicy(actor, critics, adam(actor, hy["actor_lr"]), adam(critics, hy["critic_lr"]), tau=hy["tau"],
-                            gamma=hy["gamma"], alpha=alpha_tuple(), max_q_backup=False,
+                            gamma=hy["gamma"], alpha=alpha_tuple(), max_q_backup=hy.get("max_q_backup", False),
                             deterministic_backup=hy["deterministic_backup"], eta=hy["eta"])
     if algo == "iql":
         bb = MLP(O, hid, dropout_rate=None)
@@ -112,7 +112,10 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
         for k in ref:
             assert abs(out[k] - ref[k]) <= tol * max(1.0, abs(ref[k])), (t, k, out[k], ref[k])
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
-        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol if elementwise else 10 * lr_atol)
+        # an element whose gradient is a rounding-level cancellation can take Adam's +-lr step the other way in every
+        # step: the element-wise slack grows by 2 lr per step (2.5 lr after the first)
+        step_atol = lr_atol * (1 + 0.8 * t)
+        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=step_atol if elementwise else 10 * lr_atol)
     post = g.group("post")
     if post and n_steps == m["n_steps"]:
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
@@ -173,7 +176,7 @@ def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", 
         for k in ref:
             assert abs(out[k] - ref[k]) <= tol * max(1.0, abs(ref[k])), (t, k, out[k], ref[k])
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
-        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol)
+        assert_stats_close(sd, g.group(f"stats{t}"), tol=tol, lr_atol=lr_atol * (1 + 0.8 * t))
     post = g.group("post")
     if post:
         sd = {k: v.detach().cpu() for k, v in policy.state_dict().items()}

@@ -171,12 +171,14 @@ def assert_stats_close(state: Dict[str, torch.Tensor], stats: Dict[str, np.ndarr
     """Compare a state dict with the golden per-tensor fingerprints.
 
     The three norms are compared relatively; the 64 sampled elements use
-    ``rtol=tol`` plus ``atol=lr_atol`` (Adam's sign sensitivity, SURVEY.md section 7 "hard parts").
+    ``rtol=tol`` plus ``atol=lr_atol`` (Adam's sign sensitivity, SURVEY.md section 7 "hard parts": the first Adam
+    steps move every element by about +-lr whatever the size of its gradient, so an element whose gradient is a
+    rounding-level cancellation may legitimately move the other way).  The norms get room for three such elements.
     """
     for k, ref in stats.items():
         if any(s in k for s in skip):
             continue
         got = tensor_stats(state[k])
         assert got.shape == ref.shape, k
-        np.testing.assert_allclose(got[1:3], ref[1:3], rtol=tol, err_msg=k)
+        np.testing.assert_allclose(got[1:3], ref[1:3], rtol=tol, atol=3 * lr_atol, err_msg=k)
         np.testing.assert_allclose(got[3:], ref[3:], rtol=tol, atol=lr_atol + 1e-7, err_msg=k)

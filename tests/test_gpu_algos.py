@@ -26,7 +26,7 @@ def test_td3bc_matches_reference(name):
     run_golden_steps(Golden(name), tol=TOL, verbose=True)
 
 
-@pytest.mark.parametrize("name", ["edac_small", "edac_hc"])
+@pytest.mark.parametrize("name", ["edac_small", "edac_hc", "edac_small_maxq"])
 def test_edac_matches_reference(name):
     """Ensemble critics + the input-gradient diversity loss (hand-derived double backward) vs the reference's autograd."""
     from tests.gpu_common import run_golden_steps

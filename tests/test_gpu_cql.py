@@ -7,7 +7,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4      # north_star: losses / parameters within 1e-4 relative in fp32
 
 
-@pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hopper", "cql_hc", "cql_hc_lagrange"])
+@pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hopper", "cql_hc", "cql_hc_lagrange",
+                                  "cql_small_maxq", "cql_hc_maxq"])
 @pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
 def test_cql_matches_reference(name, precision):
     """fp32 = SIMT FFMA GEMMs everywhere; tf32x3 = the wide critic GEMMs on tcgen05 with hi/lo operand split.

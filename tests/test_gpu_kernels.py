@@ -429,19 +429,26 @@ def test_cql_critic_loss_vs_autograd(rt):
     gen = torch.Generator().manual_seed(6)
     # (B, rows feeding the conservative term, rows in the `- w mean Q` term): CQL has all three equal; COMBO's
     # rho_s="mix" has nq = real rows, rho_s="model" additionally draws the conservative rows from the fake half
-    for (B, N, A, det, lag, Bc, nq_rows) in [(16, 4, 3, 1, 0, 16, 16), (256, 10, 6, 0, 1, 256, 256), (256, 10, 6, 1, 1, 256, 256),
-                                             (256, 10, 6, 1, 1, 256, 128), (256, 10, 6, 0, 0, 128, 128), (24, 4, 3, 1, 1, 15, 9)]:
+    # the last field: max_q_backup (cql.py:109-120) -- N target values per row, max over them, no entropy term
+    for (B, N, A, det, lag, Bc, nq_rows, mqb) in [(16, 4, 3, 1, 0, 16, 16, 0), (256, 10, 6, 0, 1, 256, 256, 0),
+                                                  (256, 10, 6, 1, 1, 256, 256, 0), (256, 10, 6, 1, 1, 256, 128, 0),
+                                                  (256, 10, 6, 0, 0, 128, 128, 0), (24, 4, 3, 1, 1, 15, 9, 0),
+                                                  (16, 4, 3, 0, 0, 16, 16, 1), (256, 10, 6, 1, 1, 256, 128, 1)]:
         R = Bc * N
         Mc = B + 3 * R
+        rep = N if mqb else 1
         q = torch.randn(2, Mc, generator=gen) * 3
-        tq = torch.randn(2, B, generator=gen)
+        tq = torch.randn(2, B * rep, generator=gen)
         lpn, lpp, lpq = torch.randn(B, generator=gen), torch.randn(R, generator=gen), torch.randn(R, generator=gen)
         rew, term = torch.randn(B, generator=gen), (torch.rand(B, generator=gen) < 0.1).float()
         gamma, w, T, thr, alpha, cla0 = 0.99, 5.0, 1.3, 10.0, 0.7, 0.2
         qd = q.clone().double().requires_grad_(True)
-        nq = torch.min(tq[0], tq[1]).double()
-        if not det:
-            nq = nq - alpha * lpn.double()
+        if mqb:
+            nq = torch.min(tq[0].view(B, N).max(1)[0], tq[1].view(B, N).max(1)[0]).double()
+        else:
+            nq = torch.min(tq[0], tq[1]).double()
+            if not det:
+                nq = nq - alpha * lpn.double()
         y = rew.double() + gamma * (1 - term.double()) * nq
         cla = torch.tensor([cla0], dtype=torch.double, requires_grad=True)
         losses = []
@@ -467,8 +474,8 @@ def test_cql_critic_loss_vs_autograd(rt):
         dev = lambda t: t.to(DEV)
         qg, tqg, a1, a2, a3, rg, tg = map(dev, (q, tq, lpn, lpp, lpq, rew, term))
         dq, out = torch.zeros(2, Mc, device=DEV), torch.zeros(4, device=DEV)
-        L.call("orlk_cql_critic_loss", qg.data_ptr(), Mc, tqg.data_ptr(), B, a1.data_ptr(), a2.data_ptr(), a3.data_ptr(),
-               rg.data_ptr(), tg.data_ptr(), B, nq_rows, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
+        L.call("orlk_cql_critic_loss", qg.data_ptr(), Mc, tqg.data_ptr(), B * rep, a1.data_ptr(), a2.data_ptr(), a3.data_ptr(),
+               rg.data_ptr(), tg.data_ptr(), B, nq_rows, rep, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
                mv.data_ptr(), dq.data_ptr(), Mc, out.data_ptr(), rt.cur)
         torch.cuda.synchronize()
         _close(out[0], total[0], rtol=2e-5, atol=1e-4, msg="critic1 loss")

@@ -30,7 +30,8 @@ def _run(g, ora, with_noise=True):
                 assert rel_err(sd[k].numpy(), v) < TOL, k
 
 
-@pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hc", "cql_hc_lagrange", "cql_hopper"])
+@pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hc", "cql_hc_lagrange", "cql_hopper", "cql_small_maxq",
+                                  "cql_hc_maxq"])
 def test_cql(name):
     g = Golden(name)
     _run(g, algos.CQLOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
@@ -49,7 +50,7 @@ def test_sac(name):
     _run(g, algos.SACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
 
 
-@pytest.mark.parametrize("name", ["edac_small", "edac_hc"])
+@pytest.mark.parametrize("name", ["edac_small", "edac_hc", "edac_small_maxq"])
 def test_edac(name):
     g = Golden(name)
     _run(g, algos.EDACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
