@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 18
+#define ORLK_ABI_VERSION 19
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -375,11 +375,13 @@ int orlk_dyn_val_mse(const float* out, const float* y, int E, int Bn, int D, flo
 /* Imagination epilogue (ensemble_dynamics.py:43-77): term_kind 0 halfcheetah, 1 hopper, 2 walker2d, 3 never
  * (utils/termination_fns.py).  Reference-stream mode: noise [E][S][D] float64 and midx [S] are the reference's two
  * NumPy draws.  Device mode (noise == NULL / midx == NULL): noise32 [S][D] normals for the chosen member and
- * pick_u [S] uniforms in [0,1) selecting elites[floor(u * n_elites)]. */
+ * pick_u [S] uniforms in [0,1) selecting elites[floor(u * n_elites)].
+ * uncertainty_mode (ensemble_dynamics.py:60-72): 0 "aleatoric" max_e ||sigma_e||, 1 "pairwise-diff"
+ * max_e ||m_e - mean_e m_e||, 2 "ensemble_std" sqrt(mean_d var_e m_e[d]) over the members' predicted next states m_e. */
 int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, const float* min_lv, const float* obs,
                   int64_t ld_obs, const double* noise, const int* midx, const float* noise32, const float* pick_u,
-                  const int* elites, int n_elites, int term_kind, float penalty_coef, float* next_obs, float* reward,
-                  float* raw_reward, float* penalty, unsigned char* terminal, void* stream);
+                  const int* elites, int n_elites, int term_kind, float penalty_coef, int uncertainty_mode, float* next_obs,
+                  float* reward, float* raw_reward, float* penalty, unsigned char* terminal, void* stream);
 /* Stable compaction of rows with drop[i] == 0 (mopo.py:69-73); *count_out = number of survivors. */
 int orlk_compact_rows(const unsigned char* drop, int S, const float* src, int64_t ld_src, int w, float* dst, int64_t ld_dst,
                       int* count_out, void* stream);

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -122,7 +122,7 @@ _PROTOS = {
     "orlk_sumsq_chunks": [_L], "orlk_sumsq": [_P, _L, _F, _P, _P],
     "orlk_dyn_nll": [_P, _P, _I, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P],
     "orlk_dyn_val_mse": [_P, _P, _I, _I, _I, _P, _P],
-    "orlk_dyn_step": [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P],
+    "orlk_dyn_step": [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
     "orlk_compact_rows": [_P, _I, _P, _L, _I, _P, _L, _P, _P],
     "orlk_adam_step": [_P, _I, _I, _P, _P],
     "orlk_step_end": [_P, C.c_uint, _P, _P],

@@ -152,7 +152,7 @@ __global__ void k_dyn_step(const float* __restrict__ out, int E, int S, int D, c
                            const float* __restrict__ min_lv, const float* __restrict__ obs, int64_t ld_obs,
                            const double* __restrict__ noise, const int* __restrict__ midx, const float* __restrict__ noise32,
                            const float* __restrict__ pick_u, const int* __restrict__ elites, int n_elites, int term_kind,
-                           float penalty_coef,
+                           float penalty_coef, int unc_mode,
                            float* __restrict__ next_obs, float* __restrict__ reward, float* __restrict__ raw_reward,
                            float* __restrict__ penalty, unsigned char* __restrict__ terminal) {
     orlk::pdl_enter();
@@ -180,6 +180,29 @@ __global__ void k_dyn_step(const float* __restrict__ out, int E, int S, int D, c
             }
         }
         pen = fmaxf(pen, sqrtf(n2));
+    }
+    if (unc_mode != 0) {
+        // disagreement of the members' predicted next states m_e = obs + delta_e  (ensemble_dynamics.py:63-70):
+        //   1 "pairwise-diff": max_e || m_e - mean_e m_e ||      2 "ensemble_std": sqrt( mean_d var_e m_e[d] )
+        float mbar[64];
+        for (int d = 0; d < O; ++d) mbar[d] = 0.f;
+        for (int e = 0; e < E; ++e) {
+            const float* o = out + ((int64_t)e * S + s) * 2 * D;
+            for (int d = 0; d < O; ++d) mbar[d] += o[d] + obs[(int64_t)s * ld_obs + d];
+        }
+        for (int d = 0; d < O; ++d) mbar[d] /= (float)E;
+        float worst = 0.f, var_sum = 0.f;
+        for (int e = 0; e < E; ++e) {
+            const float* o = out + ((int64_t)e * S + s) * 2 * D;
+            float n2 = 0.f;
+            for (int d = 0; d < O; ++d) {
+                const float df = (o[d] + obs[(int64_t)s * ld_obs + d]) - mbar[d];
+                n2 += df * df;
+            }
+            worst = fmaxf(worst, sqrtf(n2));
+            var_sum += n2;
+        }
+        pen = unc_mode == 1 ? worst : sqrtf(var_sum / (float)E / (float)O);
     }
     for (int d = 0; d < O; ++d) next_obs[(int64_t)s * O + d] = samp[d];
     raw_reward[s] = samp[O];
@@ -262,15 +285,16 @@ int orlk_dyn_val_mse(const float* out, const float* y, int E, int Bn, int D, flo
 
 int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, const float* min_lv, const float* obs,
                   int64_t ld_obs, const double* noise, const int* midx, const float* noise32, const float* pick_u,
-                  const int* elites, int n_elites, int term_kind, float penalty_coef, float* next_obs, float* reward,
-                  float* raw_reward, float* penalty, unsigned char* terminal, void* stream) {
+                  const int* elites, int n_elites, int term_kind, float penalty_coef, int uncertainty_mode, float* next_obs,
+                  float* reward, float* raw_reward, float* penalty, unsigned char* terminal, void* stream) {
     ORLK_REQUIRE(E > 0 && S > 0 && D > 1 && D <= 64, "sizes (D <= 64)");
     ORLK_REQUIRE(term_kind >= 0 && term_kind <= 3, "termination kind");
+    ORLK_REQUIRE(uncertainty_mode >= 0 && uncertainty_mode <= 2, "uncertainty mode");
     ORLK_REQUIRE(noise != nullptr || noise32 != nullptr, "noise");
     ORLK_REQUIRE(midx != nullptr || (pick_u != nullptr && elites != nullptr && n_elites > 0), "elite selection");
     orlk::launch(k_dyn_step, (S + 127) / 128, 128, 0, (cudaStream_t)stream, out, E, S, D, max_lv, min_lv, obs, ld_obs, noise, midx, noise32,
-                                                                 pick_u, elites, n_elites, term_kind, penalty_coef, next_obs, reward,
-                                                                 raw_reward, penalty, terminal);
+                                                                 pick_u, elites, n_elites, term_kind, penalty_coef, uncertainty_mode,
+                                                                 next_obs, reward, raw_reward, penalty, terminal);
     return check_launch("k_dyn_step");
 }
 

@@ -16,6 +16,9 @@ from . import _lib as L
 from .utils.scaler import StandardScaler
 
 
+UNCERTAINTY_MODES = {"aleatoric": 0, "pairwise-diff": 1, "ensemble_std": 2}      # ensemble_dynamics.py:60-70
+
+
 class BaseDynamics:
     def __init__(self, model: nn.Module, optim: torch.optim.Optimizer) -> None:
         self.model, self.optim = model, optim
@@ -31,8 +34,8 @@ class EnsembleDynamics(BaseDynamics):
         super().__init__(model, optim)
         self.scaler, self.terminal_fn = scaler, terminal_fn
         self._penalty_coef, self._uncertainty_mode = penalty_coef, uncertainty_mode
-        if uncertainty_mode != "aleatoric":
-            raise L.OrlkError("only uncertainty_mode='aleatoric' (MOPO) is implemented by the CUDA engine")
+        if uncertainty_mode not in UNCERTAINTY_MODES:
+            raise ValueError(f"unknown uncertainty_mode {uncertainty_mode!r}")       # ensemble_dynamics.py:71-72
         self._engine = None
         self._scaler_dev = None
         self.rng = "numpy"       # "numpy": the reference's two host draws per step; "device": Philox on the GPU
@@ -74,7 +77,8 @@ class EnsembleDynamics(BaseDynamics):
                 L.call("orlk_step_end", eng.groups_ptr, 0, eng.philox_counter.data_ptr(), eng.rt.cur)
                 n32, pick = buf[:S * eng.D], buf[S * eng.D:]
                 elites = self.model.elites.data.to(device=eng.dev, dtype=torch.int32)
-        out = eng.imagine(obs, act, mu, sd, 3 if kind is None else kind, self._penalty_coef, noise64, midx, n32, pick, elites)
+        out = eng.imagine(obs, act, mu, sd, 3 if kind is None else kind, self._penalty_coef, noise64, midx, n32, pick, elites,
+                          UNCERTAINTY_MODES[self._uncertainty_mode])
         return out
 
     @torch.no_grad()

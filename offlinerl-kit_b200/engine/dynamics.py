@@ -191,7 +191,8 @@ class DynamicsEngine(Learner):
 
     def imagine(self, obs: torch.Tensor, act: torch.Tensor, mu: torch.Tensor, sd: torch.Tensor, term_kind: int,
                 penalty_coef: float, noise64: Optional[torch.Tensor], midx: Optional[torch.Tensor],
-                noise32: Optional[torch.Tensor], pick_u: Optional[torch.Tensor], elites: Optional[torch.Tensor]):
+                noise32: Optional[torch.Tensor], pick_u: Optional[torch.Tensor], elites: Optional[torch.Tensor],
+                uncertainty_mode: int = 0):
         """One imagined transition for S device-resident states; returns device tensors."""
         rt, S, O = self.rt, obs.shape[0], obs.shape[1]
         A = act.shape[1]
@@ -206,6 +207,6 @@ class DynamicsEngine(Learner):
         ptr = lambda t: t.data_ptr() if t is not None else None
         L.call("orlk_dyn_step", run.OUT.data_ptr(), self.E, S, self.D, self.ps.extra_ptr("max_logvar"),
                self.ps.extra_ptr("min_logvar"), obs.data_ptr(), obs.stride(0), ptr(noise64), ptr(midx), ptr(noise32), ptr(pick_u),
-               ptr(elites), int(elites.numel()) if elites is not None else 0, term_kind, float(penalty_coef), nobs.data_ptr(),
-               rew.data_ptr(), raw.data_ptr(), pen.data_ptr(), term.data_ptr(), rt.cur)
+               ptr(elites), int(elites.numel()) if elites is not None else 0, term_kind, float(penalty_coef), int(uncertainty_mode),
+               nobs.data_ptr(), rew.data_ptr(), raw.data_ptr(), pen.data_ptr(), term.data_ptr(), rt.cur)
         return nobs, rew, term, raw, pen

@@ -74,7 +74,7 @@ class DynamicsOracle:
     @torch.no_grad()
     def step(self, obs: np.ndarray, action: np.ndarray, mu: np.ndarray, std: np.ndarray,
              terminal_fn: Callable, penalty_coef: float, normal_noise: np.ndarray,
-             model_idxs: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, Dict]:
+             model_idxs: np.ndarray, uncertainty_mode: str = "aleatoric") -> Tuple[np.ndarray, np.ndarray, np.ndarray, Dict]:
         """ensemble_dynamics.py:28-79 with the two NumPy draws passed in.
 
         ``normal_noise`` = np.random.normal(size=[E,B,D]) (float64, :48);
@@ -93,7 +93,15 @@ class DynamicsOracle:
         terminal = terminal_fn(obs, action, next_obs)
         info = {"raw_reward": reward}
         if penalty_coef:
-            penalty = np.amax(np.linalg.norm(sd, axis=2), axis=0)       # "aleatoric", :61-62
+            if uncertainty_mode == "aleatoric":                          # :60-62
+                penalty = np.amax(np.linalg.norm(sd, axis=2), axis=0)
+            elif uncertainty_mode == "pairwise-diff":                    # :63-67
+                m = mean[..., :-1]
+                penalty = np.amax(np.linalg.norm(m - np.mean(m, axis=0), axis=2), axis=0)
+            elif uncertainty_mode == "ensemble_std":                     # :68-70
+                penalty = np.sqrt(mean[..., :-1].var(0).mean(1))
+            else:
+                raise ValueError(uncertainty_mode)
             penalty = np.expand_dims(penalty, 1).astype(np.float32)
             reward = reward - penalty_coef * penalty
             info["penalty"] = penalty

@@ -445,7 +445,17 @@ def gen_dynamics(name, O, A, hidden, E, n_elites, B, n_batches, S, full_state, t
     o_nobs, o_rew, o_term, o_info = ora.step(obs, act, mu, std, ofn, 0.5, noise, midx)
     assert rel(o_nobs, r_nobs) < 1e-5 and rel(o_rew, r_rew) < 1e-5 and np.array_equal(o_term, r_term)
     assert rel(o_info["penalty"], r_info["penalty"]) < 1e-5
-    store = {"boot": boot, "learn_loss": np.float64(ref_loss), "val": np.asarray(ref_val, np.float64),
+    other = {}
+    for mode in ("pairwise-diff", "ensemble_std"):       # the other two penalties of ensemble_dynamics.py:60-70
+        dyn._uncertainty_mode = mode
+        np.random.set_state(st)
+        _, m_rew, _, m_info = dyn.step(obs, act)
+        _, o_rew, _, o_info2 = ora.step(obs, act, mu, std, ofn, 0.5, noise, midx, uncertainty_mode=mode)
+        assert rel(o_info2["penalty"], m_info["penalty"]) < 1e-5 and rel(o_rew, m_rew) < 1e-5, mode
+        other["step_penalty_" + mode] = m_info["penalty"]
+        other["step_reward_" + mode] = m_rew
+    dyn._uncertainty_mode = "aleatoric"
+    store = {**other, "boot": boot, "learn_loss": np.float64(ref_loss), "val": np.asarray(ref_val, np.float64),
              "step_obs": obs, "step_act": act, "step_noise": noise.astype(np.float64), "step_midx": midx,
              "step_next_obs": r_nobs, "step_reward": r_rew, "step_terminal": r_term,
              "step_penalty": r_info["penalty"], "step_raw_reward": r_info["raw_reward"],

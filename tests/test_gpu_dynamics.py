@@ -48,6 +48,14 @@ def test_dynamics_learn_validate_step(name):
     assert rel_err(nobs, g["step_next_obs"]) < TOL and rel_err(rew, g["step_reward"]) < TOL
     assert np.array_equal(term, g["step_terminal"])
     assert rel_err(info["penalty"], g["step_penalty"]) < TOL and rel_err(info["raw_reward"], g["step_raw_reward"]) < TOL
+    # the two disagreement penalties (ensemble_dynamics.py:63-70) on the same draws
+    for mode in ("pairwise-diff", "ensemble_std"):
+        dyn._uncertainty_mode = mode
+        np.random.seed(11)
+        _, rew_m, _, info_m = dyn.step(g["step_obs"], g["step_act"])
+        assert rel_err(info_m["penalty"], g["step_penalty_" + mode]) < 5 * TOL, mode
+        assert rel_err(rew_m, g["step_reward_" + mode]) < TOL, mode
+    dyn._uncertainty_mode = "aleatoric"
     # device-side noise: same distribution, different stream -> only sanity-check shapes / finiteness / penalty
     dyn.rng = "device"
     nobs2, rew2, term2, info2 = dyn.step(g["step_obs"], g["step_act"])

@@ -110,6 +110,11 @@ def test_dynamics(name):
     assert rel_err(nobs, g["step_next_obs"]) < TOL and rel_err(rew, g["step_reward"]) < TOL
     assert np.array_equal(term, g["step_terminal"])
     assert rel_err(info["penalty"], g["step_penalty"]) < TOL
+    for mode in ("pairwise-diff", "ensemble_std"):      # ensemble_dynamics.py:63-70
+        _, rew_m, _, info_m = ora.step(g["step_obs"], g["step_act"], mu, std, fn, m["penalty_coef"], g["step_noise"],
+                                       g["step_midx"], uncertainty_mode=mode)
+        assert rel_err(info_m["penalty"], g["step_penalty_" + mode]) < TOL, mode
+        assert rel_err(rew_m, g["step_reward_" + mode]) < TOL, mode
 
 
 @pytest.mark.parametrize("name", ["rollout_small", "combo_rollout_uniform"])
