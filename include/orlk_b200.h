@@ -172,7 +172,7 @@ typedef struct OrlkTcGemm {
     const float* aux; int64_t ldaux, aux_gs;
     float* rowsum; int64_t rowsum_gs, rowsum_split_stride;
     int32_t M, N, K, G;
-    int32_t epi;      /* ORLK_EPI_NONE | ORLK_EPI_RELU | ORLK_EPI_RELU_MASK */
+    int32_t epi;      /* ORLK_EPI_NONE | ORLK_EPI_RELU | ORLK_EPI_RELU_MASK | ORLK_EPI_SWISH (C only, no pre-activation copy) */
     int32_t k_splits; /* as returned by orlk_tc_effective_splits */
     int32_t passes;   /* 1 or 3 */
     int32_t n_tile;   /* output columns per CTA (multiple of 16 dividing N); 0 = N.  Small-M layers use 32 so that

@@ -680,6 +680,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (p.epi == ORLK_EPI_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            } else if (p.epi == ORLK_EPI_SWISH) {       // dynamics_module.py:12-17 (inference: the pre-activation is not kept)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = x[j] / (1.f + expf(-x[j]));
             } else if (p.epi == ORLK_EPI_RELU_MASK) {
                 // columns c0 .. c0+31 live in 128-column group c0/128 at bits 8*((c0/32)%4) .. +7
                 const uint4 mb = *reinterpret_cast<const uint4*>(mask_s + row * (BN_MAX / 32) + 4 * (c0 >> 7));
@@ -862,7 +865,8 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     // B rows that TMA cannot address (the K = obs+act wide first-layer weights, pitch 23 floats) are staged by hand
     const bool b_manual = q->ldb % 4 != 0 || q->b_gs % 4 != 0 || !aligned16(q->B);
     ORLK_REQUIRE(!b_manual || q->K <= BK, "B must be 16-byte aligned with strides that are multiples of 4 floats unless K <= 32");
-    ORLK_REQUIRE(q->epi == ORLK_EPI_NONE || q->epi == ORLK_EPI_RELU || q->epi == ORLK_EPI_RELU_MASK, "epilogue");
+    ORLK_REQUIRE(q->epi == ORLK_EPI_NONE || q->epi == ORLK_EPI_RELU || q->epi == ORLK_EPI_RELU_MASK || q->epi == ORLK_EPI_SWISH,
+                 "epilogue");
     ORLK_REQUIRE(q->epi != ORLK_EPI_RELU_MASK || q->aux != nullptr, "mask epilogue needs aux");
     const int total_slabs = (q->K + BK - 1) / BK;
     int splits = q->k_splits < 1 ? 1 : q->k_splits;

@@ -6,6 +6,7 @@ The E members live in one ParamSet ('io' layout, members contiguous per tensor);
 one problem of a grouped GEMM launch; Swish and its derivative are GEMM epilogues.
 """
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -14,7 +15,8 @@ import torch
 from .. import _lib as L
 from .core import AdamT, GP, Mat, Plan, Runtime, get_runtime
 from .learner import Learner, N_LOSS
-from .nets import GradBuf, ParamSet, adam_descs, dgrad_problem, fwd_problem, pick_cfg, wgrad_problem, wgrad_splits
+from .nets import (TC_MIN_ROWS, GradBuf, ParamSet, adam_descs, dgrad_problem, fwd_problem, pick_cfg, wgrad_problem,
+                   wgrad_splits)
 
 
 class DynRun:
@@ -31,10 +33,40 @@ class DynRun:
         self.dOUT = rt.zeros(E, M, ps.layers[-1].out_dim) if need_grad else None
 
 
-def emit_dyn_forward(rt: Runtime, plan: Plan, run: DynRun, X: Callable[[int], Mat], tag: str) -> None:
+def _tc_layer_ok(ps: ParamSet, l: int, x0: Optional[Mat]) -> bool:
+    """Can layer l of the ensemble ('io' weights [member][in][out]: an MN-major B operand) run on the tensor-core kernel?"""
+    lay = ps.layers[l]
+    ok = (lay.layout == "io" and lay.out_dim % 4 == 0 and lay.out_dim <= 256 and ps.w(l, 0) % 16 == 0 and lay.w_gs % 4 == 0
+          and ps.b(l, 0) % 16 == 0)
+    if l == 0:
+        return ok and x0 is not None and x0.ld % 4 == 0 and x0.ptr % 16 == 0
+    return ok and lay.in_dim % 4 == 0
+
+
+def emit_dyn_forward(rt: Runtime, plan: Plan, run: DynRun, X: Callable[[int], Mat], tag: str, tc_passes: int = 0) -> None:
+    """tc_passes (1 or 3; 0 = off): inference passes over many rows (rollouts: 50 000 states x 7 members) go through the
+    tcgen05 kernel, one launch per layer with the members as groups and the Swish in its epilogue."""
     ps, E, M = run.ps, run.ps.G, run.M
+    shared_x = all(X(e).ptr == X(0).ptr and X(e).ld == X(0).ld for e in range(E))
+    use_tc = (tc_passes in (1, 3) and run.Z is None and M >= TC_MIN_ROWS and shared_x
+              and os.environ.get("ORLK_DYN_TC", "1") != "0"
+              and all(_tc_layer_ok(ps, l, X(0)) for l in range(run.nh + 1)))
     for l in range(run.nh + 1):
         last = l == run.nh
+        if use_tc:
+            lay = ps.layers[l]
+            K, N = lay.in_dim, lay.out_dim
+            if l == 0:
+                a, a_gs = Mat(X(0).ptr, M, K, X(0).ld), 0
+            else:
+                a, a_gs = Mat(run.H[l - 1].data_ptr(), M, K, K), M * K
+            out = run.OUT if last else run.H[l]
+            plan.add(f"{tag}.fwd{l}.tc", rt.tc_gemm(
+                A=a, a_gs=a_gs, B=Mat(ps.w(l, 0), K, N, N), b_gs=lay.w_gs, b_mn=True, G=E,
+                passes=3 if l == 0 else tc_passes,      # raw (scaled) inputs: always fp32-grade, one k-slab
+                n_tile=(N + 31) // 32 * 32, epi=L.EPI_NONE if last else L.EPI_SWISH,
+                C=Mat(out.data_ptr(), M, N, N), c_gs=M * N, bias=ps.b(l, 0), bias_gs=lay.b_gs))
+            continue
         probs = []
         for e in range(E):
             xin = X(e) if l == 0 else Mat.of(run.H[l - 1][e])
@@ -177,10 +209,10 @@ class DynamicsEngine(Learner):
             if len(self._fwd_runs) > 8:
                 self._fwd_runs.clear()
             run = DynRun(self.rt, self.ps, S, need_grad=False)
-            xbuf = self.rt.zeros(S, self.in_dim)
+            xbuf = self.rt.zeros(S, (self.in_dim + 3) // 4 * 4)[:, :self.in_dim]   # 16-byte rows: a TMA operand
             plan = Plan(self.rt, f"dyn.fwd{S}")
             xm = Mat.of(xbuf)
-            emit_dyn_forward(self.rt, plan, run, lambda e: xm, "F")
+            emit_dyn_forward(self.rt, plan, run, lambda e: xm, "F", tc_passes=self.tc_passes)
             self._fwd_runs[S] = (run, plan, xbuf)
 
     def validate(self, x: torch.Tensor, y: torch.Tensor) -> List[float]:
@@ -199,7 +231,7 @@ class DynamicsEngine(Learner):
         self._forward_alloc(S)
         xbuf = self._fwd_runs[S][2]
         L.call("orlk_dyn_input", obs.data_ptr(), obs.stride(0), act.data_ptr(), act.stride(0), mu.data_ptr(), sd.data_ptr(), S,
-               O, A, xbuf.data_ptr(), self.in_dim, rt.cur)
+               O, A, xbuf.data_ptr(), xbuf.stride(0), rt.cur)
         run = self._forward(xbuf)
         nobs = torch.empty(S, O, dtype=torch.float32, device=self.dev)
         rew, raw, pen = (torch.empty(S, 1, dtype=torch.float32, device=self.dev) for _ in range(3))

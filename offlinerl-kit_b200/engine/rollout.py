@@ -3,6 +3,7 @@ sac.py:79-86 + dynamics/ensemble_dynamics.py:28-79).  The reference ping-pongs e
 outputs per step, 6.3 M float64 normals on one core); here only the survivor count (4 bytes) crosses per step and the
 transitions are copied out once at the end."""
 import ctypes as C
+import time
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -60,6 +61,7 @@ class RolloutEngine:
             self.tc_passes = eng.tc_passes
             self._plans.clear()
         self.actor_ps.refresh_wt()
+        t_start = time.perf_counter()
         cur = torch.as_tensor(init_obss, dtype=torch.float32).to(self.dev).contiguous()
         outs = {k: [] for k in ("obss", "next_obss", "actions", "rewards", "terminals")}
         n_total, t = 0, 0
@@ -105,6 +107,9 @@ class RolloutEngine:
             if alive == 0:
                 break
             cur = nxt[:alive]
+        t_loop = time.perf_counter()
         res = {k: torch.cat(v, 0).cpu().numpy() for k, v in outs.items()}
         res["terminals"] = res["terminals"].astype(bool)
+        # where the wall time of the last call went (the loop ends with a device sync every step)
+        self.last_timing = {"loop_ms": 1e3 * (t_loop - t_start), "export_ms": 1e3 * (time.perf_counter() - t_loop)}
         return res, {"num_transitions": n_total, "reward_mean": float(res["rewards"].astype(np.float64).mean())}

@@ -67,6 +67,7 @@ def main():
         print(json.dumps({"metric": "MOPO imagined transitions/s (state-sharded rollout, all-gather included)",
                           "value": info["num_transitions"] / (ms_max * 1e-3), "unit": "transitions/s", "n_gpus": world,
                           "ms_per_rollout": ms_max, "transitions_per_rollout": info["num_transitions"], "scaling": "strong",
+                          "last_call_split_ms": getattr(pol._roll, "last_timing", None),
                           "config": {"workload": "mopo_rollout E7 hidden200x4 S50000 H5 hc"}}))
     if dist_on:
         torch.distributed.barrier()

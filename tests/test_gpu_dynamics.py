@@ -106,3 +106,37 @@ def test_mopo_rollout_matches_reference(name):
     assert len(out2["obss"]) == info2["num_transitions"]
     if uniform:
         assert np.abs(out2["actions"]).max() <= 1.0 and abs(float(out2["actions"].mean())) < 0.2
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 2e-5), ("tf32", 5e-3)])
+def test_ensemble_forward_on_tensor_cores(precision, tol):
+    """Rollout-sized ensemble inference (dynamics_module.py:83-96) goes through the tcgen05 kernel: members as groups,
+    'io' weights as an MN-major B operand, hidden width 200 inside 224-column tiles, K = 200 with a zero-filled tail
+    slab, Swish in the epilogue.  Checked against a float64 evaluation of the same layers."""
+    from offlinerlkit_b200.modules import EnsembleDynamicsModel
+    from offlinerlkit_b200.dynamics import EnsembleDynamics
+    from offlinerlkit_b200.utils.scaler import StandardScaler
+    from offlinerlkit_b200.utils.termination_fns import termination_fn_halfcheetah
+    O, A, E, S = 17, 6, 3, 5000
+    torch.manual_seed(3)
+    model = EnsembleDynamicsModel(O, A, [200, 200, 200], num_ensemble=E, num_elites=2,
+                                  weight_decays=[2.5e-5, 5e-5, 7.5e-5, 1e-4], device=DEV)
+    with torch.no_grad():
+        for lay in list(model.backbones) + [model.output_layer]:
+            lay.bias.normal_(0.0, 0.1)
+    dyn = EnsembleDynamics(model, torch.optim.Adam(model.parameters(), lr=1e-3), StandardScaler(), termination_fn_halfcheetah)
+    eng = dyn.engine
+    eng.precision = precision
+    x = torch.randn(S, O + A, device=DEV)
+    run = eng._forward(x)
+    torch.cuda.synchronize()
+    _, plan, _ = eng._fwd_runs[S]
+    assert all(lbl.endswith(".tc") for lbl, _ in plan.flat_ops), [lbl for lbl, _ in plan.flat_ops]
+    h = x.double().unsqueeze(0).repeat(E, 1, 1)
+    layers = list(model.backbones) + [model.output_layer]
+    with torch.no_grad():
+        for i, lay in enumerate(layers):
+            h = torch.bmm(h, lay.weight.double()) + lay.bias.double()
+            if i < len(layers) - 1:
+                h = h * torch.sigmoid(h)
+    assert rel_err(run.OUT.cpu().numpy(), h.cpu().numpy()) < tol
