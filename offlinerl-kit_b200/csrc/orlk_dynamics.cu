@@ -240,6 +240,80 @@ k_compact_rows(const unsigned char* __restrict__ drop, int S, const float* __res
     }
 }
 
+// Multi-CTA form of the same stable compaction, two launches over 256-row blocks:
+//   count:   counts[b] = survivors of block b
+//   scatter: block b starts at sum(counts[0..b)), a survivor's slot inside the block is its rank among the block's
+//            survivors (warp ballots + a scan of the 8 warp totals); the last block publishes the total.
+constexpr int CMP_ROWS = 256;
+
+__global__ void __launch_bounds__(CMP_ROWS)
+k_compact_count(const unsigned char* __restrict__ drop, int S, int* __restrict__ counts) {
+    orlk::pdl_enter();
+    const int i = blockIdx.x * CMP_ROWS + threadIdx.x;
+    const int keep = (i < S && !drop[i]) ? 1 : 0;
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(CMP_ROWS)
+k_compact_scatter(const unsigned char* __restrict__ drop, int S, const float* __restrict__ src, int64_t ld_src, int w,
+                  float* __restrict__ dst, int64_t ld_dst, const int* __restrict__ counts, int* __restrict__ count_out) {
+    orlk::pdl_enter();
+    __shared__ int red[CMP_ROWS / 32];
+    __shared__ int wsum[CMP_ROWS / 32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += CMP_ROWS) part += counts[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    const int i = blockIdx.x * CMP_ROWS + threadIdx.x;
+    const bool keep = i < S && !drop[i];
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int k = 0; k < CMP_ROWS / 32; ++k) b += red[k];
+        base_s = b;
+        if (blockIdx.x == gridDim.x - 1) {
+            int tot = b;
+            for (int k = 0; k < CMP_ROWS / 32; ++k) tot += wsum[k];
+            *count_out = tot;
+        }
+    }
+    __syncthreads();
+    if (keep) {
+        int pos = base_s + __popc(bal & ((1u << lane) - 1u));
+        for (int k = 0; k < warp; ++k) pos += wsum[k];
+        const float* s_row = src + (int64_t)i * ld_src;
+        float* d_row = dst + (int64_t)pos * ld_dst;
+        for (int j = 0; j < w; ++j) d_row[j] = s_row[j];
+    }
+}
+
+// per-device scratch of the two-launch compaction (block counts), grown on demand outside stream capture
+int* compact_scratch(int n_blocks) {
+    static int* buf[64] = {nullptr};
+    static int cap[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cap[dev] < n_blocks) {
+        int want = 1024;
+        while (want < n_blocks) want *= 2;
+        int* nb = nullptr;
+        if (cudaMalloc(&nb, sizeof(int) * (size_t)want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        if (buf[dev] != nullptr) cudaFree(buf[dev]);
+        buf[dev] = nb;
+        cap[dev] = want;
+    }
+    return buf[dev];
+}
+
 }  // namespace
 
 extern "C" {
@@ -301,8 +375,18 @@ int orlk_dyn_step(const float* out, int E, int S, int D, const float* max_lv, co
 int orlk_compact_rows(const unsigned char* drop, int S, const float* src, int64_t ld_src, int w, float* dst, int64_t ld_dst,
                       int* count_out, void* stream) {
     ORLK_REQUIRE(S > 0 && w > 0, "sizes");
-    orlk::launch(k_compact_rows, 1, 1024, 0, (cudaStream_t)stream, drop, S, src, ld_src, w, dst, ld_dst, count_out);
-    return check_launch("k_compact_rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    const int n_blocks = (S + CMP_ROWS - 1) / CMP_ROWS;
+    int* counts = (S > 4096 && !capturing) ? compact_scratch(n_blocks) : nullptr;    // (the scratch may need a cudaMalloc)
+    if (counts == nullptr) {
+        orlk::launch(k_compact_rows, 1, 1024, 0, st, drop, S, src, ld_src, w, dst, ld_dst, count_out);
+        return check_launch("k_compact_rows");
+    }
+    orlk::launch(k_compact_count, n_blocks, CMP_ROWS, 0, st, drop, S, counts);
+    orlk::launch(k_compact_scatter, n_blocks, CMP_ROWS, 0, st, drop, S, src, ld_src, w, dst, ld_dst, (const int*)counts, count_out);
+    return check_launch("k_compact_scatter");
 }
 
 }  // extern "C"

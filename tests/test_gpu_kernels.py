@@ -704,3 +704,24 @@ def test_narrow_fwd_and_wgrad(rt):
                G * NS * K, None, 0, 0, bp.data_ptr(), NS, G * NS, M, K, NS, G, rt.cur)
         _close(wp.sum(0), torch.einsum("gmn,gmk->gnk", dO.double(), H.double()), rtol=1e-5, atol=1e-4, msg="head wgrad W")
         _close(bp.sum(0), dO.double().sum(1), rtol=1e-5, atol=1e-4, msg="head wgrad b")
+
+
+# ------------------------------------------------------------------------------------------------ rollout compaction
+@pytest.mark.parametrize("S", [1, 100, 4096, 5000, 50_000, 70_001])
+@pytest.mark.parametrize("p_drop", [0.0, 0.3, 1.0])
+def test_compact_rows_is_stable_and_exact(rt, S, p_drop):
+    """mopo.py:69-73 (`observations = next_observations[nonterm_mask]`): survivors keep their order, rows are copied bit
+    for bit, the count is the number of survivors.  Small inputs take the single-CTA kernel, large ones the two-launch
+    block-scan form."""
+    from offlinerlkit_b200 import _lib as L
+    gen = torch.Generator().manual_seed(S)
+    w, ld = 17, 20
+    src = torch.randn(S, ld, generator=gen).to(DEV)
+    drop = (torch.rand(S, generator=gen) < p_drop).to(torch.uint8).to(DEV)
+    dst = torch.full((S, w), float("nan"), device=DEV)
+    count = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    L.call("orlk_compact_rows", drop.data_ptr(), S, src.data_ptr(), ld, w, dst.data_ptr(), w, count.data_ptr(), rt.cur)
+    torch.cuda.synchronize()
+    want = src[:, :w][drop == 0]
+    assert int(count.item()) == want.shape[0]
+    assert torch.equal(dst[:want.shape[0]], want)
