@@ -48,7 +48,10 @@ class RolloutEngine:
             self._plans[S] = (run, plan, obs)
         return self._plans[S]
 
-    def run(self, init_obss: np.ndarray, length: int, noise: Optional[Dict[str, List[np.ndarray]]] = None):
+    def run(self, init_obss: np.ndarray, length: int, noise: Optional[Dict[str, List[np.ndarray]]] = None,
+            device_out: bool = False):
+        """device_out: return the transitions as device tensors (terminals uint8) instead of the reference's NumPy
+        arrays -- for callers that keep working on the device (parallel.rollout_state_sharded)."""
         rt, O, A = self.rt, self.O, self.A
         dyn = self.dyn
         E, D = dyn.engine.E, dyn.engine.D
@@ -108,6 +111,10 @@ class RolloutEngine:
                 break
             cur = nxt[:alive]
         t_loop = time.perf_counter()
+        if device_out:
+            res = {k: torch.cat(v, 0) for k, v in outs.items()}
+            self.last_timing = {"loop_ms": 1e3 * (t_loop - t_start), "export_ms": 0.0}
+            return res, {"num_transitions": n_total, "reward_mean": float(res["rewards"].double().mean().item())}
         res = {k: torch.cat(v, 0).cpu().numpy() for k, v in outs.items()}
         res["terminals"] = res["terminals"].astype(bool)
         # where the wall time of the last call went (the loop ends with a device sync every step)

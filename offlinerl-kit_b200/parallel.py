@@ -109,21 +109,56 @@ def _gather_ragged(arr, device) -> "np.ndarray":
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0).cpu().numpy()
 
 
-def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cpu"):
+def _gather_packed(local, device):
+    """The same gather for a dict of DEVICE tensors with a common first dimension: the columns are packed into one
+    [n, W] fp32 matrix, so the whole exchange is one size all-gather, one padded all-gather and one device-to-host copy
+    (uint8 / bool columns survive the round trip through fp32 exactly)."""
+    import numpy as np
+    world = dist.get_world_size()
+    keys = list(local)
+    n_loc = int(local[keys[0]].shape[0])
+    cols = [local[k].reshape(n_loc, -1) for k in keys]
+    widths = [int(c.shape[1]) for c in cols]
+    pack = torch.cat([c.to(torch.float32) for c in cols], 1).contiguous()
+    n = torch.tensor([n_loc], dtype=torch.int64, device=pack.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(v.item()) for v in sizes]
+    pad = torch.zeros((max(sizes + [1]), pack.shape[1]), dtype=torch.float32, device=pack.device)
+    pad[:n_loc] = pack
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    host = torch.cat([p[:v] for p, v in zip(parts, sizes)], 0).cpu().numpy()
+    out, c0 = {}, 0
+    for k, w in zip(keys, widths):
+        a = host[:, c0:c0 + w]
+        kind = local[k].dtype
+        out[k] = np.ascontiguousarray(a != 0 if kind in (torch.uint8, torch.bool) else a)
+        c0 += w
+    return out
+
+
+def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cpu", device_out: bool = False):
     """``MOPOPolicy.rollout`` (policy/model_based/mopo.py:45-79) with the start states split over the ranks.
 
     Every rank holds the full dynamics ensemble and the actor (replicated after training), imagines the whole horizon
     for its own contiguous share of ``init_obss`` with no communication, and the resulting transitions are all-gathered
     in rank order, so every rank ends up with the same fake-buffer batch.  ``rollout_fn(obs, length) -> (dict, info)`` is
     the single-GPU rollout.  The random streams differ per rank, so the result is distributed like - not bit-equal to -
-    a single-GPU rollout of all states.  Single process: plain call."""
+    a single-GPU rollout of all states.  Single process: plain call.
+    ``device_out``: ``rollout_fn`` takes ``device_out=True`` and then returns device tensors (MOPOPolicy / COMBOPolicy
+    do); the transitions are exchanged straight from device memory and reach the host once."""
     import numpy as np
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return rollout_fn(init_obss, rollout_length)
     rank, world = dist.get_rank(), dist.get_world_size()
     lo, hi = shard_rows(len(init_obss), rank, world)
-    local, info = rollout_fn(init_obss[lo:hi], rollout_length)
-    out = {k: _gather_ragged(v, device) for k, v in local.items()}
+    if device_out:
+        local, info = rollout_fn(init_obss[lo:hi], rollout_length, device_out=True)
+        out = _gather_packed(local, device)
+    else:
+        local, info = rollout_fn(init_obss[lo:hi], rollout_length)
+        out = {k: _gather_ragged(v, device) for k, v in local.items()}
     n_local = float(len(next(iter(local.values())))) if local else 0.0
     n_tot, r_sum = reduce_scalars([n_local, float(info.get("reward_mean", 0.0)) * n_local], "sum", device)
     merged = dict(info)

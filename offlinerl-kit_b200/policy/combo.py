@@ -33,8 +33,8 @@ class COMBOPolicy(CQLPolicy):
         self._roll = None
         self._split = None      # (n_real, n_fake) the step graph was built for
 
-    def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None
-                ) -> Tuple[Dict[str, np.ndarray], Dict]:
+    def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None,
+                device_out: bool = False) -> Tuple[Dict[str, np.ndarray], Dict]:
         """noise (parity tests): per-step lists ``eps`` [S_t, A] (or ``actions`` [S_t, A] with uniform_rollout),
         ``normal`` [E, S_t, D] float64, ``midx`` [S_t]."""
         from ..engine.rollout import RolloutEngine
@@ -43,7 +43,7 @@ class COMBOPolicy(CQLPolicy):
             if self._uniform_rollout:
                 uniform = (float(self.action_space.low[0]), float(self.action_space.high[0]))
             self._roll = RolloutEngine(self, uniform=uniform)
-        return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise)
+        return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise, device_out)
 
     def _make_engine(self, batch_size: int):
         from ..engine.sac_family import CQLLearner

@@ -19,13 +19,13 @@ class MOPOPolicy(SACPolicy):
         self.dynamics = dynamics
         self._roll = None
 
-    def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None
-                ) -> Tuple[Dict[str, np.ndarray], Dict]:
+    def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None,
+                device_out: bool = False) -> Tuple[Dict[str, np.ndarray], Dict]:
         """noise (parity tests): per-step lists ``eps`` [S_t, A], ``normal`` [E, S_t, D] float64, ``midx`` [S_t]."""
         from ..engine.rollout import RolloutEngine
         if self._roll is None:
             self._roll = RolloutEngine(self)
-        return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise)
+        return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise, device_out)
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
         return self._learn_mixed(batch["real"], batch["fake"], noise)

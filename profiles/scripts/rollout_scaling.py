@@ -49,7 +49,7 @@ def main():
     init = np.random.default_rng(1).standard_normal((S, O), dtype=np.float32)
 
     def run():
-        return parallel.rollout_state_sharded(pol.rollout, init, H, device=dev)
+        return parallel.rollout_state_sharded(pol.rollout, init, H, device=dev, device_out=True)
 
     for _ in range(3):
         out, info = run()

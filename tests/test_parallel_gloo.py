@@ -86,6 +86,18 @@ def _fake_rollout(obs, length):
     return out, {"num_transitions": len(out["obss"]), "reward_mean": float(out["rewards"].mean())}
 
 
+def _fake_rollout_dev(obs, length: int, device_out: bool = False):
+    """The same stand-in with the ``device_out`` contract of MOPOPolicy.rollout: torch tensors, uint8 terminals."""
+    import numpy as np
+    import torch
+    out, info = _fake_rollout(obs, length)
+    if not device_out:
+        return out, info
+    dev = {k: torch.from_numpy(v) for k, v in out.items()}
+    dev["terminals"] = dev["terminals"].to(torch.uint8)
+    return dev, info
+
+
 def _rollout_worker(rank: int, world: int, port: int, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
@@ -97,6 +109,11 @@ def _rollout_worker(rank: int, world: int, port: int, q):
     assert parallel.init("gloo")
     obs = np.random.default_rng(3).random((101, 4), dtype=np.float32)       # 101 rows: uneven 51 / 50 split
     out, info = parallel.rollout_state_sharded(_fake_rollout, obs, 3)
+    # the packed exchange of device tensors (one all-gather for the five arrays) must give the same batch
+    out2, info2 = parallel.rollout_state_sharded(_fake_rollout_dev, obs, 3, device_out=True)
+    assert out2["terminals"].dtype == np.bool_ and info2 == info
+    for k, v in out.items():
+        assert np.array_equal(np.asarray(out2[k], dtype=np.float32).reshape(v.shape), v), k
     q.put((rank, {k: v.tolist() for k, v in out.items()}, info))
     dist.barrier()
     dist.destroy_process_group()
