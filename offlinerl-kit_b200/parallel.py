@@ -111,7 +111,7 @@ def _gather_ragged(arr, device) -> "np.ndarray":
 
 def _gather_packed(local, device):
     """The same gather for a dict of DEVICE tensors with a common first dimension: the columns are packed into one
-    [n, W] fp32 matrix, so the whole exchange is one size all-gather, one padded all-gather and one device-to-host copy
+    [n, W] fp32 matrix, so the whole exchange is one size all-gather, one padded all-gather and one device-to-host copy per array
     (uint8 / bool columns survive the round trip through fp32 exactly)."""
     import numpy as np
     world = dist.get_world_size()
@@ -128,12 +128,15 @@ def _gather_packed(local, device):
     pad[:n_loc] = pack
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
-    host = torch.cat([p[:v] for p, v in zip(parts, sizes)], 0).cpu().numpy()
+    full = torch.cat([p[:v] for p, v in zip(parts, sizes)], 0)
+    # split on the device and copy each array out on its own: host blocks of <= 32 MB are recycled by the allocator,
+    # one 42 MB block would be mmap-ed and page-faulted afresh on every call
     out, c0 = {}, 0
     for k, w in zip(keys, widths):
-        a = host[:, c0:c0 + w]
-        kind = local[k].dtype
-        out[k] = np.ascontiguousarray(a != 0 if kind in (torch.uint8, torch.bool) else a)
+        a = full[:, c0:c0 + w]
+        if local[k].dtype in (torch.uint8, torch.bool):
+            a = a != 0
+        out[k] = a.contiguous().cpu().numpy()
         c0 += w
     return out
 
