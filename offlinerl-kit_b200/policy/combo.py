@@ -33,6 +33,8 @@ class COMBOPolicy(CQLPolicy):
         self._roll = None
         self._split = None      # (n_real, n_fake) the step graph was built for
 
+    device_rollouts = True      # rollout(..., device_out=True) returns CUDA tensors
+
     def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None,
                 device_out: bool = False) -> Tuple[Dict[str, np.ndarray], Dict]:
         """noise (parity tests): per-step lists ``eps`` [S_t, A] (or ``actions`` [S_t, A] with uniform_rollout),

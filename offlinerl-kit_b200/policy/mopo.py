@@ -19,6 +19,8 @@ class MOPOPolicy(SACPolicy):
         self.dynamics = dynamics
         self._roll = None
 
+    device_rollouts = True      # rollout(..., device_out=True) returns CUDA tensors
+
     def rollout(self, init_obss: np.ndarray, rollout_length: int, noise: Optional[Dict[str, np.ndarray]] = None,
                 device_out: bool = False) -> Tuple[Dict[str, np.ndarray], Dict]:
         """noise (parity tests): per-step lists ``eps`` [S_t, A], ``normal`` [E, S_t, D] float64, ``midx`` [S_t]."""

@@ -91,7 +91,11 @@ class MBPolicyTrainer(_TrainerBase):
             for _ in range(self._step_per_epoch):
                 if num_timesteps % self._rollout_freq == 0:
                     init = self.real_buffer.sample(self._rollout_batch_size)["observations"].cpu().numpy()
-                    transitions, info = self.policy.rollout(init, self._rollout_length)
+                    if getattr(self.policy, "device_rollouts", False) and getattr(self.fake_buffer, "accepts_device_batches", False):
+                        # same hand-off as mb_policy_trainer.py:71-73, with the transitions staying on the device
+                        transitions, info = self.policy.rollout(init, self._rollout_length, device_out=True)
+                    else:
+                        transitions, info = self.policy.rollout(init, self._rollout_length)
                     self.fake_buffer.add_batch(**transitions)
                     self.logger.log("num rollout transitions: {}, reward mean: {:.4f}".format(info["num_transitions"],
                                                                                              info["reward_mean"]))

@@ -527,6 +527,33 @@ def test_replay_gather_bit_exact_and_ring(rt):
     assert np.array_equal(b["next_observations"].cpu().numpy(), buf.next_observations[:buf._size])
 
 
+def test_replay_add_batch_from_device_tensors(rt):
+    """Rollout hand-off (mb_policy_trainer.py:71-73) with CUDA tensors: the host arrays get the reference's contents
+    (same ring arithmetic, incl. wrap-around and uint8 terminals) and the device table is written directly - a sample
+    taken afterwards returns exactly the host rows, without a re-upload."""
+    from offlinerlkit_b200.buffer import ReplayBuffer
+    ref = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)       # fed with NumPy arrays
+    buf = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)       # fed with CUDA tensors
+    rng = np.random.default_rng(5)
+    for k, m in enumerate((37, 37, 37, 12, 99, 100, 130)):
+        parts = (rng.standard_normal((m, 4), dtype=np.float32), rng.standard_normal((m, 4), dtype=np.float32),
+                 rng.standard_normal((m, 2), dtype=np.float32), rng.standard_normal((m, 1), dtype=np.float32),
+                 (rng.random((m, 1)) < 0.5))
+        ref.add_batch(*[p.astype(np.float32) for p in parts])
+        dev = [torch.from_numpy(p).to(DEV) for p in parts[:4]] + [torch.from_numpy(parts[4].astype(np.uint8)).to(DEV)]
+        buf.add_batch(*dev)
+        if k >= 1 and m < 100:
+            assert not buf._dirty, "device batches must not schedule a host -> device re-upload"
+        assert buf._ptr == ref._ptr and buf._size == ref._size
+        for name in ("observations", "next_observations", "actions", "rewards", "terminals"):
+            assert np.array_equal(getattr(buf, name), getattr(ref, name)), (k, name)
+        idx = np.arange(buf._size)
+        b = buf.gather(idx)
+        torch.cuda.synchronize()
+        for name in ("observations", "next_observations", "actions", "rewards", "terminals"):
+            assert np.array_equal(b[name].cpu().numpy(), getattr(ref, name)[idx]), (k, name)
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
 def _tc_case(rt, G, M, N, K, passes, epi, splits, with_bias, want_ct, want_rowsum, seed, n_tile=0, a_mn=False, b_mn=False,
              gen_mode=False):
