@@ -131,6 +131,9 @@ class ReplayBuffer:
         self.action_dim, self.action_dtype = int(action_dim), action_dtype
         self._ptr = 0
         self._size = 0
+        # rows that so far exist only in the device table (add_batch of CUDA tensors): (segments, device tensors)
+        self._host_pending: List[Tuple[list, list]] = []
+        self._host_pending_rows = 0
         self.observations = np.zeros((self._max_size,) + self.obs_shape, dtype=obs_dtype)
         self.next_observations = np.zeros((self._max_size,) + self.obs_shape, dtype=obs_dtype)
         self.actions = np.zeros((self._max_size, self.action_dim), dtype=action_dtype)
@@ -142,6 +145,37 @@ class ReplayBuffer:
         self._table: Optional[torch.Tensor] = None
         self._dirty: List[Tuple[int, int]] = []       # host row ranges [lo, hi) not yet mirrored
         self._stages: Dict[int, _Stage] = {}
+
+    # ------------------------------------------------------------------ host arrays (public attributes of the reference)
+    # buffer.py:26-30 exposes the five NumPy arrays; here they are properties so that rows which arrived as CUDA tensors
+    # are copied to the host only when somebody looks (sample_all, normalize_obs, a user reading .observations, ...).
+    def _flush_host(self) -> None:
+        if not self._host_pending:
+            return
+        pend, self._host_pending, self._host_pending_rows = self._host_pending, [], 0
+        dst = (self._h_obs, self._h_nobs, self._h_act, self._h_rew, self._h_term)
+        for segs, tensors in pend:
+            for d, t in zip(dst, tensors):
+                h = t.cpu().numpy().reshape((t.shape[0],) + d.shape[1:])
+                for lo, s0, cnt in segs:
+                    d[lo:lo + cnt] = h[s0:s0 + cnt]
+
+    def _host_prop(name):
+        def get(self):
+            self._flush_host()
+            return getattr(self, name)
+
+        def put(self, value):
+            self._flush_host()
+            setattr(self, name, value)
+        return property(get, put)
+
+    observations = _host_prop("_h_obs")
+    next_observations = _host_prop("_h_nobs")
+    actions = _host_prop("_h_act")
+    rewards = _host_prop("_h_rew")
+    terminals = _host_prop("_h_term")
+    del _host_prop
 
     # ------------------------------------------------------------------ host-side API (as the reference)
     def add(self, obs, next_obs, action, reward, terminal) -> None:
@@ -164,34 +198,41 @@ class ReplayBuffer:
         table, so the rows never travel host -> device again."""
         fields = (obss, next_obss, actions, rewards, terminals)
         dev_in = all(torch.is_tensor(f) and f.is_cuda for f in fields)
-        host = [f.detach().cpu().numpy() if torch.is_tensor(f) else np.array(f) for f in fields]
-        n = len(host[0])
-        dst = (self.observations, self.next_observations, self.actions, self.rewards, self.terminals)
-        if n >= self._max_size:        # later rows overwrite earlier ones: keep the reference's index arithmetic
-            at = np.arange(self._ptr, self._ptr + n) % self._max_size
-            for d, h in zip(dst, host):
-                d[at] = h.reshape((n,) + d.shape[1:])
-            segs = None
-            self._mark(0, self._max_size)
+        n = len(fields[0])
+        cap = self._max_size
+        direct = (dev_in and 0 < n < cap and self._table is not None and self._table.shape[0] == len(self._h_obs) == cap
+                  and self.obs_dtype == np.float32 and self.action_dtype == np.float32)
+        first = min(n, cap - self._ptr)
+        segs = [(self._ptr, 0, first)] + ([(0, first, n - first)] if n > first else [])
+        if direct:
+            O, A = self._obs_dim, self.action_dim
+            t = [f.detach().reshape(n, -1).to(torch.float32).contiguous() for f in fields]
+            t = [x.clone() if x.data_ptr() == f.data_ptr() else x for x, f in zip(t, fields)]    # ours until flushed
+            rt = self._runtime()
+            for lo, s0, cnt in segs:
+                L.call("orlk_replay_pack", t[0].data_ptr() + 4 * s0 * O, t[1].data_ptr() + 4 * s0 * O,
+                       t[2].data_ptr() + 4 * s0 * A, t[3].data_ptr() + 4 * s0, t[4].data_ptr() + 4 * s0, cnt, O, A,
+                       self._table.data_ptr(), self.row_width, lo, rt.cur)
+            rt.sync()
+            # the host arrays catch up lazily (``t`` is kept until then).  The backlog is a run of consecutive ring
+            # segments: once the newer ones cover a whole ring, the oldest has been overwritten everywhere and is dropped
+            self._host_pending.append((segs, t))
+            self._host_pending_rows += n
+            while self._host_pending_rows - self._host_pending[0][1][0].shape[0] >= cap:
+                self._host_pending_rows -= self._host_pending.pop(0)[1][0].shape[0]
         else:
-            first = min(n, self._max_size - self._ptr)
-            segs = [(self._ptr, 0, first)] + ([(0, first, n - first)] if n > first else [])
-            for d, h in zip(dst, host):
-                h = h.reshape((n,) + d.shape[1:])
-                for lo, s0, cnt in segs:
-                    d[lo:lo + cnt] = h[s0:s0 + cnt]
-            direct = (dev_in and self._table is not None and self._table.shape[0] == len(self.observations)
-                      and self.obs_dtype == np.float32 and self.action_dtype == np.float32)
-            if direct:
-                O, A = self._obs_dim, self.action_dim
-                t = [f.detach().reshape(n, -1).to(torch.float32).contiguous() for f in fields]
-                rt = self._runtime()
-                for lo, s0, cnt in segs:
-                    L.call("orlk_replay_pack", t[0].data_ptr() + 4 * s0 * O, t[1].data_ptr() + 4 * s0 * O,
-                           t[2].data_ptr() + 4 * s0 * A, t[3].data_ptr() + 4 * s0, t[4].data_ptr() + 4 * s0, cnt, O, A,
-                           self._table.data_ptr(), self.row_width, lo, rt.cur)
-                rt.sync()          # the temporaries in ``t`` are released when this returns
+            host = [f.detach().cpu().numpy() if torch.is_tensor(f) else np.array(f) for f in fields]
+            dst = (self.observations, self.next_observations, self.actions, self.rewards, self.terminals)
+            if n >= cap:               # later rows overwrite earlier ones: keep the reference's index arithmetic
+                at = np.arange(self._ptr, self._ptr + n) % cap
+                for d, h in zip(dst, host):
+                    d[at] = h.reshape((n,) + d.shape[1:])
+                self._mark(0, cap)
             else:
+                for d, h in zip(dst, host):
+                    h = h.reshape((n,) + d.shape[1:])
+                    for lo, s0, cnt in segs:
+                        d[lo:lo + cnt] = h[s0:s0 + cnt]
                 for lo, _, cnt in segs:
                     self._mark(lo, lo + cnt)
         self._ptr = (self._ptr + n) % self._max_size
@@ -245,7 +286,7 @@ class ReplayBuffer:
 
     def _sync_mirror(self) -> None:
         rt = self._runtime()
-        cap = len(self.observations)
+        cap = len(self._h_obs)
         if self._table is None or self._table.shape[0] != cap:
             self._table = torch.zeros(cap, self.row_width, dtype=torch.float32, device=rt.device)
             self._dirty = [(0, max(self._size, 0))]
@@ -301,7 +342,7 @@ class ReplayBuffer:
         B = int(idx_dev.shape[0])
         st = self._stage(B)
         st.pending = False
-        L.call("orlk_replay_gather", self._table.data_ptr(), len(self.observations), self.row_width, self._obs_dim,
+        L.call("orlk_replay_gather", self._table.data_ptr(), len(self._h_obs), self.row_width, self._obs_dim,
                self.action_dim, idx_dev.data_ptr(), B, st.obs2.data_ptr(), st.act.data_ptr(), st.rew.data_ptr(),
                st.term.data_ptr(), rt.cur)
         return st.batch

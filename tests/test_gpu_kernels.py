@@ -535,12 +535,22 @@ def test_replay_add_batch_from_device_tensors(rt):
     ref = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)       # fed with NumPy arrays
     buf = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)       # fed with CUDA tensors
     rng = np.random.default_rng(5)
+    lazy = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)      # CUDA tensors, host arrays read only at the end
+    lazy.add_batch(np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32), np.zeros((1, 2), np.float32),
+                   np.zeros((1, 1), np.float32), np.zeros((1, 1), np.float32))
+    lazy.gather(np.arange(1))                                                   # creates the device table
+    ref2 = ReplayBuffer(100, (4,), np.float32, 2, np.float32, device=DEV)
+    ref2.add_batch(np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32), np.zeros((1, 2), np.float32),
+                   np.zeros((1, 1), np.float32), np.zeros((1, 1), np.float32))
     for k, m in enumerate((37, 37, 37, 12, 99, 100, 130)):
         parts = (rng.standard_normal((m, 4), dtype=np.float32), rng.standard_normal((m, 4), dtype=np.float32),
                  rng.standard_normal((m, 2), dtype=np.float32), rng.standard_normal((m, 1), dtype=np.float32),
                  (rng.random((m, 1)) < 0.5))
         ref.add_batch(*[p.astype(np.float32) for p in parts])
         dev = [torch.from_numpy(p).to(DEV) for p in parts[:4]] + [torch.from_numpy(parts[4].astype(np.uint8)).to(DEV)]
+        lazy.add_batch(*dev)
+        ref2.add_batch(*[p.astype(np.float32) for p in parts])
+        assert lazy._host_pending_rows < 2 * 100      # bounded backlog: covered segments are dropped
         buf.add_batch(*dev)
         if k >= 1 and m < 100:
             assert not buf._dirty, "device batches must not schedule a host -> device re-upload"
@@ -552,6 +562,10 @@ def test_replay_add_batch_from_device_tensors(rt):
         torch.cuda.synchronize()
         for name in ("observations", "next_observations", "actions", "rewards", "terminals"):
             assert np.array_equal(b[name].cpu().numpy(), getattr(ref, name)[idx]), (k, name)
+    # the lazily mirrored buffer: several ring laps without a single host read, then everything must be there
+    for name in ("observations", "next_observations", "actions", "rewards", "terminals"):
+        assert np.array_equal(getattr(lazy, name), getattr(ref2, name)), name
+    assert not lazy._host_pending
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
