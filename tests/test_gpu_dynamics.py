@@ -140,3 +140,34 @@ def test_ensemble_forward_on_tensor_cores(precision, tol):
             if i < len(layers) - 1:
                 h = h * torch.sigmoid(h)
     assert rel_err(run.OUT.cpu().numpy(), h.cpu().numpy()) < tol
+
+
+def test_dynamics_train_shuffle_overlap_is_invisible(tmp_path, monkeypatch):
+    """EnsembleDynamics.train (ensemble_dynamics.py:111-176) reshuffles the bootstrap indices on a worker thread while
+    the device runs the epoch.  With and without the overlap the run must consume np.random identically and end with
+    bit-identical parameters, elites and scaler."""
+    from offlinerlkit_b200.modules import EnsembleDynamicsModel
+    from offlinerlkit_b200.dynamics import EnsembleDynamics
+    from offlinerlkit_b200.utils.logger import Logger
+    from offlinerlkit_b200.utils.scaler import StandardScaler
+    from offlinerlkit_b200.utils.termination_fns import termination_fn_halfcheetah
+    from offlinerlkit_b200.synthetic import make_dataset
+    O, A = 5, 3
+    data = make_dataset(3000, O, A, seed=2)
+    data["rewards"] = data["rewards"].reshape(-1, 1)
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ORLK_DYN_SHUFFLE_OVERLAP", flag)
+        torch.manual_seed(4)
+        np.random.seed(4)
+        model = EnsembleDynamicsModel(O, A, [24, 24], num_ensemble=3, num_elites=2, weight_decays=[2.5e-5, 5e-5, 7.5e-5], device=DEV)
+        dyn = EnsembleDynamics(model, torch.optim.Adam(model.parameters(), lr=1e-3), StandardScaler(), termination_fn_halfcheetah)
+        logger = Logger(str(tmp_path / flag))
+        logger.quiet = True
+        dyn.train(data, logger, max_epochs=3, max_epochs_since_update=5)
+        results.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, np.random.get_state()[1].copy(),
+                        dyn.scaler.mu.copy()))
+    (sd1, st1, mu1), (sd0, st0, mu0) = results
+    assert np.array_equal(st1, st0) and np.array_equal(mu1, mu0)
+    for k in sd1:
+        assert torch.equal(sd1[k], sd0[k]), k
