@@ -25,7 +25,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-NCU_TC_DRAM_BYTES_PER_LAUNCH = 16.2e6      # measured, see roofline.traffic_source
+NCU_TC_DRAM_BYTES_PER_LAUNCH = 27.7e6      # measured (mean of the six big launches, cold cache), see roofline.traffic_source
 METRIC = "CQL gradient steps/s (hc-shaped, bs256)"
 O_DIM, A_DIM, HIDDEN, BATCH, N_REPEAT, N_DATA = 17, 6, [256, 256, 256], 256, 10, 1_000_000
 HYPER = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, cql_weight=5.0, temperature=1.0, max_q_backup=False,
@@ -352,11 +352,11 @@ def run_engine(args, rank: int, world: int, local_rank: int):
                 # ncu --set full capture of this command (profiles/ncu_tc_gemm_r01.csv); the forward / dgrad launches stay
                 # in L2 (< 6 MB of DRAM traffic each), the split-K weight-gradient launches move ~46 MB each
                 "traffic": NCU_TC_DRAM_BYTES_PER_LAUNCH if on_tc else None,
-                "traffic_source": "profiles/ncu_tc_gemm_r01.csv (ncu --set full, B200, same command)" if on_tc else None,
+                "traffic_source": "profiles/ncu_tc_gemm_r01.csv (ncu --set full, B200, same command; ncu flushes the caches before each pass, in the running step the operands are L2 hits)" if on_tc else None,
                 "algorithmic_bytes_per_launch": 2 * Mc * 256 * 4 * 2 + 2 * 256 * 256 * 4,
                 # each product is three TF32 MMAs: what the tensor pipe really executes, against the TF32 (= bf16 / 2) peak
                 "tf32_mma_frac_of_tf32_peak": (3 if eng.tc_passes == 3 else 1) * achieved / (peak / 2),
-                "ncu_tensor_pipe_active_pct": 37.0 if on_tc else None,
+                "ncu_tensor_pipe_active_pct": 36.5 if on_tc else None,
                 "launches_per_step": len(big), "us_per_step": big_us, "share_of_step": big_us / step_us,
                 "step_frac": FLOP_PER_STEP * (value / world) / 1e12 / peak,
                 "fp32_simt_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
