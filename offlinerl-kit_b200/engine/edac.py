@@ -19,7 +19,7 @@ from .. import _lib as L
 from .core import GP, Mat, Plan
 from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
                       make_gradbuf, wgrad_layout)
-from .nets import GradBuf, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, pick_cfg, wgrad_problem
+from .nets import GradBuf, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, ens_n_tile, pick_cfg, wgrad_problem
 from .sac_family import LS_ACTOR, LS_ALPHA, LS_ALPHA_LOSS
 from .td3_iql import _BatchMixin
 
@@ -173,7 +173,15 @@ class EDACLearner(_BatchMixin, Learner):
             for l in range(nh):
                 lay = cps.layers[l]
                 fprobs = []
-                for e in range(E):
+                if l >= 1 and run_c.ens_tc and run_c.tc_fwd[l]:
+                    # ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1}) for all members in one tensor-core launch
+                    K, N = lay.in_dim, lay.out_dim
+                    plan.add(f"G.ubar{l}.tc", rt.tc_gemm(
+                        A=Mat(ubar[l - 1].data_ptr(), B, K, K), a_gs=B * K, B=Mat(cps.w(l, 0), K, N, N), b_gs=lay.w_gs,
+                        b_mn=True, G=E, passes=run_c.tc, n_tile=ens_n_tile(E, B, N), epi=L.EPI_RELU_MASK,
+                        C=Mat(ubar[l].data_ptr(), B, N, N), c_gs=B * N, aux=Mat(run_c.H[l].data_ptr(), B, N, N), aux_gs=B * N))
+                on_tc = l >= 1 and run_c.ens_tc and run_c.tc_fwd[l]
+                for e in ([] if on_tc else range(E)):
                     if l == 0:      # ubar_1 = m_1 * (gbar W1a),  W1a = rows O.. of W1 [in, out]
                         fprobs.append(GP(A=gbar[e].data_ptr(), lda=A, a_layout=0, B=cps.w(0, e) + 4 * O * lay.out_dim,
                                          ldb=lay.out_dim, b_layout=0, C=ubar[0][e].data_ptr(), ldc=lay.out_dim, M=B,
@@ -182,7 +190,8 @@ class EDACLearner(_BatchMixin, Learner):
                         fprobs.append(GP(A=ubar[l - 1][e].data_ptr(), lda=lay.in_dim, a_layout=0, B=cps.w(l, e), ldb=lay.out_dim,
                                          b_layout=0, C=ubar[l][e].data_ptr(), ldc=lay.out_dim, M=B, N=lay.out_dim, K=lay.in_dim,
                                          epi=L.EPI_RELU_MASK, aux=run_c.H[l][e].data_ptr(), ldaux=lay.out_dim))
-                plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim, rows_per_problem=B)))
+                if fprobs:
+                    plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim, rows_per_problem=B)))
                 for e in range(E):
                     if l + 1 < nh:  # dW_{l+1} += ubar_l^T v_{l+1}
                         wprobs.append(wgrad_problem(cps, gb_c, l + 1, e, Mat.of(ubar[l][e]), run_g.dz(l + 1, e), 1,

@@ -17,7 +17,8 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .core import GP, AdamT, Mat, Plan, Runtime, get_runtime
-from .nets import (GradBuf, Layer, ParamSet, TC_MIN_ROWS, TC_MIN_ROWS_FWD, tc_n_tile, adam_descs, dgrad_problem, fwd_problem, pick_cfg,
+from .nets import (GradBuf, Layer, ParamSet, TC_MIN_ROWS, TC_MIN_ROWS_FWD, ens_n_tile, ens_tc_ok, tc_n_tile, tc_ok_dgrad_io,
+                   tc_ok_fwd_io, adam_descs, dgrad_problem, fwd_problem, pick_cfg,
                    tc_ok_dgrad, tc_ok_fwd, tc_ok_wgrad, wgrad_problem, wgrad_splits)
 
 MAX_GROUPS = 16
@@ -266,6 +267,15 @@ class MlpRun:
         self.tc_fwd = [bool(self.tc) and l >= 1 and tc_ok_fwd(lays[l], M) for l in range(n_hidden)]
         self.tc_dgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_dgrad(lays[l], M) for l in range(n_hidden)]
         self.tc_wgrad = [bool(self.tc) and need_grad and l >= 1 and tc_ok_wgrad(lays[l], M) for l in range(n_hidden)]
+        # ensembles of short members ('io' weights): forward and input gradients of the hidden layers as ONE n-tiled
+        # tensor-core launch over all members (the weights are an MN-major B operand forward and a K-major one backward,
+        # so no transposed copies exist); their weight gradients stay on the grouped small-row kernel
+        self.ens_tc = bool(tc_passes) and ens_tc_ok(lays[:n_hidden], G, M)
+        if self.ens_tc:
+            self.tc = tc_passes
+            self.tc_fwd = [l >= 1 and tc_ok_fwd_io(lays[l]) and ens_n_tile(G, M, lays[l].out_dim) > 0 for l in range(n_hidden)]
+            self.tc_dgrad = [need_grad and l >= 1 and tc_ok_dgrad_io(lays[l]) and ens_n_tile(G, M, lays[l].in_dim) > 0
+                             for l in range(n_hidden)]
         # The tensor-core weight gradient dW[o][i] = sum_m dZ[m][o] H[m][i] reads the ROW-MAJOR gradients / activations
         # as MN-major operands (orlk_tc_gemm a_mn / b_mn); only layers whose input width is not a multiple of 32 still
         # need the transposed copies HT / dZT written by the producing kernels' epilogues.
@@ -290,7 +300,7 @@ class MlpRun:
             if not self.wgrad_mn[last]:
                 self.HT[last] = rt.zeros(G, lays[last].out_dim, self.Mt)
             self.dZT[last] = None           # never materialised
-        if any(self.tc_dgrad):
+        if any(self.tc_dgrad) and not self.ens_tc:
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
         # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
         # streaming kernels for the narrow first layer (K <= 32) and the narrow head's weight gradient
@@ -359,6 +369,13 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
         return
     for l in range(run.nh):
         lay = ps.layers[l]
+        if run.tc_fwd[l] and run.ens_tc:
+            K, N = lay.in_dim, lay.out_dim
+            plan.add(f"{tag}.fwd{l}.tc", rt.tc_gemm(
+                A=_grouped(run.H[l - 1], M, K, K), a_gs=M * K, B=Mat(ps.w(l, 0, run.store), K, N, N), b_gs=lay.w_gs, b_mn=True,
+                G=G, passes=run.tc, n_tile=ens_n_tile(G, M, N), epi=L.EPI_RELU, C=_grouped(run.H[l], M, N, N), c_gs=M * N,
+                bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
+            continue
         if run.tc_fwd[l]:
             K, N = lay.in_dim, lay.out_dim
             plan.add(f"{tag}.fwd{l}.tc", rt.tc_gemm(
@@ -450,6 +467,14 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
         raise L.OrlkError("emit_hidden_dgrad(dact=...) needs the fused chain path; call emit_dact instead")
     for l in range(run.nh - 1, down_to - 1, -1):
         lay = ps.layers[l]
+        if run.tc_dgrad[l] and run.ens_tc:
+            # dX[m][i] = sum_o dZ[m][o] W[i][o]: the 'io' weight is the K-major B operand as it is stored
+            K, N = lay.out_dim, lay.in_dim
+            plan.add(f"{tag}.dgrad{l}.tc", rt.tc_gemm(
+                A=_grouped(run.dZ[l], M, K, K), a_gs=M * K, B=Mat(ps.w(l, 0), N, K, K), b_gs=lay.w_gs, G=G, passes=run.tc,
+                n_tile=ens_n_tile(G, M, N), epi=L.EPI_RELU_MASK, C=_grouped(run.dZ[l - 1], M, N, N), c_gs=M * N,
+                aux=_grouped(run.H[l - 1], M, N, N), aux_gs=M * N))
+            continue
         if run.tc_dgrad[l]:
             K, N = lay.out_dim, lay.in_dim
             gen = {}

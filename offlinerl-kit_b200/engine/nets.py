@@ -245,6 +245,31 @@ def tc_n_tile(M: int, N: int) -> int:
     return 0 if M >= TC_MIN_ROWS or N % 32 != 0 else 32
 
 
+# Ensembles (EnsembleLinear, 'io' weights [member][in][out]) of short members: the small-row kernel costs ~2.5 us per
+# member and layer (ten 256-row critics: 25 us), an n-tiled tensor-core launch ~11 us for all members together.
+ENSEMBLE_TC = os.environ.get("ORLK_ENSEMBLE_TC", "1") != "0"
+
+
+def ens_tc_ok(lays: Sequence["Layer"], G: int, M: int) -> bool:
+    return ENSEMBLE_TC and G >= 4 and G * M >= TC_MIN_ROWS and M >= 128 and all(lay.layout == "io" for lay in lays)
+
+
+def ens_n_tile(G: int, M: int, N: int) -> int:
+    """Output columns per CTA for an ensemble launch: the narrowest 32-multiple that keeps the grid within one wave."""
+    for nt in (32, 64, 128):
+        if N % nt == 0 and G * (-(-M // 128)) * (N // nt) <= 148:
+            return nt
+    return 0
+
+
+def tc_ok_fwd_io(lay: Layer) -> bool:
+    return lay.layout == "io" and lay.in_dim % 4 == 0 and lay.out_dim % 32 == 0 and lay.out_dim <= 256 and lay.w_gs % 4 == 0
+
+
+def tc_ok_dgrad_io(lay: Layer) -> bool:
+    return lay.layout == "io" and lay.out_dim % 4 == 0 and lay.in_dim % 32 == 0 and lay.in_dim <= 256 and lay.w_gs % 4 == 0
+
+
 def tc_ok_fwd(lay: Layer, M: int) -> bool:
     return lay.layout == "oi" and lay.in_dim % 4 == 0 and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and M >= TC_MIN_ROWS_FWD
 
