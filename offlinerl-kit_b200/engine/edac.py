@@ -11,6 +11,7 @@ The diversity weight gradients go to extra split-K slots of the same GradBuf, so
 the TD part and the diversity part.
 """
 import ctypes as C
+import os
 from typing import Dict
 
 import torch
@@ -79,6 +80,50 @@ class EDACLearner(_BatchMixin, Learner):
         args = (head.data_ptr(), 2 * A, 0, rep, eps.data_ptr(), B * rep, A, X.ptr + 4 * O, X.ld, logp.data_ptr(), obs.ptr, obs.ld,
                 O, X.ptr, X.ld)
         plan.add(tag, lambda: L.call("orlk_tanh_gauss_sample", *args, self.rt.cur))
+
+    def _emit_ens_wgrads(self, plan, tag, run, gb, terms, ones, split_base, with_bias, k_splits, tiny, col0_first=0):
+        """Weight (and bias) gradients of the critic ensemble for a list of (layer, X, dY) terms, X [E,B,in] (or a Mat
+        shared by the members), dY [E,B,out] (None: a column of ones, i.e. column sums of X).  Square hidden layers go
+        to the tensor-core kernel, one launch per layer over all members with both operands read MN-major as they are
+        stored (dW[i][o] = sum_m X[m][i] dY[m][o]); their bias gradients and the narrow layers stay on the grouped
+        small-row kernel; the launches are independent and run on parallel branches of the step graph."""
+        rt, cps, E, B = self.rt, self.critic_ps, self.E, self.B
+        tc_launches, probs = [], []
+        for (l, X, dY) in terms:
+            lay = cps.layers[l]
+            shared = isinstance(X, Mat)
+            on_tc = (run.ens_tc and not shared and dY is not None and 1 <= l < run.nh and lay.in_dim % 32 == 0
+                     and lay.out_dim % 32 == 0 and lay.in_dim <= 256 and ens_n_tile(E, lay.in_dim, lay.out_dim) > 0
+                     and os.environ.get("ORLK_ENSEMBLE_TC_WGRAD", "1") != "0")
+            if on_tc:
+                i, o = lay.in_dim, lay.out_dim
+                tc_launches.append((f"{tag}{l}.tc", rt.tc_gemm(
+                    A=Mat(X.data_ptr(), B, i, i), a_gs=B * i, a_mn=True, B=Mat(dY.data_ptr(), B, o, o), b_gs=B * o, b_mn=True,
+                    G=E, passes=run.tc, n_tile=ens_n_tile(E, i, o),
+                    C=Mat(gb.ptr(lay.w_off) + 4 * split_base * gb.stride, i, o, o), c_gs=lay.w_gs)))
+                if with_bias:       # db[o] = sum_m dY[m][o]: a one-row product with the column of ones
+                    for e in range(E):
+                        probs.append(GP(A=ones.data_ptr(), lda=1, a_layout=1, B=dY[e].data_ptr(), ldb=o, b_layout=0,
+                                        C=gb.ptr(lay.b_off + e * lay.b_gs), ldc=o, M=1, N=o, K=B, k_splits=1,
+                                        split_base=split_base, c_split_stride=gb.stride, sum_split_stride=gb.stride))
+                continue
+            for e in range(E):
+                x = X if shared else Mat.of(X[e])
+                dy = Mat.of(ones) if dY is None else Mat.of(dY[e])
+                ks = k_splits[l][1] if k_splits is not None else 1
+                probs.append(wgrad_problem(cps, gb, l, e, x, dy, ks, split_base=split_base,
+                                           col0=col0_first if (l == 0 and col0_first) else 0, with_bias=with_bias))
+        rest = rt.gemm(probs, L.CFG_TINY if tiny else L.CFG_SMALL)
+        if not tc_launches:
+            plan.add(tag, rest)
+            return
+        plan.fork()
+        for b, (label, op) in enumerate(tc_launches, start=1):
+            plan.branch(b)
+            plan.add(label, op)
+        plan.branch(0)
+        plan.add(tag, rest)
+        plan.join()
 
     def _build(self) -> None:
         rt, B, O, A, E, pol = self.rt, self.B, self.O, self.A, self.E, self.policy
@@ -150,13 +195,10 @@ class EDACLearner(_BatchMixin, Learner):
         plan.add("C.td_loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
         emit_head_dgrad(rt, plan, run_c, "C.critics")
         emit_hidden_dgrad(rt, plan, run_c, "C.critics")
-        probs = []
-        for l in range(nh + 1):
-            for e in range(E):
-                xin = mXd if l == 0 else run_c.h(l - 1, e)
-                dy = run_c.dz(l, e) if l < nh else Mat.of(run_c.dOut[e])
-                probs.append(wgrad_problem(cps, gb_c, l, e, xin, dy, td_layout[l][1]))
-        plan.add("C.critics.wgrad_td", rt.gemm(probs, L.CFG_TINY if (B < TC_MIN_ROWS and s_td == 1) else L.CFG_SMALL))
+        # weight gradients of the TD loss: (layer, X [E,B,in] or a shared Mat, dY [E,B,out])
+        td_terms = [(l, (mXd if l == 0 else run_c.H[l - 1]), (run_c.dZ[l] if l < nh else run_c.dOut)) for l in range(nh + 1)]
+        self._emit_ens_wgrads(plan, "C.critics.wgrad_td", run_c, gb_c, td_terms, ones, split_base=0, with_bias=True,
+                              k_splits=td_layout, tiny=(B < TC_MIN_ROWS and s_td == 1))
         if self.eta > 0:
             # 1. input-gradient chain (upstream 1)
             run_g.dOut.fill_(1.0)
@@ -168,11 +210,9 @@ class EDACLearner(_BatchMixin, Learner):
                      self.loss_dev.data_ptr() + 4 * LS_DIV)
             plan.add("G.div", lambda: L.call("orlk_edac_div", *dargs, rt.cur))
             # 3. second chain + weight gradients into slot s_td
-            wprobs = [wgrad_problem(cps, gb_c, 0, e, Mat.of(gbar[e]), run_g.dz(0, e), 1, split_base=s_td, col0=O, with_bias=False)
-                      for e in range(E)]
+            div_terms = [(0, gbar, run_g.dZ[0])]
             for l in range(nh):
                 lay = cps.layers[l]
-                fprobs = []
                 if l >= 1 and run_c.ens_tc and run_c.tc_fwd[l]:
                     # ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1}) for all members in one tensor-core launch
                     K, N = lay.in_dim, lay.out_dim
@@ -180,28 +220,24 @@ class EDACLearner(_BatchMixin, Learner):
                         A=Mat(ubar[l - 1].data_ptr(), B, K, K), a_gs=B * K, B=Mat(cps.w(l, 0), K, N, N), b_gs=lay.w_gs,
                         b_mn=True, G=E, passes=run_c.tc, n_tile=ens_n_tile(E, B, N), epi=L.EPI_RELU_MASK,
                         C=Mat(ubar[l].data_ptr(), B, N, N), c_gs=B * N, aux=Mat(run_c.H[l].data_ptr(), B, N, N), aux_gs=B * N))
-                on_tc = l >= 1 and run_c.ens_tc and run_c.tc_fwd[l]
-                for e in ([] if on_tc else range(E)):
-                    if l == 0:      # ubar_1 = m_1 * (gbar W1a),  W1a = rows O.. of W1 [in, out]
-                        fprobs.append(GP(A=gbar[e].data_ptr(), lda=A, a_layout=0, B=cps.w(0, e) + 4 * O * lay.out_dim,
-                                         ldb=lay.out_dim, b_layout=0, C=ubar[0][e].data_ptr(), ldc=lay.out_dim, M=B,
-                                         N=lay.out_dim, K=A, epi=L.EPI_RELU_MASK, aux=run_c.H[0][e].data_ptr(), ldaux=lay.out_dim))
-                    else:           # ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1})
-                        fprobs.append(GP(A=ubar[l - 1][e].data_ptr(), lda=lay.in_dim, a_layout=0, B=cps.w(l, e), ldb=lay.out_dim,
-                                         b_layout=0, C=ubar[l][e].data_ptr(), ldc=lay.out_dim, M=B, N=lay.out_dim, K=lay.in_dim,
-                                         epi=L.EPI_RELU_MASK, aux=run_c.H[l][e].data_ptr(), ldaux=lay.out_dim))
-                if fprobs:
+                else:
+                    fprobs = []
+                    for e in range(E):
+                        if l == 0:      # ubar_1 = m_1 * (gbar W1a),  W1a = rows O.. of W1 [in, out]
+                            fprobs.append(GP(A=gbar[e].data_ptr(), lda=A, a_layout=0, B=cps.w(0, e) + 4 * O * lay.out_dim,
+                                             ldb=lay.out_dim, b_layout=0, C=ubar[0][e].data_ptr(), ldc=lay.out_dim, M=B,
+                                             N=lay.out_dim, K=A, epi=L.EPI_RELU_MASK, aux=run_c.H[0][e].data_ptr(),
+                                             ldaux=lay.out_dim))
+                        else:           # ubar_{l+1} = m_{l+1} * (ubar_l W_{l+1})
+                            fprobs.append(GP(A=ubar[l - 1][e].data_ptr(), lda=lay.in_dim, a_layout=0, B=cps.w(l, e),
+                                             ldb=lay.out_dim, b_layout=0, C=ubar[l][e].data_ptr(), ldc=lay.out_dim, M=B,
+                                             N=lay.out_dim, K=lay.in_dim, epi=L.EPI_RELU_MASK, aux=run_c.H[l][e].data_ptr(),
+                                             ldaux=lay.out_dim))
                     plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim, rows_per_problem=B)))
-                for e in range(E):
-                    if l + 1 < nh:  # dW_{l+1} += ubar_l^T v_{l+1}
-                        wprobs.append(wgrad_problem(cps, gb_c, l + 1, e, Mat.of(ubar[l][e]), run_g.dz(l + 1, e), 1,
-                                                    split_base=s_td, with_bias=False))
-                    else:           # dw_head += sum_b ubar_L
-                        wprobs.append(wgrad_problem(cps, gb_c, nh, e, Mat.of(ubar[l][e]), Mat.of(ones), 1, split_base=s_td,
-                                                    with_bias=False))
-                if l + 1 < nh:
-                    continue
-            plan.add("G.wgrad_div", rt.gemm(wprobs, L.CFG_TINY if B < TC_MIN_ROWS else L.CFG_SMALL))
+                # dW_{l+1} += ubar_l^T v_{l+1};  for the head: dw_head += sum_b ubar_L  (v = ones)
+                div_terms.append((l + 1, ubar[l], run_g.dZ[l + 1] if l + 1 < nh else None))
+            self._emit_ens_wgrads(plan, "G.wgrad_div", run_c, gb_c, div_terms, ones, split_base=s_td, with_bias=False,
+                                  k_splits=None, tiny=B < TC_MIN_ROWS, col0_first=O)
         splits = [s_td + 1] * (nh + 1)
         plan.add("C.critics.adam", rt.adam(adam_descs(cps, gb_c, splits, polyak=True), self.groups_ptr))
         mask = (1 << self.g_actor) | (1 << self.g_c) | ((1 << self.g_alpha) if self.g_alpha >= 0 else 0)
