@@ -136,7 +136,8 @@ class EDACLearner(_BatchMixin, Learner):
         run_t = self.mlp_run(cps, Bt, nh, need_grad=False, store="T")
         run_c = self.mlp_run(cps, B, nh, need_grad=True)                        # Q_e(s, a_data): TD backward
         run_g = self.mlp_run(cps, B, nh, need_grad=True, share_forward=run_c)   # same activations: input-gradient chain
-        Xa, Xt, Xd = rt.zeros(B, O + A), rt.zeros(Bt, O + A), rt.zeros(B, O + A)
+        ldx = (O + A + 3) // 4 * 4          # 16-byte rows: the critics' first layer reads them through TMA
+        Xa, Xt, Xd = rt.zeros(B, ldx)[:, :O + A], rt.zeros(Bt, ldx)[:, :O + A], rt.zeros(B, ldx)[:, :O + A]
         logp_a, lp_next, glp = rt.zeros(B), rt.zeros(Bt), rt.zeros(B)
         tq_best = rt.zeros(E, B) if self.n_next > 1 else None
         dA = rt.zeros(E, B, A)

@@ -385,6 +385,15 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
                 bias=ps.b(l, 0, run.store), bias_gs=lay.b_gs))
             continue
         same_x = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
+        if (l == 0 and run.ens_tc and same_x and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0 and lay.out_dim % 32 == 0
+                and lay.out_dim <= 256 and lay.w_gs % 4 == 0 and ens_n_tile(G, M, lay.out_dim) > 0):
+            # first layer of an ensemble on a shared input: one zero-padded k-slab, weights MN-major as stored
+            K, N = lay.in_dim, lay.out_dim
+            plan.add(f"{tag}.fwd0.tc", rt.tc_gemm(
+                A=Mat(X[0].ptr, M, K, X[0].ld), a_gs=0, B=Mat(ps.w(0, 0, run.store), K, N, N), b_gs=lay.w_gs, b_mn=True, G=G,
+                passes=3, n_tile=ens_n_tile(G, M, N), epi=L.EPI_RELU, C=_grouped(run.H[0], M, N, N), c_gs=M * N,
+                bias=ps.b(0, 0, run.store), bias_gs=lay.b_gs))
+            continue
         if (l == 0 and run.tc and run.narrow0 and M >= TC_MIN_ROWS and same_x and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0
                 and lay.out_dim % 16 == 0 and lay.out_dim <= 256 and os.environ.get("ORLK_TC_FWD0", "1") != "0"):
             # obs+act wide first layer on the tensor cores: one zero-padded k-slab, the kernel is all epilogue
