@@ -192,27 +192,42 @@ class TwinCriticLearner(Learner):
         plan.keep.append(arr)
         plan.add(tag, lambda: L.call("orlk_head_sample", *args, self.rt.cur))
 
-    def _emit_actor_update(self, plan: Plan, clamp01: bool, beside_forward=None) -> None:
-        """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)
-        ``beside_forward``: a (label, launch) that is independent of the actor forward (the noise fill) and runs on a
-        parallel branch next to it."""
-        rt, B, O, A = self.rt, self.B, self.O, self.A
-        ar, cr = self.run_actor, self.run_critic_a
+    def _emit_actor_forward(self, plan: Plan) -> None:
+        """a ~ pi(.|s) for the policy-improvement step: actor forward + sampler, writes [s | a] into Xa and logp_a.
+        Depends on the actor and the noise only, so SAC runs it beside the critics' backward pass."""
+        rt, B = self.rt, self.B
+        ar = self.run_actor
         obs = Mat.of(self.obs2).rows_(0, B)
-        if beside_forward is not None:
-            plan.fork()
-            plan.branch(1)
-            plan.add(*beside_forward)
-            plan.branch(0)
         fuse_hs = self._can_fuse_head_sample(ar)
         emit_forward(rt, plan, ar, [obs], "A.actor", skip_head=fuse_hs)
-        if beside_forward is not None:
-            plan.join()
         Xa = Mat.of(self.Xa)
         if fuse_hs:
             self._emit_head_sample(plan, "A.actor.head_sample", ar, [(0, B, 1, self.eps_actor, Xa, self.logp_a, obs)])
         else:
             self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
+
+    def _emit_actor_update(self, plan: Plan, clamp01: bool, beside_forward=None, forward_done: bool = False) -> None:
+        """a~pi(s); L = mean(alpha*logp - min Q); Adam(actor); alpha step.  (cql.py:93-106 / sac.py:111-126)
+        ``beside_forward``: a (label, launch) that is independent of the actor forward (the noise fill) and runs on a
+        parallel branch next to it.  ``forward_done``: the caller has already emitted ``_emit_actor_forward``."""
+        rt, B, O, A = self.rt, self.B, self.O, self.A
+        ar, cr = self.run_actor, self.run_critic_a
+        obs = Mat.of(self.obs2).rows_(0, B)
+        Xa = Mat.of(self.Xa)
+        if not forward_done:
+            if beside_forward is not None:
+                plan.fork()
+                plan.branch(1)
+                plan.add(*beside_forward)
+                plan.branch(0)
+            fuse_hs = self._can_fuse_head_sample(ar)
+            emit_forward(rt, plan, ar, [obs], "A.actor", skip_head=fuse_hs)
+            if beside_forward is not None:
+                plan.join()
+            if fuse_hs:
+                self._emit_head_sample(plan, "A.actor.head_sample", ar, [(0, B, 1, self.eps_actor, Xa, self.logp_a, obs)])
+            else:
+                self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
         emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
         q, dq = cr.out, cr.dOut      # [2, B, 1]
         args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
@@ -433,21 +448,39 @@ class SACLearner(TwinCriticLearner):
         obs2 = Mat.of(self.obs2)
         obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
         Xd, Xt = Mat.of(self.Xd), Mat.of(self.Xt)
-        plan.add("Q.concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
         cr = self.run_critic
-        emit_forward(rt, plan, cr, [Xd, Xd], "Q.critic")
         an = self.run_actor_n
+        par = os.environ.get("ORLK_SAC_BRANCHES", "1") != "0"
+        # Q(s, a_data) on one branch, a' ~ pi(s') and the target critics on another: they share no buffer
+        if par:
+            plan.fork()
+            plan.branch(1)
         emit_forward(rt, plan, an, [nobs], "Q.actor_next")
         self._emit_sample(plan, "Q.sample_next", an.out[0], 0, 1, self.noise_views["eps_next"], B, Xt, self.lp_next, nobs)
         emit_forward(rt, plan, self.run_target, [Xt, Xt], "Q.target")
+        if par:
+            plan.branch(0)
+        plan.add("Q.concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
+        emit_forward(rt, plan, cr, [Xd, Xd], "Q.critic")
+        if par:
+            plan.join()
         targs = (cr.out.data_ptr(), B, 2, self.run_target.out.data_ptr(), B, 2, self.lp_next.data_ptr(),
                  self.scalars.data_ptr(), 1, self.rew.data_ptr(), self.term.data_ptr(), B, self.gamma, cr.dOut.data_ptr(), B,
                  None, self.loss_dev.data_ptr() + 4 * LS_C1, None)
         plan.add("Q.loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+        # the critics' backward pass and update on one branch, the policy-improvement step's actor forward + sampler
+        # (which reads the actor and the noise only) on another; the critics it is scored by are the UPDATED ones
+        if par:
+            plan.fork()
+            plan.branch(1)
+            self._emit_actor_forward(plan)
+            plan.branch(0)
         emit_head_dgrad(rt, plan, cr, "Q.critic")
         emit_hidden_dgrad(rt, plan, cr, "Q.critic")
         emit_wgrad_adam(rt, plan, cr, [Xd, Xd], self.gb_critic, self.groups_ptr, "Q.critic", polyak=True)
-        self._emit_actor_update(plan, clamp01=True)
+        if par:
+            plan.join()
+        self._emit_actor_update(plan, clamp01=True, forward_done=par)
         self.finish_ops(plan, self.group_mask(self.g_actor, self.g_c1, self.g_c2, self.g_alpha))
         self.plans["step"] = plan
         self._built = True
