@@ -1,5 +1,6 @@
 """Gradient-step engines for TD3+BC (policy/model_free/td3bc.py:83-124) and IQL (policy/model_free/iql.py:86-139)."""
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -9,7 +10,7 @@ from .. import _lib as L
 from .core import AdamT, Mat, Plan
 from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, emit_wgrad_adam,
                       linears_of, make_gradbuf, polyak_descs)
-from .nets import ParamSet, dgrad_problem
+from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem
 
 LS_ACTOR, LS_C1, LS_C2, LS_V = 0, 4, 5, 8
 
@@ -106,32 +107,57 @@ class TD3BCLearner(_BatchMixin, Learner):
         obs, nobs = obs2.rows_(0, B), obs2.rows_(B, 2 * B)
         Xd, Xt, Xa = Mat.of(self.Xd), Mat.of(self.Xt), Mat.of(self.Xa)
 
-        def critic_phase(plan: Plan) -> None:
+        # parallel graph branches for sub-chains that share no buffer (the small-row passes emit one launch per stage and
+        # no nested fork; larger batches keep the sequential order)
+        par = B < TC_MIN_ROWS and os.environ.get("ORLK_TD3_BRANCHES", "1") != "0"
+
+        def critic_phase(plan: Plan, actor_forward=None) -> None:
             args = (self.noise.data_ptr(), B * A, 0, 0.0, 1.0, int(self.seed), self.philox_counter.data_ptr(),
                     self.noise_enable.data_ptr())
             plan.add("philox", lambda: L.call("orlk_philox_fill", *args, rt.cur))
-            plan.add("Q.concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
             cr = self.run_critic
-            emit_forward(rt, plan, cr, [Xd, Xd], "Q.critic")
             at = self.run_actor_t
+            # Q(s, a_data) on one branch, the target action and the target critics on another: no shared buffer
+            if par:
+                plan.fork()
+                plan.branch(1)
             emit_forward(rt, plan, at, [nobs], "Q.actor_old")
             fargs = (at.out.data_ptr(), A, self.noise.data_ptr(), B, A, max_a, float(pol._policy_noise), float(pol._noise_clip),
                      Xt.ptr + 4 * O, Xt.ld, nobs.ptr, nobs.ld, O, Xt.ptr, Xt.ld)
             plan.add("Q.next_action", lambda: L.call("orlk_det_actor_fwd", *fargs, rt.cur))
             emit_forward(rt, plan, self.run_target, [Xt, Xt], "Q.target")
+            if par:
+                plan.branch(0)
+            plan.add("Q.concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
+            emit_forward(rt, plan, cr, [Xd, Xd], "Q.critic")
+            if par:
+                plan.join()
             targs = (cr.out.data_ptr(), B, 2, self.run_target.out.data_ptr(), B, 2, None, None, 0, self.rew.data_ptr(),
                      self.term.data_ptr(), B, float(pol._gamma), cr.dOut.data_ptr(), B, None,
                      self.loss_dev.data_ptr() + 4 * LS_C1, None)
             plan.add("Q.loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+            # the delayed policy update's actor forward reads the actor only: beside the critics' backward pass
+            if actor_forward is not None and par:
+                plan.fork()
+                plan.branch(1)
+                actor_forward(plan)
+                plan.branch(0)
             emit_head_dgrad(rt, plan, cr, "Q.critic")
             emit_hidden_dgrad(rt, plan, cr, "Q.critic")
             emit_wgrad_adam(rt, plan, cr, [Xd, Xd], self.gb_critic, self.groups_ptr, "Q.critic", polyak=False)
+            if actor_forward is not None and par:
+                plan.join()
 
-        def actor_phase(plan: Plan) -> None:
-            ar, q1 = self.run_actor, self.run_q1
+        def actor_forward(plan: Plan) -> None:
+            ar = self.run_actor
             emit_forward(rt, plan, ar, [obs], "P.actor")
             fargs = (ar.out.data_ptr(), A, None, B, A, max_a, 0.0, 0.0, Xa.ptr + 4 * O, Xa.ld, obs.ptr, obs.ld, O, Xa.ptr, Xa.ld)
             plan.add("P.action", lambda: L.call("orlk_det_actor_fwd", *fargs, rt.cur))
+
+        def actor_phase(plan: Plan) -> None:
+            ar, q1 = self.run_actor, self.run_q1
+            if not par:
+                actor_forward(plan)
             emit_forward(rt, plan, q1, [Xa], "P.q1")
             largs = (q1.out.data_ptr(), Xa.ptr + 4 * O, Xa.ld, self.act.data_ptr(), A, B, A, float(pol._alpha),
                      q1.dOut.data_ptr(), self.dabc.data_ptr(), A, self.loss_dev.data_ptr() + 4 * LS_ACTOR)
@@ -150,7 +176,7 @@ class TD3BCLearner(_BatchMixin, Learner):
         critic_phase(p_c)
         self.finish_ops(p_c, (1 << self.g_c1) | (1 << self.g_c2))
         p_ca = Plan(rt, "td3bc.critic+actor")
-        critic_phase(p_ca)
+        critic_phase(p_ca, actor_forward)
         actor_phase(p_ca)
         self.finish_ops(p_ca, (1 << self.g_c1) | (1 << self.g_c2) | (1 << self.g_actor))
         self.plans = {"critic": p_c, "both": p_ca}
@@ -226,10 +252,25 @@ class IQLLearner(_BatchMixin, Learner):
         Xd = Mat.of(self.Xd)
         plan = Plan(rt, "iql")
         plan.add("concat", rt.concat([(Xd, obs, 1, Mat.of(self.act))]))
+        # Sub-chains that share no buffer run on parallel graph branches (small-row passes only: one launch per stage, no
+        # nested fork).  The four forward passes that read only weights nobody has updated yet start together: the target
+        # Q(s,a), V(s), the online Q(s,a) and the actor's mu(s).
+        par = B < TC_MIN_ROWS and os.environ.get("ORLK_IQL_BRANCHES", "1") != "0"
+        rv, rq, rv2, ra = self.run_v, self.run_q, self.run_v2, self.run_actor
+        if par:
+            plan.fork()
+            plan.branch(1)
         # ---- V
         emit_forward(rt, plan, self.run_qt, [Xd, Xd], "V.qtarget")
-        rv = self.run_v
+        if par:
+            plan.branch(2)
+            emit_forward(rt, plan, rq, [Xd, Xd], "Q.q")
+            plan.branch(3)
+            emit_forward(rt, plan, ra, [obs], "P.actor")
+            plan.branch(0)
         emit_forward(rt, plan, rv, [obs], "V.v")
+        if par:
+            plan.join()
         vargs = (self.run_qt.out.data_ptr(), B, rv.out.data_ptr(), B, float(pol._expectile), rv.dOut.data_ptr(),
                  self.qmin.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_V)
         plan.add("V.loss", lambda: L.call("orlk_iql_v_loss", *vargs, rt.cur))
@@ -237,26 +278,34 @@ class IQLLearner(_BatchMixin, Learner):
         emit_hidden_dgrad(rt, plan, rv, "V.v")
         emit_wgrad_adam(rt, plan, rv, [obs], self.gb_v, self.groups_ptr, "V.v", polyak=False)
         # ---- Q (updated V on s' for the target and on s for the advantage, one 2B-row pass)
-        rq, rv2 = self.run_q, self.run_v2
-        emit_forward(rt, plan, rq, [Xd, Xd], "Q.q")
+        if not par:
+            emit_forward(rt, plan, rq, [Xd, Xd], "Q.q")
         emit_forward(rt, plan, rv2, [obs2], "Q.v_new")
         v_s, v_next = rv2.out.data_ptr(), rv2.out.data_ptr() + 4 * B
         targs = (rq.out.data_ptr(), B, 2, v_next, B, 1, None, None, 0, self.rew.data_ptr(), self.term.data_ptr(), B,
                  float(pol._gamma), rq.dOut.data_ptr(), B, None, self.loss_dev.data_ptr() + 4 * LS_C1, None)
-        plan.add("Q.loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
-        emit_head_dgrad(rt, plan, rq, "Q.q")
-        emit_hidden_dgrad(rt, plan, rq, "Q.q")
-        emit_wgrad_adam(rt, plan, rq, [Xd, Xd], self.gb_q, self.groups_ptr, "Q.q", polyak=True)
-        # ---- actor
-        ra = self.run_actor
-        emit_forward(rt, plan, ra, [obs], "P.actor")
         sp = self.actor_ps.extra_ptr("sigma_param")
         aargs = (ra.out.data_ptr(), A, sp, self.act.data_ptr(), A, self.qmin.data_ptr(), v_s, B, A, float(pol._temperature),
                  self.max_mu, ra.dOut.data_ptr(), A, self.dsigma.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+        # the Q update and the actor update both start from V_new and touch disjoint parameters: two branches
+        if par:
+            plan.fork()
+            plan.branch(1)
+        else:
+            emit_forward(rt, plan, ra, [obs], "P.actor")
+        # ---- actor
         plan.add("P.loss", lambda: L.call("orlk_iql_actor_loss", *aargs, rt.cur))
         emit_head_dgrad(rt, plan, ra, "P.actor")
         emit_hidden_dgrad(rt, plan, ra, "P.actor")
         emit_wgrad_adam(rt, plan, ra, [obs], self.gb_actor, self.groups_ptr, "P.actor", polyak=False)
+        if par:
+            plan.branch(0)
+        plan.add("Q.loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+        emit_head_dgrad(rt, plan, rq, "Q.q")
+        emit_hidden_dgrad(rt, plan, rq, "Q.q")
+        emit_wgrad_adam(rt, plan, rq, [Xd, Xd], self.gb_q, self.groups_ptr, "Q.q", polyak=True)
+        if par:
+            plan.join()
         off = self.actor_ps.extra["sigma_param"][0]
         ps = self.actor_ps
         plan.add("P.sigma_adam", rt.adam([AdamT(p=ps._ptr(ps.P, off), n=A, group=self.g_actor, m=ps._ptr(ps.Mo, off),
