@@ -18,8 +18,8 @@ import torch
 
 from .. import _lib as L
 from .core import GP, Mat, Plan
-from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad, linears_of,
-                      make_gradbuf, wgrad_layout)
+from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
+                      emit_wgrad_adam, linears_of, make_gradbuf, wgrad_layout)
 from .nets import GradBuf, ParamSet, TC_MIN_ROWS, adam_descs, dgrad_problem, ens_n_tile, pick_cfg, wgrad_problem
 from .sac_family import LS_ACTOR, LS_ALPHA, LS_ALPHA_LOSS
 from .td3_iql import _BatchMixin
@@ -159,48 +159,43 @@ class EDACLearner(_BatchMixin, Learner):
                  self.noise_enable.data_ptr())
         plan.add("philox", lambda: L.call("orlk_philox_fill", *nargs, rt.cur))
 
-        # ---- actor: L = -mean min_e Q_e(s, a) + alpha mean logp      (edac.py:96-110)
-        emit_forward(rt, plan, run_a, [obs], "A.actor")
-        self._sample(plan, "A.sample", run_a.out[0], self.noise_views["eps_actor"], mXa, logp_a, obs)
-        emit_forward(rt, plan, run_ca, [mXa] * E, "A.critics")
-        largs = (run_ca.out.data_ptr(), B, E, logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha), 1,
-                 self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(), run_ca.dOut.data_ptr(), B,
-                 glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
-        plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *largs, rt.cur))
-        emit_head_dgrad(rt, plan, run_ca, "A.critics")
-        emit_hidden_dgrad(rt, plan, run_ca, "A.critics")
-        emit_dact(rt, plan, run_ca, dA, O, A, "A.critics")
-        bargs = (run_a.out.data_ptr(), 2 * A, self.noise_views["eps_actor"].data_ptr(), mXa.ptr + 4 * O, mXa.ld, dA.data_ptr(), E,
-                 B * A, A, glp.data_ptr(), B, A, run_a.dOut.data_ptr(), 2 * A)
-        plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
-        emit_head_dgrad(rt, plan, run_a, "A.actor")
-        emit_hidden_dgrad(rt, plan, run_a, "A.actor")
-        from .learner import emit_wgrad_adam
-        emit_wgrad_adam(rt, plan, run_a, [obs], gb_a, self.groups_ptr, "A.actor", polyak=False)
+        def actor_phase():
+            # ---- actor: L = -mean min_e Q_e(s, a) + alpha mean logp      (edac.py:96-110)
+            emit_forward(rt, plan, run_a, [obs], "A.actor")
+            self._sample(plan, "A.sample", run_a.out[0], self.noise_views["eps_actor"], mXa, logp_a, obs)
+            emit_forward(rt, plan, run_ca, [mXa] * E, "A.critics")
+            largs = (run_ca.out.data_ptr(), B, E, logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha), 1,
+                     self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(), run_ca.dOut.data_ptr(), B,
+                     glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+            plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *largs, rt.cur))
+            emit_head_dgrad(rt, plan, run_ca, "A.critics")
+            emit_hidden_dgrad(rt, plan, run_ca, "A.critics")
+            emit_dact(rt, plan, run_ca, dA, O, A, "A.critics")
+            bargs = (run_a.out.data_ptr(), 2 * A, self.noise_views["eps_actor"].data_ptr(), mXa.ptr + 4 * O, mXa.ld, dA.data_ptr(), E,
+                     B * A, A, glp.data_ptr(), B, A, run_a.dOut.data_ptr(), 2 * A)
+            plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
+            emit_head_dgrad(rt, plan, run_a, "A.actor")
+            emit_hidden_dgrad(rt, plan, run_a, "A.actor")
+            emit_wgrad_adam(rt, plan, run_a, [obs], gb_a, self.groups_ptr, "A.actor", polyak=False)
 
-        # ---- critics: TD to min_e Q'_e(s', a') - alpha logp'  +  eta * diversity      (edac.py:112-155)
-        emit_forward(rt, plan, run_an, [nobs], "C.actor_next")
-        self._sample(plan, "C.sample_next", run_an.out[0], self.noise_views["eps_next"], mXt, lp_next, nobs, rep=self.n_next)
-        emit_forward(rt, plan, run_t, [mXt] * E, "C.target")
-        tq = run_t.out
-        if self.n_next > 1:
-            margs = (run_t.out.data_ptr(), Bt, E, B, self.n_next, tq_best.data_ptr(), B)
-            plan.add("C.target_max", lambda: L.call("orlk_segment_max", *margs, rt.cur))
-            tq = tq_best
-        plan.add("C.concat", rt.concat([(mXd, obs, 1, Mat.of(self.act))]))
-        emit_forward(rt, plan, run_c, [mXd] * E, "C.critics")
-        use_alpha = 0 if (pol._deterministic_backup or self.n_next > 1) else 1
-        targs = (run_c.out.data_ptr(), B, E, tq.data_ptr(), B, E, lp_next.data_ptr(), self.scalars.data_ptr(), use_alpha,
-                 self.rew.data_ptr(), self.term.data_ptr(), B, float(pol._gamma), run_c.dOut.data_ptr(), B, None,
-                 self.loss_dev.data_ptr() + 4 * 12, self.loss_dev.data_ptr() + 4 * LS_TD_SUM)
-        plan.add("C.td_loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
-        emit_head_dgrad(rt, plan, run_c, "C.critics")
-        emit_hidden_dgrad(rt, plan, run_c, "C.critics")
-        # weight gradients of the TD loss: (layer, X [E,B,in] or a shared Mat, dY [E,B,out])
-        td_terms = [(l, (mXd if l == 0 else run_c.H[l - 1]), (run_c.dZ[l] if l < nh else run_c.dOut)) for l in range(nh + 1)]
-        self._emit_ens_wgrads(plan, "C.critics.wgrad_td", run_c, gb_c, td_terms, ones, split_base=0, with_bias=True,
-                              k_splits=td_layout, tiny=(B < TC_MIN_ROWS and s_td == 1))
-        if self.eta > 0:
+
+        def target_phase():
+            # ---- critics: TD to min_e Q'_e(s', a') - alpha logp'  +  eta * diversity      (edac.py:112-155)
+            emit_forward(rt, plan, run_an, [nobs], "C.actor_next")
+            self._sample(plan, "C.sample_next", run_an.out[0], self.noise_views["eps_next"], mXt, lp_next, nobs, rep=self.n_next)
+            emit_forward(rt, plan, run_t, [mXt] * E, "C.target")
+            tq = run_t.out
+            if self.n_next > 1:
+                margs = (run_t.out.data_ptr(), Bt, E, B, self.n_next, tq_best.data_ptr(), B)
+                plan.add("C.target_max", lambda: L.call("orlk_segment_max", *margs, rt.cur))
+                tq = tq_best
+            return tq
+
+        def data_forward():
+            plan.add("C.concat", rt.concat([(mXd, obs, 1, Mat.of(self.act))]))
+            emit_forward(rt, plan, run_c, [mXd] * E, "C.critics")
+
+        def g_chain():
             # 1. input-gradient chain (upstream 1)
             run_g.dOut.fill_(1.0)
             emit_head_dgrad(rt, plan, run_g, "G.chain")
@@ -237,6 +232,40 @@ class EDACLearner(_BatchMixin, Learner):
                     plan.add(f"G.ubar{l}", rt.gemm(fprobs, pick_cfg(B * E, lay.out_dim, rows_per_problem=B)))
                 # dW_{l+1} += ubar_l^T v_{l+1};  for the head: dw_head += sum_b ubar_L  (v = ones)
                 div_terms.append((l + 1, ubar[l], run_g.dZ[l + 1] if l + 1 < nh else None))
+            return div_terms
+
+        # The critics' forward on the data rows and the whole input-gradient chain of the diversity term read only the
+        # batch and the (not yet updated) critics, so they run on a branch beside the policy-improvement step and the
+        # target pass; the small-row launches emit no nested fork.
+        par = B < TC_MIN_ROWS and os.environ.get("ORLK_EDAC_BRANCHES", "1") != "0"
+        div_terms = None
+        if par:
+            plan.fork()
+            plan.branch(1)
+            data_forward()
+            if self.eta > 0:
+                div_terms = g_chain()
+            plan.branch(0)
+        actor_phase()
+        tq = target_phase()
+        if par:
+            plan.join()
+        else:
+            data_forward()
+        use_alpha = 0 if (pol._deterministic_backup or self.n_next > 1) else 1
+        targs = (run_c.out.data_ptr(), B, E, tq.data_ptr(), B, E, lp_next.data_ptr(), self.scalars.data_ptr(), use_alpha,
+                 self.rew.data_ptr(), self.term.data_ptr(), B, float(pol._gamma), run_c.dOut.data_ptr(), B, None,
+                 self.loss_dev.data_ptr() + 4 * 12, self.loss_dev.data_ptr() + 4 * LS_TD_SUM)
+        plan.add("C.td_loss", lambda: L.call("orlk_td_loss", *targs, rt.cur))
+        emit_head_dgrad(rt, plan, run_c, "C.critics")
+        emit_hidden_dgrad(rt, plan, run_c, "C.critics")
+        # weight gradients of the TD loss: (layer, X [E,B,in] or a shared Mat, dY [E,B,out])
+        td_terms = [(l, (mXd if l == 0 else run_c.H[l - 1]), (run_c.dZ[l] if l < nh else run_c.dOut)) for l in range(nh + 1)]
+        self._emit_ens_wgrads(plan, "C.critics.wgrad_td", run_c, gb_c, td_terms, ones, split_base=0, with_bias=True,
+                              k_splits=td_layout, tiny=(B < TC_MIN_ROWS and s_td == 1))
+        if self.eta > 0:
+            if div_terms is None:
+                div_terms = g_chain()
             self._emit_ens_wgrads(plan, "G.wgrad_div", run_c, gb_c, div_terms, ones, split_base=s_td, with_bias=False,
                                   k_splits=None, tiny=B < TC_MIN_ROWS, col0_first=O)
         splits = [s_td + 1] * (nh + 1)
