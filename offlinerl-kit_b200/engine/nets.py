@@ -251,15 +251,19 @@ ENSEMBLE_TC = os.environ.get("ORLK_ENSEMBLE_TC", "1") != "0"
 
 
 def ens_tc_ok(lays: Sequence["Layer"], G: int, M: int) -> bool:
-    return ENSEMBLE_TC and G >= 4 and G * M >= TC_MIN_ROWS and M >= 128 and all(lay.layout == "io" for lay in lays)
+    return ENSEMBLE_TC and G >= 4 and G * M >= TC_MIN_ROWS // 2 and M >= 128 and all(lay.layout == "io" for lay in lays)
 
 
 def ens_n_tile(G: int, M: int, N: int) -> int:
-    """Output columns per CTA for an ensemble launch: the narrowest 32-multiple that keeps the grid within one wave."""
-    for nt in (32, 64, 128):
-        if N % nt == 0 and G * (-(-M // 128)) * (N // nt) <= 148:
-            return nt
-    return 0
+    """Output columns per CTA for an ensemble launch: the narrowest 32-multiple that keeps the grid within one wave of
+    148 CTAs; ensembles too large for that (EDAC's 50 critics on hopper) take the widest tile, i.e. the fewest waves."""
+    best = 0
+    for nt in (32, 64, 128, 256):
+        if N % nt == 0:
+            best = nt
+            if G * (-(-M // 128)) * (N // nt) <= 148:
+                return nt
+    return best
 
 
 def tc_ok_fwd_io(lay: Layer) -> bool:
