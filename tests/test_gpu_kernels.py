@@ -648,6 +648,12 @@ def test_tc_gemm_forward_dgrad_wgrad_shapes(rt, passes):
     errs.append(_tc_case(rt, 1, 200, 96, 300, passes, L.EPI_NONE, 1, False, False, True, 12, a_mn=True, b_mn=True, n_tile=32))
     errs.append(_tc_case(rt, 2, 300, 256, 256, passes, L.EPI_RELU, 1, True, False, False, 13, a_mn=True))
     errs.append(_tc_case(rt, 2, 300, 256, 256, passes, L.EPI_NONE, 1, False, False, False, 14, b_mn=True))
+    # ensembles of short members (EDAC critics, 'io' weights): forward with an MN-major B in 64-column tiles, 50 members
+    # in full-width tiles (several waves), the input-gradient shape (K-major B, ReLU mask) and the weight gradient dW[i][o]
+    errs.append(_tc_case(rt, 10, 256, 256, 256, passes, L.EPI_RELU, 1, True, False, False, 42, n_tile=64, b_mn=True))
+    errs.append(_tc_case(rt, 50, 256, 256, 256, passes, L.EPI_RELU, 1, True, False, False, 43, n_tile=256, b_mn=True))
+    errs.append(_tc_case(rt, 10, 256, 256, 256, passes, L.EPI_RELU_MASK, 1, False, False, False, 44, n_tile=64))
+    errs.append(_tc_case(rt, 10, 256, 256, 256, passes, L.EPI_NONE, 1, False, False, False, 45, n_tile=64, a_mn=True, b_mn=True))
     # rank-1 operand generator (scalar-head backward folded into dgrad / wgrad), both operand orders
     errs.append(_tc_case(rt, 2, 7936, 256, 256, passes, L.EPI_RELU_MASK, 1, False, True, False, 15, gen_mode=True))
     errs.append(_tc_case(rt, 2, 256, 256, 7936, passes, L.EPI_NONE, 31, False, False, True, 16, gen_mode=True))
