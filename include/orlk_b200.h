@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 19
+#define ORLK_ABI_VERSION 20
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -369,7 +369,11 @@ int orlk_sumsq(const float* x, int64_t n, float scale, float* partial, void* str
 /* Gaussian NLL + soft-clamped logvar (ensemble_dynamics.py:193-201, dynamics_module.py:19-29): out [E][Bn][2D] = mean|raw,
  * y [E][Bn][D].  Writes dout (same shape as out), dmax[D], dmin[D] (incl. the +-coef terms) and out_loss[0]. */
 int orlk_dyn_nll(const float* out, const float* y, int E, int Bn, int D, const float* max_lv, const float* min_lv, float coef,
-                 const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss, void* stream);
+                 const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss,
+                 float* scratch, void* stream);
+/* scratch: NULL = one CTA; otherwise orlk_dyn_nll_scratch_floats(E, Bn, D) floats for the 64-rows-per-CTA form (partial
+ * records summed in block order by a second small launch: deterministic). */
+int orlk_dyn_nll_scratch_floats(int E, int Bn, int D);
 /* Holdout MSE of the mean head per member (ensemble_dynamics.py:210-217); y [Bn][D] is shared by the members. */
 int orlk_dyn_val_mse(const float* out, const float* y, int E, int Bn, int D, float* mse, void* stream);
 /* Imagination epilogue (ensemble_dynamics.py:43-77): term_kind 0 halfcheetah, 1 hopper, 2 walker2d, 3 never

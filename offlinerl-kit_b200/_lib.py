@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -120,7 +120,8 @@ _PROTOS = {
     "orlk_dyn_input": [_P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _L, _P],
     "orlk_gather_rows": [_P, _L, _I, _P, _L, _L, _I, _I, _P, _L, _L, _P],
     "orlk_sumsq_chunks": [_L], "orlk_sumsq": [_P, _L, _F, _P, _P],
-    "orlk_dyn_nll": [_P, _P, _I, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P],
+    "orlk_dyn_nll": [_P, _P, _I, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P],
+    "orlk_dyn_nll_scratch_floats": [_I, _I, _I],
     "orlk_dyn_val_mse": [_P, _P, _I, _I, _I, _P, _P],
     "orlk_dyn_step": [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
     "orlk_compact_rows": [_P, _I, _P, _L, _I, _P, _L, _P, _P],

@@ -111,6 +111,80 @@ k_dyn_nll(const float* __restrict__ out, const float* __restrict__ y, int E, int
     if (threadIdx.x == 0) out_loss[0] = loss + dec + bound;
 }
 
+// Multi-CTA form of the same loss: 64 rows per CTA write dout and one partial record [loss | gmax[D] | gmin[D]]; a single
+// small CTA sums the records in block order (deterministic) and adds the decay / bound terms.
+constexpr int NLL_ROWS = 64;
+
+__global__ void __launch_bounds__(256)
+k_dyn_nll_part(const float* __restrict__ out, const float* __restrict__ y, int n_rows, int Bn, int D,
+               const float* __restrict__ max_lv, const float* __restrict__ min_lv, float* __restrict__ dout,
+               float* __restrict__ partial) {
+    orlk::pdl_enter();
+    __shared__ float red[32];
+    __shared__ float s_g[2][256];
+    const float inv = 1.f / ((float)Bn * (float)D);
+    const int lanes_per_d = blockDim.x / D;
+    const int d = threadIdx.x % D, slot = threadIdx.x / D;
+    const int r0 = blockIdx.x * NLL_ROWS, r1 = min(n_rows, r0 + NLL_ROWS);
+    float loss = 0.f, gmax = 0.f, gmin = 0.f;
+    if (slot < lanes_per_d) {
+        const float mx = max_lv[d], mn = min_lv[d];
+        for (int r = r0 + slot; r < r1; r += lanes_per_d) {
+            const float* o = out + (int64_t)r * 2 * D;
+            const float mean = o[d], raw = o[D + d];
+            const float t1 = mx - raw;
+            const float u = mx - softplus_t(t1);
+            const float t2 = u - mn;
+            const float lv = mn + softplus_t(t2);
+            const float iv = expf(-lv);
+            const float diff = mean - y[(int64_t)r * D + d];
+            loss += (diff * diff * iv + lv) * inv;
+            const float dlv = (1.f - diff * diff * iv) * inv;
+            const float s2 = sigmoid_f(t2), s1 = sigmoid_f(t1);
+            dout[(int64_t)r * 2 * D + d] = 2.f * diff * iv * inv;
+            dout[(int64_t)r * 2 * D + D + d] = dlv * s2 * s1;
+            gmax += dlv * s2 * (1.f - s1);
+            gmin += dlv * (1.f - s2);
+        }
+    }
+    s_g[0][threadIdx.x] = gmax;
+    s_g[1][threadIdx.x] = gmin;
+    __syncthreads();
+    float* rec = partial + (int64_t)blockIdx.x * (1 + 2 * D);
+    if (threadIdx.x < D) {
+        float a = 0.f, b = 0.f;
+        for (int s = 0; s < lanes_per_d; ++s) { a += s_g[0][s * D + threadIdx.x]; b += s_g[1][s * D + threadIdx.x]; }
+        rec[1 + threadIdx.x] = a;
+        rec[1 + D + threadIdx.x] = b;
+    }
+    loss = block_sum(loss, red);
+    if (threadIdx.x == 0) rec[0] = loss;
+}
+
+__global__ void __launch_bounds__(256)
+k_dyn_nll_final(const float* __restrict__ partial, int n_blocks, int D, float coef, const float* __restrict__ max_lv,
+                const float* __restrict__ min_lv, const float* __restrict__ decay_partials, int n_decay,
+                float* __restrict__ dmax, float* __restrict__ dmin, float* __restrict__ out_loss) {
+    orlk::pdl_enter();
+    __shared__ float red[32];
+    const int W = 1 + 2 * D;
+    if (threadIdx.x < 2 * D) {
+        float a = 0.f;
+        for (int b = 0; b < n_blocks; ++b) a += partial[(int64_t)b * W + 1 + threadIdx.x];
+        if (threadIdx.x < D) dmax[threadIdx.x] = a + coef;
+        else dmin[threadIdx.x - D] = a - coef;
+    }
+    float loss = 0.f;
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) loss += partial[(int64_t)b * W];
+    float bound = threadIdx.x < D ? coef * (max_lv[threadIdx.x] - min_lv[threadIdx.x]) : 0.f;
+    float dec = 0.f;
+    for (int i = threadIdx.x; i < n_decay; i += blockDim.x) dec += decay_partials[i];
+    loss = block_sum(loss, red);
+    bound = block_sum(bound, red);
+    dec = block_sum(dec, red);
+    if (threadIdx.x == 0) out_loss[0] = loss + dec + bound;
+}
+
 // per-member holdout MSE of the mean head (ensemble_dynamics.py:210-217): one CTA per member
 __global__ void __launch_bounds__(256)
 k_dyn_val_mse(const float* __restrict__ out, const float* __restrict__ y, int Bn, int D, float* __restrict__ mse) {
@@ -343,9 +417,21 @@ int orlk_sumsq(const float* x, int64_t n, float scale, float* partial, void* str
     return check_launch("k_sumsq");
 }
 
+int orlk_dyn_nll_scratch_floats(int E, int Bn, int D) {
+    return ((E * Bn + NLL_ROWS - 1) / NLL_ROWS) * (1 + 2 * D);
+}
+
 int orlk_dyn_nll(const float* out, const float* y, int E, int Bn, int D, const float* max_lv, const float* min_lv, float coef,
-                 const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss, void* stream) {
+                 const float* decay_partials, int n_decay, float* dout, float* dmax, float* dmin, float* out_loss,
+                 float* scratch, void* stream) {
     ORLK_REQUIRE(E > 0 && Bn > 0 && D > 0 && D <= 64, "sizes (D <= 64)");
+    if (scratch != nullptr) {       // multi-CTA form; scratch holds orlk_dyn_nll_scratch_floats(E, Bn, D) floats
+        const int n_rows = E * Bn, n_blocks = (n_rows + NLL_ROWS - 1) / NLL_ROWS;
+        orlk::launch(k_dyn_nll_part, n_blocks, 256, 0, (cudaStream_t)stream, out, y, n_rows, Bn, D, max_lv, min_lv, dout, scratch);
+        orlk::launch(k_dyn_nll_final, 1, 256, 0, (cudaStream_t)stream, (const float*)scratch, n_blocks, D, coef, max_lv, min_lv,
+                     decay_partials, n_decay, dmax, dmin, out_loss);
+        return check_launch("k_dyn_nll_final");
+    }
     orlk::launch(k_dyn_nll, 1, 1024, 0, (cudaStream_t)stream, out, y, E, Bn, D, max_lv, min_lv, coef, decay_partials, n_decay, dout, dmax,
                                                    dmin, out_loss);
     return check_launch("k_dyn_nll");

@@ -108,46 +108,76 @@ class DynamicsEngine(Learner):
         Y = rt.zeros(E, Bn, D)
         nl = len(ps.layers)
         cfgs, splits = [], []
+        # short reductions (the reference's 256-row mini-batches): whole-k 32 x 16 tiles, no split-K partials for Adam to
+        # re-read -- 13 us per layer against 29 us for the split-K configuration
+        wg_tiny = Bn <= L.CFG_TILES[L.CFG_TINY][2] and os.environ.get("ORLK_DYN_WGRAD_TINY", "1") != "0"
         for l in range(nl):
             lay = ps.layers[l]
-            cfg = L.CFG_SMALL
+            cfg = L.CFG_TINY if wg_tiny else L.CFG_SMALL
             BM, BN, _ = L.CFG_TILES[cfg]
             tiles = (-(-lay.in_dim // BM)) * (-(-lay.out_dim // BN)) * E
-            splits.append(wgrad_splits(tiles, Bn, cfg))
+            splits.append(1 if wg_tiny else wgrad_splits(tiles, Bn, cfg))
             cfgs.append(cfg)
         gb = GradBuf(rt, ps, max(splits))
         plan = Plan(rt, f"dyn.learn{Bn}")
-        emit_dyn_forward(rt, plan, run, lambda e: Mat.of(X[e]), "D")
-        # weight-decay term of the reported loss: sum_l wd_l * 0.5 * sum W_l^2
+        par = os.environ.get("ORLK_DYN_BRANCHES", "1") != "0"
+        # weight-decay term of the reported loss: sum_l wd_l * 0.5 * sum W_l^2 -- reads the weights only, so it runs on a
+        # branch beside the forward pass
+        if par:
+            plan.fork()
+            plan.branch(1)
         off = 0
         for l, lay in enumerate(ps.layers):
             n = E * lay.w_numel
             args = (ps._ptr(ps.P, lay.w_off), n, 0.5 * self.wd[l], self.decay_partials.data_ptr() + 4 * off)
             plan.add(f"D.decay{l}", lambda args=args: L.call("orlk_sumsq", *args, rt.cur))
             off += rt.lib.orlk_sumsq_chunks(n)
+        if par:
+            plan.branch(0)
+        emit_dyn_forward(rt, plan, run, lambda e: Mat.of(X[e]), "D")
+        if par:
+            plan.join()
+        nll_scratch = rt.zeros(rt.lib.orlk_dyn_nll_scratch_floats(E, Bn, D))
         largs = [run.OUT.data_ptr(), Y.data_ptr(), E, Bn, D, ps.extra_ptr("max_logvar"), ps.extra_ptr("min_logvar"), 0.01,
                  self.decay_partials.data_ptr(), self.n_decay, run.dOUT.data_ptr(), self.dmax.data_ptr(), self.dmin.data_ptr(),
-                 self.loss_dev.data_ptr()]
+                 self.loss_dev.data_ptr(), nll_scratch.data_ptr()]
         state = {"coef": 0.01}
 
         def loss_op():
             largs[7] = state["coef"]
             L.call("orlk_dyn_nll", *largs, rt.cur)
         plan.add("D.loss", loss_op)
-        # backward: dH_last = (dOUT W_out^T) * swish'(Z_last), then down the stack
+
+        def wgrad_of(l):
+            probs = []
+            for e in range(E):
+                xin = Mat.of(X[e]) if l == 0 else Mat.of(run.H[l - 1][e])
+                dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
+                probs.append(wgrad_problem(ps, gb, l, e, xin, dy, splits[l]))
+            return probs
+
+        # backward: dH_last = (dOUT W_out^T) * swish'(Z_last), then down the stack.  The weight gradient of layer l needs
+        # only that layer's upstream gradient, so it runs on a branch beside the input gradient of the same layer.
+        wprobs = []
         for l in range(run.nh, 0, -1):
             probs = []
             for e in range(E):
                 dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
                 probs.append(dgrad_problem(ps, l, e, dy, Mat.of(run.dZ[l - 1][e]), L.EPI_DSWISH, Mat.of(run.Z[l - 1][e])))
+            if par:
+                plan.fork()
+                plan.branch(1)
+                plan.add(f"D.wgrad{l}", rt.gemm(wgrad_of(l), cfgs[l]))
+                plan.branch(0)
+            else:
+                wprobs += wgrad_of(l)
             plan.add(f"D.dgrad{l}", rt.gemm(probs, pick_cfg(Bn * E, ps.layers[l].in_dim, rows_per_problem=Bn)))
-        probs = []
-        for l in range(nl):
-            for e in range(E):
-                xin = Mat.of(X[e]) if l == 0 else Mat.of(run.H[l - 1][e])
-                dy = Mat.of(run.dOUT[e]) if l == run.nh else Mat.of(run.dZ[l][e])
-                probs.append(wgrad_problem(ps, gb, l, e, xin, dy, splits[l]))
-        plan.add("D.wgrad", rt.gemm(probs, L.CFG_SMALL))
+            if par:
+                plan.join()
+        if par:
+            plan.add("D.wgrad0", rt.gemm(wgrad_of(0), cfgs[0]))
+        else:
+            plan.add("D.wgrad", rt.gemm(wprobs + wgrad_of(0), cfgs[0]))
         descs = adam_descs(ps, gb, splits, polyak=False)
         # weight decay enters the gradient as wd_l * W_l (d/dW of wd * 0.5 * sum W^2); biases are not decayed
         k = 0
@@ -161,7 +191,7 @@ class DynamicsEngine(Learner):
         plan.add("D.adam", rt.adam(descs, self.groups_ptr))
         gp = C.c_void_p(self.groups_ptr)
         plan.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
-        plan.keep += [gb, run, X, Y]
+        plan.keep += [gb, run, X, Y, nll_scratch]
         self._learn_plans[Bn] = (plan, dict(X=X, Y=Y, run=run, state=state))
         return self._learn_plans[Bn]
 
