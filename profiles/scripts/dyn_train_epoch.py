@@ -21,6 +21,13 @@ O, A, N, EPOCHS = 17, 6, 1_000_000, 3
 data = make_dataset(N, O, A, seed=0)
 data["rewards"] = data["rewards"].reshape(-1, 1)
 out = {}
+# one discarded short run first: library load, graph capture and allocator warm-up are not part of the comparison
+_m = EnsembleDynamicsModel(O, A, [200, 200, 200, 200], num_ensemble=7, num_elites=5,
+                           weight_decays=[2.5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4], device="cuda:0")
+_d = EnsembleDynamics(_m, torch.optim.Adam(_m.parameters(), lr=1e-3), StandardScaler(), termination_fn_halfcheetah)
+_lg = Logger(tempfile.mkdtemp())
+_lg.quiet = True
+_d.train({k: v[:50_000] for k, v in data.items()}, _lg, max_epochs=1, max_epochs_since_update=100)
 for flag in ("0", "1"):
     os.environ["ORLK_DYN_SHUFFLE_OVERLAP"] = flag
     torch.manual_seed(0)
