@@ -49,11 +49,14 @@ def test_cql_fast_mode_tolerance(name):
     run_golden_steps(Golden(name), tol=2e-3, verbose=True, precision="tf32", elementwise=False)
 
 
-def test_cql_eager_equals_graph():
-    """The captured CUDA graph and the eager launch sequence give identical results."""
+@pytest.mark.parametrize("name", ["cql_small_lagrange", "sac_small", "iql_small", "td3bc_small", "edac_small", "sac_hc",
+                                  "edac_hc"])
+def test_cql_eager_equals_graph(name):
+    """The captured CUDA graph and the eager launch sequence (side streams + events for the parallel branches) give
+    identical results, for every algorithm whose step forks."""
     import torch
     from tests.gpu_common import run_golden_steps
-    g = Golden("cql_small_lagrange")
+    g = Golden(name)
     p1 = run_golden_steps(g, tol=TOL, use_graph=True)
     p2 = run_golden_steps(g, tol=TOL, use_graph=False)
     for (k, a), (_, b) in zip(p1.state_dict().items(), p2.state_dict().items()):

@@ -171,3 +171,25 @@ def test_dynamics_train_shuffle_overlap_is_invisible(tmp_path, monkeypatch):
     assert np.array_equal(st1, st0) and np.array_equal(mu1, mu0)
     for k in sd1:
         assert torch.equal(sd1[k], sd0[k]), k
+
+
+def test_dynamics_learn_eager_equals_graph():
+    """The branched training step (decay sums beside the forward pass, weight gradients beside the input gradients)
+    gives bit-identical parameters whether it is replayed as a CUDA graph or launched eagerly on side streams."""
+    from offlinerlkit_b200.synthetic import make_dataset
+    g = Golden("dynamics_small")
+    m = g.meta
+    d = make_dataset(m["n_data"], m["O"], m["A"], seed=m["data_seed"])
+    x = np.concatenate([d["observations"], d["actions"]], axis=-1)
+    y = np.concatenate([d["next_observations"] - d["observations"], d["rewards"].reshape(-1, 1)], axis=-1)
+    xs = (x - g["scaler_mu"]) / g["scaler_std"]
+    boot = g["boot"]
+    states = []
+    for use_graph in (True, False):
+        dyn = _build_dynamics(m, initial_state(m), g["scaler_mu"], g["scaler_std"], m["term"])
+        dyn.engine.use_graph = use_graph
+        loss = dyn.learn(xs[boot], y[boot], batch_size=m["B"])
+        states.append((loss, {k: v.detach().clone() for k, v in dyn.model.state_dict().items()}))
+    assert states[0][0] == states[1][0]
+    for k in states[0][1]:
+        assert torch.equal(states[0][1][k], states[1][1][k]), k
