@@ -108,6 +108,56 @@ class DynamicsOracle:
         return next_obs, reward, terminal, info
 
 
+def train(ora: "DynamicsOracle", inputs: np.ndarray, targets: np.ndarray, num_elites: int, max_epochs: Optional[int] = None,
+          max_epochs_since_update: int = 5, batch_size: int = 256, holdout_ratio: float = 0.2,
+          logvar_loss_coef: float = 0.01) -> Dict:
+    """dynamics/ensemble_dynamics.py:111-176: holdout split (torch ``random_split``), scaler fit on the training rows,
+    per-member bootstrap index matrix (``np.random.randint``), one ``learn`` pass + ``validate`` per epoch, per-member
+    ``update_save`` when the holdout loss improved by more than 1 %, row shuffle of the index matrix
+    (``np.random.uniform`` + argsort), early stop, elite selection and ``load_save``.  Consumes the torch CPU generator
+    and the NumPy global generator in the reference's order.  Returns the per-epoch log and the final state."""
+    data_size = inputs.shape[0]
+    holdout_size = min(int(data_size * holdout_ratio), 1000)
+    train_size = data_size - holdout_size
+    tr, ho = torch.utils.data.random_split(range(data_size), (train_size, holdout_size))      # :125
+    tx, ty = inputs[tr.indices], targets[tr.indices]
+    hx, hy = inputs[ho.indices], targets[ho.indices]
+    mu, std = scaler_fit(tx)                                                                  # :129
+    tx, hx = (tx - mu) / std, (hx - mu) / std
+    E = ora.p["backbones.0.weight"].shape[0]
+    holdout_losses = [1e10] * E
+    idxes = np.random.randint(train_size, size=[E, train_size])                               # :134
+    saved = {k: ora.p[k].detach().clone() for k in ora.p if "saved_" in k}
+    log, epoch, cnt = [], 0, 0
+    while True:
+        epoch += 1
+        train_loss = ora.learn(tx[idxes], ty[idxes], batch_size, logvar_loss_coef)            # :144
+        new = ora.validate(hx, hy)
+        log.append((train_loss, float(np.sort(new)[:num_elites].mean()), [float(v) for v in new]))
+        order = np.argsort(np.random.uniform(size=idxes.shape), axis=-1)                      # :135-137,153
+        idxes = idxes[np.arange(E)[:, None], order]
+        improved = []
+        for i, (n_, o_) in enumerate(zip(new, holdout_losses)):
+            if (o_ - n_) / o_ > 0.01:
+                improved.append(i)
+                holdout_losses[i] = n_
+        if improved:                                                                          # ensemble_linear.py:46-49
+            for k in saved:
+                saved[k][improved] = ora.p[k.replace("saved_", "")].detach()[improved]
+            cnt = 0
+        else:
+            cnt += 1
+        if cnt >= max_epochs_since_update or (max_epochs and epoch >= max_epochs):
+            break
+    elites = [i for _, i in sorted(zip(holdout_losses, range(E)), key=lambda x: x[0])][:num_elites]      # :219-223
+    with torch.no_grad():                                                                     # load_save, ensemble_linear.py:43-45
+        for k, v in saved.items():
+            ora.p[k].copy_(v)
+            ora.p[k.replace("saved_", "")].copy_(v)
+    return {"log": log, "elites": elites, "holdout_losses": [float(v) for v in holdout_losses], "mu": mu, "std": std,
+            "epochs": epoch}
+
+
 def scaler_fit(data: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """utils/scaler.py:11-23."""
     mu = np.mean(data, axis=0, keepdims=True)

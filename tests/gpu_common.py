@@ -4,7 +4,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from tests.helpers import Golden, initial_state, assert_stats_close, rel_err
+from tests.helpers import (Golden, initial_state, assert_stats_close, assert_grad_stats_close, assert_grads_close, rel_err)
 
 
 class Box:
@@ -66,6 +66,75 @@ def build_policy(meta, device="cuda:0"):
     raise KeyError(algo)
 
 
+class EngineGrads:
+    """The gradients the engine's fused Adam launches consumed, recovered from the first moments:
+    m_t = beta1 m_{t-1} + (1 - beta1) g_t  =>  g_t = (m_t - beta1 m_{t-1}) / (1 - beta1).  ``snapshot()`` before a step,
+    ``after()`` behind it.  Names follow the policy's ``state_dict`` (+ ``log_alpha`` / ``cql_log_alpha``)."""
+
+    def __init__(self, policy, eng, param_sets=None):
+        self.eng = eng
+        self.where = {}
+        for name, p in policy.named_parameters():
+            for ps in (param_sets or eng.param_sets):
+                off = (p.data_ptr() - ps.P.data_ptr()) // 4
+                if 0 <= off < ps.total and p.device == ps.P.device:
+                    self.where[name] = (ps, off, p.shape, p.numel())
+        self.beta1 = float(eng._groups[0].beta1)
+        self.prev = None
+
+    def _moments(self):
+        out = {n: ps.Mo[off:off + cnt].clone() for n, (ps, off, shp, cnt) in self.where.items()}
+        for n, attr in (("log_alpha", "alpha_mv"), ("cql_log_alpha", "cql_mv")):
+            t = getattr(self.eng, attr, None)
+            if t is not None:
+                out[n] = t[:1].clone()
+        return out
+
+    def snapshot(self):
+        self.prev = self._moments()
+
+    def after(self, names):
+        cur, b1 = self._moments(), self.beta1
+        out = {}
+        for n in names:
+            shape = self.where[n][2] if n in self.where else (1,)
+            out[n] = ((cur[n].double() - b1 * self.prev[n].double()) / (1.0 - b1)).view(shape).cpu()
+        return out
+
+
+def make_oracle(meta):
+    """The CPU oracle (pinned to the reference by tests/test_oracle_golden.py) on the fixture's initial state: supplies
+    the FULL gradient tensors of config-size runs, of which the fixture only stores fingerprints."""
+    from oracle import algos
+    algo, hy = meta["algo"], meta.get("hyper", {})
+    st = initial_state(meta)
+    alpha = (meta["target_entropy"], 0.0, meta["alpha_lr"]) if "alpha_lr" in meta else None
+    if algo == "cql":
+        return algos.CQLOracle(st, alpha=alpha, **hy)
+    if algo == "combo":
+        return algos.COMBOOracle(st, rho_s=meta["rho_s"], alpha=alpha, **hy)
+    if algo == "sac":
+        return algos.SACOracle(st, alpha=alpha, **hy)
+    if algo == "edac":
+        return algos.EDACOracle(st, alpha=alpha, **hy)
+    if algo == "iql":
+        return algos.IQLOracle(st, **hy)
+    if algo == "td3bc":
+        return algos.TD3BCOracle(st, **hy)
+    raise KeyError(algo)
+
+
+def check_step_grads(g: Golden, t: int, tap: "EngineGrads", ora, ref_batch, noise, tol: float):
+    """Engine gradients of step t vs (a) the reference's fingerprints in the fixture, (b) the oracle's full tensors:
+    relative L2 <= tol per tensor, element-wise rtol = tol with atol = tol * max|g| (north_star: 1e-4 in fp32)."""
+    stats = g.group(f"gradstats{t}")
+    got = tap.after(stats.keys())
+    assert_grad_stats_close(got, stats, tol=tol, what=f"step {t}")
+    if ora is not None:
+        ora.step(ref_batch, noise) if noise is not None else ora.step(ref_batch)
+        assert_grads_close(got, {k: ora.grads[k] for k in stats}, tol=tol, what=f"step {t}")
+
+
 def load_state(policy, state: Dict[str, torch.Tensor]) -> None:
     missing, unexpected = policy.load_state_dict(state, strict=False)
     assert not unexpected, unexpected
@@ -82,7 +151,7 @@ def make_buffer(g: Golden, device="cuda:0"):
 
 
 def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph=True, device="cuda:0", precision=None,
-                     elementwise=True):
+                     elementwise=True, grads=True):
     """Engine vs golden (= the real reference): index draw + gather bit-exact, then losses and parameters."""
     m = g.meta
     policy = build_policy(m, device)
@@ -92,6 +161,7 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
     np.random.seed(m["np_seed"])
     n_steps = n_steps or m["n_steps"]
     lr_atol = 2.5 * max(v for k, v in m["hyper"].items() if k.endswith("_lr"))
+    tap, ora = None, (make_oracle(m) if grads else None)
     for t in range(n_steps):
         batch = buf.sample(m["B"])
         torch.cuda.synchronize()
@@ -104,7 +174,13 @@ def run_golden_steps(g: Golden, n_steps=None, tol=1e-4, verbose=False, use_graph
         if precision is not None and t == 0:
             eng.precision = precision
         noise = g.noise(t) if any(k.startswith(f"noise{t}|") for k in g.z.files) else None
+        if grads and tap is None and eng.param_sets:
+            tap = EngineGrads(policy, eng)
+        if tap is not None:
+            tap.snapshot()
         out = policy.learn(batch, noise=noise) if noise is not None else policy.learn(batch)
+        if tap is not None:
+            check_step_grads(g, t, tap, ora, ref_b, noise, tol)
         ref = g.losses(t)
         if verbose:
             print(f"step {t}: engine {out}\n        golden {ref}", flush=True)
@@ -149,6 +225,7 @@ def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", 
         states.append(np.random.get_state())
     lr_atol = 2.5 * max(v for k, v in m["hyper"].items() if k.endswith("_lr"))
     sizes, keys = (m["n_real"], m["n_fake"]), ("idx", "fake_idx")
+    tap, ora = None, make_oracle(m)
     for t in range(m["n_steps"]):
         parts = []
         for i in range(2):
@@ -168,7 +245,13 @@ def run_combo_golden_steps(g: Golden, tol=1e-4, verbose=False, device="cuda:0", 
         if precision is not None and t == 0:
             policy._split = sizes
             policy.engine(m["B"]).precision = precision
+        if tap is not None:
+            tap.snapshot()
         out = policy.learn({"real": parts[0], "fake": parts[1]}, noise=g.noise(t))
+        if tap is None:         # the engine exists after the first learn: its moments started at zero
+            tap = EngineGrads(policy, policy._engine)
+            tap.prev = {k: torch.zeros_like(v) for k, v in tap._moments().items()}
+        check_step_grads(g, t, tap, ora, g.batch(t, datasets[0]), g.noise(t), tol)
         ref = g.losses(t)
         if verbose:
             print(f"step {t}: engine {out}\n        golden {ref}", flush=True)

@@ -182,3 +182,67 @@ def assert_stats_close(state: Dict[str, torch.Tensor], stats: Dict[str, np.ndarr
         assert got.shape == ref.shape, k
         np.testing.assert_allclose(got[1:3], ref[1:3], rtol=tol, atol=3 * lr_atol, err_msg=k)
         np.testing.assert_allclose(got[3:], ref[3:], rtol=tol, atol=lr_atol + 1e-7, err_msg=k)
+
+
+# ---------------------------------------------------------------------------------------------- gradients
+def grad_stats(t) -> np.ndarray:
+    """[sum, abs-sum, L2, max-abs, 64 strided elements] -- same fingerprint as make_golden.grad_stats."""
+    x = (t.detach().double().flatten().cpu().numpy() if torch.is_tensor(t) else np.asarray(t, np.float64).ravel())
+    stride = max(1, x.size // 64)
+    return np.concatenate([[x.sum(), np.abs(x).sum(), np.sqrt((x * x).sum()), np.abs(x).max()], x[::stride][:64]])
+
+
+def assert_grad_stats_close(grads: Dict[str, torch.Tensor], stats: Dict[str, np.ndarray], tol: float, what: str = ""):
+    """Gradients vs the reference's fingerprints (``gradstats{t}`` of a golden file): the same tensors must be present,
+    abs-sum / L2 / max-abs relative to ``tol``, the sampled elements with ``atol = tol * max|g|``."""
+    assert set(grads) == set(stats), (what, sorted(set(grads) ^ set(stats)))
+    for k, ref in stats.items():
+        got = grad_stats(grads[k])
+        assert got.shape == ref.shape, (what, k)
+        scale = max(ref[3], 1e-30)
+        np.testing.assert_allclose(got[1:4], ref[1:4], rtol=tol, atol=tol * scale, err_msg=f"{what} {k} norms")
+        np.testing.assert_allclose(got[4:], ref[4:], rtol=tol, atol=tol * scale, err_msg=f"{what} {k} elements")
+
+
+def assert_grads_close(got: Dict[str, torch.Tensor], ref: Dict[str, torch.Tensor], tol: float, what: str = ""):
+    """Full gradient tensors: relative L2 error <= tol per tensor and element-wise rtol = tol, atol = tol * max|g|."""
+    assert set(got) == set(ref), (what, sorted(set(got) ^ set(ref)))
+    for k, r in ref.items():
+        a = got[k].detach().double().cpu().reshape(-1).numpy()
+        b = r.detach().double().cpu().reshape(-1).numpy()
+        assert a.shape == b.shape, (what, k, a.shape, b.shape)
+        l2 = np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b * b).sum()), 1e-30)
+        assert l2 <= tol, (what, k, "rel-L2", l2)
+        np.testing.assert_allclose(a, b, rtol=tol, atol=tol * max(np.abs(b).max(), 1e-30), err_msg=f"{what} {k}")
+
+
+# ---------------------------------------------------------------------------------------------- config-5 rollout fixtures
+def cfg5_setup(meta):
+    """Inputs of a ``rollout_cfg5_*`` fixture rebuilt from its recipes (make_golden.gen_rollout_cfg5):
+    (dynamics state dict, actor state dict, scaler mu, scaler std, start states)."""
+    O, A = meta["O"], meta["A"]
+    raw = param_recipe(dynamics_shapes(O, A, meta["dyn_hidden"], meta["E"]), meta["dyn_seed"])
+    dyn = {k: torch.from_numpy(v) for k, v in raw.items()}
+    dyn["max_logvar"] = torch.full((O + 1,), 0.5)
+    dyn["min_logvar"] = torch.full((O + 1,), -10.0)
+    dyn["output_layer.weight"].mul_(0.1)
+    dyn["output_layer.bias"][..., O + 1:] = -6.0
+    dyn["elites"] = torch.tensor(meta["elites"])
+    actor = recipe_state(actorprob_shapes(O, A, meta["hidden"]), meta["param_seeds"]["actor"], "actor")
+    data = make_dataset(meta["S"], O, A, seed=meta["data_seed"])
+    x = np.concatenate([data["observations"], data["actions"]], axis=-1)
+    mu = np.mean(x, axis=0, keepdims=True)
+    std = np.std(x, axis=0, keepdims=True)
+    std[std < 1e-12] = 1.0
+    init = data["observations"].copy()
+    if meta["term"] == "walker2d":
+        init[:, 0] = 1.4 + 0.35 * init[:, 0]
+        init[:, 1] = 0.3 * init[:, 1]
+    return dyn, actor, mu, std, init
+
+
+def array_stats(x, rows: int = 64) -> np.ndarray:
+    x = np.asarray(x)
+    x2 = x.reshape(len(x), -1).astype(np.float64)
+    stride = max(1, len(x2) // rows)
+    return np.concatenate([[x2.sum(), np.abs(x2).sum(), np.sqrt((x2 * x2).sum())], x2[::stride][:rows].ravel()])

@@ -8,7 +8,7 @@ TOL = 1e-4      # north_star: losses / parameters within 1e-4 relative in fp32
 
 
 @pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hopper", "cql_hc", "cql_hc_lagrange",
-                                  "cql_small_maxq", "cql_hc_maxq"])
+                                  "cql_small_maxq", "cql_hc_maxq", "cql_hc_stochastic_backup"])
 @pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
 def test_cql_matches_reference(name, precision):
     """fp32 = SIMT FFMA GEMMs everywhere; tf32x3 = the wide critic GEMMs on tcgen05 with hi/lo operand split.
@@ -46,7 +46,7 @@ def test_cql_fast_mode_tolerance(name):
     from tests.gpu_common import run_golden_steps
     # Adam turns a rounding-level sign flip of a tiny gradient into a 2*lr parameter change, so single elements
     # are only bounded by a few lr in this mode; losses and per-tensor norms are held to 2e-3.
-    run_golden_steps(Golden(name), tol=2e-3, verbose=True, precision="tf32", elementwise=False)
+    run_golden_steps(Golden(name), tol=2e-3, verbose=True, precision="tf32", elementwise=False, grads=False)
 
 
 @pytest.mark.parametrize("name", ["cql_small_lagrange", "sac_small", "iql_small", "td3bc_small", "edac_small", "sac_hc",

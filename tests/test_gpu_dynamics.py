@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import Golden, initial_state, assert_stats_close, rel_err
+from tests.helpers import (Golden, initial_state, assert_stats_close, assert_grad_stats_close, assert_grads_close, rel_err,
+                           cfg5_setup, array_stats)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -21,7 +22,7 @@ def _build_dynamics(m, state, mu, std, term):
     assert not unexpected
     optim = torch.optim.Adam(model.parameters(), lr=m.get("lr", 1e-3))
     fn = {"halfcheetah": T.termination_fn_halfcheetah, "hopper": T.termination_fn_hopper, "walker2d": T.termination_fn_walker2d}[m["term"]]
-    return EnsembleDynamics(model, optim, StandardScaler(mu, std), fn, penalty_coef=m["penalty_coef"])
+    return EnsembleDynamics(model, optim, StandardScaler(mu, std), fn, penalty_coef=m.get("penalty_coef", 0.5))
 
 
 @pytest.mark.parametrize("name", ["dynamics_small", "dynamics_hc"])
@@ -36,8 +37,23 @@ def test_dynamics_learn_validate_step(name):
     xs = (x - mu) / std
     dyn = _build_dynamics(m, initial_state(m), mu, std, m["term"])
     boot = g["boot"]
-    loss = dyn.learn(xs[boot], y[boot], batch_size=m["B"])
+    # all mini-batches but the last, then the last one alone: its gradients are what the fixture's fingerprints describe
+    from tests.gpu_common import EngineGrads
+    from oracle import dynamics as odyn
+    nb, B = m["n_batches"], m["B"]
+    head = slice(0, (nb - 1) * B)
+    loss_a = dyn.learn(xs[boot][:, head], y[boot][:, head], batch_size=B)
+    tap = EngineGrads(dyn.model, dyn.engine, param_sets=[dyn.engine.ps])
+    tap.snapshot()
+    loss_b = dyn.learn(xs[boot][:, (nb - 1) * B:], y[boot][:, (nb - 1) * B:], batch_size=B)
+    loss = (loss_a * (nb - 1) + loss_b) / nb
     assert loss == pytest.approx(float(g["learn_loss"]), rel=TOL)
+    stats = g.group("gradstats_last")
+    got = tap.after(stats.keys())
+    assert_grad_stats_close(got, stats, tol=TOL, what=name)
+    ora = odyn.DynamicsOracle(initial_state(m), m["weight_decays"], lr=m["lr"])      # full tensors from the pinned oracle
+    ora.learn(xs[boot], y[boot], batch_size=B)
+    assert_grads_close(got, {k: ora.grads[k] for k in stats}, tol=TOL, what=name)
     sd = {k: v.detach().cpu() for k, v in dyn.model.state_dict().items()}
     assert_stats_close(sd, g.group("stats"), tol=TOL, lr_atol=2.5 * m["lr"])
     val = dyn.validate(xs[:m["holdout"]], y[:m["holdout"]])
@@ -193,3 +209,93 @@ def test_dynamics_learn_eager_equals_graph():
     assert states[0][0] == states[1][0]
     for k in states[0][1]:
         assert torch.equal(states[0][1][k], states[1][1][k]), k
+
+
+class _ListLogger:
+    """Records what EnsembleDynamics.train logs per epoch (the Logger API subset it uses)."""
+
+    def __init__(self, model_dir):
+        self.model_dir, self.rows, self._kv = str(model_dir), [], {}
+
+    def log(self, *a, **k):
+        pass
+
+    def logkv(self, k, v):
+        self._kv[k] = float(v)
+
+    def set_timestep(self, t):
+        self._kv["timestep"] = t
+
+    def dumpkvs(self, exclude=None):
+        self.rows.append(dict(self._kv))
+        self._kv = {}
+
+
+def test_dynamics_train_matches_reference(tmp_path):
+    """EnsembleDynamics.train end to end vs the reference's own run (ensemble_dynamics.py:111-176): the torch
+    ``random_split`` holdout, the scaler, the NumPy bootstrap matrix and its per-epoch row shuffles are consumed in the
+    reference's order; per-epoch train / holdout losses, the elites, the scaler and the final (load_save'd) parameters."""
+    from tests.test_oracle_golden import dynamics_train_data
+    g = Golden("dynamics_train_small")
+    m = g.meta
+    x, y = dynamics_train_data(g)
+    O = m["O"]
+    data = {"observations": x[:, :O], "actions": x[:, O:], "next_observations": x[:, :O] + y[:, :O], "rewards": y[:, O:]}
+    from offlinerlkit_b200.utils.scaler import StandardScaler
+    dyn = _build_dynamics(m, initial_state(m), None, None, m["term"])
+    dyn.scaler = StandardScaler()
+    logger = _ListLogger(tmp_path)
+    torch.manual_seed(m["torch_seed"])
+    np.random.seed(m["np_seed"])
+    dyn.train(data, logger, **m["train_kw"])
+    assert len(logger.rows) == m["epochs"]
+    assert rel_err([r["loss/dynamics_train_loss"] for r in logger.rows], g["train_loss"]) < TOL
+    assert rel_err([r["loss/dynamics_holdout_loss"] for r in logger.rows], g["holdout_loss"]) < TOL
+    assert dyn.model.elites.data.tolist() == g["elites"].tolist()
+    assert rel_err(dyn.scaler.mu, g["scaler_mu"]) < 1e-6 and rel_err(dyn.scaler.std, g["scaler_std"]) < 1e-6
+    sd = {k: v.detach().cpu().numpy() for k, v in dyn.model.state_dict().items()}
+    lr_atol = 2.5 * m["lr"]
+    for k, v in g.group("post").items():
+        assert np.abs(sd[k] - v).max() <= TOL * np.abs(v).max() + lr_atol, k
+        assert abs(np.abs(sd[k]).sum() - np.abs(v).sum()) <= 10 * TOL * np.abs(v).sum() + 3 * lr_atol, k
+
+
+@pytest.mark.parametrize("name", ["rollout_cfg5_hc", "rollout_cfg5_walker"])
+def test_rollout_config5_size_matches_reference(name):
+    """MOPOPolicy.rollout at BASELINE.json configs[4] size -- 50 000 start states x horizon 5, 7 members of 200 x 4 (the
+    tcgen05 ensemble path and the two-launch block-scan compaction are both live) -- vs the reference's own run: survivor
+    counts per step and the number of terminals exact, per-array fingerprints (norms + 64 strided rows) at 2e-4.  The
+    draws are re-made from the fixture's seeds in the reference's consumption order."""
+    from offlinerlkit_b200.nets import MLP
+    from offlinerlkit_b200.modules import ActorProb, Critic, TanhDiagGaussian
+    from offlinerlkit_b200.policy import MOPOPolicy
+    g = Golden(name)
+    m = g.meta
+    O, A, hid, E, D = m["O"], m["A"], m["hidden"], m["E"], m["O"] + 1
+    dyn_state, actor_state, mu, std, init = cfg5_setup(m)
+    dyn = _build_dynamics(m, dyn_state, mu, std, m["term"])
+    dyn.model.set_elites(m["elites"])
+    bb = MLP(O, hid)
+    actor = ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), DEV)
+    actor.load_state_dict({k[len("actor."):]: v for k, v in actor_state.items()})
+    c1, c2 = Critic(MLP(O + A, hid), DEV), Critic(MLP(O + A, hid), DEV)
+    adam = lambda mod: torch.optim.Adam(mod.parameters(), lr=1e-4)
+    pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2)
+    counts = g["counts"].tolist()
+    torch.manual_seed(m["torch_seed"])
+    np.random.seed(m["np_seed"])
+    elites = np.asarray(m["elites"])
+    eps, nrm, mid = [], [], []
+    for c in counts:            # per imagined step: eps (torch CPU generator), then normal and choice (NumPy global generator)
+        eps.append(torch.randn(c, A).numpy())
+        nrm.append(np.random.normal(size=(E, c, D)))
+        mid.append(np.random.choice(elites, size=c))
+    out, info = pol.rollout(init, m["horizon"], noise={"eps": eps, "normal": nrm, "midx": mid})
+    assert info["num_transitions"] == m["num_transitions"] == sum(counts)
+    assert int(out["terminals"].sum()) == int(g["terminal_count"])
+    for k, v in out.items():
+        got, ref = array_stats(v.astype(np.float64) if v.dtype == bool else v), g["outstats|" + k]
+        assert got.shape == ref.shape, k
+        assert rel_err(got[:3], ref[:3]) < 2e-4, (k, got[:3], ref[:3])
+        assert rel_err(got[3:], ref[3:]) < 2e-4, k
+    assert info["reward_mean"] == pytest.approx(float(g["reward_mean"]), rel=2e-4)

@@ -4,7 +4,8 @@ import pytest
 import torch
 
 from oracle import algos, dynamics as odyn, replay as oreplay
-from tests.helpers import Golden, initial_state, assert_stats_close, rel_err, FIELDS
+from tests.helpers import (Golden, initial_state, assert_stats_close, assert_grad_stats_close, rel_err, FIELDS, cfg5_setup,
+                           array_stats)
 
 TOL = 2e-5
 
@@ -22,6 +23,10 @@ def _run(g, ora, with_noise=True):
         for k in ref:
             assert out[k] == pytest.approx(ref[k], rel=TOL, abs=TOL), (t, k)
         assert_stats_close(ora.state_dict(), g.group(f"stats{t}"), tol=TOL)
+        # the gradients every Adam step of the reference consumed (step pre-hooks on the reference's own optimisers)
+        assert_grad_stats_close(ora.grads, g.group(f"gradstats{t}"), tol=TOL, what=f"step {t}")
+        for k, v in g.group(f"grads{t}").items():
+            assert rel_err(ora.grads[k].numpy(), v) < TOL, (t, k)
     post = g.group("post")
     if post:
         sd = ora.state_dict()
@@ -31,7 +36,7 @@ def _run(g, ora, with_noise=True):
 
 
 @pytest.mark.parametrize("name", ["cql_small", "cql_small_lagrange", "cql_hc", "cql_hc_lagrange", "cql_hopper", "cql_small_maxq",
-                                  "cql_hc_maxq"])
+                                  "cql_hc_maxq", "cql_hc_stochastic_backup"])
 def test_cql(name):
     g = Golden(name)
     _run(g, algos.CQLOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
@@ -50,7 +55,7 @@ def test_sac(name):
     _run(g, algos.SACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
 
 
-@pytest.mark.parametrize("name", ["edac_small", "edac_hc", "edac_small_maxq"])
+@pytest.mark.parametrize("name", ["edac_small", "edac_hc", "edac_small_maxq", "edac_hopper_e50"])
 def test_edac(name):
     g = Golden(name)
     _run(g, algos.EDACOracle(initial_state(g.meta), alpha=_alpha(g.meta), **g.meta["hyper"]))
@@ -62,7 +67,7 @@ def test_iql(name):
     _run(g, algos.IQLOracle(initial_state(g.meta), **g.meta["hyper"]), with_noise=False)
 
 
-@pytest.mark.parametrize("name", ["td3bc_small", "td3bc_walker"])
+@pytest.mark.parametrize("name", ["td3bc_small", "td3bc_walker", "td3bc_walker_b1024"])
 def test_td3bc(name):
     g = Golden(name)
     _run(g, algos.TD3BCOracle(initial_state(g.meta), **g.meta["hyper"]))
@@ -102,6 +107,7 @@ def test_dynamics(name):
     loss = ora.learn(x[boot], y[boot], batch_size=m["B"])
     assert loss == pytest.approx(float(g["learn_loss"]), rel=TOL)
     assert_stats_close({k: v.detach() for k, v in ora.p.items()}, g.group("stats"), tol=TOL)
+    assert_grad_stats_close(ora.grads, g.group("gradstats_last"), tol=TOL, what="last mini-batch")
     val = ora.validate(x[:m["holdout"]], y[:m["holdout"]])
     assert rel_err(val, g["val"]) < TOL
     fn = {"halfcheetah": odyn.term_halfcheetah, "hopper": odyn.term_hopper, "walker2d": odyn.term_walker2d}[m["term"]]
@@ -152,3 +158,70 @@ def test_rollout_compaction(name):
     for k in ("obss", "next_obss", "actions", "rewards"):
         assert rel_err(out[k], g["out|" + k]) < 1e-4, k
     assert np.array_equal(out["terminals"], g["out|terminals"])
+
+
+def test_dynamics_train_loop():
+    """ensemble_dynamics.py:111-176: holdout split, bootstrap matrix, per-epoch losses, update_save, elites, load_save."""
+    from offlinerlkit_b200.synthetic import make_dataset
+    g = Golden("dynamics_train_small")
+    m = g.meta
+    x, y = dynamics_train_data(g)
+    ora = odyn.DynamicsOracle(initial_state(m), m["weight_decays"], lr=m["lr"])
+    torch.manual_seed(m["torch_seed"])
+    np.random.seed(m["np_seed"])
+    res = odyn.train(ora, x, y, m["n_elites"], **m["train_kw"])
+    assert res["epochs"] == m["epochs"]
+    assert rel_err([r[0] for r in res["log"]], g["train_loss"]) < TOL
+    assert rel_err([r[1] for r in res["log"]], g["holdout_loss"]) < TOL
+    assert rel_err([r[2] for r in res["log"]], g["member_holdout"]) < TOL
+    assert res["elites"] == g["elites"].tolist()
+    assert np.array_equal(res["mu"], g["scaler_mu"]) and np.array_equal(res["std"], g["scaler_std"])
+    for k, v in g.group("post").items():
+        assert rel_err(ora.p[k].detach().numpy(), v) < TOL, k
+
+
+def dynamics_train_data(g):
+    """The learnable synthetic transition set of make_golden.gen_dynamics_train."""
+    from offlinerlkit_b200.synthetic import make_dataset
+    m = g.meta
+    data = make_dataset(m["n_data"], m["O"], m["A"], seed=m["data_seed"])
+    xin = np.concatenate([data["observations"], data["actions"]], 1)
+    nobs = (data["observations"] + np.tanh(xin @ g["Wd"]) + 0.05 * data["next_observations"]).astype(np.float32)
+    rew = (np.sin(xin.sum(1, keepdims=True)) + 0.05 * data["rewards"].reshape(-1, 1)).astype(np.float32)
+    return xin, np.concatenate([nobs - data["observations"], rew], axis=-1)
+
+
+@pytest.mark.parametrize("name", ["rollout_cfg5_walker"])
+def test_rollout_config5_size(name):
+    """mopo.py:45-79 at BASELINE.json configs[4] size (50 000 starts x horizon 5): survivor counts exact, array
+    fingerprints; the draws are re-made from the fixture's seeds in the reference's consumption order."""
+    from oracle import nets
+    g = Golden(name)
+    m = g.meta
+    dyn_state, actor, mu, std, init = cfg5_setup(m)
+    ora = odyn.DynamicsOracle(dyn_state, m["weight_decays"])
+    E, D, A = m["E"], m["O"] + 1, m["A"]
+    elites = np.asarray(m["elites"])
+    fn = {"halfcheetah": odyn.term_halfcheetah, "walker2d": odyn.term_walker2d}[m["term"]]
+    torch.manual_seed(m["torch_seed"])
+    np.random.seed(m["np_seed"])
+    counts = []
+
+    def select_action(obs):
+        counts.append(len(obs))
+        with torch.no_grad():
+            a, _ = nets.actforward(actor, "actor", torch.from_numpy(obs), torch.randn(len(obs), A))
+        return a.numpy()
+
+    def step(obs, act):
+        n = len(obs)
+        noise = np.random.normal(size=(E, n, D))
+        return ora.step(obs, act, mu, std, fn, m["penalty_coef"], noise, np.random.choice(elites, size=n))
+
+    out, info = odyn.rollout(select_action, step, init, m["horizon"])
+    assert counts == g["counts"].tolist()
+    assert info["num_transitions"] == m["num_transitions"]
+    assert int(out["terminals"].sum()) == int(g["terminal_count"])
+    for k, v in out.items():
+        got, ref = array_stats(v.astype(np.float64) if v.dtype == bool else v), g["outstats|" + k]
+        assert rel_err(got, ref) < 1e-4, k
