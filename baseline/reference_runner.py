@@ -5,6 +5,8 @@ The reference is installed once, in the authoring container, into the git-ignore
     cp -r /root/reference /tmp/ref_copy          # the reference tree is read-only and pip builds in-tree
     python -m pip install --no-index --no-build-isolation --find-links /opt/wheelhouse --no-deps \
         --target baseline/_ref /tmp/ref_copy
+    cp -r --update=none /tmp/ref_copy/offlinerlkit baseline/_ref/     # setup.py's find_packages() skips policy/others (no
+                                                                      # __init__.py), which policy/__init__.py imports
 
 (``--no-deps``: gym / ray / d4rl are not in the image; the five import-time stubs under ``tests/golden/_stubs`` --
 gym, gymnasium, diffusers, wandb, matplotlib -- stand in for packages the hot path never calls)

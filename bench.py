@@ -3,7 +3,7 @@
 hidden 256x3 (BASELINE.json `metric`, `configs[1]`).
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA engine (this repo)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the unmodified reference (baseline/_ref) on the host CPU
 
 One "step" = ReplayBuffer.sample(256) + CQLPolicy.learn(batch) with everything the reference's learn does
 (actor, alpha, both critics with the conservative term, polyak, loss dict).  N > 1 runs N independent seeds, one
@@ -25,7 +25,10 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-NCU_TC_DRAM_BYTES_PER_LAUNCH = 27.7e6      # measured (mean of the six big launches, cold cache), see roofline.traffic_source
+import csv
+import glob
+import re
+
 METRIC = "CQL gradient steps/s (hc-shaped, bs256)"
 O_DIM, A_DIM, HIDDEN, BATCH, N_REPEAT, N_DATA = 17, 6, [256, 256, 256], 256, 10, 1_000_000
 HYPER = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, cql_weight=5.0, temperature=1.0, max_q_backup=False,
@@ -53,19 +56,45 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_tc_summary():
+    """(csv path, mean DRAM bytes per launch, mean tensor-pipe-active %) of the hidden-layer k_tc_gemm launches, parsed at
+    run time from the newest committed `profiles/ncu_tc_gemm_r*.csv` (one `ncu --set full` capture of this command)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_tc_gemm_r*.csv")),
+                   key=lambda f: int(re.search(r"_r(\d+)", os.path.basename(f)).group(1)))
+    if not files:
+        return None, None, None
+    path = files[-1]
+    rows = [r for r in csv.reader(ln for ln in open(path) if not ln.startswith("#"))]
+    head, units = rows[0], rows[1]
+    col = {n: i for i, n in enumerate(head)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, pipe = [], []
+    for r in rows[2:]:
+        if len(r) < len(head) or re.search(r"K=\d|head|wgrad0|fwd0", r[0]):
+            continue            # the narrow first layer (one k-slab) is not one of the six 2.08 GFLOP launches
+        rd = float(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]]
+        wr = float(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
+        tot.append(rd + wr)
+        pipe.append(float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]))
+    if not tot:
+        return path, None, None
+    return os.path.relpath(path, ROOT), float(np.mean(tot)), float(np.mean(pipe))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_ms: int = 10):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], period_ms
+        self.window = None          # (t0, t1) of the timed region, time.time() clock
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -74,7 +103,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -84,9 +113,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, inside = [], None, set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -95,11 +124,15 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
+            if self.window is not None and self.window[0] <= ts <= self.window[1]:
+                inside += 1
             for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        # the sampler runs from before the warm-up steps to after the timed loops: every sample is taken while this
+        # process keeps the GPU busy with the same step; `samples_in_timed_region` counts those inside the two timed loops
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "samples_in_timed_region": inside, "period_ms": self.period_ms, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ builders
@@ -203,21 +236,39 @@ def time_oracle(device: str, steps: int, warmup: int, budget_s: float, n_data: i
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+REF_BUILD = dict(obs_dim=O_DIM, act_dim=A_DIM, hidden=HIDDEN, hyper=HYPER, alpha_lr=ALPHA_LR)
+
+
+def time_reference(device: str, steps: int, warmup: int, budget_s: float, n_data: int):
+    """steps/s of the reference's CQL step on `device`: the UNMODIFIED reference from baseline/_ref (stock
+    ReplayBuffer.sample + CQLPolicy.learn, kind "reference") when it is installed, else the oracle port of the same
+    op stream (kind "port").  Returns (rate, steps done, seconds, kind)."""
+    from baseline import reference_runner as rr
+    ok, why = rr.available()
+    if ok:
+        rate, done, dt, _ = rr.time_cql(device, steps, warmup, budget_s, n_data, BATCH, **REF_BUILD)
+        return rate, done, dt, "reference"
+    print(f"[bench] reference not importable ({why}); timing the oracle port instead", file=sys.stderr, flush=True)
+    rate, done, dt = time_oracle(device, steps, warmup, budget_s, n_data)
+    return rate, done, dt, "port"
+
+
 def run_reference(args, rank: int):
-    """The reference's algorithm on the host CPU: the oracle port (the reference is Python and absent on the GPU box,
-    so `oracle/_ref` does not exist).  Rank 0 only."""
+    """The reference's own CQL step on the box's host cores, all threads: `baseline/_ref` (the unmodified reference,
+    installed by the recipe in baseline/reference_runner.py) through its public API; rank 0 only."""
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     threads = torch.get_num_threads()
-    rate, done, dt = time_oracle("cpu", args.steps, min(args.warmup, 5), budget_s=150.0, n_data=args.rows)
-    sample = (f"{done} consecutive gradient steps of the same workload (requested {args.steps}; capped at 150 s of "
-              f"CPU time), {min(args.warmup, 5)} warm-up steps")
+    w = min(args.warmup, 5)
+    rate, done, dt, kind = time_reference("cpu", args.steps, w, budget_s=150.0, n_data=args.rows)
+    sample = (f"{done} consecutive gradient steps (buffer.sample + policy.learn) of the same workload on the same "
+              f"{args.rows}-row buffer (requested {args.steps}; capped at 150 s of CPU time), {w} warm-up steps")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "steps/s", "n_gpus": args.gpus, "steps": done,
-            "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
+            "warmup": w, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": CONFIG,
-            "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -273,6 +324,8 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         import torch.distributed as dist
     policy, buf = build_engine(device, seed=parallel.seed_for_rank(0, rank), n_data=args.rows)
     K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                 # before the warm-up: short timed regions (--steps 20 = 6 ms) still get samples
 
     # ---- warm-up through the public API (uploads the table, builds and captures the step graph)
     for _ in range(W):
@@ -292,12 +345,11 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         return e
 
     e0, e1 = ev(), ev()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
 
     # ---- (1) device-resident: indices for all K steps already in HBM, no host sync inside the timed region
     idx_all = torch.from_numpy(np.random.randint(0, buf._size, size=(K, BATCH))).to(device)
     barrier()
+    t_win0 = time.time()
     L.call("orlk_event_record", e0, rt.cur)
     for t in range(K):
         buf.gather_device(idx_all[t])
@@ -319,6 +371,13 @@ def run_engine(args, rank: int, world: int, local_rank: int):
     e2e_wall = time.perf_counter() - t0
     L.call("orlk_event_elapsed_ms", e0, e1, C.byref(ms))
     e2e_ms = max(ms.value, 1e3 * e2e_wall)
+    sampler.window = (t_win0, time.time())
+    # keep the same step running until the sampler has seen >= 0.25 s of it (not timed; clocks only)
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 0.25:
+        for _ in range(50):
+            eng.enqueue("step")
+        torch.cuda.synchronize()
     clocks = sampler.stop()
 
     dev_ms, e2e_ms = parallel.reduce_scalars([dev_ms, e2e_ms], "max", device)      # the slowest rank bounds the job
@@ -345,18 +404,20 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         kname = (f"k_tc_gemm<{eng.tc_passes}> (tcgen05.mma kind::tf32, {eng.tc_passes} MMA pass(es) per product, TMEM "
                  "accumulators, TMA operand ring; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)") if on_tc \
             else "k_gemm_grouped<128,128,16,8,8> (fp32 FFMA; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)"
+        ncu_csv, ncu_traffic, ncu_pipe = ncu_tc_summary()
         roof = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} bf16 dense (sustained)",
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the six launches, from the committed
                 # ncu --set full capture of this command (profiles/ncu_tc_gemm_r01.csv); the forward / dgrad launches stay
                 # in L2 (< 6 MB of DRAM traffic each), the split-K weight-gradient launches move ~46 MB each
-                "traffic": NCU_TC_DRAM_BYTES_PER_LAUNCH if on_tc else None,
-                "traffic_source": "profiles/ncu_tc_gemm_r01.csv (ncu --set full, B200, same command; ncu flushes the caches before each pass, in the running step the operands are L2 hits)" if on_tc else None,
+                "traffic": ncu_traffic if on_tc else None,
+                "traffic_source": (f"{ncu_csv}, parsed at run time (ncu --set full, B200, same command; ncu flushes the "
+                                   "caches before each pass, in the running step the operands are L2 hits)") if on_tc else None,
                 "algorithmic_bytes_per_launch": 2 * Mc * 256 * 4 * 2 + 2 * 256 * 256 * 4,
                 # each product is three TF32 MMAs: what the tensor pipe really executes, against the TF32 (= bf16 / 2) peak
                 "tf32_mma_frac_of_tf32_peak": (3 if eng.tc_passes == 3 else 1) * achieved / (peak / 2),
-                "ncu_tensor_pipe_active_pct": 36.5 if on_tc else None,
+                "ncu_tensor_pipe_active_pct": ncu_pipe if on_tc else None,
                 "launches_per_step": len(big), "us_per_step": big_us, "share_of_step": big_us / step_us,
                 "step_frac": FLOP_PER_STEP * (value / world) / 1e12 / peak,
                 "fp32_simt_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
@@ -389,19 +450,24 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(max(1, os.cpu_count() or 1))
             threads = torch.get_num_threads()
-            rate, done, dt = time_oracle("cpu", 200, 3, budget_s=20.0, n_data=min(args.rows, 200_000))
-            line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
-                                    "host_cpus": os.cpu_count(),
-                                    "sample": f"{done} gradient steps of the same workload in {dt:.1f} s (oracle port, "
-                                              "200k-row buffer)"}
+            # the reference's own step (baseline/_ref, unmodified) on the host cores, same 1 M-row buffer: a bounded sample
+            rate, done, dt, kind = time_reference("cpu", 400, 3, budget_s=20.0, n_data=args.rows)
+            cb = {"value": rate, "unit": "steps/s", "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
+                  "sample": f"{done} gradient steps (buffer.sample + policy.learn) of the same workload on the same "
+                            f"{args.rows}-row buffer in {dt:.1f} s, 3 warm-up steps"}
             try:
-                grate, gdone, gdt = time_oracle(device, 300, 20, budget_s=15.0, n_data=min(args.rows, 200_000))
-                line["torch_eager_gpu_port"] = {"value": grate, "unit": "steps/s", "steps": gdone,
-                                                "note": "the oracle's op stream (= the reference's ATen calls) run with "
-                                                        "device=cuda on this B200; informational denominator for the "
-                                                        "north_star's 50x target"}
+                # the north_star's denominator: the same reference code with device="cuda" on this B200 (BASELINE.md
+                # section 3, row R-GPU): 200 warm-up steps, >= 1000 timed, synchronised on both sides
+                grate, gdone, gdt, gkind = time_reference(device, 1500, 200, budget_s=40.0, n_data=args.rows)
+                cb.update({"gpu_eager_steps_s": grate, "gpu_eager_kind": gkind, "gpu_eager_steps": gdone,
+                           "speedup_vs_gpu_eager_device": value / grate, "speedup_vs_gpu_eager_e2e": e2e / grate,
+                           "target_50x_met": bool(e2e / grate >= 50.0),
+                           "gpu_eager_note": "stock CQLPolicy.learn + ReplayBuffer.sample of the reference with "
+                                             "device='cuda' on the same B200; the north_star's 50x target is against "
+                                             "this rate"})
             except Exception as ex:      # never let the informational leg break the bench line
-                line["torch_eager_gpu_port"] = {"error": repr(ex)}
+                cb["gpu_eager_error"] = repr(ex)
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.barrier()

@@ -49,6 +49,29 @@ class Batch(dict):
         self._materialise()
         return dict.values(self)
 
+    # ``{**batch}`` / ``dict(batch)`` go through ``keys()`` + ``__getitem__`` for dict SUBCLASSES that override ``keys``
+    # (CPython only takes the raw-table fast path otherwise), ``copy`` / ``__iter__`` / ``__or__`` are overridden too:
+    # every way of reading the rows materialises them first.
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def copy(self):
+        self._materialise()
+        return dict(dict.items(self))
+
+    def __or__(self, other):
+        self._materialise()
+        return dict(dict.items(self)) | other
+
+    def __ror__(self, other):
+        self._materialise()
+        return other | dict(dict.items(self))
+
     @property
     def obs2(self) -> torch.Tensor:
         """[2B, O]: observations then next_observations (one GEMM operand for the actor)."""

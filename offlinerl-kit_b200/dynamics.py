@@ -53,11 +53,15 @@ class EnsembleDynamics(BaseDynamics):
         return torch.as_tensor(np.ascontiguousarray(a)).to(device=self.engine.dev, dtype=dtype)
 
     def _scaler_tensors(self):
-        key = (id(self.scaler.mu), id(self.scaler.std))
-        if self._scaler_dev is None or self._scaler_dev[0] != key:
-            self._scaler_dev = (key, self._dev(np.asarray(self.scaler.mu, np.float32).reshape(-1)),
-                                self._dev(np.asarray(self.scaler.std, np.float32).reshape(-1)))
-        return self._scaler_dev[1], self._scaler_dev[2]
+        """Device copies of the scaler's mu / std.  The cache holds the host arrays it was made from and compares their
+        CONTENT (36-element arrays): a re-fit, a load or an in-place edit of scaler.mu / std is always seen."""
+        mu, std = self.scaler.mu, self.scaler.std
+        c = self._scaler_dev
+        if c is None or not (np.array_equal(c[0], mu) and np.array_equal(c[1], std)):
+            self._scaler_dev = c = (np.array(mu, copy=True), np.array(std, copy=True),
+                                    self._dev(np.asarray(mu, np.float32).reshape(-1)),
+                                    self._dev(np.asarray(std, np.float32).reshape(-1)))
+        return c[2], c[3]
 
     # ------------------------------------------------------------------ imagination
     def step_device(self, obs: torch.Tensor, act: torch.Tensor, noise64=None, midx=None):

@@ -38,6 +38,9 @@ class EDACLearner(_BatchMixin, Learner):
         # critic maximised over them, no entropy term
         self.n_next = 10 if policy._max_q_backup else 1
         dist = actor.dist_net
+        if (getattr(dist, "_sigma_min", -5.0), getattr(dist, "_sigma_max", 2.0)) != (-5.0, 2.0):
+            # the sampler / backward kernels clamp log sigma to the reference's default [-5, 2] (dist_module.py:95-105)
+            raise L.OrlkError("the CUDA engine implements TanhDiagGaussian with sigma_min=-5, sigma_max=2 only")
         if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
             raise L.OrlkError("EDAC engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
         lin = lambda m: [x for x in m.model if hasattr(x, "num_ensemble")]
@@ -68,8 +71,12 @@ class EDACLearner(_BatchMixin, Learner):
             la.data = self.scalars[L.SC_LOG_ALPHA:L.SC_LOG_ALPHA + 1].view(la.shape)
         self.eta = float(policy._eta)
         self.push_groups()
+        self._rebatch(self.B)
+
+    def _rebatch(self, B: int) -> None:
+        rt, A = self.rt, self.A
+        self.B = B
         self._make_stage()
-        B, A = self.B, self.A
         self.noise = rt.zeros((1 + self.n_next) * B * A)
         self.noise_views = {"eps_actor": self.noise[:B * A].view(B, A),
                             "eps_next": self.noise[B * A:].view(self.n_next * B, A)}

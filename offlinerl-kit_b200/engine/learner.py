@@ -6,6 +6,7 @@ staging batch.  Sub-classes build a ``Plan`` (ordered launches) per step variant
 CUDA graph and returns the loss scalars after a single stream synchronisation -- the ``Dict[str, float]``
 contract of ``policy.learn`` (policy/base_policy.py:25-26).
 """
+import copy
 import ctypes as C
 import os
 import struct
@@ -65,7 +66,7 @@ class Learner:
         self.scalars = self.rt.zeros(L.SC_COUNT)
         self.philox_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.noise_enable = torch.ones(1, dtype=torch.int32, device=self.dev)
-        self._noise_enabled_host = True
+        self._noise_flag = [True]       # host mirror of noise_enable (a list: shared by the per-batch-size siblings)
         self.plans: Dict[str, Plan] = {}
         self.use_graph = True
         self.steps_done = 0
@@ -117,9 +118,25 @@ class Learner:
 
     # ------------------------------------------------------------------ noise
     def set_noise_enabled(self, on: bool) -> None:
-        if on != self._noise_enabled_host:
+        if on != self._noise_flag[0]:
             self.noise_enable.fill_(1 if on else 0)
-            self._noise_enabled_host = on
+            self._noise_flag[0] = on
+
+    # ------------------------------------------------------------------ other batch sizes
+    def _rebatch(self, B: int, **kw) -> None:
+        """Everything that depends on the batch size (staging, noise block, lazily the activations and the step graphs).
+        Called by ``__init__`` and by ``for_batch``."""
+        raise NotImplementedError
+
+    def for_batch(self, B: int, **kw) -> "Learner":
+        """A sibling engine for another batch size (the reference's ``learn`` takes any batch, policy/base_policy.py:25).
+        It SHARES the parameter arenas, Adam moments and step counters, the scalar block (alpha), the loss block and the
+        Philox counter with this engine and owns its own staging memory, activations and captured step graphs."""
+        sib = copy.copy(self)
+        sib.plans = {}
+        sib.__dict__.pop("_gather_plans", None)
+        sib._rebatch(int(B), **kw)
+        return sib
 
     @property
     def tc_passes(self) -> int:
@@ -134,6 +151,11 @@ class Learner:
         """Host-side writes to the parameters (load_state_dict, custom init) invalidate derived copies."""
         for ps in self.param_sets:
             ps.refresh_wt()
+
+    def invalidate(self) -> None:
+        """After writing parameters through ``p.data`` (which no version counter sees): re-derive every derived copy."""
+        for ps in self.param_sets:
+            ps.invalidate()
 
     # ------------------------------------------------------------------ plan execution
     def run(self, key: str) -> List[float]:

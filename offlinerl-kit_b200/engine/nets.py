@@ -44,6 +44,7 @@ class ParamSet:
         self.WT = None                    # transposed weight copies (K-major operand of the tensor-core dgrad)
         self.wt_layers: List[int] = []
         self._wt_version = -1
+        self._adopted: List[torch.Tensor] = []   # the facade parameters whose storage is this arena (see _host_version)
         self.group_ids: List[int] = []     # Adam group index per member (set by the learner)
 
     # ------------------------------------------------------------------ construction from facade modules
@@ -159,13 +160,25 @@ class ParamSet:
         self.Vo = self.rt.zeros(self.total)
         self.T = self.rt.zeros(self.total) if with_target else None
 
-    @staticmethod
-    def _adopt(store: torch.Tensor, off: int, p: torch.Tensor) -> None:
+    def _adopt(self, store: torch.Tensor, off: int, p: torch.Tensor) -> None:
         """Copy the parameter's current value into the arena and re-point its storage at the arena view."""
         view = store[off:off + p.numel()].view(p.shape)
         with torch.no_grad():
             view.copy_(p.detach().to(store.device, torch.float32))
         p.data = view
+        if store is self.P:
+            self._adopted.append(p)
+
+    def _host_version(self) -> int:
+        """Changes whenever torch code writes a parameter in place (load_state_dict's ``param.copy_``, ``nn.init``,
+        ``p.mul_``).  ``p.data = view`` gives every adopted parameter its OWN version counter, so the arena tensor's
+        counter alone does not see those writes; the engine's kernels write through raw pointers and keep the
+        derived copies in sync themselves.  Writes through ``p.data`` bump nothing: call ``invalidate()`` after those."""
+        return self.P._version + sum(p._version for p in self._adopted)
+
+    def invalidate(self) -> None:
+        """Force the next ``refresh_wt`` to re-derive the transposed weight copies from the parameters."""
+        self._wt_version = -1
 
     # ------------------------------------------------------------------ transposed weight copies
     def enable_wt(self, layers: Sequence[int]) -> None:
@@ -181,7 +194,7 @@ class ParamSet:
         self.refresh_wt()
 
     def refresh_wt(self) -> None:
-        if self.WT is None or self.P._version == self._wt_version:
+        if self.WT is None or self._host_version() == self._wt_version:
             return
         with torch.no_grad():
             for l in self.wt_layers:
@@ -191,7 +204,7 @@ class ParamSet:
                     o = lay.w_off + g * lay.w_gs
                     src = self.P[o:o + lay.w_numel].view(lay.out_dim, lay.in_dim)
                     self.WT[o:o + lay.w_numel].view(lay.in_dim, lay.out_dim).copy_(src.t())
-        self._wt_version = self.P._version
+        self._wt_version = self._host_version()
 
     def wt(self, l: int, g: int = 0) -> int:
         lay = self.layers[l]

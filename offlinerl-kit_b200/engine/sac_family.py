@@ -39,6 +39,9 @@ class TwinCriticLearner(Learner):
         check_plain_mlp(actor.backbone, "actor")
         check_plain_mlp(c1.backbone, "critic")
         dist = actor.dist_net
+        if (getattr(dist, "_sigma_min", -5.0), getattr(dist, "_sigma_max", 2.0)) != (-5.0, 2.0):
+            # the sampler / backward kernels clamp log sigma to the reference's default [-5, 2] (dist_module.py:95-105)
+            raise L.OrlkError("the CUDA engine implements TanhDiagGaussian with sigma_min=-5, sigma_max=2 only")
         if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
             raise L.OrlkError("SAC/CQL engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
         a_lin = linears_of(actor)
@@ -134,6 +137,9 @@ class TwinCriticLearner(Learner):
             if ptrs == self._bound_ptrs:
                 self._bound_token = tok
                 return
+        # a foreign batch is copied into the staging memory; a still-pending draw of the bound buffer must not gather
+        # over it at the head of the step graph
+        self._bound_token = None
         B = self.B
         with torch.no_grad():
             self.obs2[:B].copy_(torch.as_tensor(batch["observations"], device=self.dev, dtype=torch.float32))
@@ -287,19 +293,11 @@ class CQLLearner(TwinCriticLearner):
 
     def __init__(self, policy, batch_size: int, seed: int = 0, n_real: Optional[int] = None, cons_rows=None):
         super().__init__(policy, batch_size)
-        rt, B, O, A = self.rt, self.B, self.O, self.A
+        rt = self.rt
         self.seed = seed
         self.N = int(policy._num_repeat_actions)
-        self.n_real = B if n_real is None else int(n_real)
-        self.c0, self.c1 = (0, B) if cons_rows is None else (int(cons_rows[0]), int(cons_rows[1]))
-        if not (0 < self.n_real <= B and 0 <= self.c0 < self.c1 <= B):
-            raise L.OrlkError("COMBO row split out of range")
-        self.Bc = self.c1 - self.c0
-        self.R = self.Bc * self.N
-        self.Mc = B + 3 * self.R
         # max_q_backup (cql.py:109-120): N next actions per row, each target critic maximised over them
         self.max_q_backup = bool(policy._max_q_backup)
-        self.Rt = B * self.N if self.max_q_backup else B        # rows through the target critics
         self.with_lagrange = bool(policy._with_lagrange)
         self.g_cql = -1
         self.cql_mv = rt.zeros(2)
@@ -312,6 +310,19 @@ class CQLLearner(TwinCriticLearner):
         self.act_lo = float(policy.action_space.low[0])
         self.act_hi = float(policy.action_space.high[0])
         self.push_groups()
+        self._rebatch(self.B, n_real=n_real, cons_rows=cons_rows)
+
+    def _rebatch(self, B: int, n_real: Optional[int] = None, cons_rows=None) -> None:
+        rt, A = self.rt, self.A
+        self.B = B
+        self.n_real = B if n_real is None else int(n_real)
+        self.c0, self.c1 = (0, B) if cons_rows is None else (int(cons_rows[0]), int(cons_rows[1]))
+        if not (0 < self.n_real <= B and 0 <= self.c0 < self.c1 <= B):
+            raise L.OrlkError("COMBO row split out of range")
+        self.Bc = self.c1 - self.c0
+        self.R = self.Bc * self.N
+        self.Mc = B + 3 * self.R
+        self.Rt = B * self.N if self.max_q_backup else B        # rows through the target critics
         self._make_stage()
         # noise block: normals first (eps_actor, eps_next, eps_pi, eps_pi_next), then uniforms (rand_act)
         R = self.R
@@ -423,9 +434,13 @@ class SACLearner(TwinCriticLearner):
 
     def __init__(self, policy, batch_size: int, seed: int = 0):
         super().__init__(policy, batch_size)
-        rt, B, A = self.rt, self.B, self.A
         self.seed = seed
         self.push_groups()
+        self._rebatch(self.B)
+
+    def _rebatch(self, B: int) -> None:
+        rt, A = self.rt, self.A
+        self.B = B
         self._make_stage()
         self.n_normal = 2 * B * A
         self.noise = rt.zeros(self.n_normal)

@@ -42,6 +42,9 @@ class _BatchMixin:
             if ptrs == self._bound_ptrs:
                 self._bound_token = tok
                 return
+        # a foreign batch is copied into the staging memory; a still-pending draw of the bound buffer must not gather
+        # over it at the head of the step graph
+        self._bound_token = None
         B = self.B
         f32 = lambda x: torch.as_tensor(x, device=self.dev, dtype=torch.float32)
         with torch.no_grad():
@@ -85,8 +88,12 @@ class TD3BCLearner(_BatchMixin, Learner):
         self.actor_ps.group_ids = [self.g_actor]
         self.critic_ps.group_ids = [self.g_c1, self.g_c2]
         self.push_groups()
+        self._rebatch(self.B)
+
+    def _rebatch(self, B: int) -> None:
+        rt, A = self.rt, self.A
+        self.B = B
         self._make_stage()
-        B, A = self.B, self.A
         self.noise = rt.zeros(B * A)
         self.noise_views = {"eps_target": self.noise.view(B, A)}
         self._built = False
@@ -230,6 +237,10 @@ class IQLLearner(_BatchMixin, Learner):
         self.g_v = self.add_group(policy.critic_v_optim)
         self.actor_ps.group_ids, self.q_ps.group_ids, self.v_ps.group_ids = [self.g_actor], [self.g_q1, self.g_q2], [self.g_v]
         self.push_groups()
+        self._rebatch(self.B)
+
+    def _rebatch(self, B: int) -> None:
+        self.B = B
         self._make_stage()
         self.noise_views = {}
         self._built = False

@@ -17,3 +17,27 @@ class BasePolicy(nn.Module):
 
     def learn(self, batch: Dict) -> Dict[str, float]:
         raise NotImplementedError
+
+
+def engine_for(policy, key, make, **kw):
+    """The policy's CUDA engine for the batch ``key`` (a batch size, or COMBO's (real, fake) split).  The first call
+    builds the engine (``make()``); a different key gets a sibling that shares parameters, Adam state and scalars and
+    owns its own staging / step graphs (engine/learner.py:Learner.for_batch) -- the reference's ``learn`` accepts any
+    batch size per call (policy/base_policy.py:25-26).  ``policy._engine`` is always the one used last."""
+    engines = policy.__dict__.setdefault("_engines", {})
+    cur = policy._engine
+    if cur is None:
+        cur = policy._engine = engines[key] = make()
+        return cur
+    if engines.get(key) is cur:
+        return cur
+    if not engines:                 # an engine installed by hand (tests): treat it as the one for this key
+        engines[key] = cur
+        return cur
+    eng = engines.get(key)
+    if eng is None:
+        B = key if isinstance(key, int) else sum(key)
+        eng = engines[key] = cur.for_batch(B, **kw)
+    eng.invalidate()                # the other sibling's updates may have by-passed this one's derived weight copies
+    policy._engine = eng
+    return eng

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .base_policy import engine_for
 from .cql import CQLPolicy
 
 
@@ -47,20 +48,23 @@ class COMBOPolicy(CQLPolicy):
             self._roll = RolloutEngine(self, uniform=uniform)
         return self._roll.run(np.asarray(init_obss, np.float32), int(rollout_length), noise, device_out)
 
+    def _rows(self):
+        n_real, n_fake = self._split
+        return dict(n_real=n_real, cons_rows=(n_real, n_real + n_fake) if self._rho_s == "model" else None)
+
     def _make_engine(self, batch_size: int):
         from ..engine.sac_family import CQLLearner
-        n_real, n_fake = self._split
-        cons = (n_real, n_real + n_fake) if self._rho_s == "model" else None
-        return CQLLearner(self, batch_size, n_real=n_real, cons_rows=cons)
+        return CQLLearner(self, batch_size, **self._rows())
+
+    def engine(self, batch_size: int):
+        # keyed by the (real, fake) split: another split is another step graph over the same parameters
+        return engine_for(self, tuple(self._split), lambda: self._make_engine(batch_size), **self._rows())
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
         real, fake = batch["real"], batch["fake"]
         size = lambda b: getattr(b, "batch_size", None) or int(b["observations"].shape[0])   # no gather forced
         split = (size(real), size(fake))
-        if self._split is None:
-            if split[0] == 0 or (self._rho_s == "model" and split[1] == 0):
-                raise ValueError("COMBO needs real rows (and model rows with rho_s='model') in every batch")
-            self._split = split
-        elif split != self._split:
-            raise RuntimeError(f"the step graph was built for a {self._split} real/fake split, got {split}")
+        if split[0] == 0 or (self._rho_s == "model" and split[1] == 0):
+            raise ValueError("COMBO needs real rows (and model rows with rho_s='model') in every batch")
+        self._split = split
         return self._learn_mixed(real, fake, noise)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy
+from .base_policy import BasePolicy, engine_for
 
 
 class EDACPolicy(BasePolicy):
@@ -49,12 +49,8 @@ class EDACPolicy(BasePolicy):
         return action.cpu().numpy()
 
     def engine(self, batch_size: int):
-        if self._engine is None:
-            from ..engine.edac import EDACLearner
-            self._engine = EDACLearner(self, batch_size)
-        elif self._engine.B != batch_size:
-            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
-        return self._engine
+        from ..engine.edac import EDACLearner
+        return engine_for(self, int(batch_size), lambda: EDACLearner(self, batch_size))
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         out = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy
+from .base_policy import BasePolicy, engine_for
 
 
 class IQLPolicy(BasePolicy):
@@ -44,12 +44,8 @@ class IQLPolicy(BasePolicy):
         return np.clip(action, self.action_space.low[0], self.action_space.high[0])
 
     def engine(self, batch_size: int):
-        if self._engine is None:
-            from ..engine.td3_iql import IQLLearner
-            self._engine = IQLLearner(self, batch_size)
-        elif self._engine.B != batch_size:
-            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
-        return self._engine
+        from ..engine.td3_iql import IQLLearner
+        return engine_for(self, int(batch_size), lambda: IQLLearner(self, batch_size))
 
     def learn(self, batch: Dict, noise=None) -> Dict[str, float]:
         return self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy
+from .base_policy import BasePolicy, engine_for
 
 
 class SACPolicy(BasePolicy):
@@ -61,11 +61,7 @@ class SACPolicy(BasePolicy):
         return SACLearner(self, batch_size)
 
     def engine(self, batch_size: int):
-        if self._engine is None:
-            self._engine = self._make_engine(batch_size)
-        elif self._engine.B != batch_size:
-            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
-        return self._engine
+        return engine_for(self, int(batch_size), lambda: self._make_engine(batch_size))
 
     def _after_step(self, out: Dict[str, float]) -> None:
         if self._is_auto_alpha and "alpha" in out:

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy
+from .base_policy import BasePolicy, engine_for
 from ..utils.noise import GaussianNoise
 
 
@@ -48,12 +48,8 @@ class TD3BCPolicy(BasePolicy):
         return action
 
     def engine(self, batch_size: int):
-        if self._engine is None:
-            from ..engine.td3_iql import TD3BCLearner
-            self._engine = TD3BCLearner(self, batch_size)
-        elif self._engine.B != batch_size:
-            raise RuntimeError(f"the step graph was built for batch size {self._engine.B}, got {batch_size}")
-        return self._engine
+        from ..engine.td3_iql import TD3BCLearner
+        return engine_for(self, int(batch_size), lambda: TD3BCLearner(self, batch_size))
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         return self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

@@ -20,6 +20,28 @@ def make_log_dirs(task_name: str, algo_name: str, seed: int, args: Dict, record_
     return path
 
 
+class _CsvStream:
+    """One ``<name>.csv`` progress stream (reference: utils/logger.py:144-198 CSVOutputHandler): the header grows when
+    new keys appear (the file is re-emitted with the wider header), missing values stay empty."""
+
+    def __init__(self, path: str, name: str) -> None:
+        self.path, self.handler_name, self.keys, self.rows = path, name, [], []
+
+    def writekvs(self, kvs: Dict) -> None:
+        extra = sorted(k for k in kvs if k not in self.keys)
+        self.rows.append(dict(kvs))
+        if extra or not os.path.exists(self.path):
+            self.keys.extend(extra)
+            with open(self.path, "w", newline="") as f:
+                w = csv.writer(f)
+                w.writerow(self.keys)
+                for r in self.rows:
+                    w.writerow([r.get(k, "") for k in self.keys])
+        else:
+            with open(self.path, "a", newline="") as f:
+                csv.writer(f).writerow([kvs.get(k, "") for k in self.keys])
+
+
 class Logger:
     def __init__(self, dir: str, ouput_config: Optional[Dict] = None) -> None:
         self._dir = dir
@@ -28,8 +50,12 @@ class Logger:
         self._timestep = 0
         for sub in ("record", "checkpoint", "model", "result"):
             os.makedirs(os.path.join(dir, sub), exist_ok=True)
-        self._csv_path = os.path.join(self.record_dir, "progress.csv")
-        self._csv_keys = None
+        # ``ouput_config`` = {file name: "csv" | "tensorboard"} as in the run scripts (run_mopo.py:224-229: the streams
+        # "dynamics_training_progress" and "policy_training_progress" are told apart by dumpkvs(exclude=...));
+        # TensorBoard streams are not reproduced.
+        cfg = ouput_config if ouput_config is not None else {"progress": "csv"}
+        self._streams = [_CsvStream(os.path.join(self.record_dir, f"{name}.csv"), name)
+                         for name, fmt in cfg.items() if fmt == "csv"]
         self.quiet = False
 
     record_dir = property(lambda self: os.path.join(self._dir, "record"))
@@ -54,15 +80,14 @@ class Logger:
         self._timestep = timestep
 
     def dumpkvs(self, exclude=None) -> None:
-        row = {"timestep": self._timestep, **self._name2val}
+        """utils/logger.py:300-309: every stream not named in ``exclude`` gets the row."""
+        row = {**self._name2val, "timestep": self._timestep}
         if not self.quiet:
             print(" | ".join(f"{k}={v:.5g}" if isinstance(v, float) else f"{k}={v}" for k, v in row.items()), flush=True)
-        if self._csv_keys is None:
-            self._csv_keys = list(row)
-            with open(self._csv_path, "w", newline="") as f:
-                csv.writer(f).writerow(self._csv_keys)
-        with open(self._csv_path, "a", newline="") as f:
-            csv.writer(f).writerow([row.get(k, "") for k in self._csv_keys])
+        for st in self._streams:
+            if exclude is not None and st.handler_name in exclude:
+                continue
+            st.writekvs(row)
         self._name2val.clear()
         self._name2cnt.clear()
 
