@@ -48,14 +48,14 @@ class _Learner:
     def _adam(self, prefix: str, lr: float) -> torch.optim.Adam:
         names = _prefixed(self.p, prefix)
         opt = torch.optim.Adam([self.p[n] for n in names], lr=lr)
-        opt._orlk_names = names
+        opt.param_groups[0]["orlk_names"] = names      # (inside a param group: survives copy.deepcopy of the optimiser)
         return opt
 
     def _apply(self, opt: torch.optim.Adam, loss: torch.Tensor, retain_graph: bool = False) -> None:
         """zero_grad / backward / step, recording the gradients that Adam consumed."""
         opt.zero_grad()
         loss.backward(retain_graph=retain_graph)
-        for n in opt._orlk_names:
+        for n in opt.param_groups[0]["orlk_names"]:
             g = self.p[n].grad
             if g is not None:
                 self.grads[n] = g.detach().clone()

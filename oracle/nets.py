@@ -16,6 +16,21 @@ LOG_SIG_MIN, LOG_SIG_MAX = -5.0, 2.0      # modules/dist_module.py:53-54
 HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
 
 
+# Every ReLU of the oracle goes through ``relu`` so that the GPU parity tests can swap in an implementation that records
+# pre-activations within rounding of zero and forces chosen mask bits (tests/kinks.py): a ReLU network's gradient is
+# only defined up to those kink decisions, and one flipped bit moves a 7936-row critic gradient by ~5e-4 (rel. L2).
+_RELU_IMPL = torch.relu
+
+
+def set_relu_impl(fn=None) -> None:
+    global _RELU_IMPL
+    _RELU_IMPL = torch.relu if fn is None else fn
+
+
+def relu(x: torch.Tensor) -> torch.Tensor:
+    return _RELU_IMPL(x)
+
+
 def count_hidden(p: P, prefix: str) -> int:
     """Number of Linear layers in ``<prefix>.model`` (nets/mlp.py:21-24: Linear at even slots)."""
     n = 0
@@ -27,7 +42,7 @@ def count_hidden(p: P, prefix: str) -> int:
 def mlp_relu(p: P, prefix: str, x: torch.Tensor) -> torch.Tensor:
     """nets/mlp.py:9-33 with ReLU activations, no dropout, no output layer."""
     for i in range(count_hidden(p, prefix)):
-        x = torch.relu(F.linear(x, p[f"{prefix}.model.{2 * i}.weight"], p[f"{prefix}.model.{2 * i}.bias"]))
+        x = relu(F.linear(x, p[f"{prefix}.model.{2 * i}.weight"], p[f"{prefix}.model.{2 * i}.bias"]))
     return x
 
 
@@ -106,7 +121,7 @@ def ensemble_critic(p: P, name: str, obs: torch.Tensor, act: torch.Tensor) -> to
     for i in range(n):
         x = ensemble_linear(p[f"{name}.model.{2 * i}.weight"], p[f"{name}.model.{2 * i}.bias"], x)
         if i < n - 1:
-            x = torch.relu(x)
+            x = relu(x)
     return x
 
 
