@@ -146,10 +146,11 @@ int orlk_gemm_tiny(const OrlkGemmDesc* descs_host, int n_descs, int total_tiles,
 
 /* Fused small-row layer chain: ONE launch runs n_stages dependent GEMM stages (stage s+1 multiplies what stage s
  * wrote: A of s+1 == C of s) for n_chains independent chains with the same M (twin critics).  A thread-block cluster of
- * 8 CTAs owns a 32-row strip for the whole chain (one 32 x 32 column tile per CTA and stage, cluster barrier between
- * stages), arithmetic as orlk_gemm_tiny's tensor-core variant (passes 1 or 3; passes_stage0 for the first stage, which
- * may see raw observations).  descs_host[chain * n_stages + stage] is a
- * HOST array of at most 16 descriptors: a_layout 0, K <= 256, N <= 256, no split-K / sums / transposed copy.
+ * 8 CTAs owns a 16-row strip for the whole chain (one 16 x 32 column tile per CTA and stage); between stages: one
+ * hardware cluster barrier, then every CTA re-reads the finished 16 KB strip from L2 (cp.async.cg).  Arithmetic as
+ * orlk_gemm_tiny's tensor-core variant (passes 1 or 3; passes_stage0 for the first stage, which may see raw
+ * observations).  descs_host[chain * n_stages + stage] is a HOST array of at most 24 descriptors: a_layout 0, K <= 256,
+ * N <= 256, no split-K / sums / transposed copy.
  * Replaces the per-layer launches of an MLP forward (nets/mlp.py:22,28) or its autograd input-gradient pass. */
 int orlk_gemm_chain_init(void); /* once per process, outside stream capture */
 int orlk_gemm_chain(const OrlkGemmDesc* descs_host, int n_chains, int n_stages, int passes, int passes_stage0, void* stream);

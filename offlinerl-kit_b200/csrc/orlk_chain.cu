@@ -1,36 +1,40 @@
 // Fused small-row MLP chain: a whole forward (or backward) pass of a few-hundred-row batch through a stack of
 // <= 256-wide layers in ONE launch.
 //
-// Standalone, each of those layers is a ~3 us kernel body behind ~3 us of launch / prologue / drain, and a CQL step has
-// ~25 of them back to back.  Here a thread-block CLUSTER of 4 CTAs owns one 32-row strip of the batch for the whole
-// chain: CTA r computes the 32 x 64 output tile of columns [64r, 64r+64) of every stage, stores it to global memory
-// (the activations / gradients are needed by the weight-gradient launches anyway) and PUSHES it over distributed shared
-// memory into the next stage's A strip of all four CTAs, so the next stage starts from shared memory after one cluster
-// barrier - no trip through L2.  The next stage's weight tile is prefetched (cp.async) while the current stage is
-// reduced and pushed.  Different strips and different networks (twin critics) never synchronise with each other.
+// Standalone, each of those layers is a ~3 us kernel body behind ~2.5 us of launch / prologue / drain, and a CQL step
+// has ~25 of them back to back.  Here a thread-block CLUSTER of 8 CTAs owns one 16-row strip of the batch for the whole
+// chain: CTA r computes the 16 x 32 output tile of columns [32r, 32r+32) of every stage and stores it to global memory
+// (the activations / gradients are needed by the weight-gradient launches anyway); after ONE hardware cluster barrier
+// (barrier.cluster release / acquire, ~0.2 us) every CTA of the strip fetches the finished 16-row strip back from L2
+// with 16-byte cp.async copies as the next stage's A operand.  A strip is 16 KB: re-reading it from L2 (~250 cycles of
+// latency, ~64 B/cycle/SM) costs less than pushing it to the seven peers over distributed shared memory (~20 B/cycle/SM
+// on this part; the first version of this kernel did that and lost 2.5 us per stage to it).  The weight tile of stage
+// s+1 is prefetched into the second half of a double buffer while stage s is being multiplied.  Different strips and
+// different networks (twin critics) never synchronise with each other; 256 rows = 16 strips = 128 CTAs per network.
 // Arithmetic: warp-level TF32 MMAs (mma.sync m16n8k8) on fragments read straight from the staged tiles, 3xTF32 hi/lo
-// split for fp32-grade results (passes == 3) or single pass; 8 k-groups of two warps (one per 32-column half of the
-// tile), fixed-order sum of the 8 partial tiles.  Stage descriptors are OrlkGemmDesc (same epilogues as
-// orlk_gemm_grouped), A always row-major [m][k]; they travel in the kernel parameters.  Replaces the per-layer launches
-// of nets/mlp.py:22,28 forward and autograd dgrad for small batches.
+// split for fp32-grade results (passes == 3) or single pass; 16 warps = 4 column tiles x 4 k groups, fixed-order sum of
+// the 4 partial tiles.  Stage descriptors are OrlkGemmDesc (same epilogues as orlk_gemm_grouped), A always row-major
+// [m][k]; they travel in the kernel parameters.  Replaces the per-layer launches of nets/mlp.py:22,28 forward and
+// autograd dgrad for small batches.
 #include <stdlib.h>
 #include "orlk_common.cuh"
 using namespace orlk;
 
 namespace {
 
-constexpr int TM = 32, TN = 64;   // output tile of one CTA
-constexpr int CL = 4;             // CTAs per cluster = column tiles per stage (N <= 256)
+constexpr int TM = 16, TN = 32;   // output tile of one CTA
+constexpr int CL = 8;             // CTAs per cluster = column tiles per stage (N <= 256)
 constexpr int KC = 256;           // max k of a stage
 constexpr int KP = KC + 4;        // pitch of a k-contiguous tile row (floats): 260 % 32 == 4 -> conflict-free fragment loads
-constexpr int PN = TN + 8;        // pitch of an n-contiguous B tile row: 72 floats (72 % 32 == 8 -> conflict-free)
+constexpr int PN = TN + 8;        // pitch of an n-contiguous B tile row: 40 floats (40 % 32 == 8 -> conflict-free)
 constexpr int NTHR = 512;
-constexpr int KG = 8;             // k groups of two warps
+constexpr int KG = 4;             // k groups (of four warps: one per 8-column tile)
 constexpr int PR = TN + 1;        // pitch of a partial tile row
-constexpr int MAX_DESC = 16;      // chains x stages per launch (kernel-parameter space)
+constexpr int MAX_DESC = 24;      // chains x stages per launch (kernel-parameter space)
 constexpr int A_FLOATS = TM * KP;
 constexpr int B_FLOATS = (TN * KP > KC * PN) ? TN * KP : KC * PN;
 constexpr int R_FLOATS = KG * TM * PR;
+static_assert(TM * TN == NTHR, "the epilogue gives every thread one element of the tile");
 
 struct ChainArgs {
     OrlkGemmDesc d[MAX_DESC];     // [chain][stage]
@@ -47,27 +51,24 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, int src
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// store into the same shared-memory location of CTA `rank` of this cluster
-__device__ __forceinline__ void dsmem_store(float* local, int rank, float v) {
-    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-__device__ __forceinline__ uint32_t tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(tf32_hi(x))); }
+// unbiased 3xTF32 split (see orlk_tc.cu:lo_tf32): hi = round-to-nearest-tf32(x), lo = rna(x - hi)
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t tf32_lo(float x) { return tf32_hi(x - __uint_as_float(tf32_hi(x))); }
 
 // Rows [t0, t0+ROWS) x k [0, 8 ceil(K/8)) of a k-contiguous operand (base[t*ld + k]) into S[t][KP], by all threads.
-// Outside the matrix (t >= T or k >= K): zeros.
+// Outside the matrix (t >= T or k >= K): zeros.  The global reads bypass L1 (cp.async.cg / ld.global.cg): the A strip of a
+// stage was written by the other CTAs of the cluster a barrier ago.
 template <int ROWS>
 __device__ __forceinline__ void stage_kc(float* S, const float* __restrict__ base, int64_t ld, int t0, int T, int K, int tid) {
     const int nb = 2 * ((K + 7) >> 3);                  // 16-byte chunks per row
@@ -82,7 +83,7 @@ __device__ __forceinline__ void stage_kc(float* S, const float* __restrict__ bas
         for (int q = tid; q < ROWS * nb * 4; q += NTHR) {
             const int r = q / (nb * 4), k = q - r * (nb * 4);
             const int t = t0 + r;
-            S[r * KP + k] = (t < T && k < K) ? __ldg(base + (int64_t)t * ld + k) : 0.f;
+            S[r * KP + k] = (t < T && k < K) ? __ldcg(base + (int64_t)t * ld + k) : 0.f;
         }
     }
 }
@@ -100,7 +101,7 @@ __device__ __forceinline__ void stage_nc(float* S, const float* __restrict__ bas
         for (int q = tid; q < nk * TN; q += NTHR) {
             const int k = q / TN, c = q - k * TN;
             const int n = n0 + c;
-            S[k * PN + c] = (k < K && n < N) ? __ldg(base + (int64_t)k * ld + n) : 0.f;
+            S[k * PN + c] = (k < K && n < N) ? __ldcg(base + (int64_t)k * ld + n) : 0.f;
         }
     }
 }
@@ -111,29 +112,30 @@ __device__ __forceinline__ void stage_b(float* Bs, const OrlkGemmDesc& d, int n0
     else stage_nc(Bs, d.B, d.ldb, n0, d.N, d.K, tid);
 }
 
-__global__ void __launch_bounds__(NTHR, 1)
+__global__ void __launch_bounds__(NTHR, 2)
 k_chain_gemm(const __grid_constant__ ChainArgs P) {
     extern __shared__ float4 smem_f4[];
-    float* A0 = reinterpret_cast<float*>(smem_f4);      // A strip of even stages  [TM][KP]
-    float* A1 = A0 + A_FLOATS;                          // A strip of odd stages (filled by the cluster's pushes)
-    float* Bs = A1 + A_FLOATS;                          // b_layout 1: [TN][KP]   b_layout 0: [KC][PN]
-    float* red = Bs + B_FLOATS;                         // [KG][TM][PR] partial tiles
+    float* As = reinterpret_cast<float*>(smem_f4);      // A strip of the current stage  [TM][KP]
+    float* B0 = As + A_FLOATS;                          // weight tiles of even / odd stages: b_layout 1: [TN][KP], 0: [KC][PN]
+    float* B1 = B0 + B_FLOATS;
+    float* red = B1 + B_FLOATS;                         // [KG][TM][PR] partial tiles
 
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
-    const int kg = wi >> 1, wsub = wi & 1;              // k group, 32-column half of the tile
+    const int nt = wi & 3, kg = wi >> 2;                // 8-column tile, k group
     const int gid = lane >> 2, tig = lane & 3;
-    const int rank = blockIdx.x % CL;                   // cluster dims (4,1,1): rank == %cluster_ctarank
+    const int rank = blockIdx.x % CL;                   // cluster dims (8,1,1): rank == %cluster_ctarank
     const int strip = blockIdx.x / CL;
     const int chain = strip / P.tiles_m, tm = strip - chain * P.tiles_m;
     const int m0 = tm * TM, n0 = rank * TN;
     const OrlkGemmDesc* D = P.d + chain * P.n_stages;
+    const int er = tid >> 5, ec = tid & 31;             // my element of the tile in the epilogue
     CHAIN_STAMP(0);
-    orlk::pdl_enter();
+    orlk::pdl_wait();                                   // nothing above touched global data
     CHAIN_STAMP(1);
 
-    // stage 0 operands from global memory: the whole input strip (every CTA of the cluster) and my weight tile
-    stage_kc<TM>(A0, D[0].A, D[0].lda, m0, D[0].M, D[0].K, tid);
-    stage_b(Bs, D[0], n0, tid);
+    // stage 0 operands from global memory: the input strip (every CTA of the cluster) and my weight tile
+    stage_kc<TM>(As, D[0].A, D[0].lda, m0, D[0].M, D[0].K, tid);
+    stage_b(B0, D[0], n0, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     for (int s = 0; s < P.n_stages; ++s) {
@@ -141,124 +143,95 @@ k_chain_gemm(const __grid_constant__ ChainArgs P) {
         const int M = d.M, N = d.N, K = d.K;
         const bool active = n0 < N;
         const bool last = s + 1 == P.n_stages;
-        float* As = (s & 1) ? A1 : A0;
-        float* An = (s & 1) ? A0 : A1;                  // the next stage's strip
-        // my four output elements: bias / mask operands prefetched off the critical path
-        float e_bias[4], e_aux[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int e = tid + j * NTHR, er = e >> 6, ec = e & 63;
-            const int em = m0 + er, en = n0 + ec;
-            const bool ok = active && em < M && en < N;
-            e_bias[j] = (ok && d.bias != nullptr) ? __ldg(d.bias + en) : 0.f;
-            e_aux[j] = (ok && d.aux != nullptr) ? __ldg(d.aux + (int64_t)em * d.ldaux + en) : 0.f;
+        float* Bs = (s & 1) ? B1 : B0;
+        if (!last) {                                    // next stage's weight tile streams in under this stage's MMAs
+            stage_b((s & 1) ? B0 : B1, D[s + 1], n0, tid);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                // weight tile (and, for stage 0, the input strip) landed
+        asm volatile("cp.async.commit_group;" ::: "memory");        // (an empty group when there is nothing to prefetch)
+        // my output element: bias / mask operands prefetched off the critical path
+        const int em = m0 + er, en = n0 + ec;
+        const bool e_ok = active && em < M && en < N;
+        const float e_bias = (e_ok && d.bias != nullptr) ? __ldg(d.bias + en) : 0.f;
+        const float e_aux = (e_ok && d.aux != nullptr) ? __ldcg(d.aux + (int64_t)em * d.ldaux + en) : 0.f;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");        // everything but the prefetch just issued
+        __syncthreads();                                // A strip and this stage's weight tile landed
         if (s < 3) CHAIN_STAMP(2 + 4 * s);
         if (active) {
-            // ---- MMAs: k group kg owns 1/8 of the k steps, its two warps the two 32-column halves of the tile
-            float cacc[2][4][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) cacc[mt][nt][0] = cacc[mt][nt][1] = cacc[mt][nt][2] = cacc[mt][nt][3] = 0.f;
-            const int nstep = (K + 7) >> 3, per8 = (nstep + KG - 1) / KG;
-            const int s_lo = min(nstep, kg * per8), s_hi = min(nstep, s_lo + per8);
+            // ---- MMAs: k group kg owns 1/4 of the k steps, its four warps the four 8-column tiles
+            float cacc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nstep = (K + 7) >> 3, per = (nstep + KG - 1) / KG;
+            const int s_lo = min(nstep, kg * per), s_hi = min(nstep, s_lo + per);
             const bool b_kc = d.b_layout == 1;
             const bool split3 = (s == 0 ? P.passes0 : P.passes) == 3;
+            const int c = nt * 8 + gid;
+#pragma unroll 2
             for (int st = s_lo; st < s_hi; ++st) {
                 const int k = 8 * st;
-                uint32_t ah[2][4], al[2][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r = mt * 16 + gid;
-                    const float a0 = As[r * KP + k + tig], a1 = As[(r + 8) * KP + k + tig];
-                    const float a2 = As[r * KP + k + tig + 4], a3 = As[(r + 8) * KP + k + tig + 4];
-                    ah[mt][0] = tf32_hi(a0); ah[mt][1] = tf32_hi(a1); ah[mt][2] = tf32_hi(a2); ah[mt][3] = tf32_hi(a3);
-                    al[mt][0] = tf32_lo(a0); al[mt][1] = tf32_lo(a1); al[mt][2] = tf32_lo(a2); al[mt][3] = tf32_lo(a3);
+                const float a0 = As[gid * KP + k + tig], a1 = As[(gid + 8) * KP + k + tig];
+                const float a2 = As[gid * KP + k + tig + 4], a3 = As[(gid + 8) * KP + k + tig + 4];
+                float b0, b1;
+                if (b_kc) {
+                    b0 = Bs[c * KP + k + tig];
+                    b1 = Bs[c * KP + k + tig + 4];
+                } else {
+                    b0 = Bs[(k + tig) * PN + c];
+                    b1 = Bs[(k + tig + 4) * PN + c];
                 }
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int c = wsub * 32 + nt * 8 + gid;
-                    float b0, b1;
-                    if (b_kc) {
-                        b0 = Bs[c * KP + k + tig];
-                        b1 = Bs[c * KP + k + tig + 4];
-                    } else {
-                        b0 = Bs[(k + tig) * PN + c];
-                        b1 = Bs[(k + tig + 4) * PN + c];
-                    }
-                    const uint32_t bh0 = tf32_hi(b0), bh1 = tf32_hi(b1);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_tf32(cacc[mt][nt], ah[mt], bh0, bh1);
-                        if (split3) {
-                            mma_tf32(cacc[mt][nt], al[mt], bh0, bh1);
-                            mma_tf32(cacc[mt][nt], ah[mt], tf32_lo(b0), tf32_lo(b1));
-                        }
-                    }
+                const uint32_t ah[4] = {tf32_hi(a0), tf32_hi(a1), tf32_hi(a2), tf32_hi(a3)};
+                const uint32_t bh0 = tf32_hi(b0), bh1 = tf32_hi(b1);
+                mma_tf32(cacc, ah, bh0, bh1);
+                if (split3) {
+                    const uint32_t al[4] = {tf32_lo(a0), tf32_lo(a1), tf32_lo(a2), tf32_lo(a3)};
+                    mma_tf32(cacc, al, bh0, bh1);
+                    mma_tf32(cacc, ah, tf32_lo(b0), tf32_lo(b1));
                 }
             }
-            // partial tiles -> shared memory
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    float* r0 = red + (kg * TM + mt * 16 + gid) * PR + wsub * 32 + nt * 8 + 2 * tig;
-                    r0[0] = cacc[mt][nt][0];
-                    r0[1] = cacc[mt][nt][1];
-                    r0[8 * PR] = cacc[mt][nt][2];
-                    r0[8 * PR + 1] = cacc[mt][nt][3];
-                }
+            // partial tile -> shared memory
+            float* r0 = red + (kg * TM + gid) * PR + nt * 8 + 2 * tig;
+            r0[0] = cacc[0];
+            r0[1] = cacc[1];
+            r0[8 * PR] = cacc[2];
+            r0[8 * PR + 1] = cacc[3];
         }
-        __syncthreads();                                // partials complete; everybody is done with Bs
+        if (last) orlk::pdl_trigger();                  // the next kernel's CTAs may take their SMs from here on
+        __syncthreads();                                // partials complete; everybody is done with As and Bs
         if (s < 3) CHAIN_STAMP(3 + 4 * s);
-        if (!last) {                                    // next stage's weight tile streams in behind the reduction
-            stage_b(Bs, D[s + 1], n0, tid);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
         if (active) {
             const int epi = d.epi;
-            const int kn = last ? 0 : 8 * ((N + 7) >> 3);     // k extent the next stage will read (zero padded)
+            float v = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = tid + j * NTHR, er = e >> 6, ec = e & 63;
-                const int em = m0 + er, en = n0 + ec;
-                float v = 0.f;
-#pragma unroll
-                for (int g = 0; g < KG; ++g) v += red[(g * TM + er) * PR + ec];      // fixed order: bit-reproducible
-                if (en < N) {
-                    v += e_bias[j];
-                    if (epi == ORLK_EPI_SWISH && d.C2 != nullptr && em < M) d.C2[(int64_t)em * d.ldc + en] = v;
-                    switch (epi) {
-                        case ORLK_EPI_RELU: v = fmaxf(v, 0.f); break;
-                        case ORLK_EPI_RELU_MASK: v = e_aux[j] > 0.f ? v : 0.f; break;
-                        case ORLK_EPI_SWISH: v = v / (1.f + expf(-v)); break;
-                        case ORLK_EPI_DSWISH: {
-                            const float sg = 1.f / (1.f + expf(-e_aux[j]));
-                            v = v * (sg * (1.f + e_aux[j] * (1.f - sg)));
-                            break;
-                        }
-                        default: break;
+            for (int g = 0; g < KG; ++g) v += red[(g * TM + er) * PR + ec];      // fixed order: bit-reproducible
+            if (em < M && en < N) {
+                v += e_bias;
+                if (epi == ORLK_EPI_SWISH && d.C2 != nullptr) d.C2[(int64_t)em * d.ldc + en] = v;
+                switch (epi) {
+                    case ORLK_EPI_RELU: v = fmaxf(v, 0.f); break;
+                    case ORLK_EPI_RELU_MASK: v = e_aux > 0.f ? v : 0.f; break;
+                    case ORLK_EPI_SWISH: v = v / (1.f + expf(-v)); break;
+                    case ORLK_EPI_DSWISH: {
+                        const float sg = 1.f / (1.f + expf(-e_aux));
+                        v = v * (sg * (1.f + e_aux * (1.f - sg)));
+                        break;
                     }
-                    if (em < M) d.C[(int64_t)em * d.ldc + en] = v;
-                    else v = 0.f;                       // rows past M stay zero all the way down the chain
-                } else v = 0.f;
-                if (en < kn) {                          // push into every CTA's next-stage strip (column en = its k index)
-#pragma unroll
-                    for (int r = 0; r < CL; ++r) dsmem_store(An + er * KP + en, r, v);
+                    default: break;
                 }
+                d.C[(int64_t)em * d.ldc + en] = v;
             }
         }
         if (s < 3) CHAIN_STAMP(4 + 4 * s);
-        // every CTA of the strip, working or not: the pushes have landed and the shared-memory buffers may be reused
-        if (!last) cluster_sync();
-        if (s < 3) CHAIN_STAMP(5 + 4 * s);
+        if (!last) {
+            // every CTA of the strip, working or not: my tile is in L2, the peers' tiles are visible after the barrier
+            cluster_arrive();
+            cluster_wait();
+            if (s < 3) CHAIN_STAMP(5 + 4 * s);
+            const OrlkGemmDesc& dn = D[s + 1];
+            stage_kc<TM>(As, dn.A, dn.lda, m0, dn.M, dn.K, tid);     // the strip all eight CTAs have just finished
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
 }
 
-constexpr size_t chain_smem() { return sizeof(float) * (2 * A_FLOATS + B_FLOATS + R_FLOATS); }
+constexpr size_t chain_smem() { return sizeof(float) * (A_FLOATS + 2 * B_FLOATS + R_FLOATS); }
 
 }  // namespace
 
@@ -289,7 +262,7 @@ extern "C" int orlk_gemm_chain_init(void) {
 // Requirements per stage: a_layout 0, K <= 256, N <= 256, k_splits <= 1, C != NULL, no row / column sums, no CT.
 extern "C" int orlk_gemm_chain(const OrlkGemmDesc* descs_host, int n_chains, int n_stages, int passes, int passes_stage0,
                                void* stream) {
-    ORLK_REQUIRE(descs_host != nullptr && n_chains > 0 && n_stages > 0 && n_chains * n_stages <= MAX_DESC, "1..16 stage descriptors");
+    ORLK_REQUIRE(descs_host != nullptr && n_chains > 0 && n_stages > 0 && n_chains * n_stages <= MAX_DESC, "1..24 stage descriptors");
     ORLK_REQUIRE((passes == 1 || passes == 3) && (passes_stage0 == 1 || passes_stage0 == 3),
                  "passes must be 1 or 3 (the fp32 FFMA mode launches the layers one by one)");
     ChainArgs args;

@@ -167,7 +167,7 @@ class Runtime:
         """One launch for whole small-row layer chains (csrc/orlk_chain.cu): ``chains[c][s]`` is stage s of chain c, the
         A operand of stage s+1 is the C output of stage s; all chains have the same number of stages and rows."""
         n_chains, n_stages = len(chains), len(chains[0])
-        assert all(len(c) == n_stages for c in chains) and n_chains * n_stages <= 16
+        assert all(len(c) == n_stages for c in chains) and n_chains * n_stages <= 24
         arr = (L.GemmDesc * (n_chains * n_stages))()
         for c, chain in enumerate(chains):
             for s_, p in enumerate(chain):

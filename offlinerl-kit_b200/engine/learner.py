@@ -273,7 +273,7 @@ class MlpRun:
         # arithmetic of the small-row kernel: 0 = fp32 FFMA (default: exact fp32, and as fast in the step because those
         # launches are bound by launch / prologue latency, not by the k loop), 3 = 3xTF32 MMAs, 1 = TF32 (ORLK_TINY_MMA=1)
         self.passes = tc_passes if os.environ.get("ORLK_TINY_MMA", "0") == "1" else 0
-        if os.environ.get("ORLK_CHAIN", "0") == "1":
+        if CHAIN_ON:
             self.passes = tc_passes
         self.Mt = (M + 3) // 4 * 4
         self.G = G = members if members is not None else ps.G      # the first `members` members of the ParamSet
@@ -356,13 +356,18 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
     return Mat(t.data_ptr(), rows, cols, ld, t)
 
 
+# Small-row passes (actor / target / policy-improvement chains) as ONE cluster launch per pass (csrc/orlk_chain.cu): 8 CTAs
+# per 16-row strip, a hardware cluster barrier + an L2 re-read of the 16 KB strip between stages instead of a kernel
+# boundary.  (Round 1's version -- 4 CTAs per 32-row strip, scalar DSMEM pushes -- lost to the per-layer launches and was
+# off.)  ORLK_CHAIN=0 restores the per-layer launches.  Tensor-core precision modes only: `fp32` stays pure FFMA.
+CHAIN_ON = os.environ.get("ORLK_CHAIN", "1") != "0"
+CHAIN_MAX_DESC = 24
+
+
 def chainable(run: "MlpRun", with_head: bool) -> bool:
     """Small-row pass whose layers all fit the fused chain kernel (csrc/orlk_chain.cu)."""
     lays = run.ps.layers[:run.nh + (1 if with_head else 0)]
-    # Off by default: measured 6.6 us per stage against ~6 us for the per-layer launches (profiles/chain_trace.py): with
-    # 4 CTAs per strip the legacy mma.sync rate (~1/16 of an SMSP issue slot per m16n8k8) makes the stage compute 3.2 us
-    # and the scalar DSMEM pushes cost 2.5 us.  Kept (and unit-tested) as the base for a 16-CTA-cluster version.
-    return (run.passes != 0 and run.M < TC_MIN_ROWS and len(lays) <= 8 and os.environ.get("ORLK_CHAIN", "0") == "1"
+    return (CHAIN_ON and run.passes != 0 and run.M < TC_MIN_ROWS and len(lays) <= 8
             and all(lay.layout == "oi" and lay.in_dim <= 256 and lay.out_dim <= 256 for lay in lays))
 
 
@@ -385,7 +390,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
             if run.has_head:
                 st.append(fwd_problem(ps, run.nh, g, run.h(run.nh - 1, g), Mat.of(run.out[g]), L.EPI_NONE, run.store))
             chains.append(st)
-        per = max(1, 16 // n_st)
+        per = max(1, CHAIN_MAX_DESC // n_st)
         for c0 in range(0, G, per):
             plan.add(f"{tag}.fwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes, passes0=3))
         return
@@ -490,7 +495,7 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
             chains.append(st)
         if dact is not None:
             plan.keep.append(dact[0])
-        per = max(1, 16 // len(chains[0]))
+        per = max(1, CHAIN_MAX_DESC // len(chains[0]))
         for c0 in range(0, G, per):
             plan.add(f"{tag}.bwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes))
         return

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib as L
 from .core import Mat, Plan
-from .learner import (Learner, MlpRun, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
+from .learner import (Learner, MlpRun, chainable, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
                       emit_wgrad_adam, linears_of, make_gradbuf)
 from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem, pick_cfg
 
@@ -179,6 +179,8 @@ class TwinCriticLearner(Learner):
 
     def _can_fuse_head_sample(self, run: MlpRun) -> bool:
         head = run.ps.layers[run.nh]
+        if chainable(run, with_head=True):
+            return False        # the head is the last stage of the pass's chain launch; the sampler follows on its own
         return (run.has_head and head.layout == "oi" and run.G == 1 and self.A <= 8 and head.in_dim % 4 == 0
                 and run.M < TC_MIN_ROWS and os.environ.get("ORLK_FUSE_HEAD_SAMPLE", "1") != "0")
 

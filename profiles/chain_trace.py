@@ -12,7 +12,7 @@ from offlinerlkit_b200 import _lib as L
 from offlinerlkit_b200.engine.core import GP, get_runtime
 
 rt = get_runtime("cuda:0")
-NAMES = ["start", "prev_done"] + [f"s{s}.{n}" for s in range(3) for n in ("landed", "mma+partials", "epilogue+push", "cluster_sync")]
+NAMES = ["start", "prev_done"] + [f"s{s}.{n}" for s in range(3) for n in ("landed", "mma+partials", "epilogue+store", "cluster_barrier")]
 
 
 def trace(G, M, dims, passes):

@@ -152,7 +152,7 @@ def check_step_grads(g: Golden, t: int, tap: "EngineGrads", ora, ref_batch, nois
     stats = g.group(f"gradstats{t}")
     got = tap.after(stats.keys())
     run = (lambda o: o.step(ref_batch, noise)) if noise is not None else (lambda o: o.step(ref_batch))
-    flips = assert_grads_close_up_to_kinks(got, ora, run, tol, what=f"{g.meta['algo']} step {t}")
+    flips = assert_grads_close_up_to_kinks(got, ora, run, tol, what=f"{g.meta['algo']} step {t}", eng=tap.eng)
     if t == 0:
         # one flipped ReLU bit moves a cancelling 7936-row gradient sum by ~5e-4 (profiles/mask_flip_r02.txt)
         assert_grad_stats_close(got, stats, tol=tol if flips == 0 else 50 * tol, what=f"step {t}")

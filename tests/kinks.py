@@ -22,9 +22,13 @@ class _KinkReLU(torch.autograd.Function):
     def forward(ctx, z, rec, call_id):
         mask = z > 0
         if rec.tau > 0:
-            near = (z.detach().abs() <= rec.tau).reshape(-1).nonzero().reshape(-1)
+            zd = z.detach()
+            near = (zd.abs() <= rec.tau).reshape(-1).nonzero().reshape(-1)
+            width = zd.shape[-1]
+            rows = zd.reshape(-1, width)
             for i in near.tolist():
-                rec.found.append((call_id, i, float(z.detach().reshape(-1)[i])))
+                rec.found.append((call_id, i, float(zd.reshape(-1)[i])))
+                rec.rows.append(torch.relu(rows[i // width]).clone())        # the post-activation row it belongs to
         forced = [(i, v) for (c, i, v) in rec.force if c == call_id]
         if forced:
             mask = mask.contiguous().clone()
@@ -44,7 +48,7 @@ class KinkRecorder:
     ``|z| <= tau`` and overrides the mask bits listed in ``force`` [(call, flat index, bool)]."""
 
     def __init__(self, tau: float = 0.0, force=()):
-        self.tau, self.force, self.found, self.calls = tau, list(force), [], 0
+        self.tau, self.force, self.found, self.rows, self.calls = tau, list(force), [], [], 0
 
     def __call__(self, z):
         cid = self.calls
@@ -74,8 +78,47 @@ def _per_tensor_ok(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], tol: floa
     return bad
 
 
+def engine_activation_rows(eng) -> Dict[int, torch.Tensor]:
+    """width -> [rows, width] stack of every post-ReLU activation row the engine holds after a step (MlpRun.H of all its
+    passes, all members)."""
+    out: Dict[int, List[torch.Tensor]] = {}
+    seen = set()
+    for v in list(eng.__dict__.values()):
+        H = getattr(v, "H", None)
+        if not isinstance(H, (list, tuple)):
+            continue
+        for h in H:
+            if torch.is_tensor(h) and h.is_floating_point() and h.data_ptr() not in seen:
+                seen.add(h.data_ptr())
+                out.setdefault(h.shape[-1], []).append(h.reshape(-1, h.shape[-1]))
+    return {w: torch.cat(v, 0) for w, v in out.items()}
+
+
+def engine_bits(eng, found, rows, match_tol: float = 3e-5):
+    """For every near-zero pre-activation of the oracle, the ENGINE's decision: the oracle's post-activation row is looked
+    up among the engine's activation rows (nearest in the max norm, which must be within ``match_tol``: the engine's
+    forward error is ~2e-6) and the engine's bit is ``H_engine[row, col] > 0``.  Returns [(call, index, bit)] for the
+    bits on which the two disagree; elements whose row the engine does not hold are skipped."""
+    acts = engine_activation_rows(eng)
+    flips = []
+    for (c, i, z), row in zip(found, rows):
+        w = row.numel()
+        if w not in acts:
+            continue
+        E = acts[w]
+        r = row.to(E.device, E.dtype)
+        d = (E - r).abs().amax(dim=1)
+        j = int(d.argmin())
+        if float(d[j]) > match_tol:
+            continue
+        bit = bool(E[j, i % w] > 0)
+        if bit != (z > 0):
+            flips.append((c, i, bit))
+    return flips
+
+
 def assert_grads_close_up_to_kinks(got: Dict[str, torch.Tensor], ora_before, run_step: Callable, tol: float, what: str = "",
-                                   taus=(5e-7, 4e-6), max_kinks: int = 48) -> int:
+                                   taus=(5e-7, 4e-6), max_kinks: int = 48, eng=None) -> int:
     """``ora_before``: the oracle in its pre-step state (it is deep-copied, never advanced here); ``run_step(ora)`` runs the
     step on a copy and returns nothing (the gradients are read from ``ora.grads``).  Returns the number of mask bits that
     had to be flipped (0 = strict agreement).  Per tensor: rel-L2 <= tol and max |diff| <= 2 tol max|g|."""
@@ -92,6 +135,23 @@ def assert_grads_close_up_to_kinks(got: Dict[str, torch.Tensor], ora_before, run
     bad = _per_tensor_ok(gotn, base, tol)
     if not bad:
         return 0
+    if eng is not None:
+        # the engine's own decisions at the oracle's near-zero pre-activations, read from its activation buffers
+        ora = copy.deepcopy(ora_before)
+        with KinkRecorder(2e-5, ()) as rec:
+            run_step(ora)
+        flips = engine_bits(eng, rec.found, rec.rows)
+        if flips:
+            adj, _ = oracle_grads(0.0, flips)
+            bad = _per_tensor_ok(gotn, adj, tol)
+            if not bad:
+                zs = {(c, i): z for c, i, z in rec.found}
+                print(f"   [{what}] gradients agree under the engine's decisions at {len(flips)} of {len(rec.found)} ReLU "
+                      f"pre-activations within 2e-5 of zero: " + ", ".join(f"z={zs[(c, i)]:.1e}" for c, i, _ in flips[:8]),
+                      flush=True)
+                return len(flips)
+        raise AssertionError(f"{what}: engine gradients differ from the oracle beyond the {len(flips)} differing ReLU "
+                             "decisions: " + "; ".join(f"{k} rel-L2 {l2:.2e} max {mx:.2e}" for k, l2, mx in bad[:6]))
     for tau in taus:
         _, found = oracle_grads(tau, ())
         assert len(found) <= max_kinks, f"{what}: {len(found)} pre-activations within {tau} of zero"
