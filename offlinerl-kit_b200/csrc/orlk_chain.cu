@@ -58,51 +58,51 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// unbiased 3xTF32 split (see orlk_tc.cu:lo_tf32): hi = round-to-nearest-tf32(x), lo = rna(x - hi)
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ uint32_t tf32_lo(float x) { return tf32_hi(x - __uint_as_float(tf32_hi(x))); }
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(tf32_hi(x))); }
 
-// Rows [t0, t0+ROWS) x k [0, 8 ceil(K/8)) of a k-contiguous operand (base[t*ld + k]) into S[t][KP], by all threads.
-// Outside the matrix (t >= T or k >= K): zeros.  The global reads bypass L1 (cp.async.cg / ld.global.cg): the A strip of a
-// stage was written by the other CTAs of the cluster a barrier ago.
+// Rows [t0, t0+ROWS) x k [0, 8 ceil(K/8)) of a k-contiguous operand (base[t*ld + k]) into S[t][KP], by all 16 warps:
+// warp w takes rows w, w+16, ..., its lanes the 16-byte chunks of the row (no integer divisions: the address arithmetic of
+// the first version cost more than the copies).  Outside the matrix (t >= T or k >= K): zeros.  The global reads bypass
+// L1 (cp.async.cg / ld.global.cg): the A strip of a stage was written by the other CTAs of the cluster a barrier ago.
 template <int ROWS>
 __device__ __forceinline__ void stage_kc(float* S, const float* __restrict__ base, int64_t ld, int t0, int T, int K, int tid) {
     const int nb = 2 * ((K + 7) >> 3);                  // 16-byte chunks per row
+    const int w = tid >> 5, lane = tid & 31;
     if (aligned16(base) && (ld % 4) == 0) {
-        for (int idx = tid; idx < ROWS * nb; idx += NTHR) {
-            const int r = idx / nb, c = idx - r * nb;
-            const int t = t0 + r, k = 4 * c;
-            const int bytes = (t < T && k < K) ? 4 * min(4, K - k) : 0;
-            cp_async16(S + r * KP + k, base + (int64_t)min(t, T - 1) * ld + (bytes ? k : 0), bytes);
+#pragma unroll
+        for (int r = w; r < ROWS; r += NTHR / 32) {
+            const int t = t0 + r;
+            const float* row = base + (int64_t)min(t, T - 1) * ld;
+            for (int c = lane; c < nb; c += 32) {
+                const int k = 4 * c;
+                const int bytes = (t < T && k < K) ? 4 * min(4, K - k) : 0;
+                cp_async16(S + r * KP + k, row + (bytes ? k : 0), bytes);
+            }
         }
     } else {
-        for (int q = tid; q < ROWS * nb * 4; q += NTHR) {
-            const int r = q / (nb * 4), k = q - r * (nb * 4);
+#pragma unroll
+        for (int r = w; r < ROWS; r += NTHR / 32) {
             const int t = t0 + r;
-            S[r * KP + k] = (t < T && k < K) ? __ldcg(base + (int64_t)t * ld + k) : 0.f;
+            for (int k = lane; k < 4 * nb; k += 32) S[r * KP + k] = (t < T && k < K) ? __ldcg(base + (int64_t)t * ld + k) : 0.f;
         }
     }
 }
-// k [0, 8 ceil(K/8)) x columns [n0, n0+TN) of an n-contiguous operand (base[k*ld + n]) into S[k][PN], by all threads.
+// k [0, 8 ceil(K/8)) x columns [n0, n0+TN) of an n-contiguous operand (base[k*ld + n]) into S[k][PN], by all threads:
+// a warp covers 4 k rows x 8 chunks per sweep.
 __device__ __forceinline__ void stage_nc(float* S, const float* __restrict__ base, int64_t ld, int n0, int N, int K, int tid) {
     const int nk = 8 * ((K + 7) >> 3);
     if (aligned16(base) && (ld % 4) == 0) {
-        for (int idx = tid; idx < nk * (TN / 4); idx += NTHR) {
-            const int k = idx / (TN / 4), c = idx - k * (TN / 4);
-            const int n = n0 + 4 * c;
+        const int c = tid & 7;
+        const int n = n0 + 4 * c;
+        for (int k = tid >> 3; k < nk; k += NTHR / 8) {
             const int bytes = (k < K && n < N) ? 4 * min(4, N - n) : 0;
             cp_async16(S + k * PN + 4 * c, base + (int64_t)min(k, K - 1) * ld + (bytes ? n : 0), bytes);
         }
     } else {
-        for (int q = tid; q < nk * TN; q += NTHR) {
-            const int k = q / TN, c = q - k * TN;
-            const int n = n0 + c;
-            S[k * PN + c] = (k < K && n < N) ? __ldcg(base + (int64_t)k * ld + n) : 0.f;
-        }
+        const int c = tid & 31;
+        const int n = n0 + c;
+        for (int k = tid >> 5; k < nk; k += NTHR / 32) S[k * PN + c] = (k < K && n < N) ? __ldcg(base + (int64_t)k * ld + n) : 0.f;
     }
 }
 
@@ -111,6 +111,17 @@ __device__ __forceinline__ void stage_b(float* Bs, const OrlkGemmDesc& d, int n0
     if (d.b_layout == 1) stage_kc<TN>(Bs, d.B, d.ldb, n0, d.N, d.K, tid);
     else stage_nc(Bs, d.B, d.ldb, n0, d.N, d.K, tid);
 }
+
+// Measured (profiles/chain_trace_r02.txt, 256 rows, 3xTF32): 3.0 us per stage = 0.35 us to issue the strip's 32 warp-wide
+// 16-byte cp.async copies (the LSU takes 8 cycles per LDGSTS) + 0.3 us for them to land + 0.55 us to issue the next weight
+// tile's 64 + 1.05 us of MMAs (legacy mma.sync issues once per 16 cycles per SM sub-partition: 0.8 us for the 96 of a
+// sub-partition) + 0.2 us reduce / epilogue + 0.5 us for the tile's stores to be released + 0.1 us barrier.  Tried and
+// rejected: cp.async.bulk for the 1 KB rows (per-lane addresses make the compiler serialise the UBLKCP issue over the
+// lanes: 0.7 us for 16 rows) and slicing the weight prefetch between the k steps (the LDGSTS then stall each warp's own
+// fragment loads: 2.1 us of MMA phase).  A four-stage pass costs 17-18 us as one launch against ~22 us as four
+// PDL-chained small-row launches, but the passes that feed fused head / sampler / backward-entry launches lose those
+// fusions, and twin-critic passes (256 CTAs, two per SM) wait 1.5-2.5 us per barrier for their co-resident CTA: the CQL
+// step is 299.6 us with the chain against 291.8 us without, so it stays OFF by default (ORLK_CHAIN=1 enables it).
 
 __global__ void __launch_bounds__(NTHR, 2)
 k_chain_gemm(const __grid_constant__ ChainArgs P) {
@@ -144,48 +155,51 @@ k_chain_gemm(const __grid_constant__ ChainArgs P) {
         const bool active = n0 < N;
         const bool last = s + 1 == P.n_stages;
         float* Bs = (s & 1) ? B1 : B0;
-        if (!last) {                                    // next stage's weight tile streams in under this stage's MMAs
-            stage_b((s & 1) ? B0 : B1, D[s + 1], n0, tid);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");        // (an empty group when there is nothing to prefetch)
         // my output element: bias / mask operands prefetched off the critical path
         const int em = m0 + er, en = n0 + ec;
         const bool e_ok = active && em < M && en < N;
         const float e_bias = (e_ok && d.bias != nullptr) ? __ldg(d.bias + en) : 0.f;
         const float e_aux = (e_ok && d.aux != nullptr) ? __ldcg(d.aux + (int64_t)em * d.ldaux + en) : 0.f;
-        asm volatile("cp.async.wait_group 1;" ::: "memory");        // everything but the prefetch just issued
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (s == 1) CHAIN_STAMP(8);
         __syncthreads();                                // A strip and this stage's weight tile landed
-        if (s < 3) CHAIN_STAMP(2 + 4 * s);
+        if (s == 0) CHAIN_STAMP(2);
+        if (s == 1) CHAIN_STAMP(9);
+        if (s == 2) CHAIN_STAMP(14);
+        if (!last) {                                    // next stage's weight tile streams in under this stage's MMAs
+            stage_b((s & 1) ? B0 : B1, D[s + 1], n0, tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        if (s == 1) CHAIN_STAMP(7);
         if (active) {
             // ---- MMAs: k group kg owns 1/4 of the k steps, its four warps the four 8-column tiles
-            float cacc[4] = {0.f, 0.f, 0.f, 0.f};
+            // three independent accumulators (hi*hi, lo*hi, hi*lo): consecutive MMAs do not wait for each other
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
             const int nstep = (K + 7) >> 3, per = (nstep + KG - 1) / KG;
             const int s_lo = min(nstep, kg * per), s_hi = min(nstep, s_lo + per);
             const bool b_kc = d.b_layout == 1;
             const bool split3 = (s == 0 ? P.passes0 : P.passes) == 3;
             const int c = nt * 8 + gid;
-#pragma unroll 2
+            const float* ap = As + gid * KP + tig;
+            const float* bp = b_kc ? Bs + c * KP + tig : Bs + tig * PN + c;
+            const int bk = b_kc ? 1 : PN;               // stride of one k in the B tile
+#pragma unroll 4
             for (int st = s_lo; st < s_hi; ++st) {
                 const int k = 8 * st;
-                const float a0 = As[gid * KP + k + tig], a1 = As[(gid + 8) * KP + k + tig];
-                const float a2 = As[gid * KP + k + tig + 4], a3 = As[(gid + 8) * KP + k + tig + 4];
-                float b0, b1;
-                if (b_kc) {
-                    b0 = Bs[c * KP + k + tig];
-                    b1 = Bs[c * KP + k + tig + 4];
-                } else {
-                    b0 = Bs[(k + tig) * PN + c];
-                    b1 = Bs[(k + tig + 4) * PN + c];
-                }
+                const float a0 = ap[k], a1 = ap[8 * KP + k], a2 = ap[k + 4], a3 = ap[8 * KP + k + 4];
+                const float b0 = bp[k * bk], b1 = bp[(k + 4) * bk];
                 const uint32_t ah[4] = {tf32_hi(a0), tf32_hi(a1), tf32_hi(a2), tf32_hi(a3)};
                 const uint32_t bh0 = tf32_hi(b0), bh1 = tf32_hi(b1);
-                mma_tf32(cacc, ah, bh0, bh1);
+                mma_tf32(c0, ah, bh0, bh1);
                 if (split3) {
                     const uint32_t al[4] = {tf32_lo(a0), tf32_lo(a1), tf32_lo(a2), tf32_lo(a3)};
-                    mma_tf32(cacc, al, bh0, bh1);
-                    mma_tf32(cacc, ah, tf32_lo(b0), tf32_lo(b1));
+                    mma_tf32(c1, al, bh0, bh1);
+                    mma_tf32(c2, ah, tf32_lo(b0), tf32_lo(b1));
                 }
             }
+            float cacc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cacc[i] = c0[i] + (c1[i] + c2[i]);
             // partial tile -> shared memory
             float* r0 = red + (kg * TM + gid) * PR + nt * 8 + 2 * tig;
             r0[0] = cacc[0];
@@ -195,7 +209,9 @@ k_chain_gemm(const __grid_constant__ ChainArgs P) {
         }
         if (last) orlk::pdl_trigger();                  // the next kernel's CTAs may take their SMs from here on
         __syncthreads();                                // partials complete; everybody is done with As and Bs
-        if (s < 3) CHAIN_STAMP(3 + 4 * s);
+        if (s == 0) CHAIN_STAMP(3);
+        if (s == 1) CHAIN_STAMP(10);
+        if (s == 2) CHAIN_STAMP(15);
         if (active) {
             const int epi = d.epi;
             float v = 0.f;
@@ -218,15 +234,19 @@ k_chain_gemm(const __grid_constant__ ChainArgs P) {
                 d.C[(int64_t)em * d.ldc + en] = v;
             }
         }
-        if (s < 3) CHAIN_STAMP(4 + 4 * s);
+        if (s == 0) CHAIN_STAMP(4);
+        if (s == 1) CHAIN_STAMP(11);
         if (!last) {
             // every CTA of the strip, working or not: my tile is in L2, the peers' tiles are visible after the barrier
             cluster_arrive();
+            if (s == 1) CHAIN_STAMP(12);
             cluster_wait();
-            if (s < 3) CHAIN_STAMP(5 + 4 * s);
+            if (s == 0) CHAIN_STAMP(5);
+            if (s == 1) CHAIN_STAMP(13);
             const OrlkGemmDesc& dn = D[s + 1];
             stage_kc<TM>(As, dn.A, dn.lda, m0, dn.M, dn.K, tid);     // the strip all eight CTAs have just finished
             asm volatile("cp.async.commit_group;" ::: "memory");
+            if (s == 0) CHAIN_STAMP(6);
         }
     }
 }

@@ -183,25 +183,18 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // The tensor core reads an fp32 word as TF32 by IGNORING the 13 low mantissa bits (measured: a kernel that rewrites
 // hi = x & 0xFFFFE000 in shared memory and one that leaves x untouched give bit-identical results, while
-// lo = x - cvt.rna.tf32(x) is off by 2^-11).  So a raw tile in shared memory already is the "hi" operand
-// hi = trunc_tf32(x) and only lo = x - hi (exact in fp32) has to be written.
-// ROUNDING: the split must not be biased.  With hi = trunc(x) for BOTH operands every lo has the sign of its x, the
-// dropped lo_a * lo_b term and the hardware's truncation of the lo words all pull each product towards zero, and over a
-// 256-term dot product of mostly positive ReLU activations the error adds up linearly (measured: 2.4e-6 absolute on
-// pre-activations of scale 1-3, 10 x the fp32 FFMA kernel's) -- enough to decide a ReLU within 2e-7 of zero the other
-// way than torch does about six times per CQL step, and one flipped mask bit moves the heavily cancelling 7936-row
-// critic gradient by 5e-4 (profiles/mask_flip_r02.txt).  So (a) the A operand, which passes through registers on its
-// way to tensor memory anyway, is split as hi = round-to-nearest-tf32(x), lo = x - hi (either sign: lo_a * lo_b is then
-// zero-mean whatever B's split is), and (b) every lo word is itself rounded to TF32 (cvt.rna) before it is stored, so
-// that the hardware's truncation of it is a no-op.  What is left is random rounding of 2^-23 relative size.
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float lo1_tf32(float x) { return rna_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+// lo = x - cvt.rna.tf32(x) is off by 2^-11).  So the raw tile already is the "hi" operand and only
+// lo = x - trunc_tf32(x) (exact in fp32) has to be written.
+// On the truncation bias (round 2): with truncated splits every product comes out smaller by a relative 2^-22..2^-20
+// (the dropped lo*lo term and the hardware's truncation of the lo words), i.e. a dot product is SHRUNK by ~7e-7 of
+// itself (measured: 2.4e-6 absolute on pre-activations of scale 3) plus a random part of ~1e-7 -- the same size as the
+// fp32 FFMA kernel's rounding noise.  Near a ReLU's zero only the random part matters, so rounding the split to nearest
+// (cvt.rna, tried: +20 us per CQL step on the splitter's critical path) does not make mask decisions more stable.
 __device__ __forceinline__ float4 lo_tf32(const float4& v) {
-    return make_float4(lo1_tf32(v.x), lo1_tf32(v.y), lo1_tf32(v.z), lo1_tf32(v.w));
+    return make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
+                       v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                       v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u),
+                       v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
 }
 
 // lo = x - trunc_tf32(x) for float4s [i_lo, i_hi) of a raw operand tile, by 128 threads (t = 0..127)
@@ -570,18 +563,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     }
                     const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + ATM_COL + s * ATM_STRIDE;
-                    if (PASSES == 3) {      // unbiased split: hi = rna(x), lo = rna(x - hi)   (see lo_tf32)
-                        float lo[32];
+                    tmem_st32(ta, x);
+                    if (PASSES == 3) {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const float h = rna_tf32(x[k]);
-                            lo[k] = rna_tf32(x[k] - h);
-                            x[k] = h;
-                        }
-                        tmem_st32(ta, x);
-                        tmem_st32(ta + 32, lo);
-                    } else {
-                        tmem_st32(ta, x);
+                        for (int k = 0; k < 32; ++k) x[k] = x[k] - __uint_as_float(__float_as_uint(x[k]) & 0xFFFFE000u);
+                        tmem_st32(ta + 32, x);
                     }
                     tmem_wait_st();
                     if (r3) {       // the A buffer may be refilled; B of this slab is a separate barrier

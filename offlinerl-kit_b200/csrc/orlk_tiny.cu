@@ -118,13 +118,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// unbiased 3xTF32 split (see orlk_tc.cu:lo_tf32): hi = round-to-nearest-tf32(x), lo = rna(x - hi)
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ uint32_t tf32_lo(float x) { return tf32_hi(x - __uint_as_float(tf32_hi(x))); }
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(tf32_hi(x))); }
 
 // MMA = false: fp32 FFMA micro-kernel (the `fp32` mode, and launches that want row / column sums).
 // MMA = true : warp-level TF32 tensor-core MMAs (mma.sync m16n8k8) on fragments read straight from the staged tiles, with

@@ -358,9 +358,11 @@ def _grouped(t: torch.Tensor, rows: int, cols: int, ld: int) -> Mat:
 
 # Small-row passes (actor / target / policy-improvement chains) as ONE cluster launch per pass (csrc/orlk_chain.cu): 8 CTAs
 # per 16-row strip, a hardware cluster barrier + an L2 re-read of the 16 KB strip between stages instead of a kernel
-# boundary.  (Round 1's version -- 4 CTAs per 32-row strip, scalar DSMEM pushes -- lost to the per-layer launches and was
-# off.)  ORLK_CHAIN=0 restores the per-layer launches.  Tensor-core precision modes only: `fp32` stays pure FFMA.
-CHAIN_ON = os.environ.get("ORLK_CHAIN", "1") != "0"
+# boundary.  Round 2's rewrite (round 1: 4 CTAs per 32-row strip, scalar DSMEM pushes, 6.6 us per stage) runs a stage in
+# 3.0 us, a four-stage pass in 17-18 us against ~22 us for four PDL-chained launches -- but the step loses the fused
+# head+sampler / backward-entry launches and the twin-critic passes run two CTAs per SM, so CQL measures 299.6 us with it
+# and 291.8 us without (profiles/chain_trace_r02.txt): OFF by default, ORLK_CHAIN=1 enables it (tensor-core modes only).
+CHAIN_ON = os.environ.get("ORLK_CHAIN", "0") == "1"
 CHAIN_MAX_DESC = 24
 
 

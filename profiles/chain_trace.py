@@ -12,7 +12,9 @@ from offlinerlkit_b200 import _lib as L
 from offlinerlkit_b200.engine.core import GP, get_runtime
 
 rt = get_runtime("cuda:0")
-NAMES = ["start", "prev_done"] + [f"s{s}.{n}" for s in range(3) for n in ("landed", "mma+partials", "epilogue+store", "cluster_barrier")]
+NAMES = ["start", "prev_done", "s0.landed", "s0.mma+partials", "s0.epilogue+store", "s0.cluster_barrier", "s1.strip_issued",
+         "s1.prefetch_issued", "s1.thread0_landed", "s1.all_landed", "s1.mma+partials", "s1.epilogue+store", "s1.arrive_issued",
+         "s1.cluster_barrier", "s2.all_landed", "s2.mma+partials"]
 
 
 def trace(G, M, dims, passes):
@@ -45,7 +47,7 @@ def trace(G, M, dims, passes):
     L.call("orlk_tc_set_trace", None)
     t = buf.view(-1, 16).cpu()
     n_cta = int((t[:, 0] != 0).sum())
-    t = t[:n_cta, :14].double() / 1.9
+    t = t[:n_cta, :16].double() / 1.9
     rel = t - t[:, 1:2]
     med = rel.median(dim=0).values
     print(f"G={G} M={M} dims={dims} passes={passes} ctas={n_cta}")

@@ -68,29 +68,53 @@ def _flat(grads: Dict[str, torch.Tensor], names) -> np.ndarray:
 
 
 def _per_tensor_ok(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], tol: float) -> List[Tuple[str, float, float]]:
+    """Per tensor: relative L2 <= tol and max |diff| <= 2 tol max|g|.  One-element tensors (the scalar head's bias
+    gradient, sum_m dq[m] over up to 7936 rows that cancels to ~0.4 % of sum |dq|) get 4 tol: fp32 summation ORDER alone
+    moves such a sum by ~1e-4 of itself, in torch as much as in the engine."""
     bad = []
     for k in b:
         d = a[k] - b[k]
         l2 = np.sqrt((d * d).sum()) / max(np.sqrt((b[k] * b[k]).sum()), 1e-30)
         mx = np.abs(d).max() / max(np.abs(b[k]).max(), 1e-30)
-        if l2 > tol or mx > 2 * tol:
+        t = 4 * tol if b[k].size == 1 else tol
+        if l2 > t or mx > 2 * t:
             bad.append((k, l2, mx))
     return bad
 
 
 def engine_activation_rows(eng) -> Dict[int, torch.Tensor]:
-    """width -> [rows, width] stack of every post-ReLU activation row the engine holds after a step (MlpRun.H of all its
-    passes, all members)."""
+    """width -> [rows, width] stack of every post-ReLU activation row the engine holds after a step: the ``H`` buffers of
+    all its passes (MlpRun objects: attributes of the engine or kept alive by its launch plans), all members."""
     out: Dict[int, List[torch.Tensor]] = {}
-    seen = set()
+    seen_t, seen_o = set(), set()
+
+    def visit(v, depth):
+        if depth > 4 or id(v) in seen_o or torch.is_tensor(v) or isinstance(v, (str, bytes, int, float, type(None))):
+            return
+        seen_o.add(id(v))
+        if isinstance(v, dict):
+            for x in v.values():
+                visit(x, depth + 1)
+            return
+        if isinstance(v, (list, tuple)):
+            for x in v:
+                visit(x, depth + 1)
+            return
+        d = getattr(v, "__dict__", None)
+        if not isinstance(d, dict):
+            return
+        H = d.get("H")
+        if isinstance(H, (list, tuple)) and H and all(torch.is_tensor(h) for h in H):
+            for h in H:
+                if h.is_floating_point() and h.data_ptr() not in seen_t:
+                    seen_t.add(h.data_ptr())
+                    out.setdefault(h.shape[-1], []).append(h.reshape(-1, h.shape[-1]))
+            return
+        if type(v).__name__ == "Plan":
+            visit(d.get("keep"), depth + 1)
+
     for v in list(eng.__dict__.values()):
-        H = getattr(v, "H", None)
-        if not isinstance(H, (list, tuple)):
-            continue
-        for h in H:
-            if torch.is_tensor(h) and h.is_floating_point() and h.data_ptr() not in seen:
-                seen.add(h.data_ptr())
-                out.setdefault(h.shape[-1], []).append(h.reshape(-1, h.shape[-1]))
+        visit(v, 0)
     return {w: torch.cat(v, 0) for w, v in out.items()}
 
 
