@@ -155,7 +155,9 @@ def check_step_grads(g: Golden, t: int, tap: "EngineGrads", ora, ref_batch, nois
     flips = assert_grads_close_up_to_kinks(got, ora, run, tol, what=f"{g.meta['algo']} step {t}", eng=tap.eng)
     if t == 0:
         # one flipped ReLU bit moves a cancelling 7936-row gradient sum by ~5e-4 (profiles/mask_flip_r02.txt)
-        assert_grad_stats_close(got, stats, tol=tol if flips == 0 else 50 * tol, what=f"step {t}")
+        # (a flipped unit's own bias-gradient element changes by a whole row's contribution: with flips only the norms are
+        # compared with the reference's raw fingerprints; the full tensors were compared above under the engine's bits)
+        assert_grad_stats_close(got, stats, tol=tol if flips == 0 else 50 * tol, what=f"step {t}", elements=flips == 0)
     run(ora)            # advance the oracle (optimiser counters, TD3+BC's update counter)
 
 
