@@ -474,6 +474,90 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ member-sharded EDAC
+def run_edac_sharded(args, rank: int, world: int, local_rank: int):
+    """BASELINE.json configs[2]: EDAC, halfcheetah-shaped, 10 critics, eta = 1, the critics sharded over the ranks (3/3/2/2 on
+    four GPUs), three NCCL all-gathers per step (engine/edac_sharded.py).  ONE training run on N GPUs: `value` is that
+    run's gradient steps/s (scaling: "strong")."""
+    import ctypes as C
+    import random
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200 import parallel
+    from offlinerlkit_b200.nets import MLP
+    from offlinerlkit_b200.modules import ActorProb, EnsembleCritic, TanhDiagGaussian
+    from offlinerlkit_b200.policy import EDACPolicy
+    from offlinerlkit_b200.buffer import ReplayBuffer
+    from offlinerlkit_b200.synthetic import make_dataset
+    device = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    dist_on = parallel.init("nccl", torch.device(device))
+    E = 10
+    random.seed(0), np.random.seed(0), torch.manual_seed(0), torch.cuda.manual_seed_all(0)      # replicated on every rank
+    ab = MLP(input_dim=O_DIM, hidden_dims=HIDDEN)
+    actor = ActorProb(ab, TanhDiagGaussian(ab.output_dim, A_DIM, unbounded=True, conditioned_sigma=True), device)
+    critics = EnsembleCritic(O_DIM, A_DIM, HIDDEN, num_ensemble=E, device=device)
+    log_alpha = torch.zeros(1, requires_grad=True, device=device)
+    policy = EDACPolicy(actor, critics, torch.optim.Adam(actor.parameters(), lr=1e-4),
+                        torch.optim.Adam(critics.parameters(), lr=3e-4), tau=0.005, gamma=0.99,
+                        alpha=(-A_DIM, log_alpha, torch.optim.Adam([log_alpha], lr=1e-4)), max_q_backup=False,
+                        deterministic_backup=False, eta=1.0)       # run_example/run_edac.py:26-58
+    policy.train()
+    if world > 1:
+        from offlinerlkit_b200.engine.edac_sharded import NcclComm
+        policy.shard_critics(rank, world, NcclComm())
+    buf = ReplayBuffer(buffer_size=args.rows, obs_shape=(O_DIM,), obs_dtype=np.float32, action_dim=A_DIM,
+                       action_dtype=np.float32, device=device)
+    buf.load_dataset(make_dataset(args.rows, O_DIM, A_DIM, seed=0))
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(W):
+        loss = policy.learn(buf.sample(BATCH))
+    eng = policy._engine
+
+    def barrier():
+        if dist_on:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    L.call("orlk_event_create", C.byref(e0))
+    L.call("orlk_event_create", C.byref(e1))
+    barrier()
+    t0w = time.time()
+    t0 = time.perf_counter()
+    L.call("orlk_event_record", e0, eng.rt.cur)
+    for _ in range(K):
+        loss = policy.learn(buf.sample(BATCH))
+    L.call("orlk_event_record", e1, eng.rt.cur)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = C.c_float()
+    L.call("orlk_event_elapsed_ms", e0, e1, C.byref(ms))
+    sampler.window = (t0w, time.time())
+    clocks = sampler.stop()
+    (t_ms,) = parallel.reduce_scalars([max(ms.value, 1e3 * wall)], "max", device)
+    if rank == 0:
+        n_launch = sum(p.n_launches for p in eng.plans.values())
+        counts = getattr(eng, "counts", [E])
+        line = {"metric": "EDAC gradient steps/s (hc-shaped, bs256, 10 critics, members sharded)", "value": K / (t_ms * 1e-3),
+                "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": "edac_halfcheetah_shaped obs17 act6 hidden256x3 batch256 E10 eta1 buffer1M (configs[2])",
+                           "members_per_rank": counts, "collectives_per_step": 0 if world == 1 else 3,
+                           "parallelism": "critic members sharded over the ranks; actor / alpha / batch / noise replicated"},
+                "clocks": clocks,
+                "e2e": {"value": K / (t_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 8 * BATCH, "d2h_bytes_per_step": 128},
+                "gpu_launches": n_launch * K, "launches_per_step": n_launch, "precision": eng.precision,
+                "last_loss": {k: float(v) for k, v in loss.items()}}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -481,6 +565,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--rows", type=int, default=N_DATA)
+    ap.add_argument("--workload", default="cql", choices=["cql", "edac_sharded"],
+                    help="cql = the headline (seed-parallel replicas); edac_sharded = BASELINE.json configs[2], ONE run with "
+                         "the 10 critics sharded over the --gpus ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=None, choices=["fp32", "tf32x3", "tf32"],
                     help="GEMM mode of the wide layers (default tf32x3, the fp32-parity tensor-core mode)")
@@ -495,6 +582,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.workload == "edac_sharded":
+        run_edac_sharded(args, rank, world, local_rank)
+        return
     run_engine(args, rank, world, local_rank)
 
 

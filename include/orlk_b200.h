@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 20
+#define ORLK_ABI_VERSION 21
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -241,6 +241,14 @@ typedef struct OrlkConcatSeg {
     int32_t pad_;
 } OrlkConcatSeg;
 int orlk_concat_rows(const OrlkConcatSeg* segs_dev, int n_segs, int total_rows, void* stream);
+/* Member-sharded ensembles (BASELINE.json configs[2], configs[4]): after an equal-block all-gather
+ * every rank holds src[world][block_stride]; rank r's block carries counts_host[r] * per_member valid floats (uneven
+ * splits: 10 critics on 4 GPUs = 3/3/2/2).  Writes them densely in rank order to dst [sum(counts)][per_member] -- the
+ * [E, B] layout the reference's ensemble-wide reductions work on: the min over critics of the actor step and of the TD
+ * target (edac.py:96-102, :124-131), the sum over critics of the normalised input gradients (:136-149), the per-member
+ * holdout losses (ensemble_dynamics.py:145-168).  world <= 8. */
+int orlk_compact_blocks(const float* src, int64_t block_stride, float* dst, int world, int per_member, const int* counts_host,
+                        void* stream);
 
 /* ------------------------------------------------------ stochastic policy head */
 /* Philox4x32-10 fill: out[i] ~ N(0,1) for i < n_normal, then U[lo,hi) for the next n_uniform

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -100,6 +100,7 @@ _PROTOS = {
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
+    "orlk_compact_blocks": [_P, _L, _P, _I, _I, _P, _P],
     "orlk_narrow_fwd": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P],
     "orlk_narrow_wgrad_chunks": [_I], "orlk_narrow_init": [],
     "orlk_narrow_wgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],

@@ -121,6 +121,23 @@ __global__ void k_concat_rows(const OrlkConcatSeg* __restrict__ segs, int n_segs
     for (int j = lane; j < sg.w1 + sg.w2; j += 32) dst[j] = j < sg.w1 ? a[j] : b[j - sg.w1];
 }
 
+// ------------------------------------------------------------------------------------------ member-sharded exchange
+// After an equal-block all-gather over `world` ranks each rank holds [world][block_stride] floats, of which rank r's block
+// carries counts[r] * per_member valid floats (ensembles split unevenly over the ranks: 10 critics on 4 GPUs = 3/3/2/2).
+// Writes them densely, in rank order, to dst.  (edac.py:96-149 / ensemble_dynamics.py:178-223 with members sharded.)
+struct CompactArgs { int counts[8]; };
+__global__ void k_compact_blocks(const float* __restrict__ src, int64_t block_stride, float* __restrict__ dst, int world,
+                                 int per_member, const __grid_constant__ CompactArgs C) {
+    orlk::pdl_enter();
+    const int r = blockIdx.y;
+    int before = 0;
+    for (int q = 0; q < r; ++q) before += C.counts[q];
+    const int64_t n = (int64_t)C.counts[r] * per_member;
+    const float* s = src + (int64_t)r * block_stride;
+    float* d = dst + (int64_t)before * per_member;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 // ------------------------------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
@@ -678,6 +695,22 @@ int orlk_concat_rows(const OrlkConcatSeg* segs_dev, int n_segs, int total_rows, 
     const int wpb = 8;
     orlk::launch(k_concat_rows, (total_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream, segs_dev, n_segs, total_rows);
     return check_launch("k_concat_rows");
+}
+
+int orlk_compact_blocks(const float* src, int64_t block_stride, float* dst, int world, int per_member, const int* counts_host,
+                        void* stream) {
+    ORLK_REQUIRE(src != nullptr && dst != nullptr && world >= 1 && world <= 8 && per_member > 0 && counts_host != nullptr, "args");
+    CompactArgs C;
+    int mx = 0;
+    for (int r = 0; r < 8; ++r) {
+        C.counts[r] = r < world ? counts_host[r] : 0;
+        mx = C.counts[r] > mx ? C.counts[r] : mx;
+    }
+    ORLK_REQUIRE(mx > 0 && (int64_t)mx * per_member <= block_stride, "a block must hold its members");
+    const int64_t n = (int64_t)mx * per_member;
+    const int bx = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+    orlk::launch(k_compact_blocks, dim3(bx, world), 256, 0, (cudaStream_t)stream, src, block_stride, dst, world, per_member, C);
+    return check_launch("k_compact_blocks");
 }
 
 int orlk_philox_fill(float* out, int64_t n_normal, int64_t n_uniform, float lo, float hi, uint64_t seed,

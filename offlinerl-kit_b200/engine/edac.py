@@ -43,12 +43,12 @@ class EDACLearner(_BatchMixin, Learner):
             raise L.OrlkError("the CUDA engine implements TanhDiagGaussian with sigma_min=-5, sigma_max=2 only")
         if not (getattr(dist, "_c_sigma", False) and getattr(dist, "_unbounded", False)):
             raise L.OrlkError("EDAC engine needs TanhDiagGaussian(unbounded=True, conditioned_sigma=True)")
-        lin = lambda m: [x for x in m.model if hasattr(x, "num_ensemble")]
         for mod in policy.critics.model:
             if not hasattr(mod, "num_ensemble") and not isinstance(mod, torch.nn.ReLU):
                 raise L.OrlkError(f"EnsembleCritic: only ReLU activations are supported, found {type(mod).__name__}")
         self.actor_ps = ParamSet.from_linear_members(rt, "actor", [linears_of(actor)], fuse_last=2)
-        self.critic_ps = ParamSet.from_ensemble(rt, "critics", lin(policy.critics), targets=lin(policy.critics_old))
+        cur, old = self._critic_layers(policy)
+        self.critic_ps = ParamSet.from_ensemble(rt, "critics", cur, targets=old)
         self.param_sets = [self.actor_ps, self.critic_ps]
         self.E = self.critic_ps.G
         self.nh_a, self.nh_c = len(self.actor_ps.layers) - 1, len(self.critic_ps.layers) - 1
@@ -81,6 +81,12 @@ class EDACLearner(_BatchMixin, Learner):
         self.noise_views = {"eps_actor": self.noise[:B * A].view(B, A),
                             "eps_next": self.noise[B * A:].view(self.n_next * B, A)}
         self._built = False
+
+    def _critic_layers(self, policy):
+        """(EnsembleLinear layers of the online critics, of the target critics) this engine trains: all members here,
+        a contiguous slice of them in the member-sharded engine (engine/edac_sharded.py)."""
+        lin = lambda m: [x for x in m.model if hasattr(x, "num_ensemble")]
+        return lin(policy.critics), lin(policy.critics_old)
 
     def _sample(self, plan, tag, head, eps, X: Mat, logp, obs: Mat, rep: int = 1):
         O, A, B = self.O, self.A, self.B

@@ -81,6 +81,21 @@ def partition_members(n_members: int, world: int) -> List[List[int]]:
     return out
 
 
+def gather_member_blocks(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """Host-level form of the member-sharded exchange (engine/edac_sharded.py does the same with ``orlk_compact_blocks``
+    inside its step graphs): every rank contributes ``local`` [counts[rank], ...]; all ranks get the dense
+    [sum(counts), ...] tensor in rank order.  One equal-block all-gather, blocks padded to the largest slice."""
+    world = dist.get_world_size(group)
+    e_max = max(counts)
+    per = local[0].numel() if local.shape[0] else int(torch.tensor(local.shape[1:]).prod())
+    send = torch.zeros(e_max * per, dtype=local.dtype, device=local.device)
+    send[:local.numel()].copy_(local.reshape(-1))
+    recv = torch.empty(world * e_max * per, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    parts = [recv[r * e_max * per:r * e_max * per + c * per] for r, c in enumerate(counts)]
+    return torch.cat(parts).view((sum(counts),) + tuple(local.shape[1:]))
+
+
 # --------------------------------------------------------------------------------------------------------------
 # State-sharded model rollouts (SURVEY.md section 8e, MOPO rollouts, variant B)
 # --------------------------------------------------------------------------------------------------------------

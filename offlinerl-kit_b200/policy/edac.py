@@ -48,7 +48,24 @@ class EDACPolicy(BasePolicy):
             action, _ = self.actforward(obs, deterministic)
         return action.cpu().numpy()
 
+    def shard_critics(self, rank: int, world: int, comm=None) -> None:
+        """Train only members partition_members(E, world)[rank] of the critic ensemble on this rank (BASELINE.json
+        configs[2]: "members sharded across GPUs"); actor, alpha, batch and noise must be replicated (same seeds).  ``comm``
+        = engine.edac_sharded.NcclComm() between processes; None when the ranks are driven by EmulatedShardGroup.  Call
+        before the first ``learn``; ``gather_critics()`` makes ``state_dict()`` whole again."""
+        if self._engine is not None:
+            raise RuntimeError("shard_critics must be called before the first learn()")
+        self._shard = (int(rank), int(world), comm)
+
+    def gather_critics(self) -> None:
+        if self._engine is not None and hasattr(self._engine, "gather_all"):
+            self._engine.gather_all()
+
     def engine(self, batch_size: int):
+        shard = getattr(self, "_shard", None)
+        if shard is not None:
+            from ..engine.edac_sharded import EDACShardedLearner
+            return engine_for(self, int(batch_size), lambda: EDACShardedLearner(self, batch_size, *shard))
         from ..engine.edac import EDACLearner
         return engine_for(self, int(batch_size), lambda: EDACLearner(self, batch_size))
 

@@ -145,3 +145,55 @@ def test_state_sharded_rollout_world2():
         for k, v in expect.items():
             assert np.array_equal(np.asarray(out[k], dtype=np.float32), v), (rank, k)
         assert info["num_transitions"] == n and info["reward_mean"] == pytest.approx(rmean, rel=1e-6)
+
+
+def _shard_worker(rank: int, world: int, port: int, q):
+    """Member-sharded EDAC exchanges (engine/edac_sharded.py) at the host level: every rank holds a slice of the critics'
+    outputs; after the padded all-gather the ensemble-wide reductions must equal the unsharded ones."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from offlinerlkit_b200 import parallel
+    assert parallel.init("gloo")
+    import torch.distributed as dist
+    E, B, A = 5, 64, 3                              # 5 critics over 2 ranks: 3 / 2 (an uneven split)
+    g = torch.Generator().manual_seed(0)
+    q_full = torch.randn(E, B, generator=g)
+    tq_full = torch.randn(E, B, generator=g)
+    gin_full = torch.randn(E, B, A, generator=g)
+    parts = parallel.partition_members(E, world)
+    counts = [len(p) for p in parts]
+    e0, e1 = parts[rank][0], parts[rank][-1] + 1
+    q_all = parallel.gather_member_blocks(q_full[e0:e1].contiguous(), counts)
+    tq_all = parallel.gather_member_blocks(tq_full[e0:e1].contiguous(), counts)
+    gin_all = parallel.gather_member_blocks(gin_full[e0:e1].contiguous(), counts)
+    ghat = gin_all / (gin_all.norm(dim=2, keepdim=True) + 1e-10)
+    q.put((rank, torch.equal(q_all, q_full), q_all.argmin(0).tolist(), tq_all.min(0).values.tolist(),
+           ghat.sum(0).tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_member_sharded_exchange_world2():
+    """X1 / X3 of the sharded EDAC step: gathered == unsharded bit for bit, hence argmin over critics (actor loss,
+    edac.py:96-102) and min over target critics (:124-131) exact, S = sum_e ghat_e (:136-149) to 1e-6."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    E, B, A = 5, 64, 3
+    g = torch.Generator().manual_seed(0)
+    q_full, tq_full, gin_full = torch.randn(E, B, generator=g), torch.randn(E, B, generator=g), torch.randn(E, B, A, generator=g)
+    S = (gin_full / (gin_full.norm(dim=2, keepdim=True) + 1e-10)).sum(0)
+    for rank, same, argmin, tmin, s in res:
+        assert same
+        assert argmin == q_full.argmin(0).tolist()
+        assert tmin == tq_full.min(0).values.tolist()
+        assert torch.allclose(torch.tensor(s), S, atol=1e-6, rtol=0)
