@@ -554,8 +554,16 @@ def run_edac_sharded(args, rank: int, world: int, local_rank: int):
         print(json.dumps(line), flush=True)
     if dist_on:
         import torch.distributed as dist
+        # a captured graph that holds NCCL kernels must die before the communicator: destroy_process_group() hung for
+        # minutes with the step graph alive (round 2, 4 x B200).  Drop the graph, synchronise, and leave without the
+        # communicator's own teardown.
+        if hasattr(eng, "_whole"):
+            eng._whole = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

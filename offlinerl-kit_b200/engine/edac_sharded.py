@@ -326,10 +326,46 @@ class EDACShardedLearner(EDACLearner):
             res["alpha"] = float(out[LS_ALPHA])
         return res
 
+    def _capture_whole_step(self) -> bool:
+        """The four segments AND the three NCCL all-gathers as ONE CUDA graph (torch's stream capture records the
+        collectives' kernels like any other launch): one graph launch per step instead of four launches and three Python
+        collective calls.  ORLK_SHARD_GRAPH=0 keeps the segmented form."""
+        if os.environ.get("ORLK_SHARD_GRAPH", "1") == "0" or not self.use_graph:
+            return False
+        rt = self.rt
+        for i in range(len(self.segments)):             # warm-up outside capture: NCCL sets its channels up lazily
+            self.plans[self.segments[i]].run_eager()
+            if i < len(self.exchanges):
+                self.comm.all_gather(*self.exchanges[i])
+        rt.sync()
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                rt.cur = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+                for i in range(len(self.segments)):
+                    self.plans[self.segments[i]].run_eager()
+                    if i < len(self.exchanges):
+                        self.comm.all_gather(*self.exchanges[i])
+        finally:
+            rt.cur = rt.exec_ptr
+        self._whole = g
+        return True
+
     def step(self, batch, noise=None) -> Dict[str, float]:
         if self.comm is None:
             raise L.OrlkError("EDACShardedLearner.step needs a communicator (NcclComm), or drive the ranks with EmulatedShardGroup")
         self.prepare(batch, noise)
+        whole = getattr(self, "_whole", None)
+        if whole is None and not getattr(self, "_whole_tried", False):
+            # (the warm-up pass inside _capture_whole_step is a real step: it advances the optimiser like any other)
+            self._whole_tried = True
+            if self._capture_whole_step():
+                return self.finish()
+            whole = None
+        if whole is not None:
+            whole.replay()
+            return self.finish()
         for i in range(len(self.segments)):
             self.run_segment(i)
             if i < len(self.exchanges):
