@@ -566,6 +566,78 @@ def run_edac_sharded(args, rank: int, world: int, local_rank: int):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------ member-sharded dynamics
+def run_dyn_sharded(args, rank: int, world: int, local_rank: int):
+    """BASELINE.json configs[4], training half: EnsembleDynamicsModel (7 members, hidden 200 x 4, halfcheetah-shaped), one
+    `learn` pass of --steps mini-batches of 256 rows per member, the members sharded over the ranks (one all-gather of the
+    shared log-variance bounds' partial gradients per mini-batch).  ONE training run on N GPUs (scaling: "strong")."""
+    import ctypes as C
+    from offlinerlkit_b200 import _lib as L
+    from offlinerlkit_b200 import parallel
+    from offlinerlkit_b200.modules import EnsembleDynamicsModel
+    from offlinerlkit_b200.dynamics import EnsembleDynamics
+    from offlinerlkit_b200.utils.scaler import StandardScaler
+    from offlinerlkit_b200.utils.termination_fns import termination_fn_halfcheetah
+    from offlinerlkit_b200.synthetic import make_dataset
+    device = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    dist_on = parallel.init("nccl", torch.device(device))
+    E, Bm = 7, 256
+    np.random.seed(0), torch.manual_seed(0), torch.cuda.manual_seed_all(0)
+    model = EnsembleDynamicsModel(O_DIM, A_DIM, [200, 200, 200, 200], num_ensemble=E, num_elites=5,
+                                  weight_decays=[2.5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4], device=device)     # run_mopo.py:60-72
+    dyn = EnsembleDynamics(model, torch.optim.Adam(model.parameters(), lr=1e-3), StandardScaler(), termination_fn_halfcheetah)
+    if world > 1:
+        from offlinerlkit_b200.engine.edac_sharded import NcclComm
+        dyn.shard_members(rank, world, NcclComm())
+    n = min(args.rows, 200_000)
+    d = make_dataset(n, O_DIM, A_DIM, seed=0)
+    x = np.concatenate([d["observations"], d["actions"]], 1)
+    y = np.concatenate([d["next_observations"] - d["observations"], d["rewards"].reshape(-1, 1)], 1)
+    dyn.scaler.fit(x)
+    eng = dyn.engine
+    src_x = torch.from_numpy(dyn.scaler.transform(x).astype(np.float32)).to(device)
+    src_y = torch.from_numpy(y.astype(np.float32)).to(device)
+    K, W = args.steps, max(args.warmup, 3)
+    idx = torch.from_numpy(np.random.randint(0, n, size=(E, Bm * max(K, W)))).to(device)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.learn(src_x, src_y, idx[:, :Bm * W].contiguous(), Bm, 0.01)
+
+    def barrier():
+        if dist_on:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0w, t0 = time.time(), time.perf_counter()
+    loss = eng.learn(src_x, src_y, idx[:, :Bm * K].contiguous(), Bm, 0.01)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.window = (t0w, time.time())
+    clocks = sampler.stop()
+    (t_ms,) = parallel.reduce_scalars([1e3 * wall], "max", device)
+    if rank == 0:
+        line = {"metric": "dynamics mini-batches/s (7 members x 256 rows, hidden 200x4, members sharded)", "value": K / (t_ms * 1e-3),
+                "unit": "mini-batches/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": "dynamics_training obs17 act6 E7 hidden200x4 batch256/member (configs[4])",
+                           "members_per_rank": eng.counts, "collectives_per_step": 0 if world == 1 else 1,
+                           "parallelism": "ensemble members sharded over the ranks; shared logvar bounds replicated"},
+                "clocks": clocks, "e2e": {"value": K / (t_ms * 1e-3), "unit": "mini-batches/s", "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0},
+                "gpu_launches": K * sum(p.n_launches for p, _ in eng._learn_plans.values()), "last_loss": float(loss)}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -573,7 +645,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--rows", type=int, default=N_DATA)
-    ap.add_argument("--workload", default="cql", choices=["cql", "edac_sharded"],
+    ap.add_argument("--workload", default="cql", choices=["cql", "edac_sharded", "dyn_sharded"],
                     help="cql = the headline (seed-parallel replicas); edac_sharded = BASELINE.json configs[2], ONE run with "
                          "the 10 critics sharded over the --gpus ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -592,6 +664,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     if args.workload == "edac_sharded":
         run_edac_sharded(args, rank, world, local_rank)
+        return
+    if args.workload == "dyn_sharded":
+        run_dyn_sharded(args, rank, world, local_rank)
         return
     run_engine(args, rank, world, local_rank)
 

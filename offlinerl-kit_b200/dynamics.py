@@ -39,14 +39,24 @@ class EnsembleDynamics(BaseDynamics):
             raise ValueError(f"unknown uncertainty_mode {uncertainty_mode!r}")       # ensemble_dynamics.py:71-72
         self._engine = None
         self._scaler_dev = None
+        self._shard = None
         self.rng = "numpy"       # "numpy": the reference's two host draws per step; "device": Philox on the GPU
+
+    def shard_members(self, rank: int, world: int, comm=None) -> None:
+        """Train only members partition_members(E, world)[rank] on this rank (BASELINE.json configs[4]: "members sharded over
+        8 x B200").  Data, seeds and the model's initial state must be replicated on every rank.  ``train`` then exchanges
+        the shared log-variance bounds' gradients per mini-batch and the holdout losses per epoch, and ends with every rank
+        holding the whole trained ensemble (rollouts need all members).  ``comm``: engine.edac_sharded.NcclComm()."""
+        if self._engine is not None:
+            raise RuntimeError("shard_members must be called before the engine is first used")
+        self._shard = (int(rank), int(world), comm)
 
     # ------------------------------------------------------------------ engine plumbing
     @property
     def engine(self):
         if self._engine is None:
             from .engine.dynamics import DynamicsEngine
-            self._engine = DynamicsEngine(self.model, self.optim)
+            self._engine = DynamicsEngine(self.model, self.optim, shard=self._shard)
         return self._engine
 
     def _dev(self, a, dtype=torch.float32) -> torch.Tensor:
@@ -153,6 +163,8 @@ class EnsembleDynamics(BaseDynamics):
                     improved.append(i)
                     holdout_losses[i] = new
             if improved:
+                if self._shard is not None:
+                    self.engine.write_back()        # the own members' trained rows -> the full model, for update_save
                 self.model.update_save(improved)
                 cnt = 0
             else:
@@ -164,6 +176,14 @@ class EnsembleDynamics(BaseDynamics):
         elites = self.select_elites(holdout_losses)
         self.model.set_elites(elites)
         self.model.load_save()
+        if self._shard is not None:
+            # every rank contributes the best snapshot of ITS members; afterwards all ranks hold the whole ensemble and the
+            # next engine (validation, rollouts) is an ordinary unsharded one
+            eng = self.engine
+            eng.read_back()
+            eng.gather_all()
+            eng.rt.sync()
+            self._engine, self._shard = None, None
         self.save(logger.model_dir)
         self.model.eval()
         logger.log("elites:{} , holdout loss: {}".format(elites, (np.sort(holdout_losses)[:self.model.num_elites]).mean()))

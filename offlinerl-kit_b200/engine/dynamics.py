@@ -77,11 +77,34 @@ def emit_dyn_forward(rt: Runtime, plan: Plan, run: DynRun, X: Callable[[int], Ma
 
 
 class DynamicsEngine(Learner):
-    def __init__(self, model, optim):
+    def __init__(self, model, optim, shard=None):
+        """shard = (rank, world, comm): train only members partition_members(E, world)[rank] (BASELINE.json configs[4],
+        "members sharded over 8 x B200").  The loss is a sum over members
+        (ensemble_dynamics.py:197-199), so the only coupling is the shared max_logvar / min_logvar: every mini-batch the
+        ranks all-gather their partial gradients of the two bounds (2 x (obs+1) floats, + the partial loss) and apply the
+        same Adam step to their replicas; ``validate`` all-gathers the per-member holdout losses (:145-168).  ``comm`` has
+        ``all_gather(send, recv)`` (engine/edac_sharded.py:NcclComm), or is None when a test drives the ranks in lockstep."""
         super().__init__(model.device)
         rt = self.rt
         self.model = model
         layers = list(model.backbones) + [model.output_layer]
+        self.E_all = int(layers[0].weight.shape[0])
+        self.shard = shard
+        self.rank, self.world, self.comm = (0, 1, None) if shard is None else shard
+        self.e0, self.e1, self.counts = 0, self.E_all, [self.E_all]
+        self._slices = []
+        if shard is not None:
+            from ..parallel import partition_members
+            from .edac_sharded import MemberSlice
+            parts = partition_members(self.E_all, self.world)
+            if min(len(p) for p in parts) == 0 or self.world > 8:
+                raise L.OrlkError(f"cannot shard {self.E_all} members over {self.world} ranks")
+            self.counts = [len(p) for p in parts]
+            self.e0, self.e1 = parts[self.rank][0], parts[self.rank][-1] + 1
+            self._slices = [MemberSlice(lay, self.e0, self.e1) for lay in layers]
+            for sl, lay in zip(self._slices, layers):
+                sl.weight_decay = float(getattr(lay, "weight_decay", 0.0))
+            layers = self._slices
         self.ps = ParamSet.from_ensemble(rt, "dynamics", layers,
                                          extra={"max_logvar": model.max_logvar, "min_logvar": model.min_logvar})
         self.E = self.ps.G
@@ -184,40 +207,133 @@ class DynamicsEngine(Learner):
         for l in range(nl):
             descs[k].wd = self.wd[l]
             k += 2
-        for name, gbuf in (("max_logvar", self.dmax), ("min_logvar", self.dmin)):
-            o = ps.extra[name][0]
-            descs.append(AdamT(p=ps._ptr(ps.P, o), n=D, group=self.g, m=ps._ptr(ps.Mo, o), v=ps._ptr(ps.Vo, o),
-                               grad=gbuf.data_ptr(), g_splits=1, g_split_stride=D))
-        plan.add("D.adam", rt.adam(descs, self.groups_ptr))
         gp = C.c_void_p(self.groups_ptr)
-        plan.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
+        plan2 = send = recv = None
+        if self.shard is None:
+            for name, gbuf in (("max_logvar", self.dmax), ("min_logvar", self.dmin)):
+                o = ps.extra[name][0]
+                descs.append(AdamT(p=ps._ptr(ps.P, o), n=D, group=self.g, m=ps._ptr(ps.Mo, o), v=ps._ptr(ps.Vo, o),
+                                   grad=gbuf.data_ptr(), g_splits=1, g_split_stride=D))
+            plan.add("D.adam", rt.adam(descs, self.groups_ptr))
+            plan.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
+        else:
+            # members: Adam on the own slice.  Shared bounds: partial gradients (and the partial loss) go to the exchange;
+            # after the all-gather the second segment sums the `world` partials in rank order inside the Adam launch
+            # (g_splits = world: the same fixed-order reduction as split-K partials) -- identical on every rank.
+            blk = 2 * D + 4
+            send, recv = rt.zeros(blk), rt.zeros(self.world * blk)
+            plan.add("D.adam", rt.adam(descs, self.groups_ptr))
+            for src, off, n in ((self.dmax, 0, D), (self.dmin, D, D), (self.loss_dev, 2 * D, 1)):
+                args = (send.data_ptr() + 4 * off, src.data_ptr(), 4 * n)
+                plan.add("X.stage", lambda args=args: L.call("orlk_memcpy_d2d_async", *args, rt.cur))
+            plan2 = Plan(rt, f"dyn.learn{Bn}.bounds")
+            bdescs = []
+            for name, off in (("max_logvar", 0), ("min_logvar", D)):
+                o = ps.extra[name][0]
+                bdescs.append(AdamT(p=ps._ptr(ps.P, o), n=D, group=self.g, m=ps._ptr(ps.Mo, o), v=ps._ptr(ps.Vo, o),
+                                    grad=recv.data_ptr() + 4 * off, g_splits=self.world, g_split_stride=blk))
+            plan2.add("D.adam_bounds", rt.adam(bdescs, self.groups_ptr))
+            plan2.add("step_end", lambda: L.call("orlk_step_end", gp, 1 << self.g, None, rt.cur))
+            plan2.keep += [send, recv]
         plan.keep += [gb, run, X, Y, nll_scratch]
-        self._learn_plans[Bn] = (plan, dict(X=X, Y=Y, run=run, state=state))
+        self._learn_plans[Bn] = (plan, dict(X=X, Y=Y, run=run, state=state, plan2=plan2, send=send, recv=recv, blk=2 * D + 4))
         return self._learn_plans[Bn]
+
+    def learn_batch_begin(self, src_x, src_y, idx, r0: int, Bn: int, coef: float):
+        """Gather mini-batch [r0, r0+Bn) of the own members and run the step up to the exchange (all of it when the
+        ensemble is not sharded).  idx is the FULL [E_all, n] bootstrap index matrix."""
+        rt, E = self.rt, self.E
+        plan, st = self._learn_plan(Bn)
+        # the direct coef * (sum max_logvar - sum min_logvar) term belongs to the ensemble, not to a member: rank 0 carries it
+        eff = float(coef) if self.rank == 0 else 0.0
+        X, Y = st["X"], st["Y"]
+        iptr = idx.data_ptr() + idx.element_size() * self.e0 * idx.stride(0)
+        L.call("orlk_gather_rows", src_x.data_ptr(), src_x.stride(0), self.in_dim, iptr, idx.stride(0), r0, E, Bn,
+               X.data_ptr(), self.in_dim, Bn * self.in_dim, rt.cur)
+        L.call("orlk_gather_rows", src_y.data_ptr(), src_y.stride(0), self.D, iptr, idx.stride(0), r0, E, Bn,
+               Y.data_ptr(), self.D, Bn * self.D, rt.cur)
+        if self.use_graph and st.get("graph_coef", eff) == eff:
+            st["state"]["coef"] = eff
+            st["graph_coef"] = eff      # (the logvar coefficient is baked into the captured launch arguments)
+            plan.launch()
+        else:
+            st["state"]["coef"] = eff
+            plan.run_eager()
+        return st
+
+    def learn_batch_end(self, st, losses: torch.Tensor, b: int) -> None:
+        """Behind the exchange: the shared bounds' Adam step from the gathered partial gradients; record the loss(es)."""
+        rt = self.rt
+        if self.shard is None:
+            L.call("orlk_memcpy_d2d_async", losses.data_ptr() + 4 * b, self.loss_dev.data_ptr(), 4, rt.cur)
+            return
+        plan2 = st["plan2"]
+        plan2.launch() if self.use_graph else plan2.run_eager()
+        recv, blk, D2 = st["recv"], st["blk"], 2 * self.D
+        for r in range(self.world):     # partial losses of all ranks (summed on the host at the end of the pass)
+            L.call("orlk_memcpy_d2d_async", losses.data_ptr() + 4 * (b * self.world + r), recv.data_ptr() + 4 * (r * blk + D2), 4,
+                   rt.cur)
 
     def learn(self, src_x: torch.Tensor, src_y: torch.Tensor, idx: torch.Tensor, batch_size: int, coef: float) -> float:
         """One pass over idx [E, n] (row ids into src_x [N,in] / src_y [N,D]) in mini-batches of ``batch_size``."""
-        rt, E = self.rt, self.E
         n = idx.shape[1]
         nb = -(-n // batch_size)
-        losses = torch.zeros(nb, dtype=torch.float32, device=self.dev)
+        losses = torch.zeros(nb * self.world, dtype=torch.float32, device=self.dev)
         self.sync_lr()
+        if self.shard is not None and self.comm is None:
+            raise L.OrlkError("a sharded DynamicsEngine needs a communicator (or a lockstep driver calling learn_batch_*)")
         for b in range(nb):
             r0 = b * batch_size
-            Bn = min(batch_size, n - r0)
-            plan, st = self._learn_plan(Bn)
-            st["state"]["coef"] = float(coef)
-            X, Y = st["X"], st["Y"]
-            L.call("orlk_gather_rows", src_x.data_ptr(), src_x.stride(0), self.in_dim, idx.data_ptr(), idx.stride(0), r0, E, Bn,
-                   X.data_ptr(), self.in_dim, Bn * self.in_dim, rt.cur)
-            L.call("orlk_gather_rows", src_y.data_ptr(), src_y.stride(0), self.D, idx.data_ptr(), idx.stride(0), r0, E, Bn,
-                   Y.data_ptr(), self.D, Bn * self.D, rt.cur)
-            if self.use_graph and abs(coef - 0.01) < 1e-12:
-                plan.launch()
-            else:
-                plan.run_eager()       # (a non-default logvar coefficient is a launch argument, not graph state)
-            L.call("orlk_memcpy_d2d_async", losses.data_ptr() + 4 * b, self.loss_dev.data_ptr(), 4, rt.cur)
-        return float(losses.cpu().numpy().astype(np.float64).mean())
+            st = self.learn_batch_begin(src_x, src_y, idx, r0, min(batch_size, n - r0), coef)
+            if self.shard is not None:
+                self.comm.all_gather(st["send"], st["recv"])
+            self.learn_batch_end(st, losses, b)
+        return self.pass_loss(losses, nb)
+
+    def pass_loss(self, losses: torch.Tensor, nb: int) -> float:
+        return float(losses.cpu().numpy().astype(np.float64).reshape(nb, self.world).sum(1).mean())
+
+    # ------------------------------------------------------------------ member-sharded bookkeeping
+    def write_back(self) -> None:
+        for s in self._slices:
+            s.write_back()
+
+    @torch.no_grad()
+    def read_back(self) -> None:
+        """The full model's rows of the own members -> the slices (after ``model.load_save()``)."""
+        for s in self._slices:
+            lay = s.src[0]
+            s.weight.data.copy_(lay.weight.data[s.e0:s.e1])
+            s.bias.data.copy_(lay.bias.data[s.e0:s.e1])
+
+    def gather_members(self, local: torch.Tensor) -> torch.Tensor:
+        """[E_r, ...] per rank -> [E_all, ...] on every rank (one padded all-gather)."""
+        if self.shard is None:
+            return local
+        e_max = max(self.counts)
+        per = local[0].numel()
+        send = torch.zeros(e_max * per, dtype=local.dtype, device=local.device)
+        send[:local.numel()].copy_(local.reshape(-1))
+        recv = torch.empty(self.world * e_max * per, dtype=local.dtype, device=local.device)
+        self.comm.all_gather(send, recv)
+        parts = [recv[r * e_max * per:r * e_max * per + c * per] for r, c in enumerate(self.counts)]
+        return torch.cat(parts).view((self.E_all,) + tuple(local.shape[1:]))
+
+    @torch.no_grad()
+    def gather_all(self) -> None:
+        """Every rank's full model gets every member's current weights (and saved_* copies) from its owner."""
+        self.write_back()
+        if self.shard is None or self.comm is None:
+            return
+        self.rt.sync()
+        for s in self._slices:
+            lay = s.src[0]
+            for name in ("weight", "bias"):
+                full = self.gather_members(getattr(s, name).data)
+                getattr(lay, name).data.copy_(full)
+                saved = getattr(lay, "saved_" + name, None)
+                if saved is not None:
+                    saved.data.copy_(full)
 
     # ------------------------------------------------------------------ inference
     def _forward(self, x: torch.Tensor) -> DynRun:
@@ -245,10 +361,19 @@ class DynamicsEngine(Learner):
             emit_dyn_forward(self.rt, plan, run, lambda e: xm, "F", tc_passes=self.tc_passes)
             self._fwd_runs[S] = (run, plan, xbuf)
 
-    def validate(self, x: torch.Tensor, y: torch.Tensor) -> List[float]:
+    def validate_local(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         run = self._forward(x)
         mse = torch.zeros(self.E, dtype=torch.float32, device=self.dev)
         L.call("orlk_dyn_val_mse", run.OUT.data_ptr(), y.data_ptr(), self.E, x.shape[0], self.D, mse.data_ptr(), self.rt.cur)
+        return mse
+
+    def validate(self, x: torch.Tensor, y: torch.Tensor) -> List[float]:
+        """Per-member holdout MSE of ALL members (sharded: the own members' losses all-gathered, ensemble_dynamics.py:145)."""
+        mse = self.validate_local(x, y)
+        if self.shard is not None:
+            if self.comm is None:
+                raise L.OrlkError("a sharded DynamicsEngine needs a communicator (or a lockstep driver calling validate_local)")
+            mse = self.gather_members(mse)
         return list(mse.cpu().numpy())
 
     def imagine(self, obs: torch.Tensor, act: torch.Tensor, mu: torch.Tensor, sd: torch.Tensor, term_kind: int,
