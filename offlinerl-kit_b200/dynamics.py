@@ -40,7 +40,11 @@ class EnsembleDynamics(BaseDynamics):
         self._engine = None
         self._scaler_dev = None
         self._shard = None
-        self.rng = "numpy"       # "numpy": the reference's two host draws per step; "device": Philox on the GPU
+        # Noise of the imagination step when the caller injects none: "device" = Philox on the GPU (default);
+        # "numpy" = the reference's two host draws per step, np.random.normal(size=[E, S, D]) float64 and
+        # np.random.choice(elites, S) (ensemble_dynamics.py:48, dynamics_module.py:118) -- the same stream as the
+        # reference under the same np.random.seed (parity tests), but 220 ms of host time per 50 000-state step.
+        self.rng = os.environ.get("ORLK_DYN_RNG", "device")
 
     def shard_members(self, rank: int, world: int, comm=None) -> None:
         """Train only members partition_members(E, world)[rank] on this rank (BASELINE.json configs[4]: "members sharded over
@@ -74,8 +78,9 @@ class EnsembleDynamics(BaseDynamics):
         return c[2], c[3]
 
     # ------------------------------------------------------------------ imagination
-    def step_device(self, obs: torch.Tensor, act: torch.Tensor, noise64=None, midx=None):
-        """One imagined step on device tensors -> (next_obs, reward, terminal(uint8), raw_reward, penalty) on the device."""
+    def step_device(self, obs: torch.Tensor, act: torch.Tensor, noise64=None, midx=None, out=None, noise_buf=None):
+        """One imagined step on device tensors -> (next_obs, reward, terminal(uint8), raw_reward, penalty) on the device.
+        ``out`` / ``noise_buf`` [S*D + S]: pre-allocated results / Philox scratch (engine/rollout.py's sync-free loop)."""
         eng = self.engine
         S = obs.shape[0]
         mu, sd = self._scaler_tensors()
@@ -86,15 +91,22 @@ class EnsembleDynamics(BaseDynamics):
                 noise64 = self._dev(np.random.normal(size=(eng.E, S, eng.D)), torch.float64)
                 midx = self._dev(self.model.random_elite_idxs(S), torch.int32)
             else:
-                buf = torch.empty(S * eng.D + S, dtype=torch.float32, device=eng.dev)
+                buf = noise_buf if noise_buf is not None else torch.empty(S * eng.D + S, dtype=torch.float32, device=eng.dev)
                 L.call("orlk_philox_fill", buf.data_ptr(), S * eng.D, S, 0.0, 1.0, 0x5eed, eng.philox_counter.data_ptr(), None,
                        eng.rt.cur)
                 L.call("orlk_step_end", eng.groups_ptr, 0, eng.philox_counter.data_ptr(), eng.rt.cur)
                 n32, pick = buf[:S * eng.D], buf[S * eng.D:]
-                elites = self.model.elites.data.to(device=eng.dev, dtype=torch.int32)
-        out = eng.imagine(obs, act, mu, sd, 3 if kind is None else kind, self._penalty_coef, noise64, midx, n32, pick, elites,
-                          UNCERTAINTY_MODES[self._uncertainty_mode])
-        return out
+                elites = self._elites_dev()
+        return eng.imagine(obs, act, mu, sd, 3 if kind is None else kind, self._penalty_coef, noise64, midx, n32, pick, elites,
+                           UNCERTAINTY_MODES[self._uncertainty_mode], out=out)
+
+    def _elites_dev(self) -> torch.Tensor:
+        """int32 device copy of model.elites (re-made when set_elites replaced the parameter)."""
+        el = self.model.elites
+        c = getattr(self, "_elites_cache", None)
+        if c is None or c[0] is not el or c[1] != el._version:
+            self._elites_cache = c = (el, el._version, el.data.to(device=self.engine.dev, dtype=torch.int32))
+        return c[2]
 
     @torch.no_grad()
     def step(self, obs: np.ndarray, action: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, Dict]:

@@ -379,8 +379,10 @@ class DynamicsEngine(Learner):
     def imagine(self, obs: torch.Tensor, act: torch.Tensor, mu: torch.Tensor, sd: torch.Tensor, term_kind: int,
                 penalty_coef: float, noise64: Optional[torch.Tensor], midx: Optional[torch.Tensor],
                 noise32: Optional[torch.Tensor], pick_u: Optional[torch.Tensor], elites: Optional[torch.Tensor],
-                uncertainty_mode: int = 0):
-        """One imagined transition for S device-resident states; returns device tensors."""
+                uncertainty_mode: int = 0, out=None):
+        """One imagined transition for S device-resident states; returns device tensors.
+        ``out`` = (next_obs [S,O], reward [S,1], terminal uint8 [S,1], raw_reward [S,1], penalty [S,1]): write there instead
+        of allocating (the sync-free rollout loop pre-allocates the whole horizon)."""
         rt, S, O = self.rt, obs.shape[0], obs.shape[1]
         A = act.shape[1]
         self._forward_alloc(S)
@@ -388,9 +390,12 @@ class DynamicsEngine(Learner):
         L.call("orlk_dyn_input", obs.data_ptr(), obs.stride(0), act.data_ptr(), act.stride(0), mu.data_ptr(), sd.data_ptr(), S,
                O, A, xbuf.data_ptr(), xbuf.stride(0), rt.cur)
         run = self._forward(xbuf)
-        nobs = torch.empty(S, O, dtype=torch.float32, device=self.dev)
-        rew, raw, pen = (torch.empty(S, 1, dtype=torch.float32, device=self.dev) for _ in range(3))
-        term = torch.empty(S, 1, dtype=torch.uint8, device=self.dev)
+        if out is not None:
+            nobs, rew, term, raw, pen = out
+        else:
+            nobs = torch.empty(S, O, dtype=torch.float32, device=self.dev)
+            rew, raw, pen = (torch.empty(S, 1, dtype=torch.float32, device=self.dev) for _ in range(3))
+            term = torch.empty(S, 1, dtype=torch.uint8, device=self.dev)
         ptr = lambda t: t.data_ptr() if t is not None else None
         L.call("orlk_dyn_step", run.OUT.data_ptr(), self.E, S, self.D, self.ps.extra_ptr("max_logvar"),
                self.ps.extra_ptr("min_logvar"), obs.data_ptr(), obs.stride(0), ptr(noise64), ptr(midx), ptr(noise32), ptr(pick_u),

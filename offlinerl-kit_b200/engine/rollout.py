@@ -48,6 +48,97 @@ class RolloutEngine:
             self._plans[S] = (run, plan, obs)
         return self._plans[S]
 
+    # ------------------------------------------------------------------ the default path: no host round trip per step
+    def _workspace(self, S: int, h: int):
+        key = (S, h)
+        ws = self.__dict__.setdefault("_ws", {})
+        if key not in ws:
+            if len(ws) > 4:
+                ws.clear()
+            dev, O, A = self.dev, self.O, self.A
+            D = self.dyn.engine.D
+            f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+            ws[key] = dict(OBS=f(h + 1, S, O), ACT=f(h, S, A), REW=f(h, S, 1), RAW=f(S, 1), PEN=f(S, 1),
+                           TERM=torch.empty(h, S, 1, dtype=torch.uint8, device=dev),
+                           DEAD=torch.zeros(h + 1, S, dtype=torch.uint8, device=dev), EPS=f(S, A), NZ=f(S * D + S))
+        return ws[key]
+
+    def _run_async(self, init_obss: np.ndarray, length: int, device_out: bool):
+        """mopo.py:45-79 without a device->host round trip per imagined step.  The reference compacts the survivors after
+        every step, which needs the survivor count on the host (a stream sync + a 4-byte read per step, and step buffers of
+        a new size each time).  Here every step runs on ALL start rows into buffers pre-allocated for the whole horizon,
+        with a per-row dead flag (dead[t+1] = dead[t] | terminal[t]); rows that are dead at step t are dropped when the
+        step's transitions are assembled at the end -- a stable selection, so the rows of step t+1 are exactly the
+        surviving rows of step t, in order, as in the reference.  While nothing terminates the result is bit-identical to the
+        per-step loop (same Philox draws); once rows die the two consume different draws for the later steps (this loop
+        also draws for dead rows), i.e. they are equal in distribution (tests/test_gpu_dynamics.py).  The host waits once,
+        for the dead counts.  (Dead rows still cost arithmetic: 0 % for halfcheetah, ~15 % for walker2d.)"""
+        rt, O, A = self.rt, self.O, self.A
+        dyn = self.dyn
+        t_start = time.perf_counter()
+        S, h = int(len(init_obss)), int(length)
+        ws = self._workspace(S, h)
+        OBS, ACT, REW, TERM, DEAD = ws["OBS"], ws["ACT"], ws["REW"], ws["TERM"], ws["DEAD"]
+        OBS[0].copy_(torch.as_tensor(init_obss, dtype=torch.float32), non_blocking=False)
+        DEAD[0].zero_()
+        for t in range(h):
+            cur = OBS[t]
+            if self.uniform is not None:        # combo.py:81-86: a ~ U(low, high), no actor pass
+                L.call("orlk_philox_fill", ACT[t].data_ptr(), 0, S * A, self.uniform[0], self.uniform[1], 0xac7,
+                       self.philox_counter.data_ptr(), None, rt.cur)
+                L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
+            else:
+                run, plan, obs_buf = self._actor_plan(S)
+                obs_buf.copy_(cur)
+                plan.run_eager()
+                eps = ws["EPS"]
+                L.call("orlk_philox_fill", eps.data_ptr(), S * A, 0, 0.0, 1.0, 0xac7, self.philox_counter.data_ptr(), None, rt.cur)
+                L.call("orlk_step_end", dyn.engine.groups_ptr, 0, self.philox_counter.data_ptr(), rt.cur)
+                L.call("orlk_tanh_gauss_sample", run.out.data_ptr(), 2 * A, 0, 1, eps.data_ptr(), S, A, ACT[t].data_ptr(), A, None,
+                       None, 0, 0, None, 0, rt.cur)
+            dyn.step_device(cur, ACT[t], out=(OBS[t + 1], REW[t], TERM[t], ws["RAW"], ws["PEN"]), noise_buf=ws["NZ"])
+            torch.bitwise_or(DEAD[t], TERM[t].view(-1), out=DEAD[t + 1])
+        # ---- assemble: the only host wait of the loop
+        n_dead = DEAD[:h].sum(dim=1, dtype=torch.int64).cpu().tolist()
+        t_loop = time.perf_counter()
+        if sum(n_dead) == 0:
+            res = {"obss": OBS[:h].reshape(h * S, O), "next_obss": OBS[1:h + 1].reshape(h * S, O), "actions": ACT.reshape(h * S, A),
+                   "rewards": REW.reshape(h * S, 1), "terminals": TERM.reshape(h * S, 1)}
+            if device_out:
+                res = {k: v.clone() for k, v in res.items()}          # the workspace is reused by the next rollout
+        else:
+            parts = {k: [] for k in ("obss", "next_obss", "actions", "rewards", "terminals")}
+            for t in range(h):
+                if n_dead[t] == S:
+                    break                       # nobody left: the reference stops here (mopo.py:71-72)
+                srcs = (OBS[t], OBS[t + 1], ACT[t], REW[t], TERM[t])
+                if n_dead[t] == 0:
+                    for k, v in zip(parts, srcs):
+                        parts[k].append(v)
+                else:
+                    keep = (DEAD[t] == 0).nonzero().squeeze(1)
+                    for k, v in zip(parts, srcs):
+                        parts[k].append(v.index_select(0, keep))
+            res = {k: torch.cat(v, 0) for k, v in parts.items()}
+        n_total = int(res["obss"].shape[0])
+        r_mean = float(res["rewards"].double().mean().item()) if n_total else 0.0
+        if device_out:
+            self.last_timing = {"loop_ms": 1e3 * (t_loop - t_start), "export_ms": 0.0}
+            return res, {"num_transitions": n_total, "reward_mean": r_mean}
+        # export through pinned host memory (torch's caching host allocator recycles the blocks between rollouts; the
+        # arrays handed out keep their block alive, so they are never overwritten by a later call)
+        out = {}
+        for k, v in res.items():
+            hbuf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            hbuf.copy_(v, non_blocking=True)
+            out[k] = hbuf
+        rt.sync()
+        torch.cuda.current_stream(self.dev).synchronize()
+        out = {k: v.numpy() for k, v in out.items()}
+        out["terminals"] = out["terminals"].astype(bool)
+        self.last_timing = {"loop_ms": 1e3 * (t_loop - t_start), "export_ms": 1e3 * (time.perf_counter() - t_loop)}
+        return out, {"num_transitions": n_total, "reward_mean": r_mean}
+
     def run(self, init_obss: np.ndarray, length: int, noise: Optional[Dict[str, List[np.ndarray]]] = None,
             device_out: bool = False):
         """device_out: return the transitions as device tensors (terminals uint8) instead of the reference's NumPy
@@ -64,6 +155,8 @@ class RolloutEngine:
             self.tc_passes = eng.tc_passes
             self._plans.clear()
         self.actor_ps.refresh_wt()
+        if noise is None and dyn.rng == "device" and not getattr(self, "sync_loop", False):
+            return self._run_async(init_obss, length, device_out)
         t_start = time.perf_counter()
         cur = torch.as_tensor(init_obss, dtype=torch.float32).to(self.dev).contiguous()
         outs = {k: [] for k in ("obss", "next_obss", "actions", "rewards", "terminals")}

@@ -124,7 +124,7 @@ def _gather_ragged(arr, device) -> "np.ndarray":
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0).cpu().numpy()
 
 
-def _gather_packed(local, device):
+def _gather_packed(local, device, to_host: bool = True):
     """The same gather for a dict of DEVICE tensors with a common first dimension: the columns are packed into one
     [n, W] fp32 matrix, so the whole exchange is one size all-gather, one padded all-gather and one device-to-host copy per array
     (uint8 / bool columns survive the round trip through fp32 exactly)."""
@@ -144,6 +144,13 @@ def _gather_packed(local, device):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     full = torch.cat([p[:v] for p, v in zip(parts, sizes)], 0)
+    if not to_host:             # device tensors: what ReplayBuffer.add_batch packs straight into its device row table
+        out, c0 = {}, 0
+        for k, w in zip(keys, widths):
+            a = full[:, c0:c0 + w]
+            out[k] = (a != 0).to(local[k].dtype) if local[k].dtype in (torch.uint8, torch.bool) else a.contiguous()
+            c0 += w
+        return out
     # split on the device and copy each array out on its own: host blocks of <= 32 MB are recycled by the allocator,
     # one 42 MB block would be mmap-ed and page-faulted afresh on every call
     out, c0 = {}, 0
@@ -156,7 +163,8 @@ def _gather_packed(local, device):
     return out
 
 
-def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cpu", device_out: bool = False):
+def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cpu", device_out: bool = False,
+                          device_result: bool = False):
     """``MOPOPolicy.rollout`` (policy/model_based/mopo.py:45-79) with the start states split over the ranks.
 
     Every rank holds the full dynamics ensemble and the actor (replicated after training), imagines the whole horizon
@@ -165,15 +173,19 @@ def rollout_state_sharded(rollout_fn, init_obss, rollout_length: int, device="cp
     the single-GPU rollout.  The random streams differ per rank, so the result is distributed like - not bit-equal to -
     a single-GPU rollout of all states.  Single process: plain call.
     ``device_out``: ``rollout_fn`` takes ``device_out=True`` and then returns device tensors (MOPOPolicy / COMBOPolicy
-    do); the transitions are exchanged straight from device memory and reach the host once."""
+    do); the transitions are exchanged straight from device memory and reach the host once.
+    ``device_result`` (with ``device_out``): return the gathered transitions as DEVICE tensors -- nothing goes through the
+    host; ``ReplayBuffer.add_batch`` packs them straight into the fake buffer's device row table."""
     import numpy as np
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if device_out and device_result:
+            return rollout_fn(init_obss, rollout_length, device_out=True)
         return rollout_fn(init_obss, rollout_length)
     rank, world = dist.get_rank(), dist.get_world_size()
     lo, hi = shard_rows(len(init_obss), rank, world)
     if device_out:
         local, info = rollout_fn(init_obss[lo:hi], rollout_length, device_out=True)
-        out = _gather_packed(local, device)
+        out = _gather_packed(local, device, to_host=not device_result)
     else:
         local, info = rollout_fn(init_obss[lo:hi], rollout_length)
         out = {k: _gather_ragged(v, device) for k, v in local.items()}

@@ -40,7 +40,7 @@ def main():
     dyn = EnsembleDynamics(model, torch.optim.Adam(model.parameters(), lr=1e-3),
                            StandardScaler(np.zeros((1, O + A), np.float32), np.ones((1, O + A), np.float32)),
                            T.termination_fn_halfcheetah, penalty_coef=0.5)
-    dyn.rng = "device"
+    assert dyn.rng == "device"                            # the default since round 2
     bb = MLP(O, [256, 256])
     actor = ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), dev)
     c1, c2 = Critic(MLP(O + A, [256, 256]), dev), Critic(MLP(O + A, [256, 256]), dev)
@@ -48,8 +48,14 @@ def main():
     pol = MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2)
     init = np.random.default_rng(1).standard_normal((S, O), dtype=np.float32)
 
+    to_host = os.environ.get("ROLLOUT_TO_HOST", "0") == "1"
+
     def run():
-        return parallel.rollout_state_sharded(pol.rollout, init, H, device=dev, device_out=True)
+        # default: the gathered transitions stay on the device (what ReplayBuffer.add_batch takes); ROLLOUT_TO_HOST=1
+        # adds the export to NumPy arrays in the reference's format
+        if to_host and not dist_on:
+            return pol.rollout(init, H)
+        return parallel.rollout_state_sharded(pol.rollout, init, H, device=dev, device_out=True, device_result=not to_host)
 
     for _ in range(3):
         out, info = run()
@@ -67,11 +73,12 @@ def main():
         print(json.dumps({"metric": "MOPO imagined transitions/s (state-sharded rollout, all-gather included)",
                           "value": info["num_transitions"] / (ms_max * 1e-3), "unit": "transitions/s", "n_gpus": world,
                           "ms_per_rollout": ms_max, "transitions_per_rollout": info["num_transitions"], "scaling": "strong",
-                          "last_call_split_ms": getattr(pol._roll, "last_timing", None),
+                          "last_call_split_ms": getattr(pol._roll, "last_timing", None), "result": "host numpy" if to_host else "device tensors",
                           "config": {"workload": "mopo_rollout E7 hidden200x4 S50000 H5 hc"}}))
     if dist_on:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

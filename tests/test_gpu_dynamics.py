@@ -58,7 +58,9 @@ def test_dynamics_learn_validate_step(name):
     assert_stats_close(sd, g.group("stats"), tol=TOL, lr_atol=2.5 * m["lr"])
     val = dyn.validate(xs[:m["holdout"]], y[:m["holdout"]])
     assert rel_err(val, g["val"]) < TOL
-    # imagination step: the facade consumes np.random exactly like the reference (normal then choice)
+    # imagination step: in "numpy" mode the facade consumes np.random exactly like the reference (normal then choice)
+    assert dyn.rng == "device"          # the default draws on the GPU
+    dyn.rng = "numpy"
     np.random.seed(11)
     nobs, rew, term, info = dyn.step(g["step_obs"], g["step_act"])
     assert rel_err(nobs, g["step_next_obs"]) < TOL and rel_err(rew, g["step_reward"]) < TOL
@@ -299,3 +301,68 @@ def test_rollout_config5_size_matches_reference(name):
         assert rel_err(got[:3], ref[:3]) < 2e-4, (k, got[:3], ref[:3])
         assert rel_err(got[3:], ref[3:]) < 2e-4, k
     assert info["reward_mean"] == pytest.approx(float(g["reward_mean"]), rel=2e-4)
+
+
+def _cfg5_policy(name):
+    from offlinerlkit_b200.nets import MLP
+    from offlinerlkit_b200.modules import ActorProb, Critic, TanhDiagGaussian
+    from offlinerlkit_b200.policy import MOPOPolicy
+    g = Golden(name)
+    m = g.meta
+    O, A, hid = m["O"], m["A"], m["hidden"]
+    dyn_state, actor_state, mu, std, init = cfg5_setup(m)
+    dyn = _build_dynamics(m, dyn_state, mu, std, m["term"])
+    dyn.model.set_elites(m["elites"])
+    bb = MLP(O, hid)
+    actor = ActorProb(bb, TanhDiagGaussian(bb.output_dim, A, unbounded=True, conditioned_sigma=True), DEV)
+    actor.load_state_dict({k[len("actor."):]: v for k, v in actor_state.items()})
+    c1, c2 = Critic(MLP(O + A, hid), DEV), Critic(MLP(O + A, hid), DEV)
+    adam = lambda mod: torch.optim.Adam(mod.parameters(), lr=1e-4)
+    return MOPOPolicy(dyn, actor, c1, c2, adam(actor), adam(c1), adam(c2), alpha=0.2), init, m
+
+
+def test_default_rollout_has_no_per_step_sync_and_equals_the_per_step_loop():
+    """The default rollout (device noise, nothing injected) runs the horizon without a host round trip per step.  With no
+    terminations (halfcheetah) it must equal the per-step loop bit for bit -- both draw the same Philox numbers."""
+    outs = []
+    for sync in (False, True):
+        pol, init, m = _cfg5_policy("rollout_cfg5_hc")
+        assert pol.dynamics.rng == "device"
+        out, info = pol.rollout(init[:6000], m["horizon"])          # the first call creates the engine
+        pol._roll.sync_loop = sync
+        pol._roll.philox_counter.zero_()
+        pol.dynamics.engine.philox_counter.zero_()
+        out, info = pol.rollout(init[:6000], m["horizon"])
+        assert info["num_transitions"] == 6000 * m["horizon"] and out["terminals"].dtype == bool
+        outs.append(out)
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_default_rollout_drops_dead_rows_like_the_reference():
+    """walker2d-style terminations: rows that terminate at step t must not appear at step t+1, the survivors keep their
+    order (mopo.py:69-73), and every array has one row per transition."""
+    pol, init, m = _cfg5_policy("rollout_cfg5_walker")
+    S, h = 20000, m["horizon"]
+    out, info = pol.rollout(init[:S], h)
+    n = info["num_transitions"]
+    assert all(len(v) == n for v in out.values()) and n < S * h
+    r0, cnt, total = 0, S, 0
+    for t in range(h):
+        obs_t, nobs_t, term_t = out["obss"][r0:r0 + cnt], out["next_obss"][r0:r0 + cnt], out["terminals"][r0:r0 + cnt, 0]
+        if t == 0:
+            assert np.array_equal(obs_t, init[:S])
+        total += cnt
+        alive = ~term_t
+        nxt = int(alive.sum())
+        r0 += cnt
+        if t + 1 < h and nxt > 0:
+            assert np.array_equal(out["obss"][r0:r0 + nxt], nobs_t[alive]), t
+        cnt = nxt
+        if cnt == 0:
+            break
+    assert total == n
+    assert 0.005 < out["terminals"].mean() < 0.5
+    # device tensors on request (what MBPolicyTrainer hands to fake_buffer.add_batch)
+    dout, dinfo = pol.rollout(init[:S], h, device_out=True)
+    assert all(v.is_cuda for v in dout.values()) and dout["obss"].shape[0] == dinfo["num_transitions"]
