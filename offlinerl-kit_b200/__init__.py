@@ -8,3 +8,9 @@ There is no CPU fallback: using a compute entry point without the built library
 or without a CUDA device raises.
 """
 __version__ = "0.1.0"
+
+
+def attach(policy, buffer=None):
+    """Put the CUDA engine behind objects built by the unmodified reference (see attach.py)."""
+    from .attach import attach as _attach
+    return _attach(policy, buffer)

@@ -11,11 +11,15 @@ from typing import Dict, Iterable, Optional
 ROOT_DIR = "log"
 
 
-def make_log_dirs(task_name: str, algo_name: str, seed: int, args: Dict, record_params: Optional[Iterable[str]] = None) -> str:
+def make_log_dirs(task_name: str, algo_name: str, seed, args: Dict, part: Optional[str] = None,
+                  record_params: Optional[Iterable[str]] = None) -> str:
+    """utils/logger.py:346-365: log/<task>/<algo>[&param=value...]/[part/]timestamp_<stamp>&<seed>."""
     if record_params is not None:
         algo_name += "".join(f"&{p}={args[p]}" for p in record_params)
     stamp = datetime.datetime.now().strftime("%y-%m%d-%H%M%S")
-    path = os.path.join(ROOT_DIR, task_name, algo_name, f"seed_{seed}&timestamp_{stamp}")
+    exp_name = f"timestamp_{stamp}&{seed}"
+    parts = [ROOT_DIR, task_name, algo_name] + ([part] if part is not None else []) + [exp_name]
+    path = os.path.join(*parts)
     os.makedirs(path, exist_ok=True)
     return path
 
@@ -91,7 +95,7 @@ class Logger:
         self._name2val.clear()
         self._name2cnt.clear()
 
-    def log(self, s: str, level=None) -> None:
+    def log(self, s: str, level=20) -> None:      # 20 = INFO, the reference's default (utils/logger.py:311)
         if not self.quiet:
             print(s, flush=True)
 
