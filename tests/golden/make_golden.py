@@ -742,6 +742,52 @@ def gen_rollout_cfg5(name, term, S=50_000, horizon=5, O=17, A=6, hidden=(256, 25
     print("   counts per step:", counts, " terminals:", int(out["terminals"].sum()))
 
 
+def gen_cql_curve(name, n_steps=500, window=50, O=5, A=3, hidden=(32, 32, 32), B=64, N=4, n_data=4096):
+    """Loss-CURVE fixture (north_star: "loss-curve parity with the reference"): the reference's CQLPolicy trained for
+    `n_steps` on its own sampler and its own torch noise; stored are the per-window mean / std of every loss key for one
+    run and, as the yardstick of what "statistically the same curve" means, the window means of a SECOND reference run
+    that sees the same batches (same np.random seed) but other torch noise.  The engine draws Philox noise, so its curve
+    is compared with run A the way run B is."""
+    hidden = list(hidden)
+    data = make_dataset(n_data, O, A, seed=0)
+    hyper = dict(actor_lr=1e-4, critic_lr=3e-4, tau=0.005, gamma=0.99, cql_weight=5.0, temperature=1.0, max_q_backup=False,
+                 deterministic_backup=True, with_lagrange=False, lagrange_threshold=10.0, cql_alpha_lr=3e-4, num_repeat_actions=N)
+
+    def run(torch_seed):
+        torch.manual_seed(0)
+        actor, c1, c2 = build_sac_like(O, A, hidden)
+        for i, m in enumerate((actor, c1, c2)):
+            overwrite_params(m, 100 + i)
+        log_alpha = torch.zeros(1, requires_grad=True)
+        pol = CQLPolicy(actor, c1, c2, torch.optim.Adam(actor.parameters(), lr=hyper["actor_lr"]),
+                        torch.optim.Adam(c1.parameters(), lr=hyper["critic_lr"]), torch.optim.Adam(c2.parameters(), lr=hyper["critic_lr"]),
+                        action_space=gym.spaces.Box(-1, 1, (A,)), tau=hyper["tau"], gamma=hyper["gamma"],
+                        alpha=(-A, log_alpha, torch.optim.Adam([log_alpha], lr=1e-4)), cql_weight=hyper["cql_weight"],
+                        temperature=hyper["temperature"], max_q_backup=False, deterministic_backup=True, with_lagrange=False,
+                        lagrange_threshold=10.0, cql_alpha_lr=3e-4, num_repeart_actions=N)
+        pol.train()
+        buf = ReplayBuffer(n_data, (O,), np.float32, A, np.float32, device="cpu")
+        buf.load_dataset(data)
+        np.random.seed(0)
+        torch.manual_seed(torch_seed)
+        rows = [pol.learn(buf.sample(B)) for _ in range(n_steps)]
+        keys = sorted(rows[0])
+        arr = np.asarray([[r[k] for k in keys] for r in rows], np.float64).reshape(n_steps // window, window, len(keys))
+        return keys, arr.mean(1), arr.std(1)
+
+    keys, mean_a, std_a = run(1)
+    _, mean_b, _ = run(2)
+    tol = 6.0 * std_a / np.sqrt(window) + 2e-3 * np.abs(mean_a) + 1e-4
+    assert (np.abs(mean_b - mean_a) <= tol).all(), np.abs(mean_b - mean_a) / tol
+    print("   second reference run vs first, worst |diff| / tol per key:",
+          dict(zip(keys, np.round((np.abs(mean_b - mean_a) / tol).max(0), 3))))
+    store = {"mean": mean_a, "std": std_a, "mean_other_noise": mean_b}
+    meta = dict(algo="cql", O=O, A=A, hidden=hidden, B=B, N=N, n_steps=n_steps, window=window, n_data=n_data, data_seed=0,
+                param_seeds={"actor": 100, "critic1": 101, "critic2": 102}, alpha_lr=1e-4, target_entropy=-A, hyper=hyper,
+                np_seed=0, keys=keys)
+    save(name, store, meta, False)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
 
@@ -794,3 +840,4 @@ if __name__ == "__main__":
         max_epochs=6)
     run(gen_rollout_cfg5, "rollout_cfg5_hc", term="halfcheetah")
     run(gen_rollout_cfg5, "rollout_cfg5_walker", term="walker2d")
+    run(gen_cql_curve, "cql_curve_small")

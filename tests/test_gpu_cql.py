@@ -106,3 +106,32 @@ def test_lazy_gather_inside_step_graph_equals_eager_gather(name):
     idx = np.random.randint(0, buf2._size, size=m["B"])
     assert np.array_equal(b2["observations"].cpu().numpy(), data["observations"][idx])
     assert np.array_equal(b2.indices.cpu().numpy(), idx)
+
+
+def test_loss_curve_matches_the_reference_statistically():
+    """north_star: "loss-curve parity with the reference".  500 CQL steps on the reference's own sampler stream; the engine
+    draws its noise from Philox, so its curve is compared with the reference's run A exactly the way a second reference
+    run with other torch noise (run B, stored in the fixture) is: per 50-step window, every loss key's mean within
+    6 sigma_window / sqrt(50) + 0.2 % of run A (make_golden.gen_cql_curve asserts that run B passes the same test)."""
+    import numpy as np
+    from tests.gpu_common import build_policy, load_state, make_buffer
+    from tests.helpers import initial_state
+    g = Golden("cql_curve_small")
+    m = g.meta
+    pol = build_policy(m)
+    load_state(pol, initial_state(m))
+    pol.train()
+    buf, _ = make_buffer(g)
+    np.random.seed(m["np_seed"])
+    rows = [pol.learn(buf.sample(m["B"])) for _ in range(m["n_steps"])]
+    keys, w = m["keys"], m["window"]
+    arr = np.asarray([[r[k] for k in keys] for r in rows], np.float64).reshape(m["n_steps"] // w, w, len(keys))
+    mean, ref_mean, ref_std = arr.mean(1), g["mean"], g["std"]
+    tol = 6.0 * ref_std / np.sqrt(w) + 2e-3 * np.abs(ref_mean) + 1e-4
+    worst = np.abs(mean - ref_mean) / tol
+    print("worst |diff| / tol per key:", dict(zip(keys, np.round(worst.max(0), 3))),
+          " (second reference run:", dict(zip(keys, np.round((np.abs(g["mean_other_noise"] - ref_mean) / tol).max(0), 3))), ")")
+    assert (worst <= 1.0).all(), (worst.max(0), keys)
+    # the curve moves: the check is not vacuous
+    j = keys.index("loss/alpha")
+    assert abs(ref_mean[-1, j] - ref_mean[0, j]) > 10 * tol[0, j]
