@@ -11,6 +11,6 @@ __version__ = "0.1.0"
 
 
 def attach(policy, buffer=None):
-    """Put the CUDA engine behind objects built by the unmodified reference (see attach.py)."""
-    from offlinerlkit_b200.attach import attach as _attach      # (absolute: this file is exec'd by the root import shim)
+    """Put the CUDA engine behind objects built by the unmodified reference (see attach_mode.py)."""
+    from offlinerlkit_b200.attach_mode import attach as _attach      # (absolute: this file is exec'd by the root import shim)
     return _attach(policy, buffer)
