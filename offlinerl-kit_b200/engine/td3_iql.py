@@ -218,7 +218,9 @@ class IQLLearner(_BatchMixin, Learner):
         self.policy, self.B = policy, int(batch_size)
         check_plain_mlp(actor.backbone, "actor")
         dist = actor.dist_net
-        if getattr(dist, "_c_sigma", True) or getattr(dist, "_unbounded", True) or dist._dist.squash:
+        # (the tanh-squashed head is told by its class name: the reference's modules carry no flag for it, dist_module.py:79)
+        squashed = any(c.__name__ == "TanhDiagGaussian" for c in type(dist).__mro__)
+        if getattr(dist, "_c_sigma", True) or getattr(dist, "_unbounded", True) or squashed:
             raise L.OrlkError("IQL engine needs DiagGaussian(unbounded=False, conditioned_sigma=False)")
         self.max_mu = float(dist._max)
         self.actor_ps = ParamSet.from_linear_members(rt, "actor", [linears_of(actor)],
