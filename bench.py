@@ -371,6 +371,12 @@ def run_engine(args, rank: int, world: int, local_rank: int):
     e2e_wall = time.perf_counter() - t0
     L.call("orlk_event_elapsed_ms", e0, e1, C.byref(ms))
     e2e_ms = max(ms.value, 1e3 * e2e_wall)
+    # ---- (3) informational: the K-step call (policy.learn_many: one host synchronisation for all K steps)
+    barrier()
+    t0 = time.perf_counter()
+    many = policy.learn_many(buf, K, BATCH)
+    torch.cuda.synchronize()
+    many_ms = 1e3 * (time.perf_counter() - t0)
     sampler.window = (t_win0, time.time())
     # keep the same step running until the sampler has seen >= 0.25 s of it (not timed; clocks only)
     t_probe = time.perf_counter()
@@ -380,7 +386,7 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
     clocks = sampler.stop()
 
-    dev_ms, e2e_ms = parallel.reduce_scalars([dev_ms, e2e_ms], "max", device)      # the slowest rank bounds the job
+    dev_ms, e2e_ms, many_ms = parallel.reduce_scalars([dev_ms, e2e_ms, many_ms], "max", device)      # the slowest rank bounds the job
     value = world * K / (dev_ms * 1e-3)
     e2e = world * K / (e2e_ms * 1e-3)
 
@@ -444,6 +450,9 @@ def run_engine(args, rank: int, world: int, local_rank: int):
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 8 * BATCH, "d2h_bytes_per_step": 4 * 32,
                         "ms_per_step": e2e_ms / K},
+                "learn_many": {"value": world * K / (many_ms * 1e-3), "unit": "steps/s", "ms_per_step": many_ms / K,
+                               "note": "policy.learn_many(buffer, K, 256): the same K steps (same index stream, same results) "
+                                       "behind one host synchronisation; informational, not the e2e headline"},
                 "gpu_launches": n_kernels * K, "launches_per_step": n_kernels, "roofline": roof, "precision": eng.precision,
                 "launch_breakdown_us": {lbl: round(us, 2) for lbl, us in top}, "eager_step_us": step_us,
                 "last_loss": {k: float(v) for k, v in loss.items()}}

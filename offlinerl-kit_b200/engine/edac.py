@@ -296,7 +296,9 @@ class EDACLearner(_BatchMixin, Learner):
         self.set_noise(noise)
         self.sync_lr()
         self.refresh()
-        out = self.run("step")
+        return self.result_of(self.run("step"))
+
+    def result_of(self, out) -> Dict[str, float]:
         res = {"loss/actor": float(out[LS_ACTOR]),
                "loss/critics": float(out[LS_TD_SUM]) + (float(out[LS_DIV]) if self.eta > 0 else 0.0)}
         if self.auto_alpha:

@@ -326,6 +326,10 @@ class EDACShardedLearner(EDACLearner):
             res["alpha"] = float(out[LS_ALPHA])
         return res
 
+    def learn_many(self, buffer, n_steps: int) -> List[Dict[str, float]]:
+        """(the sharded step is several graphs with collectives in between: K plain steps)"""
+        return [self.step(buffer.sample(self.B)) for _ in range(int(n_steps))]
+
     def _capture_whole_step(self) -> bool:
         """The four segments AND the three NCCL all-gathers as ONE CUDA graph (torch's stream capture records the
         collectives' kernels like any other launch): one graph launch per step instead of four launches and three Python

@@ -240,6 +240,62 @@ class Learner:
             plan.run_eager()
         self.steps_done += 1
 
+    # ------------------------------------------------------------------ K steps behind one host synchronisation
+    def next_key(self) -> str:
+        """Plan the next step replays (engines with step variants override; called once per step, in order)."""
+        return "step"
+
+    def result_of(self, out: Sequence[float]) -> Dict[str, float]:
+        """The reference's loss dict from one step's loss block (engines override)."""
+        raise NotImplementedError
+
+    def learn_many(self, buffer, n_steps: int) -> List[Dict[str, float]]:
+        """``n_steps`` times ``learn(buffer.sample(B))`` with ONE host synchronisation at the end instead of one per step.
+
+        Valid whenever nothing else consumes ``np.random`` between the draws (true inside a trainer epoch):
+        ``np.random.randint(0, n, size=(K, B))`` is bit-for-bit K successive ``randint(0, n, B)`` calls (SURVEY.md section
+        8c, fact i), so the batches, the Philox noise and therefore every parameter are identical to K single calls; the
+        K index rows are uploaded once, each step is one gather launch + one graph replay, and the K loss blocks are read
+        back together.  Returns the K loss dicts in order."""
+        B = self.B
+        outs: List[Dict[str, float]] = []
+        if n_steps <= 0:
+            return outs
+        if not getattr(self, "_built", False) or getattr(self, "_bound_token", None) is None:
+            outs.append(self.step(buffer.sample(B)))        # builds the plans and binds them to the buffer's staging rows
+            n_steps -= 1
+            if n_steps == 0:
+                return outs
+        stage = buffer._stages.get(B)
+        bound = getattr(self, "_bound_ptrs", None)
+        if stage is None or bound is None or bound[0] != stage.obs2.data_ptr() or not self.use_graph:
+            return outs + [self.step(buffer.sample(B)) for _ in range(n_steps)]     # foreign staging: the plain path
+        idx = np.random.randint(0, buffer._size, size=(n_steps, B))
+        pin = torch.from_numpy(idx).pin_memory()
+        idx_dev = pin.to(self.dev, non_blocking=True)
+        self.set_noise(None)
+        self.sync_lr()
+        self.refresh()
+        losses = torch.empty(n_steps, N_LOSS, dtype=torch.float32, device=self.dev)
+        keys = []
+        src = self.loss_dev.data_ptr()
+        for t in range(n_steps):
+            buffer.gather_device(idx_dev[t])
+            key = self.next_key()
+            keys.append(key)
+            plan = self.plans[key]
+            if plan.graph is None:
+                plan.capture()
+            L.call("orlk_graph_launch", plan.graph, self.rt.cur)
+            L.call("orlk_memcpy_d2d_async", losses.data_ptr() + 4 * N_LOSS * t, src, 4 * N_LOSS, self.rt.cur)
+            self.steps_done += 1
+        host = losses.cpu().tolist()                        # the one synchronisation
+        self._many_keys = keys
+        for t in range(n_steps):
+            self._many_t = t
+            outs.append(self.result_of(host[t]))
+        return outs
+
     def emit_loss_readback(self, plan: Plan) -> None:
         """Copy the loss block to pinned host memory on a detached branch (call once no later launch writes it)."""
         ld, lh = C.c_void_p(self.loss_dev.data_ptr()), C.c_void_p(self.loss_host.data_ptr())

@@ -416,7 +416,9 @@ class CQLLearner(TwinCriticLearner):
         self.set_noise(noise)
         self.sync_lr()
         self.refresh()
-        out = self.run("step")
+        return self.result_of(self.run("step"))
+
+    def result_of(self, out) -> Dict[str, float]:
         res = {"loss/actor": float(out[LS_ACTOR]), "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
         if self.auto_alpha:
             res["loss/alpha"] = float(out[LS_ALPHA_LOSS])
@@ -509,7 +511,9 @@ class SACLearner(TwinCriticLearner):
         self.set_noise(noise)
         self.sync_lr()
         self.refresh()
-        out = self.run("step")
+        return self.result_of(self.run("step"))
+
+    def result_of(self, out) -> Dict[str, float]:
         res = {"loss/actor": float(out[LS_ACTOR]), "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
         if self.auto_alpha:
             res["loss/alpha"] = float(out[LS_ALPHA_LOSS])

@@ -196,12 +196,21 @@ class TD3BCLearner(_BatchMixin, Learner):
         self.set_noise(noise)
         self.sync_lr()
         self.refresh()
+        key = self.next_key()
+        self._many_keys, self._many_t = [key], 0
+        return self.result_of(self.run(key))
+
+    def next_key(self) -> str:
+        """td3bc.py:107: the actor (and the three polyak syncs) every ``update_actor_freq``-th step"""
         pol = self.policy
-        with_actor = pol._cnt % pol._freq == 0
-        out = self.run("both" if with_actor else "critic")
-        if with_actor:
-            pol._last_actor_loss = float(out[LS_ACTOR])
+        key = "both" if pol._cnt % pol._freq == 0 else "critic"
         pol._cnt += 1
+        return key
+
+    def result_of(self, out) -> Dict[str, float]:
+        pol = self.policy
+        if self._many_keys[self._many_t] == "both":
+            pol._last_actor_loss = float(out[LS_ACTOR])
         return {"loss/actor": pol._last_actor_loss, "loss/critic1": float(out[LS_C1]), "loss/critic2": float(out[LS_C2])}
 
 
@@ -334,6 +343,8 @@ class IQLLearner(_BatchMixin, Learner):
             self._build()
         self.sync_lr()
         self.refresh()
-        out = self.run("step")
+        return self.result_of(self.run("step"))
+
+    def result_of(self, out) -> Dict[str, float]:
         return {"loss/actor": float(out[LS_ACTOR]), "loss/q1": float(out[LS_C1]), "loss/q2": float(out[LS_C2]),
                 "loss/v": float(out[LS_V])}

@@ -41,3 +41,13 @@ def engine_for(policy, key, make, **kw):
     eng.invalidate()                # the other sibling's updates may have by-passed this one's derived weight copies
     policy._engine = eng
     return eng
+
+
+def learn_many(policy, buffer, n_steps: int, batch_size: int):
+    """K-step form of ``for _ in range(K): policy.learn(buffer.sample(batch_size))`` with one host synchronisation
+    (engine/learner.py:Learner.learn_many); same index stream, same noise, same parameters, the K loss dicts in order."""
+    outs = policy.engine(int(batch_size)).learn_many(buffer, int(n_steps))
+    after = getattr(policy, "_after_step", None)
+    if outs and after is not None:
+        after(outs[-1])
+    return outs

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy, engine_for
+from .base_policy import BasePolicy, engine_for, learn_many as _learn_many
 
 
 class EDACPolicy(BasePolicy):
@@ -68,6 +68,10 @@ class EDACPolicy(BasePolicy):
             return engine_for(self, int(batch_size), lambda: EDACShardedLearner(self, batch_size, *shard))
         from ..engine.edac import EDACLearner
         return engine_for(self, int(batch_size), lambda: EDACLearner(self, batch_size))
+
+    def learn_many(self, buffer, n_steps: int, batch_size: int):
+        """``n_steps`` x ``learn(buffer.sample(batch_size))`` behind one host synchronisation (base_policy.learn_many)."""
+        return _learn_many(self, buffer, n_steps, batch_size)
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         out = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

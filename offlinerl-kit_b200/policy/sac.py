@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy, engine_for
+from .base_policy import BasePolicy, engine_for, learn_many as _learn_many
 
 
 class SACPolicy(BasePolicy):
@@ -97,6 +97,10 @@ class SACPolicy(BasePolicy):
             return out
         mix = {k: torch.cat([real[k], fake[k]], 0) for k in real.keys()}
         return SACPolicy.learn(self, mix, noise)
+
+    def learn_many(self, buffer, n_steps: int, batch_size: int):
+        """``n_steps`` x ``learn(buffer.sample(batch_size))`` behind one host synchronisation (base_policy.learn_many)."""
+        return _learn_many(self, buffer, n_steps, batch_size)
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         eng = self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0])))

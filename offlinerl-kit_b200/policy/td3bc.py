@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base_policy import BasePolicy, engine_for
+from .base_policy import BasePolicy, engine_for, learn_many as _learn_many
 from ..utils.noise import GaussianNoise
 
 
@@ -50,6 +50,10 @@ class TD3BCPolicy(BasePolicy):
     def engine(self, batch_size: int):
         from ..engine.td3_iql import TD3BCLearner
         return engine_for(self, int(batch_size), lambda: TD3BCLearner(self, batch_size))
+
+    def learn_many(self, buffer, n_steps: int, batch_size: int):
+        """``n_steps`` x ``learn(buffer.sample(batch_size))`` behind one host synchronisation (base_policy.learn_many)."""
+        return _learn_many(self, buffer, n_steps, batch_size)
 
     def learn(self, batch: Dict, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, float]:
         return self.engine((getattr(batch, "batch_size", None) or int(batch["observations"].shape[0]))).step(batch, noise)

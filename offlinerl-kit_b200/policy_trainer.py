@@ -55,11 +55,20 @@ class MFPolicyTrainer(_TrainerBase):
         for e in range(1, self._epoch + 1):
             self.policy.train()
             t0 = time.time()
-            for _ in range(self._step_per_epoch):
-                loss = self.policy.learn(self.buffer.sample(self._batch_size))
-                for k, v in loss.items():
-                    self.logger.logkv_mean(k, v)
-                num_timesteps += 1
+            many = getattr(self.policy, "learn_many", None) if getattr(self, "use_learn_many", True) else None
+            left = self._step_per_epoch
+            while left > 0:
+                if many is not None and hasattr(self.buffer, "gather_device"):
+                    # K steps behind one host synchronisation: same np.random index stream, same losses, same logged means
+                    # (mf_policy_trainer.py:52-60 spends ~55 us per step on the host between two ~300 us device steps)
+                    losses = many(self.buffer, min(left, 250), self._batch_size)
+                else:
+                    losses = [self.policy.learn(self.buffer.sample(self._batch_size))]
+                for loss in losses:
+                    for k, v in loss.items():
+                        self.logger.logkv_mean(k, v)
+                num_timesteps += len(losses)
+                left -= len(losses)
             self.logger.logkv("train/steps_per_second", self._step_per_epoch / max(time.time() - t0, 1e-9))
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()

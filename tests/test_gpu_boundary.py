@@ -144,3 +144,33 @@ def test_batch_dict_copies_materialise_the_rows():
         idx = b.indices.cpu().numpy()
         assert np.array_equal(c["observations"].cpu().numpy(), data["observations"][idx]), mode
         assert np.array_equal(c["rewards"].cpu().numpy().reshape(-1), data["rewards"][idx].reshape(-1)), mode
+
+
+@pytest.mark.parametrize("name", ["cql_small", "sac_small", "iql_small", "td3bc_small", "edac_small", "cql_hc"])
+def test_learn_many_equals_single_steps(name):
+    """``policy.learn_many(buffer, K, B)`` (K steps behind ONE host synchronisation) == K calls of
+    ``policy.learn(buffer.sample(B))``: the same np.random index stream, bit-identical loss dicts and parameters."""
+    from tests.gpu_common import build_policy, load_state, make_buffer
+    g = Golden(name)
+    m = g.meta
+    K = 7
+
+    def make():
+        pol = build_policy(m, DEV)
+        load_state(pol, initial_state(m))
+        pol.train()
+        buf, _ = make_buffer(g, DEV)
+        pol.engine(m["B"]).seed = 11
+        np.random.seed(21)
+        return pol, buf
+
+    pa, ba = make()
+    single = [pa.learn(ba.sample(m["B"])) for _ in range(K)]
+    end_a = np.random.randint(0, 1 << 30)
+    pb, bb = make()
+    many = pb.learn_many(bb, 3, m["B"]) + pb.learn_many(bb, K - 3, m["B"])
+    end_b = np.random.randint(0, 1 << 30)
+    assert end_a == end_b, "learn_many must consume np.random exactly like K sample() calls"
+    assert many == single
+    for (k, x), (_, y) in zip(pa.state_dict().items(), pb.state_dict().items()):
+        assert torch.equal(x, y), k
