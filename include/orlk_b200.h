@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 21
+#define ORLK_ABI_VERSION 22
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -199,6 +199,35 @@ int orlk_tc_effective_splits(int K, int want);
  * 4 first MMA issued, 5 last MMA issued, 6 accumulator ready, 7 epilogue stores issued, 8..15 k-slab 0..7 landed.  NULL turns it off. */
 int orlk_tc_set_trace(void* dev_buf);
 int orlk_sizeof_tc_gemm(void);
+
+/* Fused critic forward pass: ONE launch evaluates, for every member g (twin critics),
+ *   H_0 = relu(X W_0^T + b_0), H_l = relu(H_{l-1} W_l^T + b_l) (l < n_hidden), out[g][m] = H_last[m] . head_w[g] + head_b[g]
+ * on the tensor cores (3xTF32, fp32-grade).  A CTA owns a 128-row strip of one member for the whole pass: accumulators
+ * ping-pong in tensor memory, layer l's epilogue writes the A operand tiles of layer l+1 straight into shared memory and
+ * stores H_l (needed by the backward pass) with TMA from the same tiles; the head is a dot product in the last epilogue.
+ * Shapes: hidden widths all N (multiple of 32, <= 256), K0 <= 32 input columns, X [M][ldx] shared by all members
+ * (16-byte aligned rows), 'oi' weights W_l [N][K] with one member stride `gs` for every parameter tensor, Wlo[l] =
+ * W[l] - trunc_tf32(W[l]) for l >= 1 (kept by orlk_split_lo).  Replaces the per-layer launches + head of
+ * modules/critic_module.py:25-33 / nets/mlp.py:22-28 on CQL's 7936-row critic batch (policy/model_free/cql.py:133-160).
+ * The struct is read on the HOST. */
+#define ORLK_FUSED_MAX_LAYERS 4
+typedef struct OrlkFusedFwd {
+    const float* X; int64_t ldx;
+    const float* W[ORLK_FUSED_MAX_LAYERS];
+    const float* Wlo[ORLK_FUSED_MAX_LAYERS];      /* [0] unused */
+    const float* bias[ORLK_FUSED_MAX_LAYERS];
+    float* H[ORLK_FUSED_MAX_LAYERS];              /* [G][M][N] each */
+    int64_t gs, h_gs;                             /* member strides (floats) of the parameters / of H */
+    const float* head_w; const float* head_b;
+    float* out; int64_t out_gs;                   /* [G][M] */
+    int32_t M, N, K0, G, n_hidden, pad_;
+} OrlkFusedFwd;
+int orlk_fused_init(void); /* once per process, outside stream capture */
+int orlk_critic_fwd_fused(const OrlkFusedFwd* params_host, void* stream);
+int orlk_sizeof_fused_fwd(void);
+/* dst[i] = src[i] - trunc_tf32(src[i]): the low operand words of the 3xTF32 products, kept next to the weights so that
+ * the fused passes fetch them by TMA instead of recomputing them in every CTA.  16-byte aligned arrays. */
+int orlk_split_lo(const float* src, float* dst, int64_t n, void* stream);
 
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
  * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).

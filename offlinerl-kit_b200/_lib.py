@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -65,6 +65,19 @@ class TcGemm(C.Structure):
                 ("a_mn", C.c_int32), ("b_mn", C.c_int32)]
 
 
+FUSED_MAX_LAYERS = 4
+
+
+class FusedFwd(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("ldx", C.c_int64),
+                ("W", C.c_void_p * FUSED_MAX_LAYERS), ("Wlo", C.c_void_p * FUSED_MAX_LAYERS),
+                ("bias", C.c_void_p * FUSED_MAX_LAYERS), ("H", C.c_void_p * FUSED_MAX_LAYERS),
+                ("gs", C.c_int64), ("h_gs", C.c_int64),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("out", C.c_void_p), ("out_gs", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32), ("K0", C.c_int32), ("G", C.c_int32), ("n_hidden", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)
 CFG_BIG, CFG_MID, CFG_SMALL, CFG_KPAR, CFG_TINY = range(5)
 CFG_TILES = {CFG_BIG: (128, 128, 16), CFG_MID: (64, 64, 16), CFG_SMALL: (32, 32, 32), CFG_KPAR: (32, 32, 256), CFG_TINY: (32, 16, 256)}
@@ -97,6 +110,8 @@ _PROTOS = {
     "orlk_gemm_chain": [_P, _I, _I, _I, _I, _P], "orlk_gemm_chain_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],
     "orlk_sizeof_tc_gemm": [],
+    "orlk_fused_init": [], "orlk_critic_fwd_fused": [C.POINTER(FusedFwd), _P], "orlk_sizeof_fused_fwd": [],
+    "orlk_split_lo": [_P, _P, _L, _P],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],
@@ -159,7 +174,8 @@ def load() -> C.CDLL:
         raise OrlkError(f"ABI mismatch: library {lib.orlk_abi_version()} vs binding {ABI_VERSION}; rebuild")
     for fn, st in (("orlk_sizeof_gemm_desc", GemmDesc), ("orlk_sizeof_adam_desc", AdamDesc),
                    ("orlk_sizeof_adam_group", AdamGroup), ("orlk_sizeof_concat_seg", ConcatSeg),
-                   ("orlk_sizeof_tc_gemm", TcGemm), ("orlk_sizeof_sample_use", SampleUse)):
+                   ("orlk_sizeof_tc_gemm", TcGemm), ("orlk_sizeof_sample_use", SampleUse),
+                   ("orlk_sizeof_fused_fwd", FusedFwd)):
         if getattr(lib, fn)() != C.sizeof(st):
             raise OrlkError(f"struct size mismatch for {st.__name__}: C {getattr(lib, fn)()} vs ctypes {C.sizeof(st)}")
     _lib = lib

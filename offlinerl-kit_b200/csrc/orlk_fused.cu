@@ -1,0 +1,338 @@
+// Whole critic passes in ONE launch on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 = fp32-grade).  sm_100a only.
+//
+// k_critic_fwd: q[g][m] = head( relu( ... relu( relu(X W0^T + b0) W1^T + b1) ... ) )  for every member g (twin critics)
+// of a Linear+ReLU stack with equal hidden widths N <= 256 and a scalar head (reference: nets/mlp.py:22-28 forward inside
+// modules/critic_module.py:25-33, called on the 7936-row CQL critic batch, policy/model_free/cql.py:133-160).
+//
+// One CTA owns a 128-row strip of ONE member for the whole pass: the activations never leave the SM between layers.
+//   * accumulators: two 128 x N fp32 tiles in tensor memory (ping-pong over the layers, 2 x 256 columns);
+//   * layer l's epilogue (8 warps) turns accumulator columns [32c, 32c+32) into relu(acc + b) and writes them - and their
+//     lo = x - trunc_tf32(x) part - as the K-major SWIZZLE_128B A tile of k-slab c of layer l+1 (two-stage ring); the
+//     same tile leaves for H[l] in global memory by TMA store (the backward pass needs it), so the next layer's MMAs
+//     start on slab 0 while the epilogue is still draining slab 1..7;
+//   * weights: [W | W lo] k-slabs through a two-stage TMA ring; the lo copies are kept by orlk_split_lo (one tiny launch
+//     per step, off the critical path) instead of being recomputed by all 62 strips of a member;
+//   * first layer (K0 = obs+act <= 32 columns, rows not TMA-addressable): X by TMA with zero fill, W0 staged by hand;
+//   * scalar head: a dot product with the last epilogue's registers, one value per row.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected lane each), warps 2-5 / 6-9 epilogue of the even / odd
+// 32-column chunks (warp w may touch TMEM lanes 32 (w % 4) .. +31).
+#include "orlk_tcgen.cuh"
+using namespace orlk;
+using namespace orlk::tcg;
+
+namespace {
+
+constexpr int BM = 128, BK = 32, NMAX = 256, MAXL = ORLK_FUSED_MAX_LAYERS;
+constexpr int A_TILE = BM * BK * 4;            // 16 KB
+constexpr int A_STAGE = 2 * A_TILE;            // [hi | lo]
+constexpr int B_TILE = NMAX * BK * 4;          // 32 KB
+constexpr int B_STAGE = 2 * B_TILE;            // [hi | lo]
+constexpr int RING = 2 * A_STAGE + 2 * B_STAGE;     // 192 KB
+constexpr int FIXED = 8192;
+constexpr int NUM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
+
+enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 3, BAR_BFULL = 5, BAR_BEMPTY = 7, BAR_ACC = 9, BAR_COUNT = 11 };
+
+struct FwdMaps {
+    CUtensorMap x;                // X [M][K0]: box 32 (k, zero filled past K0) x 128 rows
+    CUtensorMap w[MAXL - 1];      // W_l [G][N][N], l >= 1: box 32 (k) x N
+    CUtensorMap wlo[MAXL - 1];
+    CUtensorMap h[MAXL];          // H_l [G][M][N]: box 32 x 32 (store)
+};
+
+struct FwdParams {
+    const float* W0; int64_t gs;          // first-layer weights [N][K0] of member 0; member stride of every parameter tensor
+    const float* bias[MAXL];
+    const float* head_w; const float* head_b;
+    float* out; int64_t out_gs;
+    int M, N, K0, G, L, tiles_m;
+};
+
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // SWIZZLE_128B tiles: 1024-byte aligned
+    uint8_t* b_base = base + 2 * A_STAGE;
+    uint8_t* fixed = base + RING;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 128);
+    float* bias_s = reinterpret_cast<float*>(fixed + 256);       // [MAXL][NMAX]
+    float* headw_s = bias_s + MAXL * NMAX;                        // [NMAX]
+    float* qpart_s = headw_s + NMAX;                              // [BM]
+    auto a_hi = [&](int s) { return base + s * A_STAGE; };
+    auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };
+    auto b_hi = [&](int s) { return b_base + s * B_STAGE; };
+    auto b_lo = [&](int s) { return b_base + s * B_STAGE + B_TILE; };
+    auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.tiles_m;
+    const int tile_m = blockIdx.x - g * p.tiles_m;
+    const int N = p.N, L = p.L;
+    const int KS = N / BK;                      // k-slabs of a hidden layer = 32-column chunks of an accumulator
+
+    // ---------------------------------------------------------------- prologue (touches no global data)
+    if (threadIdx.x == 32) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+        for (int l = 1; l < L; ++l) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w[l - 1]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wlo[l - 1]) : "memory");
+        }
+        for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.h[l]) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(bar(BAR_X), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(BAR_AFULL + s), 4);       // one arrival per epilogue warp of the stage's group
+            mbar_init(bar(BAR_AEMPTY + s), 1);
+            mbar_init(bar(BAR_BFULL + s), 1);
+            mbar_init(bar(BAR_BEMPTY + s), 1);
+            mbar_init(bar(BAR_ACC + s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    orlk::pdl_wait();                           // X and the weights come from earlier kernels of the step
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ------------------------------------------------------------ TMA producer
+            mbar_expect_tx(bar(BAR_X), A_TILE);
+            tma_load_3d(smem_u32(a_hi(0)), &maps.x, bar(BAR_X), 0, tile_m * BM, 0);
+            const uint32_t tx = 2u * (uint32_t)N * BK * 4;
+            int bi = 1;                         // B fill 0 (the first layer's weights) is staged by the epilogue warps
+            for (int l = 1; l < L; ++l) {
+                for (int j = 0; j < KS; ++j, ++bi) {
+                    const int s = bi & 1;
+                    mbar_wait(bar(BAR_BEMPTY + s), ((bi >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar(BAR_BFULL + s), tx);
+                    tma_load_3d(smem_u32(b_hi(s)), &maps.w[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                    tma_load_3d(smem_u32(b_lo(s)), &maps.wlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                }
+            }
+        }
+        __syncwarp();
+        orlk::pdl_trigger();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ------------------------------------------------------------ MMA issuer
+            const uint32_t idesc = instr_desc_tf32(BM, N);
+            int fa0 = 0, fa1 = 0, bi = 0;       // fills consumed so far of A stage 0 / 1, B fills consumed
+            for (int l = 0; l < L; ++l) {
+                const uint32_t acc = tmem_base + (uint32_t)(NMAX * (l & 1));
+                const int nsl = l == 0 ? 1 : KS;
+                for (int j = 0; j < nsl; ++j, ++bi) {
+                    const int sa = l == 0 ? 0 : (j & 1);
+                    const int fa = sa ? fa1 : fa0;
+                    mbar_wait(bar(BAR_AFULL + sa), fa & 1);
+                    if (sa) ++fa1; else ++fa0;
+                    const int sb = bi & 1;
+                    mbar_wait(bar(BAR_BFULL + sb), (bi >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = smem_desc_sw128(smem_u32(a_hi(sa))), adl = smem_desc_sw128(smem_u32(a_lo(sa)));
+                    const uint64_t bd = smem_desc_sw128(smem_u32(b_hi(sb))), bdl = smem_desc_sw128(smem_u32(b_lo(sb)));
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {          // UMMA_K = 8 for tf32: 32 bytes along a K-major row
+                        const uint64_t ko = (uint64_t)(2 * k);
+                        umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
+                        umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                    }
+                    umma_commit(bar(BAR_AEMPTY + sa));          // both stages are free once these MMAs have completed
+                    umma_commit(bar(BAR_BEMPTY + sb));
+                }
+                umma_commit(bar(BAR_ACC + (l & 1)));
+            }
+        }
+        __syncwarp();
+        orlk::pdl_trigger();
+    } else {
+        // ---------------------------------------------------------------- epilogue warps
+        const int grp = warp >= 6 ? 1 : 0;          // A stage (and chunk parity) this warp group produces
+        const int q = warp & 3;                     // TMEM lane quadrant
+        const int t = threadIdx.x - 64;             // 0..255
+        const int row = q * 32 + lane;
+        const int m = tile_m * BM + row;
+        // biases, head weights, first-layer weights (K-major SWIZZLE_128B tile: 16-byte chunk c of row n at c ^ (n & 7))
+#pragma unroll
+        for (int l = 0; l < MAXL; ++l)
+            if (l < L) bias_s[l * NMAX + t] = t < N ? __ldg(p.bias[l] + (int64_t)g * p.gs + t) : 0.f;
+        headw_s[t] = t < N ? __ldg(p.head_w + (int64_t)g * p.gs + t) : 0.f;
+        if (t < N) {
+            const float* wr = p.W0 + (int64_t)g * p.gs + (int64_t)t * p.K0;
+            float4* bh = reinterpret_cast<float4*>(b_hi(0));
+            float4* bl = reinterpret_cast<float4*>(b_lo(0));
+#pragma unroll
+            for (int c = 0; c < BK / 4; ++c) {
+                float4 v;
+                v.x = 4 * c + 0 < p.K0 ? __ldg(wr + 4 * c + 0) : 0.f;
+                v.y = 4 * c + 1 < p.K0 ? __ldg(wr + 4 * c + 1) : 0.f;
+                v.z = 4 * c + 2 < p.K0 ? __ldg(wr + 4 * c + 2) : 0.f;
+                v.w = 4 * c + 3 < p.K0 ? __ldg(wr + 4 * c + 3) : 0.f;
+                bh[t * 8 + (c ^ (t & 7))] = v;
+                bl[t * 8 + (c ^ (t & 7))] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+            }
+        }
+        if (grp == 0) {         // lo part of the X tile: this warp's 32 rows = 256 float4 (hi and lo tiles share the layout)
+            mbar_wait(bar(BAR_X), 0);
+            const float4* xh = reinterpret_cast<const float4*>(a_hi(0)) + q * 256;
+            float4* xl = reinterpret_cast<float4*>(a_lo(0)) + q * 256;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = xh[i * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xl[i * 32 + lane] = make_float4(lo_of(v[i].x), lo_of(v[i].y), lo_of(v[i].z), lo_of(v[i].w));
+        }
+        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t == 0) mbar_arrive(bar(BAR_BFULL + 0));
+        if (grp == 0 && lane == 0) mbar_arrive(bar(BAR_AFULL + 0));
+
+        int fe = grp == 0 ? 1 : 0;                  // fills of this group's A stage so far
+        float qacc = 0.f;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint8_t* my_hi = a_hi(grp) + q * 4096;      // this warp's 32 rows of the stage: a 32 x 32 SWIZZLE_128B store tile
+        uint8_t* my_lo = a_lo(grp) + q * 4096;
+        for (int l = 0; l < L; ++l) {
+            const bool last = l == L - 1;
+            mbar_wait(bar(BAR_ACC + (l & 1)), (l >> 1) & 1);
+            tc_fence_after();
+            if (last) orlk::pdl_trigger();          // every MMA of this strip has completed
+            const float* bl = bias_s + l * NMAX;
+            for (int c = grp; c < KS; c += 2) {
+                uint32_t v[32];
+                tmem_ld32(tlane + (uint32_t)(NMAX * (l & 1) + 32 * c), v);
+                tmem_wait_ld();
+                float x[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bl + 32 * c + 4 * j4);
+                    x[4 * j4 + 0] = fmaxf(__uint_as_float(v[4 * j4 + 0]) + b4.x, 0.f);
+                    x[4 * j4 + 1] = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b4.y, 0.f);
+                    x[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f);
+                    x[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
+                }
+                // the stage's previous content: read by the MMAs of slab c - 2 (or of the previous layer) and by this
+                // warp's own TMA store
+                if (!last && fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                if (!last) {
+                    float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        lrow[j4 ^ (lane & 7)] = make_float4(lo_of(x[4 * j4]), lo_of(x[4 * j4 + 1]), lo_of(x[4 * j4 + 2]),
+                                                            lo_of(x[4 * j4 + 3]));
+                } else {
+                    const float* hw = headw_s + 32 * c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) qacc = fmaf(x[j], hw[j], qacc);
+                }
+                tc_fence_before();                  // the TMEM reads above are ordered before the next layer's MMAs
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!last) mbar_arrive(bar(BAR_AFULL + grp));
+                    tma_store_4d(&maps.h[l], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (!last) ++fe;
+            }
+        }
+        // scalar head: even-chunk partial (warps 2-5) + odd-chunk partial (warps 6-9) + bias, fixed order
+        if (grp == 1) qpart_s[row] = qacc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (grp == 0 && m < p.M) p.out[(int64_t)g * p.out_gs + m] = (qacc + qpart_s[row]) + __ldg(p.head_b + (int64_t)g * p.gs);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tiles must outlive the stores
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// lo[i] = x[i] - trunc_tf32(x[i]) (exact in fp32): the second operand word of the 3xTF32 products
+__global__ void k_split_lo(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    orlk::pdl_enter();
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        *reinterpret_cast<float4*>(dst + i) = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+    } else {
+        for (int64_t j = i; j < n; ++j) dst[j] = lo_of(src[j]);
+    }
+}
+
+constexpr size_t FWD_SMEM = 1024 + RING + FIXED;
+
+}  // namespace
+
+extern "C" int orlk_sizeof_fused_fwd(void) { return (int)sizeof(OrlkFusedFwd); }
+
+extern "C" int orlk_fused_init(void) {
+    return check(cudaFuncSetAttribute(k_critic_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
+}
+
+extern "C" int orlk_split_lo(const float* src, float* dst, int64_t n, void* stream) {
+    ORLK_REQUIRE(src != nullptr && dst != nullptr && n > 0, "split_lo arguments");
+    ORLK_REQUIRE(aligned16(src) && aligned16(dst), "split_lo needs 16-byte aligned arrays");
+    const int64_t vec = (n + 3) / 4;
+    orlk::launch(k_split_lo, dim3((unsigned)((vec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, n);
+    return check_launch("k_split_lo");
+}
+
+extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* q, void* stream) {
+    ORLK_REQUIRE(q != nullptr, "params");
+    ORLK_REQUIRE(q->M > 0 && q->G > 0, "sizes");
+    ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
+    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
+    ORLK_REQUIRE(q->K0 >= 1 && q->K0 <= BK, "first-layer fan-in must be <= 32");
+    ORLK_REQUIRE(q->ldx % 4 == 0 && aligned16(q->X), "X rows must be 16-byte aligned");
+    ORLK_REQUIRE(q->gs % 4 == 0 && q->h_gs % 4 == 0, "member strides must be multiples of 4 floats");
+    ORLK_REQUIRE(q->head_w != nullptr && q->head_b != nullptr && q->out != nullptr, "scalar head");
+    FwdMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = make_map(&maps.x, q->X, q->ldx, 0, q->M, q->K0, 1, BM);
+    if (rc) return rc;
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < q->n_hidden; ++l) {
+        ORLK_REQUIRE(q->W[l] != nullptr && q->bias[l] != nullptr && q->H[l] != nullptr, "layer pointers");
+        ORLK_REQUIRE(aligned16(q->H[l]), "H must be 16-byte aligned");
+        if (l >= 1) {
+            ORLK_REQUIRE(q->Wlo[l] != nullptr && aligned16(q->W[l]) && aligned16(q->Wlo[l]), "hidden weights (and lo copies) must be 16-byte aligned");
+            rc = make_map(&maps.w[l - 1], q->W[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            if (rc) return rc;
+            rc = make_map(&maps.wlo[l - 1], q->Wlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            if (rc) return rc;
+        }
+        rc = make_map_c(&maps.h[l], q->H[l], q->N, q->h_gs, 0, q->M, q->N, q->G, 1);
+        if (rc) return rc;
+        p.bias[l] = q->bias[l];
+    }
+    p.W0 = q->W[0]; p.gs = q->gs;
+    p.head_w = q->head_w; p.head_b = q->head_b;
+    p.out = q->out; p.out_gs = q->out_gs;
+    p.M = q->M; p.N = q->N; p.K0 = q->K0; p.G = q->G; p.L = q->n_hidden;
+    p.tiles_m = (q->M + BM - 1) / BM;
+    const int grid = q->G * p.tiles_m;
+    orlk::launch(k_critic_fwd, dim3(grid), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps, p);
+    return check_launch("k_critic_fwd");
+}

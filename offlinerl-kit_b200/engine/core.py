@@ -91,6 +91,7 @@ class Runtime:
         self.cur = self.exec_ptr
         self._keep: List[torch.Tensor] = []
         L.call("orlk_tc_init")
+        L.call("orlk_fused_init")
         L.call("orlk_gemm_init")
         L.call("orlk_gemm_tiny_init")
         L.call("orlk_gemm_chain_init")
@@ -212,6 +213,25 @@ class Runtime:
         q.k_splits = self.lib.orlk_tc_effective_splits(Ka, k_splits)
         qp = _ctypes_pointer(q)      # the struct is read on the host at every launch: keep it alive in the closure
         return lambda: L.call("orlk_tc_gemm", qp, self.cur)
+
+    def critic_fwd_fused(self, *, X: Mat, W: Sequence[int], Wlo: Sequence[int], bias: Sequence[int], H: Sequence[int],
+                         gs: int, h_gs: int, head_w: int, head_b: int, out: int, out_gs: int, M: int, N: int, K0: int,
+                         G: int) -> Callable[[], None]:
+        """Whole Linear+ReLU critic pass + scalar head for all members in one tcgen05 launch (csrc/orlk_fused.cu)."""
+        q = L.FusedFwd()
+        q.X, q.ldx = X.ptr, X.ld
+        for l in range(len(W)):
+            q.W[l], q.Wlo[l], q.bias[l], q.H[l] = W[l], (Wlo[l] or None), bias[l], H[l]
+        q.gs, q.h_gs = gs, h_gs
+        q.head_w, q.head_b, q.out, q.out_gs = head_w, head_b, out, out_gs
+        q.M, q.N, q.K0, q.G, q.n_hidden = M, N, K0, G, len(W)
+        qp = _ctypes_pointer(q)
+        return lambda: L.call("orlk_critic_fwd_fused", qp, self.cur)
+
+    def split_lo(self, src: torch.Tensor, dst: torch.Tensor) -> Callable[[], None]:
+        """dst = src - trunc_tf32(src) over a whole parameter arena (the lo operand words of the fused passes)."""
+        sp, dp, n = C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel()
+        return lambda: L.call("orlk_split_lo", sp, dp, n, self.cur)
 
     @staticmethod
     def effective_splits(K: int, want: int, cfg: int) -> int:

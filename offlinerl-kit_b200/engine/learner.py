@@ -380,6 +380,17 @@ class MlpRun:
             self.dZT[last] = None           # never materialised
         if any(self.tc_dgrad) and not self.ens_tc:
             ps.enable_wt([l for l in range(n_hidden) if self.tc_dgrad[l]])
+        # the whole forward pass (all hidden layers + scalar head) of a long-row Linear+ReLU stack as ONE tensor-core launch
+        # that keeps the activations on the SM between layers (csrc/orlk_fused.cu); fp32-grade (3xTF32) mode only
+        widths = {lays[l].out_dim for l in range(n_hidden)}
+        self.fused_fwd = (FUSED_FWD and tc_passes == 3 and M >= TC_MIN_ROWS and not self.ens_tc and share_forward is None
+                          and 2 <= n_hidden <= L.FUSED_MAX_LAYERS and self.has_head and self.NS == 1
+                          and all(lay.layout == "oi" for lay in lays[:n_hidden + 1])
+                          and len(widths) == 1 and lays[0].out_dim % 32 == 0 and 32 <= lays[0].out_dim <= 256
+                          and lays[0].in_dim <= 32 and all(lays[l].in_dim == lays[0].out_dim for l in range(1, n_hidden + 1))
+                          and all(h is None for h in self.HT) and ps.block % 4 == 0
+                          and all(lays[l].w_off % 4 == 0 and lays[l].w_gs == ps.block and lays[l].b_gs == ps.block
+                                  for l in range(n_hidden + 1)))
         # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
         # streaming kernels for the narrow first layer (K <= 32) and the narrow head's weight gradient
         self.narrow0 = lays[0].layout == "oi" and lays[0].in_dim <= 32
@@ -429,6 +440,21 @@ def chainable(run: "MlpRun", with_head: bool) -> bool:
             and all(lay.layout == "oi" and lay.in_dim <= 256 and lay.out_dim <= 256 for lay in lays))
 
 
+FUSED_FWD = os.environ.get("ORLK_FUSED_FWD", "1") != "0"
+
+
+def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
+    """lo words of a parameter arena for the fused passes (orlk_split_lo); once per plan and store, placed by the caller
+    after the last update of that arena and before its first fused use."""
+    done = plan.__dict__.setdefault("_lo_fresh", set())
+    key = (id(ps), store)
+    if key in done:
+        return
+    done.add(key)
+    plan.keep.append(ps)
+    plan.add(f"{ps.name}.{store}.split_lo", rt.split_lo(getattr(ps, store), ps.lo_arena(store)))
+
+
 # the streaming first-layer kernel pays off for long row counts; short passes take the small-row GEMM (one k pass)
 NARROW_MIN_ROWS = int(os.environ.get("ORLK_NARROW_MIN_ROWS", "1024"))
 
@@ -451,6 +477,16 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
         per = max(1, CHAIN_MAX_DESC // n_st)
         for c0 in range(0, G, per):
             plan.add(f"{tag}.fwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes, passes0=3))
+        return
+    same_x0 = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
+    if run.fused_fwd and not skip_head and same_x0 and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0:
+        emit_lo_refresh(rt, plan, ps, run.store)        # (a no-op when the caller has placed it earlier in the step)
+        nh, N = run.nh, ps.layers[0].out_dim
+        plan.add(f"{tag}.fwd_fused.tc", rt.critic_fwd_fused(
+            X=Mat(X[0].ptr, M, ps.layers[0].in_dim, X[0].ld), W=[ps.w(l, 0, run.store) for l in range(nh)],
+            Wlo=[0] + [ps.w_lo(l, 0, run.store) for l in range(1, nh)], bias=[ps.b(l, 0, run.store) for l in range(nh)],
+            H=[run.H[l].data_ptr() for l in range(nh)], gs=ps.block, h_gs=M * N, head_w=ps.w(nh, 0, run.store),
+            head_b=ps.b(nh, 0, run.store), out=run.out.data_ptr(), out_gs=M * run.NS, M=M, N=N, K0=ps.layers[0].in_dim, G=G))
         return
     for l in range(run.nh):
         lay = ps.layers[l]

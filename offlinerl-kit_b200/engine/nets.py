@@ -206,6 +206,21 @@ class ParamSet:
                     self.WT[o:o + lay.w_numel].view(lay.in_dim, lay.out_dim).copy_(src.t())
         self._wt_version = self._host_version()
 
+    # ------------------------------------------------------------------ lo operand words (fused tensor-core passes)
+    def lo_arena(self, store: str) -> torch.Tensor:
+        """Arena shaped like ``store`` ("P", "T" or "WT") holding x - trunc_tf32(x); refreshed inside the step graph by
+        an ``orlk_split_lo`` launch (emit_lo_refresh), never on the host."""
+        name = store + "lo"
+        t = getattr(self, name, None)
+        if t is None:
+            t = self.rt.zeros(self.total)
+            setattr(self, name, t)
+        return t
+
+    def w_lo(self, l: int, g: int = 0, store: str = "P") -> int:
+        lay = self.layers[l]
+        return self._ptr(self.lo_arena(store), lay.w_off + g * lay.w_gs)
+
     def wt(self, l: int, g: int = 0) -> int:
         lay = self.layers[l]
         return self._ptr(self.WT, lay.w_off + g * lay.w_gs)

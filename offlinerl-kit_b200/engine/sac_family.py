@@ -18,7 +18,7 @@ import torch
 from .. import _lib as L
 from .core import Mat, Plan
 from .learner import (Learner, MlpRun, chainable, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
-                      emit_wgrad_adam, linears_of, make_gradbuf)
+                      emit_lo_refresh, emit_wgrad_adam, linears_of, make_gradbuf)
 from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem, pick_cfg
 
 # loss block layout (floats)
@@ -226,7 +226,10 @@ class TwinCriticLearner(Learner):
             if beside_forward is not None:
                 plan.fork()
                 plan.branch(1)
-                plan.add(*beside_forward)
+                if callable(beside_forward):
+                    beside_forward()
+                else:
+                    plan.add(*beside_forward)
                 plan.branch(0)
             fuse_hs = self._can_fuse_head_sample(ar)
             emit_forward(rt, plan, ar, [obs], "A.actor", skip_head=fuse_hs)
@@ -354,7 +357,16 @@ class CQLLearner(TwinCriticLearner):
 
         plan = Plan(rt, "cql")
         noise = self._emit_noise(plan, self.n_normal, self.n_uniform, self.act_lo, self.act_hi, defer=True)
-        self._emit_actor_update(plan, clamp01=False, beside_forward=noise)
+
+        def beside():
+            # beside the actor forward: the noise fill and - the critics are only updated at the END of a step - the lo
+            # words of the online / target critic weights that the fused critic passes fetch by TMA
+            plan.add(*noise)
+            if self.run_critic.fused_fwd:
+                emit_lo_refresh(rt, plan, self.critic_ps, "P")
+            if self.run_target.fused_fwd:
+                emit_lo_refresh(rt, plan, self.critic_ps, "T")
+        self._emit_actor_update(plan, clamp01=False, beside_forward=beside)
 
         # ---- critic phase with the UPDATED actor (cql.py:108-192)
         obs2 = Mat.of(self.obs2)

@@ -772,3 +772,68 @@ def test_compact_rows_is_stable_and_exact(rt, S, p_drop):
     want = src[:, :w][drop == 0]
     assert int(count.item()) == want.shape[0]
     assert torch.equal(dst[:want.shape[0]], want)
+
+
+# ------------------------------------------------------------------------------------------------ fused critic passes
+@pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (2560, 256, 14, 2, 2), (300, 128, 32, 4, 1),
+                                         (2048 + 77, 64, 5, 3, 3)])
+def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
+    """orlk_critic_fwd_fused: every hidden activation and the scalar head of all members against an fp64 evaluation of
+    the same Linear+ReLU stack (nets/mlp.py:22-28, modules/critic_module.py:25-33); 3xTF32 = fp32-grade."""
+    from offlinerlkit_b200.engine.core import Mat
+    gen = torch.Generator().manual_seed(M + N + K0)
+    ldx = (K0 + 3) // 4 * 4
+    X = torch.zeros(M, ldx)
+    X[:, :K0] = torch.randn(M, K0, generator=gen)
+    # one block per member, as ParamSet lays the parameters out: [W0 | b0 | W1 | b1 | ... | head_w | head_b], 4-float aligned
+    def al(n):
+        return (n + 3) // 4 * 4
+    offs, off = [], 0
+    dims = [(N, K0)] + [(N, N)] * (nh - 1) + [(1, N)]
+    for (o, i) in dims:
+        w_off = off; off = al(off + o * i)
+        b_off = off; off = al(off + o)
+        offs.append((w_off, b_off))
+    block = al(off)
+    P = torch.zeros(G * block)
+    Ws, bs = [], []
+    for g in range(G):
+        Wg, bg = [], []
+        for (o, i), (wo, bo) in zip(dims, offs):
+            W = torch.randn(o, i, generator=gen) / math.sqrt(i)
+            b = torch.randn(o, generator=gen) * 0.3
+            P[g * block + wo:g * block + wo + o * i] = W.reshape(-1)
+            P[g * block + bo:g * block + bo + o] = b
+            Wg.append(W); bg.append(b)
+        Ws.append(Wg); bs.append(bg)
+    Xd, Pd = X.to(DEV), P.to(DEV)
+    Plo = torch.full_like(Pd, float("nan"))
+    rt.split_lo(Pd, Plo)()
+    H = [torch.full((G, M, N), float("nan"), device=DEV) for _ in range(nh)]
+    out = torch.full((G, M), float("nan"), device=DEV)
+    base, lo = Pd.data_ptr(), Plo.data_ptr()
+    op = rt.critic_fwd_fused(X=Mat(Xd.data_ptr(), M, K0, ldx), W=[base + 4 * offs[l][0] for l in range(nh)],
+                             Wlo=[0] + [lo + 4 * offs[l][0] for l in range(1, nh)], bias=[base + 4 * offs[l][1] for l in range(nh)],
+                             H=[h.data_ptr() for h in H], gs=block, h_gs=M * N, head_w=base + 4 * offs[nh][0],
+                             head_b=base + 4 * offs[nh][1], out=out.data_ptr(), out_gs=M, M=M, N=N, K0=K0, G=G)
+    for _ in range(2):          # a second launch over the same buffers: barriers / ring state start clean every time
+        op()
+    torch.cuda.synchronize()
+    lo_ref = P - (P.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(Plo.cpu(), lo_ref), "split_lo"
+    for g in range(G):
+        # 3xTF32: ~3e-6 of sum_k |a_k b_k| per layer (the tolerance of the per-layer tensor-core test); errors add up
+        h = X[:, :K0].double()
+        tol = 0.0
+        for l in range(nh + 1):
+            W, b = Ws[g][l].double(), bs[g][l].double()
+            tol += 3e-6 * (h.abs() @ W.abs().t()).max().item()
+            h = h @ W.t() + b
+            if l < nh:
+                h = torch.relu(h)
+                got = H[l][g]
+            else:
+                got = out[g][:, None]
+            assert not torch.isnan(got).any(), f"layer {l} member {g}: unwritten output"
+            err = (got.double().cpu() - h).abs().max().item()
+            assert err <= tol, f"layer {l} member {g}: max err {err:.3e} vs {tol:.3e}"
