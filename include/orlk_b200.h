@@ -204,30 +204,36 @@ int orlk_sizeof_tc_gemm(void);
  *   H_0 = relu(X W_0^T + b_0), H_l = relu(H_{l-1} W_l^T + b_l) (l < n_hidden), out[g][m] = H_last[m] . head_w[g] + head_b[g]
  * on the tensor cores (3xTF32, fp32-grade).  A CTA owns a 128-row strip of one member for the whole pass: accumulators
  * ping-pong in tensor memory, layer l's epilogue writes the A operand tiles of layer l+1 straight into shared memory and
- * stores H_l (needed by the backward pass) with TMA from the same tiles; the head is a dot product in the last epilogue.
+ * stores H_l (needed by the backward pass; H[] all NULL = not stored) with TMA from the same tiles; the head is a dot
+ * product in the last epilogue.  Up to two such passes ("jobs": the online critics on the 7936-row batch and the target
+ * critics on the next-state rows) share one launch, each with its own rows, weights and outputs.
  * Shapes: hidden widths all N (multiple of 32, <= 256), K0 <= 32 input columns, X [M][ldx] shared by all members
- * (16-byte aligned rows), 'oi' weights W_l [N][K] with one member stride `gs` for every parameter tensor, Wlo[l] =
- * W[l] - trunc_tf32(W[l]) for l >= 1 (kept by orlk_split_lo).  Replaces the per-layer launches + head of
- * modules/critic_module.py:25-33 / nets/mlp.py:22-28 on CQL's 7936-row critic batch (policy/model_free/cql.py:133-160).
- * The struct is read on the HOST. */
+ * (16-byte aligned rows), 'oi' weights W_l [N][N] (l >= 1) with one member stride `gs` for every parameter tensor, Wlo[l] =
+ * W[l] - trunc_tf32(W[l]); W0pad / W0pad_lo = the first layer's [N][K0] weights zero-padded to [G][N][32] and their lo
+ * words (all three kept by orlk_fused_prep).  Replaces the per-layer launches + head of
+ * modules/critic_module.py:25-33 / nets/mlp.py:22-28 on CQL's critic batch and target rows
+ * (policy/model_free/cql.py:108-160).  The structs are read on the HOST. */
 #define ORLK_FUSED_MAX_LAYERS 4
 typedef struct OrlkFusedFwd {
     const float* X; int64_t ldx;
-    const float* W[ORLK_FUSED_MAX_LAYERS];
+    const float* W0pad; const float* W0pad_lo;    /* [G][N][32] */
+    const float* W[ORLK_FUSED_MAX_LAYERS];        /* [0] unused */
     const float* Wlo[ORLK_FUSED_MAX_LAYERS];      /* [0] unused */
     const float* bias[ORLK_FUSED_MAX_LAYERS];
-    float* H[ORLK_FUSED_MAX_LAYERS];              /* [G][M][N] each */
+    float* H[ORLK_FUSED_MAX_LAYERS];              /* [G][M][N] each, or all NULL */
     int64_t gs, h_gs;                             /* member strides (floats) of the parameters / of H */
     const float* head_w; const float* head_b;
     float* out; int64_t out_gs;                   /* [G][M] */
     int32_t M, N, K0, G, n_hidden, pad_;
 } OrlkFusedFwd;
 int orlk_fused_init(void); /* once per process, outside stream capture */
-int orlk_critic_fwd_fused(const OrlkFusedFwd* params_host, void* stream);
+int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs_host, int n_jobs, void* stream);
 int orlk_sizeof_fused_fwd(void);
-/* dst[i] = src[i] - trunc_tf32(src[i]): the low operand words of the 3xTF32 products, kept next to the weights so that
- * the fused passes fetch them by TMA instead of recomputing them in every CTA.  16-byte aligned arrays. */
-int orlk_split_lo(const float* src, float* dst, int64_t n, void* stream);
+/* Derived operand copies of a parameter arena for the fused passes, one launch per step:
+ *   dst_lo[i] = src[i] - trunc_tf32(src[i]) for the whole arena (n floats, 16-byte aligned), and - when W0 != NULL -
+ *   w0pad[0][g][o][k] = W0[g*gs + o*K0 + k] (k < K0, else 0), w0pad[1] = its lo words  (W0 inside [src, src + n)). */
+int orlk_fused_prep(const float* src, float* dst_lo, int64_t n, const float* W0, int64_t gs, int N, int K0, int G,
+                    float* w0pad, void* stream);
 
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
  * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).

@@ -69,7 +69,7 @@ FUSED_MAX_LAYERS = 4
 
 
 class FusedFwd(C.Structure):
-    _fields_ = [("X", C.c_void_p), ("ldx", C.c_int64),
+    _fields_ = [("X", C.c_void_p), ("ldx", C.c_int64), ("W0pad", C.c_void_p), ("W0pad_lo", C.c_void_p),
                 ("W", C.c_void_p * FUSED_MAX_LAYERS), ("Wlo", C.c_void_p * FUSED_MAX_LAYERS),
                 ("bias", C.c_void_p * FUSED_MAX_LAYERS), ("H", C.c_void_p * FUSED_MAX_LAYERS),
                 ("gs", C.c_int64), ("h_gs", C.c_int64),
@@ -110,8 +110,8 @@ _PROTOS = {
     "orlk_gemm_chain": [_P, _I, _I, _I, _I, _P], "orlk_gemm_chain_init": [],
     "orlk_tc_init": [], "orlk_tc_gemm": [C.POINTER(TcGemm), _P], "orlk_tc_effective_splits": [_I, _I], "orlk_tc_set_trace": [_P],
     "orlk_sizeof_tc_gemm": [],
-    "orlk_fused_init": [], "orlk_critic_fwd_fused": [C.POINTER(FusedFwd), _P], "orlk_sizeof_fused_fwd": [],
-    "orlk_split_lo": [_P, _P, _L, _P],
+    "orlk_fused_init": [], "orlk_critic_fwd_fused": [C.POINTER(FusedFwd), _I, _P], "orlk_sizeof_fused_fwd": [],
+    "orlk_fused_prep": [_P, _P, _L, _P, _L, _I, _I, _I, _P, _P],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_concat_rows": [_P, _I, _I, _P],

@@ -36,23 +36,44 @@ enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 3, BAR_BFULL = 5, BAR_BEMPTY = 7, 
 
 struct FwdMaps {
     CUtensorMap x;                // X [M][K0]: box 32 (k, zero filled past K0) x 128 rows
+    CUtensorMap w0, w0lo;         // zero-padded first-layer weights [G][N][32] and their lo words: box 32 x N
     CUtensorMap w[MAXL - 1];      // W_l [G][N][N], l >= 1: box 32 (k) x N
     CUtensorMap wlo[MAXL - 1];
     CUtensorMap h[MAXL];          // H_l [G][M][N]: box 32 x 32 (store)
 };
 
 struct FwdParams {
-    const float* W0; int64_t gs;          // first-layer weights [N][K0] of member 0; member stride of every parameter tensor
+    int64_t gs;                           // member stride of the bias / head tensors
     const float* bias[MAXL];
     const float* head_w; const float* head_b;
     float* out; int64_t out_gs;
-    int M, N, K0, G, L, tiles_m;
+    int M, N, G, L, tiles_m, store_h;
+    int no_store;                         // experiment (ORLK_FUSED_NO_STORE=1): skip the H stores, results are then incomplete
+    unsigned long long* trace;            // profiling aid (orlk_tc_set_trace): 128 clock stamps per CTA, NULL in normal operation
 };
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define FZ_GSTAMP(slot)                                                                                \
+    do {                                                                                               \
+        if (p.trace != nullptr) p.trace[(int64_t)blockIdx.x * 128 + (slot)] = gtimer_ns();             \
+    } while (0)
+#define FZ_STAMP(slot)                                                                                          \
+    do {                                                                                                        \
+        if (p.trace != nullptr) p.trace[(int64_t)blockIdx.x * 128 + (slot)] = (unsigned long long)clock64();    \
+    } while (0)
 
 __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// Up to two independent passes ("jobs") share one launch: CTAs [0, ctas0) run job 0 (the online critics on the 7936-row
+// batch), the rest job 1 (the target critics on the next-state rows, no activations stored) - side by side instead of
+// one pass starving the other of SMs.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
+k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdMaps maps1,
+             const __grid_constant__ FwdParams p0, const __grid_constant__ FwdParams p1, const int ctas0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // SWIZZLE_128B tiles: 1024-byte aligned
     uint8_t* b_base = base + 2 * A_STAGE;
@@ -70,19 +91,28 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x / p.tiles_m;
-    const int tile_m = blockIdx.x - g * p.tiles_m;
+    const bool job1 = (int)blockIdx.x >= ctas0;
+    const FwdMaps& maps = job1 ? maps1 : maps0;
+    const FwdParams& p = job1 ? p1 : p0;
+    const int cta = job1 ? (int)blockIdx.x - ctas0 : (int)blockIdx.x;
+    const int g = cta / p.tiles_m;
+    const int tile_m = cta - g * p.tiles_m;
     const int N = p.N, L = p.L;
     const int KS = N / BK;                      // k-slabs of a hidden layer = 32-column chunks of an accumulator
+    const bool store_h = p.store_h != 0 && p.no_store == 0;
 
     // ---------------------------------------------------------------- prologue (touches no global data)
+    if (threadIdx.x == 0) { FZ_STAMP(0); FZ_GSTAMP(4); }
     if (threadIdx.x == 32) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w0lo) : "memory");
         for (int l = 1; l < L; ++l) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w[l - 1]) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wlo[l - 1]) : "memory");
         }
-        for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.h[l]) : "memory");
+        if (store_h)
+            for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.h[l]) : "memory");
     }
     if (warp == 1 && lane == 0) {
         mbar_init(bar(BAR_X), 1);
@@ -101,6 +131,7 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     orlk::pdl_wait();                           // X and the weights come from earlier kernels of the step
+    if (threadIdx.x == 0) { FZ_STAMP(1); FZ_GSTAMP(5); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -112,11 +143,15 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
             mbar_expect_tx(bar(BAR_X), A_TILE);
             tma_load_3d(smem_u32(a_hi(0)), &maps.x, bar(BAR_X), 0, tile_m * BM, 0);
             const uint32_t tx = 2u * (uint32_t)N * BK * 4;
-            int bi = 1;                         // B fill 0 (the first layer's weights) is staged by the epilogue warps
+            mbar_expect_tx(bar(BAR_BFULL + 0), tx);             // fill 0: the padded first-layer weights
+            tma_load_3d(smem_u32(b_hi(0)), &maps.w0, bar(BAR_BFULL + 0), 0, 0, g);
+            tma_load_3d(smem_u32(b_lo(0)), &maps.w0lo, bar(BAR_BFULL + 0), 0, 0, g);
+            int bi = 1;
             for (int l = 1; l < L; ++l) {
                 for (int j = 0; j < KS; ++j, ++bi) {
                     const int s = bi & 1;
                     mbar_wait(bar(BAR_BEMPTY + s), ((bi >> 1) & 1) ^ 1);
+                    if (bi < 32) FZ_STAMP(80 + bi);
                     mbar_expect_tx(bar(BAR_BFULL + s), tx);
                     tma_load_3d(smem_u32(b_hi(s)), &maps.w[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
                     tma_load_3d(smem_u32(b_lo(s)), &maps.wlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
@@ -138,8 +173,10 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
                     const int fa = sa ? fa1 : fa0;
                     mbar_wait(bar(BAR_AFULL + sa), fa & 1);
                     if (sa) ++fa1; else ++fa0;
+                    if (bi < 32) FZ_STAMP(16 + bi);
                     const int sb = bi & 1;
                     mbar_wait(bar(BAR_BFULL + sb), (bi >> 1) & 1);
+                    if (bi < 32) FZ_STAMP(48 + bi);
                     tc_fence_after();
                     const uint64_t ad = smem_desc_sw128(smem_u32(a_hi(sa))), adl = smem_desc_sw128(smem_u32(a_lo(sa)));
                     const uint64_t bd = smem_desc_sw128(smem_u32(b_hi(sb))), bdl = smem_desc_sw128(smem_u32(b_lo(sb)));
@@ -165,26 +202,10 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
         const int t = threadIdx.x - 64;             // 0..255
         const int row = q * 32 + lane;
         const int m = tile_m * BM + row;
-        // biases, head weights, first-layer weights (K-major SWIZZLE_128B tile: 16-byte chunk c of row n at c ^ (n & 7))
 #pragma unroll
         for (int l = 0; l < MAXL; ++l)
             if (l < L) bias_s[l * NMAX + t] = t < N ? __ldg(p.bias[l] + (int64_t)g * p.gs + t) : 0.f;
         headw_s[t] = t < N ? __ldg(p.head_w + (int64_t)g * p.gs + t) : 0.f;
-        if (t < N) {
-            const float* wr = p.W0 + (int64_t)g * p.gs + (int64_t)t * p.K0;
-            float4* bh = reinterpret_cast<float4*>(b_hi(0));
-            float4* bl = reinterpret_cast<float4*>(b_lo(0));
-#pragma unroll
-            for (int c = 0; c < BK / 4; ++c) {
-                float4 v;
-                v.x = 4 * c + 0 < p.K0 ? __ldg(wr + 4 * c + 0) : 0.f;
-                v.y = 4 * c + 1 < p.K0 ? __ldg(wr + 4 * c + 1) : 0.f;
-                v.z = 4 * c + 2 < p.K0 ? __ldg(wr + 4 * c + 2) : 0.f;
-                v.w = 4 * c + 3 < p.K0 ? __ldg(wr + 4 * c + 3) : 0.f;
-                bh[t * 8 + (c ^ (t & 7))] = v;
-                bl[t * 8 + (c ^ (t & 7))] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
-            }
-        }
         if (grp == 0) {         // lo part of the X tile: this warp's 32 rows = 256 float4 (hi and lo tiles share the layout)
             mbar_wait(bar(BAR_X), 0);
             const float4* xh = reinterpret_cast<const float4*>(a_hi(0)) + q * 256;
@@ -194,11 +215,12 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
             for (int i = 0; i < 8; ++i) v[i] = xh[i * 32 + lane];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xl[i * 32 + lane] = make_float4(lo_of(v[i].x), lo_of(v[i].y), lo_of(v[i].z), lo_of(v[i].w));
+            fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_AFULL + 0));
         }
-        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (t == 0) mbar_arrive(bar(BAR_BFULL + 0));
-        if (grp == 0 && lane == 0) mbar_arrive(bar(BAR_AFULL + 0));
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // bias_s / headw_s complete
+        if (t == 0) FZ_STAMP(2);
 
         int fe = grp == 0 ? 1 : 0;                  // fills of this group's A stage so far
         float qacc = 0.f;
@@ -209,6 +231,7 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
             const bool last = l == L - 1;
             mbar_wait(bar(BAR_ACC + (l & 1)), (l >> 1) & 1);
             tc_fence_after();
+            if (t == 0) FZ_STAMP(112 + l);
             if (last) orlk::pdl_trigger();          // every MMA of this strip has completed
             const float* bl = bias_s + l * NMAX;
             for (int c = grp; c < KS; c += 2) {
@@ -224,35 +247,54 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
                     x[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f);
                     x[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
                 }
-                // the stage's previous content: read by the MMAs of slab c - 2 (or of the previous layer) and by this
-                // warp's own TMA store
-                if (!last && fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-                float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
-                if (!last) {
-                    float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                        lrow[j4 ^ (lane & 7)] = make_float4(lo_of(x[4 * j4]), lo_of(x[4 * j4 + 1]), lo_of(x[4 * j4 + 2]),
-                                                            lo_of(x[4 * j4 + 3]));
-                } else {
+                if (last) {
+                    // every MMA has completed: the whole B ring is idle, so each of this warp's (up to four) chunks gets
+                    // its own 4 KB store tile there and no store ever waits for the previous one
                     const float* hw = headw_s + 32 * c;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) qacc = fmaf(x[j], hw[j], qacc);
+                    if (store_h) {
+                        uint8_t* tile = b_base + ((warp - 2) * 4 + (c >> 1)) * 4096;
+                        float4* hrow = reinterpret_cast<float4*>(tile + lane * 128);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&maps.h[l], smem_u32(tile), 32 * c, tile_m * BM + q * 32, g, 0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    continue;
                 }
+                // the stage's previous content: read by the MMAs of slab c - 2 (or of the previous layer) and by this
+                // warp's own TMA store
+                if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
+                if (store_h) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
+                float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
+                float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    lrow[j4 ^ (lane & 7)] = make_float4(lo_of(x[4 * j4]), lo_of(x[4 * j4 + 1]), lo_of(x[4 * j4 + 2]),
+                                                        lo_of(x[4 * j4 + 3]));
                 tc_fence_before();                  // the TMEM reads above are ordered before the next layer's MMAs
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (!last) mbar_arrive(bar(BAR_AFULL + grp));
-                    tma_store_4d(&maps.h[l], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    mbar_arrive(bar(BAR_AFULL + grp));
+                    if (store_h) {
+                        tma_store_4d(&maps.h[l], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
-                if (!last) ++fe;
+                ++fe;
             }
         }
         // scalar head: even-chunk partial (warps 2-5) + odd-chunk partial (warps 6-9) + bias, fixed order
@@ -261,6 +303,7 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
         if (grp == 0 && m < p.M) p.out[(int64_t)g * p.out_gs + m] = (qacc + qpart_s[row]) + __ldg(p.head_b + (int64_t)g * p.gs);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tiles must outlive the stores
     }
+    if (threadIdx.x == 64) { FZ_STAMP(3); FZ_GSTAMP(6); }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -268,19 +311,82 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps, const FwdParams p) {
     }
 }
 
-// lo[i] = x[i] - trunc_tf32(x[i]) (exact in fp32): the second operand word of the 3xTF32 products
-__global__ void k_split_lo(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+// Once per step, off the critical path: lo[i] = x[i] - trunc_tf32(x[i]) (exact in fp32) over a whole parameter arena - the
+// second operand word of the 3xTF32 products - and the zero-padded copy [G][N][32] (+ lo words) of the first layer's
+// [N][K0] weights, whose rows TMA cannot address (pitch K0 floats).
+__global__ void k_fused_prep(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int nb_split,
+                             const float* __restrict__ W0, int64_t gs, int N, int K0, int G, float* __restrict__ w0pad) {
     orlk::pdl_enter();
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i);
-        *reinterpret_cast<float4*>(dst + i) = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
-    } else {
-        for (int64_t j = i; j < n; ++j) dst[j] = lo_of(src[j]);
+    if ((int)blockIdx.x < nb_split) {
+        const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (i + 3 < n) {
+            const float4 v = *reinterpret_cast<const float4*>(src + i);
+            *reinterpret_cast<float4*>(dst + i) = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+        } else {
+            for (int64_t j = i; j < n; ++j) dst[j] = lo_of(src[j]);
+        }
+        return;
+    }
+    const int64_t total = (int64_t)G * N * BK;
+    const int64_t i = ((int64_t)blockIdx.x - nb_split) * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int k = (int)(i % BK);
+        const int64_t gn = i / BK;
+        const int nn = (int)(gn % N), g = (int)(gn / N);
+        const float v = k < K0 ? src[(W0 - src) + (int64_t)g * gs + (int64_t)nn * K0 + k] : 0.f;
+        w0pad[i] = v;
+        w0pad[total + i] = lo_of(v);
     }
 }
 
 constexpr size_t FWD_SMEM = 1024 + RING + FIXED;
+
+int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
+    ORLK_REQUIRE(q->M > 0 && q->G > 0, "sizes");
+    ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
+    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
+    ORLK_REQUIRE(q->K0 >= 1 && q->K0 <= BK, "first-layer fan-in must be <= 32");
+    ORLK_REQUIRE(q->ldx % 4 == 0 && aligned16(q->X), "X rows must be 16-byte aligned");
+    ORLK_REQUIRE(q->gs % 4 == 0 && q->h_gs % 4 == 0, "member strides must be multiples of 4 floats");
+    ORLK_REQUIRE(q->head_w != nullptr && q->head_b != nullptr && q->out != nullptr, "scalar head");
+    ORLK_REQUIRE(q->W0pad != nullptr && q->W0pad_lo != nullptr && aligned16(q->W0pad) && aligned16(q->W0pad_lo), "padded first-layer weights");
+    memset(maps, 0, sizeof(*maps));
+    memset(p, 0, sizeof(*p));
+    int rc = make_map(&maps->x, q->X, q->ldx, 0, q->M, q->K0, 1, BM);
+    if (rc) return rc;
+    rc = make_map(&maps->w0, q->W0pad, BK, (int64_t)q->N * BK, q->N, BK, q->G, q->N);
+    if (rc) return rc;
+    rc = make_map(&maps->w0lo, q->W0pad_lo, BK, (int64_t)q->N * BK, q->N, BK, q->G, q->N);
+    if (rc) return rc;
+    const bool store = q->H[0] != nullptr;
+    for (int l = 0; l < q->n_hidden; ++l) {
+        ORLK_REQUIRE(q->bias[l] != nullptr, "bias pointers");
+        ORLK_REQUIRE((q->H[l] != nullptr) == store, "H: all layers or none");
+        if (l >= 1) {
+            ORLK_REQUIRE(q->W[l] != nullptr && q->Wlo[l] != nullptr && aligned16(q->W[l]) && aligned16(q->Wlo[l]),
+                         "hidden weights (and lo copies) must be 16-byte aligned");
+            rc = make_map(&maps->w[l - 1], q->W[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            if (rc) return rc;
+            rc = make_map(&maps->wlo[l - 1], q->Wlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            if (rc) return rc;
+        }
+        if (store) {
+            ORLK_REQUIRE(aligned16(q->H[l]), "H must be 16-byte aligned");
+            rc = make_map_c(&maps->h[l], q->H[l], q->N, q->h_gs, 0, q->M, q->N, q->G, 1);
+            if (rc) return rc;
+        }
+        p->bias[l] = q->bias[l];
+    }
+    p->gs = q->gs;
+    p->head_w = q->head_w; p->head_b = q->head_b;
+    p->out = q->out; p->out_gs = q->out_gs;
+    p->M = q->M; p->N = q->N; p->G = q->G; p->L = q->n_hidden;
+    p->tiles_m = (q->M + BM - 1) / BM;
+    p->store_h = store ? 1 : 0;
+    p->trace = orlk::trace_buffer();
+    { const char* e = getenv("ORLK_FUSED_NO_STORE"); p->no_store = e ? atoi(e) : 0; }
+    return 0;
+}
 
 }  // namespace
 
@@ -290,49 +396,30 @@ extern "C" int orlk_fused_init(void) {
     return check(cudaFuncSetAttribute(k_critic_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
 }
 
-extern "C" int orlk_split_lo(const float* src, float* dst, int64_t n, void* stream) {
-    ORLK_REQUIRE(src != nullptr && dst != nullptr && n > 0, "split_lo arguments");
-    ORLK_REQUIRE(aligned16(src) && aligned16(dst), "split_lo needs 16-byte aligned arrays");
+extern "C" int orlk_fused_prep(const float* src, float* dst_lo, int64_t n, const float* W0, int64_t gs, int N, int K0, int G,
+                               float* w0pad, void* stream) {
+    ORLK_REQUIRE(src != nullptr && dst_lo != nullptr && n > 0, "fused_prep arguments");
+    ORLK_REQUIRE(aligned16(src) && aligned16(dst_lo), "fused_prep needs 16-byte aligned arrays");
+    ORLK_REQUIRE(W0 == nullptr || (w0pad != nullptr && N > 0 && K0 > 0 && K0 <= BK && G > 0 && W0 >= src && W0 < src + n),
+                 "first-layer weights must lie inside the arena");
     const int64_t vec = (n + 3) / 4;
-    orlk::launch(k_split_lo, dim3((unsigned)((vec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, n);
-    return check_launch("k_split_lo");
+    const int nb_split = (int)((vec + 255) / 256);
+    const int nb_pad = W0 != nullptr ? (int)(((int64_t)G * N * BK + 255) / 256) : 0;
+    orlk::launch(k_fused_prep, dim3((unsigned)(nb_split + nb_pad)), dim3(256), 0, (cudaStream_t)stream, src, dst_lo, n, nb_split, W0, gs,
+                 N, K0, G, w0pad);
+    return check_launch("k_fused_prep");
 }
 
-extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* q, void* stream) {
-    ORLK_REQUIRE(q != nullptr, "params");
-    ORLK_REQUIRE(q->M > 0 && q->G > 0, "sizes");
-    ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
-    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
-    ORLK_REQUIRE(q->K0 >= 1 && q->K0 <= BK, "first-layer fan-in must be <= 32");
-    ORLK_REQUIRE(q->ldx % 4 == 0 && aligned16(q->X), "X rows must be 16-byte aligned");
-    ORLK_REQUIRE(q->gs % 4 == 0 && q->h_gs % 4 == 0, "member strides must be multiples of 4 floats");
-    ORLK_REQUIRE(q->head_w != nullptr && q->head_b != nullptr && q->out != nullptr, "scalar head");
-    FwdMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    int rc = make_map(&maps.x, q->X, q->ldx, 0, q->M, q->K0, 1, BM);
-    if (rc) return rc;
-    FwdParams p;
-    memset(&p, 0, sizeof(p));
-    for (int l = 0; l < q->n_hidden; ++l) {
-        ORLK_REQUIRE(q->W[l] != nullptr && q->bias[l] != nullptr && q->H[l] != nullptr, "layer pointers");
-        ORLK_REQUIRE(aligned16(q->H[l]), "H must be 16-byte aligned");
-        if (l >= 1) {
-            ORLK_REQUIRE(q->Wlo[l] != nullptr && aligned16(q->W[l]) && aligned16(q->Wlo[l]), "hidden weights (and lo copies) must be 16-byte aligned");
-            rc = make_map(&maps.w[l - 1], q->W[l], q->N, q->gs, q->N, q->N, q->G, q->N);
-            if (rc) return rc;
-            rc = make_map(&maps.wlo[l - 1], q->Wlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
-            if (rc) return rc;
-        }
-        rc = make_map_c(&maps.h[l], q->H[l], q->N, q->h_gs, 0, q->M, q->N, q->G, 1);
+extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs, int n_jobs, void* stream) {
+    ORLK_REQUIRE(jobs != nullptr && (n_jobs == 1 || n_jobs == 2), "one or two jobs");
+    static FwdMaps maps[2];         // (host scratch; launches are issued from one thread per process)
+    FwdParams p[2];
+    for (int j = 0; j < 2; ++j) {
+        const int rc = fill_fwd_job(&jobs[j < n_jobs ? j : 0], &maps[j], &p[j]);
         if (rc) return rc;
-        p.bias[l] = q->bias[l];
     }
-    p.W0 = q->W[0]; p.gs = q->gs;
-    p.head_w = q->head_w; p.head_b = q->head_b;
-    p.out = q->out; p.out_gs = q->out_gs;
-    p.M = q->M; p.N = q->N; p.K0 = q->K0; p.G = q->G; p.L = q->n_hidden;
-    p.tiles_m = (q->M + BM - 1) / BM;
-    const int grid = q->G * p.tiles_m;
-    orlk::launch(k_critic_fwd, dim3(grid), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps, p);
+    const int ctas0 = p[0].G * p[0].tiles_m;
+    const int grid = ctas0 + (n_jobs == 2 ? p[1].G * p[1].tiles_m : 0);
+    orlk::launch(k_critic_fwd, dim3(grid), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps[0], maps[1], p[0], p[1], ctas0);
     return check_launch("k_critic_fwd");
 }

@@ -214,24 +214,42 @@ class Runtime:
         qp = _ctypes_pointer(q)      # the struct is read on the host at every launch: keep it alive in the closure
         return lambda: L.call("orlk_tc_gemm", qp, self.cur)
 
-    def critic_fwd_fused(self, *, X: Mat, W: Sequence[int], Wlo: Sequence[int], bias: Sequence[int], H: Sequence[int],
-                         gs: int, h_gs: int, head_w: int, head_b: int, out: int, out_gs: int, M: int, N: int, K0: int,
-                         G: int) -> Callable[[], None]:
-        """Whole Linear+ReLU critic pass + scalar head for all members in one tcgen05 launch (csrc/orlk_fused.cu)."""
-        q = L.FusedFwd()
-        q.X, q.ldx = X.ptr, X.ld
-        for l in range(len(W)):
-            q.W[l], q.Wlo[l], q.bias[l], q.H[l] = W[l], (Wlo[l] or None), bias[l], H[l]
-        q.gs, q.h_gs = gs, h_gs
-        q.head_w, q.head_b, q.out, q.out_gs = head_w, head_b, out, out_gs
-        q.M, q.N, q.K0, q.G, q.n_hidden = M, N, K0, G, len(W)
-        qp = _ctypes_pointer(q)
-        return lambda: L.call("orlk_critic_fwd_fused", qp, self.cur)
+    @staticmethod
+    def fused_fwd_job(*, X: Mat, W0pad: int, W0pad_lo: int, W: Sequence[int], Wlo: Sequence[int], bias: Sequence[int],
+                      H: Optional[Sequence[int]], gs: int, h_gs: int, head_w: int, head_b: int, out: int, out_gs: int,
+                      M: int, N: int, K0: int, G: int) -> dict:
+        """One pass of ``critic_fwd_fused``: W / Wlo / bias / H are per hidden layer (W[0], Wlo[0] unused: the first layer
+        reads the padded copies); H = None keeps no activations (target / inference pass)."""
+        return dict(X=X, W0pad=W0pad, W0pad_lo=W0pad_lo, W=list(W), Wlo=list(Wlo), bias=list(bias),
+                    H=list(H) if H is not None else None, gs=gs, h_gs=h_gs, head_w=head_w, head_b=head_b, out=out,
+                    out_gs=out_gs, M=M, N=N, K0=K0, G=G)
 
-    def split_lo(self, src: torch.Tensor, dst: torch.Tensor) -> Callable[[], None]:
-        """dst = src - trunc_tf32(src) over a whole parameter arena (the lo operand words of the fused passes)."""
-        sp, dp, n = C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel()
-        return lambda: L.call("orlk_split_lo", sp, dp, n, self.cur)
+    def critic_fwd_fused(self, jobs: Sequence[dict]) -> Callable[[], None]:
+        """Whole Linear+ReLU critic passes + scalar heads for all members in ONE tcgen05 launch (csrc/orlk_fused.cu);
+        one or two jobs (``fused_fwd_job``) side by side."""
+        assert 1 <= len(jobs) <= 2
+        arr = (L.FusedFwd * len(jobs))()
+        for q, j in zip(arr, jobs):
+            q.X, q.ldx = j["X"].ptr, j["X"].ld
+            q.W0pad, q.W0pad_lo = j["W0pad"], j["W0pad_lo"]
+            for l in range(len(j["bias"])):
+                q.W[l], q.Wlo[l], q.bias[l] = (j["W"][l] or None), (j["Wlo"][l] or None), j["bias"][l]
+                q.H[l] = j["H"][l] if j["H"] is not None else None
+            q.gs, q.h_gs = j["gs"], j["h_gs"]
+            q.head_w, q.head_b, q.out, q.out_gs = j["head_w"], j["head_b"], j["out"], j["out_gs"]
+            q.M, q.N, q.K0, q.G, q.n_hidden = j["M"], j["N"], j["K0"], j["G"], len(j["bias"])
+        n = len(jobs)
+        return lambda: L.call("orlk_critic_fwd_fused", arr, n, self.cur)
+
+    def fused_prep(self, src: torch.Tensor, dst_lo: torch.Tensor, W0: int = 0, gs: int = 0, N: int = 0, K0: int = 0, G: int = 0,
+                   w0pad: Optional[torch.Tensor] = None) -> Callable[[], None]:
+        """dst_lo = src - trunc_tf32(src) over a whole parameter arena, and the zero-padded [2][G][N][32] copy (+ lo words)
+        of the first layer's weights: the operand copies the fused passes fetch by TMA."""
+        sp, dp, n = C.c_void_p(src.data_ptr()), C.c_void_p(dst_lo.data_ptr()), src.numel()
+        wp = C.c_void_p(w0pad.data_ptr()) if w0pad is not None else None
+        w0 = C.c_void_p(W0) if W0 else None
+        keep = (src, dst_lo, w0pad)
+        return lambda keep=keep: L.call("orlk_fused_prep", sp, dp, n, w0, gs, N, K0, G, wp, self.cur)
 
     @staticmethod
     def effective_splits(K: int, want: int, cfg: int) -> int:

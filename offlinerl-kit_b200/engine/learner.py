@@ -323,7 +323,8 @@ class MlpRun:
     """
 
     def __init__(self, rt: Runtime, ps: ParamSet, M: int, n_hidden: int, need_grad: bool, store: str = "P",
-                 tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None):
+                 tc_passes: int = 0, members: Optional[int] = None, share_forward: Optional["MlpRun"] = None,
+                 fused_min_rows: int = TC_MIN_ROWS):
         self.ps, self.M, self.nh, self.store = ps, M, n_hidden, store
         self.tc = tc_passes if M >= TC_MIN_ROWS_FWD else 0
         # arithmetic of the small-row kernel: 0 = fp32 FFMA (default: exact fp32, and as fast in the step because those
@@ -383,7 +384,8 @@ class MlpRun:
         # the whole forward pass (all hidden layers + scalar head) of a long-row Linear+ReLU stack as ONE tensor-core launch
         # that keeps the activations on the SM between layers (csrc/orlk_fused.cu); fp32-grade (3xTF32) mode only
         widths = {lays[l].out_dim for l in range(n_hidden)}
-        self.fused_fwd = (FUSED_FWD and tc_passes == 3 and M >= TC_MIN_ROWS and not self.ens_tc and share_forward is None
+        self.keep_h = True              # False: the fused forward does not store the activations (set by the owner)
+        self.fused_fwd = (FUSED_FWD and tc_passes == 3 and M >= fused_min_rows and not self.ens_tc and share_forward is None
                           and 2 <= n_hidden <= L.FUSED_MAX_LAYERS and self.has_head and self.NS == 1
                           and all(lay.layout == "oi" for lay in lays[:n_hidden + 1])
                           and len(widths) == 1 and lays[0].out_dim % 32 == 0 and 32 <= lays[0].out_dim <= 256
@@ -444,15 +446,49 @@ FUSED_FWD = os.environ.get("ORLK_FUSED_FWD", "1") != "0"
 
 
 def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
-    """lo words of a parameter arena for the fused passes (orlk_split_lo); once per plan and store, placed by the caller
-    after the last update of that arena and before its first fused use."""
+    """Derived operand copies of a parameter arena for the fused passes (orlk_fused_prep: lo words + padded first layer);
+    once per plan and store, placed by the caller after the last update of that arena and before its first fused use."""
     done = plan.__dict__.setdefault("_lo_fresh", set())
     key = (id(ps), store)
     if key in done:
         return
     done.add(key)
     plan.keep.append(ps)
-    plan.add(f"{ps.name}.{store}.split_lo", rt.split_lo(getattr(ps, store), ps.lo_arena(store)))
+    lay0 = ps.layers[0]
+    plan.add(f"{ps.name}.{store}.fused_prep", rt.fused_prep(getattr(ps, store), ps.lo_arena(store), W0=ps.w(0, 0, store),
+                                                            gs=lay0.w_gs, N=lay0.out_dim, K0=lay0.in_dim, G=ps.G,
+                                                            w0pad=ps.w0_pad(store)))
+
+
+def fused_fwd_job(rt: Runtime, run: "MlpRun", X: Mat) -> dict:
+    """``run``'s whole forward pass (hidden layers + scalar head, all members) as one job of a fused launch."""
+    ps, nh, M, G = run.ps, run.nh, run.M, run.G
+    N, K0 = ps.layers[0].out_dim, ps.layers[0].in_dim
+    pad = ps.w0_pad(run.store)
+    return rt.fused_fwd_job(
+        X=Mat(X.ptr, M, K0, X.ld), W0pad=pad[0].data_ptr(), W0pad_lo=pad[1].data_ptr(),
+        W=[0] + [ps.w(l, 0, run.store) for l in range(1, nh)], Wlo=[0] + [ps.w_lo(l, 0, run.store) for l in range(1, nh)],
+        bias=[ps.b(l, 0, run.store) for l in range(nh)], H=[run.H[l].data_ptr() for l in range(nh)] if run.keep_h else None,
+        gs=ps.block, h_gs=M * N, head_w=ps.w(nh, 0, run.store), head_b=ps.b(nh, 0, run.store), out=run.out.data_ptr(),
+        out_gs=M * run.NS, M=M, N=N, K0=K0, G=G)
+
+
+def fusable_x(run: "MlpRun", X: Sequence[Mat]) -> bool:
+    return (run.fused_fwd and all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X) and X[0].ld % 4 == 0
+            and X[0].ptr % 16 == 0)
+
+
+def emit_forward_pair(rt: Runtime, plan: Plan, run_a: "MlpRun", Xa: Sequence[Mat], tag_a: str, run_b: "MlpRun",
+                      Xb: Sequence[Mat], tag_b: str) -> bool:
+    """Two independent forward passes (e.g. the online critics on the big batch and the target critics on the next-state
+    rows) as the two jobs of ONE fused launch; False (nothing emitted) when either pass is not fusable."""
+    if not (fusable_x(run_a, Xa) and fusable_x(run_b, Xb)):
+        return False
+    plan.keep += [run_a, run_b, [x.keep for x in Xa], [x.keep for x in Xb]]
+    emit_lo_refresh(rt, plan, run_a.ps, run_a.store)
+    emit_lo_refresh(rt, plan, run_b.ps, run_b.store)
+    plan.add(f"{tag_a}+{tag_b}.fwd_fused.tc", rt.critic_fwd_fused([fused_fwd_job(rt, run_a, Xa[0]), fused_fwd_job(rt, run_b, Xb[0])]))
+    return True
 
 
 # the streaming first-layer kernel pays off for long row counts; short passes take the small-row GEMM (one k pass)
@@ -478,15 +514,9 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
         for c0 in range(0, G, per):
             plan.add(f"{tag}.fwd_chain" + (f"{c0}" if c0 else ""), rt.gemm_chain(chains[c0:c0 + per], run.passes, passes0=3))
         return
-    same_x0 = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
-    if run.fused_fwd and not skip_head and same_x0 and X[0].ld % 4 == 0 and X[0].ptr % 16 == 0:
+    if not skip_head and fusable_x(run, X):
         emit_lo_refresh(rt, plan, ps, run.store)        # (a no-op when the caller has placed it earlier in the step)
-        nh, N = run.nh, ps.layers[0].out_dim
-        plan.add(f"{tag}.fwd_fused.tc", rt.critic_fwd_fused(
-            X=Mat(X[0].ptr, M, ps.layers[0].in_dim, X[0].ld), W=[ps.w(l, 0, run.store) for l in range(nh)],
-            Wlo=[0] + [ps.w_lo(l, 0, run.store) for l in range(1, nh)], bias=[ps.b(l, 0, run.store) for l in range(nh)],
-            H=[run.H[l].data_ptr() for l in range(nh)], gs=ps.block, h_gs=M * N, head_w=ps.w(nh, 0, run.store),
-            head_b=ps.b(nh, 0, run.store), out=run.out.data_ptr(), out_gs=M * run.NS, M=M, N=N, K0=ps.layers[0].in_dim, G=G))
+        plan.add(f"{tag}.fwd_fused.tc", rt.critic_fwd_fused([fused_fwd_job(rt, run, X[0])]))
         return
     for l in range(run.nh):
         lay = ps.layers[l]

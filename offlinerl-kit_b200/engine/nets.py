@@ -209,7 +209,7 @@ class ParamSet:
     # ------------------------------------------------------------------ lo operand words (fused tensor-core passes)
     def lo_arena(self, store: str) -> torch.Tensor:
         """Arena shaped like ``store`` ("P", "T" or "WT") holding x - trunc_tf32(x); refreshed inside the step graph by
-        an ``orlk_split_lo`` launch (emit_lo_refresh), never on the host."""
+        an ``orlk_fused_prep`` launch (emit_lo_refresh), never on the host."""
         name = store + "lo"
         t = getattr(self, name, None)
         if t is None:
@@ -220,6 +220,16 @@ class ParamSet:
     def w_lo(self, l: int, g: int = 0, store: str = "P") -> int:
         lay = self.layers[l]
         return self._ptr(self.lo_arena(store), lay.w_off + g * lay.w_gs)
+
+    def w0_pad(self, store: str) -> torch.Tensor:
+        """[2][G][out][32]: the first layer's [out][in <= 32] weights zero-padded to 32 columns (TMA cannot address rows of
+        ``in`` floats) and their lo words; refreshed together with ``lo_arena`` (orlk_fused_prep)."""
+        name = store + "w0pad"
+        t = getattr(self, name, None)
+        if t is None:
+            t = self.rt.zeros(2, self.G, self.layers[0].out_dim, 32)
+            setattr(self, name, t)
+        return t
 
     def wt(self, l: int, g: int = 0) -> int:
         lay = self.layers[l]

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib as L
 from .core import Mat, Plan
-from .learner import (Learner, MlpRun, chainable, check_plain_mlp, emit_dact, emit_forward, emit_head_dgrad, emit_hidden_dgrad,
+from .learner import (Learner, MlpRun, chainable, check_plain_mlp, emit_dact, emit_forward, emit_forward_pair, emit_head_dgrad, emit_hidden_dgrad,
                       emit_lo_refresh, emit_wgrad_adam, linears_of, make_gradbuf)
 from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem, pick_cfg
 
@@ -347,8 +347,13 @@ class CQLLearner(TwinCriticLearner):
         self._alloc_actor_phase()
         self.run_actor_b = self.mlp_run(self.actor_ps, 2 * B, self.nh_a, need_grad=False)
         Rt, n_next = self.Rt, (self.N if self.max_q_backup else 1)
-        self.run_target = self.mlp_run(self.critic_ps, Rt, self.nh_c, need_grad=False, store="T")
+        # the target critics ride in the online critics' fused launch as a second job, whatever their row count (a pass of
+        # their own on the small-row kernels would have to share the SMs with that launch)
+        self.run_target = self.mlp_run(self.critic_ps, Rt, self.nh_c, need_grad=False, store="T", fused_min_rows=1)
+        self.run_target.keep_h = False
         self.run_critic = self.mlp_run(self.critic_ps, Mc, self.nh_c, need_grad=True)
+        if not self.run_critic.fused_fwd and Rt < TC_MIN_ROWS:
+            self.run_target = self.mlp_run(self.critic_ps, Rt, self.nh_c, need_grad=False, store="T")
         self.Xt = rt.zeros(Rt, (O + A + 3) // 4 * 4)[:, :O + A]
         self.Xc = rt.zeros(Mc, (O + A + 3) // 4 * 4)[:, :O + A]      # 16-byte aligned rows: a TMA operand of the first layer
         self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(Rt), rt.zeros(R), rt.zeros(R)
@@ -400,12 +405,13 @@ class CQLLearner(TwinCriticLearner):
         plan.join()
         # the target critics on (s', a') and the online critics on the 7936-row batch are independent: two branches
         cr = self.run_critic
-        plan.fork()
-        plan.branch(1)
-        emit_forward(rt, plan, self.run_target, [Xt, Xt], "C.target")
-        plan.branch(0)
-        emit_forward(rt, plan, cr, [Xc, Xc], "C.critic")
-        plan.join()
+        if not emit_forward_pair(rt, plan, cr, [Xc, Xc], "C.critic", self.run_target, [Xt, Xt], "C.target"):
+            plan.fork()
+            plan.branch(1)
+            emit_forward(rt, plan, self.run_target, [Xt, Xt], "C.target")
+            plan.branch(0)
+            emit_forward(rt, plan, cr, [Xc, Xc], "C.critic")
+            plan.join()
         pol = self.policy
         largs = (cr.out.data_ptr(), Mc, self.run_target.out.data_ptr(), Rt, self.lp_next.data_ptr(), self.lp_pi.data_ptr(),
                  self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, self.n_real, n_next, R, A, self.gamma,

@@ -1,0 +1,86 @@
+"""In-kernel timeline of the fused critic passes (run on the GPU box): per-CTA SM-clock stamps written by the kernel
+itself (orlk_tc_set_trace).  Prints the median offset in ns of each event from "predecessor complete".
+Usage: python profiles/fused_trace.py"""
+import ctypes as C
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from offlinerlkit_b200 import _lib as L
+from offlinerlkit_b200.engine.core import Mat, get_runtime
+
+rt = get_runtime("cuda:0")
+
+
+def al(n):
+    return (n + 3) // 4 * 4
+
+
+def trace_fwd(M, N, K0, nh, G):
+    ldx = al(K0)
+    X = torch.randn(M, ldx, device="cuda")
+    dims = [(N, K0)] + [(N, N)] * (nh - 1) + [(1, N)]
+    offs, off = [], 0
+    for (o, i) in dims:
+        w = off; off = al(off + o * i)
+        b = off; off = al(off + o)
+        offs.append((w, b))
+    block = al(off)
+    P = torch.randn(G * block, device="cuda") / 16
+    Plo = torch.zeros_like(P)
+    pad = torch.zeros(2, G, N, 32, device="cuda")
+    rt.fused_prep(P, Plo, W0=P.data_ptr() + 4 * offs[0][0], gs=block, N=N, K0=K0, G=G, w0pad=pad)()
+    H = [torch.zeros(G, M, N, device="cuda") for _ in range(nh)]
+    out = torch.zeros(G, M, device="cuda")
+    base, lo = P.data_ptr(), Plo.data_ptr()
+    job = rt.fused_fwd_job(X=Mat(X.data_ptr(), M, K0, ldx), W0pad=pad[0].data_ptr(), W0pad_lo=pad[1].data_ptr(),
+                           W=[0] + [base + 4 * offs[l][0] for l in range(1, nh)],
+                           Wlo=[0] + [lo + 4 * offs[l][0] for l in range(1, nh)], bias=[base + 4 * offs[l][1] for l in range(nh)],
+                           H=[h.data_ptr() for h in H], gs=block, h_gs=M * N, head_w=base + 4 * offs[nh][0],
+                           head_b=base + 4 * offs[nh][1], out=out.data_ptr(), out_gs=M, M=M, N=N, K0=K0, G=G)
+    op = rt.critic_fwd_fused([job])
+    buf = torch.zeros(1024 * 128, dtype=torch.int64, device="cuda")
+    g = C.c_void_p()
+    torch.cuda.synchronize()
+    L.call("orlk_tc_set_trace", buf.data_ptr())
+    rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
+    L.call("orlk_graph_begin", rt.cur)
+    op()
+    L.call("orlk_graph_end", rt.cur, C.byref(g))
+    rt.cur = rt.exec_ptr
+    L.call("orlk_tc_set_trace", None)
+    for _ in range(300):         # sustained load: the SM clock has settled when the last replay writes its stamps
+        L.call("orlk_graph_launch", g, rt.cur)
+    torch.cuda.synchronize()
+    t = buf.view(-1, 128).cpu()
+    n_cta = int((t[:, 0] != 0).sum())
+    if os.path.isdir("gpurun_out"):
+        import numpy as np
+        np.save(f"gpurun_out/fused_trace_M{M}_G{G}.npy", t[:n_cta].numpy())
+    gt = t[:n_cta, 4:7].double()
+    g0 = gt[:, 0].min()
+    st, wt, en = (gt[:, 0] - g0).sort().values, (gt[:, 1] - g0).sort().values, (gt[:, 2] - g0).sort().values
+    pick = lambda v: "  ".join(f"{v[int(q * (n_cta - 1))]:.0f}" for q in (0, 0.25, 0.5, 0.75, 0.9, 1.0))
+    print(f"globaltimer ns from the first CTA start (min / 25% / 50% / 75% / 90% / max over {n_cta} CTAs):")
+    print(f"   CTA start {pick(st)}\n   predecessor done {pick(wt)}\n   CTA end {pick(en)}")
+    dur = (gt[:, 2] - gt[:, 1]).sort().values
+    print(f"   per-CTA wait->end {pick(dur)}")
+    t = t[:n_cta].double() / 1.965           # SM clocks -> ns at 1965 MHz
+    rel = t - t[:, 1:2]
+    rel[t == 0] = float("nan")
+    med = rel.nanmedian(dim=0).values.tolist()
+    nsl = 1 + (nh - 1) * (N // 32)
+    print(f"fwd M={M} N={N} K0={K0} nh={nh} G={G} ctas={n_cta}: start {med[0]:.0f}  staged {med[2]:.0f}  end {med[3]:.0f}")
+    print("   acc_full per layer: " + "  ".join(f"{med[112 + l]:.0f}" for l in range(nh)))
+    print("   slab: A ready / B ready (= MMA issue) / TMA for this B issued")
+    for bi in range(nsl):
+        tma = med[80 + bi]
+        print(f"   {bi:3d}  {med[16 + bi]:7.0f} {med[48 + bi]:7.0f} " + (f"{tma:7.0f}" if tma == tma else "      -"))
+    L.call("orlk_graph_destroy", g)
+
+
+trace_fwd(7936, 256, 23, 3, 2)
+trace_fwd(128, 256, 23, 3, 1)

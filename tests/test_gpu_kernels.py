@@ -775,17 +775,14 @@ def test_compact_rows_is_stable_and_exact(rt, S, p_drop):
 
 
 # ------------------------------------------------------------------------------------------------ fused critic passes
-@pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (2560, 256, 14, 2, 2), (300, 128, 32, 4, 1),
-                                         (2048 + 77, 64, 5, 3, 3)])
-def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
-    """orlk_critic_fwd_fused: every hidden activation and the scalar head of all members against an fp64 evaluation of
-    the same Linear+ReLU stack (nets/mlp.py:22-28, modules/critic_module.py:25-33); 3xTF32 = fp32-grade."""
+def _fused_case(rt, M, N, K0, nh, G, seed, store_h=True):
+    """A random Linear+ReLU stack laid out like a ParamSet (one 4-float aligned block per member) + the fused-forward job."""
     from offlinerlkit_b200.engine.core import Mat
-    gen = torch.Generator().manual_seed(M + N + K0)
+    gen = torch.Generator().manual_seed(seed)
     ldx = (K0 + 3) // 4 * 4
     X = torch.zeros(M, ldx)
     X[:, :K0] = torch.randn(M, K0, generator=gen)
-    # one block per member, as ParamSet lays the parameters out: [W0 | b0 | W1 | b1 | ... | head_w | head_b], 4-float aligned
+
     def al(n):
         return (n + 3) // 4 * 4
     offs, off = [], 0
@@ -808,19 +805,24 @@ def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
         Ws.append(Wg); bs.append(bg)
     Xd, Pd = X.to(DEV), P.to(DEV)
     Plo = torch.full_like(Pd, float("nan"))
-    rt.split_lo(Pd, Plo)()
-    H = [torch.full((G, M, N), float("nan"), device=DEV) for _ in range(nh)]
-    out = torch.full((G, M), float("nan"), device=DEV)
+    pad = torch.full((2, G, N, 32), float("nan"), device=DEV)
     base, lo = Pd.data_ptr(), Plo.data_ptr()
-    op = rt.critic_fwd_fused(X=Mat(Xd.data_ptr(), M, K0, ldx), W=[base + 4 * offs[l][0] for l in range(nh)],
-                             Wlo=[0] + [lo + 4 * offs[l][0] for l in range(1, nh)], bias=[base + 4 * offs[l][1] for l in range(nh)],
-                             H=[h.data_ptr() for h in H], gs=block, h_gs=M * N, head_w=base + 4 * offs[nh][0],
-                             head_b=base + 4 * offs[nh][1], out=out.data_ptr(), out_gs=M, M=M, N=N, K0=K0, G=G)
-    for _ in range(2):          # a second launch over the same buffers: barriers / ring state start clean every time
-        op()
-    torch.cuda.synchronize()
-    lo_ref = P - (P.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    assert torch.equal(Plo.cpu(), lo_ref), "split_lo"
+    rt.fused_prep(Pd, Plo, W0=base + 4 * offs[0][0], gs=block, N=N, K0=K0, G=G, w0pad=pad)()
+    H = [torch.full((G, M, N), float("nan"), device=DEV) for _ in range(nh)] if store_h else None
+    out = torch.full((G, M), float("nan"), device=DEV)
+    job = rt.fused_fwd_job(X=Mat(Xd.data_ptr(), M, K0, ldx), W0pad=pad[0].data_ptr(), W0pad_lo=pad[1].data_ptr(),
+                           W=[0] + [base + 4 * offs[l][0] for l in range(1, nh)],
+                           Wlo=[0] + [lo + 4 * offs[l][0] for l in range(1, nh)], bias=[base + 4 * offs[l][1] for l in range(nh)],
+                           H=[h.data_ptr() for h in H] if store_h else None, gs=block, h_gs=M * N,
+                           head_w=base + 4 * offs[nh][0], head_b=base + 4 * offs[nh][1], out=out.data_ptr(), out_gs=M,
+                           M=M, N=N, K0=K0, G=G)
+    return dict(job=job, X=X, P=P, Ws=Ws, bs=bs, H=H, out=out, Plo=Plo, pad=pad, offs=offs, block=block, keep=(Xd, Pd),
+                dims=(M, N, K0, nh, G))
+
+
+def _check_fused(case):
+    M, N, K0, nh, G = case["dims"]
+    X, Ws, bs, H, out = case["X"], case["Ws"], case["bs"], case["H"], case["out"]
     for g in range(G):
         # 3xTF32: ~3e-6 of sum_k |a_k b_k| per layer (the tolerance of the per-layer tensor-core test); errors add up
         h = X[:, :K0].double()
@@ -831,9 +833,45 @@ def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
             h = h @ W.t() + b
             if l < nh:
                 h = torch.relu(h)
+                if H is None:
+                    continue
                 got = H[l][g]
             else:
                 got = out[g][:, None]
             assert not torch.isnan(got).any(), f"layer {l} member {g}: unwritten output"
             err = (got.double().cpu() - h).abs().max().item()
             assert err <= tol, f"layer {l} member {g}: max err {err:.3e} vs {tol:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (2560, 256, 14, 2, 2), (300, 128, 32, 4, 1),
+                                         (2048 + 77, 64, 5, 3, 3)])
+def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
+    """orlk_critic_fwd_fused: every hidden activation and the scalar head of all members against an fp64 evaluation of
+    the same Linear+ReLU stack (nets/mlp.py:22-28, modules/critic_module.py:25-33); 3xTF32 = fp32-grade."""
+    case = _fused_case(rt, M, N, K0, nh, G, seed=M + N + K0)
+    op = rt.critic_fwd_fused([case["job"]])
+    for _ in range(2):          # a second launch over the same buffers: barriers / ring state start clean every time
+        op()
+    torch.cuda.synchronize()
+    P = case["P"]
+    lo_ref = P - (P.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(case["Plo"].cpu(), lo_ref), "lo words"
+    w0, _ = case["offs"][0]
+    for g in range(G):
+        W0 = P[g * case["block"] + w0:g * case["block"] + w0 + N * K0].view(N, K0)
+        padded = torch.zeros(N, 32)
+        padded[:, :K0] = W0
+        assert torch.equal(case["pad"][0, g].cpu(), padded), "padded first layer"
+        assert torch.equal(case["pad"][1, g].cpu(), padded - (padded.view(torch.int32) & ~0x1FFF).view(torch.float32)), "its lo words"
+    _check_fused(case)
+
+
+def test_critic_forward_fused_two_jobs(rt):
+    """Two passes in one launch: the online critics on the long batch (activations stored) beside the target critics on a
+    short one (head only), as the CQL step launches them (policy/model_free/cql.py:108-160)."""
+    a = _fused_case(rt, 7936, 256, 23, 3, 2, seed=1)
+    b = _fused_case(rt, 256, 256, 23, 3, 2, seed=2, store_h=False)
+    rt.critic_fwd_fused([a["job"], b["job"]])()
+    torch.cuda.synchronize()
+    _check_fused(a)
+    _check_fused(b)
