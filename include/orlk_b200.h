@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 22
+#define ORLK_ABI_VERSION 23
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -366,12 +366,16 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
  *   critic is maximised over them before the min over critics, and lp_next is not used.
  * Computes the TD target, the 3-way logsumexp per repeat row (the reference's quirk), the optional Lagrange
  * multiplier step, the per-row upstream gradients dq[c][.] and the losses
- *   out_losses[0..1] = critic1/2 loss, [2] = cql_alpha loss, [3] = cql_alpha (old, clamped). */
+ *   out_losses[0..1] = critic1/2 loss, [2] = cql_alpha loss, [3] = cql_alpha (old, clamped).
+ * One CTA per 128 rows writes dq directly (it needs no reduction); the last CTA to finish adds the per-CTA partial sums
+ * in CTA order, writes the losses and takes the multiplier's Adam step.  scratch: orlk_cql_critic_loss_scratch_floats(B, R)
+ * floats, zero-initialised once (the kernel leaves its counter at zero). */
+int orlk_cql_critic_loss_scratch_floats(int B, int R);
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
                          const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
                          int tq_rep, int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
-                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream);
+                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, float* scratch, void* stream);
 
 /* Generic TD loss (sac.py:93-108, td3bc.py:87-104, iql.py:101-115, edac.py:124-134):
  *   y = r + gamma (1-d) [ min_{e2<E2} tq[e2] - (use_alpha ? alpha * lp_next : 0) ]

@@ -502,81 +502,47 @@ __device__ __forceinline__ float next_q(const float* __restrict__ tq, int64_t tq
     return fminf(m0, m1);
 }
 
-__global__ void __launch_bounds__(1024)
+// Many CTAs: the per-row upstream gradients dq need no reduction at all (their only scalar factor is the OLD Lagrange
+// multiplier), so every CTA writes its rows' dq in one pass and leaves six partial sums in `scratch`; the CTA that
+// finishes last adds the partials in CTA order (deterministic), writes the losses and takes the multiplier's Adam step.
+constexpr int CQL_LOSS_THREADS = 128;
+
+__global__ void __launch_bounds__(CQL_LOSS_THREADS)
 k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __restrict__ tq, int64_t tq_cs,
                   const float* __restrict__ lp_next, const float* __restrict__ lp_pi, const float* __restrict__ lp_pn,
                   const float* __restrict__ rew, const float* __restrict__ term, int B, int n_qmean, int tq_rep, int R,
                   float log_u, float gamma, float w, float T, int det_backup, int with_lagrange, float thr, float* __restrict__ scalars,
                   const OrlkAdamGroup* __restrict__ groups, int cql_alpha_group, float* __restrict__ cql_alpha_mv,
-                  float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out) {
+                  float* __restrict__ dq, int64_t dq_cs, float* __restrict__ out, float* __restrict__ scratch) {
     orlk::pdl_enter();
     __shared__ float red[32];
-    __shared__ float sh_scale;
+    __shared__ int s_last;
     const float alpha = scalars[ORLK_SC_ALPHA];
     const float invB = 1.f / (float)B, invQ = 1.f / (float)n_qmean, invR = 1.f / (float)R, invT = 1.f / T;
+    float scale = 1.f, ex = 0.f, la = 0.f;
+    if (with_lagrange) {        // the multiplier that scales this step's gradients is the one from BEFORE its own update
+        la = scalars[ORLK_SC_CQL_LOG_ALPHA];
+        ex = expf(la);
+        scale = fminf(fmaxf(ex, 0.f), 1e6f);
+    }
     float td[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int i = blockIdx.x * CQL_LOSS_THREADS + threadIdx.x;
+    if (i < B) {
+        const int b = i;
         const float nq = next_q(tq, tq_cs, lp_next, b, tq_rep, det_backup, alpha);
         const float y = rew[b] + gamma * (1.f - term[b]) * nq;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const float qq = q[c * q_cs + b];
             const float df = qq - y;
-            td[c] += df * df;
-            if (b < n_qmean) qs[c] += qq;
+            td[c] = df * df;
+            if (b < n_qmean) qs[c] = qq;
+            dq[c * dq_cs + b] = 2.f * df * invB - (b < n_qmean ? w * scale * invQ : 0.f);
         }
-    }
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    } else if (i < B + R) {
+        const int r = i - B;
         const float l1 = lp_pi[r], l2 = lp_pn[r];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const float* qc = q + c * q_cs + B;
-            const float z1 = (qc[r] - l1) * invT, z2 = (qc[R + r] - l2) * invT, z3 = (qc[2 * R + r] - log_u) * invT;
-            const float mx = fmaxf(z1, fmaxf(z2, z3));
-            ls[c] += mx + logf(expf(z1 - mx) + expf(z2 - mx) + expf(z3 - mx));
-        }
-    }
-    float cons[2], tdm[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        tdm[c] = block_sum(td[c], red) * invB;
-        const float qmean = block_sum(qs[c], red) * invQ;
-        const float lmean = block_sum(ls[c], red) * invR;
-        cons[c] = lmean * w * T - qmean * w;
-    }
-    if (threadIdx.x == 0) {
-        float scale = 1.f, closs = 0.f, calpha = 0.f;
-        float c0 = cons[0], c1 = cons[1];
-        if (with_lagrange) {
-            const float la = scalars[ORLK_SC_CQL_LOG_ALPHA];
-            const float ex = expf(la);
-            calpha = fminf(fmaxf(ex, 0.f), 1e6f);
-            c0 = calpha * (cons[0] - thr);
-            c1 = calpha * (cons[1] - thr);
-            closs = -(c0 + c1) * 0.5f;
-            const float gate = (ex >= 0.f && ex <= 1e6f) ? 1.f : 0.f;
-            const float g = -0.5f * ((cons[0] - thr) + (cons[1] - thr)) * ex * gate;
-            scalars[ORLK_SC_CQL_LOG_ALPHA] = scalar_adam(la, g, cql_alpha_mv, groups[cql_alpha_group]);
-            scale = calpha;
-        }
-        out[0] = tdm[0] + c0;
-        out[1] = tdm[1] + c1;
-        out[2] = closs;
-        out[3] = calpha;
-        sh_scale = scale;
-    }
-    __syncthreads();
-    const float scale = sh_scale;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const float nq = next_q(tq, tq_cs, lp_next, b, tq_rep, det_backup, alpha);
-        const float y = rew[b] + gamma * (1.f - term[b]) * nq;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-            dq[c * dq_cs + b] = 2.f * (q[c * q_cs + b] - y) * invB - (b < n_qmean ? w * scale * invQ : 0.f);
-    }
-    const float k = scale * w * invR;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        const float l1 = lp_pi[r], l2 = lp_pn[r];
+        const float k = scale * w * invR;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const float* qc = q + c * q_cs + B;
@@ -584,18 +550,69 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
             const float z1 = (qc[r] - l1) * invT, z2 = (qc[R + r] - l2) * invT, z3 = (qc[2 * R + r] - log_u) * invT;
             const float mx = fmaxf(z1, fmaxf(z2, z3));
             const float e1 = expf(z1 - mx), e2 = expf(z2 - mx), e3 = expf(z3 - mx);
-            const float inv = k / (e1 + e2 + e3);
+            const float sum = e1 + e2 + e3;
+            ls[c] = mx + logf(sum);
+            const float inv = k / sum;
             dc[r] = e1 * inv;
             dc[R + r] = e2 * inv;
             dc[2 * R + r] = e3 * inv;
         }
+    }
+    float part[6];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        part[3 * c + 0] = block_sum(td[c], red);
+        part[3 * c + 1] = block_sum(qs[c], red);
+        part[3 * c + 2] = block_sum(ls[c], red);
+    }
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+    float* parts = scratch + 4;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) parts[blockIdx.x * 6 + j] = part[j];
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += CQL_LOSS_THREADS) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) tot[j] += __ldcg(parts + blk * 6 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tot[j] = block_sum(tot[j], red);
+    if (threadIdx.x == 0) {
+        float cons[2], tdm[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            tdm[c] = tot[3 * c] * invB;
+            cons[c] = tot[3 * c + 2] * invR * w * T - tot[3 * c + 1] * invQ * w;
+        }
+        float closs = 0.f, calpha = 0.f;
+        float c0 = cons[0], c1 = cons[1];
+        if (with_lagrange) {
+            calpha = scale;
+            c0 = calpha * (cons[0] - thr);
+            c1 = calpha * (cons[1] - thr);
+            closs = -(c0 + c1) * 0.5f;
+            const float gate = (ex >= 0.f && ex <= 1e6f) ? 1.f : 0.f;
+            const float g = -0.5f * ((cons[0] - thr) + (cons[1] - thr)) * ex * gate;
+            scalars[ORLK_SC_CQL_LOG_ALPHA] = scalar_adam(la, g, cql_alpha_mv, groups[cql_alpha_group]);
+        }
+        out[0] = tdm[0] + c0;
+        out[1] = tdm[1] + c1;
+        out[2] = closs;
+        out[3] = calpha;
+        *counter = 0u;          // ready for the next launch (graph replay)
     }
 }
 
 // ------------------------------------------------------------------------------------------ fused Adam + polyak
 constexpr int ADAM_BLOCK_ELEMS = 256;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamGroup* __restrict__ groups) {
     orlk::pdl_enter();
     __shared__ OrlkAdamDesc sd;
@@ -620,19 +637,30 @@ k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamG
         float p = d.p[i];
         if (d.flags & ORLK_OPT_ADAM) {
             // fixed-order reduction of the split-K partials, four independent chains so the loads overlap
+            // (all loads of a 16-slot batch - and m, v - are issued before the first add: the plain loop costs one L2 round
+            // trip per four slots; the order of the additions, and so the result, is that of the plain loop)
             float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
             const float* gp = d.grad + i;
-            int s = 0;
-            for (; s + 4 <= d.g_splits; s += 4) {
-                g0 += gp[(int64_t)s * d.g_split_stride];
-                g1 += gp[(int64_t)(s + 1) * d.g_split_stride];
-                g2 += gp[(int64_t)(s + 2) * d.g_split_stride];
-                g3 += gp[(int64_t)(s + 3) * d.g_split_stride];
+            const float m_old = d.m[i], v_old = d.v[i];
+            const int full = d.g_splits & ~3;
+            for (int s0 = 0; s0 < d.g_splits; s0 += 16) {
+                float pv[16];
+                const float* gq = gp + (int64_t)s0 * d.g_split_stride;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) pv[u] = (s0 + u < d.g_splits) ? gq[(int64_t)u * d.g_split_stride] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    if (s0 + u + 4 <= full) { g0 += pv[u]; g1 += pv[u + 1]; g2 += pv[u + 2]; g3 += pv[u + 3]; }
+                    else {      // the last, incomplete group of four goes to the first chain, slot by slot
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (s0 + u + e < d.g_splits) g0 += pv[u + e];
+                    }
+                }
             }
-            for (; s < d.g_splits; ++s) g0 += gp[(int64_t)s * d.g_split_stride];
             float gr = (g0 + g1) + (g2 + g3);
             if (d.wd != 0.f) gr = fmaf(d.wd, p, gr);
-            float m = d.m[i], v = d.v[i];
+            float m = m_old, v = v_old;
             m = m + (gr - m) * (1.f - g.beta1);
             v = v * g.beta2 + (1.f - g.beta2) * gr * gr;
             d.m[i] = m; d.v[i] = v;
@@ -785,19 +813,24 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
     return check_launch("k_sac_actor_loss");
 }
 
+int orlk_cql_critic_loss_scratch_floats(int B, int R) {
+    return 4 + 6 * ((B + R + CQL_LOSS_THREADS - 1) / CQL_LOSS_THREADS);
+}
+
 int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t tq_cs, const float* lp_next,
                          const float* lp_pi, const float* lp_pn, const float* rew, const float* term, int B, int n_qmean,
                          int tq_rep, int R, int A, float gamma, float cql_weight, float temperature, int deterministic_backup, int with_lagrange,
                          float lagrange_threshold, float* scalars, OrlkAdamGroup* groups, int cql_alpha_group,
-                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, void* stream) {
+                         float* cql_alpha_mv, float* dq, int64_t dq_cs, float* out_losses, float* scratch, void* stream) {
     ORLK_REQUIRE(B > 0 && R > 0 && A > 0 && n_qmean > 0 && n_qmean <= B && tq_rep >= 1, "sizes");
     ORLK_REQUIRE(tq_rep > 1 || deterministic_backup || lp_next != nullptr, "the entropy backup needs lp_next");
     ORLK_REQUIRE(!with_lagrange || (groups != nullptr && cql_alpha_mv != nullptr), "lagrange needs its Adam state");
+    ORLK_REQUIRE(scratch != nullptr && aligned16(scratch), "scratch (orlk_cql_critic_loss_scratch_floats zero-initialised floats)");
     const float log_u = (float)log(pow(0.5, (double)A));   // cql.py:82: np.log(0.5 ** act_dim)
-    orlk::launch(k_cql_critic_loss, 1, 1024, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B, n_qmean, tq_rep,
-                                                           R, log_u, gamma, cql_weight, temperature, deterministic_backup,
-                                                           with_lagrange, lagrange_threshold, scalars, groups,
-                                                           cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses);
+    const int blocks = (B + R + CQL_LOSS_THREADS - 1) / CQL_LOSS_THREADS;
+    orlk::launch(k_cql_critic_loss, blocks, CQL_LOSS_THREADS, 0, (cudaStream_t)stream, q, q_cs, tq, tq_cs, lp_next, lp_pi, lp_pn, rew, term, B,
+                 n_qmean, tq_rep, R, log_u, gamma, cql_weight, temperature, deterministic_backup, with_lagrange, lagrange_threshold,
+                 scalars, groups, cql_alpha_group, cql_alpha_mv, dq, dq_cs, out_losses, scratch);
     return check_launch("k_cql_critic_loss");
 }
 

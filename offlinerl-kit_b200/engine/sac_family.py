@@ -357,6 +357,7 @@ class CQLLearner(TwinCriticLearner):
         self.Xt = rt.zeros(Rt, (O + A + 3) // 4 * 4)[:, :O + A]
         self.Xc = rt.zeros(Mc, (O + A + 3) // 4 * 4)[:, :O + A]      # 16-byte aligned rows: a TMA operand of the first layer
         self.lp_next, self.lp_pi, self.lp_pn = rt.zeros(Rt), rt.zeros(R), rt.zeros(R)
+        self.loss_scratch = rt.zeros(L.load().orlk_cql_critic_loss_scratch_floats(B, R))
         self.gb_actor = make_gradbuf(rt, self.actor_ps, [self.run_actor])
         self.gb_critic = make_gradbuf(rt, self.critic_ps, [self.run_critic])
 
@@ -417,7 +418,8 @@ class CQLLearner(TwinCriticLearner):
                  self.lp_pn.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), B, self.n_real, n_next, R, A, self.gamma,
                  float(pol._cql_weight), float(pol._temperature), int(bool(pol._deterministic_backup)),
                  int(self.with_lagrange), float(pol._lagrange_threshold), self.scalars.data_ptr(), self.groups_ptr,
-                 max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1)
+                 max(self.g_cql, 0), self.cql_mv.data_ptr(), cr.dOut.data_ptr(), Mc, self.loss_dev.data_ptr() + 4 * LS_C1,
+                 self.loss_scratch.data_ptr())
         plan.add("C.loss", lambda: L.call("orlk_cql_critic_loss", *largs, rt.cur))
         self.emit_loss_readback(plan)       # every loss scalar is final: the copy overlaps the backward pass
         emit_head_dgrad(rt, plan, cr, "C.critic")

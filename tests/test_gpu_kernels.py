@@ -474,10 +474,12 @@ def test_cql_critic_loss_vs_autograd(rt):
         dev = lambda t: t.to(DEV)
         qg, tqg, a1, a2, a3, rg, tg = map(dev, (q, tq, lpn, lpp, lpq, rew, term))
         dq, out = torch.zeros(2, Mc, device=DEV), torch.zeros(4, device=DEV)
+        scratch = torch.zeros(L.load().orlk_cql_critic_loss_scratch_floats(B, R), device=DEV)
         L.call("orlk_cql_critic_loss", qg.data_ptr(), Mc, tqg.data_ptr(), B * rep, a1.data_ptr(), a2.data_ptr(), a3.data_ptr(),
                rg.data_ptr(), tg.data_ptr(), B, nq_rows, rep, R, A, gamma, w, T, det, lag, thr, sc.data_ptr(), gd.data_ptr(), 0,
-               mv.data_ptr(), dq.data_ptr(), Mc, out.data_ptr(), rt.cur)
+               mv.data_ptr(), dq.data_ptr(), Mc, out.data_ptr(), scratch.data_ptr(), rt.cur)
         torch.cuda.synchronize()
+        assert scratch.view(torch.int32)[0].item() == 0, "the block counter must be left at zero for the next launch"
         _close(out[0], total[0], rtol=2e-5, atol=1e-4, msg="critic1 loss")
         _close(out[1], total[1], rtol=2e-5, atol=1e-4, msg="critic2 loss")
         _close(dq, qd.grad, rtol=2e-5, atol=1e-8, msg="dq")
