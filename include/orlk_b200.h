@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 23
+#define ORLK_ABI_VERSION 24
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -224,11 +224,33 @@ typedef struct OrlkFusedFwd {
     int64_t gs, h_gs;                             /* member strides (floats) of the parameters / of H */
     const float* head_w; const float* head_b;
     float* out; int64_t out_gs;                   /* [G][M] */
+    uint32_t* relu_bits;                          /* optional [n_hidden][G][8][M]: bit j of word [c][m] = (H_l[g][m][32c+j] > 0), for
+                                                     orlk_critic_bwd_fused */
     int32_t M, N, K0, G, n_hidden, pad_;
 } OrlkFusedFwd;
 int orlk_fused_init(void); /* once per process, outside stream capture */
 int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs_host, int n_jobs, void* stream);
 int orlk_sizeof_fused_fwd(void);
+/* Fused input-gradient chain of the same stack behind its scalar head, ONE launch:
+ *   dZ_{L-1}[m][k] = dq[g][m] * head_w[g][k] * relu'(H_{L-1})   (generated in shared memory, never stored)
+ *   dZ_{l-1} = (dZ_l W_l) * relu'(H_{l-1}),  l = L-1 .. 1        (stored: operands of the weight gradients)
+ * with relu' read from the decision bits orlk_critic_fwd_fused left (relu_bits), WT[l] = W_l^T [N (in)][N (out)] (the
+ * transposed copies the Adam kernel keeps) and WTlo[l] their lo words (orlk_fused_prep on that arena); member stride gs.
+ * Replaces autograd's backward through modules/critic_module.py:25-33 for the hidden activations (the two dgrad
+ * launches + the head's backward of CQL's critic update, policy/model_free/cql.py:190-205).  Host struct. */
+typedef struct OrlkFusedBwd {
+    const float* dq; int64_t dq_gs;               /* [G][M] */
+    const float* head_w;                          /* [G][N], member stride gs */
+    const uint32_t* relu_bits;                    /* [n_hidden][G][8][M] */
+    const float* WT[ORLK_FUSED_MAX_LAYERS];       /* [0] unused */
+    const float* WTlo[ORLK_FUSED_MAX_LAYERS];
+    float* dZ[ORLK_FUSED_MAX_LAYERS];             /* dZ[l], l = 0 .. n_hidden-2: [G][M][N] */
+    int64_t gs, dz_gs;
+    int32_t M, N, G, n_hidden;
+} OrlkFusedBwd;
+int orlk_critic_bwd_fused(const OrlkFusedBwd* params_host, void* stream);
+int orlk_sizeof_fused_bwd(void);
+
 /* Derived operand copies of a parameter arena for the fused passes, one launch per step:
  *   dst_lo[i] = src[i] - trunc_tf32(src[i]) for the whole arena (n floats, 16-byte aligned), and - when W0 != NULL -
  *   w0pad[0][g][o][k] = W0[g*gs + o*K0 + k] (k < K0, else 0), w0pad[1] = its lo words  (W0 inside [src, src + n)). */

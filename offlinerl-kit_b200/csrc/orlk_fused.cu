@@ -47,6 +47,7 @@ struct FwdParams {
     const float* bias[MAXL];
     const float* head_w; const float* head_b;
     float* out; int64_t out_gs;
+    uint32_t* bits;                       // [L][G][8][M] ReLU-decision bits of every activation (bit j of word [c][m]: column 32c+j > 0), or NULL
     int M, N, G, L, tiles_m, store_h;
     int no_store;                         // experiment (ORLK_FUSED_NO_STORE=1): skip the H stores, results are then incomplete
     unsigned long long* trace;            // profiling aid (orlk_tc_set_trace): 128 clock stamps per CTA, NULL in normal operation
@@ -247,6 +248,12 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
                     x[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f);
                     x[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
                 }
+                if (p.bits != nullptr && m < p.M) {
+                    uint32_t wbits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) wbits |= (x[j] > 0.f ? 1u : 0u) << j;
+                    p.bits[(((int64_t)l * p.G + g) * 8 + c) * p.M + m] = wbits;       // a warp's 32 rows: one 128-byte store
+                }
                 if (last) {
                     // every MMA has completed: the whole B ring is idle, so each of this warp's (up to four) chunks gets
                     // its own 4 KB store tile there and no store ever waits for the previous one
@@ -302,6 +309,242 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (grp == 0 && m < p.M) p.out[(int64_t)g * p.out_gs + m] = (qacc + qpart_s[row]) + __ldg(p.head_b + (int64_t)g * p.gs);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tiles must outlive the stores
+    }
+    if (threadIdx.x == 64) { FZ_STAMP(3); FZ_GSTAMP(6); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_critic_bwd: the input-gradient chain of the same stack behind its scalar head, one launch:
+//   dZ_{L-1}[m][k] = dq[m] * w_head[k] * relu'(H_{L-1}[m][k])          (generated, never stored)
+//   dZ_{l-1} = (dZ_l W_l) * relu'(H_{l-1})    for l = L-1 .. 1        (stored: the weight gradients need them)
+// (autograd of modules/critic_module.py:25-33 / nets/mlp.py:22-28 w.r.t. the hidden activations).  Same strip-per-CTA
+// structure as the forward pass: the generator and each layer's epilogue write the next GEMM's A tiles (hi | lo) into
+// the two-stage ring, the B operand is the transposed weight W_l^T [in][out] (kept by the Adam kernel) and its lo words
+// through TMA, accumulators ping-pong in tensor memory.  relu' comes from the decision bits the forward pass left
+// (4 bytes per 32 activations instead of re-reading H).
+struct BwdMaps {
+    CUtensorMap wt[MAXL - 1];     // W_l^T [G][N (in)][N (out)], l >= 1: box 32 (k = out) x N
+    CUtensorMap wtlo[MAXL - 1];
+    CUtensorMap dz[MAXL - 1];     // dZ_l [G][M][N], l = 0 .. L-2: box 32 x 32 (store)
+};
+
+struct BwdParams {
+    int64_t gs;
+    const float* dq; int64_t dq_gs;       // [G][M] upstream gradient of the head output
+    const float* head_w;                  // [G][N] (member stride gs)
+    const uint32_t* bits;                 // [L][G][8][M]
+    int M, N, G, L, tiles_m;
+    unsigned long long* trace;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_base = base + 2 * A_STAGE;
+    uint8_t* fixed = base + RING;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 128);
+    float* headw_s = reinterpret_cast<float*>(fixed + 256);       // [NMAX]
+    auto a_hi = [&](int s) { return base + s * A_STAGE; };
+    auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };
+    auto b_hi = [&](int s) { return b_base + s * B_STAGE; };
+    auto b_lo = [&](int s) { return b_base + s * B_STAGE + B_TILE; };
+    auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.tiles_m;
+    const int tile_m = blockIdx.x - g * p.tiles_m;
+    const int N = p.N, L = p.L;
+    const int KS = N / BK;
+    const int NG = L - 1;                       // GEMM layers of the chain
+
+    if (threadIdx.x == 0) { FZ_STAMP(0); FZ_GSTAMP(4); }
+    if (threadIdx.x == 32) {
+        for (int t = 0; t < NG; ++t) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wt[t]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wtlo[t]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.dz[t]) : "memory");
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(BAR_AFULL + s), 4);
+            mbar_init(bar(BAR_AEMPTY + s), 1);
+            mbar_init(bar(BAR_BFULL + s), 1);
+            mbar_init(bar(BAR_BEMPTY + s), 1);
+            mbar_init(bar(BAR_ACC + s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    orlk::pdl_wait();
+    if (threadIdx.x == 0) { FZ_STAMP(1); FZ_GSTAMP(5); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ------------------------------------------------------------ TMA producer: W_l^T k-slabs, l = L-1 .. 1
+            const uint32_t tx = 2u * (uint32_t)N * BK * 4;
+            int bi = 0;
+            for (int t = 0; t < NG; ++t) {
+                const int l = L - 1 - t;
+                for (int j = 0; j < KS; ++j, ++bi) {
+                    const int s = bi & 1;
+                    mbar_wait(bar(BAR_BEMPTY + s), ((bi >> 1) & 1) ^ 1);
+                    if (bi < 32) FZ_STAMP(80 + bi);
+                    mbar_expect_tx(bar(BAR_BFULL + s), tx);
+                    tma_load_3d(smem_u32(b_hi(s)), &maps.wt[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                    tma_load_3d(smem_u32(b_lo(s)), &maps.wtlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                }
+            }
+        }
+        __syncwarp();
+        orlk::pdl_trigger();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ------------------------------------------------------------ MMA issuer
+            const uint32_t idesc = instr_desc_tf32(BM, N);
+            int fa0 = 0, fa1 = 0, bi = 0;
+            for (int t = 0; t < NG; ++t) {
+                const uint32_t acc = tmem_base + (uint32_t)(NMAX * (t & 1));
+                for (int j = 0; j < KS; ++j, ++bi) {
+                    const int sa = j & 1;
+                    const int fa = sa ? fa1 : fa0;
+                    mbar_wait(bar(BAR_AFULL + sa), fa & 1);
+                    if (sa) ++fa1; else ++fa0;
+                    if (bi < 32) FZ_STAMP(16 + bi);
+                    const int sb = bi & 1;
+                    mbar_wait(bar(BAR_BFULL + sb), (bi >> 1) & 1);
+                    if (bi < 32) FZ_STAMP(48 + bi);
+                    tc_fence_after();
+                    const uint64_t ad = smem_desc_sw128(smem_u32(a_hi(sa))), adl = smem_desc_sw128(smem_u32(a_lo(sa)));
+                    const uint64_t bd = smem_desc_sw128(smem_u32(b_hi(sb))), bdl = smem_desc_sw128(smem_u32(b_lo(sb)));
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t ko = (uint64_t)(2 * k);
+                        umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
+                        umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                    }
+                    umma_commit(bar(BAR_AEMPTY + sa));
+                    umma_commit(bar(BAR_BEMPTY + sb));
+                }
+                umma_commit(bar(BAR_ACC + (t & 1)));
+            }
+        }
+        __syncwarp();
+        orlk::pdl_trigger();
+    } else {
+        // ---------------------------------------------------------------- generator + epilogue warps
+        const int grp = warp >= 6 ? 1 : 0;
+        const int q = warp & 3;
+        const int t256 = threadIdx.x - 64;
+        const int row = q * 32 + lane;
+        const int m = tile_m * BM + row;
+        const bool row_ok = m < p.M;
+        headw_s[t256] = t256 < N ? __ldg(p.head_w + (int64_t)g * p.gs + t256) : 0.f;
+        const float dq_m = row_ok ? __ldg(p.dq + (int64_t)g * p.dq_gs + m) : 0.f;
+        // ReLU-decision words of this row's chunks (c = grp, grp + 2, ...; at most four) of layer l
+        auto load_bits = [&](int l, uint32_t (&mb)[4]) {
+            const uint32_t* bp = p.bits + ((int64_t)l * p.G + g) * 8 * p.M + (row_ok ? m : 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mb[i] = (row_ok && grp + 2 * i < KS) ? __ldg(bp + (int64_t)(grp + 2 * i) * p.M) : 0u;
+        };
+        uint32_t mb[4];
+        load_bits(L - 1, mb);
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // headw_s complete
+        if (t256 == 0) FZ_STAMP(2);
+
+        int fe = 0;
+        uint8_t* my_hi = a_hi(grp) + q * 4096;
+        uint8_t* my_lo = a_lo(grp) + q * 4096;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        auto write_a = [&](const float (&x)[32]) {      // this warp's 32 rows of the stage's hi and lo tiles
+            float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
+            float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                lrow[j4 ^ (lane & 7)] = make_float4(lo_of(x[4 * j4]), lo_of(x[4 * j4 + 1]), lo_of(x[4 * j4 + 2]),
+                                                    lo_of(x[4 * j4 + 3]));
+        };
+        // ---- the generated operand of the first GEMM: dZ_{L-1} chunk by chunk, paced by the ring
+        for (int c = grp, i = 0; c < KS; c += 2, ++i) {
+            float x[32];
+            const float* hw = headw_s + 32 * c;
+            const uint32_t bits = mb[i];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? dq_m * hw[j] : 0.f;
+            if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
+            write_a(x);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_AFULL + grp));
+            ++fe;
+        }
+        // ---- epilogues: dZ_{l-1} = acc * relu'(H_{l-1}); stored, and (unless it is the last) the next GEMM's operand
+        for (int t = 0; t < NG; ++t) {
+            const int l = L - 1 - t;                // the GEMM multiplied by W_l; its output is the gradient of layer l-1
+            const bool last = t == NG - 1;
+            load_bits(l - 1, mb);
+            mbar_wait(bar(BAR_ACC + (t & 1)), (t >> 1) & 1);
+            tc_fence_after();
+            if (t256 == 0) FZ_STAMP(112 + t);
+            if (last) orlk::pdl_trigger();
+            for (int c = grp, i = 0; c < KS; c += 2, ++i) {
+                uint32_t v[32];
+                tmem_ld32(tlane + (uint32_t)(NMAX * (t & 1) + 32 * c), v);
+                tmem_wait_ld();
+                float x[32];
+                const uint32_t bits = mb[i];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                if (last) {     // every MMA has completed: own store tiles in the idle B ring, no store waits for another
+                    uint8_t* tile = b_base + ((warp - 2) * 4 + i) * 4096;
+                    float4* hrow = reinterpret_cast<float4*>(tile + lane * 128);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        hrow[j4 ^ (lane & 7)] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&maps.dz[l - 1], smem_u32(tile), 32 * c, tile_m * BM + q * 32, g, 0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    continue;
+                }
+                if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                write_a(x);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(BAR_AFULL + grp));
+                    tma_store_4d(&maps.dz[l - 1], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++fe;
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (threadIdx.x == 64) { FZ_STAMP(3); FZ_GSTAMP(6); }
     tc_fence_before();
@@ -380,6 +623,7 @@ int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
     p->gs = q->gs;
     p->head_w = q->head_w; p->head_b = q->head_b;
     p->out = q->out; p->out_gs = q->out_gs;
+    p->bits = q->relu_bits;
     p->M = q->M; p->N = q->N; p->G = q->G; p->L = q->n_hidden;
     p->tiles_m = (q->M + BM - 1) / BM;
     p->store_h = store ? 1 : 0;
@@ -392,8 +636,44 @@ int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
 
 extern "C" int orlk_sizeof_fused_fwd(void) { return (int)sizeof(OrlkFusedFwd); }
 
+extern "C" int orlk_sizeof_fused_bwd(void) { return (int)sizeof(OrlkFusedBwd); }
+
 extern "C" int orlk_fused_init(void) {
-    return check(cudaFuncSetAttribute(k_critic_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
+    int rc = check(cudaFuncSetAttribute(k_critic_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
+    if (rc) return rc;
+    return check(cudaFuncSetAttribute(k_critic_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_bwd");
+}
+
+extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
+    ORLK_REQUIRE(q != nullptr && q->M > 0 && q->G > 0, "sizes");
+    ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
+    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
+    ORLK_REQUIRE(q->gs % 4 == 0 && q->dz_gs % 4 == 0, "member strides must be multiples of 4 floats");
+    ORLK_REQUIRE(q->dq != nullptr && q->head_w != nullptr && q->relu_bits != nullptr, "dq, head weights, ReLU bits");
+    static BwdMaps maps;
+    BwdParams p;
+    memset(&maps, 0, sizeof(maps));
+    memset(&p, 0, sizeof(p));
+    for (int l = 1; l < q->n_hidden; ++l) {
+        ORLK_REQUIRE(q->WT[l] != nullptr && q->WTlo[l] != nullptr && aligned16(q->WT[l]) && aligned16(q->WTlo[l]),
+                     "transposed weights (and lo copies) must be 16-byte aligned");
+        ORLK_REQUIRE(q->dZ[l - 1] != nullptr && aligned16(q->dZ[l - 1]), "dZ must be 16-byte aligned");
+        int rc = make_map(&maps.wt[l - 1], q->WT[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+        if (rc) return rc;
+        rc = make_map(&maps.wtlo[l - 1], q->WTlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+        if (rc) return rc;
+        rc = make_map_c(&maps.dz[l - 1], q->dZ[l - 1], q->N, q->dz_gs, 0, q->M, q->N, q->G, 1);
+        if (rc) return rc;
+    }
+    p.gs = q->gs;
+    p.dq = q->dq; p.dq_gs = q->dq_gs;
+    p.head_w = q->head_w;
+    p.bits = q->relu_bits;
+    p.M = q->M; p.N = q->N; p.G = q->G; p.L = q->n_hidden;
+    p.tiles_m = (q->M + BM - 1) / BM;
+    p.trace = orlk::trace_buffer();
+    orlk::launch(k_critic_bwd, dim3(q->G * p.tiles_m), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps, p);
+    return check_launch("k_critic_bwd");
 }
 
 extern "C" int orlk_fused_prep(const float* src, float* dst_lo, int64_t n, const float* W0, int64_t gs, int N, int K0, int G,

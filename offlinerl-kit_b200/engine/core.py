@@ -217,12 +217,12 @@ class Runtime:
     @staticmethod
     def fused_fwd_job(*, X: Mat, W0pad: int, W0pad_lo: int, W: Sequence[int], Wlo: Sequence[int], bias: Sequence[int],
                       H: Optional[Sequence[int]], gs: int, h_gs: int, head_w: int, head_b: int, out: int, out_gs: int,
-                      M: int, N: int, K0: int, G: int) -> dict:
+                      M: int, N: int, K0: int, G: int, relu_bits: int = 0) -> dict:
         """One pass of ``critic_fwd_fused``: W / Wlo / bias / H are per hidden layer (W[0], Wlo[0] unused: the first layer
         reads the padded copies); H = None keeps no activations (target / inference pass)."""
         return dict(X=X, W0pad=W0pad, W0pad_lo=W0pad_lo, W=list(W), Wlo=list(Wlo), bias=list(bias),
                     H=list(H) if H is not None else None, gs=gs, h_gs=h_gs, head_w=head_w, head_b=head_b, out=out,
-                    out_gs=out_gs, M=M, N=N, K0=K0, G=G)
+                    out_gs=out_gs, M=M, N=N, K0=K0, G=G, relu_bits=relu_bits)
 
     def critic_fwd_fused(self, jobs: Sequence[dict]) -> Callable[[], None]:
         """Whole Linear+ReLU critic passes + scalar heads for all members in ONE tcgen05 launch (csrc/orlk_fused.cu);
@@ -237,9 +237,24 @@ class Runtime:
                 q.H[l] = j["H"][l] if j["H"] is not None else None
             q.gs, q.h_gs = j["gs"], j["h_gs"]
             q.head_w, q.head_b, q.out, q.out_gs = j["head_w"], j["head_b"], j["out"], j["out_gs"]
+            q.relu_bits = j.get("relu_bits") or None
             q.M, q.N, q.K0, q.G, q.n_hidden = j["M"], j["N"], j["K0"], j["G"], len(j["bias"])
         n = len(jobs)
         return lambda: L.call("orlk_critic_fwd_fused", arr, n, self.cur)
+
+    def critic_bwd_fused(self, *, dq: int, dq_gs: int, head_w: int, relu_bits: int, WT: Sequence[int], WTlo: Sequence[int],
+                         dZ: Sequence[int], gs: int, dz_gs: int, M: int, N: int, G: int) -> Callable[[], None]:
+        """Input-gradient chain of a fused critic pass behind its scalar head, one tcgen05 launch (csrc/orlk_fused.cu).
+        WT / WTlo per hidden layer ([0] unused), dZ[l] for l = 0 .. n_hidden-2."""
+        q = L.FusedBwd()
+        q.dq, q.dq_gs, q.head_w, q.relu_bits = dq, dq_gs, head_w, relu_bits
+        for l in range(len(WT)):
+            q.WT[l], q.WTlo[l] = (WT[l] or None), (WTlo[l] or None)
+        for l in range(len(dZ)):
+            q.dZ[l] = dZ[l]
+        q.gs, q.dz_gs, q.M, q.N, q.G, q.n_hidden = gs, dz_gs, M, N, G, len(WT)
+        qp = _ctypes_pointer(q)
+        return lambda: L.call("orlk_critic_bwd_fused", qp, self.cur)
 
     def fused_prep(self, src: torch.Tensor, dst_lo: torch.Tensor, W0: int = 0, gs: int = 0, N: int = 0, K0: int = 0, G: int = 0,
                    w0pad: Optional[torch.Tensor] = None) -> Callable[[], None]:

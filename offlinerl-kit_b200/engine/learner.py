@@ -393,6 +393,11 @@ class MlpRun:
                           and all(h is None for h in self.HT) and ps.block % 4 == 0
                           and all(lays[l].w_off % 4 == 0 and lays[l].w_gs == ps.block and lays[l].b_gs == ps.block
                                   for l in range(n_hidden + 1)))
+        # ... and its input-gradient chain (scalar head folded in, relu' from the decision bits the forward pass leaves)
+        self.fused_bwd = (self.fused_fwd and need_grad and FUSED_BWD and self.fuse_head_bwd
+                          and all(self.tc_dgrad[l] for l in range(1, n_hidden)) and all(t is None for t in self.dZT))
+        self.relu_bits = rt.zeros(n_hidden, G, 8, M, dtype=torch.int32) if self.fused_bwd else None
+        self.bits_written = False
         # streaming kernels for the narrow first layer / narrow head at large row counts (any precision mode)
         # streaming kernels for the narrow first layer (K <= 32) and the narrow head's weight gradient
         self.narrow0 = lays[0].layout == "oi" and lays[0].in_dim <= 32
@@ -443,6 +448,7 @@ def chainable(run: "MlpRun", with_head: bool) -> bool:
 
 
 FUSED_FWD = os.environ.get("ORLK_FUSED_FWD", "1") != "0"
+FUSED_BWD = os.environ.get("ORLK_FUSED_BWD", "1") != "0"
 
 
 def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
@@ -455,6 +461,9 @@ def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
     done.add(key)
     plan.keep.append(ps)
     lay0 = ps.layers[0]
+    if store == "WT":       # the transposed copies feed the backward chain only: no first layer there
+        plan.add(f"{ps.name}.WT.fused_prep", rt.fused_prep(ps.WT, ps.lo_arena("WT")))
+        return
     plan.add(f"{ps.name}.{store}.fused_prep", rt.fused_prep(getattr(ps, store), ps.lo_arena(store), W0=ps.w(0, 0, store),
                                                             gs=lay0.w_gs, N=lay0.out_dim, K0=lay0.in_dim, G=ps.G,
                                                             w0pad=ps.w0_pad(store)))
@@ -470,7 +479,7 @@ def fused_fwd_job(rt: Runtime, run: "MlpRun", X: Mat) -> dict:
         W=[0] + [ps.w(l, 0, run.store) for l in range(1, nh)], Wlo=[0] + [ps.w_lo(l, 0, run.store) for l in range(1, nh)],
         bias=[ps.b(l, 0, run.store) for l in range(nh)], H=[run.H[l].data_ptr() for l in range(nh)] if run.keep_h else None,
         gs=ps.block, h_gs=M * N, head_w=ps.w(nh, 0, run.store), head_b=ps.b(nh, 0, run.store), out=run.out.data_ptr(),
-        out_gs=M * run.NS, M=M, N=N, K0=K0, G=G)
+        out_gs=M * run.NS, M=M, N=N, K0=K0, G=G, relu_bits=run.relu_bits.data_ptr() if run.fused_bwd else 0)
 
 
 def fusable_x(run: "MlpRun", X: Sequence[Mat]) -> bool:
@@ -488,6 +497,7 @@ def emit_forward_pair(rt: Runtime, plan: Plan, run_a: "MlpRun", Xa: Sequence[Mat
     emit_lo_refresh(rt, plan, run_a.ps, run_a.store)
     emit_lo_refresh(rt, plan, run_b.ps, run_b.store)
     plan.add(f"{tag_a}+{tag_b}.fwd_fused.tc", rt.critic_fwd_fused([fused_fwd_job(rt, run_a, Xa[0]), fused_fwd_job(rt, run_b, Xb[0])]))
+    run_a.bits_written = run_b.bits_written = True
     return True
 
 
@@ -517,6 +527,7 @@ def emit_forward(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], tag: st
     if not skip_head and fusable_x(run, X):
         emit_lo_refresh(rt, plan, ps, run.store)        # (a no-op when the caller has placed it earlier in the step)
         plan.add(f"{tag}.fwd_fused.tc", rt.critic_fwd_fused([fused_fwd_job(rt, run, X[0])]))
+        run.bits_written = True
         return
     for l in range(run.nh):
         lay = ps.layers[l]
@@ -625,6 +636,15 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
         return
     if dact is not None:
         raise L.OrlkError("emit_hidden_dgrad(dact=...) needs the fused chain path; call emit_dact instead")
+    if run.fused_bwd and run.bits_written and down_to == 1:
+        emit_lo_refresh(rt, plan, ps, "WT")         # (a no-op when the caller has placed it earlier in the step)
+        nh, N = run.nh, ps.layers[0].out_dim
+        head = ps.layers[nh]
+        plan.add(f"{tag}.dgrad_fused.tc", rt.critic_bwd_fused(
+            dq=run.dOut.data_ptr(), dq_gs=M, head_w=ps.w(nh, 0), relu_bits=run.relu_bits.data_ptr(),
+            WT=[0] + [ps.wt(l, 0) for l in range(1, nh)], WTlo=[0] + [ps._ptr(ps.lo_arena("WT"), ps.layers[l].w_off) for l in range(1, nh)],
+            dZ=[run.dZ[l].data_ptr() for l in range(nh - 1)], gs=ps.block, dz_gs=M * N, M=M, N=N, G=G))
+        return
     for l in range(run.nh - 1, down_to - 1, -1):
         lay = ps.layers[l]
         if run.tc_dgrad[l] and run.ens_tc:

@@ -372,6 +372,8 @@ class CQLLearner(TwinCriticLearner):
                 emit_lo_refresh(rt, plan, self.critic_ps, "P")
             if self.run_target.fused_fwd:
                 emit_lo_refresh(rt, plan, self.critic_ps, "T")
+            if self.run_critic.fused_bwd:
+                emit_lo_refresh(rt, plan, self.critic_ps, "WT")
         self._emit_actor_update(plan, clamp01=False, beside_forward=beside)
 
         # ---- critic phase with the UPDATED actor (cql.py:108-192)

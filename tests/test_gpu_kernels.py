@@ -877,3 +877,53 @@ def test_critic_forward_fused_two_jobs(rt):
     torch.cuda.synchronize()
     _check_fused(a)
     _check_fused(b)
+
+
+@pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (300, 128, 32, 4, 1), (2048 + 77, 64, 5, 2, 3)])
+def test_critic_backward_fused_matches_fp64(rt, M, N, K0, nh, G):
+    """orlk_critic_bwd_fused behind orlk_critic_fwd_fused: dZ_l of every hidden layer but the last against fp64 autograd
+    algebra on the activations the forward kernel stored (so that both sides take the same ReLU decisions)."""
+    case = _fused_case(rt, M, N, K0, nh, G, seed=7 * M + nh)
+    bits = torch.full((nh, G, 8, M), -1, dtype=torch.int32, device=DEV)
+    case["job"]["relu_bits"] = bits.data_ptr()
+    rt.critic_fwd_fused([case["job"]])()
+    torch.cuda.synchronize()
+    H = [h.cpu() for h in case["H"]]
+    for l in range(nh):         # the decision bits are exactly (H > 0)
+        want = (H[l] > 0).view(G, M, N // 32, 32).to(torch.int64)
+        words = (want << torch.arange(32)).sum(-1)
+        got = bits[l].cpu().to(torch.int64).transpose(1, 2) & 0xFFFFFFFF          # [G][M][8]
+        assert torch.equal(got[..., :N // 32], words), f"relu bits of layer {l}"
+    P, offs, block = case["P"], case["offs"], case["block"]
+    WT = torch.zeros_like(P)
+    for g in range(G):
+        for l in range(1, nh):
+            wo = g * block + offs[l][0]
+            WT[wo:wo + N * N] = P[wo:wo + N * N].view(N, N).t().reshape(-1)
+    WTd = WT.to(DEV)
+    WTlo = torch.empty_like(WTd)
+    rt.fused_prep(WTd, WTlo)()
+    gen = torch.Generator().manual_seed(5)
+    dq = torch.randn(G, M, generator=gen)
+    dqd = dq.to(DEV)
+    dZ = [torch.full((G, M, N), float("nan"), device=DEV) for _ in range(nh - 1)]
+    Pd = case["keep"][1]
+    op = rt.critic_bwd_fused(dq=dqd.data_ptr(), dq_gs=M, head_w=Pd.data_ptr() + 4 * offs[nh][0], relu_bits=bits.data_ptr(),
+                             WT=[0] + [WTd.data_ptr() + 4 * offs[l][0] for l in range(1, nh)],
+                             WTlo=[0] + [WTlo.data_ptr() + 4 * offs[l][0] for l in range(1, nh)],
+                             dZ=[t.data_ptr() for t in dZ], gs=block, dz_gs=M * N, M=M, N=N, G=G)
+    for _ in range(2):
+        op()
+    torch.cuda.synchronize()
+    for g in range(G):
+        Ws = case["Ws"][g]
+        d = dq[g].double()[:, None] * Ws[nh].double() * (H[nh - 1][g] > 0)
+        tol = 0.0
+        for l in range(nh - 1, 0, -1):
+            W = Ws[l].double()                               # [out, in]
+            tol += 3e-6 * (d.abs() @ W.abs()).max().item()
+            d = (d @ W) * (H[l - 1][g] > 0)
+            got = dZ[l - 1][g]
+            assert not torch.isnan(got).any(), f"dZ[{l - 1}] member {g}: unwritten output"
+            err = (got.double().cpu() - d).abs().max().item()
+            assert err <= tol, f"dZ[{l - 1}] member {g}: max err {err:.3e} vs {tol:.3e}"
