@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 24
+#define ORLK_ABI_VERSION 25
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -372,7 +372,12 @@ typedef struct OrlkAdamGroup {
     float lr, beta1, beta2, eps;
     float tau; /* polyak coefficient for descs with a target            */
     int32_t step; /* number of optimiser steps already applied             */
-    int32_t pad_[2];
+    /* bias corrections of the NEXT step t = step + 1, kept next to the counter so that no kernel evaluates a double
+     * precision pow() on its critical path: set by the host when a group is created / restored, advanced by
+     * orlk_step_end.  step_size = (float)((double)lr / bc1) as torch.optim.Adam computes it. */
+    double bc1;      /* 1 - beta1^t */
+    float bc2_sqrt;  /* sqrt(1 - beta2^t) */
+    int32_t pad_;
 } OrlkAdamGroup;
 
 int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, int B, float* scalars, int auto_alpha,
@@ -477,7 +482,7 @@ typedef struct OrlkAdamDesc {
     int32_t g_splits;
     int32_t group;
     float wd;
-    int32_t block_start; /* prefix sum of ceil(n / 256) */
+    int32_t block_start; /* prefix sum of ceil(n / 128) */
     int32_t flags;       /* ORLK_OPT_ADAM | ORLK_OPT_POLYAK */
     int32_t cols;        /* with pT: the tensor is [n/cols, cols] row-major ...                     */
     float* pT;           /* ... and pT receives its transpose [cols, n/cols] (K-major dgrad operand) */

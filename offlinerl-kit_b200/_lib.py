@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 24
+ABI_VERSION = 25
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -35,7 +35,14 @@ class ConcatSeg(C.Structure):
 
 class AdamGroup(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("tau", C.c_float), ("step", C.c_int32), ("pad_", C.c_int32 * 2)]
+                ("tau", C.c_float), ("step", C.c_int32), ("bc1", C.c_double), ("bc2_sqrt", C.c_float), ("pad_", C.c_int32)]
+
+    def refresh(self) -> "AdamGroup":
+        """Bias corrections of the next step (t = step + 1) from the (float) betas, as the device keeps them up to date."""
+        t = self.step + 1
+        self.bc1 = 1.0 - float(self.beta1) ** t
+        self.bc2_sqrt = (1.0 - float(self.beta2) ** t) ** 0.5
+        return self
 
 
 class AdamDesc(C.Structure):

@@ -91,6 +91,33 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Same as launch(), with the highest scheduling priority the device offers (a kernel-node attribute under stream capture):
+// when CTAs of several ready grids compete for an SM, these go first.  For short launches that finish a dependency chain
+// (the per-layer optimiser updates) while long tensor-core grids of other branches still have CTAs waiting for an SM.
+template <typename... KArgs, typename... Args>
+inline void launch_high_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    prepare_kernel(reinterpret_cast<const void*>(kernel));
+    static int greatest = 1;
+    if (greatest == 1) {
+        int least = 0, g = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &g) != cudaSuccess) g = 0;
+        greatest = g;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = greatest;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -2,6 +2,7 @@
 // Everything here is latency-bound elementwise / reduction work on <= 8K rows: warp-shuffle reductions,
 // one CTA for the scalar losses, no atomics (results are run-to-run deterministic).
 #include <math.h>
+#include <stdlib.h>
 #include "orlk_common.cuh"
 using namespace orlk;
 
@@ -256,6 +257,30 @@ k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict_
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
     const int NS = 2 * A;
+    // four repeats per pass: lane = 8 * (repeat within the pass) + action dimension (A <= 8)
+    const int gi = lane & 7, gr = lane >> 3;
+    // Everything the samplers read that does not depend on the head - the noise of the first four passes of every use
+    // that contains this row, and the observation row they copy - is requested BEFORE the head's dot products, so that
+    // the kernel pays one memory round trip instead of one per pass (the stores in between keep the compiler from
+    // hoisting these loads by itself).
+    constexpr int PRE_P = 4, PRE_O = 4;
+    float epre[4][PRE_P], opre[4][PRE_O];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool in = q < U.n && m >= U.u[q].r0 && m < U.u[q].r1;
+        const int j = in ? m - U.u[q].r0 : 0;
+#pragma unroll
+        for (int pp = 0; pp < PRE_P; ++pp) {
+            const int r = 4 * pp + gr;
+            const bool on = in && r < U.u[q].rep && gi < A && U.u[q].eps != nullptr;
+            epre[q][pp] = on ? U.u[q].eps[((int64_t)j * U.u[q].rep + r) * A + gi] : 0.f;
+        }
+#pragma unroll
+        for (int oo = 0; oo < PRE_O; ++oo) {
+            const int c = lane + 32 * oo;
+            opre[q][oo] = (in && U.u[q].xout != nullptr && c < U.u[q].obs_dim) ? U.u[q].obs[(int64_t)j * U.u[q].ld_obs + c] : 0.f;
+        }
+    }
     float acc[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) acc[n] = 0.f;
@@ -280,13 +305,13 @@ k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict_
             if (n == lane + A) raw = v;
             if (lane == 0) head[(int64_t)m * NS + n] = v;
         }
-    // four repeats per pass: lane = 8 * (repeat within the pass) + action dimension (A <= 8)
-    const int gi = lane & 7, gr = lane >> 3;
     const float mu_i = __shfl_sync(0xffffffffu, mu, gi), raw_i = __shfl_sync(0xffffffffu, raw, gi);
     const float ls = fminf(fmaxf(raw_i, LOG_SIG_MIN), LOG_SIG_MAX);
     const float sigma = expf(ls);
     const float lsig = logf(sigma);
-    for (int q = 0; q < U.n; ++q) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q >= U.n) break;
         const OrlkSampleUse& u = U.u[q];
         if (m < u.r0 || m >= u.r1) continue;            // warp-uniform
         const int j = m - u.r0;
@@ -297,7 +322,12 @@ k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict_
             const int64_t o = (int64_t)j * u.rep + r;
             float t = 0.f;
             if (on) {
-                const float uu = u.eps ? fmaf(sigma, u.eps[o * A + gi], mu_i) : mu_i;
+                float e = 0.f;
+                if (u.eps) {
+                    const int pp = r0 >> 2;
+                    e = pp == 0 ? epre[q][0] : pp == 1 ? epre[q][1] : pp == 2 ? epre[q][2] : pp == 3 ? epre[q][3] : u.eps[o * A + gi];
+                }
+                const float uu = u.eps ? fmaf(sigma, e, mu_i) : mu_i;
                 const float a = tanhf(uu);
                 const float d = uu - mu_i;
                 t = -(d * d) / (2.f * sigma * sigma) - lsig - HALF_LOG_2PI - logf((1.f - a * a) + 1e-6f);
@@ -312,7 +342,12 @@ k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict_
                 for (int rr = 0; rr < 4; ++rr) {
                     if (r0 + rr >= u.rep) break;
                     float* xo = u.xout + ((int64_t)j * u.rep + r0 + rr) * u.ld_x;
-                    for (int c = lane; c < u.obs_dim; c += 32) xo[c] = ob[c];
+#pragma unroll
+                    for (int oo = 0; oo < PRE_O; ++oo) {
+                        const int c = lane + 32 * oo;
+                        if (c < u.obs_dim) xo[c] = opre[q][oo];
+                    }
+                    for (int c = lane + 32 * PRE_O; c < u.obs_dim; c += 32) xo[c] = ob[c];
                 }
             }
         }
@@ -331,7 +366,9 @@ k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c,
                   const float* __restrict__ act, int64_t ld_act, const float* __restrict__ glp, int M, int A,
                   float* __restrict__ dhead, const float* __restrict__ Wh, int Ka, const float* __restrict__ Hlast,
                   float* __restrict__ dZlast) {
-    orlk::pdl_enter();
+    // The two weight blocks staged below are written by optimiser launches only, never by the launch right in front of
+    // this one (a critic dgrad), so they are fetched while that launch is still running; its outputs are read after the wait.
+    orlk::pdl_trigger();
     extern __shared__ float sm[];
     float* w0s = sm;                                    // [n_c][Kc][A]   action columns of the critics' first layers
     float* whs = sm + (size_t)n_c * Kc * A;             // [2A][Ka]       the actor's head
@@ -353,10 +390,22 @@ k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c,
     } else {
         for (int i = threadIdx.x; i < 2 * A * Ka; i += blockDim.x) whs[i] = __ldg(Wh + i);
     }
+    orlk::pdl_wait();
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
+    // the row's inputs of the later stages, requested up front: one memory round trip instead of three
+    float pre_g = 0.f, pre_raw = 0.f, pre_e = 0.f, pre_a = 0.f;
+    if (lane < A) {
+        pre_g = glp ? glp[m] : 0.f;
+        pre_raw = head[(int64_t)m * 2 * A + A + lane];
+        pre_e = eps[(int64_t)m * A + lane];
+        pre_a = act[(int64_t)m * ld_act + lane];
+    }
+    float pre_h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pre_h[q] = (lane + 32 * q < Ka) ? __ldg(Hlast + (int64_t)m * Ka + lane + 32 * q) : 0.f;
     // ---- d/da: lanes split k, then a warp sum per action dimension
     float da[AM];
 #pragma unroll
@@ -378,13 +427,12 @@ k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c,
     float dmu = 0.f, draw = 0.f;
     if (lane < A) {
         const int i = lane;
-        const float* h = head + (int64_t)m * 2 * A;
-        const float g = glp ? glp[m] : 0.f;
-        const float raw = h[A + i];
+        const float g = pre_g;
+        const float raw = pre_raw;
         const float ls = fminf(fmaxf(raw, LOG_SIG_MIN), LOG_SIG_MAX);
         const float sigma = expf(ls);
-        const float e = eps[(int64_t)m * A + i];
-        const float a = act[(int64_t)m * ld_act + i];
+        const float e = pre_e;
+        const float a = pre_a;
         const float om = 1.f - a * a;
         float dai = 0.f;
 #pragma unroll
@@ -414,18 +462,16 @@ k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c,
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int n = n0 + lane + 32 * q;
-            if (n < Ka) dZlast[(int64_t)m * Ka + n] = __ldg(Hlast + (int64_t)m * Ka + n) > 0.f ? acc[q] : 0.f;
+            const float hv = n0 == 0 ? pre_h[q] : (n < Ka ? __ldg(Hlast + (int64_t)m * Ka + n) : 0.f);
+            if (n < Ka) dZlast[(int64_t)m * Ka + n] = hv > 0.f ? acc[q] : 0.f;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------ scalar Adam
 __device__ float scalar_adam(float p, float g, float* mv, const OrlkAdamGroup& grp) {
-    const int t = grp.step + 1;
-    const double bc1 = 1.0 - pow((double)grp.beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)grp.beta2, (double)t);
-    const float step_size = (float)((double)grp.lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const float step_size = (float)((double)grp.lr / grp.bc1);      // bias corrections: kept by the host / orlk_step_end
+    const float bc2_sqrt = grp.bc2_sqrt;
     float m = mv[0], v = mv[1];
     m = m + (g - m) * (1.f - grp.beta1);
     v = v * grp.beta2 + (1.f - grp.beta2) * g * g;
@@ -610,29 +656,38 @@ k_cql_critic_loss(const float* __restrict__ q, int64_t q_cs, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------ fused Adam + polyak
-constexpr int ADAM_BLOCK_ELEMS = 256;
+// 128-thread blocks (64 registers each): 8 K registers, so an optimiser block fits on an SM next to a resident tensor-core
+// CTA (~51 K of the 64 K registers) and the per-layer updates really overlap the weight-gradient GEMMs of the other layers
+constexpr int ADAM_BLOCK_ELEMS = 128;
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(ADAM_BLOCK_ELEMS, 8)
 k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamGroup* __restrict__ groups) {
     orlk::pdl_enter();
     __shared__ OrlkAdamDesc sd;
-    __shared__ float s_step_size, s_bc2_sqrt;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // this block's tensor = the last descriptor whose first block is <= blockIdx.x; the candidates are fetched by the
+        // lanes of one warp at once (a scalar scan is one dependent L2 round trip per descriptor)
         int p = 0;
-        while (p + 1 < n_descs && descs[p + 1].block_start <= (int)blockIdx.x) ++p;
-        sd = descs[p];
-        const OrlkAdamGroup g = groups[sd.group];
-        const int t = g.step + 1;
-        s_step_size = (float)((double)g.lr / (1.0 - pow((double)g.beta1, (double)t)));
-        s_bc2_sqrt = (float)sqrt(1.0 - pow((double)g.beta2, (double)t));
+        for (int base = 0; base < n_descs; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            const bool le = i < n_descs && descs[i].block_start <= (int)blockIdx.x;
+            const unsigned m = __ballot_sync(0xffffffffu, le);
+            if (m == 0u) break;
+            p = base + 31 - __clz(m);
+            if (m != 0xffffffffu) break;
+        }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + p);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sd);
+        for (int w = threadIdx.x; w < (int)(sizeof(OrlkAdamDesc) / 4); w += 32) dst[w] = src[w];
     }
     __syncthreads();
     const OrlkAdamDesc& d = sd;
     const OrlkAdamGroup g = groups[d.group];
+    const float s_step_size = (float)((double)g.lr / g.bc1), s_bc2_sqrt = g.bc2_sqrt;
     const int64_t base = (int64_t)(blockIdx.x - d.block_start) * ADAM_BLOCK_ELEMS;
 #pragma unroll
-    for (int j = 0; j < ADAM_BLOCK_ELEMS / 256; ++j) {
-        const int64_t i = base + j * 256 + threadIdx.x;
+    for (int j = 0; j < 1; ++j) {
+        const int64_t i = base + threadIdx.x;
         if (i >= d.n) continue;
         float p = d.p[i];
         if (d.flags & ORLK_OPT_ADAM) {
@@ -677,9 +732,26 @@ k_adam_step(const OrlkAdamDesc* __restrict__ descs, int n_descs, const OrlkAdamG
 }
 
 __global__ void k_step_end(OrlkAdamGroup* groups, unsigned int mask, unsigned long long* counter) {
-    orlk::pdl_enter();
+    // The counters (and betas) are written by this kernel and by host uploads only, so the next step's bias corrections
+    // - two double precision pow() - are evaluated while the optimiser launches in front of this one are still running.
+    orlk::pdl_trigger();
     const int g = threadIdx.x;
-    if (g < 32 && (mask >> g) & 1u) groups[g].step += 1;
+    const bool on = g < 32 && ((mask >> g) & 1u);
+    int step = 0;
+    double bc1 = 1.0;
+    float bc2_sqrt = 1.f;
+    if (on) {
+        step = groups[g].step + 1;
+        const int t = step + 1;
+        bc1 = 1.0 - pow((double)groups[g].beta1, (double)t);
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)groups[g].beta2, (double)t));
+    }
+    orlk::pdl_wait();
+    if (on) {
+        groups[g].step = step;
+        groups[g].bc1 = bc1;
+        groups[g].bc2_sqrt = bc2_sqrt;
+    }
     if (g == 0 && counter != nullptr) *counter += 1ull;
 }
 
@@ -836,7 +908,10 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
 
 int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream) {
     ORLK_REQUIRE(descs_dev != nullptr && n_descs > 0 && total_blocks > 0 && groups != nullptr, "descs");
-    orlk::launch(k_adam_step, total_blocks, 256, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
+    static int hp = -1;
+    if (hp < 0) { const char* e = getenv("ORLK_ADAM_PRIORITY"); hp = e ? atoi(e) : 1; }
+    if (hp) orlk::launch_high_priority(k_adam_step, total_blocks, ADAM_BLOCK_ELEMS, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
+    else orlk::launch(k_adam_step, total_blocks, ADAM_BLOCK_ELEMS, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
     return check_launch("k_adam_step");
 }
 

@@ -298,7 +298,7 @@ class Runtime:
             d.n, d.g_split_stride, d.g_splits, d.group = t.n, t.g_split_stride, t.g_splits, t.group
             d.wd, d.block_start, d.flags = t.wd, blk, t.flags
             d.pT, d.cols = t.pT or None, max(t.cols, 1)
-            blk += -(-t.n // 256)
+            blk += -(-t.n // 128)
         dev = self.upload_bytes(bytes(arr))
         n, total, ptr, gp = len(descs), blk, C.c_void_p(dev.data_ptr()), C.c_void_p(groups_ptr)
         return lambda: L.call("orlk_adam_step", ptr, n, total, gp, self.cur)

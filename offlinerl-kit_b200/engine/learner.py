@@ -93,6 +93,8 @@ class Learner:
         return g
 
     def push_groups(self) -> None:
+        for g in range(self._n_groups):
+            self._groups[g].refresh()
         raw = torch.frombuffer(bytearray(bytes(self._groups)), dtype=torch.uint8)
         self.groups_dev.copy_(raw.to(self.dev))
 

@@ -365,6 +365,7 @@ def test_adam_polyak_matches_torch(rt):
     pd, md, vd, td = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), tgt0.to(DEV)
     groups = (L.AdamGroup * 2)()
     groups[1].lr, groups[1].beta1, groups[1].beta2, groups[1].eps, groups[1].tau, groups[1].step = 3e-4, 0.9, 0.999, 1e-8, 0.005, 0
+    groups[1].refresh()
     gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
     gbuf = torch.zeros(splits, n, device=DEV)
     tref = tgt0.clone()
@@ -409,6 +410,7 @@ def test_sac_actor_loss_vs_autograd(rt):
         sc[0], sc[1] = la0, alpha
         groups = (L.AdamGroup * 1)()
         groups[0].lr, groups[0].beta1, groups[0].beta2, groups[0].eps = 1e-2, 0.9, 0.999, 1e-8
+        groups[0].refresh()
         gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
         mv = torch.zeros(2, device=DEV)
         qg, lg = q.to(DEV), logp.to(DEV)
@@ -469,6 +471,7 @@ def test_cql_critic_loss_vs_autograd(rt):
         sc[1], sc[2] = alpha, cla0
         groups = (L.AdamGroup * 1)()
         groups[0].lr, groups[0].beta1, groups[0].beta2, groups[0].eps = 3e-4, 0.9, 0.999, 1e-8
+        groups[0].refresh()
         gd = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).to(DEV)
         mv = torch.zeros(2, device=DEV)
         dev = lambda t: t.to(DEV)
