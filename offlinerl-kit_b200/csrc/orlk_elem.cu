@@ -240,193 +240,156 @@ __global__ void k_tanh_gauss_bwd(const float* __restrict__ head, int64_t ld_head
     }
 }
 
-// Actor head + reparameterised sampling in one launch, one warp per head row m:
+// Actor head + reparameterised sampling in one launch, one 4-warp block per head row m:
 //   head[m] = X[m] . Wh^T + bh   (mu | log-std raw, 2A outputs), then for every use u whose row range contains m and every
 //   repeat r:  a = tanh(mu + sigma * eps[o]),  logp[o],  X_out[o] = [obs[j] | a]   with j = m - r0, o = j * rep + r
 // (exactly k_skinny_fwd followed by k_tanh_gauss_sample per use; CQL's critic phase has three uses of one head pass).
+// The launch holds only a few hundred rows, so a warp has an SM scheduler to itself and runs at its dependent-issue
+// latency (~8 cycles per instruction, measured): what counts is the LENGTH of a warp's instruction stream.  Hence four
+// warps per row - each takes every fourth head output, then every fourth (use, pass of four repeats) - instead of one
+// warp doing a row's ~1400 instructions alone (10 us -> see profiles/).  Arithmetic per element as before.
 struct SampleUses {
     OrlkSampleUse u[4];
     int n;
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int HS_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * HS_WARPS)
 k_head_sample(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
               float* __restrict__ head, int M, int K, int A, const __grid_constant__ SampleUses U) {
     orlk::pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m >= M) return;
+    __shared__ float head_s[16];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int m = blockIdx.x;
     const int NS = 2 * A;
-    // four repeats per pass: lane = 8 * (repeat within the pass) + action dimension (A <= 8)
-    const int gi = lane & 7, gr = lane >> 3;
-    // Everything the samplers read that does not depend on the head - the noise of the first four passes of every use
-    // that contains this row, and the observation row they copy - is requested BEFORE the head's dot products, so that
-    // the kernel pays one memory round trip instead of one per pass (the stores in between keep the compiler from
-    // hoisting these loads by itself).
-    constexpr int PRE_P = 4, PRE_O = 4;
-    float epre[4][PRE_P], opre[4][PRE_O];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const bool in = q < U.n && m >= U.u[q].r0 && m < U.u[q].r1;
-        const int j = in ? m - U.u[q].r0 : 0;
-#pragma unroll
-        for (int pp = 0; pp < PRE_P; ++pp) {
-            const int r = 4 * pp + gr;
-            const bool on = in && r < U.u[q].rep && gi < A && U.u[q].eps != nullptr;
-            epre[q][pp] = on ? U.u[q].eps[((int64_t)j * U.u[q].rep + r) * A + gi] : 0.f;
-        }
-#pragma unroll
-        for (int oo = 0; oo < PRE_O; ++oo) {
-            const int c = lane + 32 * oo;
-            opre[q][oo] = (in && U.u[q].xout != nullptr && c < U.u[q].obs_dim) ? U.u[q].obs[(int64_t)j * U.u[q].ld_obs + c] : 0.f;
-        }
-    }
-    float acc[16];
-#pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    // ---- head outputs n = w, w + 4, ... of this row: lanes split k, then a warp sum
     const float4* x4 = reinterpret_cast<const float4*>(X + (int64_t)m * ldx);
     const int K4 = K >> 2;
-#pragma unroll 2
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k = lane; k < K4; k += 32) {
         const float4 xv = x4[k];
 #pragma unroll
-        for (int n = 0; n < 16; ++n)
+        for (int i = 0; i < 4; ++i) {
+            const int n = w + HS_WARPS * i;
             if (n < NS) {
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw) + k);
-                acc[n] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[n]))));
+                acc[i] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[i]))));
             }
-    }
-    float mu = 0.f, raw = 0.f;                          // lane i < A keeps its own action dimension
-#pragma unroll
-    for (int n = 0; n < 16; ++n)
-        if (n < NS) {
-            const float v = warp_sum(acc[n]) + (b ? __ldg(b + n) : 0.f);
-            if (n == lane) mu = v;
-            if (n == lane + A) raw = v;
-            if (lane == 0) head[(int64_t)m * NS + n] = v;
         }
-    const float mu_i = __shfl_sync(0xffffffffu, mu, gi), raw_i = __shfl_sync(0xffffffffu, raw, gi);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = w + HS_WARPS * i;
+        if (n < NS) {
+            const float v = warp_sum(acc[i]) + (b ? __ldg(b + n) : 0.f);
+            if (lane == 0) {
+                head_s[n] = v;
+                head[(int64_t)m * NS + n] = v;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- samplers: four repeats per pass, lane = 8 * (repeat within the pass) + action dimension (A <= 8);
+    //      pass t (counted over all uses that contain this row) belongs to warp t % 4
+    const int gi = lane & 7, gr = lane >> 3;
+    const float mu_i = gi < A ? head_s[gi] : 0.f, raw_i = gi < A ? head_s[A + gi] : 0.f;
     const float ls = fminf(fmaxf(raw_i, LOG_SIG_MIN), LOG_SIG_MAX);
     const float sigma = expf(ls);
     const float lsig = logf(sigma);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (q >= U.n) break;
+    int t = 0;
+    for (int q = 0; q < U.n; ++q) {
         const OrlkSampleUse& u = U.u[q];
-        if (m < u.r0 || m >= u.r1) continue;            // warp-uniform
+        if (m < u.r0 || m >= u.r1) continue;            // block-uniform
         const int j = m - u.r0;
-        const float* ob = u.xout ? u.obs + (int64_t)j * u.ld_obs : nullptr;
-        for (int r0 = 0; r0 < u.rep; r0 += 4) {
+        for (int r0 = 0; r0 < u.rep; r0 += 4, ++t) {
+            if ((t & (HS_WARPS - 1)) != w) continue;    // warp-uniform
             const int r = r0 + gr;
             const bool on = r < u.rep && gi < A;
             const int64_t o = (int64_t)j * u.rep + r;
-            float t = 0.f;
+            float tl = 0.f;
             if (on) {
-                float e = 0.f;
-                if (u.eps) {
-                    const int pp = r0 >> 2;
-                    e = pp == 0 ? epre[q][0] : pp == 1 ? epre[q][1] : pp == 2 ? epre[q][2] : pp == 3 ? epre[q][3] : u.eps[o * A + gi];
-                }
-                const float uu = u.eps ? fmaf(sigma, e, mu_i) : mu_i;
+                const float uu = u.eps ? fmaf(sigma, u.eps[o * A + gi], mu_i) : mu_i;
                 const float a = tanhf(uu);
                 const float d = uu - mu_i;
-                t = -(d * d) / (2.f * sigma * sigma) - lsig - HALF_LOG_2PI - logf((1.f - a * a) + 1e-6f);
+                tl = -(d * d) / (2.f * sigma * sigma) - lsig - HALF_LOG_2PI - logf((1.f - a * a) + 1e-6f);
                 u.act[o * u.ld_act + gi] = a;
             }
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            t += __shfl_xor_sync(0xffffffffu, t, 4);
-            if (gi == 0 && r < u.rep && u.logp) u.logp[o] = t;
+            tl += __shfl_xor_sync(0xffffffffu, tl, 1);
+            tl += __shfl_xor_sync(0xffffffffu, tl, 2);
+            tl += __shfl_xor_sync(0xffffffffu, tl, 4);
+            if (gi == 0 && r < u.rep && u.logp) u.logp[o] = tl;
             if (u.xout) {
+                const float* ob = u.obs + (int64_t)j * u.ld_obs;
+                for (int c = lane; c < u.obs_dim; c += 32) {
+                    const float ov = ob[c];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    if (r0 + rr >= u.rep) break;
-                    float* xo = u.xout + ((int64_t)j * u.rep + r0 + rr) * u.ld_x;
-#pragma unroll
-                    for (int oo = 0; oo < PRE_O; ++oo) {
-                        const int c = lane + 32 * oo;
-                        if (c < u.obs_dim) xo[c] = opre[q][oo];
-                    }
-                    for (int c = lane + 32 * PRE_O; c < u.obs_dim; c += 32) xo[c] = ob[c];
+                    for (int rr = 0; rr < 4; ++rr)
+                        if (r0 + rr < u.rep) u.xout[((int64_t)j * u.rep + r0 + rr) * u.ld_x + c] = ov;
                 }
             }
         }
     }
 }
 
-// Entry of the actor's backward pass in one launch (policy improvement step of SAC / CQL / MOPO), one warp per row m:
+// Entry of the actor's backward pass in one launch (policy improvement step of SAC / CQL / MOPO), one 4-warp block per row m:
 //   dL/da[m]      = sum_c dZ0_c[m][:] . W0_c[:, O:O+A]            (gradient of the critics w.r.t. the sampled action)
 //   dhead[m]      = tanh-Gaussian backward                          (same maths as k_tanh_gauss_bwd)
 //   dZlast[m][n]  = (dhead[m][:] . Wh[:, n]) * (Hlast[m][n] > 0)   (through the actor's head into its last hidden layer)
 // i.e. the skinny d/da product, the sampler backward and the head dgrad, which otherwise are three 3-4 us launches.
+// As in k_head_sample the launch is a few hundred rows, so the length of a warp's instruction stream is what costs:
+// the k range of the d/da product and the columns of the head dgrad are split over the block's four warps (a row used to
+// be one warp's ~1400 instructions behind a 24 KB shared-memory staging of the weights; they are L1 / L2 hits here).
+constexpr int BE_WARPS = 4;
+
 template <int AM>       // AM >= A: compile-time bound of the action dimension (8 or 32)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * BE_WARPS)
 k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c, const float* __restrict__ W0, int64_t w0_gs,
                   int ld_w0, int col0, const float* __restrict__ head, const float* __restrict__ eps,
                   const float* __restrict__ act, int64_t ld_act, const float* __restrict__ glp, int M, int A,
                   float* __restrict__ dhead, const float* __restrict__ Wh, int Ka, const float* __restrict__ Hlast,
                   float* __restrict__ dZlast) {
-    // The two weight blocks staged below are written by optimiser launches only, never by the launch right in front of
-    // this one (a critic dgrad), so they are fetched while that launch is still running; its outputs are read after the wait.
-    orlk::pdl_trigger();
-    extern __shared__ float sm[];
-    float* w0s = sm;                                    // [n_c][Kc][A]   action columns of the critics' first layers
-    float* whs = sm + (size_t)n_c * Kc * A;             // [2A][Ka]       the actor's head
-    for (int ck = threadIdx.x; ck < n_c * Kc; ck += blockDim.x) {      // one (critic, k) pair: A consecutive floats
-        const int c = ck / Kc, k = ck - c * Kc;
-        const float* src = W0 + c * w0_gs + (int64_t)k * ld_w0 + col0;
-#pragma unroll
-        for (int a = 0; a < AM; ++a)
-            if (a < A) w0s[ck * A + a] = __ldg(src + a);
-    }
-    if (aligned16(Wh) && ((2 * A * Ka) & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(Wh);
-        float4* d4 = reinterpret_cast<float4*>(whs);        // whs offset n_c*Kc*A floats: 16-byte aligned when that is a multiple of 4
-        if ((((size_t)n_c * Kc * A) & 3) == 0) {
-            for (int i = threadIdx.x; i < (2 * A * Ka) >> 2; i += blockDim.x) d4[i] = __ldg(s4 + i);
-        } else {
-            for (int i = threadIdx.x; i < 2 * A * Ka; i += blockDim.x) whs[i] = __ldg(Wh + i);
-        }
-    } else {
-        for (int i = threadIdx.x; i < 2 * A * Ka; i += blockDim.x) whs[i] = __ldg(Wh + i);
-    }
-    orlk::pdl_wait();
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m >= M) return;
-    // the row's inputs of the later stages, requested up front: one memory round trip instead of three
+    orlk::pdl_enter();
+    __shared__ float da_s[BE_WARPS][AM];
+    __shared__ float dh_s[2 * AM];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int m = blockIdx.x;
+    // inputs of the later stages, requested up front
     float pre_g = 0.f, pre_raw = 0.f, pre_e = 0.f, pre_a = 0.f;
-    if (lane < A) {
+    if (w == 0 && lane < A) {
         pre_g = glp ? glp[m] : 0.f;
         pre_raw = head[(int64_t)m * 2 * A + A + lane];
         pre_e = eps[(int64_t)m * A + lane];
         pre_a = act[(int64_t)m * ld_act + lane];
     }
-    float pre_h[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) pre_h[q] = (lane + 32 * q < Ka) ? __ldg(Hlast + (int64_t)m * Ka + lane + 32 * q) : 0.f;
-    // ---- d/da: lanes split k, then a warp sum per action dimension
+    // ---- d/da: the block's 128 threads split k, then warp sums and a fixed-order sum over the warps
     float da[AM];
 #pragma unroll
     for (int a = 0; a < AM; ++a) da[a] = 0.f;
     for (int c = 0; c < n_c; ++c) {
         const float* z = dZ0 + c * dz_gs + (int64_t)m * Kc;
-        const float* w = w0s + (size_t)c * Kc * A;
-        for (int k = lane; k < Kc; k += 32) {
+        const float* wc = W0 + c * w0_gs + col0;
+        for (int k = threadIdx.x; k < Kc; k += 32 * BE_WARPS) {
             const float zv = __ldg(z + k);
+            const float* wr = wc + (int64_t)k * ld_w0;
 #pragma unroll
             for (int a = 0; a < AM; ++a)
-                if (a < A) da[a] = fmaf(zv, w[k * A + a], da[a]);
+                if (a < A) da[a] = fmaf(zv, __ldg(wr + a), da[a]);
         }
     }
 #pragma unroll
     for (int a = 0; a < AM; ++a)
-        if (a < A) da[a] = warp_sum(da[a]);
-    // ---- sampler backward: lane i < A owns action dimension i
-    float dmu = 0.f, draw = 0.f;
-    if (lane < A) {
+        if (a < A) {
+            const float v = warp_sum(da[a]);
+            if (lane == 0) da_s[w][a] = v;
+        }
+    __syncthreads();
+    // ---- sampler backward: lane i < A of warp 0 owns action dimension i
+    if (w == 0 && lane < A) {
         const int i = lane;
+        float dai = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < BE_WARPS; ++ww) dai += da_s[ww][i];
         const float g = pre_g;
         const float raw = pre_raw;
         const float ls = fminf(fmaxf(raw, LOG_SIG_MIN), LOG_SIG_MAX);
@@ -434,37 +397,23 @@ k_actor_bwd_entry(const float* __restrict__ dZ0, int64_t dz_gs, int Kc, int n_c,
         const float e = pre_e;
         const float a = pre_a;
         const float om = 1.f - a * a;
-        float dai = 0.f;
-#pragma unroll
-        for (int q = 0; q < AM; ++q)
-            if (q == i) dai = da[q];
         const float t = 2.f * a * om / (om + 1e-6f);
         const float du = dai * om + g * t;
-        dmu = du;
-        draw = du * sigma * e - g;
+        float draw = du * sigma * e - g;
         if (!(raw >= LOG_SIG_MIN && raw <= LOG_SIG_MAX)) draw = 0.f;
-        dhead[(int64_t)m * 2 * A + i] = dmu;
+        dhead[(int64_t)m * 2 * A + i] = du;
         dhead[(int64_t)m * 2 * A + A + i] = draw;
+        dh_s[i] = du;
+        dh_s[A + i] = draw;
     }
-    // ---- head dgrad: every lane needs all 2A head gradients
-    float acc[8];
-    for (int n0 = 0; n0 < Ka; n0 += 256) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-        for (int j = 0; j < A; ++j) {
-            const float gm = __shfl_sync(0xffffffffu, dmu, j), gr = __shfl_sync(0xffffffffu, draw, j);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int n = n0 + lane + 32 * q;
-                if (n < Ka) acc[q] = fmaf(gm, whs[j * Ka + n], fmaf(gr, whs[(A + j) * Ka + n], acc[q]));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int n = n0 + lane + 32 * q;
-            const float hv = n0 == 0 ? pre_h[q] : (n < Ka ? __ldg(Hlast + (int64_t)m * Ka + n) : 0.f);
-            if (n < Ka) dZlast[(int64_t)m * Ka + n] = hv > 0.f ? acc[q] : 0.f;
-        }
+    __syncthreads();
+    // ---- head dgrad: one output column per thread and pass
+    for (int n = threadIdx.x; n < Ka; n += 32 * BE_WARPS) {
+        const float hv = __ldg(Hlast + (int64_t)m * Ka + n);
+        float acc = 0.f;
+        for (int j = 0; j < A; ++j)
+            acc = fmaf(dh_s[j], __ldg(Wh + (int64_t)j * Ka + n), fmaf(dh_s[A + j], __ldg(Wh + (int64_t)(A + j) * Ka + n), acc));
+        dZlast[(int64_t)m * Ka + n] = hv > 0.f ? acc : 0.f;
     }
 }
 
@@ -855,7 +804,7 @@ int orlk_head_sample(const float* X, int64_t ldx, const float* W, int64_t ldw, c
                      "use");
         U.u[i] = uses_host[i];
     }
-    orlk::launch(k_head_sample, (M + 7) / 8, 256, 0, (cudaStream_t)stream, X, ldx, W, ldw, b, head, M, K, A, U);
+    orlk::launch(k_head_sample, M, 32 * HS_WARPS, 0, (cudaStream_t)stream, X, ldx, W, ldw, b, head, M, K, A, U);
     return check_launch("k_head_sample");
 }
 
@@ -864,13 +813,11 @@ int orlk_actor_bwd_entry(const float* dZ0, int64_t dz_gs, int Kc, int n_c, const
                          float* dhead, const float* Wh, int Ka, const float* Hlast, float* dZlast, void* stream) {
     ORLK_REQUIRE(M > 0 && A > 0 && A <= MAX_A && Kc > 0 && Ka > 0 && n_c > 0, "sizes");
     ORLK_REQUIRE(dZ0 && W0 && head && eps && act && dhead && Wh && Hlast && dZlast, "pointers");
-    const size_t smem = sizeof(float) * ((size_t)n_c * Kc * A + (size_t)2 * A * Ka);
-    ORLK_REQUIRE(smem <= 48 * 1024, "first-layer action columns + head must fit 48 KB of shared memory");
     if (A <= 8)
-        orlk::launch(k_actor_bwd_entry<8>, (M + 7) / 8, 256, smem, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0, col0,
+        orlk::launch(k_actor_bwd_entry<8>, M, 32 * BE_WARPS, 0, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0, col0,
                      head, eps, act, ld_act, glp, M, A, dhead, Wh, Ka, Hlast, dZlast);
     else
-        orlk::launch(k_actor_bwd_entry<MAX_A>, (M + 7) / 8, 256, smem, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0,
+        orlk::launch(k_actor_bwd_entry<MAX_A>, M, 32 * BE_WARPS, 0, (cudaStream_t)stream, dZ0, dz_gs, Kc, n_c, W0, w0_gs, ld_w0,
                      col0, head, eps, act, ld_act, glp, M, A, dhead, Wh, Ka, Hlast, dZlast);
     return check_launch("k_actor_bwd_entry");
 }
@@ -909,7 +856,9 @@ int orlk_cql_critic_loss(const float* q, int64_t q_cs, const float* tq, int64_t 
 int orlk_adam_step(const OrlkAdamDesc* descs_dev, int n_descs, int total_blocks, const OrlkAdamGroup* groups, void* stream) {
     ORLK_REQUIRE(descs_dev != nullptr && n_descs > 0 && total_blocks > 0 && groups != nullptr, "descs");
     static int hp = -1;
-    if (hp < 0) { const char* e = getenv("ORLK_ADAM_PRIORITY"); hp = e ? atoi(e) : 1; }
+    // (measured: with priority the optimiser blocks crowd the SMs and keep waiting tensor-core CTAs out: 255 -> 275 us per CQL
+    // step; off by default, the launch order in emit_wgrad_adam gives the overlap instead)
+    if (hp < 0) { const char* e = getenv("ORLK_ADAM_PRIORITY"); hp = e ? atoi(e) : 0; }
     if (hp) orlk::launch_high_priority(k_adam_step, total_blocks, ADAM_BLOCK_ELEMS, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
     else orlk::launch(k_adam_step, total_blocks, ADAM_BLOCK_ELEMS, 0, (cudaStream_t)stream, descs_dev, n_descs, groups);
     return check_launch("k_adam_step");

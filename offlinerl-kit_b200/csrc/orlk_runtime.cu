@@ -86,7 +86,8 @@ int orlk_graph_end(void* stream, void** graph_exec_out) {
         free(from); free(to); free(ed);
     }
     cudaGraphExec_t ex = nullptr;
-    rc = check(cudaGraphInstantiate(&ex, g, 0), "cudaGraphInstantiate");
+    // per-node priorities (the optimiser launches, orlk::launch_high_priority) are honoured only with this flag
+    rc = check(cudaGraphInstantiate(&ex, g, cudaGraphInstantiateFlagUseNodePriority), "cudaGraphInstantiate");
     cudaGraphDestroy(g);
     if (rc) return rc;
     *graph_exec_out = (void*)ex;

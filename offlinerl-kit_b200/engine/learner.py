@@ -451,6 +451,7 @@ def chainable(run: "MlpRun", with_head: bool) -> bool:
 
 FUSED_FWD = os.environ.get("ORLK_FUSED_FWD", "1") != "0"
 FUSED_BWD = os.environ.get("ORLK_FUSED_BWD", "1") != "0"
+WGRAD_CHAIN = os.environ.get("ORLK_WGRAD_CHAIN", "0") == "1"      # measured slower (262 vs 255 us): off
 
 
 def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
@@ -815,7 +816,33 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     def adam_for(layers):
         return rt.adam(adam_descs(ps, gb, splits, polyak, layers=layers, grad_src=grad_src, members=range(G)), groups_ptr)
 
-    if len(launches) > 1:
+    n_tc = sum(1 for label, _ in launches if label.endswith(".tc"))
+    if n_tc >= 2 and WGRAD_CHAIN:
+        # Experiment (ORLK_WGRAD_CHAIN=1, off): the optimiser launches of the first layers start late because a ready grid that
+        # still waits for SMs (the next weight gradient on a parallel branch) is dispatched before any later grid.  Here the
+        # GEMMs form ONE chain on the main stream, last layer first, each followed by its Adam(+polyak) launch on a side
+        # stream.  Measured: the updates do start earlier, but the GEMMs lose the overlap of their tails (262 vs 255 us).
+        tc = sorted((i for i in range(len(launches)) if launches[i][0].endswith(".tc")), key=lambda i: -max(launch_layers[i]))
+        simt = [i for i in range(len(launches)) if not launches[i][0].endswith(".tc")]
+        side = 1
+        for n, i in enumerate(tc):
+            plan.add(*launches[i])
+            if n == len(tc) - 1:        # the last GEMM's (small) update stays behind it on the main stream
+                plan.add(f"{tag}.adam{i}", adam_for(sorted(set(launch_layers[i]))))
+                break
+            plan.fork()                 # side streams wait for this GEMM
+            if n == 0:                  # SIMT weight gradients (scalar head): beside the second GEMM
+                for j in simt:
+                    plan.branch(side)
+                    plan.add(*launches[j])
+                    plan.add(f"{tag}.adam{j}", adam_for(sorted(set(launch_layers[j]))))
+                    side = side % Plan.N_SIDE + 1
+            plan.branch(side)
+            plan.add(f"{tag}.adam{i}", adam_for(sorted(set(launch_layers[i]))))
+            side = side % Plan.N_SIDE + 1
+            plan.branch(0)
+        plan.join()
+    elif len(launches) > 1:
         # each branch: one weight-gradient launch and right behind it the Adam(+polyak) update of exactly those layers, so
         # the bandwidth-bound optimiser work of one layer overlaps the tensor-core work of the others
         plan.fork()
