@@ -56,10 +56,10 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def ncu_tc_summary():
-    """(csv path, mean DRAM bytes per launch, mean tensor-pipe-active %) of the hidden-layer k_tc_gemm launches, parsed at
-    run time from the newest committed `profiles/ncu_tc_gemm_r*.csv` (one `ncu --set full` capture of this command)."""
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_tc_gemm_r*.csv")),
+def ncu_tc_summary(stem: str = "ncu_tc_gemm"):
+    """(csv path, mean DRAM bytes per launch, mean tensor-pipe-active %) of the launches of one tensor-core kernel, parsed at
+    run time from the newest committed `profiles/<stem>_r*.csv` (one `ncu --set full` capture of this step)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", stem + "_r*.csv")),
                    key=lambda f: int(re.search(r"_r(\d+)", os.path.basename(f)).group(1)))
     if not files:
         return None, None, None
@@ -395,36 +395,60 @@ def run_engine(args, rank: int, world: int, local_rank: int):
         # ---- roofline of the dominant kernel: per-launch device time from CUDA events (eager replay of the same list)
         br = per_launch_breakdown(eng)
         Mc = BATCH + 3 * BATCH * N_REPEAT
+        D0 = 17 + 6                     # obs + act columns of the first critic layer
+        gemm = 2 * 2 * Mc * 256 * 256   # one hidden layer of both critics over the critic batch: 2.08 GFLOP
         flop = {}
         for l in (1, 2):
             for kind in ("fwd", "dgrad", "wgrad"):
-                flop[f"C.critic.{kind}{l}"] = flop[f"C.critic.{kind}{l}.tc"] = 2 * 2 * Mc * 256 * 256
-        flop["C.critic.wgrad_big"] = 2 * 2 * 2 * Mc * 256 * 256
+                flop[f"C.critic.{kind}{l}"] = flop[f"C.critic.{kind}{l}.tc"] = gemm
+        flop["C.critic.wgrad_big"] = 2 * gemm
+        # fused passes: first layer + two hidden layers + scalar head of the online critics (+ the target critics' 256 rows)
+        fwd_flop = gemm * 2 + 2 * 2 * Mc * D0 * 256 + 2 * 2 * Mc * 256
+        fwd_flop += (gemm * 2 + 2 * 2 * Mc * D0 * 256 + 2 * 2 * Mc * 256) * BATCH // Mc
+        flop["C.critic+C.target.fwd_fused.tc"] = fwd_flop
+        flop["C.critic.fwd_fused.tc"] = gemm * 2 + 2 * 2 * Mc * D0 * 256 + 2 * 2 * Mc * 256
+        flop["C.critic.dgrad_fused.tc"] = gemm * 2
         big = [(lbl, us) for lbl, us in br if lbl in flop]
         on_tc = any(lbl.endswith(".tc") for lbl, _ in big)
         big_us = sum(us for _, us in big)
         big_flop = sum(flop[lbl] for lbl, _ in big)
         step_us = sum(us for _, us in br)
-        achieved = big_flop / (big_us * 1e-6) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        kname = (f"k_tc_gemm<{eng.tc_passes}> (tcgen05.mma kind::tf32, {eng.tc_passes} MMA pass(es) per product, TMEM "
-                 "accumulators, TMA operand ring; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)") if on_tc \
-            else "k_gemm_grouped<128,128,16,8,8> (fp32 FFMA; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)"
-        ncu_csv, ncu_traffic, ncu_pipe = ncu_tc_summary()
+        fused = [(lbl, us) for lbl, us in big if "fwd_fused" in lbl]
+        if fused:
+            # the dominant kernel of the step: the fused forward pass of the critics (one launch)
+            dom_lbl, dom_us = fused[0]
+            achieved = flop[dom_lbl] / (dom_us * 1e-6) / 1e12
+            kname = ("k_critic_fwd (tcgen05.mma kind::tf32, 3 MMA passes per product; first layer + two hidden layers + scalar "
+                     "head of both critics over 7936 rows and of both target critics over 256 rows in one launch: TMEM "
+                     "ping-pong accumulators, the epilogue writes the next layer's operand tiles, weights by TMA)")
+            ncu_csv, ncu_traffic, ncu_pipe = ncu_tc_summary("ncu_critic_fwd")
+            # X in, three activation tensors + decision bits + q out, weights (+ lo words) once per member
+            alg_bytes = Mc * 24 * 4 + 3 * 2 * Mc * 256 * 4 + 3 * 2 * Mc * 32 + 2 * Mc * 4 + 2 * 2 * 2 * (256 * 32 + 2 * 65536) * 4
+            n_dom, dom_total_us = 1, dom_us
+        else:
+            achieved = big_flop / (big_us * 1e-6) / 1e12
+            kname = (f"k_tc_gemm<{eng.tc_passes}> (tcgen05.mma kind::tf32, {eng.tc_passes} MMA pass(es) per product, TMEM "
+                     "accumulators, TMA operand ring; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)") if on_tc \
+                else "k_gemm_grouped<128,128,16,8,8> (fp32 FFMA; hidden-layer fwd/dgrad/wgrad of both critics over 7936 rows)"
+            ncu_csv, ncu_traffic, ncu_pipe = ncu_tc_summary()
+            alg_bytes = 2 * Mc * 256 * 4 * 2 + 2 * 256 * 256 * 4
+            n_dom, dom_total_us = len(big), big_us
         roof = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} bf16 dense (sustained)",
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the six launches, from the committed
-                # ncu --set full capture of this command (profiles/ncu_tc_gemm_r01.csv); the forward / dgrad launches stay
-                # in L2 (< 6 MB of DRAM traffic each), the split-K weight-gradient launches move ~46 MB each
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+                # step (parsed at run time; ncu flushes the caches before each pass, in the running step the operands are L2 hits)
                 "traffic": ncu_traffic if on_tc else None,
-                "traffic_source": (f"{ncu_csv}, parsed at run time (ncu --set full, B200, same command; ncu flushes the "
-                                   "caches before each pass, in the running step the operands are L2 hits)") if on_tc else None,
-                "algorithmic_bytes_per_launch": 2 * Mc * 256 * 4 * 2 + 2 * 256 * 256 * 4,
+                "traffic_source": (f"{ncu_csv}, parsed at run time (ncu --set full, B200, same step)") if on_tc else None,
+                "algorithmic_bytes_per_launch": alg_bytes,
                 # each product is three TF32 MMAs: what the tensor pipe really executes, against the TF32 (= bf16 / 2) peak
                 "tf32_mma_frac_of_tf32_peak": (3 if eng.tc_passes == 3 else 1) * achieved / (peak / 2),
                 "ncu_tensor_pipe_active_pct": ncu_pipe if on_tc else None,
-                "launches_per_step": len(big), "us_per_step": big_us, "share_of_step": big_us / step_us,
+                "launches_per_step": n_dom, "us_per_step": dom_total_us, "share_of_step": dom_total_us / step_us,
+                # all tensor-core launches of the critic update together (fused forward, fused dgrad chain, weight gradients)
+                "all_tensor_core_launches": {"launches": len(big), "us_per_step": big_us, "tflops": big_flop / (big_us * 1e-6) / 1e12,
+                                             "frac": big_flop / (big_us * 1e-6) / 1e12 / peak, "share_of_step": big_us / step_us},
                 "step_frac": FLOP_PER_STEP * (value / world) / 1e12 / peak,
                 "fp32_simt_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
                 "frac_of_fp32_simt_peak": achieved / (148 * 128 * 2 * 1.965e9 / 1e12)}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 25
+#define ORLK_ABI_VERSION 26
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -383,6 +383,16 @@ typedef struct OrlkAdamGroup {
 int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, int B, float* scalars, int auto_alpha,
                         int clamp01, float target_entropy, OrlkAdamGroup* groups, int alpha_group, float* alpha_mv,
                         float* dq, int64_t dq_es, float* glp, float* out_losses, void* stream);
+
+/* Policy-improvement step, twin critics with scalar heads, everything that needs no batch reduction in one launch:
+ *   q[c][m] = H[c][m] . Wh[c] + bh[c]  (H [2][B][K], member strides h_gs / w_gs / b_gs),
+ *   dq[c][m] = d/dq_c mean_b(alpha logp - min(q_0, q_1))  (as orlk_sac_actor_loss writes it for E = 2),  glp[m] = alpha / B,
+ *   dZ[c][m][k] = dq[c][m] * Wh[c][k] * (H[c][m][k] > 0)   (the heads' input gradient, as orlk_skinny_dgrad with H as mask).
+ * The loss value and the temperature step (orlk_sac_actor_loss on q) then run beside the backward pass.
+ * Replaces Critic.last forward + autograd through it in sac.py:111-120 / cql.py:93-100. */
+int orlk_twin_head_actor(const float* H, int64_t h_gs, const float* Wh, int64_t w_gs, const float* bh, int64_t b_gs,
+                         const float* scalars, int B, int K, float* q, int64_t q_gs, float* dq, int64_t dq_gs, float* glp,
+                         float* dZ, int64_t dz_gs, void* stream);
 
 /* CQL critic phase loss (cql.py:108-205) for both critics; also COMBO's (combo.py:133-208), whose TD rows are the
  * real+fake mix (B), whose `- w * mean Q` term runs over the first n_qmean (= real) rows only (combo.py:196-203) and

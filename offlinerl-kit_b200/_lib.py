@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 25
+ABI_VERSION = 26
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -142,6 +142,7 @@ _PROTOS = {
     "orlk_cql_critic_loss": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _I, _F, _P, _P, _I, _P,
                              _P, _L, _P, _P, _P],
     "orlk_cql_critic_loss_scratch_floats": [_I, _I],
+    "orlk_twin_head_actor": [_P, _L, _P, _L, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "orlk_segment_max": [_P, _L, _I, _I, _I, _P, _L, _P],
     "orlk_td_loss": [_P, _L, _I, _P, _L, _I, _P, _P, _I, _P, _P, _I, _F, _P, _L, _P, _P, _P, _P],
     "orlk_iql_v_loss": [_P, _L, _P, _I, _F, _P, _P, _P, _P],

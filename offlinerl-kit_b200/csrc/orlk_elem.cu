@@ -478,6 +478,51 @@ __global__ void k_sac_actor_loss(const float* __restrict__ q, int64_t q_es, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------ twin scalar heads, policy step
+// The critics' scalar heads, the gradient of the policy-improvement loss w.r.t. their outputs and that gradient pulled
+// back through the heads, in ONE launch (k_skinny_fwd + the dq / glp part of k_sac_actor_loss + k_skinny_dgrad):
+//   q_c[m] = H_c[m] . w_c + b_c;  dq_c[m] = d/dq_c mean_b(alpha logp - min(q_0, q_1)) = -1/B for the smaller one (ties: half each);
+//   glp[m] = alpha / B;  dZ_c[m][k] = dq_c[m] * w_c[k] * (H_c[m][k] > 0)
+// None of these needs a batch reduction; the loss VALUE and the temperature step do, and run beside the backward pass
+// (k_sac_actor_loss on q, off the critical path).  One 4-warp block per row (sac.py:111-120, cql.py:93-100).
+constexpr int TH_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * TH_WARPS)
+k_twin_head_actor(const float* __restrict__ H, int64_t h_gs, const float* __restrict__ Wh, int64_t w_gs, const float* __restrict__ bh,
+                  int64_t b_gs, const float* __restrict__ scalars, int B, int K, float* __restrict__ q, int64_t q_gs,
+                  float* __restrict__ dq, int64_t dq_gs, float* __restrict__ glp, float* __restrict__ dZ, int64_t dz_gs) {
+    orlk::pdl_enter();
+    __shared__ float part[2][TH_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int m = blockIdx.x;
+    const float* h0 = H + (int64_t)m * K;
+    const float* h1 = H + h_gs + (int64_t)m * K;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = threadIdx.x; k < K; k += 32 * TH_WARPS) {
+        a0 = fmaf(h0[k], __ldg(Wh + k), a0);
+        a1 = fmaf(h1[k], __ldg(Wh + w_gs + k), a1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) { part[0][w] = a0; part[1][w] = a1; }
+    __syncthreads();
+    float q0 = __ldg(bh), q1 = __ldg(bh + b_gs);
+#pragma unroll
+    for (int ww = 0; ww < TH_WARPS; ++ww) { q0 += part[0][ww]; q1 += part[1][ww]; }
+    const float invB = 1.f / (float)B;
+    const float d0 = q0 < q1 ? -invB : (q0 == q1 ? -0.5f * invB : 0.f);       // torch.min(a, b): ties split the gradient evenly
+    const float d1 = q1 < q0 ? -invB : (q0 == q1 ? -0.5f * invB : 0.f);
+    if (threadIdx.x == 0) {
+        q[m] = q0; q[q_gs + m] = q1;
+        dq[m] = d0; dq[dq_gs + m] = d1;
+        glp[m] = scalars[ORLK_SC_ALPHA] * invB;
+    }
+    for (int k = threadIdx.x; k < K; k += 32 * TH_WARPS) {
+        dZ[(int64_t)m * K + k] = h0[k] > 0.f ? d0 * __ldg(Wh + k) : 0.f;
+        dZ[dz_gs + (int64_t)m * K + k] = h1[k] > 0.f ? d1 * __ldg(Wh + w_gs + k) : 0.f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ CQL critic loss
 // Bootstrap value of row b.  tq_rep == 1: min over the two target critics at (s', a'), minus alpha * log pi(a'|s') unless
 // the backup is deterministic (cql.py:121-132).  tq_rep == N > 1 (max_q_backup, cql.py:109-120): each target critic is
@@ -830,6 +875,15 @@ int orlk_sac_actor_loss(const float* q, int64_t q_es, int E, const float* logp, 
     orlk::launch(k_sac_actor_loss, 1, 256, 0, (cudaStream_t)stream, q, q_es, E, logp, B, scalars, auto_alpha, clamp01, target_entropy,
                                                          groups, alpha_group, alpha_mv, dq, dq_es, glp, out_losses);
     return check_launch("k_sac_actor_loss");
+}
+
+int orlk_twin_head_actor(const float* H, int64_t h_gs, const float* Wh, int64_t w_gs, const float* bh, int64_t b_gs,
+                         const float* scalars, int B, int K, float* q, int64_t q_gs, float* dq, int64_t dq_gs, float* glp,
+                         float* dZ, int64_t dz_gs, void* stream) {
+    ORLK_REQUIRE(H && Wh && bh && scalars && q && dq && glp && dZ && B > 0 && K > 0, "twin_head_actor arguments");
+    orlk::launch(k_twin_head_actor, B, 32 * TH_WARPS, 0, (cudaStream_t)stream, H, h_gs, Wh, w_gs, bh, b_gs, scalars, B, K, q, q_gs, dq,
+                 dq_gs, glp, dZ, dz_gs);
+    return check_launch("k_twin_head_actor");
 }
 
 int orlk_cql_critic_loss_scratch_floats(int B, int R) {

@@ -615,7 +615,8 @@ def emit_head_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str) -> None:
     plan.add(f"{tag}.head_dgrad", lambda: L.call("orlk_skinny_dgrad", *args, rt.cur))
 
 
-def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1, dact=None) -> None:
+def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: int = 1, dact=None,
+                      from_layer: Optional[int] = None) -> None:
     """dZ[l-1] = (dZ[l] W_l) * relu'(H[l-1]) for l = nh-1 .. down_to.  ``dact = (dA, col0, ncols)`` appends
     dA[g] = dZ[0][g] . W0[:, col0:col0+ncols] (the gradient w.r.t. some input columns, emit_dact) to the pass."""
     ps, G, M = run.ps, run.G, run.M
@@ -648,7 +649,7 @@ def emit_hidden_dgrad(rt: Runtime, plan: Plan, run: MlpRun, tag: str, down_to: i
             WT=[0] + [ps.wt(l, 0) for l in range(1, nh)], WTlo=[0] + [ps._ptr(ps.lo_arena("WT"), ps.layers[l].w_off) for l in range(1, nh)],
             dZ=[run.dZ[l].data_ptr() for l in range(nh - 1)], gs=ps.block, dz_gs=M * N, M=M, N=N, G=G))
         return
-    for l in range(run.nh - 1, down_to - 1, -1):
+    for l in range(run.nh - 1 if from_layer is None else from_layer, down_to - 1, -1):
         lay = ps.layers[l]
         if run.tc_dgrad[l] and run.ens_tc:
             # dX[m][i] = sum_o dZ[m][o] W[i][o]: the 'io' weight is the K-major B operand as it is stored
@@ -728,8 +729,11 @@ def make_gradbuf(rt: Runtime, ps: ParamSet, runs: Sequence["MlpRun"]) -> GradBuf
 
 
 def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: GradBuf, groups_ptr: int, tag: str,
-                    polyak: bool) -> None:
-    """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update."""
+                    polyak: bool, only_layers: Optional[Sequence[int]] = None, do_wgrad: bool = True, do_adam: bool = True) -> None:
+    """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update.
+    ``only_layers``: just these layers (the caller schedules the others elsewhere, e.g. as soon as their dZ exists);
+    ``do_wgrad`` / ``do_adam``: only the gradient launches / only the update (which must not run before the layer's own
+    input-gradient launch has read the old weights)."""
     ps, G, M = run.ps, run.G, run.M
     plan.keep += [run, gb, [x.keep for x in X]]
     big, small, tiny = [], [], []
@@ -741,6 +745,8 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     launch_layers: List[List[int]] = []                       # the layers whose gradients each launch produces
     grouped_layers = {L.CFG_BIG: [], L.CFG_SMALL: [], L.CFG_TINY: []}
     for l in range(n_l):
+        if only_layers is not None and l not in only_layers:
+            continue
         cfg, s = layout[l]
         lay = ps.layers[l]
         same_x = all(x.ptr == X[0].ptr and x.ld == X[0].ld for x in X)
@@ -816,6 +822,14 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     def adam_for(layers):
         return rt.adam(adam_descs(ps, gb, splits, polyak, layers=layers, grad_src=grad_src, members=range(G)), groups_ptr)
 
+    if not (do_wgrad and do_adam):
+        assert only_layers is not None
+        if do_wgrad:
+            for label, op in launches:
+                plan.add(label, op)
+        if do_adam:
+            plan.add(f"{tag}.adam", adam_for(sorted(set(only_layers))))
+        return
     n_tc = sum(1 for label, _ in launches if label.endswith(".tc"))
     if n_tc >= 2 and WGRAD_CHAIN:
         # Experiment (ORLK_WGRAD_CHAIN=1, off): the optimiser launches of the first layers start late because a ready grid that
@@ -854,4 +868,4 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     else:
         for label, op in launches:
             plan.add(label, op)
-        plan.add(f"{tag}.adam", adam_for(range(n_l)))
+        plan.add(f"{tag}.adam", adam_for(range(n_l) if only_layers is None else sorted(set(only_layers))))

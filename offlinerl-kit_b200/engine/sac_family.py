@@ -239,13 +239,37 @@ class TwinCriticLearner(Learner):
                 self._emit_head_sample(plan, "A.actor.head_sample", ar, [(0, B, 1, self.eps_actor, Xa, self.logp_a, obs)])
             else:
                 self._emit_sample(plan, "A.sample", ar.out[0], 0, 1, self.eps_actor, B, Xa, self.logp_a, obs)
-        emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
         q, dq = cr.out, cr.dOut      # [2, B, 1]
-        args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
-                int(clamp01), self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(),
-                dq.data_ptr(), B, self.glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
-        plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
-        emit_head_dgrad(rt, plan, cr, "A.critic")
+        chead = cr.ps.layers[cr.nh]
+        forked = False
+        fuse_th = (cr.G == 2 and cr.has_head and cr.NS == 1 and chead.layout == "oi" and not chainable(cr, with_head=True)
+                   and not cr.fused_fwd and not cr.fuse_head_bwd and cr.dZT[cr.nh - 1] is None and B < TC_MIN_ROWS
+                   and os.environ.get("ORLK_FUSE_TWIN_HEAD", "1") != "0")
+        if fuse_th:
+            # heads + d(loss)/dq + the heads' input gradient need no batch reduction: one launch on the critical path; the
+            # loss value and the temperature step (which do) run beside the backward pass on q
+            emit_forward(rt, plan, cr, [Xa, Xa], "A.critic", skip_head=True)
+            K = chead.in_dim
+            hargs = (cr.H[cr.nh - 1].data_ptr(), B * K, cr.ps.w(cr.nh, 0), chead.w_gs, cr.ps.b(cr.nh, 0), chead.b_gs,
+                     self.scalars.data_ptr(), B, K, q.data_ptr(), B, dq.data_ptr(), B, self.glp.data_ptr(),
+                     cr.dZ[cr.nh - 1].data_ptr(), B * K)
+            plan.add("A.critic.head_fwd_bwd", lambda: L.call("orlk_twin_head_actor", *hargs, rt.cur))
+            self._dq_scratch, self._glp_scratch = rt.zeros(2, B), rt.zeros(B)
+            args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
+                    int(clamp01), self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(),
+                    self._dq_scratch.data_ptr(), B, self._glp_scratch.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+            plan.fork()
+            plan.branch(1)
+            plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
+            plan.branch(0)
+            forked = True
+        else:
+            emit_forward(rt, plan, cr, [Xa, Xa], "A.critic")
+            args = (q.data_ptr(), B, 2, self.logp_a.data_ptr(), B, self.scalars.data_ptr(), int(self.auto_alpha),
+                    int(clamp01), self.target_entropy, self.groups_ptr, max(self.g_alpha, 0), self.alpha_mv.data_ptr(),
+                    dq.data_ptr(), B, self.glp.data_ptr(), self.loss_dev.data_ptr() + 4 * LS_ACTOR)
+            plan.add("A.loss", lambda: L.call("orlk_sac_actor_loss", *args, rt.cur))
+            emit_head_dgrad(rt, plan, cr, "A.critic")
         head = ar.out[0]
         c0, ah = cr.ps.layers[0], ar.ps.layers[ar.nh]
         fuse_entry = (not getattr(cr, "pending_head_dgrad", False) and c0.layout == "oi" and ah.layout == "oi" and ar.G == 1
@@ -270,8 +294,39 @@ class TwinCriticLearner(Learner):
                      self.glp.data_ptr(), B, A, ar.dOut.data_ptr(), 2 * A)
             plan.add("A.head_bwd", lambda: L.call("orlk_tanh_gauss_bwd", *bargs, rt.cur))
             emit_head_dgrad(rt, plan, ar, "A.actor")
-        emit_hidden_dgrad(rt, plan, ar, "A.actor")
-        emit_wgrad_adam(rt, plan, ar, [obs], self.gb_actor, self.groups_ptr, "A.actor", polyak=False)
+        nh = ar.nh
+        split = (fuse_entry and nh >= 2 and not any(ar.tc_wgrad) and not chainable(ar, with_head=True)
+                 and os.environ.get("ORLK_ACTOR_WGRAD_SPLIT", "1") != "0")
+        if split:
+            # weight gradients layer by layer, each as soon as its dZ exists (beside the remaining input-gradient launches);
+            # a layer's Adam step only after its OWN input-gradient launch has read the old weights; the first layer - which
+            # the next forward pass needs first - last, on the main stream
+            wa = lambda tag, layers, **kw: emit_wgrad_adam(rt, plan, ar, [obs], self.gb_actor, self.groups_ptr, tag, polyak=False,
+                                                           only_layers=layers, **kw)
+            plan.fork()
+            plan.branch(2)
+            wa("A.actor.top", [nh - 1, nh], do_adam=False)
+            plan.branch(0)
+            pending = ("A.actor.top", [nh - 1, nh], 2)         # (tag, layers, side stream) whose Adam waits for the next dgrad
+            for l in range(nh - 1, 0, -1):
+                emit_hidden_dgrad(rt, plan, ar, "A.actor", down_to=l, from_layer=l)        # reads W[l], writes dZ[l - 1]
+                plan.fork()
+                plan.branch(pending[2])
+                wa(pending[0], pending[1], do_wgrad=False)
+                if l - 1 >= 1:
+                    side = 3 if pending[2] == 2 else 2
+                    plan.branch(side)
+                    wa(f"A.actor.l{l - 1}", [l - 1], do_adam=False)
+                    pending = (f"A.actor.l{l - 1}", [l - 1], side)
+                plan.branch(0)
+            wa("A.actor.l0", [0])
+            plan.join()
+            forked = False
+        else:
+            emit_hidden_dgrad(rt, plan, ar, "A.actor")
+            emit_wgrad_adam(rt, plan, ar, [obs], self.gb_actor, self.groups_ptr, "A.actor", polyak=False)
+        if forked:
+            plan.join()
 
     def _alloc_actor_phase(self) -> None:
         rt, B, A = self.rt, self.B, self.A
