@@ -396,6 +396,22 @@ class Plan:
         self.ops.append(("join", op))
         self._branch = 0
 
+    # ---- point-to-point dependencies between branches (what fork / join cannot express)
+    def record_event(self) -> C.c_void_p:
+        """An event recorded at the current position of the current branch; ``wait_event`` makes another branch wait for it."""
+        ev = C.c_void_p()
+        L.call("orlk_event_create_notiming", C.byref(ev))
+        self.keep.append(ev)
+        b = self._branch
+        op = lambda: L.call("orlk_event_record", ev, self.rt.cur)
+        self.ops.append(("fork", (lambda: self._on_side(b, op)) if b else op))
+        return ev
+
+    def wait_event(self, ev: C.c_void_p) -> None:
+        b = self._branch
+        op = lambda: L.call("orlk_stream_wait_event", self.rt.cur, ev)
+        self.ops.append(("join", (lambda: self._on_side(b, op)) if b else op))
+
     # ---- a detached launch: runs on its own stream after everything issued so far, joined by join_detached()
     @property
     def has_detached(self) -> bool:

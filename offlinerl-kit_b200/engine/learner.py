@@ -729,11 +729,13 @@ def make_gradbuf(rt: Runtime, ps: ParamSet, runs: Sequence["MlpRun"]) -> GradBuf
 
 
 def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: GradBuf, groups_ptr: int, tag: str,
-                    polyak: bool, only_layers: Optional[Sequence[int]] = None, do_wgrad: bool = True, do_adam: bool = True) -> None:
+                    polyak: bool, only_layers: Optional[Sequence[int]] = None, do_wgrad: bool = True, do_adam: bool = True,
+                    tail_ops: Optional[Dict[int, Callable[[], None]]] = None) -> None:
     """All weight / bias gradients of the pass (split-K partials) and the fused Adam(+polyak) update.
     ``only_layers``: just these layers (the caller schedules the others elsewhere, e.g. as soon as their dZ exists);
     ``do_wgrad`` / ``do_adam``: only the gradient launches / only the update (which must not run before the layer's own
-    input-gradient launch has read the old weights)."""
+    input-gradient launch has read the old weights).  ``tail_ops[l]()`` emits further launches on the branch of layer l's
+    gradient launch, behind its update."""
     ps, G, M = run.ps, run.G, run.M
     plan.keep += [run, gb, [x.keep for x in X]]
     big, small, tiny = [], [], []
@@ -859,11 +861,21 @@ def emit_wgrad_adam(rt: Runtime, plan: Plan, run: MlpRun, X: Sequence[Mat], gb: 
     elif len(launches) > 1:
         # each branch: one weight-gradient launch and right behind it the Adam(+polyak) update of exactly those layers, so
         # the bandwidth-bound optimiser work of one layer overlaps the tensor-core work of the others
+        # (a scalar head folded into the operand generator: the last hidden layer's weight gradient READS the head weights,
+        # so the head's own update waits for that launch - an event between the two branches, no cost: the GEMM runs first)
         plan.fork()
+        ev_gen = None
         for i, (label, op) in enumerate(launches):
             plan.branch(i % (Plan.N_SIDE + 1))
             plan.add(label, op)
+            if run.fuse_head_bwd and run.nh - 1 in launch_layers[i]:
+                ev_gen = plan.record_event()
+            if run.fuse_head_bwd and launch_layers[i] == [run.nh] and ev_gen is not None:
+                plan.wait_event(ev_gen)
             plan.add(f"{tag}.adam{i}", adam_for(sorted(set(launch_layers[i]))))
+            for l in launch_layers[i]:
+                if tail_ops and l in tail_ops:
+                    tail_ops[l]()
         plan.join()
     else:
         for label, op in launches:
