@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 26
+#define ORLK_ABI_VERSION 27
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -48,7 +48,13 @@ int orlk_device_info(int device, int* out4);
 int orlk_graph_begin(void* stream);
 int orlk_graph_end(void* stream, void** graph_exec_out);
 int orlk_graph_launch(void* graph_exec, void* stream);
+int orlk_capture_status(void* stream); /* diagnostic (ORLK_GRAPH_DEBUG): 0 not capturing, 1 capturing, 2 invalidated; returned as the value */
 int orlk_graph_launch_sync(void* graph_exec, void* stream); /* launch, then wait for the stream */
+/* launch, then wait only for `ev`, which a node inside the graph records (orlk_event_record_external under capture): the
+ * step's loss block has reached pinned host memory - policy.learn's Dict[str, float] contract (base_policy.py:25-26) - while
+ * the rest of the step (the critics' backward pass) is still running and the caller already draws the next batch */
+int orlk_graph_launch_wait_event(void* graph_exec, void* stream, void* ev);
+int orlk_event_record_external(void* ev, void* stream); /* under capture: an external event-record node; else cudaEventRecord */
 int orlk_graph_destroy(void* graph_exec);
 int orlk_stream_sync(void* stream);
 /* side streams + ordering events: independent launches of a step (e.g. the weight gradients of different layers)

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 26
+ABI_VERSION = 27
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -106,7 +106,8 @@ _PROTOS = {
     "orlk_sizeof_gemm_desc": [], "orlk_sizeof_adam_desc": [], "orlk_sizeof_adam_group": [], "orlk_sizeof_concat_seg": [],
     "orlk_device_info": [_I, C.POINTER(C.c_int)],
     "orlk_graph_begin": [_P], "orlk_graph_end": [_P, C.POINTER(C.c_void_p)], "orlk_graph_launch": [_P, _P],
-    "orlk_graph_destroy": [_P], "orlk_stream_sync": [_P], "orlk_graph_launch_sync": [_P, _P],
+    "orlk_graph_destroy": [_P], "orlk_stream_sync": [_P], "orlk_graph_launch_sync": [_P, _P], "orlk_capture_status": [_P],
+    "orlk_graph_launch_wait_event": [_P, _P, _P], "orlk_event_record_external": [_P, _P],
     "orlk_stream_create": [C.POINTER(C.c_void_p)], "orlk_stream_destroy": [_P], "orlk_stream_wait_event": [_P, _P],
     "orlk_event_create_notiming": [C.POINTER(C.c_void_p)],
     "orlk_memcpy_h2d_async": [_P, _P, C.c_size_t, _P], "orlk_memcpy_d2h_async": [_P, _P, C.c_size_t, _P],

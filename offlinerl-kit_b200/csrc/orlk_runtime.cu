@@ -67,6 +67,12 @@ int orlk_graph_begin(void* stream) {
     return check(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
 }
 
+int orlk_capture_status(void* stream) {     /* 0 = not capturing, 1 = capturing, 2 = capture invalidated, < 0 = query failed */
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return st == cudaStreamCaptureStatusActive ? 1 : (st == cudaStreamCaptureStatusInvalidated ? 2 : 0);
+}
+
 int orlk_graph_end(void* stream, void** graph_exec_out) {
     ORLK_REQUIRE(graph_exec_out != nullptr, "graph_exec_out is NULL");
     cudaGraph_t g = nullptr;
@@ -102,6 +108,21 @@ int orlk_graph_launch_sync(void* graph_exec, void* stream) {
     int rc = check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
     if (rc) return rc;
     return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+
+int orlk_graph_launch_wait_event(void* graph_exec, void* stream, void* ev) {
+    int rc = check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
+    if (rc) return rc;
+    return check(cudaEventSynchronize((cudaEvent_t)ev), "cudaEventSynchronize");
+}
+
+int orlk_event_record_external(void* ev, void* stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    int rc = check(cudaStreamIsCapturing((cudaStream_t)stream, &st), "cudaStreamIsCapturing");
+    if (rc) return rc;
+    if (st == cudaStreamCaptureStatusActive)        // an event-record NODE: every launch of the graph records the event
+        return check(cudaEventRecordWithFlags((cudaEvent_t)ev, (cudaStream_t)stream, cudaEventRecordExternal), "cudaEventRecordWithFlags");
+    return check(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream), "cudaEventRecord");
 }
 
 int orlk_graph_destroy(void* graph_exec) {

@@ -1,5 +1,7 @@
 """Core host plumbing: device views, GEMM/Adam descriptor tables, launch plans (CUDA graph capture)."""
 import ctypes as C
+import gc
+import os
 import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
@@ -455,15 +457,33 @@ class Plan:
         g = C.c_void_p()
         rt = self.rt
         torch.cuda.synchronize(rt.device)
+        # No CUDA call other than the captured launches may come from this thread while the capture is open: a finaliser that
+        # the cyclic collector happens to run in the middle (an old Plan destroying its graph) invalidates the capture
+        # silently.  So: pending destructions first, the collector off for the duration, late finalisers deferred.
+        _flush_deferred_graphs()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        _CAPTURING[0] = True
         rt.cur = C.c_void_p(rt.capture_stream.cuda_stream)
         try:
             L.call("orlk_graph_begin", rt.cur)
             try:
-                self.run_eager()
+                if os.environ.get("ORLK_GRAPH_DEBUG", "0") == "2":      # which launch breaks a capture
+                    cap = C.c_void_p(rt.cur.value)
+                    for lbl, op in self.ops:
+                        op()
+                        st = L.load().orlk_capture_status(cap)
+                        if st != 1:
+                            raise L.OrlkError(f"capture of plan {self.name!r} left state {st} behind op {lbl!r}")
+                else:
+                    self.run_eager()
             finally:
                 L.call("orlk_graph_end", rt.cur, C.byref(g))
         finally:
             rt.cur = rt.exec_ptr
+            _CAPTURING[0] = False
+            if gc_was_on:
+                gc.enable()
         self.graph = g
 
     def launch(self) -> None:
@@ -474,7 +494,22 @@ class Plan:
     def __del__(self):
         try:
             if self.graph is not None:
-                L.load().orlk_graph_destroy(self.graph)
+                if _CAPTURING[0]:
+                    _DEFERRED_GRAPHS.append(self.graph)
+                else:
+                    L.load().orlk_graph_destroy(self.graph)
+        except Exception:
+            pass
+
+
+_CAPTURING = [False]
+_DEFERRED_GRAPHS: List[C.c_void_p] = []
+
+
+def _flush_deferred_graphs() -> None:
+    while _DEFERRED_GRAPHS:
+        try:
+            L.load().orlk_graph_destroy(_DEFERRED_GRAPHS.pop())
         except Exception:
             pass
 

@@ -77,6 +77,11 @@ class Learner:
             raise L.OrlkError(f"unknown precision {self.precision!r}; choose one of {sorted(PRECISIONS)}")
         self.param_sets: List[ParamSet] = []
         self._launch_sync = L.load().orlk_graph_launch_sync
+        self._launch_wait = L.load().orlk_graph_launch_wait_event
+        # recorded by a node of the step graph right behind the loss block's device-to-host copy: ``learn`` returns on it
+        self._loss_ev = C.c_void_p()
+        L.call("orlk_event_create_notiming", C.byref(self._loss_ev))
+        self.early_return = os.environ.get("ORLK_EARLY_RETURN", "1") != "0"
 
     # ------------------------------------------------------------------ Adam groups
     def add_group(self, optim: Optional[torch.optim.Optimizer], tau: float = 0.0, **hyper) -> int:
@@ -186,7 +191,13 @@ class Learner:
         if self.use_graph:
             if plan.graph is None:
                 plan.capture()
-            rc = self._launch_sync(plan.graph, self.rt.cur)      # launch + stream sync in one host call
+            if self.early_return and getattr(plan, "loss_event", False):
+                # launch + wait for the loss block only (one host call): the losses are final long before the step is, and
+                # everything the caller can do next - draw a batch, launch the next step, read parameters through torch -
+                # is ordered behind this graph on the same stream
+                rc = self._launch_wait(plan.graph, self.rt.cur, self._loss_ev)
+            else:
+                rc = self._launch_sync(plan.graph, self.rt.cur)      # launch + stream sync in one host call
             if rc:
                 L.check(rc, "orlk_graph_launch_sync")
         else:
@@ -206,6 +217,7 @@ class Learner:
             p2.ops = head + list(plan.ops)
             p2.flat_ops = head + list(plan.flat_ops)
             p2.keep = list(plan.keep) + [tok, plan]
+            p2.loss_event = getattr(plan, "loss_event", False)
             cache[k] = p2
         return p2
 
@@ -222,6 +234,7 @@ class Learner:
             p2.ops = head + list(plan.ops)
             p2.flat_ops = head + list(plan.flat_ops)
             p2.keep = list(plan.keep) + [t for t, _ in srcs] + [plan]
+            p2.loss_event = getattr(plan, "loss_event", False)
             cache[k] = p2
         return p2
 
@@ -301,7 +314,12 @@ class Learner:
     def emit_loss_readback(self, plan: Plan) -> None:
         """Copy the loss block to pinned host memory on a detached branch (call once no later launch writes it)."""
         ld, lh = C.c_void_p(self.loss_dev.data_ptr()), C.c_void_p(self.loss_host.data_ptr())
-        plan.detach("losses_d2h", lambda: L.call("orlk_memcpy_d2h_async", lh, ld, 4 * N_LOSS, self.rt.cur))
+
+        def op():
+            L.call("orlk_memcpy_d2h_async", lh, ld, 4 * N_LOSS, self.rt.cur)
+            L.call("orlk_event_record_external", self._loss_ev, self.rt.cur)
+        plan.detach("losses_d2h", op)
+        plan.loss_event = True
 
     def finish_ops(self, plan: Plan, group_mask: int) -> None:
         gp, cp = C.c_void_p(self.groups_ptr), C.c_void_p(self.philox_counter.data_ptr())
