@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 27
+#define ORLK_ABI_VERSION 28
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -220,6 +220,10 @@ int orlk_sizeof_tc_gemm(void);
  * modules/critic_module.py:25-33 / nets/mlp.py:22-28 on CQL's critic batch and target rows
  * (policy/model_free/cql.py:108-160).  The structs are read on the HOST. */
 #define ORLK_FUSED_MAX_LAYERS 4
+/* CTA pairs (clusters of two; needs N % 64 == 0): M = 256 MMAs over two 128-row strips, each SM loads half of every weight
+ * slab.  Halves the weight bytes per SM (the L2 -> SM path of a TPC bounds the single-CTA kernel when both SMs of a TPC
+ * hold a strip), costs ~2 us of pair synchronisation per pass: pays from a few dozen strips on. */
+#define ORLK_FUSED_PAIRS 1
 typedef struct OrlkFusedFwd {
     const float* X; int64_t ldx;
     const float* W0pad; const float* W0pad_lo;    /* [G][N][32] */
@@ -232,7 +236,8 @@ typedef struct OrlkFusedFwd {
     float* out; int64_t out_gs;                   /* [G][M] */
     uint32_t* relu_bits;                          /* optional [n_hidden][G][8][M]: bit j of word [c][m] = (H_l[g][m][32c+j] > 0), for
                                                      orlk_critic_bwd_fused */
-    int32_t M, N, K0, G, n_hidden, pad_;
+    int32_t M, N, K0, G, n_hidden;
+    int32_t flags;                                /* ORLK_FUSED_PAIRS (of jobs[0]): CTA pairs, tcgen05.mma.cta_group::2 */
 } OrlkFusedFwd;
 int orlk_fused_init(void); /* once per process, outside stream capture */
 int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs_host, int n_jobs, void* stream);

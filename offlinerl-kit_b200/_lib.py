@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 27
+ABI_VERSION = 28
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -82,7 +82,10 @@ class FusedFwd(C.Structure):
                 ("gs", C.c_int64), ("h_gs", C.c_int64),
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("out", C.c_void_p), ("out_gs", C.c_int64), ("relu_bits", C.c_void_p),
                 ("M", C.c_int32), ("N", C.c_int32), ("K0", C.c_int32), ("G", C.c_int32), ("n_hidden", C.c_int32),
-                ("pad_", C.c_int32)]
+                ("flags", C.c_int32)]
+
+
+FUSED_PAIRS = 1
 
 
 class FusedBwd(C.Structure):

@@ -32,7 +32,7 @@ constexpr int FIXED = 8192;
 constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 
-enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 3, BAR_BFULL = 5, BAR_BEMPTY = 7, BAR_ACC = 9, BAR_COUNT = 11 };
+enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 3, BAR_ACC = 5, BAR_BFULL = 7, BAR_BEMPTY = 11, BAR_COUNT = 15 };
 
 struct FwdMaps {
     CUtensorMap x;                // X [M][K0]: box 32 (k, zero filled past K0) x 128 rows
@@ -72,8 +72,52 @@ __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__f
 // Up to two independent passes ("jobs") share one launch: CTAs [0, ctas0) run job 0 (the online critics on the 7936-row
 // batch), the rest job 1 (the target critics on the next-state rows, no activations stored) - side by side instead of
 // one pass starving the other of SMs.
+//
+// PAIR = true: CTA pairs (thread-block clusters of two, tcgen05.mma.cta_group::2, M = 256 over two strips).  Each CTA keeps
+// its own 128 rows of A and its own accumulators, but only HALF of every weight slab (N/2 rows: 32 KB instead of 64 KB
+// per slab and SM, a four-stage ring in the same shared memory); the leader CTA issues the MMAs for both, its barriers
+// collect the A tiles of both CTAs (remote arrivals) and the bytes of both CTAs' TMA loads, and its commits are
+// multicast to the stage / accumulator barriers of both.  What it buys: the L2 -> SM path of a TPC, which bounds the
+// second SM of a pair in the single-CTA kernel, carries half the bytes.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA's part of a pair's operand: the bytes are counted on the LEADER's barrier (a shared::cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {        // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdMaps maps1,
+k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdMaps maps1,
              const __grid_constant__ FwdParams p0, const __grid_constant__ FwdParams p1, const int ctas0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // SWIZZLE_128B tiles: 1024-byte aligned
@@ -86,8 +130,10 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
     float* qpart_s = headw_s + NMAX;                              // [BM]
     auto a_hi = [&](int s) { return base + s * A_STAGE; };
     auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };
-    auto b_hi = [&](int s) { return b_base + s * B_STAGE; };
-    auto b_lo = [&](int s) { return b_base + s * B_STAGE + B_TILE; };
+    constexpr int NSB = PAIR ? 4 : 2;                      // weight ring stages
+    constexpr int BST = PAIR ? B_STAGE / 2 : B_STAGE;      // bytes per stage: [hi | lo] of this CTA's rows of the slab
+    auto b_hi = [&](int s) { return b_base + s * BST; };
+    auto b_lo = [&](int s) { return b_base + s * BST + BST / 2; };
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -100,6 +146,8 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
     const int tile_m = cta - g * p.tiles_m;
     const int N = p.N, L = p.L;
     const int KS = N / BK;                      // k-slabs of a hidden layer = 32-column chunks of an accumulator
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int b_rows = PAIR ? N / 2 : N;        // weight rows this CTA keeps of every slab
     const bool store_h = p.store_h != 0 && p.no_store == 0;
 
     // ---------------------------------------------------------------- prologue (touches no global data)
@@ -118,23 +166,32 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
     if (warp == 1 && lane == 0) {
         mbar_init(bar(BAR_X), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(BAR_AFULL + s), 4);       // one arrival per epilogue warp of the stage's group
+            mbar_init(bar(BAR_AFULL + s), PAIR ? 8 : 4);    // one arrival per epilogue warp of the stage's group (of both CTAs)
             mbar_init(bar(BAR_AEMPTY + s), 1);
+            mbar_init(bar(BAR_ACC + s), 1);
+        }
+        for (int s = 0; s < NSB; ++s) {
             mbar_init(bar(BAR_BFULL + s), 1);
             mbar_init(bar(BAR_BEMPTY + s), 1);
-            mbar_init(bar(BAR_ACC + s), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     orlk::pdl_wait();                           // X and the weights come from earlier kernels of the step
     if (threadIdx.x == 0) { FZ_STAMP(1); FZ_GSTAMP(5); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();               // the pair's barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -143,28 +200,33 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
             // ------------------------------------------------------------ TMA producer
             mbar_expect_tx(bar(BAR_X), A_TILE);
             tma_load_3d(smem_u32(a_hi(0)), &maps.x, bar(BAR_X), 0, tile_m * BM, 0);
-            const uint32_t tx = 2u * (uint32_t)N * BK * 4;
-            mbar_expect_tx(bar(BAR_BFULL + 0), tx);             // fill 0: the padded first-layer weights
-            tma_load_3d(smem_u32(b_hi(0)), &maps.w0, bar(BAR_BFULL + 0), 0, 0, g);
-            tma_load_3d(smem_u32(b_lo(0)), &maps.w0lo, bar(BAR_BFULL + 0), 0, 0, g);
-            int bi = 1;
-            for (int l = 1; l < L; ++l) {
-                for (int j = 0; j < KS; ++j, ++bi) {
-                    const int s = bi & 1;
-                    mbar_wait(bar(BAR_BEMPTY + s), ((bi >> 1) & 1) ^ 1);
-                    if (bi < 32) FZ_STAMP(80 + bi);
+            const uint32_t tx = 2u * (uint32_t)N * BK * 4;      // a whole slab: hi + lo (of both CTAs' halves)
+            const int n_fill = 1 + (L - 1) * KS;                // fill 0: the padded first-layer weights
+            for (int bi = 0; bi < n_fill; ++bi) {
+                const int s = bi % NSB, nf = bi / NSB;
+                const int l = bi == 0 ? 0 : 1 + (bi - 1) / KS, j = bi == 0 ? 0 : (bi - 1) % KS;
+                const CUtensorMap* mh = l == 0 ? &maps.w0 : &maps.w[l - 1];
+                const CUtensorMap* ml = l == 0 ? &maps.w0lo : &maps.wlo[l - 1];
+                mbar_wait(bar(BAR_BEMPTY + s), (nf & 1) ^ 1);
+                if (bi < 32) FZ_STAMP(80 + bi);
+                if (PAIR) {
+                    const uint32_t lb = map_to_rank(bar(BAR_BFULL + s), 0);
+                    if (rank == 0) mbar_expect_tx(bar(BAR_BFULL + s), tx);
+                    tma_load_3d_pair(smem_u32(b_hi(s)), mh, lb, j * BK, (int)rank * b_rows, g);
+                    tma_load_3d_pair(smem_u32(b_lo(s)), ml, lb, j * BK, (int)rank * b_rows, g);
+                } else {
                     mbar_expect_tx(bar(BAR_BFULL + s), tx);
-                    tma_load_3d(smem_u32(b_hi(s)), &maps.w[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
-                    tma_load_3d(smem_u32(b_lo(s)), &maps.wlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                    tma_load_3d(smem_u32(b_hi(s)), mh, bar(BAR_BFULL + s), j * BK, 0, g);
+                    tma_load_3d(smem_u32(b_lo(s)), ml, bar(BAR_BFULL + s), j * BK, 0, g);
                 }
             }
         }
         __syncwarp();
         orlk::pdl_trigger();
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ------------------------------------------------------------ MMA issuer
-            const uint32_t idesc = instr_desc_tf32(BM, N);
+        if ((!PAIR || rank == 0) && elect_one()) {
+            // ------------------------------------------------------------ MMA issuer (the leader CTA's, for a pair)
+            const uint32_t idesc = instr_desc_tf32(PAIR ? 2 * BM : BM, N);
             int fa0 = 0, fa1 = 0, bi = 0;       // fills consumed so far of A stage 0 / 1, B fills consumed
             for (int l = 0; l < L; ++l) {
                 const uint32_t acc = tmem_base + (uint32_t)(NMAX * (l & 1));
@@ -175,8 +237,8 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
                     mbar_wait(bar(BAR_AFULL + sa), fa & 1);
                     if (sa) ++fa1; else ++fa0;
                     if (bi < 32) FZ_STAMP(16 + bi);
-                    const int sb = bi & 1;
-                    mbar_wait(bar(BAR_BFULL + sb), (bi >> 1) & 1);
+                    const int sb = bi % NSB;
+                    mbar_wait(bar(BAR_BFULL + sb), (bi / NSB) & 1);
                     if (bi < 32) FZ_STAMP(48 + bi);
                     tc_fence_after();
                     const uint64_t ad = smem_desc_sw128(smem_u32(a_hi(sa))), adl = smem_desc_sw128(smem_u32(a_lo(sa)));
@@ -184,14 +246,26 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {          // UMMA_K = 8 for tf32: 32 bytes along a K-major row
                         const uint64_t ko = (uint64_t)(2 * k);
-                        umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
-                        umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                        if (PAIR) {
+                            umma_tf32_pair(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_pair(acc, adl + ko, bd + ko, idesc, 1u);
+                            umma_tf32_pair(acc, ad + ko, bdl + ko, idesc, 1u);
+                        } else {
+                            umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
+                            umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                        }
                     }
-                    umma_commit(bar(BAR_AEMPTY + sa));          // both stages are free once these MMAs have completed
-                    umma_commit(bar(BAR_BEMPTY + sb));
+                    if (PAIR) {                                 // both stages are free (in both CTAs) once these MMAs have completed
+                        umma_commit_pair(bar(BAR_AEMPTY + sa));
+                        umma_commit_pair(bar(BAR_BEMPTY + sb));
+                    } else {
+                        umma_commit(bar(BAR_AEMPTY + sa));
+                        umma_commit(bar(BAR_BEMPTY + sb));
+                    }
                 }
-                umma_commit(bar(BAR_ACC + (l & 1)));
+                if (PAIR) umma_commit_pair(bar(BAR_ACC + (l & 1)));
+                else umma_commit(bar(BAR_ACC + (l & 1)));
             }
         }
         __syncwarp();
@@ -218,7 +292,10 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
             for (int i = 0; i < 8; ++i) xl[i * 32 + lane] = make_float4(lo_of(v[i].x), lo_of(v[i].y), lo_of(v[i].z), lo_of(v[i].w));
             fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_AFULL + 0));
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + 0), 0));
+                else mbar_arrive(bar(BAR_AFULL + 0));
+            }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");     // bias_s / headw_s complete
         if (t == 0) FZ_STAMP(2);
@@ -295,7 +372,8 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(bar(BAR_AFULL + grp));
+                    if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + grp), 0));
+                    else mbar_arrive(bar(BAR_AFULL + grp));
                     if (store_h) {
                         tma_store_4d(&maps.h[l], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -313,8 +391,10 @@ k_critic_fwd(const __grid_constant__ FwdMaps maps0, const __grid_constant__ FwdM
     if (threadIdx.x == 64) { FZ_STAMP(3); FZ_GSTAMP(6); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();               // neither CTA leaves (or frees tensor memory) while the other may still use it
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -584,7 +664,7 @@ __global__ void k_fused_prep(const float* __restrict__ src, float* __restrict__ 
 
 constexpr size_t FWD_SMEM = 1024 + RING + FIXED;
 
-int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
+int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p, bool pair) {
     ORLK_REQUIRE(q->M > 0 && q->G > 0, "sizes");
     ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
     ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
@@ -597,9 +677,10 @@ int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
     memset(p, 0, sizeof(*p));
     int rc = make_map(&maps->x, q->X, q->ldx, 0, q->M, q->K0, 1, BM);
     if (rc) return rc;
-    rc = make_map(&maps->w0, q->W0pad, BK, (int64_t)q->N * BK, q->N, BK, q->G, q->N);
+    const int wbox = pair ? q->N / 2 : q->N;        // weight rows per TMA box: a CTA of a pair loads half of every slab
+    rc = make_map(&maps->w0, q->W0pad, BK, (int64_t)q->N * BK, q->N, BK, q->G, wbox);
     if (rc) return rc;
-    rc = make_map(&maps->w0lo, q->W0pad_lo, BK, (int64_t)q->N * BK, q->N, BK, q->G, q->N);
+    rc = make_map(&maps->w0lo, q->W0pad_lo, BK, (int64_t)q->N * BK, q->N, BK, q->G, wbox);
     if (rc) return rc;
     const bool store = q->H[0] != nullptr;
     for (int l = 0; l < q->n_hidden; ++l) {
@@ -608,9 +689,9 @@ int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
         if (l >= 1) {
             ORLK_REQUIRE(q->W[l] != nullptr && q->Wlo[l] != nullptr && aligned16(q->W[l]) && aligned16(q->Wlo[l]),
                          "hidden weights (and lo copies) must be 16-byte aligned");
-            rc = make_map(&maps->w[l - 1], q->W[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            rc = make_map(&maps->w[l - 1], q->W[l], q->N, q->gs, q->N, q->N, q->G, wbox);
             if (rc) return rc;
-            rc = make_map(&maps->wlo[l - 1], q->Wlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+            rc = make_map(&maps->wlo[l - 1], q->Wlo[l], q->N, q->gs, q->N, q->N, q->G, wbox);
             if (rc) return rc;
         }
         if (store) {
@@ -626,6 +707,7 @@ int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p) {
     p->bits = q->relu_bits;
     p->M = q->M; p->N = q->N; p->G = q->G; p->L = q->n_hidden;
     p->tiles_m = (q->M + BM - 1) / BM;
+    if (pair) p->tiles_m = (p->tiles_m + 1) & ~1;   // whole pairs per member: an odd last strip gets a partner that is all padding
     p->store_h = store ? 1 : 0;
     p->trace = orlk::trace_buffer();
     { const char* e = getenv("ORLK_FUSED_NO_STORE"); p->no_store = e ? atoi(e) : 0; }
@@ -639,7 +721,9 @@ extern "C" int orlk_sizeof_fused_fwd(void) { return (int)sizeof(OrlkFusedFwd); }
 extern "C" int orlk_sizeof_fused_bwd(void) { return (int)sizeof(OrlkFusedBwd); }
 
 extern "C" int orlk_fused_init(void) {
-    int rc = check(cudaFuncSetAttribute(k_critic_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
+    int rc = check(cudaFuncSetAttribute(k_critic_fwd_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd");
+    if (rc) return rc;
+    rc = check(cudaFuncSetAttribute(k_critic_fwd_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd (pairs)");
     if (rc) return rc;
     return check(cudaFuncSetAttribute(k_critic_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_bwd");
 }
@@ -694,12 +778,30 @@ extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs, int n_jobs, void*
     ORLK_REQUIRE(jobs != nullptr && (n_jobs == 1 || n_jobs == 2), "one or two jobs");
     static FwdMaps maps[2];         // (host scratch; launches are issued from one thread per process)
     FwdParams p[2];
+    bool pair = (jobs[0].flags & ORLK_FUSED_PAIRS) != 0;
+    for (int j = 0; j < n_jobs; ++j) pair = pair && jobs[j].N % 64 == 0;
     for (int j = 0; j < 2; ++j) {
-        const int rc = fill_fwd_job(&jobs[j < n_jobs ? j : 0], &maps[j], &p[j]);
+        const int rc = fill_fwd_job(&jobs[j < n_jobs ? j : 0], &maps[j], &p[j], pair);
         if (rc) return rc;
     }
     const int ctas0 = p[0].G * p[0].tiles_m;
     const int grid = ctas0 + (n_jobs == 2 ? p[1].G * p[1].tiles_m : 0);
-    orlk::launch(k_critic_fwd, dim3(grid), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps[0], maps[1], p[0], p[1], ctas0);
+    if (pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = FWD_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = orlk::pdl_enabled() ? 2 : 1;
+        cudaLaunchKernelEx(&cfg, k_critic_fwd_t<true>, maps[0], maps[1], p[0], p[1], ctas0);
+        return check_launch("k_critic_fwd (pairs)");
+    }
+    orlk::launch(k_critic_fwd_t<false>, dim3(grid), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps[0], maps[1], p[0], p[1], ctas0);
     return check_launch("k_critic_fwd");
 }

@@ -226,10 +226,15 @@ class Runtime:
                     H=list(H) if H is not None else None, gs=gs, h_gs=h_gs, head_w=head_w, head_b=head_b, out=out,
                     out_gs=out_gs, M=M, N=N, K0=K0, G=G, relu_bits=relu_bits)
 
-    def critic_fwd_fused(self, jobs: Sequence[dict]) -> Callable[[], None]:
+    def critic_fwd_fused(self, jobs: Sequence[dict], pairs: Optional[bool] = None) -> Callable[[], None]:
         """Whole Linear+ReLU critic passes + scalar heads for all members in ONE tcgen05 launch (csrc/orlk_fused.cu);
-        one or two jobs (``fused_fwd_job``) side by side."""
+        one or two jobs (``fused_fwd_job``) side by side.  ``pairs``: CTA pairs (cta_group::2); None = when the launch
+        has at least 64 strips (ORLK_FUSED_2CTA=0 / 1 forces it off / on)."""
         assert 1 <= len(jobs) <= 2
+        if pairs is None:
+            env = os.environ.get("ORLK_FUSED_2CTA", "auto")
+            strips = sum(j["G"] * (-(-j["M"] // 128)) for j in jobs)
+            pairs = env == "1" or (env not in ("0", "1") and strips >= 64)
         arr = (L.FusedFwd * len(jobs))()
         for q, j in zip(arr, jobs):
             q.X, q.ldx = j["X"].ptr, j["X"].ld
@@ -241,6 +246,7 @@ class Runtime:
             q.head_w, q.head_b, q.out, q.out_gs = j["head_w"], j["head_b"], j["out"], j["out_gs"]
             q.relu_bits = j.get("relu_bits") or None
             q.M, q.N, q.K0, q.G, q.n_hidden = j["M"], j["N"], j["K0"], j["G"], len(j["bias"])
+            q.flags = L.FUSED_PAIRS if pairs else 0
         n = len(jobs)
         return lambda: L.call("orlk_critic_fwd_fused", arr, n, self.cur)
 

@@ -848,13 +848,15 @@ def _check_fused(case):
             assert err <= tol, f"layer {l} member {g}: max err {err:.3e} vs {tol:.3e}"
 
 
+@pytest.mark.parametrize("pairs", [False, True])
 @pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (2560, 256, 14, 2, 2), (300, 128, 32, 4, 1),
                                          (2048 + 77, 64, 5, 3, 3)])
-def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G):
+def test_critic_forward_fused_matches_fp64(rt, M, N, K0, nh, G, pairs):
     """orlk_critic_fwd_fused: every hidden activation and the scalar head of all members against an fp64 evaluation of
-    the same Linear+ReLU stack (nets/mlp.py:22-28, modules/critic_module.py:25-33); 3xTF32 = fp32-grade."""
+    the same Linear+ReLU stack (nets/mlp.py:22-28, modules/critic_module.py:25-33); 3xTF32 = fp32-grade.  Single CTAs and
+    CTA pairs (cta_group::2; odd strip counts get a padding partner)."""
     case = _fused_case(rt, M, N, K0, nh, G, seed=M + N + K0)
-    op = rt.critic_fwd_fused([case["job"]])
+    op = rt.critic_fwd_fused([case["job"]], pairs=pairs)
     for _ in range(2):          # a second launch over the same buffers: barriers / ring state start clean every time
         op()
     torch.cuda.synchronize()
@@ -876,10 +878,13 @@ def test_critic_forward_fused_two_jobs(rt):
     short one (head only), as the CQL step launches them (policy/model_free/cql.py:108-160)."""
     a = _fused_case(rt, 7936, 256, 23, 3, 2, seed=1)
     b = _fused_case(rt, 256, 256, 23, 3, 2, seed=2, store_h=False)
-    rt.critic_fwd_fused([a["job"], b["job"]])()
-    torch.cuda.synchronize()
-    _check_fused(a)
-    _check_fused(b)
+    for pairs in (False, True):
+        for t in (a["out"], b["out"]):
+            t.fill_(float("nan"))
+        rt.critic_fwd_fused([a["job"], b["job"]], pairs=pairs)()
+        torch.cuda.synchronize()
+        _check_fused(a)
+        _check_fused(b)
 
 
 @pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (300, 128, 32, 4, 1), (2048 + 77, 64, 5, 2, 3)])
