@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 28
+#define ORLK_ABI_VERSION 29
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -267,6 +267,14 @@ int orlk_sizeof_fused_bwd(void);
  *   w0pad[0][g][o][k] = W0[g*gs + o*K0 + k] (k < K0, else 0), w0pad[1] = its lo words  (W0 inside [src, src + n)). */
 int orlk_fused_prep(const float* src, float* dst_lo, int64_t n, const float* W0, int64_t gs, int N, int K0, int G,
                     float* w0pad, void* stream);
+/* The same for up to four arenas in ONE launch (a step's online, target and transposed critic weights). Host array. */
+typedef struct OrlkFusedPrep {
+    const float* src; float* dst_lo; int64_t n;
+    const float* W0; int64_t gs; float* w0pad;     /* W0 == NULL: lo words only */
+    int32_t N, K0, G, pad_;
+} OrlkFusedPrep;
+int orlk_fused_prep_multi(const OrlkFusedPrep* jobs_host, int n_jobs, void* stream);
+int orlk_sizeof_fused_prep(void);
 
 /* Narrow-output linear layers (N <= 16: Critic.last, dist_net.mu/sigma, Actor.last;
  * modules/critic_module.py:15,26, dist_module.py:57-60, actor_module.py:44,49).

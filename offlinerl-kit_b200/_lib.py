@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 28
+ABI_VERSION = 29
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -88,6 +88,11 @@ class FusedFwd(C.Structure):
 FUSED_PAIRS = 1
 
 
+class FusedPrep(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_lo", C.c_void_p), ("n", C.c_int64), ("W0", C.c_void_p), ("gs", C.c_int64),
+                ("w0pad", C.c_void_p), ("N", C.c_int32), ("K0", C.c_int32), ("G", C.c_int32), ("pad_", C.c_int32)]
+
+
 class FusedBwd(C.Structure):
     _fields_ = [("dq", C.c_void_p), ("dq_gs", C.c_int64), ("head_w", C.c_void_p), ("relu_bits", C.c_void_p),
                 ("WT", C.c_void_p * FUSED_MAX_LAYERS), ("WTlo", C.c_void_p * FUSED_MAX_LAYERS),
@@ -130,6 +135,7 @@ _PROTOS = {
     "orlk_sizeof_tc_gemm": [],
     "orlk_fused_init": [], "orlk_critic_fwd_fused": [C.POINTER(FusedFwd), _I, _P], "orlk_sizeof_fused_fwd": [],
     "orlk_critic_bwd_fused": [C.POINTER(FusedBwd), _P], "orlk_sizeof_fused_bwd": [],
+    "orlk_fused_prep_multi": [C.POINTER(FusedPrep), _I, _P], "orlk_sizeof_fused_prep": [],
     "orlk_fused_prep": [_P, _P, _L, _P, _L, _I, _I, _I, _P, _P],
     "orlk_skinny_fwd": [_P, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _P],
     "orlk_skinny_dgrad": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P],
@@ -196,7 +202,8 @@ def load() -> C.CDLL:
     for fn, st in (("orlk_sizeof_gemm_desc", GemmDesc), ("orlk_sizeof_adam_desc", AdamDesc),
                    ("orlk_sizeof_adam_group", AdamGroup), ("orlk_sizeof_concat_seg", ConcatSeg),
                    ("orlk_sizeof_tc_gemm", TcGemm), ("orlk_sizeof_sample_use", SampleUse),
-                   ("orlk_sizeof_fused_fwd", FusedFwd), ("orlk_sizeof_fused_bwd", FusedBwd)):
+                   ("orlk_sizeof_fused_fwd", FusedFwd), ("orlk_sizeof_fused_bwd", FusedBwd),
+                   ("orlk_sizeof_fused_prep", FusedPrep)):
         if getattr(lib, fn)() != C.sizeof(st):
             raise OrlkError(f"struct size mismatch for {st.__name__}: C {getattr(lib, fn)()} vs ctypes {C.sizeof(st)}")
     _lib = lib

@@ -662,6 +662,40 @@ __global__ void k_fused_prep(const float* __restrict__ src, float* __restrict__ 
     }
 }
 
+// the same for up to four arenas in one launch (blockIdx.y = arena): the step's derived copies of the online, target and
+// transposed critic weights cost one launch slot at the start of the step instead of three
+struct PrepJobs {
+    OrlkFusedPrep j[4];
+    int nb_split[4];
+};
+
+__global__ void k_fused_prep_multi(const PrepJobs P) {
+    orlk::pdl_enter();
+    const OrlkFusedPrep& q = P.j[blockIdx.y];
+    const int nb_split = P.nb_split[blockIdx.y];
+    if ((int)blockIdx.x < nb_split) {
+        const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (i + 3 < q.n) {
+            const float4 v = *reinterpret_cast<const float4*>(q.src + i);
+            *reinterpret_cast<float4*>(q.dst_lo + i) = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+        } else {
+            for (int64_t j = i; j < q.n; ++j) q.dst_lo[j] = lo_of(q.src[j]);
+        }
+        return;
+    }
+    if (q.W0 == nullptr) return;
+    const int64_t total = (int64_t)q.G * q.N * BK;
+    const int64_t i = ((int64_t)blockIdx.x - nb_split) * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int k = (int)(i % BK);
+        const int64_t gn = i / BK;
+        const int nn = (int)(gn % q.N), g = (int)(gn / q.N);
+        const float v = k < q.K0 ? q.W0[(int64_t)g * q.gs + (int64_t)nn * q.K0 + k] : 0.f;
+        q.w0pad[i] = v;
+        q.w0pad[total + i] = lo_of(v);
+    }
+}
+
 constexpr size_t FWD_SMEM = 1024 + RING + FIXED;
 
 int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p, bool pair) {
@@ -772,6 +806,26 @@ extern "C" int orlk_fused_prep(const float* src, float* dst_lo, int64_t n, const
     orlk::launch(k_fused_prep, dim3((unsigned)(nb_split + nb_pad)), dim3(256), 0, (cudaStream_t)stream, src, dst_lo, n, nb_split, W0, gs,
                  N, K0, G, w0pad);
     return check_launch("k_fused_prep");
+}
+
+extern "C" int orlk_sizeof_fused_prep(void) { return (int)sizeof(OrlkFusedPrep); }
+
+extern "C" int orlk_fused_prep_multi(const OrlkFusedPrep* jobs, int n_jobs, void* stream) {
+    ORLK_REQUIRE(jobs != nullptr && n_jobs >= 1 && n_jobs <= 4, "1..4 arenas");
+    PrepJobs P;
+    memset(&P, 0, sizeof(P));
+    int nbx = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const OrlkFusedPrep& q = jobs[j];
+        ORLK_REQUIRE(q.src != nullptr && q.dst_lo != nullptr && q.n > 0 && aligned16(q.src) && aligned16(q.dst_lo), "fused_prep arguments");
+        ORLK_REQUIRE(q.W0 == nullptr || (q.w0pad != nullptr && q.N > 0 && q.K0 > 0 && q.K0 <= BK && q.G > 0), "first-layer weights");
+        P.j[j] = q;
+        P.nb_split[j] = (int)(((q.n + 3) / 4 + 255) / 256);
+        const int nb = P.nb_split[j] + (q.W0 != nullptr ? (int)(((int64_t)q.G * q.N * BK + 255) / 256) : 0);
+        nbx = nb > nbx ? nb : nbx;
+    }
+    orlk::launch(k_fused_prep_multi, dim3((unsigned)nbx, (unsigned)n_jobs), dim3(256), 0, (cudaStream_t)stream, P);
+    return check_launch("k_fused_prep_multi");
 }
 
 extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs, int n_jobs, void* stream) {

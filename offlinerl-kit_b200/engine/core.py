@@ -264,6 +264,20 @@ class Runtime:
         qp = _ctypes_pointer(q)
         return lambda: L.call("orlk_critic_bwd_fused", qp, self.cur)
 
+    def fused_prep_multi(self, jobs: Sequence[dict]) -> Callable[[], None]:
+        """``fused_prep`` for up to four arenas in one launch; jobs: dicts with the keyword arguments of ``fused_prep``."""
+        assert 1 <= len(jobs) <= 4
+        arr = (L.FusedPrep * len(jobs))()
+        keep = []
+        for q, j in zip(arr, jobs):
+            q.src, q.dst_lo, q.n = j["src"].data_ptr(), j["dst_lo"].data_ptr(), j["src"].numel()
+            q.W0, q.gs = (j.get("W0") or None), j.get("gs", 0)
+            q.w0pad = j["w0pad"].data_ptr() if j.get("w0pad") is not None else None
+            q.N, q.K0, q.G = j.get("N", 0), j.get("K0", 0), j.get("G", 0)
+            keep.append((j["src"], j["dst_lo"], j.get("w0pad")))
+        n = len(jobs)
+        return lambda keep=keep: L.call("orlk_fused_prep_multi", arr, n, self.cur)
+
     def fused_prep(self, src: torch.Tensor, dst_lo: torch.Tensor, W0: int = 0, gs: int = 0, N: int = 0, K0: int = 0, G: int = 0,
                    w0pad: Optional[torch.Tensor] = None) -> Callable[[], None]:
         """dst_lo = src - trunc_tf32(src) over a whole parameter arena, and the zero-padded [2][G][N][32] copy (+ lo words)

@@ -490,6 +490,26 @@ def emit_lo_refresh(rt: Runtime, plan: Plan, ps: ParamSet, store: str) -> None:
                                                             w0pad=ps.w0_pad(store)))
 
 
+def emit_lo_refresh_many(rt: Runtime, plan: Plan, items: Sequence[Tuple[ParamSet, str]]) -> None:
+    """``emit_lo_refresh`` for several (ParamSet, store) pairs in ONE launch (orlk_fused_prep_multi)."""
+    done = plan.__dict__.setdefault("_lo_fresh", set())
+    jobs = []
+    for ps, store in items:
+        key = (id(ps), store)
+        if key in done:
+            continue
+        done.add(key)
+        plan.keep.append(ps)
+        lay0 = ps.layers[0]
+        if store == "WT":
+            jobs.append(dict(src=ps.WT, dst_lo=ps.lo_arena("WT")))
+        else:
+            jobs.append(dict(src=getattr(ps, store), dst_lo=ps.lo_arena(store), W0=ps.w(0, 0, store), gs=lay0.w_gs,
+                             N=lay0.out_dim, K0=lay0.in_dim, G=ps.G, w0pad=ps.w0_pad(store)))
+    if jobs:
+        plan.add("fused_prep", rt.fused_prep_multi(jobs))
+
+
 def fused_fwd_job(rt: Runtime, run: "MlpRun", X: Mat) -> dict:
     """``run``'s whole forward pass (hidden layers + scalar head, all members) as one job of a fused launch."""
     ps, nh, M, G = run.ps, run.nh, run.M, run.G

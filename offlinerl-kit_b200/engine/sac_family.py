@@ -18,7 +18,7 @@ import torch
 from .. import _lib as L
 from .core import Mat, Plan
 from .learner import (Learner, MlpRun, chainable, check_plain_mlp, emit_dact, emit_forward, emit_forward_pair, emit_head_dgrad, emit_hidden_dgrad,
-                      emit_lo_refresh, emit_wgrad_adam, linears_of, make_gradbuf)
+                      emit_lo_refresh, emit_lo_refresh_many, emit_wgrad_adam, linears_of, make_gradbuf)
 from .nets import TC_MIN_ROWS, ParamSet, dgrad_problem, pick_cfg
 
 # loss block layout (floats)
@@ -423,12 +423,10 @@ class CQLLearner(TwinCriticLearner):
             # beside the actor forward: the noise fill and - the critics are only updated at the END of a step - the lo
             # words of the online / target critic weights that the fused critic passes fetch by TMA
             plan.add(*noise)
-            if self.run_critic.fused_fwd:
-                emit_lo_refresh(rt, plan, self.critic_ps, "P")
-            if self.run_target.fused_fwd:
-                emit_lo_refresh(rt, plan, self.critic_ps, "T")
-            if self.run_critic.fused_bwd:
-                emit_lo_refresh(rt, plan, self.critic_ps, "WT")
+            items = ([(self.critic_ps, "P")] if self.run_critic.fused_fwd else []) \
+                + ([(self.critic_ps, "T")] if self.run_target.fused_fwd else []) \
+                + ([(self.critic_ps, "WT")] if self.run_critic.fused_bwd else [])
+            emit_lo_refresh_many(rt, plan, items)
         self._emit_actor_update(plan, clamp01=False, beside_forward=beside)
 
         # ---- critic phase with the UPDATED actor (cql.py:108-192)
