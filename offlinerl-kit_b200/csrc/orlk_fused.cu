@@ -32,7 +32,7 @@ constexpr int FIXED = 8192;
 constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 
-enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 3, BAR_ACC = 5, BAR_BFULL = 7, BAR_BEMPTY = 11, BAR_COUNT = 15 };
+enum { BAR_X = 0, BAR_AFULL = 1, BAR_AEMPTY = 4, BAR_ACC = 7, BAR_BFULL = 9, BAR_BEMPTY = 13, BAR_COUNT = 17 };
 
 struct FwdMaps {
     CUtensorMap x;                // X [M][K0]: box 32 (k, zero filled past K0) x 128 rows
@@ -121,16 +121,20 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
              const __grid_constant__ FwdParams p0, const __grid_constant__ FwdParams p1, const int ctas0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // SWIZZLE_128B tiles: 1024-byte aligned
-    uint8_t* b_base = base + 2 * A_STAGE;
+    // ring split of the 192 KB: single CTA: 2 A stages (64 KB) + 2 weight stages of 64 KB; pair: 3 A stages (96 KB: the A
+    // round trip  MMA done -> multicast commit -> epilogue writes -> remote arrive -> issue  is longer than one slab's MMAs,
+    // two stages left the mainloop waiting for A every other slab) + 3 weight stages of 32 KB
+    constexpr int NSA = PAIR ? 3 : 2;
+    uint8_t* b_base = base + NSA * A_STAGE;
     uint8_t* fixed = base + RING;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 128);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 192);
     float* bias_s = reinterpret_cast<float*>(fixed + 256);       // [MAXL][NMAX]
     float* headw_s = bias_s + MAXL * NMAX;                        // [NMAX]
     float* qpart_s = headw_s + NMAX;                              // [BM]
     auto a_hi = [&](int s) { return base + s * A_STAGE; };
     auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };
-    constexpr int NSB = PAIR ? 4 : 2;                      // weight ring stages
+    constexpr int NSB = PAIR ? 3 : 2;                      // weight ring stages
     constexpr int BST = PAIR ? B_STAGE / 2 : B_STAGE;      // bytes per stage: [hi | lo] of this CTA's rows of the slab
     auto b_hi = [&](int s) { return b_base + s * BST; };
     auto b_lo = [&](int s) { return b_base + s * BST + BST / 2; };
@@ -165,11 +169,14 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
     }
     if (warp == 1 && lane == 0) {
         mbar_init(bar(BAR_X), 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(BAR_AFULL + s), PAIR ? 8 : 4);    // one arrival per epilogue warp of the stage's group (of both CTAs)
-            mbar_init(bar(BAR_AEMPTY + s), 1);
-            mbar_init(bar(BAR_ACC + s), 1);
+        for (int s = 0; s < NSA; ++s) {
+            mbar_init(bar(BAR_AFULL + s), PAIR ? 8 : 4);    // one arrival per epilogue warp of the chunk's group (of both CTAs)
+            // free again = the MMAs that read the stage have completed (1, a commit) AND the four warps that filled it have
+            // seen their TMA stores of its tiles read the shared memory (4; with three stages the next writer of a
+            // stage is a warp of the OTHER group, whose own bulk-group wait says nothing about those stores)
+            mbar_init(bar(BAR_AEMPTY + s), 5);
         }
+        for (int s = 0; s < 2; ++s) mbar_init(bar(BAR_ACC + s), 1);
         for (int s = 0; s < NSB; ++s) {
             mbar_init(bar(BAR_BFULL + s), 1);
             mbar_init(bar(BAR_BEMPTY + s), 1);
@@ -227,15 +234,13 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
         if ((!PAIR || rank == 0) && elect_one()) {
             // ------------------------------------------------------------ MMA issuer (the leader CTA's, for a pair)
             const uint32_t idesc = instr_desc_tf32(PAIR ? 2 * BM : BM, N);
-            int fa0 = 0, fa1 = 0, bi = 0;       // fills consumed so far of A stage 0 / 1, B fills consumed
+            int bi = 0;                         // slabs issued so far = index of the A fill and of the B fill they consume
             for (int l = 0; l < L; ++l) {
                 const uint32_t acc = tmem_base + (uint32_t)(NMAX * (l & 1));
                 const int nsl = l == 0 ? 1 : KS;
                 for (int j = 0; j < nsl; ++j, ++bi) {
-                    const int sa = l == 0 ? 0 : (j & 1);
-                    const int fa = sa ? fa1 : fa0;
-                    mbar_wait(bar(BAR_AFULL + sa), fa & 1);
-                    if (sa) ++fa1; else ++fa0;
+                    const int sa = bi % NSA;
+                    mbar_wait(bar(BAR_AFULL + sa), (bi / NSA) & 1);
                     if (bi < 32) FZ_STAMP(16 + bi);
                     const int sb = bi % NSB;
                     mbar_wait(bar(BAR_BFULL + sb), (bi / NSB) & 1);
@@ -300,17 +305,21 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
         asm volatile("bar.sync 1, 256;" ::: "memory");     // bias_s / headw_s complete
         if (t == 0) FZ_STAMP(2);
 
-        int fe = grp == 0 ? 1 : 0;                  // fills of this group's A stage so far
         float qacc = 0.f;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint8_t* my_hi = a_hi(grp) + q * 4096;      // this warp's 32 rows of the stage: a 32 x 32 SWIZZLE_128B store tile
-        uint8_t* my_lo = a_lo(grp) + q * 4096;
+        int prev_stage = grp == 0 ? 0 : -1;         // stage of this warp's previous A fill (group 0 wrote the X tile's lo words)
         for (int l = 0; l < L; ++l) {
             const bool last = l == L - 1;
             mbar_wait(bar(BAR_ACC + (l & 1)), (l >> 1) & 1);
             tc_fence_after();
             if (t == 0) FZ_STAMP(112 + l);
-            if (last) orlk::pdl_trigger();          // every MMA of this strip has completed
+            if (last) {
+                orlk::pdl_trigger();                // every MMA of this strip has completed
+                // the last layer's store tiles take the upper 128 KB of the ring (all of it is idle now), which in pair mode
+                // includes an A stage: every warp's earlier stores must have read their tiles first
+                if (store_h && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             const float* bl = bias_s + l * NMAX;
             for (int c = grp; c < KS; c += 2) {
                 uint32_t v[32];
@@ -338,7 +347,7 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
 #pragma unroll
                     for (int j = 0; j < 32; ++j) qacc = fmaf(x[j], hw[j], qacc);
                     if (store_h) {
-                        uint8_t* tile = b_base + ((warp - 2) * 4 + (c >> 1)) * 4096;
+                        uint8_t* tile = base + (RING - 32 * 4096) + ((warp - 2) * 4 + (c >> 1)) * 4096;
                         float4* hrow = reinterpret_cast<float4*>(tile + lane * 128);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
@@ -352,13 +361,18 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
                     }
                     continue;
                 }
-                // the stage's previous content: read by the MMAs of slab c - 2 (or of the previous layer) and by this
-                // warp's own TMA store
-                if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
-                if (store_h) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
+                // A fill number 1 + l * KS + c (fill 0 was the X tile) goes to stage fill % NSA; the stage's previous content
+                // was read by the MMAs of the slab NSA fills earlier and by this warp's own TMA store
+                const int af = 1 + l * KS + c, sa = af % NSA;
+                uint8_t* my_hi = a_hi(sa) + q * 4096;       // this warp's 32 rows of the stage: a 32 x 32 SWIZZLE_128B store tile
+                uint8_t* my_lo = a_lo(sa) + q * 4096;
+                if (lane == 0 && prev_stage >= 0) {         // this warp's stores of its previous fill have read their tiles
+                    if (store_h) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(bar(BAR_AEMPTY + prev_stage));
                 }
+                prev_stage = sa;
+                if (af >= NSA) mbar_wait(bar(BAR_AEMPTY + sa), (af / NSA - 1) & 1);
+                __syncwarp();
                 float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
                 float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
 #pragma unroll
@@ -372,14 +386,13 @@ k_critic_fwd_t(const __grid_constant__ FwdMaps maps0, const __grid_constant__ Fw
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + grp), 0));
-                    else mbar_arrive(bar(BAR_AFULL + grp));
+                    if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + sa), 0));
+                    else mbar_arrive(bar(BAR_AFULL + sa));
                     if (store_h) {
                         tma_store_4d(&maps.h[l], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
-                ++fe;
             }
         }
         // scalar head: even-chunk partial (warps 2-5) + odd-chunk partial (warps 6-9) + bias, fixed order
@@ -429,7 +442,7 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
     uint8_t* b_base = base + 2 * A_STAGE;
     uint8_t* fixed = base + RING;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 128);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 192);
     float* headw_s = reinterpret_cast<float*>(fixed + 256);       // [NMAX]
     auto a_hi = [&](int s) { return base + s * A_STAGE; };
     auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };

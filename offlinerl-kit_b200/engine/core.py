@@ -229,12 +229,12 @@ class Runtime:
     def critic_fwd_fused(self, jobs: Sequence[dict], pairs: Optional[bool] = None) -> Callable[[], None]:
         """Whole Linear+ReLU critic passes + scalar heads for all members in ONE tcgen05 launch (csrc/orlk_fused.cu);
         one or two jobs (``fused_fwd_job``) side by side.  ``pairs``: CTA pairs (cta_group::2); None = when the launch
-        has at least 64 strips (ORLK_FUSED_2CTA=0 / 1 forces it off / on)."""
+        has at least 32 strips (ORLK_FUSED_2CTA=0 / 1 forces it off / on)."""
         assert 1 <= len(jobs) <= 2
         if pairs is None:
             env = os.environ.get("ORLK_FUSED_2CTA", "auto")
             strips = sum(j["G"] * (-(-j["M"] // 128)) for j in jobs)
-            pairs = env == "1" or (env not in ("0", "1") and strips >= 64)
+            pairs = env == "1" or (env not in ("0", "1") and strips >= 32)
         arr = (L.FusedFwd * len(jobs))()
         for q, j in zip(arr, jobs):
             q.X, q.ldx = j["X"].ptr, j["X"].ld

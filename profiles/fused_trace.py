@@ -19,7 +19,7 @@ def al(n):
     return (n + 3) // 4 * 4
 
 
-def trace_fwd(M, N, K0, nh, G):
+def trace_fwd(M, N, K0, nh, G, pairs=False):
     ldx = al(K0)
     X = torch.randn(M, ldx, device="cuda")
     dims = [(N, K0)] + [(N, N)] * (nh - 1) + [(1, N)]
@@ -41,7 +41,7 @@ def trace_fwd(M, N, K0, nh, G):
                            Wlo=[0] + [lo + 4 * offs[l][0] for l in range(1, nh)], bias=[base + 4 * offs[l][1] for l in range(nh)],
                            H=[h.data_ptr() for h in H], gs=block, h_gs=M * N, head_w=base + 4 * offs[nh][0],
                            head_b=base + 4 * offs[nh][1], out=out.data_ptr(), out_gs=M, M=M, N=N, K0=K0, G=G)
-    op = rt.critic_fwd_fused([job])
+    op = rt.critic_fwd_fused([job], pairs=pairs)
     buf = torch.zeros(1024 * 128, dtype=torch.int64, device="cuda")
     g = C.c_void_p()
     torch.cuda.synchronize()
@@ -73,7 +73,7 @@ def trace_fwd(M, N, K0, nh, G):
     rel[t == 0] = float("nan")
     med = rel.nanmedian(dim=0).values.tolist()
     nsl = 1 + (nh - 1) * (N // 32)
-    print(f"fwd M={M} N={N} K0={K0} nh={nh} G={G} ctas={n_cta}: start {med[0]:.0f}  staged {med[2]:.0f}  end {med[3]:.0f}")
+    print(f"fwd {'PAIRS ' if pairs else ''}M={M} N={N} K0={K0} nh={nh} G={G} ctas={n_cta}: start {med[0]:.0f}  staged {med[2]:.0f}  end {med[3]:.0f}")
     print("   acc_full per layer: " + "  ".join(f"{med[112 + l]:.0f}" for l in range(nh)))
     print("   slab: A ready / B ready (= MMA issue) / TMA for this B issued")
     for bi in range(nsl):
@@ -84,3 +84,5 @@ def trace_fwd(M, N, K0, nh, G):
 
 trace_fwd(7936, 256, 23, 3, 2)
 trace_fwd(128, 256, 23, 3, 1)
+trace_fwd(7936, 256, 23, 3, 2, pairs=True)
+trace_fwd(256, 256, 23, 3, 1, pairs=True)
