@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORLK_ABI_VERSION 29
+#define ORLK_ABI_VERSION 30
 #define ORLK_ERR_BAD_ARG 10001
 #define ORLK_ERR_UNSUPPORTED 10002
 
@@ -258,6 +258,7 @@ typedef struct OrlkFusedBwd {
     float* dZ[ORLK_FUSED_MAX_LAYERS];             /* dZ[l], l = 0 .. n_hidden-2: [G][M][N] */
     int64_t gs, dz_gs;
     int32_t M, N, G, n_hidden;
+    int32_t flags, pad_;                          /* ORLK_FUSED_PAIRS */
 } OrlkFusedBwd;
 int orlk_critic_bwd_fused(const OrlkFusedBwd* params_host, void* stream);
 int orlk_sizeof_fused_bwd(void);

@@ -8,7 +8,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liborlk_b200.so")
-ABI_VERSION = 29
+ABI_VERSION = 30
 
 c_f32p = C.c_void_p     # all device pointers travel as integers
 c_stream = C.c_void_p
@@ -97,7 +97,8 @@ class FusedBwd(C.Structure):
     _fields_ = [("dq", C.c_void_p), ("dq_gs", C.c_int64), ("head_w", C.c_void_p), ("relu_bits", C.c_void_p),
                 ("WT", C.c_void_p * FUSED_MAX_LAYERS), ("WTlo", C.c_void_p * FUSED_MAX_LAYERS),
                 ("dZ", C.c_void_p * FUSED_MAX_LAYERS), ("gs", C.c_int64), ("dz_gs", C.c_int64),
-                ("M", C.c_int32), ("N", C.c_int32), ("G", C.c_int32), ("n_hidden", C.c_int32)]
+                ("M", C.c_int32), ("N", C.c_int32), ("G", C.c_int32), ("n_hidden", C.c_int32),
+                ("flags", C.c_int32), ("pad_", C.c_int32)]
 
 
 EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_SWISH, EPI_DSWISH = range(5)

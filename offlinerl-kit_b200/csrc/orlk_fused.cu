@@ -435,19 +435,23 @@ struct BwdParams {
     unsigned long long* trace;
 };
 
+template <bool PAIR>       // CTA pairs as in k_critic_fwd_t
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdParams p) {
+k_critic_bwd_t(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* b_base = base + 2 * A_STAGE;
+    constexpr int NSA = PAIR ? 3 : 2;
+    constexpr int NSB = PAIR ? 3 : 2;
+    constexpr int BST = PAIR ? B_STAGE / 2 : B_STAGE;
+    uint8_t* b_base = base + NSA * A_STAGE;
     uint8_t* fixed = base + RING;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fixed);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fixed + 192);
     float* headw_s = reinterpret_cast<float*>(fixed + 256);       // [NMAX]
     auto a_hi = [&](int s) { return base + s * A_STAGE; };
     auto a_lo = [&](int s) { return base + s * A_STAGE + A_TILE; };
-    auto b_hi = [&](int s) { return b_base + s * B_STAGE; };
-    auto b_lo = [&](int s) { return b_base + s * B_STAGE + B_TILE; };
+    auto b_hi = [&](int s) { return b_base + s * BST; };
+    auto b_lo = [&](int s) { return b_base + s * BST + BST / 2; };
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -457,6 +461,8 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
     const int N = p.N, L = p.L;
     const int KS = N / BK;
     const int NG = L - 1;                       // GEMM layers of the chain
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int b_rows = PAIR ? N / 2 : N;
 
     if (threadIdx.x == 0) { FZ_STAMP(0); FZ_GSTAMP(4); }
     if (threadIdx.x == 32) {
@@ -467,24 +473,33 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(BAR_AFULL + s), 4);
-            mbar_init(bar(BAR_AEMPTY + s), 1);
+        for (int s = 0; s < NSA; ++s) {
+            mbar_init(bar(BAR_AFULL + s), PAIR ? 8 : 4);
+            mbar_init(bar(BAR_AEMPTY + s), 5);      // the MMAs' commit + the four writer warps (their TMA stores have read the tiles)
+        }
+        for (int s = 0; s < NSB; ++s) {
             mbar_init(bar(BAR_BFULL + s), 1);
             mbar_init(bar(BAR_BEMPTY + s), 1);
-            mbar_init(bar(BAR_ACC + s), 1);
         }
+        for (int s = 0; s < 2; ++s) mbar_init(bar(BAR_ACC + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     orlk::pdl_wait();
     if (threadIdx.x == 0) { FZ_STAMP(1); FZ_GSTAMP(5); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -496,32 +511,37 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
             for (int t = 0; t < NG; ++t) {
                 const int l = L - 1 - t;
                 for (int j = 0; j < KS; ++j, ++bi) {
-                    const int s = bi & 1;
-                    mbar_wait(bar(BAR_BEMPTY + s), ((bi >> 1) & 1) ^ 1);
+                    const int s = bi % NSB;
+                    mbar_wait(bar(BAR_BEMPTY + s), ((bi / NSB) & 1) ^ 1);
                     if (bi < 32) FZ_STAMP(80 + bi);
-                    mbar_expect_tx(bar(BAR_BFULL + s), tx);
-                    tma_load_3d(smem_u32(b_hi(s)), &maps.wt[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
-                    tma_load_3d(smem_u32(b_lo(s)), &maps.wtlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                    if (PAIR) {
+                        const uint32_t lb = map_to_rank(bar(BAR_BFULL + s), 0);
+                        if (rank == 0) mbar_expect_tx(bar(BAR_BFULL + s), tx);
+                        tma_load_3d_pair(smem_u32(b_hi(s)), &maps.wt[l - 1], lb, j * BK, (int)rank * b_rows, g);
+                        tma_load_3d_pair(smem_u32(b_lo(s)), &maps.wtlo[l - 1], lb, j * BK, (int)rank * b_rows, g);
+                    } else {
+                        mbar_expect_tx(bar(BAR_BFULL + s), tx);
+                        tma_load_3d(smem_u32(b_hi(s)), &maps.wt[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                        tma_load_3d(smem_u32(b_lo(s)), &maps.wtlo[l - 1], bar(BAR_BFULL + s), j * BK, 0, g);
+                    }
                 }
             }
         }
         __syncwarp();
         orlk::pdl_trigger();
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ------------------------------------------------------------ MMA issuer
-            const uint32_t idesc = instr_desc_tf32(BM, N);
-            int fa0 = 0, fa1 = 0, bi = 0;
+        if ((!PAIR || rank == 0) && elect_one()) {
+            // ------------------------------------------------------------ MMA issuer (the leader CTA's, for a pair)
+            const uint32_t idesc = instr_desc_tf32(PAIR ? 2 * BM : BM, N);
+            int bi = 0;
             for (int t = 0; t < NG; ++t) {
                 const uint32_t acc = tmem_base + (uint32_t)(NMAX * (t & 1));
                 for (int j = 0; j < KS; ++j, ++bi) {
-                    const int sa = j & 1;
-                    const int fa = sa ? fa1 : fa0;
-                    mbar_wait(bar(BAR_AFULL + sa), fa & 1);
-                    if (sa) ++fa1; else ++fa0;
+                    const int sa = bi % NSA;
+                    mbar_wait(bar(BAR_AFULL + sa), (bi / NSA) & 1);
                     if (bi < 32) FZ_STAMP(16 + bi);
-                    const int sb = bi & 1;
-                    mbar_wait(bar(BAR_BFULL + sb), (bi >> 1) & 1);
+                    const int sb = bi % NSB;
+                    mbar_wait(bar(BAR_BFULL + sb), (bi / NSB) & 1);
                     if (bi < 32) FZ_STAMP(48 + bi);
                     tc_fence_after();
                     const uint64_t ad = smem_desc_sw128(smem_u32(a_hi(sa))), adl = smem_desc_sw128(smem_u32(a_lo(sa)));
@@ -529,14 +549,26 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t ko = (uint64_t)(2 * k);
-                        umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
-                        umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                        if (PAIR) {
+                            umma_tf32_pair(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_pair(acc, adl + ko, bd + ko, idesc, 1u);
+                            umma_tf32_pair(acc, ad + ko, bdl + ko, idesc, 1u);
+                        } else {
+                            umma_tf32(acc, ad + ko, bd + ko, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32(acc, adl + ko, bd + ko, idesc, 1u);
+                            umma_tf32(acc, ad + ko, bdl + ko, idesc, 1u);
+                        }
                     }
-                    umma_commit(bar(BAR_AEMPTY + sa));
-                    umma_commit(bar(BAR_BEMPTY + sb));
+                    if (PAIR) {
+                        umma_commit_pair(bar(BAR_AEMPTY + sa));
+                        umma_commit_pair(bar(BAR_BEMPTY + sb));
+                    } else {
+                        umma_commit(bar(BAR_AEMPTY + sa));
+                        umma_commit(bar(BAR_BEMPTY + sb));
+                    }
                 }
-                umma_commit(bar(BAR_ACC + (t & 1)));
+                if (PAIR) umma_commit_pair(bar(BAR_ACC + (t & 1)));
+                else umma_commit(bar(BAR_ACC + (t & 1)));
             }
         }
         __syncwarp();
@@ -562,11 +594,25 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
         asm volatile("bar.sync 1, 256;" ::: "memory");     // headw_s complete
         if (t256 == 0) FZ_STAMP(2);
 
-        int fe = 0;
-        uint8_t* my_hi = a_hi(grp) + q * 4096;
-        uint8_t* my_lo = a_lo(grp) + q * 4096;
+        int prev_stage = -1;                        // stage of this warp's previous A fill
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        auto write_a = [&](const float (&x)[32]) {      // this warp's 32 rows of the stage's hi and lo tiles
+        // A fill number af (sequential over the chain: GEMM t, chunk c -> t * KS + c) goes to stage af % NSA.  Before
+        // writing: confirm that this warp's stores of its previous fill have read their tiles (an arrival on THAT stage's
+        // free barrier), then wait until the target stage is free (MMAs done + its previous writers' confirmations).
+        auto claim = [&](int af) -> int {
+            const int sa = af % NSA;
+            if (lane == 0 && prev_stage >= 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(bar(BAR_AEMPTY + prev_stage));
+            }
+            prev_stage = sa;
+            if (af >= NSA) mbar_wait(bar(BAR_AEMPTY + sa), (af / NSA - 1) & 1);
+            __syncwarp();
+            return sa;
+        };
+        auto write_a = [&](int sa, const float (&x)[32]) {      // this warp's 32 rows of the stage's hi and lo tiles
+            uint8_t* my_hi = a_hi(sa) + q * 4096;
+            uint8_t* my_lo = a_lo(sa) + q * 4096;
             float4* hrow = reinterpret_cast<float4*>(my_hi + lane * 128);
             float4* lrow = reinterpret_cast<float4*>(my_lo + lane * 128);
 #pragma unroll
@@ -584,12 +630,14 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
             const uint32_t bits = mb[i];
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? dq_m * hw[j] : 0.f;
-            if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
-            write_a(x);
+            const int sa = claim(c);
+            write_a(sa, x);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_AFULL + grp));
-            ++fe;
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + sa), 0));
+                else mbar_arrive(bar(BAR_AFULL + sa));
+            }
         }
         // ---- epilogues: dZ_{l-1} = acc * relu'(H_{l-1}); stored, and (unless it is the last) the next GEMM's operand
         for (int t = 0; t < NG; ++t) {
@@ -599,7 +647,12 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
             mbar_wait(bar(BAR_ACC + (t & 1)), (t >> 1) & 1);
             tc_fence_after();
             if (t256 == 0) FZ_STAMP(112 + t);
-            if (last) orlk::pdl_trigger();
+            if (last) {
+                orlk::pdl_trigger();
+                // the last layer's store tiles take the upper 128 KB of the (now idle) ring: every warp's earlier stores first
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             for (int c = grp, i = 0; c < KS; c += 2, ++i) {
                 uint32_t v[32];
                 tmem_ld32(tlane + (uint32_t)(NMAX * (t & 1) + 32 * c), v);
@@ -609,7 +662,7 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
                 if (last) {     // every MMA has completed: own store tiles in the idle B ring, no store waits for another
-                    uint8_t* tile = b_base + ((warp - 2) * 4 + i) * 4096;
+                    uint8_t* tile = base + (RING - 32 * 4096) + ((warp - 2) * 4 + i) * 4096;
                     float4* hrow = reinterpret_cast<float4*>(tile + lane * 128);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
@@ -622,19 +675,17 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
                     }
                     continue;
                 }
-                if (fe > 0) mbar_wait(bar(BAR_AEMPTY + grp), (fe - 1) & 1);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-                write_a(x);
+                const int sa = claim((t + 1) * KS + c);
+                write_a(sa, x);
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(bar(BAR_AFULL + grp));
-                    tma_store_4d(&maps.dz[l - 1], smem_u32(my_hi), 32 * c, tile_m * BM + q * 32, g, 0);
+                    if (PAIR && rank != 0) mbar_arrive_remote(map_to_rank(bar(BAR_AFULL + sa), 0));
+                    else mbar_arrive(bar(BAR_AFULL + sa));
+                    tma_store_4d(&maps.dz[l - 1], smem_u32(a_hi(sa) + q * 4096), 32 * c, tile_m * BM + q * 32, g, 0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                ++fe;
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -642,8 +693,10 @@ k_critic_bwd(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdPa
     if (threadIdx.x == 64) { FZ_STAMP(3); FZ_GSTAMP(6); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -772,7 +825,9 @@ extern "C" int orlk_fused_init(void) {
     if (rc) return rc;
     rc = check(cudaFuncSetAttribute(k_critic_fwd_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_fwd (pairs)");
     if (rc) return rc;
-    return check(cudaFuncSetAttribute(k_critic_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_bwd");
+    rc = check(cudaFuncSetAttribute(k_critic_bwd_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_bwd");
+    if (rc) return rc;
+    return check(cudaFuncSetAttribute(k_critic_bwd_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM), "smem attr k_critic_bwd (pairs)");
 }
 
 extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
@@ -783,15 +838,17 @@ extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
     ORLK_REQUIRE(q->dq != nullptr && q->head_w != nullptr && q->relu_bits != nullptr, "dq, head weights, ReLU bits");
     static BwdMaps maps;
     BwdParams p;
+    const bool pair = (q->flags & ORLK_FUSED_PAIRS) != 0 && q->N % 64 == 0;
+    const int wbox = pair ? q->N / 2 : q->N;
     memset(&maps, 0, sizeof(maps));
     memset(&p, 0, sizeof(p));
     for (int l = 1; l < q->n_hidden; ++l) {
         ORLK_REQUIRE(q->WT[l] != nullptr && q->WTlo[l] != nullptr && aligned16(q->WT[l]) && aligned16(q->WTlo[l]),
                      "transposed weights (and lo copies) must be 16-byte aligned");
         ORLK_REQUIRE(q->dZ[l - 1] != nullptr && aligned16(q->dZ[l - 1]), "dZ must be 16-byte aligned");
-        int rc = make_map(&maps.wt[l - 1], q->WT[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+        int rc = make_map(&maps.wt[l - 1], q->WT[l], q->N, q->gs, q->N, q->N, q->G, wbox);
         if (rc) return rc;
-        rc = make_map(&maps.wtlo[l - 1], q->WTlo[l], q->N, q->gs, q->N, q->N, q->G, q->N);
+        rc = make_map(&maps.wtlo[l - 1], q->WTlo[l], q->N, q->gs, q->N, q->N, q->G, wbox);
         if (rc) return rc;
         rc = make_map_c(&maps.dz[l - 1], q->dZ[l - 1], q->N, q->dz_gs, 0, q->M, q->N, q->G, 1);
         if (rc) return rc;
@@ -802,8 +859,25 @@ extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
     p.bits = q->relu_bits;
     p.M = q->M; p.N = q->N; p.G = q->G; p.L = q->n_hidden;
     p.tiles_m = (q->M + BM - 1) / BM;
+    if (pair) p.tiles_m = (p.tiles_m + 1) & ~1;
     p.trace = orlk::trace_buffer();
-    orlk::launch(k_critic_bwd, dim3(q->G * p.tiles_m), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(q->G * p.tiles_m);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = FWD_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = orlk::pdl_enabled() ? 2 : 1;
+        cudaLaunchKernelEx(&cfg, k_critic_bwd_t<true>, maps, p);
+        return check_launch("k_critic_bwd (pairs)");
+    }
+    orlk::launch(k_critic_bwd_t<false>, dim3(q->G * p.tiles_m), dim3(NUM_THREADS), FWD_SMEM, (cudaStream_t)stream, maps, p);
     return check_launch("k_critic_bwd");
 }
 

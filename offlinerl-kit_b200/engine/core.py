@@ -251,7 +251,8 @@ class Runtime:
         return lambda: L.call("orlk_critic_fwd_fused", arr, n, self.cur)
 
     def critic_bwd_fused(self, *, dq: int, dq_gs: int, head_w: int, relu_bits: int, WT: Sequence[int], WTlo: Sequence[int],
-                         dZ: Sequence[int], gs: int, dz_gs: int, M: int, N: int, G: int) -> Callable[[], None]:
+                         dZ: Sequence[int], gs: int, dz_gs: int, M: int, N: int, G: int,
+                         pairs: Optional[bool] = None) -> Callable[[], None]:
         """Input-gradient chain of a fused critic pass behind its scalar head, one tcgen05 launch (csrc/orlk_fused.cu).
         WT / WTlo per hidden layer ([0] unused), dZ[l] for l = 0 .. n_hidden-2."""
         q = L.FusedBwd()
@@ -261,6 +262,10 @@ class Runtime:
         for l in range(len(dZ)):
             q.dZ[l] = dZ[l]
         q.gs, q.dz_gs, q.M, q.N, q.G, q.n_hidden = gs, dz_gs, M, N, G, len(WT)
+        if pairs is None:       # CTA pairs (cta_group::2) from 32 strips on, as for the forward pass
+            env = os.environ.get("ORLK_FUSED_2CTA", "auto")
+            pairs = env == "1" or (env not in ("0", "1") and G * (-(-M // 128)) >= 32)
+        q.flags = L.FUSED_PAIRS if pairs else 0
         qp = _ctypes_pointer(q)
         return lambda: L.call("orlk_critic_bwd_fused", qp, self.cur)
 

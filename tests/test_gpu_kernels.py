@@ -887,8 +887,9 @@ def test_critic_forward_fused_two_jobs(rt):
         _check_fused(b)
 
 
+@pytest.mark.parametrize("pairs", [False, True])
 @pytest.mark.parametrize("M,N,K0,nh,G", [(7936, 256, 23, 3, 2), (300, 128, 32, 4, 1), (2048 + 77, 64, 5, 2, 3)])
-def test_critic_backward_fused_matches_fp64(rt, M, N, K0, nh, G):
+def test_critic_backward_fused_matches_fp64(rt, M, N, K0, nh, G, pairs):
     """orlk_critic_bwd_fused behind orlk_critic_fwd_fused: dZ_l of every hidden layer but the last against fp64 autograd
     algebra on the activations the forward kernel stored (so that both sides take the same ReLU decisions)."""
     case = _fused_case(rt, M, N, K0, nh, G, seed=7 * M + nh)
@@ -919,7 +920,7 @@ def test_critic_backward_fused_matches_fp64(rt, M, N, K0, nh, G):
     op = rt.critic_bwd_fused(dq=dqd.data_ptr(), dq_gs=M, head_w=Pd.data_ptr() + 4 * offs[nh][0], relu_bits=bits.data_ptr(),
                              WT=[0] + [WTd.data_ptr() + 4 * offs[l][0] for l in range(1, nh)],
                              WTlo=[0] + [WTlo.data_ptr() + 4 * offs[l][0] for l in range(1, nh)],
-                             dZ=[t.data_ptr() for t in dZ], gs=block, dz_gs=M * N, M=M, N=N, G=G)
+                             dZ=[t.data_ptr() for t in dZ], gs=block, dz_gs=M * N, M=M, N=N, G=G, pairs=pairs)
     for _ in range(2):
         op()
     torch.cuda.synchronize()
