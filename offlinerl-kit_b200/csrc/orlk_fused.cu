@@ -495,7 +495,10 @@ k_critic_bwd_t(const __grid_constant__ BwdMaps maps, const __grid_constant__ Bwd
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
-    orlk::pdl_wait();
+    // Only dq (the loss launch right in front) and the decision bits depend on earlier launches of the step; the weight
+    // slabs and the head weights were final long before (last step's Adam, this step's fused_prep): the producer starts
+    // its TMA loads and the epilogue warps stage the head weights while the predecessor is still finishing, and only the
+    // warps that read dq / bits wait for it.
     if (threadIdx.x == 0) { FZ_STAMP(1); FZ_GSTAMP(5); }
     tc_fence_before();
     __syncthreads();
@@ -582,12 +585,15 @@ k_critic_bwd_t(const __grid_constant__ BwdMaps maps, const __grid_constant__ Bwd
         const int m = tile_m * BM + row;
         const bool row_ok = m < p.M;
         headw_s[t256] = t256 < N ? __ldg(p.head_w + (int64_t)g * p.gs + t256) : 0.f;
-        const float dq_m = row_ok ? __ldg(p.dq + (int64_t)g * p.dq_gs + m) : 0.f;
+        orlk::pdl_wait();
+        // (dq and the decision bits are written by earlier launches of the step: ordinary loads, NOT __ldg - a read-only
+        // load may be hoisted above the wait, and then reads what the loss launch has not written yet)
+        const float dq_m = row_ok ? __ldcg(p.dq + (int64_t)g * p.dq_gs + m) : 0.f;
         // ReLU-decision words of this row's chunks (c = grp, grp + 2, ...; at most four) of layer l
         auto load_bits = [&](int l, uint32_t (&mb)[4]) {
             const uint32_t* bp = p.bits + ((int64_t)l * p.G + g) * 8 * p.M + (row_ok ? m : 0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) mb[i] = (row_ok && grp + 2 * i < KS) ? __ldg(bp + (int64_t)(grp + 2 * i) * p.M) : 0u;
+            for (int i = 0; i < 4; ++i) mb[i] = (row_ok && grp + 2 * i < KS) ? __ldcg(bp + (int64_t)(grp + 2 * i) * p.M) : 0u;
         };
         uint32_t mb[4];
         load_bits(L - 1, mb);
