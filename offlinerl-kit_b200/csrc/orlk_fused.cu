@@ -842,7 +842,7 @@ extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
     ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
     ORLK_REQUIRE(q->gs % 4 == 0 && q->dz_gs % 4 == 0, "member strides must be multiples of 4 floats");
     ORLK_REQUIRE(q->dq != nullptr && q->head_w != nullptr && q->relu_bits != nullptr, "dq, head weights, ReLU bits");
-    static BwdMaps maps;
+    BwdMaps maps;
     BwdParams p;
     const bool pair = (q->flags & ORLK_FUSED_PAIRS) != 0 && q->N % 64 == 0;
     const int wbox = pair ? q->N / 2 : q->N;
@@ -923,7 +923,7 @@ extern "C" int orlk_fused_prep_multi(const OrlkFusedPrep* jobs, int n_jobs, void
 
 extern "C" int orlk_critic_fwd_fused(const OrlkFusedFwd* jobs, int n_jobs, void* stream) {
     ORLK_REQUIRE(jobs != nullptr && (n_jobs == 1 || n_jobs == 2), "one or two jobs");
-    static FwdMaps maps[2];         // (host scratch; launches are issued from one thread per process)
+    FwdMaps maps[2];
     FwdParams p[2];
     bool pair = (jobs[0].flags & ORLK_FUSED_PAIRS) != 0;
     for (int j = 0; j < n_jobs; ++j) pair = pair && jobs[j].N % 64 == 0;

@@ -114,3 +114,21 @@ def test_facade_state_dict_layout():
             assert len(sd) == 42
         for k, v in ref.items():
             assert tuple(sd[k].shape) == tuple(v.shape), k
+
+
+def test_adam_group_bias_corrections_follow_torch():
+    """The group table carries the bias corrections of the NEXT step (the kernels no longer evaluate pow() themselves):
+    AdamGroup.refresh() must give what torch.optim.Adam computes for step t = step + 1 (torch/optim/adam.py, single-tensor
+    path: bias_correction1 = 1 - beta1 ** step, bias_correction2_sqrt = sqrt(1 - beta2 ** step))."""
+    import math
+    from offlinerlkit_b200 import _lib as L
+    g = L.AdamGroup()
+    g.lr, g.beta1, g.beta2, g.eps = 3e-4, 0.9, 0.999, 1e-8
+    for step in (0, 1, 7, 1000, 123456):
+        g.step = step
+        g.refresh()
+        t = step + 1
+        b1, b2 = float(g.beta1), float(g.beta2)          # the float32 values the kernels see
+        assert g.bc1 == 1.0 - b1 ** t
+        assert abs(g.bc2_sqrt - math.sqrt(1.0 - b2 ** t)) <= 1e-7
+        assert ctypes.sizeof(L.AdamGroup) == 40
