@@ -936,3 +936,23 @@ def test_critic_backward_fused_matches_fp64(rt, M, N, K0, nh, G, pairs):
             assert not torch.isnan(got).any(), f"dZ[{l - 1}] member {g}: unwritten output"
             err = (got.double().cpu() - d).abs().max().item()
             assert err <= tol, f"dZ[{l - 1}] member {g}: max err {err:.3e} vs {tol:.3e}"
+
+
+def test_fused_prep_multi_equals_single(rt):
+    """orlk_fused_prep_multi (one launch for several arenas) writes exactly what orlk_fused_prep writes per arena."""
+    gen = torch.Generator().manual_seed(11)
+    G, N, K0 = 2, 256, 23
+    arenas = [torch.randn(n, generator=gen).to(DEV) for n in (G * (N * K0 + 1000), 70_001 * 4, 4096)]
+    lo_a = [torch.full_like(a, float("nan")) for a in arenas]
+    lo_b = [torch.full_like(a, float("nan")) for a in arenas]
+    pad_a = torch.full((2, G, N, 32), float("nan"), device=DEV)
+    pad_b = torch.full((2, G, N, 32), float("nan"), device=DEV)
+    gs = N * K0 + 1000
+    rt.fused_prep(arenas[0], lo_a[0], W0=arenas[0].data_ptr(), gs=gs, N=N, K0=K0, G=G, w0pad=pad_a)()
+    rt.fused_prep(arenas[1], lo_a[1])()
+    rt.fused_prep(arenas[2], lo_a[2])()
+    rt.fused_prep_multi([dict(src=arenas[0], dst_lo=lo_b[0], W0=arenas[0].data_ptr(), gs=gs, N=N, K0=K0, G=G, w0pad=pad_b),
+                         dict(src=arenas[1], dst_lo=lo_b[1]), dict(src=arenas[2], dst_lo=lo_b[2])])()
+    torch.cuda.synchronize()
+    for a, b in zip(lo_a + [pad_a], lo_b + [pad_b]):
+        assert not torch.isnan(b).any() and torch.equal(a, b)
