@@ -735,7 +735,12 @@ extern "C" int orlk_tc_gemm(const OrlkTcGemm* q, void* stream) {
     const size_t smem = 1024 + FIXED_SMEM + ring_bytes;
     const int grid = q->G * p.tiles_m * p.tiles_n * splits;
     cudaStream_t s = (cudaStream_t)stream;
-    if (q->passes == 3) orlk::launch(k_tc_gemm<3>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
+    static int hp = -1;     // experiment (ORLK_TC_PRIORITY=1): the GEMMs' CTAs are dispatched before optimiser / SIMT blocks
+    if (hp < 0) { const char* e = getenv("ORLK_TC_PRIORITY"); hp = e ? atoi(e) : 0; }
+    if (hp) {
+        if (q->passes == 3) orlk::launch_high_priority(k_tc_gemm<3>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
+        else orlk::launch_high_priority(k_tc_gemm<1>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
+    } else if (q->passes == 3) orlk::launch(k_tc_gemm<3>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
     else orlk::launch(k_tc_gemm<1>, grid, NUM_THREADS, smem, s, tmA, tmB, tmC, p);
     return check_launch("k_tc_gemm");
 }
