@@ -123,6 +123,39 @@ class EnsembleDynamics(BaseDynamics):
             info["penalty"] = pen.cpu().numpy()
         return next_obs, reward, terminal, info
 
+    @torch.no_grad()
+    def sample_next_obss(self, obs: torch.Tensor, action: torch.Tensor, num_samples: int, noise: Optional[torch.Tensor] = None
+                         ) -> torch.Tensor:
+        """ensemble_dynamics.py:81-99 (the uncertainty samples of MOBILE's penalty): ``num_samples`` draws of every ELITE
+        member's Gaussian next-observation prediction, [num_samples, n_elites, B, obs_dim] on the device.  The ensemble
+        forward pass runs on the engine (tensor cores from 2048 rows up); the elementwise tail follows the reference line
+        by line.  ``noise`` [num_samples, n_elites, B, obs_dim + 1]: parity hook - the reference draws
+        ``torch.randn_like(std)`` once per sample."""
+        eng = self.engine
+        obs_d = torch.as_tensor(obs, dtype=torch.float32, device=eng.dev).contiguous()
+        act_d = torch.as_tensor(action, dtype=torch.float32, device=eng.dev).contiguous()
+        S, O, A = obs_d.shape[0], obs_d.shape[1], act_d.shape[1]
+        mu, sd = self._scaler_tensors()
+        xbuf = eng.input_buffer(S)
+        L.call("orlk_dyn_input", obs_d.data_ptr(), obs_d.stride(0), act_d.data_ptr(), act_d.stride(0), mu.data_ptr(), sd.data_ptr(),
+               S, O, A, xbuf.data_ptr(), xbuf.stride(0), eng.rt.cur)
+        out = eng._forward(xbuf).OUT                                    # [E, S, 2 D]: mean | raw log-variance
+        D = out.shape[-1] // 2
+        mean, logvar = out[..., :D].clone(), out[..., D:]
+        max_lv, min_lv = self.model.max_logvar, self.model.min_logvar   # soft_clamp, dynamics_module.py:8-16
+        logvar = max_lv - torch.nn.functional.softplus(max_lv - logvar)
+        logvar = min_lv + torch.nn.functional.softplus(logvar - min_lv)
+        mean[..., :-1] += obs_d
+        std = torch.sqrt(torch.exp(logvar))
+        el = self._elites_dev().long()
+        mean, std = mean[el], std[el]
+        if noise is None:
+            noise = torch.randn((num_samples,) + tuple(std.shape), dtype=torch.float32, device=eng.dev)
+        else:
+            noise = torch.as_tensor(noise, dtype=torch.float32, device=eng.dev)
+        samples = mean[None] + noise * std[None]
+        return samples[..., :-1]
+
     # ------------------------------------------------------------------ training
     def format_samples_for_training(self, data: Dict) -> Tuple[np.ndarray, np.ndarray]:
         inputs = np.concatenate((data["observations"], data["actions"]), axis=-1)

@@ -108,6 +108,23 @@ class DynamicsOracle:
         return next_obs, reward, terminal, info
 
 
+@torch.no_grad()
+def sample_next_obss(ora: "DynamicsOracle", obs: np.ndarray, action: np.ndarray, mu: np.ndarray, std: np.ndarray,
+                     elites: np.ndarray, noise: np.ndarray) -> np.ndarray:
+    """dynamics/ensemble_dynamics.py:81-99 (MOBILE's uncertainty samples): every elite member's Gaussian prediction of the
+    next observation, ``num_samples`` draws each.  ``noise`` [num_samples, n_elites, B, D] = the reference's
+    ``torch.randn_like(std)`` draws in order (one per sample).  Returns [num_samples, n_elites, B, obs_dim]."""
+    obs_act = np.concatenate([obs, action], axis=-1)
+    obs_act = (obs_act - mu) / std                                       # scaler.transform_tensor (scaler.py:34-38)
+    mean, logvar = nets.dynamics_forward(ora.p, torch.as_tensor(obs_act, dtype=torch.float32))
+    mean = mean.clone()
+    mean[..., :-1] += torch.as_tensor(obs, dtype=torch.float32)          # :90
+    sd = torch.sqrt(torch.exp(logvar))                                   # :91
+    mean, sd = mean[elites], sd[elites]                                  # :93-94
+    samples = mean[None] + torch.as_tensor(noise, dtype=torch.float32) * sd[None]        # :96
+    return samples[..., :-1].numpy()                                     # :97
+
+
 def train(ora: "DynamicsOracle", inputs: np.ndarray, targets: np.ndarray, num_elites: int, max_epochs: Optional[int] = None,
           max_epochs_since_update: int = 5, batch_size: int = 256, holdout_ratio: float = 0.2,
           logvar_loss_coef: float = 0.01) -> Dict:

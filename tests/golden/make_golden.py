@@ -536,6 +536,38 @@ def gen_dynamics(name, O, A, hidden, E, n_elites, B, n_batches, S, full_state, t
     save(name, store, meta, full_state)
 
 
+def gen_sample_next(name, O, A, hidden, E, n_elites, S, num_samples, elites):
+    """EnsembleDynamics.sample_next_obss (ensemble_dynamics.py:81-99), the first half of MOBILE's penalty: the torch CPU
+    generator is seeded, so the reference's ``torch.randn_like(std)`` draws can be replayed as explicit noise."""
+    wds = [2.5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4][:len(hidden)] + [1e-4]
+    model = EnsembleDynamicsModel(O, A, hidden, num_ensemble=E, num_elites=n_elites, weight_decays=wds, device="cpu")
+    overwrite_params(model, 170)
+    with torch.no_grad():
+        model.max_logvar.fill_(0.5)
+        model.min_logvar.fill_(-10.0)
+    model.set_elites(list(elites))
+    data = make_dataset(2048, O, A, seed=0)
+    data["rewards"] = data["rewards"].reshape(-1, 1)
+    dyn = EnsembleDynamics(model, torch.optim.Adam(model.parameters(), lr=1e-3), StandardScaler(), termination_fn_halfcheetah)
+    inputs, _ = dyn.format_samples_for_training(data)
+    dyn.scaler.fit(inputs)
+    mu, std = odyn.scaler_fit(inputs)
+    obs, act = data["observations"][:S].copy(), data["actions"][:S].copy()
+    torch.manual_seed(21)
+    ref = dyn.sample_next_obss(torch.as_tensor(obs), torch.as_tensor(act), num_samples).numpy()
+    torch.manual_seed(21)
+    noise = torch.stack([torch.randn(len(elites), S, O + 1) for _ in range(num_samples)], 0).numpy()
+    pre = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ora = odyn.DynamicsOracle(pre, wds, lr=1e-3)
+    got = odyn.sample_next_obss(ora, obs, act, mu, std, np.asarray(elites), noise)
+    assert ref.shape == (num_samples, len(elites), S, O) and rel(got, ref) < 1e-5, (ref.shape, rel(got, ref))
+    store = {"obs": obs, "act": act, "noise": noise, "next_obss": ref, "scaler_mu": mu, "scaler_std": std,
+             "elites": np.asarray(elites, np.int64)}
+    meta = dict(algo="dynamics_sample_next", O=O, A=A, hidden=hidden, E=E, n_elites=n_elites, S=S, num_samples=num_samples,
+                weight_decays=wds, param_seed=170, data_seed=0, n_data=2048, torch_seed=21)
+    save(name, store, meta, True)
+
+
 def gen_rollout(name, O, A, hidden, dyn_hidden, E, n_elites, S, horizon, term="hopper", uniform=False):
     """MOPOPolicy.rollout (mopo.py:45-79): compaction order and per-step RNG consumption.
     uniform: COMBOPolicy.rollout with uniform_rollout=True (combo.py:67-107) -- NumPy uniform actions, no actor."""
@@ -838,6 +870,10 @@ if __name__ == "__main__":
                 horizon=4, term="hopper", uniform=True)
     run(gen_dynamics_train, "dynamics_train_small", O=5, A=3, hidden=[24, 24, 24, 24], E=3, n_elites=2, n_data=640, B=32,
         max_epochs=6)
+    run(gen_sample_next, "dynamics_sample_next_small", O=5, A=3, hidden=[24, 24, 24, 24], E=3, n_elites=2, S=32, num_samples=4,
+        elites=[2, 0])
+    run(gen_sample_next, "dynamics_sample_next_hc", O=17, A=6, hidden=[200, 200, 200, 200], E=7, n_elites=5, S=96,
+        num_samples=10, elites=[6, 1, 3, 0, 4])
     run(gen_rollout_cfg5, "rollout_cfg5_hc", term="halfcheetah")
     run(gen_rollout_cfg5, "rollout_cfg5_walker", term="walker2d")
     run(gen_cql_curve, "cql_curve_small")

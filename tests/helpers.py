@@ -144,7 +144,7 @@ def initial_state(meta) -> Dict[str, torch.Tensor]:
             cs = recipe_state(shp, ps[c], c)
             st.update(cs)
             st.update({k.replace(c + ".", c + "_old.", 1): v.clone() for k, v in cs.items()})
-    elif algo == "dynamics":
+    elif algo in ("dynamics", "dynamics_sample_next"):
         raw = param_recipe(dynamics_shapes(O, A, hid, meta["E"]), meta["param_seed"])
         st = {k: torch.from_numpy(v) for k, v in raw.items()}
         st["max_logvar"] = torch.full((O + 1,), 0.5)

@@ -55,8 +55,8 @@ CLASSES = [
     ("modules", "DiagGaussian", ["__init__", "forward"]),
     ("modules", "EnsembleDynamicsModel", ["__init__", "forward", "load_save", "update_save", "get_decay_loss", "set_elites",
                                           "random_elite_idxs"]),
-    ("dynamics", "EnsembleDynamics", ["__init__", "step", "format_samples_for_training", "train", "learn", "validate",
-                                      "select_elites", "save", "load"]),
+    ("dynamics", "EnsembleDynamics", ["__init__", "step", "sample_next_obss", "format_samples_for_training", "train", "learn",
+                                      "validate", "select_elites", "save", "load"]),
     ("policy", "SACPolicy", ["__init__", "train", "eval", "actforward", "select_action", "learn"]),
     ("policy", "CQLPolicy", ["__init__", "learn", "select_action"]),
     ("policy", "EDACPolicy", ["__init__", "train", "eval", "actforward", "select_action", "learn"]),

@@ -191,6 +191,21 @@ def test_dynamics_train_shuffle_overlap_is_invisible(tmp_path, monkeypatch):
         assert torch.equal(sd1[k], sd0[k]), k
 
 
+@pytest.mark.parametrize("name", ["dynamics_sample_next_small", "dynamics_sample_next_hc"])
+def test_sample_next_obss_matches_reference(name):
+    """EnsembleDynamics.sample_next_obss (ensemble_dynamics.py:81-99) with the reference's draws injected; elites as set by
+    ``set_elites`` (not the first n members)."""
+    g = Golden(name)
+    m = dict(g.meta, algo="dynamics", term="halfcheetah")
+    dyn = _build_dynamics(m, initial_state(g.meta), g["scaler_mu"], g["scaler_std"], "halfcheetah")
+    dyn.model.set_elites([int(e) for e in g["elites"]])
+    got = dyn.sample_next_obss(torch.as_tensor(g["obs"]), torch.as_tensor(g["act"]), m["num_samples"], noise=g["noise"])
+    assert tuple(got.shape) == (m["num_samples"], m["n_elites"], m["S"], m["O"]) and got.is_cuda
+    assert rel_err(got.cpu().numpy(), g["next_obss"]) < 2e-4
+    free = dyn.sample_next_obss(torch.as_tensor(g["obs"]), torch.as_tensor(g["act"]), 3)        # own draws: shape and sanity
+    assert tuple(free.shape) == (3, m["n_elites"], m["S"], m["O"]) and bool(torch.isfinite(free).all())
+
+
 def test_dynamics_learn_eager_equals_graph():
     """The branched training step (decay sums beside the forward pass, weight gradients beside the input gradients)
     gives bit-identical parameters whether it is replayed as a CUDA graph or launched eagerly on side streams."""

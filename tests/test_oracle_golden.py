@@ -123,6 +123,18 @@ def test_dynamics(name):
         assert rel_err(rew_m, g["step_reward_" + mode]) < TOL, mode
 
 
+@pytest.mark.parametrize("name", ["dynamics_sample_next_small", "dynamics_sample_next_hc"])
+def test_dynamics_sample_next_obss(name):
+    """ensemble_dynamics.py:81-99 (MOBILE's uncertainty samples) against the reference's output under a seeded torch
+    generator, replayed from the stored draws."""
+    g = Golden(name)
+    m = g.meta
+    ora = odyn.DynamicsOracle(initial_state(m), m["weight_decays"], lr=1e-3)
+    got = odyn.sample_next_obss(ora, g["obs"], g["act"], g["scaler_mu"], g["scaler_std"], g["elites"], g["noise"])
+    assert got.shape == (m["num_samples"], m["n_elites"], m["S"], m["O"])
+    assert rel_err(got, g["next_obss"]) < TOL
+
+
 @pytest.mark.parametrize("name", ["rollout_small", "combo_rollout_uniform"])
 def test_rollout_compaction(name):
     """mopo.py:45-79 / combo.py:67-107: stable survivor compaction and per-step draw order, replayed with stored noise."""
