@@ -75,7 +75,7 @@ __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__f
 //
 // PAIR = true: CTA pairs (thread-block clusters of two, tcgen05.mma.cta_group::2, M = 256 over two strips).  Each CTA keeps
 // its own 128 rows of A and its own accumulators, but only HALF of every weight slab (N/2 rows: 32 KB instead of 64 KB
-// per slab and SM, a four-stage ring in the same shared memory); the leader CTA issues the MMAs for both, its barriers
+// per slab and SM; three A and three weight stages in the same shared memory); the leader CTA issues the MMAs for both, its barriers
 // collect the A tiles of both CTAs (remote arrivals) and the bytes of both CTAs' TMA loads, and its commits are
 // multicast to the stage / accumulator barriers of both.  What it buys: the L2 -> SM path of a TPC, which bounds the
 // second SM of a pair in the single-CTA kernel, carries half the bytes.
