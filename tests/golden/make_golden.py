@@ -870,10 +870,10 @@ if __name__ == "__main__":
                 horizon=4, term="hopper", uniform=True)
     run(gen_dynamics_train, "dynamics_train_small", O=5, A=3, hidden=[24, 24, 24, 24], E=3, n_elites=2, n_data=640, B=32,
         max_epochs=6)
+    run(gen_rollout_cfg5, "rollout_cfg5_hc", term="halfcheetah")
+    run(gen_rollout_cfg5, "rollout_cfg5_walker", term="walker2d")
+    run(gen_cql_curve, "cql_curve_small")
     run(gen_sample_next, "dynamics_sample_next_small", O=5, A=3, hidden=[24, 24, 24, 24], E=3, n_elites=2, S=32, num_samples=4,
         elites=[2, 0])
     run(gen_sample_next, "dynamics_sample_next_hc", O=17, A=6, hidden=[200, 200, 200, 200], E=7, n_elites=5, S=96,
         num_samples=10, elites=[6, 1, 3, 0, 4])
-    run(gen_rollout_cfg5, "rollout_cfg5_hc", term="halfcheetah")
-    run(gen_rollout_cfg5, "rollout_cfg5_walker", term="walker2d")
-    run(gen_cql_curve, "cql_curve_small")
