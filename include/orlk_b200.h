@@ -213,7 +213,7 @@ int orlk_sizeof_tc_gemm(void);
  * stores H_l (needed by the backward pass; H[] all NULL = not stored) with TMA from the same tiles; the head is a dot
  * product in the last epilogue.  Up to two such passes ("jobs": the online critics on the 7936-row batch and the target
  * critics on the next-state rows) share one launch, each with its own rows, weights and outputs.
- * Shapes: hidden widths all N (multiple of 32, <= 256), K0 <= 32 input columns, X [M][ldx] shared by all members
+ * Shapes: hidden widths all N (32 or a multiple of 64, <= 256), K0 <= 32 input columns, X [M][ldx] shared by all members
  * (16-byte aligned rows), 'oi' weights W_l [N][N] (l >= 1) with one member stride `gs` for every parameter tensor, Wlo[l] =
  * W[l] - trunc_tf32(W[l]); W0pad / W0pad_lo = the first layer's [N][K0] weights zero-padded to [G][N][32] and their lo
  * words (all three kept by orlk_fused_prep).  Replaces the per-layer launches + head of

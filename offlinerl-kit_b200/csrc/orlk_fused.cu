@@ -773,7 +773,9 @@ constexpr size_t FWD_SMEM = 1024 + RING + FIXED;
 int fill_fwd_job(const OrlkFusedFwd* q, FwdMaps* maps, FwdParams* p, bool pair) {
     ORLK_REQUIRE(q->M > 0 && q->G > 0, "sizes");
     ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
-    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
+    // (an even number of 32-column chunks: the two epilogue groups then alternate on every layer, which the stage-free
+    // protocol - a writer confirms its stores when it reaches its next chunk - relies on)
+    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && (q->N == 32 || q->N % 64 == 0), "hidden width must be 32 or a multiple of 64 up to 256");
     ORLK_REQUIRE(q->K0 >= 1 && q->K0 <= BK, "first-layer fan-in must be <= 32");
     ORLK_REQUIRE(q->ldx % 4 == 0 && aligned16(q->X), "X rows must be 16-byte aligned");
     ORLK_REQUIRE(q->gs % 4 == 0 && q->h_gs % 4 == 0, "member strides must be multiples of 4 floats");
@@ -839,7 +841,7 @@ extern "C" int orlk_fused_init(void) {
 extern "C" int orlk_critic_bwd_fused(const OrlkFusedBwd* q, void* stream) {
     ORLK_REQUIRE(q != nullptr && q->M > 0 && q->G > 0, "sizes");
     ORLK_REQUIRE(q->n_hidden >= 2 && q->n_hidden <= MAXL, "2..4 hidden layers");
-    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && q->N % 32 == 0, "hidden width must be a multiple of 32 in [32,256]");
+    ORLK_REQUIRE(q->N >= 32 && q->N <= NMAX && (q->N == 32 || q->N % 64 == 0), "hidden width must be 32 or a multiple of 64 up to 256");
     ORLK_REQUIRE(q->gs % 4 == 0 && q->dz_gs % 4 == 0, "member strides must be multiples of 4 floats");
     ORLK_REQUIRE(q->dq != nullptr && q->head_w != nullptr && q->relu_bits != nullptr, "dq, head weights, ReLU bits");
     BwdMaps maps;

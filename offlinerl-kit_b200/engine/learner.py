@@ -408,7 +408,7 @@ class MlpRun:
         self.fused_fwd = (FUSED_FWD and tc_passes == 3 and M >= fused_min_rows and not self.ens_tc and share_forward is None
                           and 2 <= n_hidden <= L.FUSED_MAX_LAYERS and self.has_head and self.NS == 1
                           and all(lay.layout == "oi" for lay in lays[:n_hidden + 1])
-                          and len(widths) == 1 and lays[0].out_dim % 32 == 0 and 32 <= lays[0].out_dim <= 256
+                          and len(widths) == 1 and (lays[0].out_dim == 32 or lays[0].out_dim % 64 == 0) and 32 <= lays[0].out_dim <= 256
                           and lays[0].in_dim <= 32 and all(lays[l].in_dim == lays[0].out_dim for l in range(1, n_hidden + 1))
                           and all(h is None for h in self.HT) and ps.block % 4 == 0
                           and all(lays[l].w_off % 4 == 0 and lays[l].w_gs == ps.block and lays[l].b_gs == ps.block
